@@ -1,0 +1,206 @@
+/*
+ * rnabloom_gpu.h -- C-ABI of librnabloom_gpu.so: RNA-Bloom's k-mer / Bloom-filter hot path on B200 (sm_100a).
+ *
+ * This is the drop-in boundary.  The reference (bcgsc/RNA-Bloom, 100 % Java) has no FFI seam, so each entry
+ * point below names the Java method(s) it replaces; a thin JNI shim (jni/rnabloom_jni.c) binds
+ * them to rnabloom.gpu.* classes that subclass the reference's BloomFilter / CountingBloomFilter /
+ * BloomFilterDeBruijnGraph.  Citations are relative to /root/reference/src/rnabloom/.
+ *
+ * Conventions
+ *   - every call returns int32: RB_OK or a negative RB_E* code; rb_last_error() gives the text.
+ *   - all pointers are HOST pointers unless the function name ends in _dev (then: device pointers on the
+ *     context's GPU).  Host buffers are caller-owned and may be reused as soon as the call returns.
+ *   - calls on one graph/filter from several host threads are serialised internally (the reference shares one
+ *     graph between N unsynchronised workers, RNABloom.java:1189-1205); different contexts are independent.
+ *   - results are complete (device-synchronised) when a host-pointer call returns; _dev calls are
+ *     stream-ordered on the context's stream and need rb_ctx_sync() before the host looks at device memory.
+ *
+ * Read ingest layout (ours; not the reference's .2bit record format, see DESIGN.md "Ingest"):
+ *   packed : 2-bit codes A0 C1 G2 T/U3, base b at bits 2*(b&31).. of little-endian 64-bit word b>>5
+ *   mask   : optional 1 bit per base, bit (b&31) of 32-bit word b>>5, set = base unusable (non-ACGTU, or
+ *            below the PHRED33 quality floor).  NULL = every base usable.
+ *   read i covers bases [read_off[i], read_off[i]+read_len[i]) of those two streams (absolute base indices;
+ *   any alignment).  read_off == NULL selects the uniform layout: read i starts at i*uniform_stride and has
+ *   uniform_len bases.
+ *   A k-mer is inserted iff none of its k bases is masked -- identical to the reference's "maximal runs of
+ *   good-quality ACGTU of length >= k" segmentation (RNABloom.java:567-595, util/SeqUtils.java:1430-1438).
+ */
+#ifndef RNABLOOM_GPU_H
+#define RNABLOOM_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB_API __attribute__((visibility("default")))
+
+typedef struct rb_ctx rb_ctx;
+typedef struct rb_filter rb_filter;
+typedef struct rb_graph rb_graph;
+
+enum {
+    RB_OK = 0,
+    RB_EINVAL = -1,  /* bad argument */
+    RB_ENOMEM = -2,  /* host or device allocation failed */
+    RB_ECUDA = -3,   /* CUDA runtime error (text in rb_last_error) */
+    RB_ENCCL = -4,   /* reserved for the multi-GPU exchange */
+    RB_EIO = -5,     /* file I/O */
+    RB_ESTATE = -6   /* object not in a state that allows the call (e.g. no rpkbf) */
+};
+
+enum { RB_BLOOM = 0, RB_COUNTING = 1 };                      /* rb_filter kinds */
+enum { RB_DBGBF = 0, RB_CBF = 1, RB_RPKBF = 2, RB_FPKBF = 3 }; /* filters of a graph */
+enum { RB_MODE_FWD = 0, RB_MODE_RC = 1, RB_MODE_CANON = 2 }; /* k-merizer strand mode */
+
+/* flags of rb_graph_add_reads* -- which insert worker body is reproduced */
+#define RB_REVCOMP 1u               /* ReverseComplement iterators (stranded graphs only; CanonicalHashFunction.java:188-206 ignores it) */
+#define RB_ADD_COUNT_IF_PRESENT 2u  /* graph.addCountIfPresent instead of graph.add  (graph/BloomFilterDeBruijnGraph.java:424-428) */
+#define RB_DBG_ONLY 4u              /* graph.addDbgOnly                            (:430-436; FragmentsToGraphWorker RNABloom.java:1489-1516) */
+#define RB_STORE_READ_PAIRS 8u      /* also rpkbf.add(pair hash) at distance d_read (RNABloom.java:587-592) */
+#define RB_STORE_FRAG_PAIRS 16u     /* also fpkbf.add(pair hash) at distance d_frag (RNABloom.java:1503-1512) */
+#define RB_PAIRS_EXISTING_ONLY 32u  /* pair add only if both k-mers are in dbgbf   (RNABloom.java:389-399); implies no k-mer insert */
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+RB_API int32_t rb_version(void);
+RB_API int32_t rb_ctx_create(int32_t device, rb_ctx** out);
+RB_API int32_t rb_ctx_destroy(rb_ctx* ctx);
+RB_API const char* rb_last_error(rb_ctx* ctx);          /* ctx may be NULL: error of the last failed create */
+RB_API int32_t rb_ctx_set_stream(rb_ctx* ctx, void* cuda_stream); /* run on a caller stream (NULL = back to the own stream) */
+RB_API int32_t rb_ctx_sync(rb_ctx* ctx);
+RB_API int32_t rb_ctx_set_rng_seed(rb_ctx* ctx, uint64_t seed);  /* MiniFloat coin flips (util/MiniFloat.java:31-38 uses Math.random) */
+RB_API int32_t rb_ctx_set_subbatch_kmers(rb_ctx* ctx, int64_t kmers); /* tuning: k-mers per kernel launch */
+RB_API int64_t rb_ctx_kernel_launches(rb_ctx* ctx);     /* number of kernels this context has launched so far */
+/* device-side stopwatch on the context's stream (CUDA events): start, then stop returns the elapsed milliseconds */
+RB_API int32_t rb_timer_start(rb_ctx* ctx);
+RB_API int32_t rb_timer_stop(rb_ctx* ctx, float* elapsed_ms);
+RB_API int32_t rb_host_alloc(void** p, int64_t bytes);  /* pinned host memory for fast transfers */
+RB_API int32_t rb_host_free(void* p);
+RB_API int32_t rb_dev_alloc(rb_ctx* ctx, void** p, int64_t bytes);
+RB_API int32_t rb_dev_free(rb_ctx* ctx, void* p);
+RB_API int32_t rb_memcpy_h2d(rb_ctx* ctx, void* dst_dev, const void* src, int64_t bytes);
+RB_API int32_t rb_memcpy_d2h(rb_ctx* ctx, void* dst, const void* src_dev, int64_t bytes);
+
+/* ---- host-side helpers (pure host logic, no device traffic) ------------------------------------------------ */
+/* BloomFilter.getExpectedSize (bloom/BloomFilter.java:196-199; same in CountingBloomFilter.java:265-268) */
+RB_API int64_t rb_expected_size(int64_t n_elements, float fpr, int32_t num_hash);
+/* MiniFloat.toFloat (util/MiniFloat.java:40-45) */
+RB_API float rb_minifloat_to_float(int8_t b);
+/* Pack ASCII reads into the ingest layout on the host.  quals may be NULL (FASTA path).  Read i occupies
+ * ascii[ascii_off[i], ascii_off[i+1]); its bases land at base offset out_read_off[i] (reads are padded to a
+ * multiple of 32 bases so they start on word boundaries).  Returns the number of bases of stream written. */
+RB_API int64_t rb_pack_reads_host(const char* bases, const char* quals, const int64_t* ascii_off, int64_t n_reads,
+                                  int32_t min_qual, uint64_t* packed, uint32_t* mask, int64_t* out_read_off,
+                                  int32_t* out_read_len);
+/* exclusive prefix sum of max(0, len-k+1): where read i's k-mers start in the outputs of rb_graph_count_reads */
+RB_API int64_t rb_kmer_offsets(const int32_t* read_len, int64_t n_reads, int32_t uniform_len, int32_t k, int64_t* off);
+
+/* ---- stand-alone filters -------------------------------------------------------------------------------------
+ * BloomFilter(size bits, numHash, hashFunction)            bloom/BloomFilter.java:47-59
+ * CountingBloomFilter(size bytes, numHash, hashFunction)   bloom/CountingBloomFilter.java:48-61
+ * k is what HashFunction carries: it enters the multi-hash expansion NTM64 (bloom/hash/NTHash.java:518-527). */
+RB_API int32_t rb_filter_create(rb_ctx* ctx, int32_t kind, int64_t size, int32_t num_hash, int32_t k, rb_filter** out);
+RB_API int32_t rb_filter_destroy(rb_filter* f);                       /* destroy()  BloomFilter.java:246-251 */
+RB_API int32_t rb_filter_empty(rb_filter* f);                         /* empty()    BloomFilter.java:240-244 */
+RB_API int64_t rb_filter_size(const rb_filter* f);                    /* bits (Bloom) or bytes (counting) */
+RB_API int64_t rb_filter_num_bytes(const rb_filter* f);               /* bytes of the backing array = file size */
+RB_API int32_t rb_filter_num_hash(const rb_filter* f);                /* getNumHash() */
+RB_API int32_t rb_filter_device_ptr(rb_filter* f, void** p);          /* HBM address of the byte array */
+/* bulk forms of the `long hashVal` overloads: base[i] is hVals[0]; the other numHash-1 values are derived with NTM64
+ *   add(long)            BloomFilter.java:139-141     lookup(long)          :180-182
+ *   lookupThenAdd(long)  BloomFilter.java:143-145     (out[i] = 1 if all bits were already set; duplicates inside one
+ *                                                      call behave as first-then-repeat)
+ *   increment(long)      CountingBloomFilter.java:126-128   getCount(long) :231-233   incrementAndGet :196-222 */
+RB_API int32_t rb_filter_add_hashes(rb_filter* f, const int64_t* base, int64_t n);
+RB_API int32_t rb_filter_lookup_hashes(rb_filter* f, const int64_t* base, int64_t n, uint8_t* out);
+RB_API int32_t rb_filter_lookup_then_add_hashes(rb_filter* f, const int64_t* base, int64_t n, uint8_t* out);
+RB_API int32_t rb_cbf_increment_hashes(rb_filter* f, const int64_t* base, int64_t n);
+RB_API int32_t rb_cbf_increment_and_get_hashes(rb_filter* f, const int64_t* base, int64_t n, float* out);
+RB_API int32_t rb_cbf_count_hashes(rb_filter* f, const int64_t* base, int64_t n, float* out);
+/* getPopCount / getFPR: set bits (Bloom) or non-zero bytes (counting); fpr = (pop/size)^numHash in double, cast to float
+ *   BloomFilter.java:185-194,201-203   CountingBloomFilter.java:254-263   buffer/UnsafeByteBuffer.java:121-150 */
+RB_API int32_t rb_filter_popcount(rb_filter* f, int64_t* out);
+RB_API int32_t rb_filter_fpr(rb_filter* f, float* out);
+/* host mirror: the device array is byte-identical to UnsafeByteBuffer's (bit i = byte i/8, mask 1<<(i%8)) */
+RB_API int32_t rb_filter_download(rb_filter* f, void* dst, int64_t nbytes);
+RB_API int32_t rb_filter_upload(rb_filter* f, const void* src, int64_t nbytes);
+/* save(desc, bits) / file constructors: BloomFilter.java:70-124, CountingBloomFilter.java:66-118 */
+RB_API int32_t rb_filter_save(rb_filter* f, const char* desc_path, const char* bits_path);
+RB_API int32_t rb_filter_load(rb_ctx* ctx, int32_t kind, const char* desc_path, const char* bits_path, int32_t k,
+                              int32_t load_bits, rb_filter** out);
+
+/* getIndex(hashVal, size) = (hashVal >>> 1) % size for an arbitrary positive 63-bit size (bloom/BloomFilter.java:108-111,
+ * CountingBloomFilter.java:101-104): the device index arithmetic exposed for parity checks. */
+RB_API int32_t rb_index_hashes(rb_ctx* ctx, const int64_t* hash, int64_t n, int64_t size, int64_t* index_out);
+
+/* ---- k-merizer alone (hash parity, and the "hash only" operator) --------------------------------------------
+ * NTHashIterator / CanonicalNTHashIterator / ReverseComplementNTHashIterator (bloom/hash/*.java): for every k-mer
+ * position of every read writes fhash, rhash, base (= hVals[0]) at rb_kmer_offsets()[read] + pos.  Outputs may be NULL.
+ * Masked bases hash as seed 0 (like 'N', NTHash.java:135-168). */
+RB_API int32_t rb_kmerize(rb_ctx* ctx, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off,
+                          const int32_t* read_len, int64_t n_reads, int32_t uniform_len, int64_t uniform_stride,
+                          int32_t k, int32_t mode, int64_t* fhash, int64_t* rhash, int64_t* base);
+/* Paired*NTHashIterator (bloom/hash/PairedNTHashIterator.java:55-85 and twins): pair base hash hValsP[0] for positions
+ * pos <= len-k-d; out index = rb_kmer_offsets(k+d)[read] + pos. */
+RB_API int32_t rb_kmerize_pairs(rb_ctx* ctx, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off,
+                                const int32_t* read_len, int64_t n_reads, int32_t uniform_len, int64_t uniform_stride,
+                                int32_t k, int32_t d, int32_t mode, int64_t* pair_base);
+
+/* ---- BloomFilterDeBruijnGraph ---------------------------------------------------------------------------------
+ * ctor  graph/BloomFilterDeBruijnGraph.java:75-104 ; initializePairKmersBloomFilter :352-359 ;
+ * set{Read,Frag}PairedKmerDistance :361-389 ; destroy :211-275 */
+RB_API int32_t rb_graph_create(rb_ctx* ctx, int64_t dbgbf_bits, int64_t cbf_bytes, int64_t pkbf_bits, int32_t dbgbf_num_hash,
+                               int32_t cbf_num_hash, int32_t pkbf_num_hash, int32_t k, int32_t stranded,
+                               int32_t use_read_paired_kmers, rb_graph** out);
+RB_API int32_t rb_graph_destroy(rb_graph* g);
+RB_API int32_t rb_graph_init_fpkbf(rb_graph* g, int64_t pkbf_bits, int32_t pkbf_num_hash);
+RB_API int32_t rb_graph_set_distances(rb_graph* g, int32_t d_read, int32_t d_frag);
+RB_API int32_t rb_graph_filter(rb_graph* g, int32_t which, rb_filter** out); /* borrowed handle; NULL if absent */
+RB_API int32_t rb_graph_clear(rb_graph* g);                                 /* clearDbgbf/Cbf/Rpkbf/Fpkbf :211-245 */
+
+/* Bulk insert = the body of the five live insert workers (RNABloom.java:364-732,1463-1539): for every usable k-mer of
+ * every read, graph.add / addCountIfPresent / addDbgOnly (graph :405-436), plus pair adds when flagged (:455-461).
+ * n_kmers_out (nullable) receives the number of k-mer instances processed. */
+RB_API int32_t rb_graph_add_reads(rb_graph* g, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off,
+                                  const int32_t* read_len, int64_t n_reads, int32_t uniform_len, int64_t uniform_stride,
+                                  uint32_t flags, int64_t* n_kmers_out);
+RB_API int32_t rb_graph_add_reads_dev(rb_graph* g, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off,
+                                      const int32_t* read_len, int64_t n_reads, int32_t uniform_len, int64_t uniform_stride,
+                                      uint32_t flags, int64_t* n_kmers_out);
+/* FASTQ/FASTA convenience: ASCII bases (+ PHRED33 qualities or NULL), read i = [ascii_off[i], ascii_off[i+1]).
+ * Segmentation and 2-bit packing run on the GPU. */
+RB_API int32_t rb_graph_add_reads_ascii(rb_graph* g, const char* bases, const char* quals, const int64_t* ascii_off,
+                                        int64_t n_reads, int32_t min_qual, uint32_t flags, int64_t* n_kmers_out);
+
+/* Bulk lookup = graph.getKmers(seq) (graph :1224-1226 -> HashFunction.java:55-85 / CanonicalHashFunction.java:46-78):
+ * per k-mer position count = dbgbf.lookup ? cbf.getCount + 1 : 0 (graph :562-570), 0 when the k-mer covers a masked base;
+ * fhash/rhash (nullable) are Kmer.fHashVal / CanonicalKmer.rHashVal.  Output index = rb_kmer_offsets(k)[read] + pos. */
+RB_API int32_t rb_graph_count_reads(rb_graph* g, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off,
+                                    const int32_t* read_len, int64_t n_reads, int32_t uniform_len, int64_t uniform_stride,
+                                    float* counts, int64_t* fhash, int64_t* rhash, int64_t* n_kmers_out);
+RB_API int32_t rb_graph_count_reads_dev(rb_graph* g, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off,
+                                        const int32_t* read_len, int64_t n_reads, int32_t uniform_len, int64_t uniform_stride,
+                                        float* counts, int64_t* fhash, int64_t* rhash, int64_t* n_kmers_out);
+/* per-hash forms: graph.add(long[]) :405, contains :538, getCount(long) :552 */
+RB_API int32_t rb_graph_add_hashes(rb_graph* g, const int64_t* base, int64_t n, uint32_t flags);
+RB_API int32_t rb_graph_count_hashes(rb_graph* g, const int64_t* base, int64_t n, float* counts);
+/* pair ops: addReadSingleKmerPair / addFragmentSingleKmerPair :455-461, lookup{Read,Fragment}KmerPair :526-532;
+ * pair_hash[i] is Kmer.getKmerPairHashValue (graph/Kmer.java:65-67, CanonicalKmer.java:69-72) */
+RB_API int32_t rb_graph_add_pair_hashes(rb_graph* g, int32_t which, const int64_t* pair_hash, int64_t n);
+RB_API int32_t rb_graph_lookup_pair_hashes(rb_graph* g, int32_t which, const int64_t* pair_hash, int64_t n, uint8_t* out);
+/* save / file constructor: graph :297-339,121-189.  Writes <path>, <path>.dbgbf[.desc], <path>.cbf[.desc], <path>.rpkbf[.desc]
+ * (if present) and <path>.fpkbf[.desc] (if present) in the reference's format, so the unmodified JAR can restoreGraph() them. */
+RB_API int32_t rb_graph_save(rb_graph* g, const char* path);
+RB_API int32_t rb_graph_load(rb_ctx* ctx, const char* path, int32_t load_dbgbf, int32_t load_fpkbf, rb_graph** out);
+
+/* ---- synthetic workload generator (bench + fixtures; not a reference operator) ----------------------------------
+ * Deterministic, counter-based: read r of a virtual genome (seed, genome_len), length L, err_ppm substitutions per
+ * 1e6 bases; written in the uniform ingest layout (stride = stride_bases, multiple of 32) into device memory. */
+RB_API int32_t rb_synth_reads_dev(rb_ctx* ctx, uint64_t seed, uint64_t genome_len, uint64_t first_read, int64_t n_reads,
+                                  int32_t L, uint32_t err_ppm, int64_t stride_bases, uint64_t* packed_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RNABLOOM_GPU_H */

@@ -1,0 +1,397 @@
+// rb_kernels.cuh -- the CUDA kernels of the hot path (sm_100a).  One thread owns kChunk consecutive k-mer positions:
+// it seeds the rolling ntHash once, then per group of kGroup k-mers issues every filter probe before consuming any
+// (memory-level parallelism is what a random-sector workload lives on).  Citations: /root/reference/src/rnabloom/.
+#pragma once
+#include "rb_device.cuh"
+
+namespace rb {
+
+constexpr int kThreads = 256;
+
+struct GraphDev {
+    BitFilter dbg;
+    ByteFilter cbf;
+    HashMults hm;
+    ClaimTable ct;
+    uint64_t rng_seed;
+    int k;
+};
+
+enum { POLICY_ADD = 0, POLICY_COUNT_IF_PRESENT = 1, POLICY_DBG_ONLY = 2 };
+
+// Walks the positions [pos, pos+n) of the launch, crossing read boundaries when needed.
+template <int MODE>
+struct PositionWalker {
+    KmerWalker<MODE> wk;
+    int64_t read;
+    int32_t in_read, npos;
+    bool primed;
+    __device__ __forceinline__ void start(const Ingest& g, int64_t pos, int k, const RollLut& lut) {
+        locate(g, pos, read, in_read);
+        npos = read_npos(g, read);
+        wk.init(g, read_start(g, read) + in_read, k, lut);
+        primed = true;
+    }
+    // moves to the next position (no-op on the very first call)
+    __device__ __forceinline__ void advance(const Ingest& g, int k, const RollLut& lut) {
+        if (primed) { primed = false; return; }
+        if (++in_read < npos) { wk.roll(lut); return; }
+        do { ++read; npos = read_npos(g, read); } while (npos <= 0);
+        in_read = 0;
+        wk.init(g, read_start(g, read), k, lut);
+    }
+};
+
+// ---- graph.add / addCountIfPresent / addDbgOnly over reads (graph/BloomFilterDeBruijnGraph.java:405-436) ----------
+template <int MODE, int MAXH, int POLICY>
+__global__ void __launch_bounds__(kThreads) k_graph_insert(const Ingest g, const GraphDev gd) {
+    __shared__ RollLut lut;
+    build_lut(&lut, gd.k);
+    const int64_t pos = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * kChunk;
+    if (pos >= g.n_pos) return;
+    const int n = (int)min((int64_t)kChunk, g.n_pos - pos);
+    PositionWalker<MODE> pw;
+    pw.start(g, pos, gd.k, lut);
+
+    for (int i0 = 0; i0 < n; i0 += kGroup) {
+        uint64_t base[kGroup];
+        uint32_t wd[kGroup][MAXH];
+        uint32_t ok = 0;
+        // stage 1: hash kGroup k-mers and put every dbgbf probe in flight
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) {
+            if (i0 + j < n) {
+                pw.advance(g, gd.k, lut);
+                base[j] = pw.wk.base();
+                if (pw.wk.bad == 0) {
+                    ok |= 1u << j;
+#pragma unroll
+                    for (int h = 0; h < MAXH; ++h)
+                        if (h < gd.dbg.num_hash) {
+                            const uint64_t idx = fm_index(expand_hash(base[j], h, gd.hm), gd.dbg.fm);
+                            wd[j][h] = ld_cg(&gd.dbg.words[idx >> 5]);
+                        }
+                }
+            }
+        }
+        // stage 2: dbgbf.lookupThenAdd (bloom/BloomFilter.java:147-155)
+        uint32_t found = 0;
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) {
+            if (ok & (1u << j)) {
+                uint32_t clear = 0;
+#pragma unroll
+                for (int h = 0; h < MAXH; ++h)
+                    if (h < gd.dbg.num_hash) {
+                        const uint64_t idx = fm_index(expand_hash(base[j], h, gd.hm), gd.dbg.fm);
+                        if (!((wd[j][h] >> (idx & 31)) & 1u)) clear |= 1u << h;
+                    }
+                if (clear == 0) found |= 1u << j;
+                else if (POLICY == POLICY_COUNT_IF_PRESENT) { /* absent: nothing to do */ }
+                else {
+                    bool first = true;
+                    if (POLICY == POLICY_ADD) first = claim_first(gd.ct, base[j]);
+                    if (!first) found |= 1u << j;  // a concurrent duplicate owns the first sighting
+                    else {
+#pragma unroll
+                        for (int h = 0; h < MAXH; ++h)
+                            if (clear & (1u << h)) {
+                                const uint64_t idx = fm_index(expand_hash(base[j], h, gd.hm), gd.dbg.fm);
+                                atomicOr(&gd.dbg.words[idx >> 5], 1u << (idx & 31));
+                            }
+                    }
+                }
+            }
+        }
+        if (POLICY == POLICY_DBG_ONLY) continue;
+        // stage 3: cbf probes of the present k-mers in flight, then the min-increment
+        uint32_t wc[kGroup][MAXH];
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j)
+            if (found & (1u << j)) {
+#pragma unroll
+                for (int h = 0; h < MAXH; ++h)
+                    if (h < gd.cbf.num_hash) {
+                        const uint64_t idx = fm_index(expand_hash(base[j], h, gd.hm), gd.cbf.fm);
+                        wc[j][h] = ld_cg(&gd.cbf.words[idx >> 2]);
+                    }
+            }
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j)
+            if (found & (1u << j)) {
+                if (POLICY == POLICY_COUNT_IF_PRESENT) {  // "&& cbf.getCount(hashVals) > 0" (graph :425)
+                    int mn = 127;
+#pragma unroll
+                    for (int h = 0; h < MAXH; ++h)
+                        if (h < gd.cbf.num_hash) {
+                            const uint64_t idx = fm_index(expand_hash(base[j], h, gd.hm), gd.cbf.fm);
+                            const int v = byte_of(wc[j][h], (int)(idx & 3) * 8);
+                            mn = v < mn ? v : mn;
+                        }
+                    if (!(minifloat_to_float(mn) > 0.f)) continue;
+                }
+                cbf_increment<MAXH>(gd.cbf, base[j], gd.hm, mix64(base[j] ^ gd.rng_seed) + (uint64_t)(pos + i0 + j) * 0x632BE59BD9B4E019ULL, wc[j]);
+            }
+    }
+}
+
+// ---- graph.getKmers / getCount over reads (graph :562-570, :1224-1226; HashFunction.java:55-85) --------------------
+template <int MODE, int MAXH>
+__global__ void __launch_bounds__(kThreads) k_graph_count(const Ingest g, const GraphDev gd, float* __restrict__ counts,
+                                                         int64_t* __restrict__ fhash, int64_t* __restrict__ rhash) {
+    __shared__ RollLut lut;
+    build_lut(&lut, gd.k);
+    const int64_t pos = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * kChunk;
+    if (pos >= g.n_pos) return;
+    const int n = (int)min((int64_t)kChunk, g.n_pos - pos);
+    PositionWalker<MODE> pw;
+    pw.start(g, pos, gd.k, lut);
+    for (int i0 = 0; i0 < n; i0 += kGroup) {
+        uint64_t base[kGroup];
+        uint32_t wd[kGroup][MAXH], wc[kGroup][MAXH];
+        uint32_t ok = 0;
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) {
+            if (i0 + j < n) {
+                pw.advance(g, gd.k, lut);
+                base[j] = pw.wk.base();
+                const int64_t o = g.out_base + pos + i0 + j;
+                if (fhash) fhash[o] = (int64_t)pw.wk.f;
+                if (rhash) rhash[o] = (int64_t)pw.wk.r;
+                if (pw.wk.bad == 0) {
+                    ok |= 1u << j;
+#pragma unroll
+                    for (int h = 0; h < MAXH; ++h) {
+                        if (h < gd.dbg.num_hash) {
+                            const uint64_t idx = fm_index(expand_hash(base[j], h, gd.hm), gd.dbg.fm);
+                            wd[j][h] = ld_cg(&gd.dbg.words[idx >> 5]);
+                        }
+                        if (h < gd.cbf.num_hash) {
+                            const uint64_t idx = fm_index(expand_hash(base[j], h, gd.hm), gd.cbf.fm);
+                            wc[j][h] = ld_cg(&gd.cbf.words[idx >> 2]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) {
+            if (i0 + j < n) {
+                float c = 0.f;
+                if (ok & (1u << j)) {
+                    bool all = true;
+                    int mn = 127;
+#pragma unroll
+                    for (int h = 0; h < MAXH; ++h) {
+                        if (h < gd.dbg.num_hash) {
+                            const uint64_t idx = fm_index(expand_hash(base[j], h, gd.hm), gd.dbg.fm);
+                            all = all && ((wd[j][h] >> (idx & 31)) & 1u);
+                        }
+                        if (h < gd.cbf.num_hash) {
+                            const uint64_t idx = fm_index(expand_hash(base[j], h, gd.hm), gd.cbf.fm);
+                            const int v = byte_of(wc[j][h], (int)(idx & 3) * 8);
+                            mn = v < mn ? v : mn;
+                        }
+                    }
+                    if (all) c = minifloat_to_float(mn) + 1.f;
+                }
+                if (counts) counts[g.out_base + pos + i0 + j] = c;
+            }
+        }
+    }
+}
+
+// ---- the k-merizer alone: NTHashIterator family (bloom/hash/NTHashIterator.java:47-69 and twins) --------------------
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) k_kmerize(const Ingest g, int k, int64_t* __restrict__ fhash, int64_t* __restrict__ rhash,
+                                                     int64_t* __restrict__ base) {
+    __shared__ RollLut lut;
+    build_lut(&lut, k);
+    const int64_t pos = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * kChunk;
+    if (pos >= g.n_pos) return;
+    const int n = (int)min((int64_t)kChunk, g.n_pos - pos);
+    PositionWalker<MODE> pw;
+    pw.start(g, pos, k, lut);
+    for (int i = 0; i < n; ++i) {
+        pw.advance(g, k, lut);
+        const int64_t o = g.out_base + pos + i;
+        if (fhash) fhash[o] = (int64_t)pw.wk.f;
+        if (rhash) rhash[o] = (int64_t)pw.wk.r;
+        if (base) base[o] = (int64_t)pw.wk.base();
+    }
+}
+
+// ---- paired k-mers: Paired*NTHashIterator (bloom/hash/PairedNTHashIterator.java:55-85, Canonical...:39-60, RC...:35-56)
+// positions are pair positions (len-k-d+1 per read).  PAIR_OP: 0 = write hValsP[0]; 1 = pkbf.add (graph :455-461);
+// 2 = pkbf.add only when both k-mers are in dbgbf (RNABloom.java:389-399)
+__device__ __forceinline__ int count_masked(const uint32_t* mask, int64_t start, int n) {
+    if (!mask) return 0;
+    int c = 0;
+    for (int64_t b = start; b < start + n;) {
+        const int sh = (int)(b & 31);
+        const int take = min(32 - sh, (int)(start + n - b));
+        const uint32_t w = __ldg(&mask[b >> 5]) >> sh;
+        c += __popc(take == 32 ? w : (w & ((1u << take) - 1u)));
+        b += take;
+    }
+    return c;
+}
+template <int MODE, int MAXH, int PAIR_OP>
+__global__ void __launch_bounds__(kThreads) k_pairs(const Ingest g, const GraphDev gd, const BitFilter pk, int d,
+                                                   int64_t* __restrict__ pair_out) {
+    __shared__ RollLut lut;
+    build_lut(&lut, gd.k);
+    const int64_t pos = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * kChunk;
+    if (pos >= g.n_pos) return;
+    const int n = (int)min((int64_t)kChunk, g.n_pos - pos);
+    const int k = gd.k;
+    int64_t read; int32_t in_read;
+    locate(g, pos, read, in_read);
+    int32_t npos = read_npos(g, read);
+    KmerWalker<MODE> L, R;
+    int span_bad = 0;
+    bool primed = false;
+    for (int i = 0; i < n; ++i) {
+        if (!primed || in_read >= npos) {
+            if (primed) { do { ++read; npos = read_npos(g, read); } while (npos <= 0); in_read = 0; }
+            const int64_t s = read_start(g, read) + in_read;
+            L.init(g, s, k, lut);
+            R.init(g, s + d, k, lut);
+            span_bad = count_masked(g.mask, s, k + d);
+            primed = true;
+        } else {
+            // the base leaving the span is L's out base, the base entering is R's in base
+            const int64_t bo = L.out.b, bi = R.in.b;
+            if (g.mask) span_bad += (int)((__ldg(&g.mask[bi >> 5]) >> (bi & 31)) & 1u) - (int)((__ldg(&g.mask[bo >> 5]) >> (bo & 31)) & 1u);
+            L.roll(lut);
+            R.roll(lut);
+        }
+        uint64_t p;
+        if (MODE == 0) p = combine_hash(L.f, R.f);
+        else if (MODE == 1) p = combine_hash(R.r, L.r);
+        else {
+            const uint64_t p1 = combine_hash(L.f, R.f), p2 = combine_hash(R.r, L.r);
+            p = ((int64_t)p2 < (int64_t)p1) ? p2 : p1;  // Math.min on long
+        }
+        if (PAIR_OP == 0) pair_out[g.out_base + pos + i] = (int64_t)p;
+        else if (span_bad == 0) {
+            bool go = true;
+            if (PAIR_OP == 2) go = bf_lookup<MAXH>(gd.dbg, L.base(), gd.hm) && bf_lookup<MAXH>(gd.dbg, R.base(), gd.hm);
+            if (go) bf_add<MAXH>(pk, p, gd.hm);
+        }
+        ++in_read;
+    }
+}
+
+// ---- per-hash operators: the `long hashVal` overloads (bloom/BloomFilter.java:139-182, CountingBloomFilter.java:126-251) -
+enum { OP_BF_ADD = 0, OP_BF_LOOKUP, OP_BF_LTA, OP_CBF_INC, OP_CBF_INC_GET, OP_CBF_COUNT, OP_GRAPH_ADD, OP_GRAPH_COUNT_IF_PRESENT,
+       OP_GRAPH_COUNT };
+template <int MAXH, int OP>
+__global__ void __launch_bounds__(kThreads) k_hash_op(const int64_t* __restrict__ base, int64_t n, const GraphDev gd,
+                                                     uint8_t* __restrict__ out8, float* __restrict__ outf) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t b = (uint64_t)base[i];
+    if (OP == OP_BF_ADD) bf_add<MAXH>(gd.dbg, b, gd.hm);
+    else if (OP == OP_BF_LOOKUP) out8[i] = bf_lookup<MAXH>(gd.dbg, b, gd.hm) ? 1 : 0;
+    else if (OP == OP_BF_LTA) out8[i] = bf_lookup_then_add<MAXH>(gd.dbg, gd.ct, b, gd.hm) ? 1 : 0;
+    else if (OP == OP_CBF_INC) cbf_increment<MAXH>(gd.cbf, b, gd.hm, (mix64(b ^ gd.rng_seed) + (uint64_t)i * 0x632BE59BD9B4E019ULL), nullptr);
+    else if (OP == OP_CBF_INC_GET) outf[i] = minifloat_to_float(cbf_increment<MAXH>(gd.cbf, b, gd.hm, (mix64(b ^ gd.rng_seed) + (uint64_t)i * 0x632BE59BD9B4E019ULL), nullptr));
+    else if (OP == OP_CBF_COUNT) outf[i] = minifloat_to_float(cbf_min<MAXH>(gd.cbf, b, gd.hm));
+    else if (OP == OP_GRAPH_ADD) {
+        if (bf_lookup_then_add<MAXH>(gd.dbg, gd.ct, b, gd.hm)) cbf_increment<MAXH>(gd.cbf, b, gd.hm, (mix64(b ^ gd.rng_seed) + (uint64_t)i * 0x632BE59BD9B4E019ULL), nullptr);
+    } else if (OP == OP_GRAPH_COUNT_IF_PRESENT) {
+        if (bf_lookup<MAXH>(gd.dbg, b, gd.hm) && minifloat_to_float(cbf_min<MAXH>(gd.cbf, b, gd.hm)) > 0.f)
+            cbf_increment<MAXH>(gd.cbf, b, gd.hm, (mix64(b ^ gd.rng_seed) + (uint64_t)i * 0x632BE59BD9B4E019ULL), nullptr);
+    } else if (OP == OP_GRAPH_COUNT) {
+        outf[i] = bf_lookup<MAXH>(gd.dbg, b, gd.hm) ? minifloat_to_float(cbf_min<MAXH>(gd.cbf, b, gd.hm)) + 1.f : 0.f;
+    }
+}
+
+// ---- a8 getIndex exposed on its own (bloom/BloomFilter.java:108-111) -------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_index(const int64_t* __restrict__ hash, int64_t n, const FastMod fm, int64_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i < n) out[i] = (int64_t)fm_index((uint64_t)hash[i], fm);
+}
+
+// ---- popcount: set bits (Bloom) / non-zero bytes (counting)  (bloom/buffer/UnsafeByteBuffer.java:121-150) -------------
+// Pure streaming read of the array: uint4 loads, warp shuffle reduction, one atomic per warp.
+template <int BYTES_MODE>
+__global__ void __launch_bounds__(kThreads) k_popcount(const uint4* __restrict__ v, int64_t n_vec, unsigned long long* out) {
+    unsigned long long c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * kThreads) {
+        const uint4 x = __ldg(&v[i]);
+        if (BYTES_MODE) c += (__popc(__vcmpne4(x.x, 0)) + __popc(__vcmpne4(x.y, 0)) + __popc(__vcmpne4(x.z, 0)) + __popc(__vcmpne4(x.w, 0))) >> 3;
+        else c += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+// ---- synthetic reads (bench / fixtures; a counter-based generator the CPU checker restates bit for bit) ----------------
+__device__ __forceinline__ int synth_genome_base(uint64_t seed, uint64_t pos) { return (int)(mix64(seed ^ mix64(pos)) & 3); }
+__global__ void __launch_bounds__(kThreads) k_synth_reads(uint64_t seed, uint64_t genome_len, uint64_t first_read, int64_t n_reads, int L,
+                                                         uint32_t err_ppm, int64_t stride_bases, uint64_t* __restrict__ packed) {
+    const int words_per_read = (int)(stride_bases >> 5);
+    const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (t >= n_reads * words_per_read) return;
+    const int64_t rl = t / words_per_read;
+    const int wi = (int)(t - rl * words_per_read);
+    const uint64_t r = first_read + (uint64_t)rl;
+    const uint64_t h = mix64(seed * 0x100000001B3ULL + 2 * r + 1);
+    const uint64_t p0 = (h >> 1) % (genome_len - (uint64_t)L + 1);
+    const int rc = (int)(h & 1);
+    uint64_t w = 0;
+    for (int j = 0; j < 32; ++j) {
+        const int i = wi * 32 + j;
+        if (i >= L) break;
+        int b = rc ? 3 - synth_genome_base(seed, p0 + (uint64_t)(L - 1 - i)) : synth_genome_base(seed, p0 + (uint64_t)i);
+        const uint64_t e = mix64((seed + 0x5851F42D4C957F2DULL) ^ mix64(r * 1024 + (uint64_t)i));
+        if ((uint32_t)(e % 1000000u) < err_ppm) b = (b + 1 + (int)((e >> 40) % 3)) & 3;
+        w |= (uint64_t)b << (2 * j);
+    }
+    packed[rl * words_per_read + wi] = w;
+}
+
+// ---- FASTQ/FASTA front end: ASCII (+PHRED33) -> 2-bit codes + usable-base mask ------------------------------------------
+// One thread per 32-base output word.  Replaces the host regex pre-pass (util/SeqUtils.java:1430-1438, RNABloom.java:567-577).
+__global__ void __launch_bounds__(kThreads) k_pack_ascii(const char* __restrict__ bases, const char* __restrict__ quals,
+                                                        const int64_t* __restrict__ ascii_off, const int64_t* __restrict__ word_off,
+                                                        int64_t n_reads, int64_t n_words, int min_qual, uint64_t* __restrict__ packed,
+                                                        uint32_t* __restrict__ mask) {
+    const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (t >= n_words) return;
+    int64_t lo = 0, hi = n_reads;  // read whose word range contains t
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(&word_off[mid]) <= t) lo = mid; else hi = mid;
+    }
+    const int64_t a0 = __ldg(&ascii_off[lo]);
+    const int len = (int)(__ldg(&ascii_off[lo + 1]) - a0);
+    const int first = (int)(t - __ldg(&word_off[lo])) * 32;
+    uint64_t w = 0;
+    uint32_t m = 0;
+    const int qlo = '!' + min_qual;
+    for (int j = 0; j < 32; ++j) {
+        const int i = first + j;
+        if (i >= len) { m |= 1u << j; continue; }
+        const unsigned char c = (unsigned char)bases[a0 + i];
+        int code = 0;
+        bool ok = true;
+        switch (c) {
+            case 'A': case 'a': code = 0; break;
+            case 'C': case 'c': code = 1; break;
+            case 'G': case 'g': code = 2; break;
+            case 'T': case 't': case 'U': case 'u': code = 3; break;
+            default: ok = false;
+        }
+        if (quals) { const unsigned char q = (unsigned char)quals[a0 + i]; if (q < qlo || q > '~') ok = false; }
+        w |= (uint64_t)code << (2 * j);
+        if (!ok) m |= 1u << j;
+    }
+    packed[t] = w;
+    mask[t] = m;
+}
+
+}  // namespace rb

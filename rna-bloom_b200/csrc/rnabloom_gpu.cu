@@ -1,0 +1,1089 @@
+// rnabloom_gpu.cu -- host side of librnabloom_gpu.so: the C-ABI of include/rnabloom_gpu.h over the kernels in
+// rb_kernels.cuh.  Owns device memory, streams, sub-batching and the reference's file formats.  No torch, no oracle:
+// if CUDA is unavailable every entry point fails with RB_ECUDA.  Citations: /root/reference/src/rnabloom/.
+#include "../../include/rnabloom_gpu.h"
+#include "rb_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace rb;
+
+// ------------------------------------------------------------------------------------------------------------------
+struct rb_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::recursive_mutex mu;
+    std::string err;
+    uint64_t rng_seed = 0x243F6A8885A308D3ULL;
+    int64_t subbatch_kmers = 1LL << 25;
+    int64_t launches = 0;
+    int sm_count = 148;
+    // claim table (DESIGN.md "Linearisation")
+    unsigned long long* claim = nullptr;
+    int64_t claim_cap = 0, claim_used = 0;
+    // staging (host-pointer entry points)
+    void* stage[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int64_t stage_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long* scratch = nullptr;  // 8-byte device scalar
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+struct rb_filter {
+    rb_ctx* ctx;
+    int kind;
+    int64_t size;      // bits or bytes
+    int64_t nbytes;    // logical byte length (file size)
+    int64_t alloc;     // allocated bytes (multiple of 256, >= nbytes + 16)
+    int num_hash, k;
+    uint32_t* dev;
+    bool in_graph;
+};
+struct rb_graph {
+    rb_ctx* ctx;
+    rb_filter *dbg, *cbf, *rpk, *fpk;
+    int k, stranded, hd, hc, hp, hmax;
+    int d_read, d_frag;
+};
+
+static thread_local std::string g_create_err;
+
+static int32_t fail(rb_ctx* c, int32_t code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_err = msg;
+    return code;
+}
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? RB_ENOMEM : RB_ECUDA,                      \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                              \
+    } while (0)
+#define LOCK(c) std::lock_guard<std::recursive_mutex> lock_((c)->mu); cudaSetDevice((c)->device)
+#define LAUNCH_CHECK()                                                                                    \
+    do {                                                                                                  \
+        ++ctx->launches;                                                                                  \
+        cudaError_t e_ = cudaGetLastError();                                                              \
+        if (e_ != cudaSuccess) return fail(ctx, RB_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
+    } while (0)
+
+static FastMod make_fm(int64_t size) {
+    FastMod fm;
+    fm.size = (uint64_t)size;
+    fm.pow2 = (size & (size - 1)) == 0;
+    fm.mask = (uint64_t)size - 1;
+    fm.magic = fm.pow2 ? 0 : (uint64_t)((((unsigned __int128)1) << 64) / (unsigned __int128)size);
+    return fm;
+}
+static HashMults make_hm(int k) {
+    HashMults hm;
+    for (int i = 0; i < kMaxHash; ++i) hm.m[i] = (uint64_t)(int64_t)i ^ ((uint64_t)(int64_t)k * kMultiSeed);
+    return hm;
+}
+static inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- context ---------------------------------------------------------------------------------------------------------
+extern "C" int32_t rb_version(void) { return 100; }
+
+extern "C" int32_t rb_ctx_create(int32_t device, rb_ctx** out) {
+    if (!out) return fail(nullptr, RB_EINVAL, "rb_ctx_create: out is NULL");
+    *out = nullptr;
+    rb_ctx* ctx = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, RB_ECUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count is 0"));
+    if (device < 0 || device >= n) return fail(nullptr, RB_EINVAL, "rb_ctx_create: bad device index");
+    CK(cudaSetDevice(device));
+    rb_ctx* c = new rb_ctx();
+    c->device = device;
+    ctx = c;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    if (e != cudaSuccess || prop.major < 10) {
+        std::string m = e != cudaSuccess ? cudaGetErrorString(e) : "device is not sm_100 (this library ships sm_100a code only)";
+        delete c;
+        return fail(nullptr, RB_ECUDA, m);
+    }
+    e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&c->scratch, 64);
+    if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, RB_ECUDA, m); }
+    c->stream = c->own_stream;
+    *out = c;
+    return RB_OK;
+}
+extern "C" int32_t rb_ctx_destroy(rb_ctx* ctx) {
+    if (!ctx) return RB_EINVAL;
+    {
+        LOCK(ctx);
+        cudaStreamSynchronize(ctx->stream);
+        for (int i = 0; i < 8; ++i) if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+        if (ctx->claim) cudaFree(ctx->claim);
+        if (ctx->scratch) cudaFree(ctx->scratch);
+        if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
+        if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    }
+    delete ctx;
+    return RB_OK;
+}
+extern "C" const char* rb_last_error(rb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+extern "C" int32_t rb_ctx_set_stream(rb_ctx* ctx, void* s) {
+    if (!ctx) return RB_EINVAL;
+    LOCK(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return RB_OK;
+}
+extern "C" int32_t rb_ctx_sync(rb_ctx* ctx) {
+    if (!ctx) return RB_EINVAL;
+    LOCK(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RB_OK;
+}
+extern "C" int32_t rb_ctx_set_rng_seed(rb_ctx* ctx, uint64_t seed) { if (!ctx) return RB_EINVAL; ctx->rng_seed = seed; return RB_OK; }
+extern "C" int32_t rb_ctx_set_subbatch_kmers(rb_ctx* ctx, int64_t kmers) {
+    if (!ctx || kmers < 1024) return RB_EINVAL;
+    LOCK(ctx);
+    ctx->subbatch_kmers = kmers;
+    return RB_OK;
+}
+extern "C" int64_t rb_ctx_kernel_launches(rb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int32_t rb_timer_start(rb_ctx* ctx) {
+    if (!ctx) return RB_EINVAL;
+    LOCK(ctx);
+    if (!ctx->ev0) { CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1)); }
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    return RB_OK;
+}
+extern "C" int32_t rb_timer_stop(rb_ctx* ctx, float* ms) {
+    if (!ctx || !ms || !ctx->ev0) return RB_EINVAL;
+    LOCK(ctx);
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return RB_OK;
+}
+extern "C" int32_t rb_host_alloc(void** p, int64_t bytes) {
+    if (!p || bytes < 0) return RB_EINVAL;
+    return cudaHostAlloc(p, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault) == cudaSuccess ? RB_OK : RB_ENOMEM;
+}
+extern "C" int32_t rb_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? RB_OK : RB_ECUDA; }
+extern "C" int32_t rb_dev_alloc(rb_ctx* ctx, void** p, int64_t bytes) {
+    if (!ctx || !p || bytes < 0) return RB_EINVAL;
+    LOCK(ctx);
+    CK(cudaMalloc(p, (size_t)std::max<int64_t>(bytes, 16)));
+    return RB_OK;
+}
+extern "C" int32_t rb_dev_free(rb_ctx* ctx, void* p) {
+    if (!ctx) return RB_EINVAL;
+    LOCK(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(p));
+    return RB_OK;
+}
+extern "C" int32_t rb_memcpy_h2d(rb_ctx* ctx, void* dst, const void* src, int64_t bytes) {
+    if (!ctx) return RB_EINVAL;
+    LOCK(ctx);
+    CK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RB_OK;
+}
+extern "C" int32_t rb_memcpy_d2h(rb_ctx* ctx, void* dst, const void* src, int64_t bytes) {
+    if (!ctx) return RB_EINVAL;
+    LOCK(ctx);
+    CK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RB_OK;
+}
+
+// grow-only device staging slot
+static int32_t stage_get(rb_ctx* ctx, int slot, int64_t bytes, void** p) {
+    bytes = std::max<int64_t>(bytes, 256);
+    if (ctx->stage_bytes[slot] < bytes) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->stage[slot]) CK(cudaFree(ctx->stage[slot]));
+        ctx->stage[slot] = nullptr; ctx->stage_bytes[slot] = 0;
+        const int64_t want = bytes + bytes / 4 + 256;
+        CK(cudaMalloc(&ctx->stage[slot], (size_t)want));
+        ctx->stage_bytes[slot] = want;
+    }
+    *p = ctx->stage[slot];
+    return RB_OK;
+}
+
+// Make room in the claim table for `n` more claims (clears it when the load factor would pass 1/2).
+static int32_t claim_reserve(rb_ctx* ctx, int64_t n, ClaimTable* ct) {
+    int64_t need = 1024;
+    while (need < 2 * n) need <<= 1;
+    if (ctx->claim_cap < need) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->claim) CK(cudaFree(ctx->claim));
+        ctx->claim = nullptr; ctx->claim_cap = 0;
+        CK(cudaMalloc(&ctx->claim, (size_t)(need + 1) * 8));
+        ctx->claim_cap = need;
+        ctx->claim_used = ctx->claim_cap;  // force the clear below
+    }
+    if (ctx->claim_used + n > ctx->claim_cap / 2) {
+        CK(cudaMemsetAsync(ctx->claim, 0, (size_t)(ctx->claim_cap + 1) * 8, ctx->stream));
+        ctx->claim_used = 0;
+    }
+    ctx->claim_used += n;
+    ct->slots = ctx->claim;
+    ct->mask = (uint64_t)ctx->claim_cap - 1;
+    int lg = 0;
+    while ((1LL << lg) < ctx->claim_cap) ++lg;
+    ct->shift = 64 - lg;
+    return RB_OK;
+}
+static void claim_invalidate(rb_ctx* ctx) { ctx->claim_used = ctx->claim_cap; }  // after empty()/upload(): stale claims must go
+
+// ---- host helpers ------------------------------------------------------------------------------------------------------
+extern "C" int64_t rb_expected_size(int64_t n, float fpr, int32_t num_hash) {  // BloomFilter.java:196-199
+    const double r = (double)(-num_hash) / std::log(1 - std::exp(std::log((double)fpr) / (double)num_hash));
+    return (int64_t)std::ceil((double)n * r);
+}
+extern "C" float rb_minifloat_to_float(int8_t b) { return minifloat_to_float((int)b); }
+
+extern "C" int64_t rb_kmer_offsets(const int32_t* read_len, int64_t n_reads, int32_t uniform_len, int32_t k, int64_t* off) {
+    int64_t acc = 0;
+    for (int64_t i = 0; i < n_reads; ++i) {
+        if (off) off[i] = acc;
+        const int32_t len = read_len ? read_len[i] : uniform_len;
+        acc += std::max(0, len - k + 1);
+    }
+    if (off) off[n_reads] = acc;
+    return acc;
+}
+extern "C" int64_t rb_pack_reads_host(const char* bases, const char* quals, const int64_t* ascii_off, int64_t n_reads, int32_t min_qual,
+                                      uint64_t* packed, uint32_t* mask, int64_t* out_read_off, int32_t* out_read_len) {
+    int64_t word = 0;
+    const int qlo = '!' + min_qual;
+    for (int64_t r = 0; r < n_reads; ++r) {
+        const int64_t a0 = ascii_off[r];
+        const int len = (int)(ascii_off[r + 1] - a0);
+        out_read_off[r] = word * 32;
+        out_read_len[r] = len;
+        const int nw = (len + 31) / 32;
+        for (int wi = 0; wi < nw; ++wi) {
+            uint64_t w = 0; uint32_t m = 0;
+            for (int j = 0; j < 32; ++j) {
+                const int i = wi * 32 + j;
+                if (i >= len) { m |= 1u << j; continue; }
+                int code = 0; bool ok = true;
+                switch ((unsigned char)bases[a0 + i]) {
+                    case 'A': case 'a': code = 0; break;
+                    case 'C': case 'c': code = 1; break;
+                    case 'G': case 'g': code = 2; break;
+                    case 'T': case 't': case 'U': case 'u': code = 3; break;
+                    default: ok = false;
+                }
+                if (quals) { const unsigned char q = (unsigned char)quals[a0 + i]; if (q < qlo || q > '~') ok = false; }
+                w |= (uint64_t)code << (2 * j);
+                if (!ok) m |= 1u << j;
+            }
+            packed[word] = w;
+            if (mask) mask[word] = m;
+            ++word;
+        }
+    }
+    return word * 32;
+}
+
+// ---- filters -------------------------------------------------------------------------------------------------------------
+static int32_t filter_alloc(rb_ctx* ctx, int kind, int64_t size, int num_hash, int k, rb_filter** out) {
+    if (!ctx || !out) return RB_EINVAL;
+    if (size <= 0 || num_hash < 1 || num_hash > kMaxHash || k < 1) return fail(ctx, RB_EINVAL, "filter: size/num_hash/k out of range");
+    rb_filter* f = new rb_filter();
+    f->ctx = ctx; f->kind = kind; f->size = size; f->num_hash = num_hash; f->k = k; f->in_graph = false;
+    f->nbytes = kind == RB_BLOOM ? size / 8 + ((size % 8) ? 1 : 0) : size;  // UnsafeBitBuffer.java:44-49
+    f->alloc = div_up(f->nbytes + 16, 256) * 256;
+    cudaError_t e = cudaMalloc(&f->dev, (size_t)f->alloc);
+    if (e != cudaSuccess) { delete f; return fail(ctx, RB_ENOMEM, std::string("cudaMalloc(filter): ") + cudaGetErrorString(e)); }
+    e = cudaMemsetAsync(f->dev, 0, (size_t)f->alloc, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(f->dev); delete f; return fail(ctx, RB_ECUDA, cudaGetErrorString(e)); }
+    *out = f;
+    return RB_OK;
+}
+extern "C" int32_t rb_filter_create(rb_ctx* ctx, int32_t kind, int64_t size, int32_t num_hash, int32_t k, rb_filter** out) {
+    if (!ctx || !out || (kind != RB_BLOOM && kind != RB_COUNTING)) return RB_EINVAL;
+    LOCK(ctx);
+    return filter_alloc(ctx, kind, size, num_hash, k, out);
+}
+static int32_t filter_free(rb_filter* f) {
+    rb_ctx* ctx = f->ctx;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(f->dev));
+    delete f;
+    return RB_OK;
+}
+extern "C" int32_t rb_filter_destroy(rb_filter* f) {
+    if (!f) return RB_EINVAL;
+    if (f->in_graph) return fail(f->ctx, RB_ESTATE, "filter belongs to a graph; destroy the graph");
+    LOCK(f->ctx);
+    return filter_free(f);
+}
+extern "C" int32_t rb_filter_empty(rb_filter* f) {
+    if (!f) return RB_EINVAL;
+    rb_ctx* ctx = f->ctx;
+    LOCK(ctx);
+    CK(cudaMemsetAsync(f->dev, 0, (size_t)f->alloc, ctx->stream));
+    claim_invalidate(ctx);
+    return RB_OK;
+}
+extern "C" int64_t rb_filter_size(const rb_filter* f) { return f ? f->size : 0; }
+extern "C" int64_t rb_filter_num_bytes(const rb_filter* f) { return f ? f->nbytes : 0; }
+extern "C" int32_t rb_filter_num_hash(const rb_filter* f) { return f ? f->num_hash : 0; }
+extern "C" int32_t rb_filter_device_ptr(rb_filter* f, void** p) { if (!f || !p) return RB_EINVAL; *p = f->dev; return RB_OK; }
+
+static GraphDev filter_view(rb_filter* f) {  // a lone filter seen through the graph-shaped kernel argument
+    GraphDev gd;
+    memset(&gd, 0, sizeof gd);
+    gd.hm = make_hm(f->k);
+    gd.k = f->k;
+    gd.rng_seed = f->ctx->rng_seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(f->ctx->launches + 1);  // fresh coins every launch
+    gd.dbg.words = f->dev; gd.dbg.fm = make_fm(f->size); gd.dbg.num_hash = f->num_hash;
+    gd.cbf.words = f->dev; gd.cbf.fm = make_fm(f->size); gd.cbf.num_hash = f->num_hash;
+    return gd;
+}
+
+template <int OP>
+static void launch_hash_op(int maxh, int64_t n, cudaStream_t s, const int64_t* base, const GraphDev& gd, uint8_t* o8, float* of) {
+    const int grid = (int)div_up(n, kThreads);
+    if (maxh <= 2) k_hash_op<2, OP><<<grid, kThreads, 0, s>>>(base, n, gd, o8, of);
+    else if (maxh <= 3) k_hash_op<3, OP><<<grid, kThreads, 0, s>>>(base, n, gd, o8, of);
+    else if (maxh <= 4) k_hash_op<4, OP><<<grid, kThreads, 0, s>>>(base, n, gd, o8, of);
+    else k_hash_op<8, OP><<<grid, kThreads, 0, s>>>(base, n, gd, o8, of);
+}
+static void dispatch_hash_op(int op, int maxh, int64_t n, cudaStream_t s, const int64_t* base, const GraphDev& gd, uint8_t* o8, float* of) {
+    switch (op) {
+        case OP_BF_ADD: launch_hash_op<OP_BF_ADD>(maxh, n, s, base, gd, o8, of); break;
+        case OP_BF_LOOKUP: launch_hash_op<OP_BF_LOOKUP>(maxh, n, s, base, gd, o8, of); break;
+        case OP_BF_LTA: launch_hash_op<OP_BF_LTA>(maxh, n, s, base, gd, o8, of); break;
+        case OP_CBF_INC: launch_hash_op<OP_CBF_INC>(maxh, n, s, base, gd, o8, of); break;
+        case OP_CBF_INC_GET: launch_hash_op<OP_CBF_INC_GET>(maxh, n, s, base, gd, o8, of); break;
+        case OP_CBF_COUNT: launch_hash_op<OP_CBF_COUNT>(maxh, n, s, base, gd, o8, of); break;
+        case OP_GRAPH_ADD: launch_hash_op<OP_GRAPH_ADD>(maxh, n, s, base, gd, o8, of); break;
+        case OP_GRAPH_COUNT_IF_PRESENT: launch_hash_op<OP_GRAPH_COUNT_IF_PRESENT>(maxh, n, s, base, gd, o8, of); break;
+        default: launch_hash_op<OP_GRAPH_COUNT>(maxh, n, s, base, gd, o8, of); break;
+    }
+}
+
+// host-pointer per-hash operator: H2D hashes, run, D2H results, in sub-batches
+static int32_t run_hash_op(rb_ctx* ctx, int op, GraphDev gd, int maxh, const int64_t* base, int64_t n, uint8_t* out8, float* outf) {
+    if (n < 0 || (n > 0 && !base)) return fail(ctx, RB_EINVAL, "hash op: bad arguments");
+    const bool needs_claim = (op == OP_BF_LTA || op == OP_GRAPH_ADD);
+    const int64_t step = ctx->subbatch_kmers;
+    for (int64_t i0 = 0; i0 < n; i0 += step) {
+        const int64_t m = std::min(step, n - i0);
+        void *dbase, *dout;
+        int32_t rc = stage_get(ctx, 0, m * 8, &dbase); if (rc) return rc;
+        rc = stage_get(ctx, 1, m * 4, &dout); if (rc) return rc;
+        if (needs_claim) { rc = claim_reserve(ctx, m, &gd.ct); if (rc) return rc; }
+        CK(cudaMemcpyAsync(dbase, base + i0, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+        dispatch_hash_op(op, maxh, m, ctx->stream, (const int64_t*)dbase, gd, (uint8_t*)dout, (float*)dout);
+        LAUNCH_CHECK();
+        if (out8) CK(cudaMemcpyAsync(out8 + i0, dout, (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+        if (outf) CK(cudaMemcpyAsync(outf + i0, dout, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return RB_OK;
+}
+#define FILTER_OP(f, want_kind, op, o8, of)                                                      \
+    if (!(f)) return RB_EINVAL;                                                                  \
+    rb_ctx* ctx = (f)->ctx;                                                                      \
+    LOCK(ctx);                                                                                   \
+    if ((f)->kind != (want_kind)) return fail(ctx, RB_EINVAL, "wrong filter kind for this call"); \
+    return run_hash_op(ctx, (op), filter_view(f), (f)->num_hash, base, n, (o8), (of))
+
+extern "C" int32_t rb_filter_add_hashes(rb_filter* f, const int64_t* base, int64_t n) { FILTER_OP(f, RB_BLOOM, OP_BF_ADD, nullptr, nullptr); }
+extern "C" int32_t rb_filter_lookup_hashes(rb_filter* f, const int64_t* base, int64_t n, uint8_t* out) { FILTER_OP(f, RB_BLOOM, OP_BF_LOOKUP, out, nullptr); }
+extern "C" int32_t rb_filter_lookup_then_add_hashes(rb_filter* f, const int64_t* base, int64_t n, uint8_t* out) { FILTER_OP(f, RB_BLOOM, OP_BF_LTA, out, nullptr); }
+extern "C" int32_t rb_cbf_increment_hashes(rb_filter* f, const int64_t* base, int64_t n) { FILTER_OP(f, RB_COUNTING, OP_CBF_INC, nullptr, nullptr); }
+extern "C" int32_t rb_cbf_increment_and_get_hashes(rb_filter* f, const int64_t* base, int64_t n, float* out) { FILTER_OP(f, RB_COUNTING, OP_CBF_INC_GET, nullptr, out); }
+extern "C" int32_t rb_cbf_count_hashes(rb_filter* f, const int64_t* base, int64_t n, float* out) { FILTER_OP(f, RB_COUNTING, OP_CBF_COUNT, nullptr, out); }
+
+extern "C" int32_t rb_filter_popcount(rb_filter* f, int64_t* out) {
+    if (!f || !out) return RB_EINVAL;
+    rb_ctx* ctx = f->ctx;
+    LOCK(ctx);
+    CK(cudaMemsetAsync(ctx->scratch, 0, 8, ctx->stream));
+    const int64_t n_vec = f->alloc / 16;  // the padding beyond nbytes is always zero
+    const int grid = (int)std::min<int64_t>(div_up(n_vec, kThreads), (int64_t)ctx->sm_count * 16);
+    if (f->kind == RB_BLOOM) k_popcount<0><<<grid, kThreads, 0, ctx->stream>>>((const uint4*)f->dev, n_vec, ctx->scratch);
+    else k_popcount<1><<<grid, kThreads, 0, ctx->stream>>>((const uint4*)f->dev, n_vec, ctx->scratch);
+    LAUNCH_CHECK();
+    unsigned long long v = 0;
+    CK(cudaMemcpyAsync(&v, ctx->scratch, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *out = (int64_t)v;
+    return RB_OK;
+}
+extern "C" int32_t rb_filter_fpr(rb_filter* f, float* out) {  // BloomFilter.java:185-194
+    if (!f || !out) return RB_EINVAL;
+    int64_t pop = 0;
+    const int32_t rc = rb_filter_popcount(f, &pop);
+    if (rc) return rc;
+    *out = (float)std::pow((double)pop / (double)f->size, f->num_hash);
+    return RB_OK;
+}
+extern "C" int32_t rb_filter_download(rb_filter* f, void* dst, int64_t nbytes) {
+    if (!f || !dst) return RB_EINVAL;
+    rb_ctx* ctx = f->ctx;
+    LOCK(ctx);
+    if (nbytes != f->nbytes) return fail(ctx, RB_EINVAL, "download: nbytes must equal rb_filter_num_bytes()");
+    CK(cudaMemcpyAsync(dst, f->dev, (size_t)nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RB_OK;
+}
+extern "C" int32_t rb_filter_upload(rb_filter* f, const void* src, int64_t nbytes) {
+    if (!f || !src) return RB_EINVAL;
+    rb_ctx* ctx = f->ctx;
+    LOCK(ctx);
+    if (nbytes != f->nbytes) return fail(ctx, RB_EINVAL, "upload: nbytes must equal rb_filter_num_bytes()");
+    CK(cudaMemcpyAsync(f->dev, src, (size_t)nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    claim_invalidate(ctx);
+    return RB_OK;
+}
+
+// Float.toString look-alike for the "fpr:" line of the .desc files (value is informational: the reader skips it,
+// bloom/BloomFilter.java:73-88)
+static std::string java_float(float v) {
+    if (v == 0.f) return "0.0";
+    char buf[64];
+    int prec = 1;
+    for (; prec <= 9; ++prec) { snprintf(buf, sizeof buf, "%.*e", prec - 1, (double)v); if (strtof(buf, nullptr) == v) break; }
+    snprintf(buf, sizeof buf, "%.*e", prec - 1, (double)v);
+    std::string s(buf);
+    const size_t epos = s.find('e');
+    std::string mant = s.substr(0, epos);
+    const int ex = atoi(s.c_str() + epos + 1);
+    std::string digits;
+    for (char c : mant) if (c >= '0' && c <= '9') digits.push_back(c);
+    const bool neg = v < 0;
+    std::string out;
+    if (ex >= -3 && ex < 7) {
+        if (ex >= 0) {
+            std::string ip = digits.substr(0, std::min<size_t>(digits.size(), (size_t)ex + 1));
+            while ((int)ip.size() < ex + 1) ip.push_back('0');
+            std::string fp = digits.size() > (size_t)ex + 1 ? digits.substr(ex + 1) : "0";
+            out = ip + "." + fp;
+        } else {
+            out = "0." + std::string((size_t)(-ex - 1), '0') + digits;
+        }
+    } else {
+        out = digits.substr(0, 1) + "." + (digits.size() > 1 ? digits.substr(1) : "0") + "E" + std::to_string(ex);
+    }
+    return neg ? "-" + out : out;
+}
+
+static int32_t write_file(rb_ctx* ctx, const char* path, const void* data, size_t n) {
+    FILE* fp = fopen(path, "wb");
+    if (!fp) return fail(ctx, RB_EIO, std::string("cannot open for writing: ") + path);
+    const size_t w = n ? fwrite(data, 1, n, fp) : 0;
+    if (fclose(fp) != 0 || w != n) return fail(ctx, RB_EIO, std::string("short write: ") + path);
+    return RB_OK;
+}
+extern "C" int32_t rb_filter_save(rb_filter* f, const char* desc_path, const char* bits_path) {  // BloomFilter.java:113-124
+    if (!f || !desc_path || !bits_path) return RB_EINVAL;
+    rb_ctx* ctx = f->ctx;
+    LOCK(ctx);
+    float fpr = 0;
+    int32_t rc = rb_filter_fpr(f, &fpr);
+    if (rc) return rc;
+    const std::string desc = "size:" + std::to_string(f->size) + "\nnumhash:" + std::to_string(f->num_hash) + "\nfpr:" + java_float(fpr) + "\n";
+    rc = write_file(ctx, desc_path, desc.data(), desc.size());
+    if (rc) return rc;
+    std::vector<uint8_t> host((size_t)f->nbytes);
+    rc = rb_filter_download(f, host.data(), f->nbytes);
+    if (rc) return rc;
+    return write_file(ctx, bits_path, host.data(), host.size());
+}
+static int32_t read_desc(rb_ctx* ctx, const char* path, std::vector<std::pair<std::string, std::string>>* kv) {
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return fail(ctx, RB_EIO, std::string("cannot open: ") + path);
+    char line[512];
+    while (fgets(line, sizeof line, fp)) {
+        std::string s(line);
+        while (!s.empty() && (s.back() == '\n' || s.back() == '\r')) s.pop_back();
+        const size_t c = s.find(':');
+        if (c == std::string::npos) continue;
+        kv->emplace_back(s.substr(0, c), s.substr(c + 1));
+    }
+    fclose(fp);
+    return RB_OK;
+}
+extern "C" int32_t rb_filter_load(rb_ctx* ctx, int32_t kind, const char* desc_path, const char* bits_path, int32_t k, int32_t load_bits,
+                                  rb_filter** out) {  // BloomFilter.java:70-106
+    if (!ctx || !desc_path || !out) return RB_EINVAL;
+    LOCK(ctx);
+    std::vector<std::pair<std::string, std::string>> kv;
+    int32_t rc = read_desc(ctx, desc_path, &kv);
+    if (rc) return rc;
+    int64_t size = 0; int num_hash = 0;
+    for (auto& e : kv) { if (e.first == "size") size = atoll(e.second.c_str()); else if (e.first == "numhash") num_hash = atoi(e.second.c_str()); }
+    rb_filter* f = nullptr;
+    rc = filter_alloc(ctx, kind, size, num_hash, k, &f);
+    if (rc) return rc;
+    if (load_bits) {
+        if (!bits_path) { filter_free(f); return RB_EINVAL; }
+        FILE* fp = fopen(bits_path, "rb");
+        if (!fp) { filter_free(f); return fail(ctx, RB_EIO, std::string("cannot open: ") + bits_path); }
+        std::vector<uint8_t> host((size_t)f->nbytes);
+        const size_t got = fread(host.data(), 1, host.size(), fp);
+        fclose(fp);
+        if (got != host.size()) { filter_free(f); return fail(ctx, RB_EIO, std::string("file shorter than the filter: ") + bits_path); }
+        rc = rb_filter_upload(f, host.data(), f->nbytes);
+        if (rc) { filter_free(f); return rc; }
+    }
+    *out = f;
+    return RB_OK;
+}
+
+extern "C" int32_t rb_index_hashes(rb_ctx* ctx, const int64_t* hash, int64_t n, int64_t size, int64_t* out) {
+    if (!ctx || n < 0 || size <= 0 || (n > 0 && (!hash || !out))) return RB_EINVAL;
+    LOCK(ctx);
+    if (n == 0) return RB_OK;
+    void *din, *dout;
+    int32_t rc = stage_get(ctx, 0, n * 8, &din); if (rc) return rc;
+    rc = stage_get(ctx, 1, n * 8, &dout); if (rc) return rc;
+    CK(cudaMemcpyAsync(din, hash, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_index<<<(int)div_up(n, kThreads), kThreads, 0, ctx->stream>>>((const int64_t*)din, n, make_fm(size), (int64_t*)dout);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RB_OK;
+}
+
+// ---- ingest plumbing ---------------------------------------------------------------------------------------------------
+struct ReadsArg {
+    const uint64_t* packed; const uint32_t* mask; const int64_t* read_off; const int32_t* read_len;
+    int64_t n_reads; int32_t uniform_len; int64_t uniform_stride;
+    bool on_device;
+};
+// One launch worth of reads, all pointers on the device.
+struct Launch { Ingest ing; int64_t n_pos; };
+
+typedef int32_t (*LaunchFn)(rb_ctx* ctx, const Ingest& ing, void* user);
+
+// Splits the reads into launches of at most ctx->subbatch_kmers positions (span = bases a position needs: k or k+d),
+// stages host data when needed, and calls fn for each launch.  total_out receives the number of positions.
+static int32_t for_each_launch(rb_ctx* ctx, const ReadsArg& ra, int span, LaunchFn fn, void* user, int64_t* total_out) {
+    if (ra.n_reads < 0 || (ra.n_reads > 0 && !ra.packed)) return fail(ctx, RB_EINVAL, "reads: packed is NULL");
+    const bool uniform = ra.read_off == nullptr;
+    if (uniform && (ra.uniform_len <= 0 || ra.uniform_stride < ra.uniform_len)) return fail(ctx, RB_EINVAL, "reads: bad uniform layout");
+    if (!uniform && !ra.read_len) return fail(ctx, RB_EINVAL, "reads: read_len is NULL");
+    int64_t total = 0;
+    if (uniform) {
+        const int32_t npos = std::max(0, ra.uniform_len - span + 1);
+        total = npos * ra.n_reads;
+        if (npos > 0) {
+            const int64_t reads_per = std::max<int64_t>(1, ctx->subbatch_kmers / npos);
+            for (int64_t r0 = 0; r0 < ra.n_reads; r0 += reads_per) {
+                const int64_t nr = std::min(reads_per, ra.n_reads - r0);
+                Ingest ing;
+                memset(&ing, 0, sizeof ing);
+                ing.n_reads = nr; ing.n_pos = nr * npos; ing.out_base = r0 * npos;
+                ing.uniform_stride = ra.uniform_stride; ing.uniform_len = ra.uniform_len; ing.uniform_npos = npos;
+                const int64_t b_lo = r0 * ra.uniform_stride, b_hi = (r0 + nr - 1) * ra.uniform_stride + ra.uniform_len;
+                if (ra.on_device) { ing.packed = ra.packed; ing.mask = ra.mask; ing.first_base = b_lo; }
+                else {
+                    const int64_t w_lo = b_lo >> 5, w_hi = (b_hi + 31) >> 5;
+                    void* dp; int32_t rc = stage_get(ctx, 0, (w_hi - w_lo) * 8, &dp); if (rc) return rc;
+                    CK(cudaMemcpyAsync(dp, ra.packed + w_lo, (size_t)(w_hi - w_lo) * 8, cudaMemcpyHostToDevice, ctx->stream));
+                    ing.packed = (const uint64_t*)dp - w_lo;
+                    if (ra.mask) {
+                        void* dm; rc = stage_get(ctx, 1, (w_hi - w_lo) * 4, &dm); if (rc) return rc;
+                        CK(cudaMemcpyAsync(dm, ra.mask + w_lo, (size_t)(w_hi - w_lo) * 4, cudaMemcpyHostToDevice, ctx->stream));
+                        ing.mask = (const uint32_t*)dm - w_lo;
+                    }
+                    ing.first_base = b_lo;
+                }
+                const int32_t rc = fn(ctx, ing, user);
+                if (rc) return rc;
+                if (!ra.on_device) CK(cudaStreamSynchronize(ctx->stream));  // staging is reused by the next launch
+            }
+        }
+    } else {
+        // per-read tables are needed on the host to cut launches
+        std::vector<int64_t> h_off; std::vector<int32_t> h_len;
+        const int64_t* off = ra.read_off; const int32_t* len = ra.read_len;
+        if (ra.on_device) {
+            h_off.resize((size_t)ra.n_reads); h_len.resize((size_t)ra.n_reads);
+            CK(cudaMemcpyAsync(h_off.data(), ra.read_off, (size_t)ra.n_reads * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(h_len.data(), ra.read_len, (size_t)ra.n_reads * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            off = h_off.data(); len = h_len.data();
+        }
+        std::vector<int64_t> pos_off((size_t)ra.n_reads + 1);
+        for (int64_t i = 0; i < ra.n_reads; ++i) { pos_off[(size_t)i] = total; total += std::max(0, len[i] - span + 1); }
+        pos_off[(size_t)ra.n_reads] = total;
+        int64_t r0 = 0;
+        while (r0 < ra.n_reads) {
+            int64_t r1 = r0 + 1;
+            while (r1 < ra.n_reads && pos_off[(size_t)r1 + 1] - pos_off[(size_t)r0] <= ctx->subbatch_kmers) ++r1;
+            const int64_t nr = r1 - r0, npos = pos_off[(size_t)r1] - pos_off[(size_t)r0];
+            if (npos > 0) {
+                Ingest ing;
+                memset(&ing, 0, sizeof ing);
+                ing.n_reads = nr; ing.n_pos = npos; ing.out_base = pos_off[(size_t)r0]; ing.pos_bias = pos_off[(size_t)r0];
+                void *d_po, *d_ro = nullptr, *d_rl = nullptr;
+                int32_t rc = stage_get(ctx, 2, (nr + 1) * 8, &d_po); if (rc) return rc;
+                CK(cudaMemcpyAsync(d_po, pos_off.data() + r0, (size_t)(nr + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+                ing.pos_off = (const int64_t*)d_po;
+                if (ra.on_device) { ing.packed = ra.packed; ing.mask = ra.mask; ing.read_off = ra.read_off + r0; ing.read_len = ra.read_len + r0; }
+                else {
+                    int64_t b_lo = INT64_MAX, b_hi = 0;
+                    for (int64_t i = r0; i < r1; ++i) if (len[i] > 0) { b_lo = std::min(b_lo, off[i]); b_hi = std::max(b_hi, off[i] + len[i]); }
+                    if (b_lo < 0) return fail(ctx, RB_EINVAL, "reads: negative read_off");
+                    const int64_t w_lo = b_lo >> 5, w_hi = (b_hi + 31) >> 5;
+                    void* dp; rc = stage_get(ctx, 0, (w_hi - w_lo) * 8, &dp); if (rc) return rc;
+                    CK(cudaMemcpyAsync(dp, ra.packed + w_lo, (size_t)(w_hi - w_lo) * 8, cudaMemcpyHostToDevice, ctx->stream));
+                    ing.packed = (const uint64_t*)dp - w_lo;
+                    if (ra.mask) {
+                        void* dm; rc = stage_get(ctx, 1, (w_hi - w_lo) * 4, &dm); if (rc) return rc;
+                        CK(cudaMemcpyAsync(dm, ra.mask + w_lo, (size_t)(w_hi - w_lo) * 4, cudaMemcpyHostToDevice, ctx->stream));
+                        ing.mask = (const uint32_t*)dm - w_lo;
+                    }
+                    rc = stage_get(ctx, 3, nr * 8, &d_ro); if (rc) return rc;
+                    rc = stage_get(ctx, 4, nr * 4, &d_rl); if (rc) return rc;
+                    CK(cudaMemcpyAsync(d_ro, off + r0, (size_t)nr * 8, cudaMemcpyHostToDevice, ctx->stream));
+                    CK(cudaMemcpyAsync(d_rl, len + r0, (size_t)nr * 4, cudaMemcpyHostToDevice, ctx->stream));
+                    ing.read_off = (const int64_t*)d_ro; ing.read_len = (const int32_t*)d_rl;
+                }
+                rc = fn(ctx, ing, user);
+                if (rc) return rc;
+                CK(cudaStreamSynchronize(ctx->stream));  // staging (slot 2 at least) is reused by the next launch
+            }
+            r0 = r1;
+        }
+    }
+    if (total_out) *total_out = total;
+    return RB_OK;
+}
+
+// ---- k-merizer ---------------------------------------------------------------------------------------------------------
+struct KmerizeUser { int k, mode, d; int64_t *f, *r, *b; int64_t *hf, *hr, *hb; bool pairs; };
+static int32_t kmerize_launch(rb_ctx* ctx, const Ingest& ing, void* user) {
+    KmerizeUser* u = (KmerizeUser*)user;
+    const int grid = (int)div_up(div_up(ing.n_pos, kChunk), kThreads);
+    // outputs: device staging slots 5..7 indexed by launch-local position
+    Ingest g = ing;
+    const int64_t out0 = ing.out_base;
+    g.out_base = 0;
+    int64_t *df = nullptr, *dr = nullptr, *db = nullptr;
+    int32_t rc;
+    if (u->hf) { void* p; rc = stage_get(ctx, 5, ing.n_pos * 8, &p); if (rc) return rc; df = (int64_t*)p; }
+    if (u->hr) { void* p; rc = stage_get(ctx, 6, ing.n_pos * 8, &p); if (rc) return rc; dr = (int64_t*)p; }
+    if (u->hb) { void* p; rc = stage_get(ctx, 7, ing.n_pos * 8, &p); if (rc) return rc; db = (int64_t*)p; }
+    if (u->pairs) {
+        GraphDev gd; memset(&gd, 0, sizeof gd); gd.k = u->k; gd.hm = make_hm(u->k);
+        BitFilter none; memset(&none, 0, sizeof none);
+        if (u->mode == RB_MODE_FWD) k_pairs<0, 2, 0><<<grid, kThreads, 0, ctx->stream>>>(g, gd, none, u->d, db);
+        else if (u->mode == RB_MODE_RC) k_pairs<1, 2, 0><<<grid, kThreads, 0, ctx->stream>>>(g, gd, none, u->d, db);
+        else k_pairs<2, 2, 0><<<grid, kThreads, 0, ctx->stream>>>(g, gd, none, u->d, db);
+    } else {
+        if (u->mode == RB_MODE_FWD) k_kmerize<0><<<grid, kThreads, 0, ctx->stream>>>(g, u->k, df, dr, db);
+        else if (u->mode == RB_MODE_RC) k_kmerize<1><<<grid, kThreads, 0, ctx->stream>>>(g, u->k, df, dr, db);
+        else k_kmerize<2><<<grid, kThreads, 0, ctx->stream>>>(g, u->k, df, dr, db);
+    }
+    LAUNCH_CHECK();
+    if (u->hf) CK(cudaMemcpyAsync(u->hf + out0, df, (size_t)ing.n_pos * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (u->hr) CK(cudaMemcpyAsync(u->hr + out0, dr, (size_t)ing.n_pos * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (u->hb) CK(cudaMemcpyAsync(u->hb + out0, db, (size_t)ing.n_pos * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RB_OK;
+}
+extern "C" int32_t rb_kmerize(rb_ctx* ctx, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
+                              int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, int32_t k, int32_t mode, int64_t* fhash,
+                              int64_t* rhash, int64_t* base) {
+    if (!ctx || k < 1 || mode < 0 || mode > 2) return RB_EINVAL;
+    LOCK(ctx);
+    ReadsArg ra{packed, mask, read_off, read_len, n_reads, uniform_len, uniform_stride, false};
+    KmerizeUser u{k, mode, 0, nullptr, nullptr, nullptr, fhash, rhash, base, false};
+    return for_each_launch(ctx, ra, k, kmerize_launch, &u, nullptr);
+}
+extern "C" int32_t rb_kmerize_pairs(rb_ctx* ctx, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
+                                    int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, int32_t k, int32_t d, int32_t mode,
+                                    int64_t* pair_base) {
+    if (!ctx || k < 1 || d < 1 || mode < 0 || mode > 2 || !pair_base) return RB_EINVAL;
+    LOCK(ctx);
+    ReadsArg ra{packed, mask, read_off, read_len, n_reads, uniform_len, uniform_stride, false};
+    KmerizeUser u{k, mode, d, nullptr, nullptr, nullptr, nullptr, nullptr, pair_base, true};
+    return for_each_launch(ctx, ra, k + d, kmerize_launch, &u, nullptr);
+}
+
+// ---- graph ---------------------------------------------------------------------------------------------------------------
+extern "C" int32_t rb_graph_create(rb_ctx* ctx, int64_t dbg_bits, int64_t cbf_bytes, int64_t pkbf_bits, int32_t hd, int32_t hc, int32_t hp,
+                                   int32_t k, int32_t stranded, int32_t use_pairs, rb_graph** out) {
+    if (!ctx || !out) return RB_EINVAL;
+    LOCK(ctx);
+    rb_graph* g = new rb_graph();
+    memset(g, 0, sizeof *g);
+    g->ctx = ctx; g->k = k; g->stranded = stranded ? 1 : 0; g->hd = hd; g->hc = hc; g->hp = hp; g->hmax = std::max(hd, hc);
+    g->d_read = -1; g->d_frag = -1;
+    int32_t rc = filter_alloc(ctx, RB_BLOOM, dbg_bits, hd, k, &g->dbg);
+    if (!rc) rc = filter_alloc(ctx, RB_COUNTING, cbf_bytes, hc, k, &g->cbf);
+    if (!rc && use_pairs) rc = filter_alloc(ctx, RB_BLOOM, pkbf_bits, hp, k, &g->rpk);
+    if (rc) {
+        if (g->dbg) filter_free(g->dbg);
+        if (g->cbf) filter_free(g->cbf);
+        if (g->rpk) filter_free(g->rpk);
+        delete g;
+        return rc;
+    }
+    g->dbg->in_graph = g->cbf->in_graph = true;
+    if (g->rpk) g->rpk->in_graph = true;
+    *out = g;
+    return RB_OK;
+}
+extern "C" int32_t rb_graph_destroy(rb_graph* g) {
+    if (!g) return RB_EINVAL;
+    LOCK(g->ctx);
+    if (g->dbg) filter_free(g->dbg);
+    if (g->cbf) filter_free(g->cbf);
+    if (g->rpk) filter_free(g->rpk);
+    if (g->fpk) filter_free(g->fpk);
+    delete g;
+    return RB_OK;
+}
+extern "C" int32_t rb_graph_init_fpkbf(rb_graph* g, int64_t bits, int32_t hp) {  // graph :352-359
+    if (!g) return RB_EINVAL;
+    LOCK(g->ctx);
+    if (g->fpk) return rb_filter_empty(g->fpk);
+    const int32_t rc = filter_alloc(g->ctx, RB_BLOOM, bits, hp, g->k, &g->fpk);
+    if (!rc) g->fpk->in_graph = true;
+    return rc;
+}
+extern "C" int32_t rb_graph_set_distances(rb_graph* g, int32_t d_read, int32_t d_frag) { if (!g) return RB_EINVAL; g->d_read = d_read; g->d_frag = d_frag; return RB_OK; }
+extern "C" int32_t rb_graph_filter(rb_graph* g, int32_t which, rb_filter** out) {
+    if (!g || !out) return RB_EINVAL;
+    *out = which == RB_DBGBF ? g->dbg : which == RB_CBF ? g->cbf : which == RB_RPKBF ? g->rpk : which == RB_FPKBF ? g->fpk : nullptr;
+    return RB_OK;
+}
+extern "C" int32_t rb_graph_clear(rb_graph* g) {
+    if (!g) return RB_EINVAL;
+    LOCK(g->ctx);
+    int32_t rc = rb_filter_empty(g->dbg);
+    if (!rc) rc = rb_filter_empty(g->cbf);
+    if (!rc && g->rpk) rc = rb_filter_empty(g->rpk);
+    if (!rc && g->fpk) rc = rb_filter_empty(g->fpk);
+    return rc;
+}
+static GraphDev graph_view(rb_graph* g) {
+    GraphDev gd;
+    memset(&gd, 0, sizeof gd);
+    gd.k = g->k; gd.hm = make_hm(g->k);
+    gd.rng_seed = g->ctx->rng_seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(g->ctx->launches + 1);  // fresh coins every launch
+    gd.dbg.words = g->dbg->dev; gd.dbg.fm = make_fm(g->dbg->size); gd.dbg.num_hash = g->hd;
+    gd.cbf.words = g->cbf->dev; gd.cbf.fm = make_fm(g->cbf->size); gd.cbf.num_hash = g->hc;
+    return gd;
+}
+static BitFilter bit_view(rb_filter* f) { BitFilter b; b.words = f->dev; b.fm = make_fm(f->size); b.num_hash = f->num_hash; return b; }
+
+template <int MODE, int MAXH>
+static void launch_insert(int policy, int grid, cudaStream_t s, const Ingest& ing, const GraphDev& gd) {
+    if (policy == POLICY_ADD) k_graph_insert<MODE, MAXH, POLICY_ADD><<<grid, kThreads, 0, s>>>(ing, gd);
+    else if (policy == POLICY_COUNT_IF_PRESENT) k_graph_insert<MODE, MAXH, POLICY_COUNT_IF_PRESENT><<<grid, kThreads, 0, s>>>(ing, gd);
+    else k_graph_insert<MODE, MAXH, POLICY_DBG_ONLY><<<grid, kThreads, 0, s>>>(ing, gd);
+}
+template <int MAXH>
+static void launch_insert_mode(int mode, int policy, int grid, cudaStream_t s, const Ingest& ing, const GraphDev& gd) {
+    if (mode == RB_MODE_FWD) launch_insert<0, MAXH>(policy, grid, s, ing, gd);
+    else if (mode == RB_MODE_RC) launch_insert<1, MAXH>(policy, grid, s, ing, gd);
+    else launch_insert<2, MAXH>(policy, grid, s, ing, gd);
+}
+struct InsertUser { rb_graph* g; int mode, policy; };
+static int32_t insert_launch(rb_ctx* ctx, const Ingest& ing, void* user) {
+    InsertUser* u = (InsertUser*)user;
+    GraphDev gd = graph_view(u->g);
+    if (u->policy == POLICY_ADD) { const int32_t rc = claim_reserve(ctx, ing.n_pos, &gd.ct); if (rc) return rc; }
+    const int grid = (int)div_up(div_up(ing.n_pos, kChunk), kThreads);
+    const int maxh = u->g->hmax;
+    if (maxh <= 2) launch_insert_mode<2>(u->mode, u->policy, grid, ctx->stream, ing, gd);
+    else if (maxh <= 3) launch_insert_mode<3>(u->mode, u->policy, grid, ctx->stream, ing, gd);
+    else if (maxh <= 4) launch_insert_mode<4>(u->mode, u->policy, grid, ctx->stream, ing, gd);
+    else launch_insert_mode<8>(u->mode, u->policy, grid, ctx->stream, ing, gd);
+    LAUNCH_CHECK();
+    return RB_OK;
+}
+struct PairUser { rb_graph* g; rb_filter* pk; int mode, d, op; };
+template <int MODE, int MAXH>
+static void launch_pairs_op(int op, int grid, cudaStream_t s, const Ingest& ing, const GraphDev& gd, const BitFilter& pk, int d) {
+    if (op == 1) k_pairs<MODE, MAXH, 1><<<grid, kThreads, 0, s>>>(ing, gd, pk, d, nullptr);
+    else k_pairs<MODE, MAXH, 2><<<grid, kThreads, 0, s>>>(ing, gd, pk, d, nullptr);
+}
+template <int MAXH>
+static void launch_pairs_mode(int mode, int op, int grid, cudaStream_t s, const Ingest& ing, const GraphDev& gd, const BitFilter& pk, int d) {
+    if (mode == RB_MODE_FWD) launch_pairs_op<0, MAXH>(op, grid, s, ing, gd, pk, d);
+    else if (mode == RB_MODE_RC) launch_pairs_op<1, MAXH>(op, grid, s, ing, gd, pk, d);
+    else launch_pairs_op<2, MAXH>(op, grid, s, ing, gd, pk, d);
+}
+static int32_t pairs_launch(rb_ctx* ctx, const Ingest& ing, void* user) {
+    PairUser* u = (PairUser*)user;
+    const GraphDev gd = graph_view(u->g);
+    const BitFilter pk = bit_view(u->pk);
+    const int grid = (int)div_up(div_up(ing.n_pos, kChunk), kThreads);
+    const int maxh = std::max(u->g->hd, u->pk->num_hash);
+    if (maxh <= 2) launch_pairs_mode<2>(u->mode, u->op, grid, ctx->stream, ing, gd, pk, u->d);
+    else if (maxh <= 3) launch_pairs_mode<3>(u->mode, u->op, grid, ctx->stream, ing, gd, pk, u->d);
+    else if (maxh <= 4) launch_pairs_mode<4>(u->mode, u->op, grid, ctx->stream, ing, gd, pk, u->d);
+    else launch_pairs_mode<8>(u->mode, u->op, grid, ctx->stream, ing, gd, pk, u->d);
+    LAUNCH_CHECK();
+    return RB_OK;
+}
+static int graph_mode(const rb_graph* g, uint32_t flags) {  // CanonicalHashFunction.java:179-206 ignores reverse-complement
+    if (!g->stranded) return RB_MODE_CANON;
+    return (flags & RB_REVCOMP) ? RB_MODE_RC : RB_MODE_FWD;
+}
+static int32_t graph_add_reads(rb_graph* g, const ReadsArg& ra, uint32_t flags, int64_t* n_kmers_out) {
+    rb_ctx* ctx = g->ctx;
+    const int mode = graph_mode(g, flags);
+    int64_t total = 0;
+    if (!(flags & RB_PAIRS_EXISTING_ONLY)) {
+        InsertUser u{g, mode, (flags & RB_DBG_ONLY) ? POLICY_DBG_ONLY : (flags & RB_ADD_COUNT_IF_PRESENT) ? POLICY_COUNT_IF_PRESENT : POLICY_ADD};
+        const int32_t rc = for_each_launch(ctx, ra, g->k, insert_launch, &u, &total);
+        if (rc) return rc;
+    }
+    if (flags & (RB_STORE_READ_PAIRS | RB_PAIRS_EXISTING_ONLY)) {
+        if (!g->rpk || g->d_read < 1) return fail(ctx, RB_ESTATE, "read-pair insert needs rpkbf and a read pair distance");
+        PairUser u{g, g->rpk, mode, g->d_read, (flags & RB_PAIRS_EXISTING_ONLY) ? 2 : 1};
+        const int32_t rc = for_each_launch(ctx, ra, g->k + g->d_read, pairs_launch, &u, nullptr);
+        if (rc) return rc;
+    }
+    if (flags & RB_STORE_FRAG_PAIRS) {
+        if (!g->fpk || g->d_frag < 1) return fail(ctx, RB_ESTATE, "fragment-pair insert needs fpkbf and a fragment pair distance");
+        PairUser u{g, g->fpk, mode, g->d_frag, 1};
+        const int32_t rc = for_each_launch(ctx, ra, g->k + g->d_frag, pairs_launch, &u, nullptr);
+        if (rc) return rc;
+    }
+    if (n_kmers_out) *n_kmers_out = total;
+    return RB_OK;
+}
+extern "C" int32_t rb_graph_add_reads(rb_graph* g, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
+                                      int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, uint32_t flags, int64_t* n_kmers_out) {
+    if (!g) return RB_EINVAL;
+    rb_ctx* ctx = g->ctx;
+    LOCK(ctx);
+    ReadsArg ra{packed, mask, read_off, read_len, n_reads, uniform_len, uniform_stride, false};
+    const int32_t rc = graph_add_reads(g, ra, flags, n_kmers_out);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RB_OK;
+}
+extern "C" int32_t rb_graph_add_reads_dev(rb_graph* g, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off,
+                                          const int32_t* read_len, int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, uint32_t flags,
+                                          int64_t* n_kmers_out) {
+    if (!g) return RB_EINVAL;
+    LOCK(g->ctx);
+    ReadsArg ra{packed, mask, read_off, read_len, n_reads, uniform_len, uniform_stride, true};
+    return graph_add_reads(g, ra, flags, n_kmers_out);
+}
+
+extern "C" int32_t rb_graph_add_reads_ascii(rb_graph* g, const char* bases, const char* quals, const int64_t* ascii_off, int64_t n_reads,
+                                            int32_t min_qual, uint32_t flags, int64_t* n_kmers_out) {
+    if (!g || !bases || !ascii_off || n_reads < 0) return RB_EINVAL;
+    rb_ctx* ctx = g->ctx;
+    LOCK(ctx);
+    if (n_kmers_out) *n_kmers_out = 0;
+    if (n_reads == 0) return RB_OK;
+    // per-read word offsets (reads start on 32-base word boundaries) -- host pass over n_reads+1 integers only
+    std::vector<int64_t> word_off((size_t)n_reads + 1), read_off((size_t)n_reads);
+    std::vector<int32_t> read_len((size_t)n_reads);
+    int64_t words = 0;
+    for (int64_t r = 0; r < n_reads; ++r) {
+        const int64_t len = ascii_off[r + 1] - ascii_off[r];
+        if (len < 0 || len > INT32_MAX) return fail(ctx, RB_EINVAL, "ascii_off must be non-decreasing");
+        word_off[(size_t)r] = words; read_off[(size_t)r] = words * 32; read_len[(size_t)r] = (int32_t)len;
+        words += (len + 31) / 32;
+    }
+    word_off[(size_t)n_reads] = words;
+    const int64_t a_lo = ascii_off[0], a_hi = ascii_off[n_reads];
+    char *d_b = nullptr, *d_q = nullptr; int64_t *d_ao = nullptr, *d_wo = nullptr, *d_ro = nullptr; int32_t* d_rl = nullptr;
+    uint64_t* d_packed = nullptr; uint32_t* d_mask = nullptr;
+    auto cleanup = [&]() { cudaFree(d_b); cudaFree(d_q); cudaFree(d_ao); cudaFree(d_wo); cudaFree(d_ro); cudaFree(d_rl); cudaFree(d_packed); cudaFree(d_mask); };
+#define CKF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ctx, RB_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+    CKF(cudaMalloc(&d_b, (size_t)(a_hi - a_lo) + 16));
+    if (quals) CKF(cudaMalloc(&d_q, (size_t)(a_hi - a_lo) + 16));
+    CKF(cudaMalloc(&d_ao, (size_t)(n_reads + 1) * 8));
+    CKF(cudaMalloc(&d_wo, (size_t)(n_reads + 1) * 8));
+    CKF(cudaMalloc(&d_ro, (size_t)n_reads * 8));
+    CKF(cudaMalloc(&d_rl, (size_t)n_reads * 4));
+    CKF(cudaMalloc(&d_packed, (size_t)(words + 2) * 8));
+    CKF(cudaMalloc(&d_mask, (size_t)(words + 2) * 4));
+    CKF(cudaMemcpyAsync(d_b, bases + a_lo, (size_t)(a_hi - a_lo), cudaMemcpyHostToDevice, ctx->stream));
+    if (quals) CKF(cudaMemcpyAsync(d_q, quals + a_lo, (size_t)(a_hi - a_lo), cudaMemcpyHostToDevice, ctx->stream));
+    CKF(cudaMemcpyAsync(d_ao, ascii_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CKF(cudaMemcpyAsync(d_wo, word_off.data(), (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CKF(cudaMemcpyAsync(d_ro, read_off.data(), (size_t)n_reads * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CKF(cudaMemcpyAsync(d_rl, read_len.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (words > 0) {
+        k_pack_ascii<<<(int)div_up(words, kThreads), kThreads, 0, ctx->stream>>>(d_b - a_lo, d_q ? d_q - a_lo : nullptr, d_ao, d_wo, n_reads, words,
+                                                                                 min_qual, d_packed, d_mask);
+        ++ctx->launches;
+        CKF(cudaGetLastError());
+    }
+    ReadsArg ra{d_packed, d_mask, d_ro, d_rl, n_reads, 0, 0, true};
+    int32_t rc = graph_add_reads(g, ra, flags, n_kmers_out);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cleanup();
+    if (!rc && e != cudaSuccess) rc = fail(ctx, RB_ECUDA, cudaGetErrorString(e));
+    return rc;
+#undef CKF
+}
+
+struct CountUser { rb_graph* g; int mode; float* counts; int64_t *fh, *rh; bool on_device; };
+template <int MAXH>
+static void launch_count_mode(int mode, int grid, cudaStream_t s, const Ingest& ing, const GraphDev& gd, float* c, int64_t* f, int64_t* r) {
+    if (mode == RB_MODE_FWD) k_graph_count<0, MAXH><<<grid, kThreads, 0, s>>>(ing, gd, c, f, r);
+    else k_graph_count<2, MAXH><<<grid, kThreads, 0, s>>>(ing, gd, c, f, r);
+}
+static int32_t count_launch(rb_ctx* ctx, const Ingest& ing_in, void* user) {
+    CountUser* u = (CountUser*)user;
+    const GraphDev gd = graph_view(u->g);
+    Ingest ing = ing_in;
+    float* dc = u->counts; int64_t *df = u->fh, *dr = u->rh;
+    const int64_t out0 = ing.out_base;
+    if (!u->on_device) {  // results go through device staging, indexed by launch-local position
+        ing.out_base = 0;
+        int32_t rc; void* p;
+        if (u->counts) { rc = stage_get(ctx, 5, ing.n_pos * 4, &p); if (rc) return rc; dc = (float*)p; }
+        if (u->fh) { rc = stage_get(ctx, 6, ing.n_pos * 8, &p); if (rc) return rc; df = (int64_t*)p; }
+        if (u->rh) { rc = stage_get(ctx, 7, ing.n_pos * 8, &p); if (rc) return rc; dr = (int64_t*)p; }
+    }
+    const int grid = (int)div_up(div_up(ing.n_pos, kChunk), kThreads);
+    const int maxh = u->g->hmax;
+    if (maxh <= 2) launch_count_mode<2>(u->mode, grid, ctx->stream, ing, gd, dc, df, dr);
+    else if (maxh <= 3) launch_count_mode<3>(u->mode, grid, ctx->stream, ing, gd, dc, df, dr);
+    else if (maxh <= 4) launch_count_mode<4>(u->mode, grid, ctx->stream, ing, gd, dc, df, dr);
+    else launch_count_mode<8>(u->mode, grid, ctx->stream, ing, gd, dc, df, dr);
+    LAUNCH_CHECK();
+    if (!u->on_device) {
+        if (u->counts) CK(cudaMemcpyAsync(u->counts + out0, dc, (size_t)ing.n_pos * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (u->fh) CK(cudaMemcpyAsync(u->fh + out0, df, (size_t)ing.n_pos * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (u->rh) CK(cudaMemcpyAsync(u->rh + out0, dr, (size_t)ing.n_pos * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return RB_OK;
+}
+static int32_t graph_count_reads(rb_graph* g, const ReadsArg& ra, float* counts, int64_t* fh, int64_t* rh, int64_t* n_out) {
+    CountUser u{g, g->stranded ? RB_MODE_FWD : RB_MODE_CANON, counts, fh, g->stranded ? nullptr : rh, ra.on_device};
+    return for_each_launch(g->ctx, ra, g->k, count_launch, &u, n_out);
+}
+extern "C" int32_t rb_graph_count_reads(rb_graph* g, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
+                                        int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, float* counts, int64_t* fhash, int64_t* rhash,
+                                        int64_t* n_kmers_out) {
+    if (!g) return RB_EINVAL;
+    rb_ctx* ctx = g->ctx;
+    LOCK(ctx);
+    ReadsArg ra{packed, mask, read_off, read_len, n_reads, uniform_len, uniform_stride, false};
+    const int32_t rc = graph_count_reads(g, ra, counts, fhash, rhash, n_kmers_out);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RB_OK;
+}
+extern "C" int32_t rb_graph_count_reads_dev(rb_graph* g, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off,
+                                            const int32_t* read_len, int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, float* counts,
+                                            int64_t* fhash, int64_t* rhash, int64_t* n_kmers_out) {
+    if (!g) return RB_EINVAL;
+    LOCK(g->ctx);
+    ReadsArg ra{packed, mask, read_off, read_len, n_reads, uniform_len, uniform_stride, true};
+    return graph_count_reads(g, ra, counts, fhash, rhash, n_kmers_out);
+}
+extern "C" int32_t rb_graph_add_hashes(rb_graph* g, const int64_t* base, int64_t n, uint32_t flags) {
+    if (!g) return RB_EINVAL;
+    rb_ctx* ctx = g->ctx;
+    LOCK(ctx);
+    if (flags & RB_DBG_ONLY) return run_hash_op(ctx, OP_BF_ADD, graph_view(g), g->hmax, base, n, nullptr, nullptr);
+    return run_hash_op(ctx, (flags & RB_ADD_COUNT_IF_PRESENT) ? OP_GRAPH_COUNT_IF_PRESENT : OP_GRAPH_ADD, graph_view(g), g->hmax, base, n, nullptr, nullptr);
+}
+extern "C" int32_t rb_graph_count_hashes(rb_graph* g, const int64_t* base, int64_t n, float* counts) {
+    if (!g || !counts) return RB_EINVAL;
+    LOCK(g->ctx);
+    return run_hash_op(g->ctx, OP_GRAPH_COUNT, graph_view(g), g->hmax, base, n, nullptr, counts);
+}
+extern "C" int32_t rb_graph_add_pair_hashes(rb_graph* g, int32_t which, const int64_t* pair_hash, int64_t n) {
+    if (!g) return RB_EINVAL;
+    rb_filter* f = which == RB_RPKBF ? g->rpk : which == RB_FPKBF ? g->fpk : nullptr;
+    if (!f) return fail(g->ctx, RB_ESTATE, "pair filter not initialised");
+    return rb_filter_add_hashes(f, pair_hash, n);
+}
+extern "C" int32_t rb_graph_lookup_pair_hashes(rb_graph* g, int32_t which, const int64_t* pair_hash, int64_t n, uint8_t* out) {
+    if (!g) return RB_EINVAL;
+    rb_filter* f = which == RB_RPKBF ? g->rpk : which == RB_FPKBF ? g->fpk : nullptr;
+    if (!f) return fail(g->ctx, RB_ESTATE, "pair filter not initialised");
+    return rb_filter_lookup_hashes(f, pair_hash, n, out);
+}
+
+// ---- persistence (graph :297-339, file ctor :121-189) -------------------------------------------------------------------------
+extern "C" int32_t rb_graph_save(rb_graph* g, const char* path) {
+    if (!g || !path) return RB_EINVAL;
+    rb_ctx* ctx = g->ctx;
+    LOCK(ctx);
+    const std::string p(path);
+    const std::string desc = "dbgbfCbfMaxNumHash:" + std::to_string(g->hmax) + "\nstranded:" + (g->stranded ? "true" : "false") + "\nk:" +
+                             std::to_string(g->k) + "\nreadPairedKmersDistance:" + std::to_string(g->d_read) +
+                             "\nfragmentPairedKmersDistance:" + std::to_string(g->d_frag) + "\n";
+    int32_t rc = write_file(ctx, path, desc.data(), desc.size());
+    if (!rc) rc = rb_filter_save(g->dbg, (p + ".dbgbf.desc").c_str(), (p + ".dbgbf").c_str());
+    if (!rc) rc = rb_filter_save(g->cbf, (p + ".cbf.desc").c_str(), (p + ".cbf").c_str());
+    if (!rc && g->rpk) rc = rb_filter_save(g->rpk, (p + ".rpkbf.desc").c_str(), (p + ".rpkbf").c_str());
+    if (!rc && g->fpk) rc = rb_filter_save(g->fpk, (p + ".fpkbf.desc").c_str(), (p + ".fpkbf").c_str());
+    return rc;
+}
+static bool file_exists(const std::string& p) { FILE* f = fopen(p.c_str(), "rb"); if (f) fclose(f); return f != nullptr; }
+extern "C" int32_t rb_graph_load(rb_ctx* ctx, const char* path, int32_t load_dbgbf, int32_t load_fpkbf, rb_graph** out) {
+    if (!ctx || !path || !out) return RB_EINVAL;
+    LOCK(ctx);
+    std::vector<std::pair<std::string, std::string>> kv;
+    int32_t rc = read_desc(ctx, path, &kv);
+    if (rc) return rc;
+    rb_graph* g = new rb_graph();
+    memset(g, 0, sizeof *g);
+    g->ctx = ctx; g->d_read = -1; g->d_frag = -1;
+    for (auto& e : kv) {
+        if (e.first == "dbgbfCbfMaxNumHash") g->hmax = atoi(e.second.c_str());
+        else if (e.first == "stranded") g->stranded = e.second == "true";
+        else if (e.first == "k") g->k = atoi(e.second.c_str());
+        else if (e.first == "readPairedKmersDistance") g->d_read = atoi(e.second.c_str());
+        else if (e.first == "fragmentPairedKmersDistance") g->d_frag = atoi(e.second.c_str());
+    }
+    const std::string p(path);
+    rc = rb_filter_load(ctx, RB_BLOOM, (p + ".dbgbf.desc").c_str(), (p + ".dbgbf").c_str(), g->k, load_dbgbf, &g->dbg);
+    if (!rc) rc = rb_filter_load(ctx, RB_COUNTING, (p + ".cbf.desc").c_str(), (p + ".cbf").c_str(), g->k, 1, &g->cbf);
+    if (!rc && file_exists(p + ".rpkbf.desc")) rc = rb_filter_load(ctx, RB_BLOOM, (p + ".rpkbf.desc").c_str(), (p + ".rpkbf").c_str(), g->k, 1, &g->rpk);
+    if (!rc && load_fpkbf && file_exists(p + ".fpkbf.desc"))
+        rc = rb_filter_load(ctx, RB_BLOOM, (p + ".fpkbf.desc").c_str(), (p + ".fpkbf").c_str(), g->k, 1, &g->fpk);
+    if (rc) {
+        if (g->dbg) filter_free(g->dbg);
+        if (g->cbf) filter_free(g->cbf);
+        if (g->rpk) filter_free(g->rpk);
+        if (g->fpk) filter_free(g->fpk);
+        delete g;
+        return rc;
+    }
+    g->hd = g->dbg->num_hash; g->hc = g->cbf->num_hash; g->hp = g->rpk ? g->rpk->num_hash : (g->fpk ? g->fpk->num_hash : 0);
+    g->hmax = std::max(g->hd, g->hc);
+    g->dbg->in_graph = g->cbf->in_graph = true;
+    if (g->rpk) g->rpk->in_graph = true;
+    if (g->fpk) g->fpk->in_graph = true;
+    *out = g;
+    return RB_OK;
+}
+
+// ---- synthetic workload ----------------------------------------------------------------------------------------------------
+extern "C" int32_t rb_synth_reads_dev(rb_ctx* ctx, uint64_t seed, uint64_t genome_len, uint64_t first_read, int64_t n_reads, int32_t L,
+                                      uint32_t err_ppm, int64_t stride_bases, uint64_t* packed_dev) {
+    if (!ctx || !packed_dev || n_reads < 0 || L < 1 || stride_bases < L || (stride_bases & 31) || genome_len < (uint64_t)L) return RB_EINVAL;
+    LOCK(ctx);
+    const int64_t threads = n_reads * (stride_bases >> 5);
+    if (threads == 0) return RB_OK;
+    k_synth_reads<<<(int)div_up(threads, kThreads), kThreads, 0, ctx->stream>>>(seed, genome_len, first_read, n_reads, L, err_ppm, stride_bases, packed_dev);
+    LAUNCH_CHECK();
+    return RB_OK;
+}

@@ -1,0 +1,443 @@
+"""Host-side mirror of the reference's operator surface (same class and method names, argument meaning and error
+behaviour) over the C-ABI.  The Java originals: bloom/BloomFilter.java, bloom/CountingBloomFilter.java,
+graph/BloomFilterDeBruijnGraph.java (relative to /root/reference/src/rnabloom/).  Bulk methods take numpy arrays;
+what was a per-k-mer Java call (`add(long[])`, `getCount(long)`) is the same call on an array of base hashes.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import binding as B
+from .binding import RBError
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One GPU: device memory, stream, claim table (rb_ctx)."""
+
+    def __init__(self, device=0):
+        self.L = B.lib()
+        h = C.c_void_p()
+        rc = self.L.rb_ctx_create(device, C.byref(h))
+        if rc:
+            raise RBError(rc, (self.L.rb_last_error(None) or b"").decode())
+        self.h = h
+        self.device = device
+
+    def check(self, rc):
+        if rc:
+            raise RBError(rc, (self.L.rb_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if self.h:
+            self.L.rb_ctx_destroy(self.h)
+            self.h = None
+
+    def sync(self):
+        self.check(self.L.rb_ctx_sync(self.h))
+
+    def set_stream(self, cuda_stream_ptr):
+        self.check(self.L.rb_ctx_set_stream(self.h, cuda_stream_ptr))
+
+    def set_rng_seed(self, seed):
+        self.check(self.L.rb_ctx_set_rng_seed(self.h, seed))
+
+    def set_subbatch_kmers(self, n):
+        self.check(self.L.rb_ctx_set_subbatch_kmers(self.h, n))
+
+    def kernel_launches(self):
+        return self.L.rb_ctx_kernel_launches(self.h)
+
+    def timer_start(self):
+        self.check(self.L.rb_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self.check(self.L.rb_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def host_alloc(self, nbytes, dtype=np.uint8):
+        """Pinned host memory as a numpy array (kept alive by the returned object)."""
+        p = C.c_void_p()
+        self.check(self.L.rb_host_alloc(C.byref(p), nbytes))
+        buf = (C.c_uint8 * nbytes).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype)
+        self._pinned = getattr(self, "_pinned", []) + [p]
+        return arr
+
+    def dev_alloc(self, nbytes):
+        p = C.c_void_p()
+        self.check(self.L.rb_dev_alloc(self.h, C.byref(p), nbytes))
+        return p.value
+
+    def dev_free(self, p):
+        self.check(self.L.rb_dev_free(self.h, p))
+
+    def h2d(self, dst, arr):
+        arr = np.ascontiguousarray(arr)
+        self.check(self.L.rb_memcpy_h2d(self.h, dst, _ptr(arr), arr.nbytes))
+
+    def d2h(self, arr, src):
+        self.check(self.L.rb_memcpy_d2h(self.h, _ptr(arr), src, arr.nbytes))
+
+    def synth_reads_dev(self, seed, genome_len, first_read, n_reads, L, err_ppm, stride_bases, packed_dev):
+        self.check(self.L.rb_synth_reads_dev(self.h, seed, genome_len, first_read, n_reads, L, err_ppm, stride_bases, packed_dev))
+
+    def index(self, hashes, size):
+        """getIndex for an array of hash values (BloomFilter.java:108-111)."""
+        a = np.ascontiguousarray(hashes, dtype=np.int64)
+        out = np.zeros(a.size, dtype=np.int64)
+        self.check(self.L.rb_index_hashes(self.h, _ptr(a), a.size, size, _ptr(out)))
+        return out
+
+    def kmerize(self, reads, k, mode):
+        """NTHashIterator family over every read: returns (fhash, rhash, base) per k-mer position."""
+        n = reads.n_positions(k)
+        f, r, b = (np.zeros(n, dtype=np.int64) for _ in range(3))
+        self.check(self.L.rb_kmerize(self.h, *reads.args(), k, mode, _ptr(f), _ptr(r), _ptr(b)))
+        return f, r, b
+
+    def kmerize_pairs(self, reads, k, d, mode):
+        p = np.zeros(reads.n_positions(k + d), dtype=np.int64)
+        self.check(self.L.rb_kmerize_pairs(self.h, *reads.args(), k, d, mode, _ptr(p)))
+        return p
+
+
+class PackedReads:
+    """Reads in the ingest layout of include/rnabloom_gpu.h (2-bit codes + optional unusable-base mask)."""
+
+    def __init__(self, packed, mask, read_off, read_len, n_reads, uniform_len=0, uniform_stride=0):
+        self.packed, self.mask, self.read_off, self.read_len = packed, mask, read_off, read_len
+        self.n_reads, self.uniform_len, self.uniform_stride = n_reads, uniform_len, uniform_stride
+
+    def args(self):
+        return (_ptr(self.packed), _ptr(self.mask), _ptr(self.read_off), _ptr(self.read_len), self.n_reads, self.uniform_len,
+                self.uniform_stride)
+
+    def lengths(self):
+        return self.read_len if self.read_len is not None else np.full(self.n_reads, self.uniform_len, dtype=np.int32)
+
+    def n_positions(self, span):
+        return int(np.maximum(self.lengths().astype(np.int64) - span + 1, 0).sum())
+
+    def offsets(self, span):
+        n = np.maximum(self.lengths().astype(np.int64) - span + 1, 0)
+        return np.concatenate([[0], np.cumsum(n)])
+
+
+def pack_reads(seqs, quals=None, min_qual=3, use_mask=True):
+    """ASCII reads (list of str/bytes) -> PackedReads via rb_pack_reads_host."""
+    L = B.lib()
+    bs = [s.encode("latin-1") if isinstance(s, str) else bytes(s) for s in seqs]
+    off = np.zeros(len(bs) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(b) for b in bs])
+    bases = np.frombuffer(b"".join(bs) + b"\0", dtype=np.uint8)
+    q = None
+    if quals is not None:
+        qs = [s.encode("latin-1") if isinstance(s, str) else bytes(s) for s in quals]
+        q = np.frombuffer(b"".join(qs) + b"\0", dtype=np.uint8)
+    words = int(sum((len(b) + 31) // 32 for b in bs)) + 1
+    packed = np.zeros(words, dtype=np.uint64)
+    mask = np.zeros(words, dtype=np.uint32)
+    read_off = np.zeros(len(bs), dtype=np.int64)
+    read_len = np.zeros(len(bs), dtype=np.int32)
+    L.rb_pack_reads_host(_ptr(bases), _ptr(q), _ptr(off), len(bs), min_qual, _ptr(packed), _ptr(mask), _ptr(read_off), _ptr(read_len))
+    return PackedReads(packed, mask if use_mask else None, read_off, read_len, len(bs))
+
+
+def pack_uniform(codes, stride=None):
+    """(n, L) array of 2-bit codes -> uniform-layout PackedReads (stride rounded up to a multiple of 32 bases)."""
+    codes = np.ascontiguousarray(codes, dtype=np.uint64)
+    n, L = codes.shape
+    stride = stride or ((L + 31) // 32) * 32
+    padded = np.zeros((n, stride), dtype=np.uint64)
+    padded[:, :L] = codes
+    sh = (2 * (np.arange(stride) % 32)).astype(np.uint64)
+    words = np.bitwise_or.reduce((padded << sh).reshape(n, stride // 32, 32), axis=2)
+    return PackedReads(np.ascontiguousarray(words.reshape(-1)), None, None, None, n, L, stride)
+
+
+class _Filter:
+    def __init__(self, ctx, handle, owned=True):
+        self.ctx, self.h, self.owned = ctx, handle, owned
+
+    @property
+    def size(self):
+        return self.ctx.L.rb_filter_size(self.h)
+
+    @property
+    def num_bytes(self):
+        return self.ctx.L.rb_filter_num_bytes(self.h)
+
+    def getNumHash(self):
+        return self.ctx.L.rb_filter_num_hash(self.h)
+
+    def getPopCount(self):
+        v = C.c_int64()
+        self.ctx.check(self.ctx.L.rb_filter_popcount(self.h, C.byref(v)))
+        return v.value
+
+    def getFPR(self):
+        v = C.c_float()
+        self.ctx.check(self.ctx.L.rb_filter_fpr(self.h, C.byref(v)))
+        return v.value
+
+    def empty(self):
+        self.ctx.check(self.ctx.L.rb_filter_empty(self.h))
+
+    def destroy(self):
+        if self.h and self.owned:
+            self.ctx.check(self.ctx.L.rb_filter_destroy(self.h))
+        self.h = None
+
+    def download(self):
+        out = np.zeros(self.num_bytes, dtype=np.uint8)
+        self.ctx.check(self.ctx.L.rb_filter_download(self.h, _ptr(out), out.nbytes))
+        return out
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.uint8)
+        self.ctx.check(self.ctx.L.rb_filter_upload(self.h, _ptr(arr), arr.nbytes))
+
+    def save(self, desc_path, bits_path):
+        self.ctx.check(self.ctx.L.rb_filter_save(self.h, str(desc_path).encode(), str(bits_path).encode()))
+
+    def equivalent(self, other):  # BloomFilter.java:253-257
+        return self.size == other.size and self.getNumHash() == other.getNumHash() and bool((self.download() == other.download()).all())
+
+    def device_ptr(self):
+        p = C.c_void_p()
+        self.ctx.check(self.ctx.L.rb_filter_device_ptr(self.h, C.byref(p)))
+        return p.value
+
+
+def _hashes(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+class BloomFilter(_Filter):
+    """bloom/BloomFilter.java"""
+
+    def __init__(self, ctx, size, numHash, k, _handle=None):
+        if _handle is None:
+            h = C.c_void_p()
+            ctx.check(ctx.L.rb_filter_create(ctx.h, B.RB_BLOOM, size, numHash, k, C.byref(h)))
+            super().__init__(ctx, h)
+        else:
+            super().__init__(ctx, _handle, owned=False)
+
+    @classmethod
+    def load(cls, ctx, desc_path, bits_path, k, loadBits=True):
+        h = C.c_void_p()
+        ctx.check(ctx.L.rb_filter_load(ctx.h, B.RB_BLOOM, str(desc_path).encode(), str(bits_path).encode(), k, int(loadBits), C.byref(h)))
+        f = cls(ctx, 0, 0, k, _handle=h)
+        f.owned = True
+        return f
+
+    def add(self, hashVals):
+        a = _hashes(hashVals)
+        self.ctx.check(self.ctx.L.rb_filter_add_hashes(self.h, _ptr(a), a.size))
+
+    def lookup(self, hashVals):
+        a = _hashes(hashVals)
+        out = np.zeros(a.size, dtype=np.uint8)
+        self.ctx.check(self.ctx.L.rb_filter_lookup_hashes(self.h, _ptr(a), a.size, _ptr(out)))
+        return out.astype(bool)
+
+    def lookupThenAdd(self, hashVals):
+        a = _hashes(hashVals)
+        out = np.zeros(a.size, dtype=np.uint8)
+        self.ctx.check(self.ctx.L.rb_filter_lookup_then_add_hashes(self.h, _ptr(a), a.size, _ptr(out)))
+        return out.astype(bool)
+
+    @staticmethod
+    def getExpectedSize(expNumElements, fpr, numHash):
+        return B.lib().rb_expected_size(expNumElements, fpr, numHash)
+
+
+class CountingBloomFilter(_Filter):
+    """bloom/CountingBloomFilter.java"""
+
+    def __init__(self, ctx, size, numHash, k, _handle=None):
+        if _handle is None:
+            h = C.c_void_p()
+            ctx.check(ctx.L.rb_filter_create(ctx.h, B.RB_COUNTING, size, numHash, k, C.byref(h)))
+            super().__init__(ctx, h)
+        else:
+            super().__init__(ctx, _handle, owned=False)
+
+    def increment(self, hashVals):
+        a = _hashes(hashVals)
+        self.ctx.check(self.ctx.L.rb_cbf_increment_hashes(self.h, _ptr(a), a.size))
+
+    def incrementAndGet(self, hashVals):
+        a = _hashes(hashVals)
+        out = np.zeros(a.size, dtype=np.float32)
+        self.ctx.check(self.ctx.L.rb_cbf_increment_and_get_hashes(self.h, _ptr(a), a.size, _ptr(out)))
+        return out
+
+    def getCount(self, hashVals):
+        a = _hashes(hashVals)
+        out = np.zeros(a.size, dtype=np.float32)
+        self.ctx.check(self.ctx.L.rb_cbf_count_hashes(self.h, _ptr(a), a.size, _ptr(out)))
+        return out
+
+    getExpectedSize = BloomFilter.getExpectedSize
+
+
+class BloomFilterDeBruijnGraph:
+    """graph/BloomFilterDeBruijnGraph.java"""
+
+    def __init__(self, ctx, dbgbfNumBits, cbfNumBytes, pkbfNumBits, dbgbfNumHash, cbfNumHash, pkbfNumHash, k, stranded,
+                 useReadPairedKmers, _handle=None):
+        self.ctx = ctx
+        self.k = k
+        self.stranded = bool(stranded)
+        if _handle is None:
+            h = C.c_void_p()
+            ctx.check(ctx.L.rb_graph_create(ctx.h, dbgbfNumBits, cbfNumBytes, pkbfNumBits, dbgbfNumHash, cbfNumHash, pkbfNumHash, k,
+                                            int(stranded), int(useReadPairedKmers), C.byref(h)))
+            self.h = h
+        else:
+            self.h = _handle
+
+    @classmethod
+    def load(cls, ctx, graphFile, loadDbgBits=True, loadFpkbf=True):
+        h = C.c_void_p()
+        ctx.check(ctx.L.rb_graph_load(ctx.h, str(graphFile).encode(), int(loadDbgBits), int(loadFpkbf), C.byref(h)))
+        g = cls(ctx, 0, 0, 0, 0, 0, 0, 0, False, False, _handle=h)
+        with open(graphFile) as fh:
+            for line in fh:
+                key, _, val = line.strip().partition(":")
+                if key == "k":
+                    g.k = int(val)
+                elif key == "stranded":
+                    g.stranded = val == "true"
+        return g
+
+    def destroy(self):
+        if self.h:
+            self.ctx.check(self.ctx.L.rb_graph_destroy(self.h))
+            self.h = None
+
+    def _filter(self, which, cls):
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.L.rb_graph_filter(self.h, which, C.byref(h)))
+        return cls(self.ctx, 0, 0, self.k, _handle=h) if h.value else None
+
+    def getDbgbf(self):
+        return self._filter(B.RB_DBGBF, BloomFilter)
+
+    def getCbf(self):
+        return self._filter(B.RB_CBF, CountingBloomFilter)
+
+    def getRpkbf(self):
+        return self._filter(B.RB_RPKBF, BloomFilter)
+
+    def getFpkbf(self):
+        return self._filter(B.RB_FPKBF, BloomFilter)
+
+    def initializePairKmersBloomFilter(self, pkbfNumBits, pkbfNumHash):
+        self.ctx.check(self.ctx.L.rb_graph_init_fpkbf(self.h, pkbfNumBits, pkbfNumHash))
+
+    def setPairedKmerDistances(self, readPairedKmersDistance, fragmentPairedKmersDistance=-1):
+        self.ctx.check(self.ctx.L.rb_graph_set_distances(self.h, readPairedKmersDistance, fragmentPairedKmersDistance))
+
+    def clear(self):
+        self.ctx.check(self.ctx.L.rb_graph_clear(self.h))
+
+    # ---- bulk insert: the bodies of the *ToGraphWorker classes (RNABloom.java:364-732,1463-1539) ----
+    def addReads(self, reads, flags=0):
+        n = C.c_int64()
+        self.ctx.check(self.ctx.L.rb_graph_add_reads(self.h, *reads.args(), flags, C.byref(n)))
+        return n.value
+
+    def addReadsAscii(self, seqs, quals=None, minQual=3, flags=0):
+        bs = [s.encode("latin-1") if isinstance(s, str) else bytes(s) for s in seqs]
+        off = np.zeros(len(bs) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(b) for b in bs])
+        bases = np.frombuffer(b"".join(bs) + b"\0", dtype=np.uint8)
+        q = None
+        if quals is not None:
+            q = np.frombuffer(b"".join(s.encode("latin-1") if isinstance(s, str) else bytes(s) for s in quals) + b"\0", dtype=np.uint8)
+        n = C.c_int64()
+        self.ctx.check(self.ctx.L.rb_graph_add_reads_ascii(self.h, _ptr(bases), _ptr(q), _ptr(off), len(bs), minQual, flags, C.byref(n)))
+        return n.value
+
+    def addReadsDev(self, packed_dev, n_reads, uniform_len, uniform_stride, flags=0):
+        n = C.c_int64()
+        self.ctx.check(self.ctx.L.rb_graph_add_reads_dev(self.h, packed_dev, None, None, None, n_reads, uniform_len, uniform_stride, flags,
+                                                         C.byref(n)))
+        return n.value
+
+    # ---- bulk lookup: graph.getKmers (graph :1224-1226) ----
+    def getKmers(self, reads, want_hashes=True):
+        n = reads.n_positions(self.k)
+        counts = np.zeros(n, dtype=np.float32)
+        fh = np.zeros(n, dtype=np.int64) if want_hashes else None
+        rh = np.zeros(n, dtype=np.int64) if (want_hashes and not self.stranded) else None
+        got = C.c_int64()
+        self.ctx.check(self.ctx.L.rb_graph_count_reads(self.h, *reads.args(), _ptr(counts), _ptr(fh), _ptr(rh), C.byref(got)))
+        assert got.value == n
+        return counts, fh, rh
+
+    def getKmersDev(self, packed_dev, n_reads, uniform_len, uniform_stride, counts_dev, fhash_dev=None, rhash_dev=None):
+        n = C.c_int64()
+        self.ctx.check(self.ctx.L.rb_graph_count_reads_dev(self.h, packed_dev, None, None, None, n_reads, uniform_len, uniform_stride,
+                                                           counts_dev, fhash_dev, rhash_dev, C.byref(n)))
+        return n.value
+
+    # ---- per-hash forms ----
+    def add(self, hashVals, flags=0):
+        a = _hashes(hashVals)
+        self.ctx.check(self.ctx.L.rb_graph_add_hashes(self.h, _ptr(a), a.size, flags))
+
+    def addCountIfPresent(self, hashVals):
+        self.add(hashVals, B.ADD_COUNT_IF_PRESENT)
+
+    def addDbgOnly(self, hashVals):
+        self.add(hashVals, B.DBG_ONLY)
+
+    def getCount(self, hashVals):
+        a = _hashes(hashVals)
+        out = np.zeros(a.size, dtype=np.float32)
+        self.ctx.check(self.ctx.L.rb_graph_count_hashes(self.h, _ptr(a), a.size, _ptr(out)))
+        return out
+
+    def contains(self, hashVals):
+        return self.getDbgbf().lookup(hashVals)
+
+    def addReadSingleKmerPair(self, pairHashVals):
+        a = _hashes(pairHashVals)
+        self.ctx.check(self.ctx.L.rb_graph_add_pair_hashes(self.h, B.RB_RPKBF, _ptr(a), a.size))
+
+    def addFragmentSingleKmerPair(self, pairHashVals):
+        a = _hashes(pairHashVals)
+        self.ctx.check(self.ctx.L.rb_graph_add_pair_hashes(self.h, B.RB_FPKBF, _ptr(a), a.size))
+
+    def lookupReadKmerPair(self, pairHashVals):
+        a = _hashes(pairHashVals)
+        out = np.zeros(a.size, dtype=np.uint8)
+        self.ctx.check(self.ctx.L.rb_graph_lookup_pair_hashes(self.h, B.RB_RPKBF, _ptr(a), a.size, _ptr(out)))
+        return out.astype(bool)
+
+    def lookupFragmentKmerPair(self, pairHashVals):
+        a = _hashes(pairHashVals)
+        out = np.zeros(a.size, dtype=np.uint8)
+        self.ctx.check(self.ctx.L.rb_graph_lookup_pair_hashes(self.h, B.RB_FPKBF, _ptr(a), a.size, _ptr(out)))
+        return out.astype(bool)
+
+    def getDbgbfFPR(self):
+        return self.getDbgbf().getFPR()
+
+    def getCbfFPR(self):
+        return self.getCbf().getFPR()
+
+    def getFPR(self):  # graph :588-590
+        return self.getDbgbfFPR() * self.getCbfFPR()
+
+    def save(self, graphFile):
+        self.ctx.check(self.ctx.L.rb_graph_save(self.h, str(graphFile).encode()))

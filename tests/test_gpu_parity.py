@@ -1,0 +1,539 @@
+"""Parity of the CUDA path (through the C-ABI) with the CPU oracle -- run on the B200 box with `-m gpu`.
+
+Contract: P1 hashes exact, P2 indices exact, P3 add-only filters exact for any order,
+P4 counting filter exact on collision-free fixtures / duplicates linearised / envelope on loaded filters,
+P5 multiplicities kept <= 17 so MiniFloat stays deterministic.  Bit-exact comparisons throughout (integer path).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import rnabloom_b200 as rb
+from oracle import pyref as P
+from oracle.binding import (F_ADD_COUNT_IF_PRESENT, F_DBG_ONLY, F_REVCOMP, F_STORE_FRAG_PAIRS, F_STORE_READ_PAIRS, MODE_CANON,
+                            MODE_FWD, MODE_RC, OracleGraph)
+
+pytestmark = pytest.mark.gpu
+hx = lambda s: int(s, 16)  # noqa: E731
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = rb.Context(0)
+    yield c
+    c.close()
+
+
+def rand_reads(rng, n, lo, hi, n_rate=0.0, alphabet="ACGT"):
+    out = []
+    for _ in range(n):
+        L = int(rng.integers(lo, hi + 1))
+        s = rng.choice(list(alphabet), size=L)
+        if n_rate:
+            s[rng.random(L) < n_rate] = "N"
+        out.append("".join(s))
+    return out
+
+
+def oracle_kmerize(orc, seqs, k, mode):
+    f, r, b = [], [], []
+    for s in seqs:
+        a, c, d = orc.kmer_hashes(s, k, mode)
+        f.append(a), r.append(c), b.append(d)
+    return np.concatenate(f), np.concatenate(r), np.concatenate(b)
+
+
+# ---- P1: hashes --------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [17, 25, 35, 64, 65, 100])
+def test_kmerize_matches_oracle(ctx, orc, k):
+    rng = np.random.default_rng(k)
+    seqs = rand_reads(rng, 300, 1, 400, alphabet="ACGTacgtU") + ["A" * k, "ACGT" * 50, "G" * (k - 1), ""]
+    pr = rb.pack_reads(seqs)
+    for mode in (MODE_FWD, MODE_RC, MODE_CANON):
+        f, r, b = ctx.kmerize(pr, k, mode)
+        of, orr, ob = oracle_kmerize(orc, seqs, k, mode)
+        if mode != MODE_RC:
+            assert (f == of).all()
+        if mode != MODE_FWD:
+            assert (r == orr).all()
+        assert (b == ob).all()
+
+
+def test_kmerize_masked_bases_hash_as_N(ctx, orc):
+    rng = np.random.default_rng(5)
+    seqs = rand_reads(rng, 200, 30, 300, n_rate=0.03)
+    pr = rb.pack_reads(seqs)
+    f, r, b = ctx.kmerize(pr, 25, MODE_CANON)
+    of, orr, ob = oracle_kmerize(orc, seqs, 25, MODE_CANON)
+    assert (f == of).all() and (r == orr).all() and (b == ob).all()
+
+
+def test_kmerize_golden(ctx, kat):
+    for e in kat["hashes"][::3]:
+        pr = rb.pack_reads([e["seq"]])
+        f, r, b = ctx.kmerize(pr, e["k"], MODE_CANON)
+        U = lambda a: [int(x) & P.M64 for x in a]  # noqa: E731
+        assert U(f) == [hx(x) for x in e["f"]] and U(r) == [hx(x) for x in e["r"]] and U(b) == [hx(x) for x in e["canon"]]
+
+
+def test_kmerize_uniform_layout_and_many_launches(ctx, orc):
+    reads = orc.synth_reads(3, 50000, 0, 3000, 150, 10000)
+    code = np.zeros(256, dtype=np.uint8)
+    code[list(b"ACGT")] = [0, 1, 2, 3]
+    pr = rb.pack_uniform(code[reads], stride=160)
+    ctx.set_subbatch_kmers(50000)  # forces several launches
+    try:
+        f, r, b = ctx.kmerize(pr, 25, MODE_CANON)
+    finally:
+        ctx.set_subbatch_kmers(1 << 25)
+    of, orr, ob = oracle_kmerize(orc, [bytes(x) for x in reads], 25, MODE_CANON)
+    assert (f == of).all() and (r == orr).all() and (b == ob).all()
+
+
+@pytest.mark.parametrize("k,d", [(25, 10), (35, 105), (17, 1), (25, 200)])
+def test_pair_hashes_match_oracle(ctx, orc, k, d):
+    rng = np.random.default_rng(k * 1000 + d)
+    seqs = rand_reads(rng, 200, 1, 420)
+    pr = rb.pack_reads(seqs)
+    for mode in (MODE_FWD, MODE_RC, MODE_CANON):
+        p = ctx.kmerize_pairs(pr, k, d, mode)
+        want = np.concatenate([orc.pair_hashes(s, k, d, mode)[2] for s in seqs])
+        assert (p == want).all()
+
+
+def test_pair_hashes_golden(ctx, kat):
+    for e in kat["pairs"]:
+        p = ctx.kmerize_pairs(rb.pack_reads([e["seq"]]), e["k"], e["d"], e["mode"])
+        assert [int(x) & P.M64 for x in p] == [hx(x) for x in e["p"]]
+
+
+# ---- P2: indices ---------------------------------------------------------------------------------------------------------
+def test_index_matches_oracle_for_arbitrary_sizes(ctx, orc, kat):
+    rng = np.random.default_rng(1)
+    sizes = [1, 2, 3, 5, 1021, 2 ** 33, 2 ** 36, 8589934583, 68719476735, 2 ** 62 + 57, 2 ** 63 - 1, 2 ** 63 - 25, 10 ** 12 + 39]
+    sizes += [int(x) for x in rng.integers(1, 2 ** 62, size=40)]
+    for size in sizes:
+        h = rng.integers(-2 ** 63, 2 ** 63 - 1, size=4000, dtype=np.int64)
+        edge = np.array([0, 1, -1, -2 ** 63, 2 ** 63 - 1, (size << 1) & (2 ** 63 - 1), ((size << 1) - 1) & (2 ** 63 - 1)], dtype=np.int64)
+        h = np.concatenate([h, edge])
+        got = ctx.index(h, size)
+        want = (h.view(np.uint64) >> np.uint64(1)) % np.uint64(size)
+        assert (got.view(np.uint64) == want).all(), size
+    for e in kat["index"]:
+        assert ctx.index([P.signed(hx(e["h"]))], e["size"])[0] == e["idx"]
+
+
+# ---- graph.add / getKmers --------------------------------------------------------------------------------------------------
+def make_graphs(ctx, orc, dbg_bits, cbf_bytes, pk_bits, hd, hc, hp, k, stranded, pairs):
+    return (rb.BloomFilterDeBruijnGraph(ctx, dbg_bits, cbf_bytes, pk_bits, hd, hc, hp, k, stranded, pairs),
+            OracleGraph(orc, dbg_bits, cbf_bytes, pk_bits, hd, hc, hp, k, stranded, pairs))
+
+
+def assert_same_state(g, og, pairs=False, frag=False):
+    assert (g.getDbgbf().download() == og.dbgbf()).all(), "dbgbf differs"
+    assert (g.getCbf().download() == og.cbf()).all(), "cbf differs"
+    if pairs:
+        assert (g.getRpkbf().download() == og.rpkbf()).all(), "rpkbf differs"
+    if frag:
+        assert (g.getFpkbf().download() == og.fpkbf()).all(), "fpkbf differs"
+
+
+def test_graph_golden_vectors(ctx, orc, kat):
+    """The frozen small graphs: sequential add order, heavy slot sharing -> only one read per call keeps the order."""
+    for e in kat["graphs"]:
+        g = rb.BloomFilterDeBruijnGraph(ctx, e["dbg_bits"], e["cbf_bytes"], 64, e["hd"], e["hc"], 1, e["k"], e["stranded"], False)
+        for i, r in enumerate(e["reads"]):
+            # one k-mer per call keeps the reference's sequential order on these tiny, collision-heavy filters
+            pr = rb.pack_reads([r])
+            mode = MODE_CANON if not e["stranded"] else (MODE_RC if i % 2 else MODE_FWD)
+            _, _, base = ctx.kmerize(pr, e["k"], mode)
+            for b in base:
+                g.add([b])
+        assert bytes(g.getDbgbf().download()).hex() == e["dbgbf"]
+        assert bytes(g.getCbf().download()).hex() == e["cbf"]
+        counts, _, _ = g.getKmers(rb.pack_reads([e["query"]]))
+        assert counts.tolist() == e["counts"]
+        g.destroy()
+
+
+def np_slots(base, k, h, size):
+    """numpy restatement of NTM64 + getIndex for many base hashes: (n, h) slot indices."""
+    base = np.asarray(base, dtype=np.int64).view(np.uint64)
+    ks = np.uint64((k * P.MULTI_SEED) & P.M64)
+    cols = [base >> np.uint64(1)]
+    for i in range(1, h):
+        t = base * (np.uint64(i) ^ ks)
+        t ^= t >> np.uint64(27)
+        cols.append(t >> np.uint64(1))
+    return np.stack(cols, axis=1) % np.uint64(size)
+
+
+@pytest.mark.parametrize("n_reads", [120, 800])
+@pytest.mark.parametrize("stranded,k,hd,hc", [(False, 25, 3, 3), (True, 25, 3, 3), (False, 35, 2, 2), (False, 17, 3, 2), (True, 64, 1, 4),
+                                              (False, 100, 5, 3)])
+def test_graph_add_collision_free_is_bit_exact(ctx, orc, stranded, k, hd, hc, n_reads):
+    """P3 + P4(ii): dbgbf byte-identical always; cbf byte-identical to the sequential oracle wherever no two distinct k-mers
+    share a counter (which k-mers share one is computed from the fixture itself, so nothing is waved through)."""
+    reads = orc.synth_reads(k, 30000 * n_reads // 800 + 500, 0, n_reads, 150, 8000)  # ~4x coverage: multiplicities < 17
+    seqs = [bytes(r) for r in reads]
+    dbg_bits, cbf_bytes = (1 << 31) - 1, (1 << 29) + 7     # non power-of-two on purpose
+    g, og = make_graphs(ctx, orc, dbg_bits, cbf_bytes, 64, hd, hc, 1, k, stranded, False)
+    for i, s in enumerate(seqs):
+        og.add_read(s, flags=F_REVCOMP if (stranded and i % 2) else 0)
+    assert og.cbf().max() <= 16, "fixture reached the probabilistic MiniFloat range"
+    pr_fwd = rb.pack_reads(seqs[0::2]) if stranded else rb.pack_reads(seqs)
+    n = g.addReads(pr_fwd)
+    if stranded:
+        n += g.addReads(rb.pack_reads(seqs[1::2]), flags=rb.REVCOMP)
+    assert n == len(seqs) * (150 - k + 1)
+    assert (g.getDbgbf().download() == og.dbgbf()).all(), "dbgbf differs"
+    # which counters are shared between distinct k-mers in this fixture?
+    bases = []
+    for i, s in enumerate(seqs):
+        mode = MODE_CANON if not stranded else (MODE_RC if i % 2 else MODE_FWD)
+        bases.append(orc.kmer_hashes(s, k, mode)[2])
+    distinct = np.unique(np.concatenate(bases))
+    slots = np_slots(distinct, k, hc, cbf_bytes)
+    uniq, cnt = np.unique(slots.reshape(-1), return_counts=True)
+    shared = set(uniq[cnt > 1].tolist())
+    touched = np.array([any(int(x) in shared for x in row) for row in slots]) if shared else np.zeros(len(slots), bool)
+    assert touched.mean() < 0.01
+    may_differ = set(int(x) for row in slots[touched] for x in row)
+    diff = np.nonzero(g.getCbf().download() != og.cbf())[0]
+    assert set(diff.tolist()) <= may_differ, "cbf differs on counters no other k-mer shares"
+    if n_reads == 120:
+        assert not shared or len(diff) <= len(may_differ)
+    # lookups: counts and hashes for every k-mer of every read
+    pr = rb.pack_reads(seqs[:100])
+    counts, fh, rh = g.getKmers(pr)
+    off = 0
+    for s in seqs[:100]:
+        c, f, r = og.count_seq(s)
+        m = len(c)
+        assert (fh[off:off + m] == f).all()
+        if not stranded:
+            assert (rh[off:off + m] == r).all()
+        if not len(diff):
+            assert (counts[off:off + m] == c).all()
+        off += m
+    assert g.getDbgbf().getPopCount() == int(np.unpackbits(og.dbgbf()).sum())
+    assert g.getCbf().getPopCount() == int((og.cbf() != 0).sum())
+    g.destroy(), og.close()
+
+
+def test_duplicates_inside_one_batch_are_linearised(ctx, orc):
+    """P4(i): m copies of a read in ONE call -> every k-mer ends with exactly m-1 increments (count m)."""
+    rng = np.random.default_rng(17)
+    base_reads = rand_reads(rng, 20, 150, 150)
+    for m in (2, 5, 16):
+        seqs = base_reads * m
+        g, og = make_graphs(ctx, orc, 1 << 30, 1 << 30, 64, 3, 3, 1, 25, False, False)
+        for s in seqs:
+            og.add_read(s)
+        g.addReads(rb.pack_reads(seqs))
+        assert_same_state(g, og)
+        counts, _, _ = g.getKmers(rb.pack_reads(base_reads))
+        assert (counts == float(m)).all()
+        g.destroy(), og.close()
+    # the same through the per-hash operator, heavy duplication of few keys
+    keys = rng.integers(-2 ** 63, 2 ** 63 - 1, size=50, dtype=np.int64)
+    many = np.repeat(keys, 12)
+    rng.shuffle(many)
+    g = rb.BloomFilterDeBruijnGraph(ctx, 1 << 30, 1 << 28, 64, 3, 3, 1, 25, False, False)
+    g.add(many)
+    assert (g.getCount(keys) == 12.0).all()
+    bf = rb.BloomFilter(ctx, 1 << 30, 3, 25)
+    found = bf.lookupThenAdd(many)
+    assert int((~found).sum()) == len(keys)  # exactly one "absent" per distinct key
+    assert bf.lookupThenAdd(many).all()
+    g.destroy(), bf.destroy()
+
+
+def test_loaded_filter_dbgbf_exact_cbf_within_envelope(ctx, orc):
+    """P3 + P4(iii): small filters with real false positives.  dbgbf stays exact; cbf must sit inside the envelope
+    spanned by the sequential oracle over permutations of the same reads (the reference itself is order dependent)."""
+    reads = orc.synth_reads(9, 20000, 0, 700, 150, 5000)
+    seqs = [bytes(r) for r in reads]
+    dbg_bits, cbf_bytes = 600_011, 150_001
+    g = rb.BloomFilterDeBruijnGraph(ctx, dbg_bits, cbf_bytes, 64, 3, 3, 1, 25, False, False)
+    g.addReads(rb.pack_reads(seqs))
+    got_cbf = g.getCbf().download().astype(np.int16)
+    rng = np.random.default_rng(0)
+    lo, hi = None, None
+    for p in range(4):
+        og = OracleGraph(orc, dbg_bits, cbf_bytes, 64, 3, 3, 1, 25, False, False)
+        order = np.arange(len(seqs)) if p == 0 else rng.permutation(len(seqs))
+        for i in order:
+            og.add_read(seqs[i])
+        if p == 0:
+            assert (g.getDbgbf().download() == og.dbgbf()).all()
+        c = og.cbf().astype(np.int16)
+        lo = c if lo is None else np.minimum(lo, c)
+        hi = c if hi is None else np.maximum(hi, c)
+        og.close()
+    outside = ((got_cbf < lo - 1) | (got_cbf > hi + 1)).mean()
+    assert outside < 0.01, outside
+    assert abs(int(got_cbf.sum()) - int(((lo + hi) // 2).sum())) < 0.02 * int(hi.sum())
+    g.destroy()
+
+
+def test_insert_policies_and_pair_filters(ctx, orc):
+    rng = np.random.default_rng(23)
+    seqs = rand_reads(rng, 300, 20, 400, n_rate=0.004)
+    for stranded in (False, True):
+        k, d_read, d_frag = 25, 10, 60
+        g, og = make_graphs(ctx, orc, (1 << 30) + 1, (1 << 28) + 5, (1 << 27) + 3, 3, 3, 2, k, stranded, True)
+        g.initializePairKmersBloomFilter((1 << 26) + 9, 2), og.init_fpkbf((1 << 26) + 9, 2)
+        g.setPairedKmerDistances(d_read, d_frag), og.set_distances(d_read, d_frag)
+        pr = rb.pack_reads(seqs)
+        fl = F_STORE_READ_PAIRS | F_STORE_FRAG_PAIRS
+        for s in seqs:
+            og.add_read(s, flags=fl)
+        g.addReads(pr, flags=rb.STORE_READ_PAIRS | rb.STORE_FRAG_PAIRS)
+        assert_same_state(g, og, True, True)
+        for s in seqs[:100]:
+            og.add_read(s, flags=F_REVCOMP)
+        g.addReads(rb.pack_reads(seqs[:100]), flags=rb.REVCOMP)
+        assert_same_state(g, og, True, True)
+        for s in seqs[50:200]:
+            og.add_read(s, flags=F_ADD_COUNT_IF_PRESENT)
+        g.addReads(rb.pack_reads(seqs[50:200]), flags=rb.ADD_COUNT_IF_PRESENT)
+        assert_same_state(g, og, True, True)
+        more = rand_reads(rng, 100, 100, 200)
+        for s in more:
+            og.add_read(s, flags=F_DBG_ONLY | F_STORE_READ_PAIRS | F_REVCOMP)
+        g.addReads(rb.pack_reads(more), flags=rb.DBG_ONLY | rb.STORE_READ_PAIRS | rb.REVCOMP)
+        assert_same_state(g, og, True, True)
+        # pair lookups against the frozen filters
+        mode = MODE_FWD if stranded else MODE_CANON
+        _, _, ph = orc.pair_hashes(seqs[7], k, d_read, mode) if len(seqs[7]) >= k + d_read else (None, None, np.zeros(0, np.int64))
+        if len(ph) and "N" not in seqs[7]:
+            assert g.lookupReadKmerPair(ph).all()
+        junk = rng.integers(-2 ** 63, 2 ** 63 - 1, size=2000, dtype=np.int64)
+        want = np.array([orc.lib.orc_bf_lookup1(orc.lib.orc_graph_rpkbf(og.g), int(x)) for x in junk], dtype=bool)
+        assert (g.lookupReadKmerPair(junk) == want).all()
+        g.destroy(), og.close()
+
+
+def test_pairs_existing_only(ctx, orc):
+    rng = np.random.default_rng(29)
+    seqs = rand_reads(rng, 100, 150, 150)
+    k, d = 25, 10
+    g, og = make_graphs(ctx, orc, 1 << 30, 1 << 28, 1 << 27, 3, 3, 3, k, False, True)
+    g.setPairedKmerDistances(d), og.set_distances(d, -1)
+    for s in seqs[:50]:
+        og.add_read(s)
+    g.addReads(rb.pack_reads(seqs[:50]))
+    # FastaPairedKmersToGraphWorker with existingKmersOnly (RNABloom.java:389-399)
+    rp = orc.lib.orc_graph_rpkbf(og.g)
+    for s in seqs:
+        L, R, Pp = orc.pair_hashes(s, k, d, MODE_CANON)
+        for l, r, p in zip(L, R, Pp):
+            if orc.lib.orc_bf_lookup1(orc.lib.orc_graph_dbgbf(og.g), int(l)) and orc.lib.orc_bf_lookup1(orc.lib.orc_graph_dbgbf(og.g), int(r)):
+                orc.lib.orc_bf_add1(rp, int(p))
+    g.addReads(rb.pack_reads(seqs), flags=rb.PAIRS_EXISTING_ONLY)
+    assert_same_state(g, og, True)
+    g.destroy(), og.close()
+
+
+def test_fastq_ascii_ingest_matches_regex_segmentation(ctx, orc, kat):
+    rng = np.random.default_rng(31)
+    seqs, quals = [], []
+    for e in kat["segments"]:
+        seqs.append(e["seq"]), quals.append(e["qual"])
+    for _ in range(300):
+        L = int(rng.integers(10, 260))
+        s = rng.choice(list("ACGT"), size=L)
+        s[rng.random(L) < 0.01] = "N"
+        q = rng.integers(35, 74, size=L)
+        q[rng.random(L) < 0.03] = 33 + rng.integers(0, 3)
+        seqs.append("".join(s)), quals.append("".join(chr(x) for x in q))
+    for min_qual in (0, 3, 20):
+        g, og = make_graphs(ctx, orc, (1 << 28) + 1, (1 << 26) + 1, 64, 3, 3, 1, 25, False, False)
+        n_want = sum(og.add_read(s, q, min_qual) for s, q in zip(seqs, quals))
+        n = g.addReadsAscii(seqs, quals, min_qual)
+        assert_same_state(g, og)
+        g.clear()
+        n2 = g.addReads(rb.pack_reads(seqs, quals, min_qual))   # host packing path gives the same filters
+        assert n == n2
+        assert_same_state(g, og)
+        # k-mer instances processed include masked windows; usable ones equal the oracle's count
+        assert n_want <= n
+        g.destroy(), og.close()
+    # FASTA path (no qualities)
+    g, og = make_graphs(ctx, orc, (1 << 28) + 1, (1 << 26) + 1, 64, 3, 3, 1, 25, False, False)
+    for s in seqs:
+        og.add_read(s)
+    g.addReadsAscii(seqs)
+    assert_same_state(g, og)
+    g.destroy(), og.close()
+
+
+def test_getkmers_with_invalid_nucleotides(ctx, orc):
+    rng = np.random.default_rng(37)
+    seqs = rand_reads(rng, 120, 10, 300, n_rate=0.01)
+    g, og = make_graphs(ctx, orc, 1 << 28, 1 << 26, 64, 3, 3, 1, 25, False, False)
+    for s in seqs:
+        og.add_read(s)
+    g.addReads(rb.pack_reads(seqs))
+    counts, fh, rh = g.getKmers(rb.pack_reads(seqs))
+    off = 0
+    for s in seqs:
+        c, f, r = og.count_seq(s)
+        m = len(c)
+        assert (counts[off:off + m] == c).all() and (fh[off:off + m] == f).all() and (rh[off:off + m] == r).all()
+        off += m
+    assert off == len(counts)
+    g.destroy(), og.close()
+
+
+def test_subbatching_and_claim_table_recycling_do_not_change_results(ctx, orc):
+    reads = orc.synth_reads(41, 15000, 0, 1000, 150, 5000)
+    seqs = [bytes(r) for r in reads]
+    g, og = make_graphs(ctx, orc, (1 << 30) - 3, (1 << 28) - 1, 64, 3, 3, 1, 25, False, False)
+    for s in seqs:
+        og.add_read(s)
+    ctx.set_subbatch_kmers(4096)  # ~30 launches, the claim table is cleared many times
+    try:
+        g.addReads(rb.pack_reads(seqs))
+        assert_same_state(g, og)
+        counts, _, _ = g.getKmers(rb.pack_reads(seqs[:50]))
+    finally:
+        ctx.set_subbatch_kmers(1 << 25)
+    c0 = np.concatenate([og.count_seq(s)[0] for s in seqs[:50]])
+    assert (counts == c0).all()
+    g.destroy(), og.close()
+
+
+# ---- per-hash operators ---------------------------------------------------------------------------------------------------
+def test_filter_hash_operators(ctx, orc):
+    rng = np.random.default_rng(43)
+    lib = orc.lib
+    for size, h, k in ((1 << 20, 3, 25), (999_983, 2, 35), (77, 4, 17), (1, 1, 25)):
+        keys = rng.integers(-2 ** 63, 2 ** 63 - 1, size=3000, dtype=np.int64)
+        bf, obf = rb.BloomFilter(ctx, size, h, k), lib.orc_bf_create(size, h, k)
+        bf.add(keys[:1500])
+        for x in keys[:1500]:
+            lib.orc_bf_add1(obf, int(x))
+        assert (bf.download() == orc.bf_array(obf)).all()
+        want = np.array([lib.orc_bf_lookup1(obf, int(x)) for x in keys], dtype=bool)
+        assert (bf.lookup(keys) == want).all()
+        assert bf.getPopCount() == lib.orc_bf_popcount(obf)
+        assert bf.getFPR() == lib.orc_bf_fpr(obf)
+        bf.destroy(), lib.orc_bf_destroy(obf)
+    # counting filter: distinct keys on a sparse filter -> exact, incl. multiplicities through repeated calls
+    keys = rng.integers(-2 ** 63, 2 ** 63 - 1, size=2000, dtype=np.int64)
+    cbf, ocbf = rb.CountingBloomFilter(ctx, (1 << 28) + 3, 3, 25), lib.orc_cbf_create((1 << 28) + 3, 3, 25)
+    mult = rng.integers(1, 16, size=len(keys))
+    rep = np.repeat(keys, mult)
+    rng.shuffle(rep)
+    cbf.increment(rep)
+    for x in rep:
+        lib.orc_cbf_increment1(ocbf, int(x))
+    assert (cbf.download() == orc.cbf_array(ocbf)).all()
+    assert (cbf.getCount(keys) == mult.astype(np.float32)).all()
+    got = cbf.incrementAndGet(keys[:100])
+    assert (got == (mult[:100] + 1).astype(np.float32)).all()
+    assert cbf.getPopCount() == lib.orc_cbf_popcount(ocbf)
+    cbf.destroy(), lib.orc_cbf_destroy(ocbf)
+
+
+def test_minifloat_probabilistic_range_is_statistically_right(ctx):
+    """P5: above byte value 16 the reference flips Math.random() coins; compare the distribution, not the bytes."""
+    cbf = rb.CountingBloomFilter(ctx, 1 << 26, 1, 25)
+    rng = np.random.default_rng(47)
+    keys = rng.integers(-2 ** 63, 2 ** 63 - 1, size=4000, dtype=np.int64)
+    for _ in range(40):
+        cbf.increment(keys)
+    c = cbf.getCount(keys)
+    # 40 increments: 16 deterministic, then 24 at p=1/2 -> byte 16 + Binomial-ish; E[float] ~= 40 (the counter is unbiased)
+    assert 16 < c.min() and c.max() <= 160
+    assert abs(c.mean() - 40.0) < 1.0
+    cbf.destroy()
+
+
+def test_upload_download_save_load_roundtrip(ctx, orc, tmp_path):
+    reads = orc.synth_reads(51, 10000, 0, 300, 150, 3000)
+    seqs = [bytes(r) for r in reads]
+    g, og = make_graphs(ctx, orc, (1 << 24) + 5, (1 << 22) + 1, (1 << 20) + 7, 3, 2, 2, 25, True, True)
+    g.setPairedKmerDistances(10, 30), og.set_distances(10, 30)
+    g.initializePairKmersBloomFilter(1 << 20, 2), og.init_fpkbf(1 << 20, 2)
+    for s in seqs:
+        og.add_read(s, flags=F_STORE_READ_PAIRS | F_STORE_FRAG_PAIRS)
+    g.addReads(rb.pack_reads(seqs), flags=rb.STORE_READ_PAIRS | rb.STORE_FRAG_PAIRS)
+    path = tmp_path / "rnabloom.graph"
+    g.save(path)
+    # raw dumps are the byte arrays themselves (UnsafeByteBuffer.write :160-183); desc grammar BloomFilter.java:113-124
+    assert (np.fromfile(str(path) + ".dbgbf", dtype=np.uint8) == og.dbgbf()).all()
+    assert (np.fromfile(str(path) + ".cbf", dtype=np.uint8) == og.cbf()).all()
+    assert (np.fromfile(str(path) + ".rpkbf", dtype=np.uint8) == og.rpkbf()).all()
+    assert (np.fromfile(str(path) + ".fpkbf", dtype=np.uint8) == og.fpkbf()).all()
+    desc = open(str(path) + ".dbgbf.desc").read().splitlines()
+    assert desc[0] == "size:%d" % ((1 << 24) + 5) and desc[1] == "numhash:3" and desc[2].startswith("fpr:")
+    assert abs(float(desc[2][4:].replace("E", "e")) - g.getDbgbfFPR()) < 1e-9
+    assert open(path).read() == "dbgbfCbfMaxNumHash:3\nstranded:true\nk:25\nreadPairedKmersDistance:10\nfragmentPairedKmersDistance:30\n"
+    g2 = rb.BloomFilterDeBruijnGraph.load(ctx, path)
+    assert g2.getDbgbf().equivalent(g.getDbgbf()) and g2.getCbf().equivalent(g.getCbf())
+    assert g2.getRpkbf().equivalent(g.getRpkbf()) and g2.getFpkbf().equivalent(g.getFpkbf())
+    c1, _, _ = g.getKmers(rb.pack_reads(seqs[:40]))
+    c2, _, _ = g2.getKmers(rb.pack_reads(seqs[:40]))
+    assert (c1 == c2).all()
+    # upload of an oracle-built array, then continue inserting on the GPU
+    g.clear()
+    g.getDbgbf().upload(og.dbgbf()), g.getCbf().upload(og.cbf())
+    for s in seqs[:100]:
+        og.add_read(s)
+    g.addReads(rb.pack_reads(seqs[:100]))
+    assert_same_state(g, og)
+    g.destroy(), g2.destroy(), og.close()
+
+
+def test_error_codes(ctx):
+    with pytest.raises(rb.RBError) as ei:
+        rb.BloomFilter(ctx, 0, 3, 25)
+    assert ei.value.code == -1
+    with pytest.raises(rb.RBError):
+        rb.BloomFilter(ctx, 100, 9, 25)
+    g = rb.BloomFilterDeBruijnGraph(ctx, 1 << 20, 1 << 20, 1 << 20, 2, 2, 2, 25, False, False)
+    with pytest.raises(rb.RBError) as ei:
+        g.addReads(rb.pack_reads(["ACGT" * 40]), flags=rb.STORE_READ_PAIRS)
+    assert ei.value.code == -6
+    with pytest.raises(rb.RBError):
+        rb.BloomFilterDeBruijnGraph.load(ctx, "/nonexistent/graph")
+    g.destroy()
+
+
+# ---- BASELINE.json sizes: size-independent properties ---------------------------------------------------------------------
+@pytest.mark.skipif(os.environ.get("RB_SKIP_FULLSIZE") == "1", reason="full-size filters skipped")
+def test_full_size_filters_properties(ctx):
+    """configs[1] filter sizes (8 GiB Bloom = 2^36 bits, 8 GiB counting = 2^33 bytes), device-resident synthetic reads.
+    Properties: (a) after one pass every k-mer of the inserted reads has count >= 1 and the sum of 1/count over the
+    instances equals the number of distinct k-mers D; (b) popcount(dbgbf) == 3*D up to hash collisions; (c) a second
+    identical pass adds exactly the multiplicity to every count (idempotence of dbgbf: popcount unchanged)."""
+    import ctypes as C
+    n_reads, L, stride, k = 400_000, 150, 160, 25
+    nk = n_reads * (L - k + 1)
+    g = rb.BloomFilterDeBruijnGraph(ctx, 1 << 36, 1 << 33, 64, 3, 3, 1, k, False, False)
+    packed = ctx.dev_alloc(n_reads * stride // 4 + 64)
+    counts_dev = ctx.dev_alloc(nk * 4)
+    ctx.synth_reads_dev(77, 20_000_000, 0, n_reads, L, 2000, stride, packed)
+    assert g.addReadsDev(packed, n_reads, L, stride) == nk
+    c1 = np.zeros(nk, dtype=np.float32)
+    g.getKmersDev(packed, n_reads, L, stride, counts_dev)
+    ctx.sync(), ctx.d2h(c1, counts_dev)
+    assert c1.min() >= 1.0
+    D = float((1.0 / c1.astype(np.float64)).sum())
+    pop = g.getDbgbf().getPopCount()
+    assert c1.max() <= 17.0          # 3x coverage keeps every count in the exact MiniFloat range
+    assert abs(D - round(D)) < 1e-6 * D and abs(pop - 3 * D) < 2e-3 * 3 * D
+    assert g.getCbf().getPopCount() <= 3 * D
+    g.addReadsDev(packed, n_reads, L, stride)
+    c2 = np.zeros(nk, dtype=np.float32)
+    g.getKmersDev(packed, n_reads, L, stride, counts_dev)
+    ctx.sync(), ctx.d2h(c2, counts_dev)
+    small = c1 <= 8  # stay inside the deterministic MiniFloat range after doubling
+    assert (c2[small] == 2 * c1[small]).all()
+    assert g.getDbgbf().getPopCount() == pop
+    ctx.dev_free(packed), ctx.dev_free(counts_dev)
+    g.destroy()
