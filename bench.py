@@ -160,13 +160,14 @@ def config_dict(reads_per_step, n_gpus):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=22)   # 3 + 22 steps of 4 M reads = the 100 M reads (50 M pairs) of configs[1]
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--reads-per-step", type=int, default=4_000_000)
     ap.add_argument("--subbatch-kmers", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--genome", type=int, default=GENOME, help="experiments only: virtual genome length (coverage knob)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -189,9 +190,10 @@ def main():
     nk = n_reads * KMERS_PER_READ
     total_steps = args.warmup + args.steps
     words = n_reads * STRIDE // 32
-    batches = [ctx.dev_alloc(words * 8 + 64) for _ in range(total_steps)]
+    n_batches = min(total_steps, max(1, 100_000_000 // n_reads))   # the data set has 100 M reads; longer runs wrap around
+    batches = [ctx.dev_alloc(words * 8 + 64) for _ in range(n_batches)]
     for s, p in enumerate(batches):
-        ctx.synth_reads_dev(SEED, GENOME, s * n_reads, n_reads, READ_LEN, ERR_PPM, STRIDE, p)
+        ctx.synth_reads_dev(SEED, args.genome, s * n_reads, n_reads, READ_LEN, ERR_PPM, STRIDE, p)
     counts_dev = ctx.dev_alloc(nk * 4)
     ctx.sync()
 
@@ -205,7 +207,7 @@ def main():
         return t_i, t_l
 
     for s in range(args.warmup):
-        step(batches[s])
+        step(batches[s % n_batches])
     ctx.sync()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -214,7 +216,7 @@ def main():
     t_ins = t_look = 0.0
     wall0 = time.perf_counter()
     for s in range(args.warmup, total_steps):
-        a, b = step(batches[s])
+        a, b = step(batches[s % n_batches])
         t_ins += a
         t_look += b
     ctx.sync()
@@ -231,7 +233,7 @@ def main():
         e_steps = max(2, min(args.steps, 5))
         h_packed = [ctx.host_alloc(words * 8, np.uint64) for _ in range(e_steps + 1)]
         for i, hp in enumerate(h_packed):
-            ctx.d2h(hp, batches[i])       # the same synthetic reads, now living in pinned host memory
+            ctx.d2h(hp, batches[i % n_batches])       # the same synthetic reads, now living in pinned host memory
         h_counts = ctx.host_alloc(nk * 4, np.float32)
         reads = [rb.PackedReads(hp, None, None, None, n_reads, READ_LEN, STRIDE) for hp in h_packed]
         from rnabloom_b200.filters import _ptr

@@ -135,7 +135,7 @@ RB_API int32_t rb_filter_load(rb_ctx* ctx, int32_t kind, const char* desc_path, 
 RB_API int32_t rb_index_hashes(rb_ctx* ctx, const int64_t* hash, int64_t n, int64_t size, int64_t* index_out);
 
 /* ---- k-merizer alone (hash parity, and the "hash only" operator) --------------------------------------------
- * NTHashIterator / CanonicalNTHashIterator / ReverseComplementNTHashIterator (bloom/hash/*.java): for every k-mer
+ * NTHashIterator / CanonicalNTHashIterator / ReverseComplementNTHashIterator (bloom/hash/ *NTHashIterator.java): for every k-mer
  * position of every read writes fhash, rhash, base (= hVals[0]) at rb_kmer_offsets()[read] + pos.  Outputs may be NULL.
  * Masked bases hash as seed 0 (like 'N', NTHash.java:135-168). */
 RB_API int32_t rb_kmerize(rb_ctx* ctx, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off,

@@ -91,28 +91,31 @@ struct ByteFilter {   // CountingBloomFilter over UnsafeByteBuffer: slot i = byt
     int num_hash;
 };
 
-// byte RMW inside a 32-bit word.  Values are Java signed bytes.
+// byte RMW inside a 32-bit word.  Counter bytes are 0..127 (MiniFloat saturates at Byte.MAX_VALUE, util/MiniFloat.java:31-38),
+// which leaves bit 7 free: during an insert kernel it is the per-slot lock of the increment protocol below and is always clear
+// again when the kernel ends.
+constexpr uint32_t kLockBit = 0x80u;
 __device__ __forceinline__ int byte_of(uint32_t w, int sh) { return (int)(int8_t)(w >> sh); }
-// slot = max(slot, v)   (signed)
-__device__ __forceinline__ void byte_raise(uint32_t* wp, int sh, int v) {
-    uint32_t old = ld_cg(wp);
-    while (byte_of(old, sh) < v) {
-        const uint32_t nw = (old & ~(0xFFu << sh)) | ((uint32_t)(v & 0xFF) << sh);
-        const uint32_t got = atomicCAS(wp, old, nw);
-        if (got == old) return;
-        old = got;
-    }
-}
-// if slot == expect: slot = v, return true.  Other bytes of the word may change concurrently.
-__device__ __forceinline__ bool byte_cas(uint32_t* wp, int sh, int expect, int v) {
-    uint32_t old = ld_cg(wp);
-    while (byte_of(old, sh) == expect) {
-        const uint32_t nw = (old & ~(0xFFu << sh)) | ((uint32_t)(v & 0xFF) << sh);
+// if the byte (all 8 bits) equals `expect`: byte = nv, return true.  `old` is the caller's latest view of the word.
+__device__ __forceinline__ bool byte_cas(uint32_t* wp, int sh, uint32_t expect, uint32_t nv, uint32_t old) {
+    for (;;) {
+        if (((old >> sh) & 0xFFu) != expect) return false;
+        const uint32_t nw = (old & ~(0xFFu << sh)) | (nv << sh);
         const uint32_t got = atomicCAS(wp, old, nw);
         if (got == old) return true;
         old = got;
     }
-    return false;
+}
+// low 7 bits of the byte = max(low 7 bits, v); a lock bit held by somebody else is preserved.  Values only grow, so a
+// stale `old` that already shows >= v proves there is nothing to do.
+__device__ __forceinline__ void byte_raise(uint32_t* wp, int sh, uint32_t v, uint32_t old) {
+    for (;;) {
+        if (((old >> sh) & 0x7Fu) >= v) return;
+        const uint32_t nw = (old & ~(0x7Fu << sh)) | (v << sh);
+        const uint32_t got = atomicCAS(wp, old, nw);
+        if (got == old) return;
+        old = got;
+    }
 }
 
 // ---- claim table: elects exactly one "first" instance per distinct base hash between two clears ------------------
@@ -138,39 +141,56 @@ __device__ __forceinline__ bool claim_first(const ClaimTable& t, uint64_t key) {
 
 // ---- a11 CountingBloomFilter.increment (bloom/CountingBloomFilter.java:170-194), linearisable ---------------------
 // Reference: min over the h slots, u = MiniFloat.increment(min), every slot that equals min becomes u.
-// Here: all slots equal to min except the LAST one are raised to u first (idempotent), then the last one is
-// compare-and-swapped min -> u as the commit point; a failed commit means another instance got in between, so the whole
-// step is retried on fresh values.  Concurrent duplicates of one k-mer therefore each add exactly one increment.
+// Concurrent version (DESIGN.md "Linearisation"): the LAST slot that holds the minimum is the k-mer's designated slot.
+//   1. read the h slots; if one of them is locked, somebody (maybe a duplicate of this very k-mer) is mid-increment: retry
+//   2. lock + bump the designated slot in one CAS  (min, unlocked) -> (u, locked)          <- linearisation point
+//   3. raise every other slot that showed the minimum to u (max semantics, commutes with other k-mers' raises)
+//   4. clear the lock bit (fire-and-forget atomicAnd)
+// A thread holds at most one lock and never waits while holding it, so the protocol cannot deadlock; duplicates of one
+// k-mer serialise on the designated slot (each adds exactly one increment), and k-mers that merely share a counter see
+// each other's updates as if they had run one after the other.
+constexpr int kLockSpinLimit = 1 << 16;  // only a corrupt (>127) uploaded byte could keep a slot "locked" for ever
 template <int MAXH>
 __device__ __forceinline__ int cbf_increment(const ByteFilter& cbf, uint64_t base, const HashMults& hm, uint64_t rng_key,
                                              const uint32_t* preloaded /* MAXH words or nullptr */) {
     uint64_t idx[MAXH];
 #pragma unroll
     for (int h = 0; h < MAXH; ++h) idx[h] = (h < cbf.num_hash) ? fm_index(expand_hash(base, h, hm), cbf.fm) : 0;
-    for (uint32_t attempt = 0;; ++attempt) {
+    for (int attempt = 0;; ++attempt) {
+        uint32_t w[MAXH];
+        uint32_t any_lock = 0;
+#pragma unroll
+        for (int h = 0; h < MAXH; ++h)
+            if (h < cbf.num_hash) w[h] = (attempt == 0 && preloaded) ? preloaded[h] : ld_cg(&cbf.words[idx[h] >> 2]);
         int v[MAXH];
         int mn = 127;
 #pragma unroll
         for (int h = 0; h < MAXH; ++h) {
             if (h < cbf.num_hash) {
-                const uint32_t w = (attempt == 0 && preloaded) ? preloaded[h] : ld_cg(&cbf.words[idx[h] >> 2]);
-                v[h] = byte_of(w, (int)(idx[h] & 3) * 8);
+                const uint32_t b = (w[h] >> ((int)(idx[h] & 3) * 8)) & 0xFFu;
+                any_lock |= b & kLockBit;
+                v[h] = (int)(b & 0x7Fu);
                 mn = v[h] < mn ? v[h] : mn;
             } else v[h] = 127;
         }
-        const int u = minifloat_increment(mn, mix64(rng_key + attempt));
+        if (any_lock && attempt < kLockSpinLimit) { __nanosleep(40); continue; }
+        const int u = minifloat_increment(mn, mix64(rng_key + (uint64_t)attempt));
         if (u == mn) return u;
         int D = 0;
 #pragma unroll
         for (int h = 0; h < MAXH; ++h) if (h < cbf.num_hash && v[h] == mn) D = h;
         uint64_t idxD = 0;
+        uint32_t wD = 0;
 #pragma unroll
-        for (int h = 0; h < MAXH; ++h) if (h == D) idxD = idx[h];
+        for (int h = 0; h < MAXH; ++h) if (h == D) { idxD = idx[h]; wD = w[h]; }
+        const int shD = (int)(idxD & 3) * 8;
+        if (!byte_cas(&cbf.words[idxD >> 2], shD, (uint32_t)mn, (uint32_t)u | kLockBit, wD)) continue;
 #pragma unroll
         for (int h = 0; h < MAXH; ++h)
             if (h < cbf.num_hash && h != D && v[h] == mn && idx[h] != idxD)
-                byte_raise(&cbf.words[idx[h] >> 2], (int)(idx[h] & 3) * 8, u);
-        if (byte_cas(&cbf.words[idxD >> 2], (int)(idxD & 3) * 8, mn, u)) return u;
+                byte_raise(&cbf.words[idx[h] >> 2], (int)(idx[h] & 3) * 8, (uint32_t)u, w[h]);
+        atomicAnd(&cbf.words[idxD >> 2], ~(kLockBit << shD));
+        return u;
     }
 }
 

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kThreads) k_graph_insert(const Ingest g, const
                 }
             }
         }
-        if (POLICY == POLICY_DBG_ONLY) continue;
+        if constexpr (POLICY != POLICY_DBG_ONLY) {
         // stage 3: cbf probes of the present k-mers in flight, then the min-increment
         uint32_t wc[kGroup][MAXH];
 #pragma unroll
@@ -125,13 +125,14 @@ __global__ void __launch_bounds__(kThreads) k_graph_insert(const Ingest g, const
                     for (int h = 0; h < MAXH; ++h)
                         if (h < gd.cbf.num_hash) {
                             const uint64_t idx = fm_index(expand_hash(base[j], h, gd.hm), gd.cbf.fm);
-                            const int v = byte_of(wc[j][h], (int)(idx & 3) * 8);
+                            const int v = (int)((wc[j][h] >> ((int)(idx & 3) * 8)) & 0x7Fu);  // bit 7 may be a live lock
                             mn = v < mn ? v : mn;
                         }
                     if (!(minifloat_to_float(mn) > 0.f)) continue;
                 }
                 cbf_increment<MAXH>(gd.cbf, base[j], gd.hm, mix64(base[j] ^ gd.rng_seed) + (uint64_t)(pos + i0 + j) * 0x632BE59BD9B4E019ULL, wc[j]);
             }
+        }
     }
 }
 
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(kThreads) k_hash_op(const int64_t* __restrict_
     else if (OP == OP_GRAPH_ADD) {
         if (bf_lookup_then_add<MAXH>(gd.dbg, gd.ct, b, gd.hm)) cbf_increment<MAXH>(gd.cbf, b, gd.hm, (mix64(b ^ gd.rng_seed) + (uint64_t)i * 0x632BE59BD9B4E019ULL), nullptr);
     } else if (OP == OP_GRAPH_COUNT_IF_PRESENT) {
-        if (bf_lookup<MAXH>(gd.dbg, b, gd.hm) && minifloat_to_float(cbf_min<MAXH>(gd.cbf, b, gd.hm)) > 0.f)
+        if (bf_lookup<MAXH>(gd.dbg, b, gd.hm) && minifloat_to_float(cbf_min<MAXH>(gd.cbf, b, gd.hm) & 0x7F) > 0.f)
             cbf_increment<MAXH>(gd.cbf, b, gd.hm, (mix64(b ^ gd.rng_seed) + (uint64_t)i * 0x632BE59BD9B4E019ULL), nullptr);
     } else if (OP == OP_GRAPH_COUNT) {
         outf[i] = bf_lookup<MAXH>(gd.dbg, b, gd.hm) ? minifloat_to_float(cbf_min<MAXH>(gd.cbf, b, gd.hm)) + 1.f : 0.f;

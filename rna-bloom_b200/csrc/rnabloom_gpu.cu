@@ -28,6 +28,7 @@ struct rb_ctx {
     // claim table (DESIGN.md "Linearisation")
     unsigned long long* claim = nullptr;
     int64_t claim_cap = 0, claim_used = 0;
+    const void* claim_owner = nullptr;  // the bit array the current claims refer to
     // staging (host-pointer entry points)
     void* stage[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int64_t stage_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -111,6 +112,9 @@ extern "C" int32_t rb_ctx_create(int32_t device, rb_ctx** out) {
         delete c;
         return fail(nullptr, RB_ECUDA, m);
     }
+    // Every filter probe is an isolated 32 B sector of a multi-GiB array: ask L2 to fetch exactly that from HBM instead of
+    // the whole 128 B line (measured 4x DRAM over-fetch otherwise; profiles/r01_notes.md).  Process-wide device limit.
+    if (!getenv("RB_KEEP_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&c->scratch, 64);
     if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, RB_ECUDA, m); }
@@ -218,7 +222,8 @@ static int32_t stage_get(rb_ctx* ctx, int slot, int64_t bytes, void** p) {
 }
 
 // Make room in the claim table for `n` more claims (clears it when the load factor would pass 1/2).
-static int32_t claim_reserve(rb_ctx* ctx, int64_t n, ClaimTable* ct) {
+static int32_t claim_reserve(rb_ctx* ctx, int64_t n, const void* owner, ClaimTable* ct) {
+    if (owner != ctx->claim_owner) { ctx->claim_owner = owner; ctx->claim_used = ctx->claim_cap; }  // claims are per filter
     int64_t need = 1024;
     while (need < 2 * n) need <<= 1;
     if (ctx->claim_cap < need) {
@@ -306,6 +311,7 @@ static int32_t filter_alloc(rb_ctx* ctx, int kind, int64_t size, int num_hash, i
     cudaError_t e = cudaMalloc(&f->dev, (size_t)f->alloc);
     if (e != cudaSuccess) { delete f; return fail(ctx, RB_ENOMEM, std::string("cudaMalloc(filter): ") + cudaGetErrorString(e)); }
     e = cudaMemsetAsync(f->dev, 0, (size_t)f->alloc, ctx->stream);
+    ctx->claim_used = ctx->claim_cap;  // a fresh filter may reuse the address of a destroyed one: drop stale claims
     if (e != cudaSuccess) { cudaFree(f->dev); delete f; return fail(ctx, RB_ECUDA, cudaGetErrorString(e)); }
     *out = f;
     return RB_OK;
@@ -384,7 +390,7 @@ static int32_t run_hash_op(rb_ctx* ctx, int op, GraphDev gd, int maxh, const int
         void *dbase, *dout;
         int32_t rc = stage_get(ctx, 0, m * 8, &dbase); if (rc) return rc;
         rc = stage_get(ctx, 1, m * 4, &dout); if (rc) return rc;
-        if (needs_claim) { rc = claim_reserve(ctx, m, &gd.ct); if (rc) return rc; }
+        if (needs_claim) { rc = claim_reserve(ctx, m, gd.dbg.words, &gd.ct); if (rc) return rc; }
         CK(cudaMemcpyAsync(dbase, base + i0, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
         dispatch_hash_op(op, maxh, m, ctx->stream, (const int64_t*)dbase, gd, (uint8_t*)dout, (float*)dout);
         LAUNCH_CHECK();
@@ -803,7 +809,7 @@ struct InsertUser { rb_graph* g; int mode, policy; };
 static int32_t insert_launch(rb_ctx* ctx, const Ingest& ing, void* user) {
     InsertUser* u = (InsertUser*)user;
     GraphDev gd = graph_view(u->g);
-    if (u->policy == POLICY_ADD) { const int32_t rc = claim_reserve(ctx, ing.n_pos, &gd.ct); if (rc) return rc; }
+    if (u->policy == POLICY_ADD) { const int32_t rc = claim_reserve(ctx, ing.n_pos, gd.dbg.words, &gd.ct); if (rc) return rc; }
     const int grid = (int)div_up(div_up(ing.n_pos, kChunk), kThreads);
     const int maxh = u->g->hmax;
     if (maxh <= 2) launch_insert_mode<2>(u->mode, u->policy, grid, ctx->stream, ing, gd);

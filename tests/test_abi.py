@@ -74,3 +74,14 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|liboracle|orc_", text, re.M), f
+
+
+def test_jni_shim_compiles_against_stub():
+    """No JDK in the image: the shim is at least checked for syntax/type errors against a stand-in jni.h."""
+    import subprocess
+    subprocess.check_call(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "tests", "jni_stub"),
+                           "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "jni", "rnabloom_jni.c")])
+    text = open(os.path.join(ROOT, "java", "rnabloom", "gpu", "Native.java")).read()
+    natives = set(re.findall(r"public static native \w+ (\w+)\(", text))
+    shim = set(re.findall(r"Java_rnabloom_gpu_Native_(\w+)\(", open(os.path.join(ROOT, "jni", "rnabloom_jni.c")).read()))
+    assert natives == shim, (natives ^ shim)
