@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--subbatch-kmers", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sharded", action="store_true", help="experiments only: run the sharded pipeline even on one GPU")
     ap.add_argument("--genome", type=int, default=GENOME, help="experiments only: virtual genome length (coverage knob)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -175,7 +176,12 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
-    if world > 1:
+    if world > 1 or args.sharded:
+        if world == 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29533")
+            os.environ.setdefault("RANK", "0")
+            os.environ.setdefault("WORLD_SIZE", "1")
         from bench_multi import run_sharded   # hash-sharded filters + all-to-all (rna-bloom_b200/sharded.py)
         run_sharded(args, rank, world, local_rank)
         return

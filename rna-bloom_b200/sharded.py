@@ -1,0 +1,214 @@
+"""Hash-sharded BloomFilterDeBruijnGraph over the GPUs of one box: one process per GPU, filters split by index range, probes routed
+to the owner of their index with all-to-all exchanges (torch.distributed: NCCL over NVLink on GPUs, gloo in the CPU tests).
+
+This module is host plumbing only.  Every phase between two exchanges is a CUDA kernel behind the C-ABI (`rb_shard_*`,
+include/rnabloom_gpu.h, kernels in csrc/rb_shard.cuh); `GpuBackend` forwards to it.  The orchestration takes the backend as a
+parameter so that the exchange protocol itself (region layout, reply positions, round structure) can be exercised on CPU
+with a stand-in backend that lives in tests/ -- the product has no CPU path.
+
+The logical filters are exactly the reference's single arrays (graph/BloomFilterDeBruijnGraph.java:75-104): concatenating the ranks'
+shares gives the byte array a single-GPU (or Java) run produces.
+"""
+import contextlib
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import binding as B
+from .binding import RBError
+
+POLICY_ADD, POLICY_COUNT_IF_PRESENT, POLICY_DBG_ONLY = 0, 1, 2
+
+
+class GpuBackend:
+    """rb_shard_* over device tensors (pointers are passed straight through)."""
+
+    def __init__(self, ctx, n_ranks, rank, dbg_bits, cbf_bytes, hd, hc, k, stranded, max_kmers_per_round):
+        self.ctx = ctx
+        self.L = ctx.L
+        h = C.c_void_p()
+        ctx.check(self.L.rb_shard_create(ctx.h, n_ranks, rank, dbg_bits, cbf_bytes, hd, hc, k, int(stranded), max_kmers_per_round, C.byref(h)))
+        self.h = h
+        geom = (C.c_int64 * 8)()
+        ctx.check(self.L.rb_shard_geometry(self.h, geom))
+        (self.cap_keys, self.cap_dbg, self.cap_cbf, self.cap_lookup, self.dbg_shard, self.cbf_shard, self.local_dbg_bits,
+         self.local_cbf_bytes) = [int(x) for x in geom]
+        self.device = torch.device("cuda", ctx.device)
+        # kernels, torch tensor ops and the NCCL exchanges are all ordered on one (non-default) stream
+        self.stream = torch.cuda.Stream(device=self.device)
+        ctx.set_stream(self.stream.cuda_stream)
+
+    def close(self):
+        if self.h:
+            self.ctx.check(self.L.rb_shard_destroy(self.h))
+            self.h = None
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def _reads(self, reads):
+        # reads: (packed_ptr, mask_ptr, read_off_ptr, read_len_ptr, n_reads, uniform_len, uniform_stride) with raw device pointers
+        return reads
+
+    def route_keys(self, reads, flags, send, cnt):
+        n = C.c_int64()
+        self.ctx.check(self.L.rb_shard_route_keys(self.h, *reads, flags, self._p(send), self._p(cnt), C.byref(n)))
+        return n.value
+
+    def aggregate(self, recv, recv_cnt):
+        self.ctx.check(self.L.rb_shard_aggregate(self.h, self._p(recv), self._p(recv_cnt)))
+
+    def emit_dbg(self, send, cnt):
+        self.ctx.check(self.L.rb_shard_emit_dbg(self.h, self._p(send), self._p(cnt)))
+
+    def apply_dbg(self, recv, recv_cnt, reply, set_bits):
+        self.ctx.check(self.L.rb_shard_apply_dbg(self.h, self._p(recv), self._p(recv_cnt), self._p(reply), int(set_bits)))
+
+    def emit_cbf_reads(self, reply_home, policy, send, cnt):
+        self.ctx.check(self.L.rb_shard_emit_cbf_reads(self.h, self._p(reply_home), policy, self._p(send), self._p(cnt)))
+
+    def apply_cbf_read(self, recv, recv_cnt, reply):
+        self.ctx.check(self.L.rb_shard_apply_cbf_read(self.h, self._p(recv), self._p(recv_cnt), self._p(reply)))
+
+    def emit_cbf_raises(self, reply_home, policy, send, cnt):
+        self.ctx.check(self.L.rb_shard_emit_cbf_raises(self.h, self._p(reply_home), policy, self._p(send), self._p(cnt)))
+
+    def apply_cbf_raise(self, recv, recv_cnt):
+        self.ctx.check(self.L.rb_shard_apply_cbf_raise(self.h, self._p(recv), self._p(recv_cnt)))
+
+    def route_lookup(self, reads, send, cnt, fhash=None, rhash=None):
+        n = C.c_int64()
+        self.ctx.check(self.L.rb_shard_route_lookup(self.h, *reads, self._p(send), self._p(cnt), self._p(fhash), self._p(rhash), C.byref(n)))
+        return n.value
+
+    def apply_lookup(self, recv, recv_cnt, reply):
+        self.ctx.check(self.L.rb_shard_apply_lookup(self.h, self._p(recv), self._p(recv_cnt), self._p(reply)))
+
+    def combine_lookup(self, reply_home, counts):
+        self.ctx.check(self.L.rb_shard_combine_lookup(self.h, self._p(reply_home), self._p(counts)))
+
+    def overflow(self):
+        f = C.c_int32()
+        self.ctx.check(self.L.rb_shard_overflow(self.h, C.byref(f)))
+        return bool(f.value)
+
+    def local_filter(self, which):
+        from .filters import BloomFilter, CountingBloomFilter
+        h = C.c_void_p()
+        self.ctx.check(self.L.rb_shard_filter(self.h, which, C.byref(h)))
+        cls = BloomFilter if which == B.RB_DBGBF else CountingBloomFilter
+        return cls(self.ctx, 0, 0, 0, _handle=h)
+
+    def download(self, which):
+        return self.local_filter(which).download()
+
+    def popcount(self, which):
+        return self.local_filter(which).getPopCount()
+
+
+class ShardedGraph:
+    """graph.add / graph.getKmers for reads that live on this rank, against filters sharded over all ranks."""
+
+    def __init__(self, backend, rank, world, group=None):
+        self.be, self.rank, self.world, self.group = backend, rank, world, group
+        self.cap_max = max(backend.cap_keys, backend.cap_dbg, backend.cap_cbf, backend.cap_lookup)
+        dev = backend.device
+        n = world * self.cap_max
+        self.send = torch.empty(n, dtype=torch.int64, device=dev)
+        self.recv = self.send if world == 1 else torch.empty(n, dtype=torch.int64, device=dev)
+        self.cnt_s = torch.zeros(world, dtype=torch.int32, device=dev)
+        self.cnt_r = self.cnt_s if world == 1 else torch.zeros(world, dtype=torch.int32, device=dev)
+        self.reply = torch.empty(n, dtype=torch.uint8, device=dev)
+        self.reply_home = self.reply if world == 1 else torch.empty(n, dtype=torch.uint8, device=dev)
+        self.exchanged_bytes = 0
+
+    # ---- exchanges -------------------------------------------------------------------------------------------------------
+    def _forward(self, cap):
+        """send regions [world][cap] + counts -> owners."""
+        if self.world == 1:
+            return
+        n = self.world * cap
+        dist.all_to_all_single(self.cnt_r, self.cnt_s, group=self.group)
+        dist.all_to_all_single(self.recv[:n], self.send[:n], group=self.group)
+        self.exchanged_bytes += n * 8
+
+    def _backward(self, cap):
+        """reply regions travel back to where the probes came from (same offsets)."""
+        if self.world == 1:
+            return
+        n = self.world * cap
+        dist.all_to_all_single(self.reply_home[:n], self.reply[:n], group=self.group)
+        self.exchanged_bytes += n
+
+    # ---- one round = at most max_kmers_per_round k-mers per rank ------------------------------------------------------------
+    def _on_stream(self):
+        s = getattr(self.be, "stream", None)
+        return torch.cuda.stream(s) if s is not None else contextlib.nullcontext()
+
+    def add_round(self, reads, flags=0):
+        with self._on_stream():
+            return self._add_round(reads, flags)
+
+    def count_round(self, reads, counts, fhash=None, rhash=None):
+        with self._on_stream():
+            return self._count_round(reads, counts, fhash, rhash)
+
+    def _add_round(self, reads, flags=0):
+        be = self.be
+        policy = POLICY_DBG_ONLY if flags & B.DBG_ONLY else POLICY_COUNT_IF_PRESENT if flags & B.ADD_COUNT_IF_PRESENT else POLICY_ADD
+        n = be.route_keys(reads, flags, self.send, self.cnt_s)
+        self._forward(be.cap_keys)
+        be.aggregate(self.recv, self.cnt_r)
+        be.emit_dbg(self.send, self.cnt_s)
+        self._forward(be.cap_dbg)
+        be.apply_dbg(self.recv, self.cnt_r, self.reply, set_bits=policy != POLICY_COUNT_IF_PRESENT)
+        if policy == POLICY_DBG_ONLY:
+            return n
+        self._backward(be.cap_dbg)
+        be.emit_cbf_reads(self.reply_home, policy, self.send, self.cnt_s)
+        self._forward(be.cap_cbf)
+        be.apply_cbf_read(self.recv, self.cnt_r, self.reply)
+        self._backward(be.cap_cbf)
+        be.emit_cbf_raises(self.reply_home, policy, self.send, self.cnt_s)
+        self._forward(be.cap_cbf)
+        be.apply_cbf_raise(self.recv, self.cnt_r)
+        return n
+
+    def _count_round(self, reads, counts, fhash=None, rhash=None):
+        be = self.be
+        n = be.route_lookup(reads, self.send, self.cnt_s, fhash, rhash)
+        self._forward(be.cap_lookup)
+        be.apply_lookup(self.recv, self.cnt_r, self.reply)
+        self._backward(be.cap_lookup)
+        be.combine_lookup(self.reply_home, counts)
+        return n
+
+    def check_overflow(self):
+        """A send region overflowed (pathologically skewed hashes): results of the round are incomplete -> loud failure."""
+        flag = torch.tensor([1 if self.be.overflow() else 0], dtype=torch.int32, device=self.be.device)
+        if self.world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+        if int(flag.item()):
+            raise RBError(-6, "sharded exchange: a send region overflowed; lower max_kmers_per_round")
+
+    # ---- whole logical arrays (tests, save) --------------------------------------------------------------------------------
+    def gather_filter(self, which, total_bytes):
+        """Concatenate the ranks' shares -> the reference's single byte array (valid on every rank)."""
+        local = np.ascontiguousarray(self.be.download(which))
+        if self.world == 1:
+            return local[:total_bytes]
+        share = (self.be.dbg_shard // 8) if which == B.RB_DBGBF else self.be.cbf_shard
+        buf = torch.zeros(share, dtype=torch.uint8)
+        buf[: min(len(local), share)] = torch.from_numpy(local[:share].copy())
+        out = [torch.zeros(share, dtype=torch.uint8) for _ in range(self.world)]
+        dev = self.be.device
+        if dev.type == "cuda":   # NCCL groups only move device tensors
+            outd = [o.to(dev) for o in out]
+            dist.all_gather(outd, buf.to(dev), group=self.group)
+            out = [o.cpu() for o in outd]
+        else:
+            dist.all_gather(out, buf, group=self.group)
+        return torch.cat(out).numpy()[:total_bytes]
