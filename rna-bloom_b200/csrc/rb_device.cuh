@@ -139,6 +139,16 @@ __device__ __forceinline__ bool claim_first(const ClaimTable& t, uint64_t key) {
     }
 }
 
+// continue a claim whose first probe hit another key
+__device__ __forceinline__ bool claim_first_from(const ClaimTable& t, uint64_t key, uint64_t s) {
+    for (;;) {
+        const unsigned long long old = atomicCAS(&t.slots[s], 0ULL, (unsigned long long)key);
+        if (old == 0ULL) return true;
+        if (old == key) return false;
+        s = (s + 1) & t.mask;
+    }
+}
+
 // ---- a11 CountingBloomFilter.increment (bloom/CountingBloomFilter.java:170-194), linearisable ---------------------
 // Reference: min over the h slots, u = MiniFloat.increment(min), every slot that equals min becomes u.
 // Concurrent version (DESIGN.md "Linearisation"): the LAST slot that holds the minimum is the k-mer's designated slot.

@@ -43,6 +43,11 @@ struct PositionWalker {
 };
 
 // ---- graph.add / addCountIfPresent / addDbgOnly over reads (graph/BloomFilterDeBruijnGraph.java:405-436) ----------
+// Every stage issues the memory operations of all kGroup k-mers before it looks at any result, so a group costs a handful of
+// HBM/L2 round trips instead of one dependent chain per k-mer:
+//   1 dbgbf probes            2 claim CAS (k-mers with a clear bit)  + red.or of the clear bits
+//   3 cbf probes              4 lock+bump CAS of the designated counter -> raise CAS of the other minimum counters -> unlock
+// Anything unusual (claim-slot collision, locked or concurrently changed counter) falls back to the generic loops of rb_device.cuh.
 template <int MODE, int MAXH, int POLICY>
 __global__ void __launch_bounds__(kThreads) k_graph_insert(const Ingest g, const GraphDev gd) {
     __shared__ RollLut lut;
@@ -75,63 +80,148 @@ __global__ void __launch_bounds__(kThreads) k_graph_insert(const Ingest g, const
             }
         }
         // stage 2: dbgbf.lookupThenAdd (bloom/BloomFilter.java:147-155)
-        uint32_t found = 0;
+        uint32_t found = 0, need_claim = 0;
+        uint32_t clear[kGroup];
 #pragma unroll
         for (int j = 0; j < kGroup; ++j) {
+            clear[j] = 0;
             if (ok & (1u << j)) {
-                uint32_t clear = 0;
 #pragma unroll
                 for (int h = 0; h < MAXH; ++h)
                     if (h < gd.dbg.num_hash) {
                         const uint64_t idx = fm_index(expand_hash(base[j], h, gd.hm), gd.dbg.fm);
-                        if (!((wd[j][h] >> (idx & 31)) & 1u)) clear |= 1u << h;
+                        if (!((wd[j][h] >> (idx & 31)) & 1u)) clear[j] |= 1u << h;
                     }
-                if (clear == 0) found |= 1u << j;
-                else if (POLICY == POLICY_COUNT_IF_PRESENT) { /* absent: nothing to do */ }
-                else {
-                    bool first = true;
-                    if (POLICY == POLICY_ADD) first = claim_first(gd.ct, base[j]);
-                    if (!first) found |= 1u << j;  // a concurrent duplicate owns the first sighting
-                    else {
-#pragma unroll
-                        for (int h = 0; h < MAXH; ++h)
-                            if (clear & (1u << h)) {
-                                const uint64_t idx = fm_index(expand_hash(base[j], h, gd.hm), gd.dbg.fm);
-                                atomicOr(&gd.dbg.words[idx >> 5], 1u << (idx & 31));
-                            }
-                    }
-                }
+                if (clear[j] == 0) found |= 1u << j;
+                else if (POLICY != POLICY_COUNT_IF_PRESENT) need_claim |= 1u << j;
             }
         }
+        if (POLICY == POLICY_ADD && need_claim) {
+            unsigned long long got[kGroup];
+            uint64_t slot[kGroup];
+#pragma unroll
+            for (int j = 0; j < kGroup; ++j)   // all first-probe claims in flight together
+                if ((need_claim & (1u << j)) && base[j] != 0) {
+                    slot[j] = (base[j] * 0x9E3779B97F4A7C15ULL) >> gd.ct.shift;
+                    got[j] = atomicCAS(&gd.ct.slots[slot[j]], 0ULL, (unsigned long long)base[j]);
+                }
+#pragma unroll
+            for (int j = 0; j < kGroup; ++j)
+                if (need_claim & (1u << j)) {
+                    bool first;
+                    if (base[j] == 0) first = claim_first(gd.ct, 0);
+                    else if (got[j] == 0ULL) first = true;
+                    else if (got[j] == base[j]) first = false;
+                    else first = claim_first_from(gd.ct, base[j], (slot[j] + 1) & gd.ct.mask);
+                    if (!first) { found |= 1u << j; need_claim &= ~(1u << j); }  // a concurrent duplicate owns the first sighting
+                }
+        }
+        if (POLICY != POLICY_COUNT_IF_PRESENT) {
+#pragma unroll
+            for (int j = 0; j < kGroup; ++j)
+                if (need_claim & (1u << j)) {
+#pragma unroll
+                    for (int h = 0; h < MAXH; ++h)
+                        if (clear[j] & (1u << h)) {
+                            const uint64_t idx = fm_index(expand_hash(base[j], h, gd.hm), gd.dbg.fm);
+                            atomicOr(&gd.dbg.words[idx >> 5], 1u << (idx & 31));
+                        }
+                }
+        }
         if constexpr (POLICY != POLICY_DBG_ONLY) {
-        // stage 3: cbf probes of the present k-mers in flight, then the min-increment
-        uint32_t wc[kGroup][MAXH];
+            if (!found) continue;
+            // stage 3: cbf probes of the present k-mers in flight
+            uint32_t wc[kGroup][MAXH];
 #pragma unroll
-        for (int j = 0; j < kGroup; ++j)
-            if (found & (1u << j)) {
-#pragma unroll
-                for (int h = 0; h < MAXH; ++h)
-                    if (h < gd.cbf.num_hash) {
-                        const uint64_t idx = fm_index(expand_hash(base[j], h, gd.hm), gd.cbf.fm);
-                        wc[j][h] = ld_cg(&gd.cbf.words[idx >> 2]);
-                    }
-            }
-#pragma unroll
-        for (int j = 0; j < kGroup; ++j)
-            if (found & (1u << j)) {
-                if (POLICY == POLICY_COUNT_IF_PRESENT) {  // "&& cbf.getCount(hashVals) > 0" (graph :425)
-                    int mn = 127;
+            for (int j = 0; j < kGroup; ++j)
+                if (found & (1u << j)) {
 #pragma unroll
                     for (int h = 0; h < MAXH; ++h)
                         if (h < gd.cbf.num_hash) {
                             const uint64_t idx = fm_index(expand_hash(base[j], h, gd.hm), gd.cbf.fm);
-                            const int v = (int)((wc[j][h] >> ((int)(idx & 3) * 8)) & 0x7Fu);  // bit 7 may be a live lock
-                            mn = v < mn ? v : mn;
+                            wc[j][h] = ld_cg(&gd.cbf.words[idx >> 2]);
                         }
-                    if (!(minifloat_to_float(mn) > 0.f)) continue;
                 }
-                cbf_increment<MAXH>(gd.cbf, base[j], gd.hm, mix64(base[j] ^ gd.rng_seed) + (uint64_t)(pos + i0 + j) * 0x632BE59BD9B4E019ULL, wc[j]);
+            // stage 4a: pick minimum / designated counter, issue every lock+bump CAS (rb_device.cuh "cbf_increment" protocol)
+            uint32_t fast = 0, slow = 0, raise[kGroup], gotw[kGroup];
+            int u[kGroup], dsg[kGroup];
+#pragma unroll
+            for (int j = 0; j < kGroup; ++j) {
+                raise[j] = 0; u[j] = 0; dsg[j] = 0; gotw[j] = 0;
+                if (found & (1u << j)) {
+                    uint32_t lock = 0;
+                    int mn = 127, v[MAXH];
+                    uint64_t idx[MAXH];
+#pragma unroll
+                    for (int h = 0; h < MAXH; ++h) {
+                        v[h] = 127; idx[h] = 0;
+                        if (h < gd.cbf.num_hash) {
+                            idx[h] = fm_index(expand_hash(base[j], h, gd.hm), gd.cbf.fm);
+                            const uint32_t b = (wc[j][h] >> ((int)(idx[h] & 3) * 8)) & 0xFFu;
+                            lock |= b & kLockBit;
+                            v[h] = (int)(b & 0x7Fu);
+                            mn = v[h] < mn ? v[h] : mn;
+                        }
+                    }
+                    if (POLICY == POLICY_COUNT_IF_PRESENT && mn == 0) continue;   // "&& cbf.getCount(hashVals) > 0" (graph :425)
+                    if (lock) { slow |= 1u << j; continue; }
+                    const uint64_t rk = mix64(base[j] ^ gd.rng_seed) + (uint64_t)(pos + i0 + j) * 0x632BE59BD9B4E019ULL;
+                    u[j] = minifloat_increment(mn, mix64(rk));
+                    if (u[j] == mn) continue;
+                    int D = 0;
+#pragma unroll
+                    for (int h = 0; h < MAXH; ++h) if (h < gd.cbf.num_hash && v[h] == mn) D = h;
+                    uint64_t idxD = 0; uint32_t wD = 0;
+#pragma unroll
+                    for (int h = 0; h < MAXH; ++h) if (h == D) { idxD = idx[h]; wD = wc[j][h]; }
+#pragma unroll
+                    for (int h = 0; h < MAXH; ++h)
+                        if (h < gd.cbf.num_hash && h != D && v[h] == mn && idx[h] != idxD) raise[j] |= 1u << h;
+                    dsg[j] = D;
+                    const int sh = (int)(idxD & 3) * 8;
+                    const uint32_t nw = (wD & ~(0xFFu << sh)) | (((uint32_t)u[j] | kLockBit) << sh);
+                    gotw[j] = atomicCAS(&gd.cbf.words[idxD >> 2], wD, nw);
+                    if (true) fast |= 1u << j;
+                }
             }
+            // stage 4b: lock holders raise the other minimum counters (all raise CAS in flight), everybody else goes the slow way
+            uint32_t gr[kGroup][MAXH];
+#pragma unroll
+            for (int j = 0; j < kGroup; ++j)
+                if (fast & (1u << j)) {
+                    uint32_t wD = 0;
+#pragma unroll
+                    for (int h = 0; h < MAXH; ++h) if (h == dsg[j]) wD = wc[j][h];
+                    if (gotw[j] != wD) { fast &= ~(1u << j); slow |= 1u << j; continue; }
+#pragma unroll
+                    for (int h = 0; h < MAXH; ++h)
+                        if (raise[j] & (1u << h)) {
+                            const uint64_t idx = fm_index(expand_hash(base[j], h, gd.hm), gd.cbf.fm);
+                            const int sh = (int)(idx & 3) * 8;
+                            const uint32_t old = wc[j][h];
+                            gr[j][h] = atomicCAS(&gd.cbf.words[idx >> 2], old, (old & ~(0x7Fu << sh)) | ((uint32_t)u[j] << sh));
+                        }
+                }
+            // stage 4c: finish raises that lost a race on another byte of their word, then release the locks
+#pragma unroll
+            for (int j = 0; j < kGroup; ++j)
+                if (fast & (1u << j)) {
+#pragma unroll
+                    for (int h = 0; h < MAXH; ++h)
+                        if ((raise[j] & (1u << h)) && gr[j][h] != wc[j][h]) {
+                            const uint64_t idx = fm_index(expand_hash(base[j], h, gd.hm), gd.cbf.fm);
+                            byte_raise(&gd.cbf.words[idx >> 2], (int)(idx & 3) * 8, (uint32_t)u[j], gr[j][h]);
+                        }
+                    uint64_t idxD = 0;
+#pragma unroll
+                    for (int h = 0; h < MAXH; ++h) if (h == dsg[j]) idxD = fm_index(expand_hash(base[j], h, gd.hm), gd.cbf.fm);
+                    atomicAnd(&gd.cbf.words[idxD >> 2], ~(kLockBit << ((int)(idxD & 3) * 8)));
+                }
+            // slow path only after this thread has released every lock it held
+#pragma unroll
+            for (int j = 0; j < kGroup; ++j)
+                if (slow & (1u << j))
+                    cbf_increment<MAXH>(gd.cbf, base[j], gd.hm, mix64(base[j] ^ gd.rng_seed) + (uint64_t)(pos + i0 + j) * 0x632BE59BD9B4E019ULL + 1, nullptr);
         }
     }
 }
