@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--subbatch-kmers", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--engine", default=os.environ.get("RB_ENGINE", "direct"), choices=["direct", "bucketed"])
     ap.add_argument("--sharded", action="store_true", help="experiments only: run the sharded pipeline even on one GPU")
     ap.add_argument("--genome", type=int, default=GENOME, help="experiments only: virtual genome length (coverage knob)")
     args = ap.parse_args()
@@ -187,6 +188,7 @@ def main():
         return
 
     import rnabloom_b200 as rb
+    os.environ["RB_ENGINE"] = args.engine
     args.warmup = max(args.warmup, 3)
     ctx = rb.Context(local_rank)
     if args.subbatch_kmers:

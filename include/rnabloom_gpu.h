@@ -157,7 +157,12 @@ RB_API int32_t rb_graph_destroy(rb_graph* g);
 RB_API int32_t rb_graph_init_fpkbf(rb_graph* g, int64_t pkbf_bits, int32_t pkbf_num_hash);
 RB_API int32_t rb_graph_set_distances(rb_graph* g, int32_t d_read, int32_t d_frag);
 RB_API int32_t rb_graph_filter(rb_graph* g, int32_t which, rb_filter** out); /* borrowed handle; NULL if absent */
-RB_API int32_t rb_graph_clear(rb_graph* g);                                 /* clearDbgbf/Cbf/Rpkbf/Fpkbf :211-245 */
+RB_API int32_t rb_graph_clear(rb_graph* g);
+/* Execution engine of the read-level insert/lookup calls (same results, different HBM schedule):
+ *   RB_ENGINE_DIRECT   one fused kernel, every probe an isolated HBM sector access (bounded by DRAM row activations)
+ *   RB_ENGINE_BUCKETED probes partitioned by 32 MiB filter slice and applied slice by slice out of L2 (needs numHash(dbgbf)+numHash(cbf) <= 8) */
+enum { RB_ENGINE_DIRECT = 0, RB_ENGINE_BUCKETED = 1 };
+RB_API int32_t rb_graph_set_engine(rb_graph* g, int32_t engine);                                 /* clearDbgbf/Cbf/Rpkbf/Fpkbf :211-245 */
 
 /* Bulk insert = the body of the five live insert workers (RNABloom.java:364-732,1463-1539): for every usable k-mer of
  * every read, graph.add / addCountIfPresent / addDbgOnly (graph :405-436), plus pair adds when flagged (:455-461).

@@ -18,6 +18,18 @@ pytestmark = pytest.mark.gpu
 hx = lambda s: int(s, 16)  # noqa: E731
 
 
+@pytest.fixture(autouse=True, params=["direct", "bucketed"])
+def engine(request):
+    """Every test runs once per execution engine of the read-level calls (RB_ENGINE is read when a graph is created)."""
+    old = os.environ.get("RB_ENGINE")
+    os.environ["RB_ENGINE"] = request.param
+    yield request.param
+    if old is None:
+        os.environ.pop("RB_ENGINE", None)
+    else:
+        os.environ["RB_ENGINE"] = old
+
+
 @pytest.fixture(scope="module")
 def ctx():
     c = rb.Context(0)
