@@ -212,7 +212,9 @@ typedef struct rb_shard rb_shard;
 RB_API int32_t rb_shard_create(rb_ctx* ctx, int32_t n_ranks, int32_t rank, int64_t dbgbf_bits, int64_t cbf_bytes, int32_t dbgbf_num_hash,
                                int32_t cbf_num_hash, int32_t k, int32_t stranded, int64_t max_kmers_per_round, rb_shard** out);
 RB_API int32_t rb_shard_destroy(rb_shard* sh);
-/* geom[0..7] = cap_keys, cap_dbg, cap_cbf, cap_lookup, dbg_shard_bits, cbf_shard_bytes, local_dbg_bits, local_cbf_bytes */
+/* geom[0..9] = cap_keys, cap_dbg, cap_cbf, cap_lookup (records per send region), dbg_shard_bits, cbf_shard_bytes, local_dbg_bits,
+ * local_cbf_bytes, regions_per_rank, count_stride.  A send buffer holds n_ranks * regions_per_rank regions of `cap` records, grouped by
+ * destination rank; the count array holds one int32 per region, count_stride ints apart. */
 RB_API int32_t rb_shard_geometry(rb_shard* sh, int64_t* geom);
 RB_API int32_t rb_shard_filter(rb_shard* sh, int32_t which, rb_filter** out);   /* local share as a filter handle (download, popcount) */
 RB_API int32_t rb_shard_overflow(rb_shard* sh, int32_t* flag);                  /* 1 if any send region overflowed since the last call */

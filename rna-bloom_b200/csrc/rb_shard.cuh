@@ -18,9 +18,11 @@
 
 namespace rb {
 
+constexpr int kCntStride = 32;  // ints between two region counters: one counter per 128 B line (atomics to one line serialise in L2)
+constexpr int kShardSub = 16;   // send regions per destination rank: spreads the cursor atomics (one hot counter per rank throttles at ~1.4 G/s)
 struct ShardGeom {
     int n_ranks;
-    int64_t cap;            // capacity (records) of each per-destination region of the send buffer
+    int64_t cap;            // capacity (records) of each of the n_ranks * kShardSub regions of the send buffer
     uint64_t dbg_shard;     // bits per rank of the dbgbf (multiple of 1024)
     uint64_t cbf_shard;     // bytes per rank of the cbf (multiple of 4)
 };
@@ -31,12 +33,13 @@ __device__ __forceinline__ int home_of(uint64_t key, int n_ranks) {
 }
 
 // Claims a slot of region `dest` (warp-aggregated) and returns its position in the send buffer, or -1 on overflow.
-__device__ __forceinline__ int64_t region_push(int* __restrict__ cnt, int dest, int64_t cap, int* __restrict__ overflow) {
+__device__ __forceinline__ int64_t region_push(int* __restrict__ cnt, int dest_rank, int64_t cap, int* __restrict__ overflow) {
+    const int dest = dest_rank * kShardSub + (int)(blockIdx.x % kShardSub);
     const unsigned peers = __match_any_sync(__activemask(), dest);
     const int leader = __ffs(peers) - 1;
     const int lane = threadIdx.x & 31;
     int base = 0;
-    if (lane == leader) base = atomicAdd(&cnt[dest], __popc(peers));
+    if (lane == leader) base = atomicAdd(&cnt[dest * kCntStride], __popc(peers));
     base = __shfl_sync(peers, base, leader);
     const int p = base + __popc(peers & ((1u << lane) - 1u));
     if (p >= cap) { *overflow = 1; return -1; }
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(kThreads) k_agg_insert(const int64_t* __restri
                                                         const AggTable t) {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const int src = (int)(i / sg.cap);
-    if (src >= sg.n_ranks || (i - (int64_t)src * sg.cap) >= recv_cnt[src]) return;
+    if (src >= sg.n_ranks * kShardSub || (i - (int64_t)src * sg.cap) >= recv_cnt[src * kCntStride]) return;
     const uint64_t key = (uint64_t)recv[i];
     if (key == 0) { atomicAdd(&t.counts[t.mask + 1], 1u); return; }
     uint64_t s = (key * 0x9E3779B97F4A7C15ULL) >> t.shift;
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(kThreads) k_apply_dbg(const int64_t* __restric
                                                        uint32_t* __restrict__ words, uint8_t* __restrict__ reply) {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const int src = (int)(i / sg.cap);
-    if (src >= sg.n_ranks || (i - (int64_t)src * sg.cap) >= recv_cnt[src]) return;
+    if (src >= sg.n_ranks * kShardSub || (i - (int64_t)src * sg.cap) >= recv_cnt[src * kCntStride]) return;
     const uint64_t idx = (uint64_t)recv[i];
     const uint32_t bit = 1u << (idx & 31);
     uint32_t w = ld_cg(&words[idx >> 5]);
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(kThreads) k_apply_cbf_read(const int64_t* __re
                                                             const uint32_t* __restrict__ words, uint8_t* __restrict__ reply) {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const int src = (int)(i / sg.cap);
-    if (src >= sg.n_ranks || (i - (int64_t)src * sg.cap) >= recv_cnt[src]) return;
+    if (src >= sg.n_ranks * kShardSub || (i - (int64_t)src * sg.cap) >= recv_cnt[src * kCntStride]) return;
     const uint64_t idx = (uint64_t)recv[i];
     reply[i] = (uint8_t)(ld_cg(&words[idx >> 2]) >> ((idx & 3) * 8));
 }
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(kThreads) k_apply_cbf_raise(const int64_t* __r
                                                              uint32_t* __restrict__ words) {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const int src = (int)(i / sg.cap);
-    if (src >= sg.n_ranks || (i - (int64_t)src * sg.cap) >= recv_cnt[src]) return;
+    if (src >= sg.n_ranks * kShardSub || (i - (int64_t)src * sg.cap) >= recv_cnt[src * kCntStride]) return;
     const uint64_t rec = (uint64_t)recv[i];
     const uint64_t idx = rec & 0x00FFFFFFFFFFFFFFULL;
     uint32_t* wp = &words[idx >> 2];
@@ -305,7 +308,7 @@ __global__ void __launch_bounds__(kThreads) k_apply_lookup(const int64_t* __rest
                                                           uint8_t* __restrict__ reply) {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const int src = (int)(i / sg.cap);
-    if (src >= sg.n_ranks || (i - (int64_t)src * sg.cap) >= recv_cnt[src]) return;
+    if (src >= sg.n_ranks * kShardSub || (i - (int64_t)src * sg.cap) >= recv_cnt[src * kCntStride]) return;
     const uint64_t rec = (uint64_t)recv[i];
     const uint64_t idx = rec & 0x7FFFFFFFFFFFFFFFULL;
     if (rec >> 63) reply[i] = (uint8_t)(ld_cg(&cbf_words[idx >> 2]) >> ((idx & 3) * 8));

@@ -1140,7 +1140,7 @@ struct rb_shard {
     int64_t lookup_inst;                  // instances of the last route_lookup
 };
 
-static int64_t region_cap(int64_t total, int n_ranks) { return (int64_t)((double)total / n_ranks * 1.06) + 4096; }
+static int64_t region_cap(int64_t total, int n_ranks) { return (int64_t)((double)total / (n_ranks * kShardSub) * 1.08) + 2048; }
 
 extern "C" int32_t rb_shard_create(rb_ctx* ctx, int32_t n_ranks, int32_t rank, int64_t dbg_bits, int64_t cbf_bytes, int32_t hd, int32_t hc, int32_t k,
                                    int32_t stranded, int64_t max_kmers, rb_shard** out) {
@@ -1162,10 +1162,10 @@ extern "C" int32_t rb_shard_create(rb_ctx* ctx, int32_t n_ranks, int32_t rank, i
     sh->cap_dbg = region_cap(recv_keys * hd, n_ranks);
     sh->cap_cbf = region_cap(recv_keys * hc, n_ranks);
     sh->cap_lookup = region_cap(max_kmers * (hd + hc), n_ranks);
-    if ((double)sh->cap_lookup * n_ranks > 2.0e9 || (double)sh->cap_dbg * n_ranks > 2.0e9)
+    if ((double)sh->cap_lookup * n_ranks * kShardSub > 2.0e9 || (double)sh->cap_dbg * n_ranks * kShardSub > 2.0e9)
         { delete sh; return fail(ctx, RB_EINVAL, "shard: max_kmers_per_round too large for 32-bit reply positions"); }
     int64_t T = 1024;
-    while (T < 2 * recv_keys) T <<= 1;
+    while ((double)T < 1.6 * (double)recv_keys) T <<= 1;   // linear probing at a load factor of at most 0.63
     sh->tab_slots = T + 1;
     int lg = 0; while ((1LL << lg) < T) ++lg;
     sh->tab.mask = (uint64_t)T - 1; sh->tab.shift = 64 - lg;
@@ -1206,7 +1206,7 @@ extern "C" int32_t rb_shard_destroy(rb_shard* sh) {
 extern "C" int32_t rb_shard_geometry(rb_shard* sh, int64_t* geom) {
     if (!sh || !geom) return RB_EINVAL;
     geom[0] = sh->cap_keys; geom[1] = sh->cap_dbg; geom[2] = sh->cap_cbf; geom[3] = sh->cap_lookup;
-    geom[4] = (int64_t)sh->dbg_shard; geom[5] = (int64_t)sh->cbf_shard; geom[6] = sh->dbg->size; geom[7] = sh->cbf->size;
+    geom[4] = (int64_t)sh->dbg_shard; geom[5] = (int64_t)sh->cbf_shard; geom[6] = sh->dbg->size; geom[7] = sh->cbf->size; geom[8] = kShardSub; geom[9] = kCntStride;
     return RB_OK;
 }
 extern "C" int32_t rb_shard_filter(rb_shard* sh, int32_t which, rb_filter** out) {
@@ -1225,7 +1225,7 @@ extern "C" int32_t rb_shard_overflow(rb_shard* sh, int32_t* flag) {
 }
 static ShardGeom shard_geom(const rb_shard* sh, int64_t cap) { ShardGeom g; g.n_ranks = sh->n_ranks; g.cap = cap; g.dbg_shard = sh->dbg_shard; g.cbf_shard = sh->cbf_shard; return g; }
 static int slot_grid(const rb_shard* sh) { return (int)div_up(sh->tab_slots, kThreads); }
-static int region_grid(const rb_shard* sh, int64_t cap) { return (int)div_up(cap * sh->n_ranks, kThreads); }
+static int region_grid(const rb_shard* sh, int64_t cap) { return (int)div_up(cap * sh->n_ranks * kShardSub, kThreads); }
 
 struct RouteUser { rb_shard* sh; int mode; int64_t* send; int* cnt; int64_t *fh, *rh; bool lookup; int launches; };
 static int32_t route_launch(rb_ctx* ctx, const Ingest& ing, void* user) {
@@ -1258,7 +1258,7 @@ static int32_t shard_route(rb_shard* sh, const uint64_t* packed, const uint32_t*
                            int32_t uniform_len, int64_t uniform_stride, int mode, bool lookup, int64_t* send, int32_t* cnt, int64_t* fh, int64_t* rh,
                            int64_t* n_out) {
     rb_ctx* ctx = sh->ctx;
-    CK(cudaMemsetAsync(cnt, 0, (size_t)sh->n_ranks * 4, ctx->stream));
+    CK(cudaMemsetAsync(cnt, 0, (size_t)sh->n_ranks * kShardSub * kCntStride * 4, ctx->stream));
     ReadsArg ra{packed, mask, read_off, read_len, n_reads, uniform_len, uniform_stride, true};
     RouteUser u{sh, mode, send, cnt, fh, rh, lookup, 0};
     const int64_t keep = ctx->subbatch_kmers;
@@ -1299,7 +1299,7 @@ extern "C" int32_t rb_shard_emit_dbg(rb_shard* sh, int64_t* send, int32_t* cnt) 
     if (!sh || !send || !cnt) return RB_EINVAL;
     rb_ctx* ctx = sh->ctx;
     LOCK(ctx);
-    CK(cudaMemsetAsync(cnt, 0, (size_t)sh->n_ranks * 4, ctx->stream));
+    CK(cudaMemsetAsync(cnt, 0, (size_t)sh->n_ranks * kShardSub * kCntStride * 4, ctx->stream));
     const HashMults hm = make_hm(sh->k);
     const FastMod fm = make_fm(sh->dbg_bits);
     const ShardGeom sg = shard_geom(sh, sh->cap_dbg);
@@ -1322,7 +1322,7 @@ extern "C" int32_t rb_shard_emit_cbf_reads(rb_shard* sh, const uint8_t* reply_ho
     if (!sh || !reply_home || !send || !cnt) return RB_EINVAL;
     rb_ctx* ctx = sh->ctx;
     LOCK(ctx);
-    CK(cudaMemsetAsync(cnt, 0, (size_t)sh->n_ranks * 4, ctx->stream));
+    CK(cudaMemsetAsync(cnt, 0, (size_t)sh->n_ranks * kShardSub * kCntStride * 4, ctx->stream));
     const HashMults hm = make_hm(sh->k);
     const FastMod fm = make_fm(sh->cbf_bytes);
     const ShardGeom sg = shard_geom(sh, sh->cap_cbf);
@@ -1344,7 +1344,7 @@ extern "C" int32_t rb_shard_emit_cbf_raises(rb_shard* sh, const uint8_t* reply_h
     if (!sh || !reply_home || !send || !cnt) return RB_EINVAL;
     rb_ctx* ctx = sh->ctx;
     LOCK(ctx);
-    CK(cudaMemsetAsync(cnt, 0, (size_t)sh->n_ranks * 4, ctx->stream));
+    CK(cudaMemsetAsync(cnt, 0, (size_t)sh->n_ranks * kShardSub * kCntStride * 4, ctx->stream));
     const HashMults hm = make_hm(sh->k);
     const FastMod fm = make_fm(sh->cbf_bytes);
     const ShardGeom sg = shard_geom(sh, sh->cap_cbf);
@@ -1433,7 +1433,7 @@ static int32_t bucket_engine_get(rb_graph* g, int64_t n_round, BucketEngine** ou
     auto alloc_regions = [&](Regions* r, int n, int64_t cap, int rec_bytes) -> cudaError_t {
         r->n = n; r->cap = cap / kSub + 4096;   // capacity of each of the kSub sub-regions
         cudaError_t er = cudaMalloc(&r->data, (size_t)n * kSub * (size_t)r->cap * rec_bytes);
-        if (er == cudaSuccess) er = cudaMalloc(&r->count, (size_t)kMaxCursorRegions * kSub * 4);
+        if (er == cudaSuccess) er = cudaMalloc(&r->count, (size_t)kMaxCursorRegions * kSub * kCursorPad * 4);
         return er;
     };
     auto alloc_plan = [&](SortPlan* p, int R, int64_t records) -> cudaError_t {
@@ -1539,7 +1539,7 @@ static int32_t bucket_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     const HashMults hm = make_hm(g->k);
     // B1 keys by range (cursor scatter)
     Regions keys = e->keys; keys.n = bg.n_key_ranges;
-    CK(cudaMemsetAsync(keys.count, 0, (size_t)keys.n * kSub * 4, ctx->stream));
+    CK(cudaMemsetAsync(keys.count, 0, (size_t)keys.n * kSub * kCursorPad * 4, ctx->stream));
     const int grid_pos = (int)div_up(div_up(ing.n_pos, kChunk), kThreads);
     const size_t sm_keys = (size_t)keys.n * 8;
     if (mode == RB_MODE_FWD) kb_route_keys<0><<<grid_pos, kThreads, sm_keys, ctx->stream>>>(ing, g->k, bg, keys, e->overflow);
@@ -1593,7 +1593,7 @@ static int32_t bucket_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     if (with_cbf) {
         // B5 + B6
         Regions raises = e->raises; raises.n = bg.n_cbf_slices;
-        CK(cudaMemsetAsync(raises.count, 0, (size_t)raises.n * kSub * 4, ctx->stream));
+        CK(cudaMemsetAsync(raises.count, 0, (size_t)raises.n * kSub * kCursorPad * 4, ctx->stream));
         const uint64_t seed = ctx->rng_seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(ctx->launches + 1);
         const size_t sm_c = ((size_t)1 << kIdRangeLog2) * 8 + (size_t)raises.n * 8;
         if (g->hc <= 4) {

@@ -31,10 +31,10 @@ class GpuBackend:
         h = C.c_void_p()
         ctx.check(self.L.rb_shard_create(ctx.h, n_ranks, rank, dbg_bits, cbf_bytes, hd, hc, k, int(stranded), max_kmers_per_round, C.byref(h)))
         self.h = h
-        geom = (C.c_int64 * 8)()
+        geom = (C.c_int64 * 10)()
         ctx.check(self.L.rb_shard_geometry(self.h, geom))
         (self.cap_keys, self.cap_dbg, self.cap_cbf, self.cap_lookup, self.dbg_shard, self.cbf_shard, self.local_dbg_bits,
-         self.local_cbf_bytes) = [int(x) for x in geom]
+         self.local_cbf_bytes, self.regions_per_rank, self.count_stride) = [int(x) for x in geom]
         self.device = torch.device("cuda", ctx.device)
         # kernels, torch tensor ops and the NCCL exchanges are all ordered on one (non-default) stream
         self.stream = torch.cuda.Stream(device=self.device)
@@ -115,12 +115,14 @@ class ShardedGraph:
     def __init__(self, backend, rank, world, group=None):
         self.be, self.rank, self.world, self.group = backend, rank, world, group
         self.cap_max = max(backend.cap_keys, backend.cap_dbg, backend.cap_cbf, backend.cap_lookup)
+        self.rpr = getattr(backend, "regions_per_rank", 1)   # send regions per destination rank
+        cs = getattr(backend, "count_stride", 1)
         dev = backend.device
-        n = world * self.cap_max
+        n = world * self.rpr * self.cap_max
         self.send = torch.empty(n, dtype=torch.int64, device=dev)
         self.recv = self.send if world == 1 else torch.empty(n, dtype=torch.int64, device=dev)
-        self.cnt_s = torch.zeros(world, dtype=torch.int32, device=dev)
-        self.cnt_r = self.cnt_s if world == 1 else torch.zeros(world, dtype=torch.int32, device=dev)
+        self.cnt_s = torch.zeros(world * self.rpr * cs, dtype=torch.int32, device=dev)
+        self.cnt_r = self.cnt_s if world == 1 else torch.zeros(world * self.rpr * cs, dtype=torch.int32, device=dev)
         self.reply = torch.empty(n, dtype=torch.uint8, device=dev)
         self.reply_home = self.reply if world == 1 else torch.empty(n, dtype=torch.uint8, device=dev)
         self.exchanged_bytes = 0
@@ -130,7 +132,7 @@ class ShardedGraph:
         """send regions [world][cap] + counts -> owners."""
         if self.world == 1:
             return
-        n = self.world * cap
+        n = self.world * self.rpr * cap
         dist.all_to_all_single(self.cnt_r, self.cnt_s, group=self.group)
         dist.all_to_all_single(self.recv[:n], self.send[:n], group=self.group)
         self.exchanged_bytes += n * 8
@@ -139,7 +141,7 @@ class ShardedGraph:
         """reply regions travel back to where the probes came from (same offsets)."""
         if self.world == 1:
             return
-        n = self.world * cap
+        n = self.world * self.rpr * cap
         dist.all_to_all_single(self.reply_home[:n], self.reply[:n], group=self.group)
         self.exchanged_bytes += n
 
