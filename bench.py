@@ -240,8 +240,12 @@ def main():
     if not args.no_e2e:
         e_steps = max(2, min(args.steps, 5))
         h_packed = [ctx.host_alloc(words * 8, np.uint64) for _ in range(e_steps + 1)]
-        for i, hp in enumerate(h_packed):
-            ctx.d2h(hp, batches[i % n_batches])       # the same synthetic reads, now living in pinned host memory
+        tmp = ctx.dev_alloc(words * 8 + 64)
+        for i, hp in enumerate(h_packed):   # fresh reads (ids after the timed ones), generated on the device, parked in pinned host memory
+            ctx.synth_reads_dev(SEED, args.genome, (total_steps + i) * n_reads, n_reads, READ_LEN, ERR_PPM, STRIDE, tmp)
+            ctx.sync()
+            ctx.d2h(hp, tmp)
+        ctx.dev_free(tmp)
         h_counts = ctx.host_alloc(nk * 4, np.float32)
         reads = [rb.PackedReads(hp, None, None, None, n_reads, READ_LEN, STRIDE) for hp in h_packed]
         from rnabloom_b200.filters import _ptr

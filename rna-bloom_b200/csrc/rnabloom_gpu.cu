@@ -32,8 +32,12 @@ struct rb_ctx {
     int64_t claim_cap = 0, claim_used = 0;
     const void* claim_owner = nullptr;  // the bit array the current claims refer to
     // staging (host-pointer entry points)
-    void* stage[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    int64_t stage_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void* stage[16] = {};
+    int64_t stage_bytes[16] = {};
+    cudaStream_t copy_stream = nullptr;             // D2H of lookup results overlaps the next launch
+    cudaEvent_t ev_kernel[2] = {nullptr, nullptr};  // kernel of parity p finished (results ready in staging p)
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};    // D2H out of staging p finished (staging p reusable)
+    int64_t count_launch_index = 0;
     unsigned long long* scratch = nullptr;  // 8-byte device scalar
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -121,6 +125,11 @@ extern "C" int32_t rb_ctx_create(int32_t device, rb_ctx** out) {
     // the whole 128 B line (measured 4x DRAM over-fetch otherwise; profiles/r01_notes.md).  Process-wide device limit.
     if (!getenv("RB_KEEP_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&c->ev_kernel[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&c->scratch, 64);
     if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, RB_ECUDA, m); }
     c->stream = c->own_stream;
@@ -132,7 +141,10 @@ extern "C" int32_t rb_ctx_destroy(rb_ctx* ctx) {
     {
         LOCK(ctx);
         cudaStreamSynchronize(ctx->stream);
-        for (int i = 0; i < 8; ++i) if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+        if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+        for (int i = 0; i < 16; ++i) if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+        for (int i = 0; i < 2; ++i) { if (ctx->ev_kernel[i]) cudaEventDestroy(ctx->ev_kernel[i]); if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]); }
+        if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
         if (ctx->claim) cudaFree(ctx->claim);
         if (ctx->scratch) cudaFree(ctx->scratch);
         if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
@@ -216,6 +228,7 @@ static int32_t stage_get(rb_ctx* ctx, int slot, int64_t bytes, void** p) {
     bytes = std::max<int64_t>(bytes, 256);
     if (ctx->stage_bytes[slot] < bytes) {
         CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaStreamSynchronize(ctx->copy_stream));
         if (ctx->stage[slot]) CK(cudaFree(ctx->stage[slot]));
         ctx->stage[slot] = nullptr; ctx->stage_bytes[slot] = 0;
         const int64_t want = bytes + bytes / 4 + 256;
@@ -616,9 +629,8 @@ static int32_t for_each_launch(rb_ctx* ctx, const ReadsArg& ra, int span, Launch
                     }
                     ing.first_base = b_lo;
                 }
-                const int32_t rc = fn(ctx, ing, user);
+                const int32_t rc = fn(ctx, ing, user);   // staging reuse is safe: copies and kernels are ordered on one stream
                 if (rc) return rc;
-                if (!ra.on_device) CK(cudaStreamSynchronize(ctx->stream));  // staging is reused by the next launch
             }
         }
     } else {
@@ -670,7 +682,6 @@ static int32_t for_each_launch(rb_ctx* ctx, const ReadsArg& ra, int span, Launch
                 }
                 rc = fn(ctx, ing, user);
                 if (rc) return rc;
-                CK(cudaStreamSynchronize(ctx->stream));  // staging (slot 2 at least) is reused by the next launch
             }
             r0 = r1;
         }
@@ -978,12 +989,15 @@ static int32_t count_launch(rb_ctx* ctx, const Ingest& ing_in, void* user) {
     Ingest ing = ing_in;
     float* dc = u->counts; int64_t *df = u->fh, *dr = u->rh;
     const int64_t out0 = ing.out_base;
-    if (!u->on_device) {  // results go through device staging, indexed by launch-local position
+    const int par = (int)(ctx->count_launch_index++ & 1);
+    if (!u->on_device) {  // results go through device staging (double buffered), indexed by launch-local position
         ing.out_base = 0;
         int32_t rc; void* p;
-        if (u->counts) { rc = stage_get(ctx, 5, ing.n_pos * 4, &p); if (rc) return rc; dc = (float*)p; }
-        if (u->fh) { rc = stage_get(ctx, 6, ing.n_pos * 8, &p); if (rc) return rc; df = (int64_t*)p; }
-        if (u->rh) { rc = stage_get(ctx, 7, ing.n_pos * 8, &p); if (rc) return rc; dr = (int64_t*)p; }
+        const int s0 = par ? 8 : 5;
+        if (u->counts) { rc = stage_get(ctx, s0, ing.n_pos * 4, &p); if (rc) return rc; dc = (float*)p; }
+        if (u->fh) { rc = stage_get(ctx, s0 + 1, ing.n_pos * 8, &p); if (rc) return rc; df = (int64_t*)p; }
+        if (u->rh) { rc = stage_get(ctx, s0 + 2, ing.n_pos * 8, &p); if (rc) return rc; dr = (int64_t*)p; }
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[par], 0));   // the previous D2H out of this staging set is done
     }
     bool bucketed_done = false;
     if (u->g->engine == RB_ENGINE_BUCKETED && u->g->hd + u->g->hc <= 8 && dc) {
@@ -1000,10 +1014,13 @@ static int32_t count_launch(rb_ctx* ctx, const Ingest& ing_in, void* user) {
     else if (maxh <= 4) launch_count_mode<4>(u->mode, grid, ctx->stream, ing, gd, dc, df, dr);
     else launch_count_mode<8>(u->mode, grid, ctx->stream, ing, gd, dc, df, dr);
     if (!bucketed_done) LAUNCH_CHECK();
-    if (!u->on_device) {
-        if (u->counts) CK(cudaMemcpyAsync(u->counts + out0, dc, (size_t)ing.n_pos * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        if (u->fh) CK(cudaMemcpyAsync(u->fh + out0, df, (size_t)ing.n_pos * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        if (u->rh) CK(cudaMemcpyAsync(u->rh + out0, dr, (size_t)ing.n_pos * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!u->on_device) {   // D2H on the copy stream: overlaps the next launch's kernel
+        CK(cudaEventRecord(ctx->ev_kernel[par], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kernel[par], 0));
+        if (u->counts) CK(cudaMemcpyAsync(u->counts + out0, dc, (size_t)ing.n_pos * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (u->fh) CK(cudaMemcpyAsync(u->fh + out0, df, (size_t)ing.n_pos * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (u->rh) CK(cudaMemcpyAsync(u->rh + out0, dr, (size_t)ing.n_pos * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_copy[par], ctx->copy_stream));
     }
     return RB_OK;
 }
@@ -1019,8 +1036,9 @@ extern "C" int32_t rb_graph_count_reads(rb_graph* g, const uint64_t* packed, con
     LOCK(ctx);
     ReadsArg ra{packed, mask, read_off, read_len, n_reads, uniform_len, uniform_stride, false};
     const int32_t rc = graph_count_reads(g, ra, counts, fhash, rhash, n_kmers_out);
-    if (rc) return rc;
+    if (rc) { cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->copy_stream); return rc; }
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
     return RB_OK;
 }
 extern "C" int32_t rb_graph_count_reads_dev(rb_graph* g, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off,
