@@ -7,7 +7,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 _SO = os.path.join(_HERE, "librnabloom_gpu.so")
-_SRC = [os.path.join(_HERE, "csrc", n) for n in ("rnabloom_gpu.cu", "rb_kernels.cuh", "rb_device.cuh")] + [
+_SRC = [os.path.join(_HERE, "csrc", n) for n in ("rnabloom_gpu.cu", "rb_kernels.cuh", "rb_device.cuh", "rb_shard.cuh", "rb_bucket.cuh")] + [
     os.path.join(_ROOT, "include", "rnabloom_gpu.h")]
 
 RB_BLOOM, RB_COUNTING = 0, 1
@@ -110,6 +110,7 @@ def lib():
         "rb_graph_set_distances": (i32, [vp, i32, i32]),
         "rb_graph_filter": (i32, [vp, i32, C.POINTER(vp)]),
         "rb_graph_clear": (i32, [vp]),
+        "rb_graph_set_engine": (i32, [vp, i32]),
         "rb_graph_add_reads": (i32, [vp] + reads + [u32, C.POINTER(i64)]),
         "rb_graph_add_reads_dev": (i32, [vp] + reads + [u32, C.POINTER(i64)]),
         "rb_graph_add_reads_ascii": (i32, [vp, vp, vp, vp, i64, i32, u32, C.POINTER(i64)]),
