@@ -160,8 +160,11 @@ RB_API int32_t rb_graph_filter(rb_graph* g, int32_t which, rb_filter** out); /* 
 RB_API int32_t rb_graph_clear(rb_graph* g);
 /* Execution engine of the read-level insert/lookup calls (same results, different HBM schedule):
  *   RB_ENGINE_DIRECT   one fused kernel, every probe an isolated HBM sector access (bounded by DRAM row activations)
- *   RB_ENGINE_BUCKETED probes partitioned by 32 MiB filter slice and applied slice by slice out of L2 (needs numHash(dbgbf)+numHash(cbf) <= 8) */
-enum { RB_ENGINE_DIRECT = 0, RB_ENGINE_BUCKETED = 1 };
+ *   RB_ENGINE_BUCKETED probes partitioned by 32 MiB filter slice and applied slice by slice out of L2 (needs numHash(dbgbf)+numHash(cbf) <= 8)
+ *   RB_ENGINE_SLICED   probes tile-sorted by 64 MiB filter slice, applied slice by slice out of L2, answers gathered through
+ *                      remembered positions; rounds of up to 2^29 k-mers (needs numHash(dbgbf) <= 3 and numHash(cbf) <= 3,
+ *                      otherwise the direct engine serves the call) */
+enum { RB_ENGINE_DIRECT = 0, RB_ENGINE_BUCKETED = 1, RB_ENGINE_SLICED = 2 };
 RB_API int32_t rb_graph_set_engine(rb_graph* g, int32_t engine);                                 /* clearDbgbf/Cbf/Rpkbf/Fpkbf :211-245 */
 
 /* Bulk insert = the body of the five live insert workers (RNABloom.java:364-732,1463-1539): for every usable k-mer of

@@ -7,7 +7,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 _SO = os.path.join(_HERE, "librnabloom_gpu.so")
-_SRC = [os.path.join(_HERE, "csrc", n) for n in ("rnabloom_gpu.cu", "rb_kernels.cuh", "rb_device.cuh", "rb_shard.cuh", "rb_bucket.cuh")] + [
+_SRC = [os.path.join(_HERE, "csrc", n) for n in ("rnabloom_gpu.cu", "rb_kernels.cuh", "rb_device.cuh", "rb_shard.cuh", "rb_bucket.cuh", "rb_sliced.cuh",
+                                                 "rb_sliced_host.inl")] + [
     os.path.join(_ROOT, "include", "rnabloom_gpu.h")]
 
 RB_BLOOM, RB_COUNTING = 0, 1
@@ -57,7 +58,14 @@ def lib():
         return _lib
     if not os.path.exists(_SO):
         raise RBError(-3, "librnabloom_gpu.so is not built (run __graft_entry__.build()); there is no CPU fallback")
-    L = C.CDLL(_SO)
+    _lib = bind(_SO)
+    return _lib
+
+
+def bind(path, allow_missing=False):
+    """dlopen `path` and declare the signature of every entry point.  allow_missing is for the host-emulation build of the
+    kernels that tests/test_emu_parity.py uses (it has no sharded pipeline); the product library must export everything."""
+    L = C.CDLL(path)
     vp, i64, i32, u32, u64, f32, cp = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_uint64, C.c_float, C.c_char_p
     reads = [vp, vp, vp, vp, i64, i32, i64]  # packed, mask, read_off, read_len, n_reads, uniform_len, uniform_stride
     sigs = {
@@ -141,9 +149,10 @@ def lib():
         "rb_synth_reads_dev": (i32, [vp, u64, u64, u64, i64, i32, u32, i64, vp]),
     }
     for name, (res, args) in sigs.items():
+        if allow_missing and not hasattr(L, name):
+            continue
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
     L._sigs = sigs
-    _lib = L
     return L

@@ -216,7 +216,7 @@ struct CtaScatter {
 // ---- B1: k-merise, scatter every usable k-mer's base hash by key range ---------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(kThreads) kb_route_keys(const Ingest g, int k, const BucketGeom bg, const Regions out, int* overflow) {
-    extern __shared__ unsigned int smem[];
+    RB_DYN_SMEM(unsigned int, smem);
     __shared__ RollLut lut;
     build_lut(&lut, k);
     const int64_t pos = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * kChunk;
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kThreads) kb_aggregate(const Regions in, const
 // ---- B3: one probe per (distinct key, hash); counting sort by filter slice -------------------------------------------------------------
 template <int MAXJ, int PASS>   // MAXJ >= hd + hc
 __global__ void __launch_bounds__(kThreads) kb_emit_probes(const AggTable2 t, const HashMults hm, const BucketGeom bg, int with_cbf, const SortPlan plan) {
-    extern __shared__ unsigned int smem[];
+    RB_DYN_SMEM(unsigned int, smem);
     SortWriter<uint64_t, PASS> sw;
     sw.begin(smem, plan);
     const int64_t total = (int64_t)t.zero_slot + 1;
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(kThreads) kb_emit_probes(const AggTable2 t, co
 template <int MODE, int MAXJ, int PASS>
 __global__ void __launch_bounds__(kThreads) kb_route_lookup(const Ingest g, int k, const HashMults hm, const BucketGeom bg, const SortPlan plan,
                                                            uint8_t* __restrict__ usable, int64_t* __restrict__ fhash, int64_t* __restrict__ rhash) {
-    extern __shared__ unsigned int smem[];
+    RB_DYN_SMEM(unsigned int, smem);
     __shared__ RollLut lut;
     build_lut(&lut, k);
     SortWriter<uint64_t, PASS> sw;
@@ -338,7 +338,7 @@ template <int PASS, int SET>
 __global__ void __launch_bounds__(kThreads) kb_apply_probes(const SortPlan in, const BucketGeom bg, uint32_t* __restrict__ dbg_words,
                                                            const uint32_t* __restrict__ cbf_words, int64_t dbg_bytes, int64_t cbf_bytes,
                                                            int want_answers, const SortPlan out, unsigned int* done) {
-    extern __shared__ unsigned int smem[];
+    RB_DYN_SMEM(unsigned int, smem);
     constexpr int U = 4;   // probes in flight per thread
     SortWriter<uint32_t, PASS> sw;
     if (want_answers) sw.begin(smem, out);
@@ -417,7 +417,7 @@ constexpr int kCombineThreads = 1024;
 template <int MAXH>
 __global__ void __launch_bounds__(kCombineThreads) kb_combine_insert(const SortPlan in, const AggTable2 t, const HashMults hm, const BucketGeom bg, int policy,
                                                              uint64_t rng_seed, const Regions out, int* overflow) {
-    extern __shared__ unsigned int smem[];
+    RB_DYN_SMEM(unsigned int, smem);
     uint8_t* ans = reinterpret_cast<uint8_t*>(smem);                         // 128 KiB
     unsigned int* sc_mem = smem + (1 << kIdRangeLog2) * 2;                   // scatter bins behind it
     const int64_t total = (int64_t)t.zero_slot + 1;
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(kThreads) kb_apply_raises(const Regions in, ui
 // ---- B8: per instance range: gather the answers, write the counts (graph :562-570) ---------------------------------------------------------------
 __global__ void __launch_bounds__(kCombineThreads) kb_combine_lookup(const SortPlan in, int64_t n_inst, int hd, int hc, const uint8_t* __restrict__ usable,
                                                              float* __restrict__ counts, int64_t out_base) {
-    extern __shared__ unsigned int smem[];
+    RB_DYN_SMEM(unsigned int, smem);
     uint8_t* ans = reinterpret_cast<uint8_t*>(smem);
     for (int r = blockIdx.x; r < in.R; r += gridDim.x) {
         gather_answers(in, r, ans);

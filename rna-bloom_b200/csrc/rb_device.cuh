@@ -3,8 +3,16 @@
 // Everything here is integer / bitwise work bounded by HBM random-sector traffic (no tensor cores).
 // Citations are relative to /root/reference/src/rnabloom/.
 #pragma once
-#include <cuda_runtime.h>
 #include <stdint.h>
+#ifdef RB_EMU
+// host emulation of the kernels for logic tests without a GPU (tests/emu/cuda_emu.h; never part of the product library)
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+// RB_LAUNCH(grid, block, dynamic smem bytes, stream, kernel)(args...);  the kernel goes last so template commas survive the preprocessor
+#define RB_LAUNCH(grid, block, smem, stream, ...) __VA_ARGS__<<<(grid), (block), (smem), (stream)>>>
+#define RB_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#endif
 
 namespace rb {
 

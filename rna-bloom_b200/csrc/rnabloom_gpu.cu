@@ -3,8 +3,11 @@
 // if CUDA is unavailable every entry point fails with RB_ECUDA.  Citations: /root/reference/src/rnabloom/.
 #include "../../include/rnabloom_gpu.h"
 #include "rb_kernels.cuh"
+#include "rb_sliced.cuh"
+#ifndef RB_EMU   // the host emulation (tests/emu) covers the direct and the sliced engine only
 #include "rb_shard.cuh"
 #include "rb_bucket.cuh"
+#endif
 
 #include <algorithm>
 #include <cmath>
@@ -25,6 +28,7 @@ struct rb_ctx {
     std::string err;
     uint64_t rng_seed = 0x243F6A8885A308D3ULL;
     int64_t subbatch_kmers = 1LL << 25;
+    bool subbatch_user_set = false;   // the sliced engine picks its own (much larger) round size unless the caller chose one
     int64_t launches = 0;
     int sm_count = 148;
     // claim table (DESIGN.md "Linearisation")
@@ -52,6 +56,7 @@ struct rb_filter {
     bool in_graph;
 };
 struct BucketEngine;
+struct SlicedEngine;
 struct rb_graph {
     rb_ctx* ctx;
     rb_filter *dbg, *cbf, *rpk, *fpk;
@@ -59,6 +64,7 @@ struct rb_graph {
     int d_read, d_frag;
     int engine;            // RB_ENGINE_DIRECT / RB_ENGINE_BUCKETED
     BucketEngine* be;      // lazily built
+    SlicedEngine* se;      // lazily built
 };
 
 static thread_local std::string g_create_err;
@@ -172,6 +178,7 @@ extern "C" int32_t rb_ctx_set_subbatch_kmers(rb_ctx* ctx, int64_t kmers) {
     if (!ctx || kmers < 1024) return RB_EINVAL;
     LOCK(ctx);
     ctx->subbatch_kmers = kmers;
+    ctx->subbatch_user_set = true;
     return RB_OK;
 }
 extern "C" int64_t rb_ctx_kernel_launches(rb_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -379,10 +386,10 @@ static GraphDev filter_view(rb_filter* f) {  // a lone filter seen through the g
 template <int OP>
 static void launch_hash_op(int maxh, int64_t n, cudaStream_t s, const int64_t* base, const GraphDev& gd, uint8_t* o8, float* of) {
     const int grid = (int)div_up(n, kThreads);
-    if (maxh <= 2) k_hash_op<2, OP><<<grid, kThreads, 0, s>>>(base, n, gd, o8, of);
-    else if (maxh <= 3) k_hash_op<3, OP><<<grid, kThreads, 0, s>>>(base, n, gd, o8, of);
-    else if (maxh <= 4) k_hash_op<4, OP><<<grid, kThreads, 0, s>>>(base, n, gd, o8, of);
-    else k_hash_op<8, OP><<<grid, kThreads, 0, s>>>(base, n, gd, o8, of);
+    if (maxh <= 2) RB_LAUNCH(grid, kThreads, 0, s, k_hash_op<2, OP>)(base, n, gd, o8, of);
+    else if (maxh <= 3) RB_LAUNCH(grid, kThreads, 0, s, k_hash_op<3, OP>)(base, n, gd, o8, of);
+    else if (maxh <= 4) RB_LAUNCH(grid, kThreads, 0, s, k_hash_op<4, OP>)(base, n, gd, o8, of);
+    else RB_LAUNCH(grid, kThreads, 0, s, k_hash_op<8, OP>)(base, n, gd, o8, of);
 }
 static void dispatch_hash_op(int op, int maxh, int64_t n, cudaStream_t s, const int64_t* base, const GraphDev& gd, uint8_t* o8, float* of) {
     switch (op) {
@@ -439,8 +446,8 @@ extern "C" int32_t rb_filter_popcount(rb_filter* f, int64_t* out) {
     CK(cudaMemsetAsync(ctx->scratch, 0, 8, ctx->stream));
     const int64_t n_vec = f->alloc / 16;  // the padding beyond nbytes is always zero
     const int grid = (int)std::min<int64_t>(div_up(n_vec, kThreads), (int64_t)ctx->sm_count * 16);
-    if (f->kind == RB_BLOOM) k_popcount<0><<<grid, kThreads, 0, ctx->stream>>>((const uint4*)f->dev, n_vec, ctx->scratch);
-    else k_popcount<1><<<grid, kThreads, 0, ctx->stream>>>((const uint4*)f->dev, n_vec, ctx->scratch);
+    if (f->kind == RB_BLOOM) RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_popcount<0>)((const uint4*)f->dev, n_vec, ctx->scratch);
+    else RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_popcount<1>)((const uint4*)f->dev, n_vec, ctx->scratch);
     LAUNCH_CHECK();
     unsigned long long v = 0;
     CK(cudaMemcpyAsync(&v, ctx->scratch, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -578,7 +585,7 @@ extern "C" int32_t rb_index_hashes(rb_ctx* ctx, const int64_t* hash, int64_t n, 
     int32_t rc = stage_get(ctx, 0, n * 8, &din); if (rc) return rc;
     rc = stage_get(ctx, 1, n * 8, &dout); if (rc) return rc;
     CK(cudaMemcpyAsync(din, hash, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    k_index<<<(int)div_up(n, kThreads), kThreads, 0, ctx->stream>>>((const int64_t*)din, n, make_fm(size), (int64_t*)dout);
+    RB_LAUNCH((int)div_up(n, kThreads), kThreads, 0, ctx->stream, k_index)((const int64_t*)din, n, make_fm(size), (int64_t*)dout);
     LAUNCH_CHECK();
     CK(cudaMemcpyAsync(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -707,13 +714,13 @@ static int32_t kmerize_launch(rb_ctx* ctx, const Ingest& ing, void* user) {
     if (u->pairs) {
         GraphDev gd; memset(&gd, 0, sizeof gd); gd.k = u->k; gd.hm = make_hm(u->k);
         BitFilter none; memset(&none, 0, sizeof none);
-        if (u->mode == RB_MODE_FWD) k_pairs<0, 2, 0><<<grid, kThreads, 0, ctx->stream>>>(g, gd, none, u->d, db);
-        else if (u->mode == RB_MODE_RC) k_pairs<1, 2, 0><<<grid, kThreads, 0, ctx->stream>>>(g, gd, none, u->d, db);
-        else k_pairs<2, 2, 0><<<grid, kThreads, 0, ctx->stream>>>(g, gd, none, u->d, db);
+        if (u->mode == RB_MODE_FWD) RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_pairs<0, 2, 0>)(g, gd, none, u->d, db);
+        else if (u->mode == RB_MODE_RC) RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_pairs<1, 2, 0>)(g, gd, none, u->d, db);
+        else RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_pairs<2, 2, 0>)(g, gd, none, u->d, db);
     } else {
-        if (u->mode == RB_MODE_FWD) k_kmerize<0><<<grid, kThreads, 0, ctx->stream>>>(g, u->k, df, dr, db);
-        else if (u->mode == RB_MODE_RC) k_kmerize<1><<<grid, kThreads, 0, ctx->stream>>>(g, u->k, df, dr, db);
-        else k_kmerize<2><<<grid, kThreads, 0, ctx->stream>>>(g, u->k, df, dr, db);
+        if (u->mode == RB_MODE_FWD) RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_kmerize<0>)(g, u->k, df, dr, db);
+        else if (u->mode == RB_MODE_RC) RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_kmerize<1>)(g, u->k, df, dr, db);
+        else RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_kmerize<2>)(g, u->k, df, dr, db);
     }
     LAUNCH_CHECK();
     if (u->hf) CK(cudaMemcpyAsync(u->hf + out0, df, (size_t)ing.n_pos * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -763,13 +770,14 @@ extern "C" int32_t rb_graph_create(rb_ctx* ctx, int64_t dbg_bits, int64_t cbf_by
     g->dbg->in_graph = g->cbf->in_graph = true;
     if (g->rpk) g->rpk->in_graph = true;
     const char* eng = getenv("RB_ENGINE");
-    g->engine = (eng && !strcmp(eng, "bucketed")) ? RB_ENGINE_BUCKETED : RB_ENGINE_DIRECT;
+    g->engine = (eng && !strcmp(eng, "bucketed")) ? RB_ENGINE_BUCKETED : (eng && !strcmp(eng, "sliced")) ? RB_ENGINE_SLICED : RB_ENGINE_DIRECT;
     *out = g;
     return RB_OK;
 }
 static void bucket_engine_free(rb_graph* g);
+static void sliced_engine_free(rb_graph* g);
 extern "C" int32_t rb_graph_set_engine(rb_graph* g, int32_t engine) {
-    if (!g || (engine != RB_ENGINE_DIRECT && engine != RB_ENGINE_BUCKETED)) return RB_EINVAL;
+    if (!g || (engine != RB_ENGINE_DIRECT && engine != RB_ENGINE_BUCKETED && engine != RB_ENGINE_SLICED)) return RB_EINVAL;
     LOCK(g->ctx);
     g->engine = engine;
     return RB_OK;
@@ -778,6 +786,7 @@ extern "C" int32_t rb_graph_destroy(rb_graph* g) {
     if (!g) return RB_EINVAL;
     LOCK(g->ctx);
     bucket_engine_free(g);
+    sliced_engine_free(g);
     if (g->dbg) filter_free(g->dbg);
     if (g->cbf) filter_free(g->cbf);
     if (g->rpk) filter_free(g->rpk);
@@ -821,9 +830,9 @@ static BitFilter bit_view(rb_filter* f) { BitFilter b; b.words = f->dev; b.fm = 
 
 template <int MODE, int MAXH>
 static void launch_insert(int policy, int grid, cudaStream_t s, const Ingest& ing, const GraphDev& gd) {
-    if (policy == POLICY_ADD) k_graph_insert<MODE, MAXH, POLICY_ADD><<<grid, kThreads, 0, s>>>(ing, gd);
-    else if (policy == POLICY_COUNT_IF_PRESENT) k_graph_insert<MODE, MAXH, POLICY_COUNT_IF_PRESENT><<<grid, kThreads, 0, s>>>(ing, gd);
-    else k_graph_insert<MODE, MAXH, POLICY_DBG_ONLY><<<grid, kThreads, 0, s>>>(ing, gd);
+    if (policy == POLICY_ADD) RB_LAUNCH(grid, kThreads, 0, s, k_graph_insert<MODE, MAXH, POLICY_ADD>)(ing, gd);
+    else if (policy == POLICY_COUNT_IF_PRESENT) RB_LAUNCH(grid, kThreads, 0, s, k_graph_insert<MODE, MAXH, POLICY_COUNT_IF_PRESENT>)(ing, gd);
+    else RB_LAUNCH(grid, kThreads, 0, s, k_graph_insert<MODE, MAXH, POLICY_DBG_ONLY>)(ing, gd);
 }
 template <int MAXH>
 static void launch_insert_mode(int mode, int policy, int grid, cudaStream_t s, const Ingest& ing, const GraphDev& gd) {
@@ -833,8 +842,22 @@ static void launch_insert_mode(int mode, int policy, int grid, cudaStream_t s, c
 }
 struct InsertUser { rb_graph* g; int mode, policy; };
 static int32_t bucket_insert_round(rb_graph* g, const Ingest& ing, int mode, int policy, bool* fell_back);
+static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int policy, bool* fell_back);
+static int32_t sliced_count_round(rb_graph* g, const Ingest& ing, int mode, float* counts, int64_t* fh, int64_t* rh, bool* fell_back);
+static int64_t sliced_round_kmers(const rb_ctx* ctx);
+// the sliced engine amortises one sweep of the filters over a whole round, so its rounds are much larger than the direct launches
+struct RoundSize {
+    rb_ctx* c; int64_t keep;
+    RoundSize(rb_graph* g) : c(g->ctx), keep(g->ctx->subbatch_kmers) { if (g->engine == RB_ENGINE_SLICED) c->subbatch_kmers = sliced_round_kmers(c); }
+    ~RoundSize() { c->subbatch_kmers = keep; }
+};
 static int32_t insert_launch(rb_ctx* ctx, const Ingest& ing, void* user) {
     InsertUser* u = (InsertUser*)user;
+    if (u->g->engine == RB_ENGINE_SLICED) {
+        bool fell_back = false;
+        const int32_t rc = sliced_insert_round(u->g, ing, u->mode, u->policy, &fell_back);
+        if (rc || !fell_back) return rc;
+    }
     if (u->g->engine == RB_ENGINE_BUCKETED && u->g->hd + u->g->hc <= 8) {
         bool fell_back = false;
         const int32_t rc = bucket_insert_round(u->g, ing, u->mode, u->policy, &fell_back);
@@ -854,8 +877,8 @@ static int32_t insert_launch(rb_ctx* ctx, const Ingest& ing, void* user) {
 struct PairUser { rb_graph* g; rb_filter* pk; int mode, d, op; };
 template <int MODE, int MAXH>
 static void launch_pairs_op(int op, int grid, cudaStream_t s, const Ingest& ing, const GraphDev& gd, const BitFilter& pk, int d) {
-    if (op == 1) k_pairs<MODE, MAXH, 1><<<grid, kThreads, 0, s>>>(ing, gd, pk, d, nullptr);
-    else k_pairs<MODE, MAXH, 2><<<grid, kThreads, 0, s>>>(ing, gd, pk, d, nullptr);
+    if (op == 1) RB_LAUNCH(grid, kThreads, 0, s, k_pairs<MODE, MAXH, 1>)(ing, gd, pk, d, nullptr);
+    else RB_LAUNCH(grid, kThreads, 0, s, k_pairs<MODE, MAXH, 2>)(ing, gd, pk, d, nullptr);
 }
 template <int MAXH>
 static void launch_pairs_mode(int mode, int op, int grid, cudaStream_t s, const Ingest& ing, const GraphDev& gd, const BitFilter& pk, int d) {
@@ -886,6 +909,7 @@ static int32_t graph_add_reads(rb_graph* g, const ReadsArg& ra, uint32_t flags, 
     int64_t total = 0;
     if (!(flags & RB_PAIRS_EXISTING_ONLY)) {
         InsertUser u{g, mode, (flags & RB_DBG_ONLY) ? POLICY_DBG_ONLY : (flags & RB_ADD_COUNT_IF_PRESENT) ? POLICY_COUNT_IF_PRESENT : POLICY_ADD};
+        RoundSize rs(g);
         const int32_t rc = for_each_launch(ctx, ra, g->k, insert_launch, &u, &total);
         if (rc) return rc;
     }
@@ -962,7 +986,7 @@ extern "C" int32_t rb_graph_add_reads_ascii(rb_graph* g, const char* bases, cons
     CKF(cudaMemcpyAsync(d_ro, read_off.data(), (size_t)n_reads * 8, cudaMemcpyHostToDevice, ctx->stream));
     CKF(cudaMemcpyAsync(d_rl, read_len.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, ctx->stream));
     if (words > 0) {
-        k_pack_ascii<<<(int)div_up(words, kThreads), kThreads, 0, ctx->stream>>>(d_b - a_lo, d_q ? d_q - a_lo : nullptr, d_ao, d_wo, n_reads, words,
+        RB_LAUNCH((int)div_up(words, kThreads), kThreads, 0, ctx->stream, k_pack_ascii)(d_b - a_lo, d_q ? d_q - a_lo : nullptr, d_ao, d_wo, n_reads, words,
                                                                                  min_qual, d_packed, d_mask);
         ++ctx->launches;
         CKF(cudaGetLastError());
@@ -979,8 +1003,8 @@ extern "C" int32_t rb_graph_add_reads_ascii(rb_graph* g, const char* bases, cons
 struct CountUser { rb_graph* g; int mode; float* counts; int64_t *fh, *rh; bool on_device; };
 template <int MAXH>
 static void launch_count_mode(int mode, int grid, cudaStream_t s, const Ingest& ing, const GraphDev& gd, float* c, int64_t* f, int64_t* r) {
-    if (mode == RB_MODE_FWD) k_graph_count<0, MAXH><<<grid, kThreads, 0, s>>>(ing, gd, c, f, r);
-    else k_graph_count<2, MAXH><<<grid, kThreads, 0, s>>>(ing, gd, c, f, r);
+    if (mode == RB_MODE_FWD) RB_LAUNCH(grid, kThreads, 0, s, k_graph_count<0, MAXH>)(ing, gd, c, f, r);
+    else RB_LAUNCH(grid, kThreads, 0, s, k_graph_count<2, MAXH>)(ing, gd, c, f, r);
 }
 static int32_t bucket_count_round(rb_graph* g, const Ingest& ing, int mode, float* counts, int64_t* fh, int64_t* rh, bool* fell_back);
 static int32_t count_launch(rb_ctx* ctx, const Ingest& ing_in, void* user) {
@@ -1000,6 +1024,12 @@ static int32_t count_launch(rb_ctx* ctx, const Ingest& ing_in, void* user) {
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[par], 0));   // the previous D2H out of this staging set is done
     }
     bool bucketed_done = false;
+    if (u->g->engine == RB_ENGINE_SLICED && dc) {
+        bool fell_back = false;
+        const int32_t rc = sliced_count_round(u->g, ing, u->mode, dc, df, dr, &fell_back);
+        if (rc) return rc;
+        bucketed_done = !fell_back;
+    }
     if (u->g->engine == RB_ENGINE_BUCKETED && u->g->hd + u->g->hc <= 8 && dc) {
         bool fell_back = false;
         const int32_t rc = bucket_count_round(u->g, ing, u->mode, dc, df, dr, &fell_back);
@@ -1026,6 +1056,7 @@ static int32_t count_launch(rb_ctx* ctx, const Ingest& ing_in, void* user) {
 }
 static int32_t graph_count_reads(rb_graph* g, const ReadsArg& ra, float* counts, int64_t* fh, int64_t* rh, int64_t* n_out) {
     CountUser u{g, g->stranded ? RB_MODE_FWD : RB_MODE_CANON, counts, fh, g->stranded ? nullptr : rh, ra.on_device};
+    RoundSize rs(g);
     return for_each_launch(g->ctx, ra, g->k, count_launch, &u, n_out);
 }
 extern "C" int32_t rb_graph_count_reads(rb_graph* g, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
@@ -1137,11 +1168,18 @@ extern "C" int32_t rb_synth_reads_dev(rb_ctx* ctx, uint64_t seed, uint64_t genom
     LOCK(ctx);
     const int64_t threads = n_reads * (stride_bases >> 5);
     if (threads == 0) return RB_OK;
-    k_synth_reads<<<(int)div_up(threads, kThreads), kThreads, 0, ctx->stream>>>(seed, genome_len, first_read, n_reads, L, err_ppm, stride_bases, packed_dev);
+    RB_LAUNCH((int)div_up(threads, kThreads), kThreads, 0, ctx->stream, k_synth_reads)(seed, genome_len, first_read, n_reads, L, err_ppm, stride_bases, packed_dev);
     LAUNCH_CHECK();
     return RB_OK;
 }
 
+#include "rb_sliced_host.inl"
+
+#ifdef RB_EMU
+static void bucket_engine_free(rb_graph*) {}
+static int32_t bucket_insert_round(rb_graph*, const Ingest&, int, int, bool* fell_back) { *fell_back = true; return RB_OK; }
+static int32_t bucket_count_round(rb_graph*, const Ingest&, int, float*, int64_t*, int64_t*, bool* fell_back) { *fell_back = true; return RB_OK; }
+#else
 // ---- hash-sharded graph (one rank's share; phases of rb_shard.cuh) ---------------------------------------------------------------
 struct rb_shard {
     rb_ctx* ctx;
@@ -1256,15 +1294,15 @@ static int32_t route_launch(rb_ctx* ctx, const Ingest& ing, void* user) {
     g.out_base = 0;
     if (!u->lookup) {
         const ShardGeom sg = shard_geom(sh, sh->cap_keys);
-        if (u->mode == RB_MODE_FWD) k_route_keys<0><<<grid, kThreads, 0, ctx->stream>>>(g, sh->k, sg, u->send, u->cnt, sh->overflow);
-        else if (u->mode == RB_MODE_RC) k_route_keys<1><<<grid, kThreads, 0, ctx->stream>>>(g, sh->k, sg, u->send, u->cnt, sh->overflow);
-        else k_route_keys<2><<<grid, kThreads, 0, ctx->stream>>>(g, sh->k, sg, u->send, u->cnt, sh->overflow);
+        if (u->mode == RB_MODE_FWD) RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_route_keys<0>)(g, sh->k, sg, u->send, u->cnt, sh->overflow);
+        else if (u->mode == RB_MODE_RC) RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_route_keys<1>)(g, sh->k, sg, u->send, u->cnt, sh->overflow);
+        else RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_route_keys<2>)(g, sh->k, sg, u->send, u->cnt, sh->overflow);
     } else {
         const ShardGeom sg = shard_geom(sh, sh->cap_lookup);
         const HashMults hm = make_hm(sh->k);
         const FastMod fd = make_fm(sh->dbg_bits), fc = make_fm(sh->cbf_bytes);
         sh->lookup_inst = ing.n_pos;
-#define RL(MODE, MAXH) k_route_lookup<MODE, MAXH><<<grid, kThreads, 0, ctx->stream>>>(g, sh->k, hm, fd, fc, sh->hd, sh->hc, sg, u->send, u->cnt, sh->pos_lookup, u->fh, u->rh, sh->overflow)
+#define RL(MODE, MAXH) RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_route_lookup<MODE, MAXH>)(g, sh->k, hm, fd, fc, sh->hd, sh->hc, sg, u->send, u->cnt, sh->pos_lookup, u->fh, u->rh, sh->overflow)
         if (u->mode == RB_MODE_FWD) { if (sh->hmax <= 3) RL(0, 3); else if (sh->hmax <= 4) RL(0, 4); else RL(0, 8); }
         else { if (sh->hmax <= 3) RL(2, 3); else if (sh->hmax <= 4) RL(2, 4); else RL(2, 8); }
 #undef RL
@@ -1309,7 +1347,7 @@ extern "C" int32_t rb_shard_aggregate(rb_shard* sh, const int64_t* recv, const i
     LOCK(ctx);
     CK(cudaMemsetAsync(sh->tab.keys, 0, (size_t)sh->tab_slots * 8, ctx->stream));
     CK(cudaMemsetAsync(sh->tab.counts, 0, (size_t)sh->tab_slots * 4, ctx->stream));
-    k_agg_insert<<<region_grid(sh, sh->cap_keys), kThreads, 0, ctx->stream>>>(recv, recv_cnt, shard_geom(sh, sh->cap_keys), sh->tab);
+    RB_LAUNCH(region_grid(sh, sh->cap_keys), kThreads, 0, ctx->stream, k_agg_insert)(recv, recv_cnt, shard_geom(sh, sh->cap_keys), sh->tab);
     LAUNCH_CHECK();
     return RB_OK;
 }
@@ -1321,9 +1359,9 @@ extern "C" int32_t rb_shard_emit_dbg(rb_shard* sh, int64_t* send, int32_t* cnt) 
     const HashMults hm = make_hm(sh->k);
     const FastMod fm = make_fm(sh->dbg_bits);
     const ShardGeom sg = shard_geom(sh, sh->cap_dbg);
-    if (sh->hd <= 3) k_emit_dbg<3><<<slot_grid(sh), kThreads, 0, ctx->stream>>>(sh->tab, hm, fm, sh->hd, sg, send, cnt, sh->pos_dbg, sh->overflow);
-    else if (sh->hd <= 4) k_emit_dbg<4><<<slot_grid(sh), kThreads, 0, ctx->stream>>>(sh->tab, hm, fm, sh->hd, sg, send, cnt, sh->pos_dbg, sh->overflow);
-    else k_emit_dbg<8><<<slot_grid(sh), kThreads, 0, ctx->stream>>>(sh->tab, hm, fm, sh->hd, sg, send, cnt, sh->pos_dbg, sh->overflow);
+    if (sh->hd <= 3) RB_LAUNCH(slot_grid(sh), kThreads, 0, ctx->stream, k_emit_dbg<3>)(sh->tab, hm, fm, sh->hd, sg, send, cnt, sh->pos_dbg, sh->overflow);
+    else if (sh->hd <= 4) RB_LAUNCH(slot_grid(sh), kThreads, 0, ctx->stream, k_emit_dbg<4>)(sh->tab, hm, fm, sh->hd, sg, send, cnt, sh->pos_dbg, sh->overflow);
+    else RB_LAUNCH(slot_grid(sh), kThreads, 0, ctx->stream, k_emit_dbg<8>)(sh->tab, hm, fm, sh->hd, sg, send, cnt, sh->pos_dbg, sh->overflow);
     LAUNCH_CHECK();
     return RB_OK;
 }
@@ -1331,8 +1369,8 @@ extern "C" int32_t rb_shard_apply_dbg(rb_shard* sh, const int64_t* recv, const i
     if (!sh || !recv || !recv_cnt || !reply) return RB_EINVAL;
     rb_ctx* ctx = sh->ctx;
     LOCK(ctx);
-    if (set_bits) k_apply_dbg<1><<<region_grid(sh, sh->cap_dbg), kThreads, 0, ctx->stream>>>(recv, recv_cnt, shard_geom(sh, sh->cap_dbg), sh->dbg->dev, reply);
-    else k_apply_dbg<0><<<region_grid(sh, sh->cap_dbg), kThreads, 0, ctx->stream>>>(recv, recv_cnt, shard_geom(sh, sh->cap_dbg), sh->dbg->dev, reply);
+    if (set_bits) RB_LAUNCH(region_grid(sh, sh->cap_dbg), kThreads, 0, ctx->stream, k_apply_dbg<1>)(recv, recv_cnt, shard_geom(sh, sh->cap_dbg), sh->dbg->dev, reply);
+    else RB_LAUNCH(region_grid(sh, sh->cap_dbg), kThreads, 0, ctx->stream, k_apply_dbg<0>)(recv, recv_cnt, shard_geom(sh, sh->cap_dbg), sh->dbg->dev, reply);
     LAUNCH_CHECK();
     return RB_OK;
 }
@@ -1344,7 +1382,7 @@ extern "C" int32_t rb_shard_emit_cbf_reads(rb_shard* sh, const uint8_t* reply_ho
     const HashMults hm = make_hm(sh->k);
     const FastMod fm = make_fm(sh->cbf_bytes);
     const ShardGeom sg = shard_geom(sh, sh->cap_cbf);
-#define EC(MAXH) k_combine_dbg_emit_cbf<MAXH><<<slot_grid(sh), kThreads, 0, ctx->stream>>>(sh->tab, hm, fm, sh->hd, sh->hc, sg, sh->pos_dbg, reply_home, policy, sh->inc, send, cnt, sh->pos_cbf, sh->overflow)
+#define EC(MAXH) RB_LAUNCH(slot_grid(sh), kThreads, 0, ctx->stream, k_combine_dbg_emit_cbf<MAXH>)(sh->tab, hm, fm, sh->hd, sh->hc, sg, sh->pos_dbg, reply_home, policy, sh->inc, send, cnt, sh->pos_cbf, sh->overflow)
     if (sh->hc <= 3) EC(3); else if (sh->hc <= 4) EC(4); else EC(8);
 #undef EC
     LAUNCH_CHECK();
@@ -1354,7 +1392,7 @@ extern "C" int32_t rb_shard_apply_cbf_read(rb_shard* sh, const int64_t* recv, co
     if (!sh || !recv || !recv_cnt || !reply) return RB_EINVAL;
     rb_ctx* ctx = sh->ctx;
     LOCK(ctx);
-    k_apply_cbf_read<<<region_grid(sh, sh->cap_cbf), kThreads, 0, ctx->stream>>>(recv, recv_cnt, shard_geom(sh, sh->cap_cbf), sh->cbf->dev, reply);
+    RB_LAUNCH(region_grid(sh, sh->cap_cbf), kThreads, 0, ctx->stream, k_apply_cbf_read)(recv, recv_cnt, shard_geom(sh, sh->cap_cbf), sh->cbf->dev, reply);
     LAUNCH_CHECK();
     return RB_OK;
 }
@@ -1367,7 +1405,7 @@ extern "C" int32_t rb_shard_emit_cbf_raises(rb_shard* sh, const uint8_t* reply_h
     const FastMod fm = make_fm(sh->cbf_bytes);
     const ShardGeom sg = shard_geom(sh, sh->cap_cbf);
     const uint64_t seed = ctx->rng_seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(ctx->launches + 1);
-#define ER(MAXH) k_combine_cbf_emit_raise<MAXH><<<slot_grid(sh), kThreads, 0, ctx->stream>>>(sh->tab, hm, fm, sh->hc, sg, sh->inc, sh->pos_cbf, reply_home, policy, seed, send, cnt, sh->overflow)
+#define ER(MAXH) RB_LAUNCH(slot_grid(sh), kThreads, 0, ctx->stream, k_combine_cbf_emit_raise<MAXH>)(sh->tab, hm, fm, sh->hc, sg, sh->inc, sh->pos_cbf, reply_home, policy, seed, send, cnt, sh->overflow)
     if (sh->hc <= 3) ER(3); else if (sh->hc <= 4) ER(4); else ER(8);
 #undef ER
     LAUNCH_CHECK();
@@ -1377,7 +1415,7 @@ extern "C" int32_t rb_shard_apply_cbf_raise(rb_shard* sh, const int64_t* recv, c
     if (!sh || !recv || !recv_cnt) return RB_EINVAL;
     rb_ctx* ctx = sh->ctx;
     LOCK(ctx);
-    k_apply_cbf_raise<<<region_grid(sh, sh->cap_cbf), kThreads, 0, ctx->stream>>>(recv, recv_cnt, shard_geom(sh, sh->cap_cbf), sh->cbf->dev);
+    RB_LAUNCH(region_grid(sh, sh->cap_cbf), kThreads, 0, ctx->stream, k_apply_cbf_raise)(recv, recv_cnt, shard_geom(sh, sh->cap_cbf), sh->cbf->dev);
     LAUNCH_CHECK();
     return RB_OK;
 }
@@ -1385,7 +1423,7 @@ extern "C" int32_t rb_shard_apply_lookup(rb_shard* sh, const int64_t* recv, cons
     if (!sh || !recv || !recv_cnt || !reply) return RB_EINVAL;
     rb_ctx* ctx = sh->ctx;
     LOCK(ctx);
-    k_apply_lookup<<<region_grid(sh, sh->cap_lookup), kThreads, 0, ctx->stream>>>(recv, recv_cnt, shard_geom(sh, sh->cap_lookup), sh->dbg->dev, sh->cbf->dev, reply);
+    RB_LAUNCH(region_grid(sh, sh->cap_lookup), kThreads, 0, ctx->stream, k_apply_lookup)(recv, recv_cnt, shard_geom(sh, sh->cap_lookup), sh->dbg->dev, sh->cbf->dev, reply);
     LAUNCH_CHECK();
     return RB_OK;
 }
@@ -1394,7 +1432,7 @@ extern "C" int32_t rb_shard_combine_lookup(rb_shard* sh, const uint8_t* reply_ho
     rb_ctx* ctx = sh->ctx;
     LOCK(ctx);
     if (sh->lookup_inst == 0) return RB_OK;
-    k_combine_lookup<<<(int)div_up(sh->lookup_inst, kThreads), kThreads, 0, ctx->stream>>>(sh->lookup_inst, sh->hd, sh->hc, sh->pos_lookup, reply_home, counts);
+    RB_LAUNCH((int)div_up(sh->lookup_inst, kThreads), kThreads, 0, ctx->stream, k_combine_lookup)(sh->lookup_inst, sh->hd, sh->hc, sh->pos_lookup, reply_home, counts);
     LAUNCH_CHECK();
     return RB_OK;
 }
@@ -1512,11 +1550,11 @@ static int32_t persistent_grid(rb_ctx* ctx, K kernel, int threads, size_t smem, 
 }
 static int writer_groups(int R) { int c = kWriterCursors / std::max(R, 1); return std::max(1, std::min(64, c)); }
 static int32_t scan_plan(rb_ctx* ctx, BucketEngine* e, const SortPlan& p) {
-    kb_scan_regions<<<p.R, 1024, 0, ctx->stream>>>(p.hist, p.C, e->tot);
+    RB_LAUNCH(p.R, 1024, 0, ctx->stream, kb_scan_regions)(p.hist, p.C, e->tot);
     LAUNCH_CHECK();
-    kb_scan_totals<<<1, 1024, 0, ctx->stream>>>(e->tot, p.R, p.roff);
+    RB_LAUNCH(1, 1024, 0, ctx->stream, kb_scan_totals)(e->tot, p.R, p.roff);
     LAUNCH_CHECK();
-    kb_spread_cursors<<<(int)div_up((int64_t)p.R * p.C, 256), 256, 0, ctx->stream>>>(p.hist, p.R * p.C, p.cursor);
+    RB_LAUNCH((int)div_up((int64_t)p.R * p.C, 256), 256, 0, ctx->stream, kb_spread_cursors)(p.hist, p.R * p.C, p.cursor);
     LAUNCH_CHECK();
     return RB_OK;
 }
@@ -1535,13 +1573,13 @@ static int32_t bucket_apply(rb_graph* g, BucketEngine* e, const BucketGeom& bg, 
     out.C = writer_groups(out.R);
     if (want_answers) {
         CK(cudaMemsetAsync(out.hist, 0, (size_t)out.R * out.C * 4, ctx->stream));
-        kb_apply_probes<0, SET><<<grid, kThreads, sm, ctx->stream>>>(in, bg, g->dbg->dev, g->cbf->dev, g->dbg->nbytes, g->cbf->nbytes, 1, out, e->done);
+        RB_LAUNCH(grid, kThreads, sm, ctx->stream, kb_apply_probes<0, SET>)(in, bg, g->dbg->dev, g->cbf->dev, g->dbg->nbytes, g->cbf->nbytes, 1, out, e->done);
         LAUNCH_CHECK();
         rc = scan_plan(ctx, e, out);
         if (rc) return rc;
     }
     CK(cudaMemsetAsync(e->done, 0, (size_t)(in.R + 2) * 4, ctx->stream));
-    kb_apply_probes<1, SET><<<grid, kThreads, sm, ctx->stream>>>(in, bg, g->dbg->dev, g->cbf->dev, g->dbg->nbytes, g->cbf->nbytes, want_answers, out, e->done);
+    RB_LAUNCH(grid, kThreads, sm, ctx->stream, kb_apply_probes<1, SET>)(in, bg, g->dbg->dev, g->cbf->dev, g->dbg->nbytes, g->cbf->nbytes, want_answers, out, e->done);
     LAUNCH_CHECK();
     *answers_out = out;
     return RB_OK;
@@ -1560,9 +1598,9 @@ static int32_t bucket_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     CK(cudaMemsetAsync(keys.count, 0, (size_t)keys.n * kSub * kCursorPad * 4, ctx->stream));
     const int grid_pos = (int)div_up(div_up(ing.n_pos, kChunk), kThreads);
     const size_t sm_keys = (size_t)keys.n * 8;
-    if (mode == RB_MODE_FWD) kb_route_keys<0><<<grid_pos, kThreads, sm_keys, ctx->stream>>>(ing, g->k, bg, keys, e->overflow);
-    else if (mode == RB_MODE_RC) kb_route_keys<1><<<grid_pos, kThreads, sm_keys, ctx->stream>>>(ing, g->k, bg, keys, e->overflow);
-    else kb_route_keys<2><<<grid_pos, kThreads, sm_keys, ctx->stream>>>(ing, g->k, bg, keys, e->overflow);
+    if (mode == RB_MODE_FWD) RB_LAUNCH(grid_pos, kThreads, sm_keys, ctx->stream, kb_route_keys<0>)(ing, g->k, bg, keys, e->overflow);
+    else if (mode == RB_MODE_RC) RB_LAUNCH(grid_pos, kThreads, sm_keys, ctx->stream, kb_route_keys<1>)(ing, g->k, bg, keys, e->overflow);
+    else RB_LAUNCH(grid_pos, kThreads, sm_keys, ctx->stream, kb_route_keys<2>)(ing, g->k, bg, keys, e->overflow);
     LAUNCH_CHECK();
     int flag = 0;
     rc = read_flag(ctx, e->overflow, &flag);
@@ -1579,7 +1617,7 @@ static int32_t bucket_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     int grid = 0;
     rc = persistent_grid(ctx, kb_aggregate, kThreads, 0, &grid);
     if (rc) return rc;
-    kb_aggregate<<<grid, kThreads, 0, ctx->stream>>>(keys, t, e->done);
+    RB_LAUNCH(grid, kThreads, 0, ctx->stream, kb_aggregate)(keys, t, e->done);
     LAUNCH_CHECK();
     // B3 probes sorted by filter slice
     SortPlan probes = e->probes;
@@ -1595,13 +1633,13 @@ static int32_t bucket_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     }
     probes.C = writer_groups(probes.R);
     CK(cudaMemsetAsync(probes.hist, 0, (size_t)probes.R * probes.C * 4, ctx->stream));
-    if (small) kb_emit_probes<6, 0><<<grid, kThreads, sm_p, ctx->stream>>>(t, hm, bg, with_cbf, probes);
-    else kb_emit_probes<8, 0><<<grid, kThreads, sm_p, ctx->stream>>>(t, hm, bg, with_cbf, probes);
+    if (small) RB_LAUNCH(grid, kThreads, sm_p, ctx->stream, kb_emit_probes<6, 0>)(t, hm, bg, with_cbf, probes);
+    else RB_LAUNCH(grid, kThreads, sm_p, ctx->stream, kb_emit_probes<8, 0>)(t, hm, bg, with_cbf, probes);
     LAUNCH_CHECK();
     rc = scan_plan(ctx, e, probes);
     if (rc) return rc;
-    if (small) kb_emit_probes<6, 1><<<grid, kThreads, sm_p, ctx->stream>>>(t, hm, bg, with_cbf, probes);
-    else kb_emit_probes<8, 1><<<grid, kThreads, sm_p, ctx->stream>>>(t, hm, bg, with_cbf, probes);
+    if (small) RB_LAUNCH(grid, kThreads, sm_p, ctx->stream, kb_emit_probes<6, 1>)(t, hm, bg, with_cbf, probes);
+    else RB_LAUNCH(grid, kThreads, sm_p, ctx->stream, kb_emit_probes<8, 1>)(t, hm, bg, with_cbf, probes);
     LAUNCH_CHECK();
     // B4
     SortPlan answers;
@@ -1616,16 +1654,16 @@ static int32_t bucket_insert_round(rb_graph* g, const Ingest& ing, int mode, int
         const size_t sm_c = ((size_t)1 << kIdRangeLog2) * 8 + (size_t)raises.n * 8;
         if (g->hc <= 4) {
             CK(cudaFuncSetAttribute(kb_combine_insert<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
-            kb_combine_insert<4><<<ctx->sm_count, kCombineThreads, sm_c, ctx->stream>>>(answers, t, hm, bg, policy, seed, raises, e->overflow);
+            RB_LAUNCH(ctx->sm_count, kCombineThreads, sm_c, ctx->stream, kb_combine_insert<4>)(answers, t, hm, bg, policy, seed, raises, e->overflow);
         } else {
             CK(cudaFuncSetAttribute(kb_combine_insert<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
-            kb_combine_insert<8><<<ctx->sm_count, kCombineThreads, sm_c, ctx->stream>>>(answers, t, hm, bg, policy, seed, raises, e->overflow);
+            RB_LAUNCH(ctx->sm_count, kCombineThreads, sm_c, ctx->stream, kb_combine_insert<8>)(answers, t, hm, bg, policy, seed, raises, e->overflow);
         }
         LAUNCH_CHECK();
         CK(cudaMemsetAsync(e->done, 0, (size_t)(raises.n + 2) * 4, ctx->stream));
         rc = persistent_grid(ctx, kb_apply_raises, kThreads, 0, &grid);
         if (rc) return rc;
-        kb_apply_raises<<<grid, kThreads, 0, ctx->stream>>>(raises, g->cbf->dev, g->cbf->nbytes, e->done);
+        RB_LAUNCH(grid, kThreads, 0, ctx->stream, kb_apply_raises)(raises, g->cbf->dev, g->cbf->nbytes, e->done);
         LAUNCH_CHECK();
     }
     rc = read_flag(ctx, e->overflow, &flag);
@@ -1650,7 +1688,7 @@ static int32_t bucket_count_round(rb_graph* g, const Ingest& ing, int mode, floa
     const size_t sm_p = (size_t)probes.R * 4;
     const bool small = g->hd + g->hc <= 6;
     int grid = 0;
-#define RL(MODE, MAXJ, PASS) kb_route_lookup<MODE, MAXJ, PASS><<<grid, kThreads, sm_p, ctx->stream>>>(ing, g->k, hm, bg, probes, e->usable, fh, rh)
+#define RL(MODE, MAXJ, PASS) RB_LAUNCH(grid, kThreads, sm_p, ctx->stream, kb_route_lookup<MODE, MAXJ, PASS>)(ing, g->k, hm, bg, probes, e->usable, fh, rh)
 #define RLA(MODE, MAXJ) { rc = persistent_grid(ctx, kb_route_lookup<MODE, MAXJ, 1>, kThreads, sm_p, &grid); if (rc) return rc; \
         if (sm_p > 48 * 1024) CK(cudaFuncSetAttribute(kb_route_lookup<MODE, MAXJ, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_p)); \
         probes.C = writer_groups(probes.R); CK(cudaMemsetAsync(probes.hist, 0, (size_t)probes.R * probes.C * 4, ctx->stream)); RL(MODE, MAXJ, 0); LAUNCH_CHECK(); rc = scan_plan(ctx, e, probes); if (rc) return rc; RL(MODE, MAXJ, 1); LAUNCH_CHECK(); }
@@ -1663,7 +1701,8 @@ static int32_t bucket_count_round(rb_graph* g, const Ingest& ing, int mode, floa
     if (rc) return rc;
     const size_t sm_c = ((size_t)1 << kIdRangeLog2) * 8;
     CK(cudaFuncSetAttribute(kb_combine_lookup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
-    kb_combine_lookup<<<ctx->sm_count, kCombineThreads, sm_c, ctx->stream>>>(answers, ing.n_pos, g->hd, g->hc, e->usable, counts, ing.out_base);
+    RB_LAUNCH(ctx->sm_count, kCombineThreads, sm_c, ctx->stream, kb_combine_lookup)(answers, ing.n_pos, g->hd, g->hc, e->usable, counts, ing.out_base);
     LAUNCH_CHECK();
     return RB_OK;
 }
+#endif  // !RB_EMU

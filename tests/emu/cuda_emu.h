@@ -1,0 +1,180 @@
+// cuda_emu.h -- TEST INFRASTRUCTURE ONLY.  Never part of librnabloom_gpu.so, never loaded by the product path.
+//
+// There is no GPU in the development container, so index arithmetic / data-movement mistakes in a kernel would only show
+// up on the (scarce) B200 box.  This shim lets g++ compile the *unchanged* kernel sources of rna-bloom_b200/csrc for the
+// host (-DRB_EMU): one OS thread per CUDA thread of a CTA, CTAs one after the other, __syncthreads = a barrier,
+// atomics = __atomic builtins, the handful of CUDA runtime calls the host code makes = malloc/memcpy.  tests/test_emu_parity.py
+// then runs the same parity tests the GPU suite runs (against the oracle) through the resulting library.
+// It checks the LOGIC of the kernels, not their performance or their memory-model behaviour on the device.
+#pragma once
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <barrier>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) alignas(n)
+
+struct EmuDim3 { unsigned x = 1, y = 1, z = 1; };
+struct uint2 { unsigned x, y; };
+struct uint4 { unsigned x, y, z, w; };
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+
+namespace emu {
+inline thread_local EmuDim3 t_threadIdx, t_blockIdx;
+inline EmuDim3 g_blockDim, g_gridDim;
+inline unsigned char* g_dyn_smem = nullptr;
+inline std::barrier<>* g_cta_barrier = nullptr;
+inline std::vector<std::unique_ptr<std::barrier<>>> g_warp_barrier;
+inline unsigned long long g_warp_xchg[64][32];
+
+template <typename F>
+inline void run_grid(unsigned grid, unsigned block, size_t smem, F&& body) {
+    if (grid == 0 || block == 0) return;
+    std::vector<unsigned char> dyn(smem + 64);
+    g_dyn_smem = (unsigned char*)(((uintptr_t)dyn.data() + 63) & ~(uintptr_t)63);
+    g_blockDim.x = block;
+    g_gridDim.x = grid;
+    std::barrier<> outer((ptrdiff_t)block);
+    std::unique_ptr<std::barrier<>> inner;
+    auto worker = [&](unsigned tid) {
+        for (unsigned b = 0; b < grid; ++b) {
+            if (tid == 0) {
+                inner.reset(new std::barrier<>((ptrdiff_t)block));
+                g_cta_barrier = inner.get();
+                g_warp_barrier.clear();
+                for (unsigned w = 0; w * 32 < block; ++w)
+                    g_warp_barrier.emplace_back(new std::barrier<>((ptrdiff_t)std::min(32u, block - w * 32)));
+            }
+            outer.arrive_and_wait();
+            t_threadIdx.x = tid;
+            t_blockIdx.x = b;
+            body();
+            inner->arrive_and_drop();   // a thread that has left the kernel no longer takes part in __syncthreads
+            outer.arrive_and_wait();
+        }
+    };
+    if (block == 1) { worker(0); return; }
+    std::vector<std::thread> th;
+    th.reserve(block);
+    for (unsigned t = 0; t < block; ++t) th.emplace_back(worker, t);
+    for (auto& t : th) t.join();
+}
+
+template <typename K>
+struct Launcher {
+    unsigned grid, block; size_t smem; K kern;
+    template <typename... A>
+    void operator()(A... args) const { run_grid(grid, block, smem, [&]() { kern(args...); }); }
+};
+template <typename K>
+inline Launcher<K> launcher(long long grid, long long block, size_t smem, void*, K kern) { return Launcher<K>{(unsigned)grid, (unsigned)block, smem, kern}; }
+}  // namespace emu
+
+#define threadIdx emu::t_threadIdx
+#define blockIdx emu::t_blockIdx
+#define blockDim emu::g_blockDim
+#define gridDim emu::g_gridDim
+#define RB_LAUNCH(grid, block, smem, stream, ...) emu::launcher((grid), (block), (smem), (void*)(stream), &__VA_ARGS__)
+#define RB_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::g_dyn_smem)
+
+static inline void __syncthreads() { emu::g_cta_barrier->arrive_and_wait(); }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __nanosleep(unsigned) { std::this_thread::yield(); }
+
+// ---- warp shuffles (full-mask, convergent uses only) -----------------------------------------------------------------
+template <typename T>
+static inline T emu_shfl(T v, int src_lane) {
+    const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    unsigned long long bits = 0;
+    memcpy(&bits, &v, sizeof(T));
+    emu::g_warp_xchg[w][l] = bits;
+    emu::g_warp_barrier[w]->arrive_and_wait();
+    unsigned long long got = emu::g_warp_xchg[w][(unsigned)src_lane & 31];
+    emu::g_warp_barrier[w]->arrive_and_wait();
+    T out;
+    memcpy(&out, &got, sizeof(T));
+    return out;
+}
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_shfl(v, (int)((threadIdx.x & 31) ^ (unsigned)m)); }
+template <typename T> static inline T __shfl_up_sync(unsigned, T v, int d) { const int l = (int)(threadIdx.x & 31); const T o = emu_shfl(v, l >= d ? l - d : l); return l >= d ? o : v; }
+template <typename T> static inline T __shfl_sync(unsigned, T v, int src) { return emu_shfl(v, src); }
+
+// ---- atomics -----------------------------------------------------------------------------------------------------------
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicAnd(unsigned* p, unsigned v) { return __atomic_fetch_and(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicCAS(unsigned* p, unsigned cmp, unsigned v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
+static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
+static inline unsigned long long atomicExch(unsigned long long* p, unsigned long long v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+
+// ---- loads / stores / integer intrinsics ---------------------------------------------------------------------------------
+template <typename T> static inline T __ldg(const T* p) { return *p; }
+template <typename T> static inline T __ldcg(const T* p) { return *(const volatile T*)p; }
+template <typename T> static inline T __ldcs(const T* p) { return *p; }
+template <typename T> static inline void __stcs(T* p, T v) { *p = v; }
+static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) { return (unsigned long long)(((unsigned __int128)a * b) >> 64); }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline unsigned __vcmpne4(unsigned a, unsigned b) {
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) if (((a >> (8 * i)) & 0xFF) != ((b >> (8 * i)) & 0xFF)) r |= 0xFFu << (8 * i);
+    return r;
+}
+template <typename A, typename B> static inline auto min(A a, B b) -> decltype(a + b) { return a < b ? a : b; }
+template <typename A, typename B> static inline auto max(A a, B b) -> decltype(a + b) { return a > b ? a : b; }
+
+// ---- the slice of the runtime API the host code uses (everything is synchronous) ----------------------------------------
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+typedef void* cudaEvent_t;
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
+enum { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0, cudaLimitMaxL2FetchGranularity = 5,
+       cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+struct cudaDeviceProp { int major = 10, minor = 0, multiProcessorCount = 2; };
+static inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated allocation failure"; }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { *p = cudaDeviceProp(); return cudaSuccess; }
+static inline cudaError_t cudaDeviceSetLimit(int, size_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = malloc(1); return cudaSuccess; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = malloc(1); return cudaSuccess; }
+static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = malloc(1); return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 1.0f; return cudaSuccess; }
+template <typename T>
+static inline cudaError_t cudaMalloc(T** p, size_t n) {
+    void* q = nullptr;
+    if (posix_memalign(&q, 256, (n + 255) & ~(size_t)255) != 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
+    memset(q, 0xA5, n);   // device memory is not zeroed: make reliance on that visible
+    *p = (T*)q;
+    return cudaSuccess;
+}
+static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return posix_memalign(p, 256, (n + 255) & ~(size_t)255) == 0 ? cudaSuccess : cudaErrorMemoryAllocation; }
+static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
+template <typename K> static inline cudaError_t cudaFuncSetAttribute(K, int, int) { return cudaSuccess; }
+template <typename K> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* occ, K, int, size_t) { *occ = 1; return cudaSuccess; }
