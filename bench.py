@@ -167,7 +167,7 @@ def main():
     ap.add_argument("--subbatch-kmers", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--engine", default=os.environ.get("RB_ENGINE", "direct"), choices=["direct", "bucketed"])
+    ap.add_argument("--engine", default=os.environ.get("RB_ENGINE", "direct"), choices=["direct", "bucketed", "sliced"])
     ap.add_argument("--sharded", action="store_true", help="experiments only: run the sharded pipeline even on one GPU")
     ap.add_argument("--genome", type=int, default=GENOME, help="experiments only: virtual genome length (coverage knob)")
     args = ap.parse_args()
@@ -217,6 +217,8 @@ def main():
     for s in range(args.warmup):
         step(batches[s % n_batches])
     ctx.sync()
+    ctx.profile_enable(True)   # CUDA events around every kernel launch of the timed region (a few microseconds per launch)
+    ctx.profile_read()
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
@@ -231,6 +233,8 @@ def main():
     wall = time.perf_counter() - wall0
     launches = ctx.kernel_launches() - l0
     clocks = sampler.stop()
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
     t_total_ms = t_ins + t_look
     value = nk * args.steps / (t_total_ms * 1e-3)
     hbm, peak_src = peaks()
@@ -264,23 +268,35 @@ def main():
         e2e = {"value": nk * e_steps / te, "unit": "k-mers/s", "h2d_bytes_per_step": 2 * words * 8, "d2h_bytes_per_step": nk * 4,
                "steps": e_steps, "ms_per_step": 1e3 * te / e_steps}
 
-    # ---- roofline of the dominant kernel (live CUDA-event time over the timed region) -----------------------------------
+    # ---- roofline (live CUDA-event times of the timed region; algorithmic bytes = SURVEY 8d sector model, 192.15 B per k-mer and phase)
+    kmers_total = nk * args.steps
     ins_dominant = t_ins >= t_look
-    sub = (1 << 25) if not args.subbatch_kmers else args.subbatch_kmers
-    launches_per_pass = -(-n_reads // max(1, sub // KMERS_PER_READ))
-    kern_ms = (t_ins if ins_dominant else t_look) / (args.steps * launches_per_pass)
-    kmers_per_launch = nk / launches_per_pass
     a_k = A_INSERT if ins_dominant else A_LOOKUP
-    achieved = kmers_per_launch * a_k / (kern_ms * 1e-3) / 1e9
-    traffic = None
+    kern_ms = {k: round(v[0] / args.steps, 4) for k, v in prof.items()}       # per step
+    top = max(prof.items(), key=lambda kv: kv[1][0]) if prof else ("?", (0.0, 1))
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("k_graph_insert" if ins_dominant else "k_graph_count")
-    roofline = {"bound": "hbm", "kernel": "k_graph_insert" if ins_dominant else "k_graph_count", "achieved": achieved, "peak": hbm,
+    traffic_tab = json.load(open(tp)) if os.path.exists(tp) else {}
+    if args.engine == "direct":
+        name = "k_graph_insert" if ins_dominant else "k_graph_count"
+        ms_sum, calls = prof.get(name, (t_ins if ins_dominant else t_look, args.steps))
+        kmers_per_launch = kmers_total / calls
+        ms_per_launch = ms_sum / calls
+        traffic = traffic_tab.get(name)
+    else:
+        # a phase of the sliced / bucketed engine is a chain of kernels over one round; the sector model prices the phase (the k-mer
+        # operation), so the roofline line is the whole chain: every launch between the phase's first and last kernel, memsets included
+        name = ("insert" if ins_dominant else "lookup") + " round of the %s engine (kernel chain, see kernels_ms_per_step)" % args.engine
+        rounds = max(1, prof.get("ks_route_keys<2>" if ins_dominant else "ks_route_lookup<2>", (0.0, args.steps))[1])
+        kmers_per_launch = kmers_total / rounds
+        ms_per_launch = (t_ins if ins_dominant else t_look) / rounds
+        traffic = traffic_tab.get(args.engine + ("_insert_round" if ins_dominant else "_lookup_round"))
+    achieved = kmers_per_launch * a_k / (ms_per_launch * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": hbm,
                 "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_kmer": a_k, "kmers_per_launch": kmers_per_launch, "ms_per_launch": kern_ms,
+                "algorithmic_bytes_per_kmer": a_k, "kmers_per_launch": kmers_per_launch, "ms_per_launch": ms_per_launch,
                 "insert_gkmers_s": nk * args.steps / t_ins / 1e6, "lookup_gkmers_s": nk * args.steps / t_look / 1e6,
-                "step_frac": value * A_STEP / 1e9 / hbm}
+                "step_frac": value * A_STEP / 1e9 / hbm, "engine": args.engine, "kernels_ms_per_step": kern_ms,
+                "top_kernel": top[0], "top_kernel_share_of_step": top[1][0] / t_total_ms}
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -294,7 +310,7 @@ def main():
 
     line = {"metric": "k-mers/s (insert+lookup) at k=25, 2x150 bp reads", "value": value, "unit": "k-mers/s", "n_gpus": 1,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config_dict(n_reads, 1),
+            "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": dict(config_dict(n_reads, 1), engine=args.engine),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "wall_s_timed_region": wall}
     print(json.dumps(line), flush=True)

@@ -73,6 +73,11 @@ RB_API int32_t rb_ctx_set_rng_seed(rb_ctx* ctx, uint64_t seed);  /* MiniFloat co
 RB_API int32_t rb_ctx_set_subbatch_kmers(rb_ctx* ctx, int64_t kmers); /* tuning: k-mers per kernel launch */
 RB_API int64_t rb_ctx_kernel_launches(rb_ctx* ctx);     /* number of kernels this context has launched so far */
 /* device-side stopwatch on the context's stream (CUDA events): start, then stop returns the elapsed milliseconds */
+/* Per-kernel device time (CUDA events around every launch of the read-level engines) -- measurement only (bench.py's roofline):
+ * enable, run, then read: names receives the kernel names joined by '\n', ms / calls the summed time and launch count of each. */
+RB_API int32_t rb_ctx_profile_enable(rb_ctx* ctx, int32_t on);
+RB_API int32_t rb_ctx_profile_read(rb_ctx* ctx, char* names, int64_t names_len, float* ms, int32_t* calls, int32_t max_entries,
+                                   int32_t* n_out);
 RB_API int32_t rb_timer_start(rb_ctx* ctx);
 RB_API int32_t rb_timer_stop(rb_ctx* ctx, float* elapsed_ms);
 RB_API int32_t rb_host_alloc(void** p, int64_t bytes);  /* pinned host memory for fast transfers */

@@ -78,6 +78,8 @@ def bind(path, allow_missing=False):
         "rb_ctx_set_rng_seed": (i32, [vp, u64]),
         "rb_ctx_set_subbatch_kmers": (i32, [vp, i64]),
         "rb_ctx_kernel_launches": (i64, [vp]),
+        "rb_ctx_profile_enable": (i32, [vp, i32]),
+        "rb_ctx_profile_read": (i32, [vp, vp, i64, vp, vp, i32, C.POINTER(i32)]),
         "rb_timer_start": (i32, [vp]),
         "rb_timer_stop": (i32, [vp, C.POINTER(f32)]),
         "rb_host_alloc": (i32, [C.POINTER(vp), i64]),

@@ -38,7 +38,6 @@ constexpr int kSlThreads = 256;        // every kernel here runs 256-thread CTAs
 constexpr int kSlMaxH = 3;             // hashes per filter the engine is built for
 constexpr int kSlNJ = 2 * kSlMaxH;     // probe slots per k-mer: dbgbf hashes at 0..2, cbf hashes at 3..5
 constexpr int kSlRoundKmers = 4;       // k-mers per thread and sort round
-constexpr int kSlChunk = 4096;         // records per work item of the apply kernels
 constexpr int kSlPad = 32;             // one cursor per 128 B line (atomics to one line serialise in L2)
 constexpr int kSlMaxRegions = 2048;    // bucket ids are kept in 12 bits, 0xFFF = no record
 constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
@@ -48,6 +47,7 @@ struct SlArena {
     unsigned int* cursor;     // [B * kSlPad] records appended to region b so far (may pass the capacity: overflow)
     const uint32_t* roff;     // [B + 1] region offsets in records (the whole arena holds < 2^32 records)
     int B;
+    int chunk;                // records per work item of the kernels that consume the arena region by region
 };
 struct SlGeom {
     FastMod dbg_fm, cbf_fm;   // global index arithmetic (reference semantics)
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_route_lookup(const Ingest g, in
     }
 }
 
-// ---- work list of an arena: chunk_prefix[b] = number of kSlChunk-record work items in the regions before b --------------------------------
+// ---- work list of an arena: chunk_prefix[b] = number of arena.chunk-record work items in the regions before b --------------------------------
 __global__ void __launch_bounds__(kSlThreads) ks_chunk_prefix(const SlArena arena, int* __restrict__ chunk_prefix) {
     RB_DYN_SMEM(unsigned char, sl_smem);
     uint32_t* v = reinterpret_cast<uint32_t*>(sl_smem);
@@ -238,15 +238,17 @@ __global__ void __launch_bounds__(kSlThreads) ks_chunk_prefix(const SlArena aren
     for (int b = threadIdx.x; b < arena.B; b += kSlThreads) {
         const uint32_t cap = arena.roff[b + 1] - arena.roff[b];
         const uint32_t cnt = min(arena.cursor[(size_t)b * kSlPad], cap);
-        v[b] = (cnt + kSlChunk - 1) / kSlChunk;
+        v[b] = (cnt + (uint32_t)arena.chunk - 1) / (uint32_t)arena.chunk;
     }
     __syncthreads();
     const uint32_t total = cta_exclusive_scan(v, arena.B, scratch);
     for (int b = threadIdx.x; b < arena.B; b += kSlThreads) chunk_prefix[b] = (int)v[b];
     if (threadIdx.x == 0) chunk_prefix[arena.B] = (int)total;
 }
-// Work items are dealt round-robin in region order, so at any moment the whole grid works on a few neighbouring regions and the
-// filter slices they address stay L2-resident without any grid barrier.
+// Work items are dealt round-robin in region order, so at any moment the whole grid works inside a window of gridDim.x * chunk
+// records.  The window must be a small fraction of a region (the host sizes grid and chunk for that): then one, at region
+// boundaries two, filter slices are live and they stay L2-resident without any grid barrier.  (Measured with a window as large
+// as a region: 109 B of DRAM reads per probe, i.e. no residency at all -- profiles/r01_notes.md section 6.)
 struct SlWork { int b; uint32_t first, n; };
 __device__ __forceinline__ void sl_load_prefix(int* pre, const int* __restrict__ chunk_prefix, int B) {
     for (int i = threadIdx.x; i <= B; i += kSlThreads) pre[i] = chunk_prefix[i];
@@ -259,9 +261,9 @@ __device__ __forceinline__ SlWork sl_work_item(const SlArena& arena, const int* 
     w.b = lo;
     const uint32_t r_lo = __ldg(&arena.roff[lo]), cap = __ldg(&arena.roff[lo + 1]) - r_lo;
     const uint32_t cnt = min(arena.cursor[(size_t)lo * kSlPad], cap);
-    const uint32_t off = (uint32_t)(c - pre[lo]) * kSlChunk;
+    const uint32_t off = (uint32_t)(c - pre[lo]) * (uint32_t)arena.chunk;
     w.first = r_lo + off;
-    w.n = min((uint32_t)kSlChunk, cnt - off);
+    w.n = min((uint32_t)arena.chunk, cnt - off);
     return w;
 }
 
@@ -371,14 +373,29 @@ __global__ void __launch_bounds__(kSlThreads) ks_aggregate(const SlArena arena, 
     const unsigned long long* rec = reinterpret_cast<const unsigned long long*>(arena.data);
     for (int c = blockIdx.x; c < total; c += gridDim.x) {
         const SlWork w = sl_work_item(arena, pre, c);
-        for (uint32_t i = threadIdx.x; i < w.n; i += kSlThreads) {
-            const uint64_t key = __ldcs(rec + w.first + i);
-            if (key == 0) { atomicAdd(&t.counts[t.n_slots], 1u); continue; }
-            uint64_t s = sl_mixkey(key) >> t.shift;
-            for (;;) {
-                const unsigned long long old = atomicCAS(&t.keys[s], 0ULL, (unsigned long long)key);
-                if (old == 0ULL || old == key) { atomicAdd(&t.counts[s], 1u); break; }
-                if (++s == t.n_slots) s = 0;
+        constexpr int U = 4;   // keys in flight per thread: the CAS round trip to L2 is the cost
+        for (uint32_t i0 = threadIdx.x; i0 < w.n; i0 += kSlThreads * U) {
+            unsigned long long key[U], old[U];
+            uint64_t s[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) key[u] = (i0 + u * kSlThreads < w.n) ? __ldcs(rec + w.first + i0 + u * kSlThreads) : 0ULL;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                s[u] = sl_mixkey(key[u]) >> t.shift;
+                old[u] = 0ULL;
+                if (key[u] != 0ULL) old[u] = atomicCAS(&t.keys[s[u]], 0ULL, key[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (i0 + u * kSlThreads >= w.n) continue;
+                if (key[u] == 0ULL) { atomicAdd(&t.counts[t.n_slots], 1u); continue; }   // key 0 lives in the extra slot
+                uint64_t at = s[u];
+                unsigned long long o = old[u];
+                while (o != 0ULL && o != key[u]) {   // linear probing
+                    if (++at == t.n_slots) at = 0;
+                    o = atomicCAS(&t.keys[at], 0ULL, key[u]);
+                }
+                atomicAdd(&t.counts[at], 1u);
             }
         }
     }

@@ -33,6 +33,10 @@ static int env_int(const char* name, int dflt, int lo, int hi) {
     const int x = atoi(v);
     return x < lo ? lo : (x > hi ? hi : x);
 }
+// Consumers walk an arena region by region with a window of grid * chunk records in flight; the window has to stay a small
+// fraction of a region or several filter / table slices are live at once and fall out of L2.
+static int sl_chunk() { return env_int("RB_SLICED_CHUNK", 2048, 256, 1 << 16); }
+static int sl_consumer_occ() { return env_int("RB_SLICED_CONSUMER_OCC", 2, 1, 8); }
 static int64_t sl_pow2_at_least(int64_t v) { int64_t p = 1024; while (p < v) p <<= 1; return p; }
 // capacity of a region that expects `expected` records from uniform hashes: 4 % + 8 sigma + a constant
 static int64_t sl_capacity(double expected) { return (int64_t)(expected * 1.04 + 8.0 * std::sqrt(expected + 1.0)) + 2048; }
@@ -140,7 +144,7 @@ static int32_t sl_persistent_grid(rb_ctx* ctx, K kernel, size_t smem, int* grid)
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kSlThreads, smem));
     if (occ < 1) return fail(ctx, RB_ECUDA, "sliced engine: kernel does not fit on an SM");
-    *grid = ctx->sm_count * std::min(occ, 8);
+    *grid = ctx->sm_count * std::min(occ, sl_consumer_occ());
     return RB_OK;
 }
 template <typename K>
@@ -153,11 +157,12 @@ static int32_t sl_chunk_prefix(rb_ctx* ctx, SlicedEngine* e, const SlArena& a) {
     const size_t sm = ((size_t)((a.B + 3) & ~3) + 296) * 4;
     int32_t rc = sl_allow_smem(ctx, ks_chunk_prefix, sm);
     if (rc) return rc;
+    PROF("ks_chunk_prefix");
     RB_LAUNCH(1, kSlThreads, sm, ctx->stream, ks_chunk_prefix)(a, e->chunk_prefix);
     LAUNCH_CHECK();
     return RB_OK;
 }
-static SlArena sl_probe_arena(SlicedEngine* e) { SlArena a; a.data = e->probe_data; a.cursor = e->probe_cursor; a.roff = e->probe_roff; a.B = e->probe_B; return a; }
+static SlArena sl_probe_arena(SlicedEngine* e) { SlArena a; a.data = e->probe_data; a.cursor = e->probe_cursor; a.roff = e->probe_roff; a.B = e->probe_B; a.chunk = sl_chunk(); return a; }
 
 // S1..S3
 static int32_t sliced_count_round(rb_graph* g, const Ingest& ing, int mode, float* counts, int64_t* fh, int64_t* rh, bool* fell_back) {
@@ -173,9 +178,11 @@ static int32_t sliced_count_round(rb_graph* g, const Ingest& ing, int mode, floa
     const size_t sm_sort = TileSort<uint32_t, kSlRoundKmers * kSlNJ>::smem_bytes(probes.B);
     if (mode == RB_MODE_FWD) {
         rc = sl_allow_smem(ctx, ks_route_lookup<0>, sm_sort); if (rc) return rc;
+        PROF("ks_route_lookup<0>");
         RB_LAUNCH(grid_pos, kSlThreads, sm_sort, ctx->stream, ks_route_lookup<0>)(ing, g->k, hm, e->sg, probes, e->pos, fh, rh, e->overflow);
     } else {
         rc = sl_allow_smem(ctx, ks_route_lookup<2>, sm_sort); if (rc) return rc;
+        PROF("ks_route_lookup<2>");
         RB_LAUNCH(grid_pos, kSlThreads, sm_sort, ctx->stream, ks_route_lookup<2>)(ing, g->k, hm, e->sg, probes, e->pos, fh, rh, e->overflow);
     }
     LAUNCH_CHECK();
@@ -189,9 +196,11 @@ static int32_t sliced_count_round(rb_graph* g, const Ingest& ing, int mode, floa
     int grid = 0;
     rc = sl_persistent_grid(ctx, ks_apply_probes<0>, sm_pre, &grid);
     if (rc) return rc;
+    PROF("ks_apply_probes<0>");
     RB_LAUNCH(grid, kSlThreads, sm_pre, ctx->stream, ks_apply_probes<0>)(probes, e->chunk_prefix, e->sg, g->dbg->dev, g->cbf->dev, e->ans);
     LAUNCH_CHECK();
     const int grid_c = (int)div_up(ing.n_pos, (int64_t)kSlThreads * kSlRoundKmers);
+    PROF("ks_combine_lookup");
     RB_LAUNCH(grid_c, kSlThreads, 0, ctx->stream, ks_combine_lookup)(e->pos, e->ans, ing.n_pos, g->hd, g->hc, counts, ing.out_base);
     LAUNCH_CHECK();
     return RB_OK;
@@ -206,18 +215,21 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     if (e->unsupported) { *fell_back = true; return RB_OK; }
     const HashMults hm = make_hm(g->k);
     // I1 keys by range
-    SlArena keys; keys.data = e->key_data; keys.cursor = e->key_cursor; keys.roff = e->key_roff; keys.B = e->key_B;
+    SlArena keys; keys.data = e->key_data; keys.cursor = e->key_cursor; keys.roff = e->key_roff; keys.B = e->key_B; keys.chunk = sl_chunk();
     CK(cudaMemsetAsync(keys.cursor, 0, (size_t)keys.B * kSlPad * 4, ctx->stream));
     const int grid_pos = (int)div_up(ing.n_pos, (int64_t)kSlThreads * kChunk);
     const size_t sm_keys = TileSort<unsigned long long, kChunk>::smem_bytes(keys.B);
     if (mode == RB_MODE_FWD) {
         rc = sl_allow_smem(ctx, ks_route_keys<0>, sm_keys); if (rc) return rc;
+        PROF("ks_route_keys<0>");
         RB_LAUNCH(grid_pos, kSlThreads, sm_keys, ctx->stream, ks_route_keys<0>)(ing, g->k, e->key_B, e->key_shift, keys, e->overflow);
     } else if (mode == RB_MODE_RC) {
         rc = sl_allow_smem(ctx, ks_route_keys<1>, sm_keys); if (rc) return rc;
+        PROF("ks_route_keys<1>");
         RB_LAUNCH(grid_pos, kSlThreads, sm_keys, ctx->stream, ks_route_keys<1>)(ing, g->k, e->key_B, e->key_shift, keys, e->overflow);
     } else {
         rc = sl_allow_smem(ctx, ks_route_keys<2>, sm_keys); if (rc) return rc;
+        PROF("ks_route_keys<2>");
         RB_LAUNCH(grid_pos, kSlThreads, sm_keys, ctx->stream, ks_route_keys<2>)(ing, g->k, e->key_B, e->key_shift, keys, e->overflow);
     }
     LAUNCH_CHECK();
@@ -227,18 +239,22 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     if (flag) { *fell_back = true; return RB_OK; }   // extreme key skew: nothing modified yet
     // I2 aggregate
     SlTable t; t.keys = e->tab_keys; t.counts = e->tab_counts; t.n_slots = (uint64_t)e->T; t.shift = e->tab_shift;
+    PROF("memset(table)");
     CK(cudaMemsetAsync(t.keys, 0, (size_t)(e->T + 1) * 8, ctx->stream));
     CK(cudaMemsetAsync(t.counts, 0, (size_t)(e->T + 1) * 4, ctx->stream));
+    if (ctx->prof_pending) prof_end(ctx);
     rc = sl_chunk_prefix(ctx, e, keys);
     if (rc) return rc;
     int grid = 0;
     rc = sl_persistent_grid(ctx, ks_aggregate, (size_t)(keys.B + 1) * 4, &grid);
     if (rc) return rc;
+    PROF("ks_aggregate");
     RB_LAUNCH(grid, kSlThreads, (size_t)(keys.B + 1) * 4, ctx->stream, ks_aggregate)(keys, e->chunk_prefix, t);
     LAUNCH_CHECK();
     // I3 dense distinct keys
     CK(cudaMemsetAsync(e->n_distinct, 0, 4, ctx->stream));
     const int grid_t = (int)div_up(e->T + 1, (int64_t)kSlThreads * kSlCompactPer);
+    PROF("ks_compact_table");
     RB_LAUNCH(grid_t, kSlThreads, 0, ctx->stream, ks_compact_table)(t, e->dkey, e->dmult, e->n_distinct);
     LAUNCH_CHECK();
     // I4 probes by filter slice
@@ -249,6 +265,7 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     rc = sl_allow_smem(ctx, ks_emit_probes, sm_sort);
     if (rc) return rc;
     const int grid_d = (int)div_up(ing.n_pos, (int64_t)kSlThreads * kSlRoundKmers);   // distinct keys <= instances
+    PROF("ks_emit_probes");
     RB_LAUNCH(grid_d, kSlThreads, sm_sort, ctx->stream, ks_emit_probes)(e->dkey, e->n_distinct, hm, e->sg, with_cbf, probes, e->pos, e->overflow);
     LAUNCH_CHECK();
     rc = sl_read_flag(ctx, e->overflow, &flag);
@@ -260,20 +277,23 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     const size_t sm_pre = (size_t)(probes.B + 1) * 4;
     if (policy != POLICY_COUNT_IF_PRESENT) {
         rc = sl_persistent_grid(ctx, ks_apply_probes<1>, sm_pre, &grid); if (rc) return rc;
+        PROF("ks_apply_probes<1>");
         RB_LAUNCH(grid, kSlThreads, sm_pre, ctx->stream, ks_apply_probes<1>)(probes, e->chunk_prefix, e->sg, g->dbg->dev, g->cbf->dev, e->ans);
     } else {
         rc = sl_persistent_grid(ctx, ks_apply_probes<0>, sm_pre, &grid); if (rc) return rc;
+        PROF("ks_apply_probes<0>");
         RB_LAUNCH(grid, kSlThreads, sm_pre, ctx->stream, ks_apply_probes<0>)(probes, e->chunk_prefix, e->sg, g->dbg->dev, g->cbf->dev, e->ans);
     }
     LAUNCH_CHECK();
     if (with_cbf) {
         // I6 + I7
-        SlArena raises; raises.data = e->raise_data; raises.cursor = e->raise_cursor; raises.roff = e->raise_roff; raises.B = e->sg.n_raise;
+        SlArena raises; raises.data = e->raise_data; raises.cursor = e->raise_cursor; raises.roff = e->raise_roff; raises.B = e->sg.n_raise; raises.chunk = sl_chunk();
         CK(cudaMemsetAsync(raises.cursor, 0, (size_t)raises.B * kSlPad * 4, ctx->stream));
         const uint64_t seed = ctx->rng_seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(ctx->launches + 1);
         const size_t sm_r = TileSort<uint32_t, kSlRoundKmers * kSlMaxH>::smem_bytes(raises.B);
         rc = sl_allow_smem(ctx, ks_combine_insert, sm_r);
         if (rc) return rc;
+        PROF("ks_combine_insert");
         RB_LAUNCH(grid_d, kSlThreads, sm_r, ctx->stream, ks_combine_insert)(e->dkey, e->dmult, e->n_distinct, e->pos, e->ans, hm, e->sg, policy, seed, raises,
                                                                          e->overflow);
         LAUNCH_CHECK();
@@ -282,6 +302,7 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
         const size_t sm_rp = (size_t)(raises.B + 1) * 4;
         rc = sl_persistent_grid(ctx, ks_apply_raises, sm_rp, &grid);
         if (rc) return rc;
+        PROF("ks_apply_raises");
         RB_LAUNCH(grid, kSlThreads, sm_rp, ctx->stream, ks_apply_raises)(raises, e->chunk_prefix, e->sg, g->cbf->dev);
         LAUNCH_CHECK();
         rc = sl_read_flag(ctx, e->overflow, &flag);

@@ -44,6 +44,13 @@ struct rb_ctx {
     int64_t count_launch_index = 0;
     unsigned long long* scratch = nullptr;  // 8-byte device scalar
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // per-kernel CUDA-event timing (rb_ctx_profile_enable / rb_ctx_profile_read): bench.py's roofline numbers come from here
+    struct ProfSpan { const char* name; cudaEvent_t a, b; };
+    bool prof_on = false;
+    const char* prof_pending = nullptr;
+    cudaEvent_t prof_pending_ev = nullptr;
+    std::vector<ProfSpan> prof_spans;
+    std::vector<cudaEvent_t> prof_pool;
 };
 struct rb_filter {
     rb_ctx* ctx;
@@ -81,12 +88,71 @@ static int32_t fail(rb_ctx* c, int32_t code, const std::string& msg) {
                         std::string(#call) + ": " + cudaGetErrorString(e_));                              \
     } while (0)
 #define LOCK(c) std::lock_guard<std::recursive_mutex> lock_((c)->mu); cudaSetDevice((c)->device)
+static void prof_begin(rb_ctx* c, const char* name);
+static void prof_end(rb_ctx* c);
+#define PROF(name) do { if (ctx->prof_on) prof_begin(ctx, name); } while (0)
 #define LAUNCH_CHECK()                                                                                    \
     do {                                                                                                  \
         ++ctx->launches;                                                                                  \
+        if (ctx->prof_pending) prof_end(ctx);                                                             \
         cudaError_t e_ = cudaGetLastError();                                                              \
         if (e_ != cudaSuccess) return fail(ctx, RB_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
     } while (0)
+
+static cudaEvent_t prof_event(rb_ctx* c) {
+    if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+static void prof_begin(rb_ctx* c, const char* name) {
+    c->prof_pending = name;
+    c->prof_pending_ev = prof_event(c);
+    cudaEventRecord(c->prof_pending_ev, c->stream);
+}
+static void prof_end(rb_ctx* c) {
+    cudaEvent_t b = prof_event(c);
+    cudaEventRecord(b, c->stream);
+    c->prof_spans.push_back({c->prof_pending, c->prof_pending_ev, b});
+    c->prof_pending = nullptr;
+}
+extern "C" int32_t rb_ctx_profile_enable(rb_ctx* ctx, int32_t on) {
+    if (!ctx) return RB_EINVAL;
+    LOCK(ctx);
+    ctx->prof_on = on != 0;
+    return RB_OK;
+}
+// Sums the device time of every profiled launch since the last read, per kernel name.  names receives the names joined by '\n'.
+extern "C" int32_t rb_ctx_profile_read(rb_ctx* ctx, char* names, int64_t names_len, float* ms, int32_t* calls, int32_t max_entries, int32_t* n_out) {
+    if (!ctx || !names || !ms || !calls || !n_out || names_len < 1) return RB_EINVAL;
+    LOCK(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<std::string> order;
+    std::vector<double> tot;
+    std::vector<int> cnt;
+    for (auto& sp : ctx->prof_spans) {
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, sp.a, sp.b));
+        size_t i = 0;
+        while (i < order.size() && order[i] != sp.name) ++i;
+        if (i == order.size()) { order.push_back(sp.name); tot.push_back(0.0); cnt.push_back(0); }
+        tot[i] += t; cnt[i] += 1;
+        ctx->prof_pool.push_back(sp.a); ctx->prof_pool.push_back(sp.b);
+    }
+    ctx->prof_spans.clear();
+    std::string joined;
+    int32_t n = 0;
+    for (size_t i = 0; i < order.size() && n < max_entries; ++i) {
+        if ((int64_t)(joined.size() + order[i].size() + 2) > names_len) break;
+        if (n) joined += "\n";
+        joined += order[i];
+        ms[n] = (float)tot[i]; calls[n] = cnt[i];
+        ++n;
+    }
+    memcpy(names, joined.c_str(), joined.size() + 1);
+    *n_out = n;
+    return RB_OK;
+}
 
 static FastMod make_fm(int64_t size) {
     FastMod fm;
@@ -154,6 +220,8 @@ extern "C" int32_t rb_ctx_destroy(rb_ctx* ctx) {
         if (ctx->claim) cudaFree(ctx->claim);
         if (ctx->scratch) cudaFree(ctx->scratch);
         if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
+        for (auto& sp : ctx->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+        for (auto e : ctx->prof_pool) cudaEventDestroy(e);
         if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     }
     delete ctx;
@@ -867,6 +935,7 @@ static int32_t insert_launch(rb_ctx* ctx, const Ingest& ing, void* user) {
     if (u->policy == POLICY_ADD) { const int32_t rc = claim_reserve(ctx, ing.n_pos, gd.dbg.words, &gd.ct); if (rc) return rc; }
     const int grid = (int)div_up(div_up(ing.n_pos, kChunk), kThreads);
     const int maxh = u->g->hmax;
+    PROF("k_graph_insert");
     if (maxh <= 2) launch_insert_mode<2>(u->mode, u->policy, grid, ctx->stream, ing, gd);
     else if (maxh <= 3) launch_insert_mode<3>(u->mode, u->policy, grid, ctx->stream, ing, gd);
     else if (maxh <= 4) launch_insert_mode<4>(u->mode, u->policy, grid, ctx->stream, ing, gd);
@@ -1038,6 +1107,7 @@ static int32_t count_launch(rb_ctx* ctx, const Ingest& ing_in, void* user) {
     }
     const int grid = (int)div_up(div_up(ing.n_pos, kChunk), kThreads);
     const int maxh = u->g->hmax;
+    if (!bucketed_done) PROF("k_graph_count");
     if (bucketed_done) { /* counts are already in dc */ }
     else if (maxh <= 2) launch_count_mode<2>(u->mode, grid, ctx->stream, ing, gd, dc, df, dr);
     else if (maxh <= 3) launch_count_mode<3>(u->mode, grid, ctx->stream, ing, gd, dc, df, dr);

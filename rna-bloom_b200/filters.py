@@ -51,6 +51,20 @@ class Context:
     def kernel_launches(self):
         return self.L.rb_ctx_kernel_launches(self.h)
 
+    def profile_enable(self, on=True):
+        """Per-kernel CUDA-event timing of the read-level engines (measurement only)."""
+        self.check(self.L.rb_ctx_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        """{kernel name: (summed ms, launches)} since the last read."""
+        names = C.create_string_buffer(8192)
+        ms = (C.c_float * 64)()
+        calls = (C.c_int32 * 64)()
+        n = C.c_int32()
+        self.check(self.L.rb_ctx_profile_read(self.h, names, 8192, ms, calls, 64, C.byref(n)))
+        ns = names.value.decode().split("\n") if n.value else []
+        return {ns[i]: (float(ms[i]), int(calls[i])) for i in range(n.value)}
+
     def timer_start(self):
         self.check(self.L.rb_timer_start(self.h))
 

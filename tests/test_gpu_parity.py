@@ -18,16 +18,38 @@ pytestmark = pytest.mark.gpu
 hx = lambda s: int(s, 16)  # noqa: E731
 
 
-@pytest.fixture(autouse=True, params=["direct", "bucketed"])
+# tests whose calls go through an execution engine (read-level insert / lookup on a graph); everything else runs once
+ENGINE_TESTS = {"test_graph_add_collision_free_is_bit_exact", "test_duplicates_inside_one_batch_are_linearised",
+                "test_loaded_filter_dbgbf_exact_cbf_within_envelope", "test_insert_policies_and_pair_filters", "test_pairs_existing_only",
+                "test_fastq_ascii_ingest_matches_regex_segmentation", "test_getkmers_with_invalid_nucleotides",
+                "test_subbatching_and_claim_table_recycling_do_not_change_results", "test_full_size_filters_properties",
+                "test_upload_download_save_load_roundtrip"}
+# "sliced-small": slices of 16 KiB / 32 KiB so that the small test filters span hundreds of regions (the default 64 MiB slices
+# would put every test filter into one or two regions and leave the multi-region paths to the full-size test alone)
+SMALL_SLICES = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_RAISE_LOG2": "14", "RB_SLICE_TABLE_LOG2": "10"}
+
+
+@pytest.fixture(autouse=True, params=["direct", "bucketed", "sliced", "sliced-small"])
 def engine(request):
-    """Every test runs once per execution engine of the read-level calls (RB_ENGINE is read when a graph is created)."""
-    old = os.environ.get("RB_ENGINE")
-    os.environ["RB_ENGINE"] = request.param
+    """Engine-dependent tests run once per execution engine of the read-level calls (RB_ENGINE is read when a graph is created)."""
+    name = request.node.originalname or request.node.name
+    if request.param != "direct" and name not in ENGINE_TESTS:
+        pytest.skip("engine independent")
+    if request.param == "sliced-small" and name == "test_full_size_filters_properties":
+        pytest.skip("full-size filters use the production slice geometry")
+    keys = ["RB_ENGINE"] + list(SMALL_SLICES)
+    old = {k: os.environ.get(k) for k in keys}
+    os.environ["RB_ENGINE"] = request.param.split("-")[0]
+    for k in SMALL_SLICES:
+        os.environ.pop(k, None)
+    if request.param == "sliced-small":
+        os.environ.update(SMALL_SLICES)
     yield request.param
-    if old is None:
-        os.environ.pop("RB_ENGINE", None)
-    else:
-        os.environ["RB_ENGINE"] = old
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
 
 
 @pytest.fixture(scope="module")
