@@ -10,12 +10,13 @@
 //
 //   lookup (graph.getKmers / getCount, graph/BloomFilterDeBruijnGraph.java:562-570)
 //     S1 ks_route_lookup    hash every k-mer, tile-sort its h_d + h_c probes by filter slice, remember the positions
+//        (_u: uniform read layout -- the k-mers of a CTA are hashed through XOR-prefix arrays of rotated base seeds)
 //     S2 ks_apply_probes<0> slice by slice: read bit / counter, write the answer byte
 //     S3 ks_combine_lookup  gather the answers: count = MiniFloat(min counter) + 1 if all bits are set
 //   insert (graph.add, :405-412; addCountIfPresent :424-428; addDbgOnly :430-436)
-//     I1 ks_route_keys      tile-sort the base hashes by key range
-//     I2 ks_aggregate       key range by key range: (key -> multiplicity) in an L2-resident slice of a hash table
-//     I3 ks_compact_table   occupied slots -> dense (key, multiplicity) arrays
+//     I1 ks_route_keys      tile-sort the base hashes by key range (top bits of a multiplicative hash of the key)
+//     I2 ks_split_keys      tile-sort every range again by the next hash bits: sub-ranges of ~1 Ki keys
+//     I3 ks_dedup           one CTA per sub-range: (key -> multiplicity) in a shared-memory hash table -> dense distinct keys
 //     I4 ks_emit_probes     per distinct key: probes tile-sorted by filter slice, positions remembered
 //     I5 ks_apply_probes<1> test-and-set the dbgbf bits (old bit is the answer), read the counters
 //     I6 ks_combine_insert  present = AND(old bits); replay m-1+present min-increments on the counter values
@@ -44,10 +45,13 @@ constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
 
 struct SlArena {
     void* data;               // records; region b = [roff[b], roff[b+1])
-    unsigned int* cursor;     // [B * kSlPad] records appended to region b so far (may pass the capacity: overflow)
-    const uint32_t* roff;     // [B + 1] region offsets in records (the whole arena holds < 2^32 records)
+    unsigned int* cursor;     // [B * cursor_stride] records appended to region b so far (may pass the capacity: overflow)
+    const uint32_t* roff;     // [B + 1] region offsets in records (the whole arena holds < 2^32 records), or nullptr (see cap)
     int B;
     int chunk;                // records per work item of the kernels that consume the arena region by region
+    uint32_t cap;             // roff == nullptr: every region holds cap records, region b = [b * cap, (b + 1) * cap)
+    int cursor_stride;        // cursor of region b = cursor[b * cursor_stride] (kSlPad when the regions are few and hot)
+    int rank_mode;            // SL_RANK_BALLOT / SL_RANK_ATOMS (TileSort)
 };
 struct SlGeom {
     FastMod dbg_fm, cbf_fm;   // global index arithmetic (reference semantics)
@@ -55,12 +59,6 @@ struct SlGeom {
     int dbg_log2, cbf_log2;   // slice sizes: 2^dbg_log2 bits, 2^cbf_log2 bytes
     int n_dbg, n_cbf;         // probe region = dbgbf slice, or n_dbg + cbf slice
     int raise_log2, n_raise;  // counter raises: record = slice-local byte index | value << raise_log2 (raise_log2 <= 25)
-};
-struct SlTable {
-    unsigned long long* keys;   // T + 1 slots, 0 = empty; slot T stands for key 0
-    unsigned int* counts;
-    uint64_t n_slots;           // T (power of two)
-    int shift;                  // slot = mixkey >> shift
 };
 __device__ __forceinline__ uint64_t sl_mixkey(uint64_t key) { return key * 0x9E3779B97F4A7C15ULL; }
 
@@ -95,62 +93,129 @@ __device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t* v, int n, uint3
 }
 
 // ---- CTA-wide multisplit of up to 256 * E records into the regions of an arena -------------------------------------------------
+// Ranking (which place a record takes inside its (tile, bucket) run):
+//   ballot (default)  the 32 lanes of a warp find their same-bucket peers with one __ballot_sync per bucket-id bit (what
+//                     cub::BlockRadixRank's match path does); the first peer bumps a warp-private 16-bit counter, no atomics.
+//                     ~45 issue slots per row of 32 records.
+//   atoms             shared-memory atomicAdd whose return value is the rank; ATOMS costs 1-2 cycles per *lane* on this part
+//                     (B300_MICROARCH.md "Atomics"; measured here: ks_route_lookup 19 cycles per k-mer and SM, 6 ATOMS each).
+// Then: per-bucket totals, one global cursor bump per (tile, bucket) -- issued early, consumed after the scan and the staging so
+// its ~1 us round trip overlaps them --, records staged in bucket order, copied out so that consecutive threads write
+// consecutive addresses.
+enum { SL_RANK_BALLOT = 0, SL_RANK_ATOMS = 1 };
+constexpr int kSlWarps = kSlThreads / 32;
+constexpr int kSlBucketsPerThread = kSlMaxRegions / kSlThreads;
+__device__ __forceinline__ uint32_t sl_region_lo(const SlArena& a, int region) { return a.roff ? __ldg(&a.roff[region]) : (uint32_t)region * a.cap; }
+__device__ __forceinline__ uint32_t sl_region_hi(const SlArena& a, int region) { return a.roff ? __ldg(&a.roff[region + 1]) : (uint32_t)(region + 1) * a.cap; }
 template <typename REC, int E>
 struct TileSort {
     uint32_t *start, *gdst, *glim, *scratch;   // [B] [B] [B] [296]
+    uint16_t* whist;                           // [8 * B] per-warp counters, then per-warp offsets inside the (tile, bucket) run
     REC* stage;                                // [256 * E] records in bucket order
     uint16_t* tag;                             // [256 * E] bucket of each staged record
-    int B;
-    static size_t smem_bytes(int B) {
-        const size_t words = ((size_t)3 * B + 296 + 3) & ~(size_t)3;
-        return words * 4 + (size_t)kSlThreads * E * sizeof(REC) + (size_t)kSlThreads * E * 2;
-    }
+    int B, nbits;
+    static __host__ __device__ size_t words_of(int B) { return ((size_t)3 * B + 296 + (size_t)kSlWarps * B / 2 + 4 + 3) & ~(size_t)3; }
+    static __host__ __device__ size_t smem_bytes(int B) { return words_of(B) * 4 + (size_t)kSlThreads * E * sizeof(REC) + (size_t)kSlThreads * E * 2; }
     __device__ __forceinline__ void init(unsigned char* smem, int B_) {
         B = B_;
+        nbits = 0;
+        while ((1 << nbits) < B) ++nbits;
         start = reinterpret_cast<uint32_t*>(smem);
         gdst = start + B;
         glim = gdst + B;
         scratch = glim + B;
-        const size_t words = ((size_t)3 * B + 296 + 3) & ~(size_t)3;
+        whist = reinterpret_cast<uint16_t*>(scratch + 296);
+        const size_t words = ((size_t)3 * B + 296 + (size_t)kSlWarps * B / 2 + 4 + 3) & ~(size_t)3;
         stage = reinterpret_cast<REC*>(smem + words * 4);
         tag = reinterpret_cast<uint16_t*>(smem + words * 4 + (size_t)kSlThreads * E * sizeof(REC));
     }
-    // bkt[e] < 0: no record.  slot[e] receives the arena position the record was written to (kNoSlot: none, or dropped because its
-    // region is full -- *overflow is set then).  Every thread of the CTA must call it.
-    __device__ __forceinline__ void run(const SlArena& out, const int (&bkt)[E], const REC (&rec)[E], uint32_t (&slot)[E], int* overflow) {
-        const int t = threadIdx.x;
-        for (int b = t; b < B; b += kSlThreads) start[b] = 0;
-        __syncthreads();
-        uint32_t br[E];   // bucket | rank inside (tile, bucket) << 12
+    // bkt[e] < 0: no record, else the record goes to region region0 + bkt[e] of `out`.  slot[e] receives the arena position it was
+    // written to (kNoSlot: none, or dropped because its region is full -- *overflow is set then).  Every thread of the CTA calls it.
+    __device__ __forceinline__ void run(const SlArena& out, int region0, const int (&bkt)[E], const REC (&rec)[E], uint32_t (&slot)[E], int* overflow) {
+        const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+        uint32_t br[E];   // bucket | place inside the (tile, bucket) run << 12
+        uint32_t at[kSlBucketsPerThread];
+        if (out.rank_mode == SL_RANK_ATOMS) {
+            for (int b = t; b < B; b += kSlThreads) start[b] = 0;
+            __syncthreads();
 #pragma unroll
-        for (int e = 0; e < E; ++e) br[e] = bkt[e] >= 0 ? ((uint32_t)bkt[e] | (atomicAdd(&start[bkt[e]], 1u) << 12)) : 0xFFFu;
-        __syncthreads();
-        for (int b = t; b < B; b += kSlThreads) {   // one cursor bump per (tile, bucket)
-            const uint32_t c = start[b];
-            uint32_t lo = 0, hi = 0, at = 0;
-            if (c) {
-                lo = __ldg(&out.roff[b]);
-                hi = __ldg(&out.roff[b + 1]);
-                at = atomicAdd(&out.cursor[(size_t)b * kSlPad], c);
-                if (at > hi - lo) at = hi - lo;
-                if (at + c > hi - lo) *overflow = 1;
+            for (int e = 0; e < E; ++e) br[e] = bkt[e] >= 0 ? ((uint32_t)bkt[e] | (atomicAdd(&start[bkt[e]], 1u) << 12)) : 0xFFFu;
+            __syncthreads();
+        } else {
+            uint32_t* wz = reinterpret_cast<uint32_t*>(whist);
+            for (int i = t; i < (kSlWarps * B + 1) / 2; i += kSlThreads) wz[i] = 0;
+            __syncthreads();
+            uint16_t* mine = whist + warp * B;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const bool valid = bkt[e] >= 0;
+                const uint32_t b = valid ? (uint32_t)bkt[e] : 0u;
+                uint32_t peers = __ballot_sync(0xffffffffu, valid);
+                for (int bit = 0; bit < nbits; ++bit) {
+                    const uint32_t one = (b >> bit) & 1u;
+                    const uint32_t v = __ballot_sync(0xffffffffu, one);
+                    peers &= one ? v : ~v;
+                }
+                const int leader = __ffs(peers) - 1;   // a valid lane is its own peer, so peers != 0 there
+                uint32_t base = 0;
+                if (valid && lane == leader) { base = mine[b]; mine[b] = (uint16_t)(base + __popc(peers)); }
+                __syncwarp();
+                base = __shfl_sync(0xffffffffu, base, valid ? leader : lane);
+                br[e] = valid ? (b | ((base + __popc(peers & ((1u << lane) - 1u))) << 12)) : 0xFFFu;
             }
-            gdst[b] = lo + at;
-            glim[b] = hi;
+            __syncthreads();
+        }
+        // per-bucket totals; warp counters become warp offsets; the cursor bumps go out now and are consumed after the staging
+#pragma unroll
+        for (int q = 0; q < kSlBucketsPerThread; ++q) {
+            const int b = t + q * kSlThreads;
+            at[q] = 0;
+            if (b < B) {
+                uint32_t run = start[b];
+                if (out.rank_mode != SL_RANK_ATOMS) {
+                    run = 0;
+#pragma unroll
+                    for (int w = 0; w < kSlWarps; ++w) { const uint32_t c = whist[w * B + b]; whist[w * B + b] = (uint16_t)run; run += c; }
+                    start[b] = run;
+                }
+                if (run) at[q] = atomicAdd(&out.cursor[(size_t)(region0 + b) * out.cursor_stride], run);
+            }
         }
         const uint32_t total = cta_exclusive_scan(start, B, scratch);   // start[b] = staging position of the bucket's first record
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            slot[e] = kNoSlot;
             if ((br[e] & 0xFFFu) != 0xFFFu) {
-                const uint32_t b = br[e] & 0xFFFu, r = br[e] >> 12;
-                const uint32_t p = start[b] + r, d = gdst[b] + r;
+                const uint32_t b = br[e] & 0xFFFu;
+                uint32_t r = br[e] >> 12;
+                if (out.rank_mode != SL_RANK_ATOMS) r += whist[warp * B + b];
+                const uint32_t p = start[b] + r;
                 stage[p] = rec[e];
                 tag[p] = (uint16_t)b;
-                if (d < glim[b]) slot[e] = d;
+                br[e] = b | (r << 12);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kSlBucketsPerThread; ++q) {
+            const int b = t + q * kSlThreads;
+            if (b < B) {
+                const uint32_t cnt = (b + 1 < B ? start[b + 1] : total) - start[b];
+                const uint32_t lo = sl_region_lo(out, region0 + b), hi = sl_region_hi(out, region0 + b);
+                uint32_t a = at[q];
+                if (a > hi - lo) a = hi - lo;
+                if (cnt && a + cnt > hi - lo) *overflow = 1;
+                gdst[b] = lo + a;
+                glim[b] = hi;
             }
         }
         __syncthreads();
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            slot[e] = kNoSlot;
+            if ((br[e] & 0xFFFu) != 0xFFFu) {
+                const uint32_t b = br[e] & 0xFFFu, d = gdst[b] + (br[e] >> 12);
+                if (d < glim[b]) slot[e] = d;
+            }
+        }
         REC* data = reinterpret_cast<REC*>(out.data);
         for (uint32_t p = t; p < total; p += kSlThreads) {   // consecutive threads -> consecutive addresses inside a bucket's run
             const uint32_t b = tag[p];
@@ -195,6 +260,155 @@ __device__ __forceinline__ void sl_load_answers(const uint32_t* pos, int64_t fir
     for (int e = 0; e < kSlRoundKmers * kSlNJ; ++e) a[e] = slot[e] != kNoSlot ? (uint32_t)__ldg(ans + slot[e]) : 0u;
 }
 
+// ---- prefix k-merizer (uniform read layout) ----------------------------------------------------------------------------------------------
+// ntHash is a XOR of rotated per-base seeds (bloom/hash/NTHash.java:332-373), so with x = index of a base in the CTA's span of the
+// packed stream,  Gf(x) = rotl(S[b_x], -x),  Gr(x) = rotl(S[3-b_x], x)  and their XOR-prefixes Pf, Pr:
+//     forward  hash of the k-mer at x = rotl(Pf(x+k) ^ Pf(x), x+k-1)        reverse hash = rotr(Pr(x+k) ^ Pr(x), x)
+// -- two prefix look-ups per strand and k-mer, no k-step seeding and no per-thread rolling state (the rolling recurrence :584-629 is
+// this sum evaluated incrementally).  Masked / non-ACGT bases contribute 0 exactly as in the walker (NTHash.java:39-43 "N" seed),
+// and a prefix count of them gives the number of unusable bases in any window.  The span (garbage between reads included:
+// it cancels in Pf(x+k) ^ Pf(x)) is scanned once per CTA: 8 bases per thread, warp-shuffle XOR-scan of the thread totals.
+constexpr int kPfxPer = 8;
+constexpr int kPfxSpan = kSlThreads * kPfxPer;   // bases a CTA can cover
+constexpr int kSlTile = kSlThreads * kSlRoundKmers;   // k-mer positions per CTA of the uniform-layout kernels
+struct PrefixKmerizer {
+    unsigned long long *lf, *lr, *of, *orv;   // [kPfxSpan + 8] thread-local exclusive prefixes, [257] thread offsets
+    uint16_t* lb; uint32_t* ob;               // masked-base counts
+    int64_t abs_lo;
+    static size_t smem_bytes() { return (size_t)(kPfxSpan + 8) * 16 + 264 * 16 + (size_t)(kPfxSpan + 8) * 2 + 264 * 4 + 3 * kSlWarps * 8; }
+    __device__ __forceinline__ int64_t abs_of(const Ingest& g, int64_t p) const {   // first base of launch-local position p
+        const int64_t read = p / g.uniform_npos;
+        return g.first_base + read * g.uniform_stride + (p - read * g.uniform_npos);
+    }
+    // every thread of the CTA calls it; tile0 = first position of the CTA
+    template <int MODE>
+    __device__ __forceinline__ void build(unsigned char* smem, const Ingest& g, int k, int64_t tile0) {
+        lf = reinterpret_cast<unsigned long long*>(smem);
+        lr = lf + (kPfxSpan + 8);
+        of = lr + (kPfxSpan + 8);
+        orv = of + 264;
+        unsigned long long* wtot = orv + 264;                     // [3 * kSlWarps]
+        lb = reinterpret_cast<uint16_t*>(wtot + 3 * kSlWarps);
+        ob = reinterpret_cast<uint32_t*>(lb + (kPfxSpan + 8));
+        const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+        const int64_t last = min(tile0 + kSlTile, g.n_pos) - 1;
+        abs_lo = abs_of(g, tile0);
+        const int span = (int)(abs_of(g, last) + k - abs_lo);   // <= kPfxSpan (the host checks the layout)
+        BaseCursor cur;
+        cur.seek(g.packed, g.mask, abs_lo + (int64_t)t * kPfxPer);
+        unsigned long long xf = 0, xr = 0;
+        uint32_t xb = 0;
+#pragma unroll
+        for (int i = 0; i < kPfxPer; ++i) {
+            const int x = t * kPfxPer + i;
+            lf[x] = xf; lr[x] = xr; lb[x] = (uint16_t)xb;
+            if (x < span) {
+                const int c = cur.next();
+                if (c & 4) ++xb;
+                else {
+                    if (MODE != 1) xf ^= rotl64(seed_of_code(c & 3), 64 - (x & 63));
+                    if (MODE != 0) xr ^= rotl64(seed_of_code(3 - (c & 3)), x & 63);
+                }
+            }
+        }
+        // exclusive scan of the thread totals: inclusive warp scans, then the totals of the warps before
+        unsigned long long sf = xf, sr = xr;
+        uint32_t sb = xb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long yf = __shfl_up_sync(0xffffffffu, sf, o), yr = __shfl_up_sync(0xffffffffu, sr, o);
+            const uint32_t yb = __shfl_up_sync(0xffffffffu, sb, o);
+            if (lane >= o) { sf ^= yf; sr ^= yr; sb += yb; }
+        }
+        if (lane == 31) { wtot[warp] = sf; wtot[kSlWarps + warp] = sr; wtot[2 * kSlWarps + warp] = sb; }
+        __syncthreads();
+        unsigned long long ef = sf ^ xf, er = sr ^ xr;
+        uint32_t eb = sb - xb;
+        for (int w = 0; w < warp; ++w) { ef ^= wtot[w]; er ^= wtot[kSlWarps + w]; eb += (uint32_t)wtot[2 * kSlWarps + w]; }
+        of[t] = ef; orv[t] = er; ob[t] = eb;
+        if (t == kSlThreads - 1) {
+            of[kSlThreads] = ef ^ xf; orv[kSlThreads] = er ^ xr; ob[kSlThreads] = eb + xb;
+            lf[kPfxSpan] = 0; lr[kPfxSpan] = 0; lb[kPfxSpan] = 0;
+        }
+        __syncthreads();
+    }
+    // hashes of launch-local position p; bad = number of unusable bases in the window
+    template <int MODE>
+    __device__ __forceinline__ void eval(const Ingest& g, int k, int64_t p, uint64_t& f, uint64_t& r, int& bad) const {
+        const int x = (int)(abs_of(g, p) - abs_lo), y = x + k;
+        f = 0; r = 0;
+        if (MODE != 1) f = rotl64((lf[y] ^ of[y >> 3]) ^ (lf[x] ^ of[x >> 3]), (y - 1) & 63);
+        if (MODE != 0) r = rotr64((lr[y] ^ orv[y >> 3]) ^ (lr[x] ^ orv[x >> 3]), x & 63);
+        bad = (int)((lb[y] + ob[y >> 3]) - (lb[x] + ob[x >> 3]));
+    }
+    template <int MODE>
+    static __device__ __forceinline__ uint64_t base_of(uint64_t f, uint64_t r) {
+        if (MODE == 0) return f;
+        if (MODE == 1) return r;
+        return ((int64_t)r < (int64_t)f) ? r : f;   // canonical: signed min (NTHash.java:494)
+    }
+};
+
+// ---- S1 (uniform layout): one CTA = 1024 consecutive k-mer positions, hashed through the prefix arrays, one tile sort -------------------
+template <int MODE>
+__global__ void __launch_bounds__(kSlThreads) ks_route_lookup_u(const Ingest g, int k, const HashMults hm, const SlGeom sg, const SlArena arena,
+                                                               uint32_t* __restrict__ pos, int64_t* __restrict__ fhash, int64_t* __restrict__ rhash,
+                                                               int* overflow) {
+    RB_DYN_SMEM(unsigned char, sl_smem);
+    const int64_t tile0 = (int64_t)blockIdx.x * kSlTile;
+    PrefixKmerizer pk;
+    pk.build<MODE>(sl_smem, g, k, tile0);
+    const int64_t p0 = tile0 + (int64_t)threadIdx.x * kSlRoundKmers;
+    int bkt[kSlRoundKmers * kSlNJ];
+    uint32_t rec[kSlRoundKmers * kSlNJ], slot[kSlRoundKmers * kSlNJ];
+#pragma unroll
+    for (int i = 0; i < kSlRoundKmers; ++i) {
+#pragma unroll
+        for (int j = 0; j < kSlNJ; ++j) { bkt[i * kSlNJ + j] = -1; rec[i * kSlNJ + j] = 0; }
+        if (p0 + i < g.n_pos) {
+            uint64_t f, r; int bad;
+            pk.eval<MODE>(g, k, p0 + i, f, r, bad);
+            if (fhash) fhash[g.out_base + p0 + i] = (int64_t)f;
+            if (rhash) rhash[g.out_base + p0 + i] = (int64_t)r;
+            if (bad == 0) sl_probes(sg, hm, PrefixKmerizer::base_of<MODE>(f, r), true, &bkt[i * kSlNJ], &rec[i * kSlNJ]);
+        }
+    }
+    __syncthreads();   // the tile sort reuses the shared memory of the prefix arrays
+    TileSort<uint32_t, kSlRoundKmers * kSlNJ> ts;
+    ts.init(sl_smem, arena.B);
+    ts.run(arena, 0, bkt, rec, slot, overflow);
+    if (p0 < g.n_pos) sl_store_positions(pos, p0, slot);
+}
+// ---- I1 (uniform layout) -------------------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kSlThreads) ks_route_keys_u(const Ingest g, int k, int n_ranges, int range_shift, const SlArena arena, int* overflow) {
+    RB_DYN_SMEM(unsigned char, sl_smem);
+    const int64_t tile0 = (int64_t)blockIdx.x * kSlTile;
+    PrefixKmerizer pk;
+    pk.build<MODE>(sl_smem, g, k, tile0);
+    const int64_t p0 = tile0 + (int64_t)threadIdx.x * kSlRoundKmers;
+    int bkt[kSlRoundKmers];
+    unsigned long long rec[kSlRoundKmers];
+    uint32_t slot[kSlRoundKmers];
+#pragma unroll
+    for (int i = 0; i < kSlRoundKmers; ++i) {
+        bkt[i] = -1; rec[i] = 0;
+        if (p0 + i < g.n_pos) {
+            uint64_t f, r; int bad;
+            pk.eval<MODE>(g, k, p0 + i, f, r, bad);
+            if (bad == 0) {
+                const uint64_t b = PrefixKmerizer::base_of<MODE>(f, r);
+                rec[i] = b;
+                bkt[i] = n_ranges > 1 ? (int)(sl_mixkey(b) >> range_shift) : 0;
+            }
+        }
+    }
+    __syncthreads();
+    TileSort<unsigned long long, kSlRoundKmers> ts;
+    ts.init(sl_smem, arena.B);
+    ts.run(arena, 0, bkt, rec, slot, overflow);
+}
+
 // ---- S1: k-merise, tile-sort the probes of every usable k-mer instance by filter slice --------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(kSlThreads) ks_route_lookup(const Ingest g, int k, const HashMults hm, const SlGeom sg, const SlArena arena,
@@ -225,7 +439,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_route_lookup(const Ingest g, in
                 if (pw.wk.bad == 0) sl_probes(sg, hm, pw.wk.base(), true, &bkt[i * kSlNJ], &rec[i * kSlNJ]);
             }
         }
-        ts.run(arena, bkt, rec, slot, overflow);
+        ts.run(arena, 0, bkt, rec, slot, overflow);
         if (r0 < n) sl_store_positions(pos, pos0 + r0, slot);
     }
 }
@@ -236,8 +450,8 @@ __global__ void __launch_bounds__(kSlThreads) ks_chunk_prefix(const SlArena aren
     uint32_t* v = reinterpret_cast<uint32_t*>(sl_smem);
     uint32_t* scratch = v + ((arena.B + 3) & ~3);
     for (int b = threadIdx.x; b < arena.B; b += kSlThreads) {
-        const uint32_t cap = arena.roff[b + 1] - arena.roff[b];
-        const uint32_t cnt = min(arena.cursor[(size_t)b * kSlPad], cap);
+        const uint32_t cap = sl_region_hi(arena, b) - sl_region_lo(arena, b);
+        const uint32_t cnt = min(arena.cursor[(size_t)b * arena.cursor_stride], cap);
         v[b] = (cnt + (uint32_t)arena.chunk - 1) / (uint32_t)arena.chunk;
     }
     __syncthreads();
@@ -259,8 +473,8 @@ __device__ __forceinline__ SlWork sl_work_item(const SlArena& arena, const int* 
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= c) lo = mid; else hi = mid; }
     SlWork w;
     w.b = lo;
-    const uint32_t r_lo = __ldg(&arena.roff[lo]), cap = __ldg(&arena.roff[lo + 1]) - r_lo;
-    const uint32_t cnt = min(arena.cursor[(size_t)lo * kSlPad], cap);
+    const uint32_t r_lo = sl_region_lo(arena, lo), cap = sl_region_hi(arena, lo) - r_lo;
+    const uint32_t cnt = min(arena.cursor[(size_t)lo * arena.cursor_stride], cap);
     const uint32_t off = (uint32_t)(c - pre[lo]) * (uint32_t)arena.chunk;
     w.first = r_lo + off;
     w.n = min((uint32_t)arena.chunk, cnt - off);
@@ -309,11 +523,13 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
     }
 }
 
-// ---- S3: gather the answers of 4 k-mer instances per thread, write the counts (graph :562-570) ----------------------------------------
-__global__ void __launch_bounds__(kSlThreads) ks_combine_lookup(const uint32_t* __restrict__ pos, const uint8_t* __restrict__ ans, int64_t n_inst, int hd,
-                                                               int hc, float* __restrict__ counts, int64_t out_base) {
-    const int64_t i0 = ((int64_t)blockIdx.x * kSlThreads + threadIdx.x) * kSlRoundKmers;
-    if (i0 >= n_inst) return;
+// ---- S3: gather the answers, write the counts (graph :562-570) ---------------------------------------------------------------------------
+// Same CTA / thread -> k-mer mapping as the route kernel that wrote the positions (FLAT = 1: ks_route_lookup_u, 1024 consecutive
+// k-mers per CTA; FLAT = 0: ks_route_lookup, 16 consecutive k-mers per thread in 4 rounds): the answers of a CTA round sit in
+// the few hundred runs its tile sort wrote, so the 32 B sectors a CTA gathers from are shared by its own threads (L1 hits)
+// instead of being fetched again by CTAs on other SMs (measured with mismatched mappings: 43 ms per 504 M k-mers).
+__device__ __forceinline__ void sl_counts_of_group(const uint32_t* __restrict__ pos, const uint8_t* __restrict__ ans, int64_t i0, int64_t n_inst, int hd, int hc,
+                                                   float* __restrict__ counts, int64_t out_base) {
     uint32_t slot[kSlRoundKmers * kSlNJ], a[kSlRoundKmers * kSlNJ];
     sl_load_answers(pos, i0, ans, slot, a);
 #pragma unroll
@@ -330,6 +546,21 @@ __global__ void __launch_bounds__(kSlThreads) ks_combine_lookup(const uint32_t* 
                 c = minifloat_to_float(mn) + 1.f;
             }
             counts[out_base + i0 + i] = c;
+        }
+    }
+}
+template <int FLAT>
+__global__ void __launch_bounds__(kSlThreads) ks_combine_lookup(const uint32_t* __restrict__ pos, const uint8_t* __restrict__ ans, int64_t n_inst, int hd,
+                                                               int hc, float* __restrict__ counts, int64_t out_base) {
+    if (FLAT) {
+        const int64_t i0 = ((int64_t)blockIdx.x * kSlThreads + threadIdx.x) * kSlRoundKmers;
+        if (i0 < n_inst) sl_counts_of_group(pos, ans, i0, n_inst, hd, hc, counts, out_base);
+    } else {
+        const int64_t pos0 = ((int64_t)blockIdx.x * kSlThreads + threadIdx.x) * kChunk;
+#pragma unroll 1
+        for (int r0 = 0; r0 < kChunk; r0 += kSlRoundKmers) {
+            if (pos0 + r0 >= n_inst) return;
+            sl_counts_of_group(pos, ans, pos0 + r0, n_inst, hd, hc, counts, out_base);
         }
     }
 }
@@ -361,73 +592,79 @@ __global__ void __launch_bounds__(kSlThreads) ks_route_keys(const Ingest g, int 
             }
         }
     }
-    ts.run(arena, bkt, rec, slot, overflow);
+    ts.run(arena, 0, bkt, rec, slot, overflow);
 }
 
-// ---- I2: aggregate the keys range by range (the slice of the table a range maps to stays in L2 while its keys stream by) ----------------
-__global__ void __launch_bounds__(kSlThreads) ks_aggregate(const SlArena arena, const int* __restrict__ chunk_prefix, const SlTable t) {
+// ---- I2: second-level split: the keys of every range are tile-sorted again by their next hash bits ------------------------------------------
+// After it a sub-range holds ~1 Ki keys: small enough for a shared-memory hash table, so no global table is ever touched
+// (the L2-sliced global table this replaces ran at 4-9 G keys/s: one CAS + one add per key against ~24 B of table per key).
+__global__ void __launch_bounds__(kSlThreads) ks_split_keys(const SlArena in, const int* __restrict__ chunk_prefix, int sub_bits, int sub_shift,
+                                                           const SlArena out, int* overflow) {
     RB_DYN_SMEM(unsigned char, sl_smem);
-    int* pre = reinterpret_cast<int*>(sl_smem);
-    sl_load_prefix(pre, chunk_prefix, arena.B);
-    const int total = pre[arena.B];
-    const unsigned long long* rec = reinterpret_cast<const unsigned long long*>(arena.data);
+    TileSort<unsigned long long, kSlRoundKmers> ts;
+    const int n_sub = 1 << sub_bits;
+    ts.init(sl_smem, n_sub);
+    int* pre = reinterpret_cast<int*>(sl_smem + TileSort<unsigned long long, kSlRoundKmers>::smem_bytes(n_sub));
+    sl_load_prefix(pre, chunk_prefix, in.B);
+    const int total = pre[in.B];
+    const unsigned long long* rec_in = reinterpret_cast<const unsigned long long*>(in.data);
     for (int c = blockIdx.x; c < total; c += gridDim.x) {
-        const SlWork w = sl_work_item(arena, pre, c);
-        constexpr int U = 4;   // keys in flight per thread: the CAS round trip to L2 is the cost
-        for (uint32_t i0 = threadIdx.x; i0 < w.n; i0 += kSlThreads * U) {
-            unsigned long long key[U], old[U];
-            uint64_t s[U];
+        const SlWork w = sl_work_item(in, pre, c);   // in.chunk <= 256 * kSlRoundKmers keys
+        int bkt[kSlRoundKmers];
+        unsigned long long rec[kSlRoundKmers];
+        uint32_t slot[kSlRoundKmers];
 #pragma unroll
-            for (int u = 0; u < U; ++u) key[u] = (i0 + u * kSlThreads < w.n) ? __ldcs(rec + w.first + i0 + u * kSlThreads) : 0ULL;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                s[u] = sl_mixkey(key[u]) >> t.shift;
-                old[u] = 0ULL;
-                if (key[u] != 0ULL) old[u] = atomicCAS(&t.keys[s[u]], 0ULL, key[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (i0 + u * kSlThreads >= w.n) continue;
-                if (key[u] == 0ULL) { atomicAdd(&t.counts[t.n_slots], 1u); continue; }   // key 0 lives in the extra slot
-                uint64_t at = s[u];
-                unsigned long long o = old[u];
-                while (o != 0ULL && o != key[u]) {   // linear probing
-                    if (++at == t.n_slots) at = 0;
-                    o = atomicCAS(&t.keys[at], 0ULL, key[u]);
-                }
-                atomicAdd(&t.counts[at], 1u);
+        for (int i = 0; i < kSlRoundKmers; ++i) {
+            const uint32_t idx = threadIdx.x + i * kSlThreads;
+            bkt[i] = -1; rec[i] = 0;
+            if (idx < w.n) {
+                rec[i] = __ldcs(rec_in + w.first + idx);
+                bkt[i] = n_sub > 1 ? (int)((sl_mixkey(rec[i]) >> sub_shift) & (uint64_t)(n_sub - 1)) : 0;
             }
         }
+        ts.run(out, w.b * n_sub, bkt, rec, slot, overflow);
     }
 }
 
-// ---- I3: occupied table slots -> dense (key, multiplicity) arrays ---------------------------------------------------------------------------
-constexpr int kSlCompactPer = 8;
-__global__ void __launch_bounds__(kSlThreads) ks_compact_table(const SlTable t, unsigned long long* __restrict__ dkey, unsigned int* __restrict__ dmult,
-                                                              unsigned int* n_distinct) {
-    __shared__ unsigned int tile_count, tile_base;
-    const int64_t total = (int64_t)t.n_slots + 1;
-    const int64_t tile0 = (int64_t)blockIdx.x * (kSlThreads * kSlCompactPer);
-    if (threadIdx.x == 0) tile_count = 0;
-    __syncthreads();
-    unsigned int m[kSlCompactPer], rank[kSlCompactPer];
-    unsigned long long key[kSlCompactPer];
-#pragma unroll
-    for (int i = 0; i < kSlCompactPer; ++i) {
-        const int64_t s = tile0 + (int64_t)i * kSlThreads + threadIdx.x;
-        m[i] = s < total ? t.counts[s] : 0u;
-        rank[i] = 0; key[i] = 0;
-        if (m[i]) {
-            key[i] = (s == (int64_t)t.n_slots) ? 0ULL : t.keys[s];
-            rank[i] = atomicAdd(&tile_count, 1u);
+// ---- I3: one CTA per sub-range: (key -> multiplicity) in a shared-memory hash table, distinct keys appended to the dense arrays ----------------
+constexpr int kSlDedupSlots = 8192;   // 64 KiB of keys + 32 KiB of counters; a sub-range holds fewer keys than that (host: cap < slots)
+__global__ void __launch_bounds__(kSlThreads) ks_dedup(const SlArena in, int n_regions, int hash_shift, unsigned long long* __restrict__ dkey,
+                                                      unsigned int* __restrict__ dmult, unsigned int* n_distinct) {
+    RB_DYN_SMEM(unsigned char, sl_smem);
+    unsigned long long* tkeys = reinterpret_cast<unsigned long long*>(sl_smem);
+    unsigned int* tcnt = reinterpret_cast<unsigned int*>(tkeys + kSlDedupSlots);
+    __shared__ unsigned int n_occ, n_zero, out_base;
+    const unsigned long long* rec = reinterpret_cast<const unsigned long long*>(in.data);
+    for (int sr = blockIdx.x; sr < n_regions; sr += gridDim.x) {
+        const uint32_t lo = sl_region_lo(in, sr);
+        const uint32_t n = min(in.cursor[(size_t)sr * in.cursor_stride], sl_region_hi(in, sr) - lo);
+        if (n == 0) continue;   // the whole CTA
+        uint32_t T = 256;
+        while (T < 2 * n && T < (uint32_t)kSlDedupSlots) T <<= 1;
+        for (uint32_t i = threadIdx.x; i < T; i += kSlThreads) { tkeys[i] = 0ULL; tcnt[i] = 0u; }
+        if (threadIdx.x == 0) { n_occ = 0; n_zero = 0; }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n; i += kSlThreads) {
+            const unsigned long long key = __ldcs(rec + lo + i);
+            if (key == 0ULL) { atomicAdd(&n_zero, 1u); continue; }   // 0 marks an empty slot
+            uint32_t s = (uint32_t)((sl_mixkey(key) << hash_shift) >> 40) & (T - 1);   // hash bits the two splits did not use
+            for (;;) {
+                const unsigned long long old = atomicCAS(&tkeys[s], 0ULL, key);
+                if (old == 0ULL || old == key) { atomicAdd(&tcnt[s], 1u); break; }
+                s = (s + 1) & (T - 1);
+            }
         }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < T; i += kSlThreads)
+            if (tcnt[i]) tcnt[i] |= atomicAdd(&n_occ, 1u) << 16;   // multiplicity (< 2^16: a sub-range holds < 8192 keys) | dense rank
+        __syncthreads();
+        if (threadIdx.x == 0) out_base = atomicAdd(n_distinct, n_occ + (n_zero ? 1u : 0u));
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < T; i += kSlThreads)
+            if (tcnt[i]) { const uint32_t d = out_base + (tcnt[i] >> 16); dkey[d] = tkeys[i]; dmult[d] = tcnt[i] & 0xFFFFu; }
+        if (threadIdx.x == 0 && n_zero) { dkey[out_base + n_occ] = 0ULL; dmult[out_base + n_occ] = n_zero; }
+        __syncthreads();
     }
-    __syncthreads();
-    if (threadIdx.x == 0) tile_base = tile_count ? atomicAdd(n_distinct, tile_count) : 0u;
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < kSlCompactPer; ++i)
-        if (m[i]) { dkey[tile_base + rank[i]] = key[i]; dmult[tile_base + rank[i]] = m[i]; }
 }
 
 // ---- I4: the probes of every distinct key, tile-sorted by filter slice ---------------------------------------------------------------------------
@@ -448,7 +685,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_emit_probes(const unsigned long
         for (int j = 0; j < kSlNJ; ++j) { bkt[i * kSlNJ + j] = -1; rec[i * kSlNJ + j] = 0; }
         if (d0 + i < nd) sl_probes(sg, hm, (uint64_t)dkey[d0 + i], with_cbf != 0, &bkt[i * kSlNJ], &rec[i * kSlNJ]);
     }
-    ts.run(arena, bkt, rec, slot, overflow);
+    ts.run(arena, 0, bkt, rec, slot, overflow);
     if (d0 < nd) sl_store_positions(pos, d0, slot);
 }
 
@@ -520,7 +757,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_combine_insert(const unsigned l
             }
         }
     }
-    ts.run(raises, bkt, rec, rslot, overflow);
+    ts.run(raises, 0, bkt, rec, rslot, overflow);
 }
 
 // ---- I7: raise the counters slice by slice ------------------------------------------------------------------------------------------------------

@@ -8,8 +8,8 @@ struct SlicedEngine {
     uint32_t* probe_data; uint8_t* ans; unsigned int* probe_cursor; uint32_t* probe_roff; int probe_B;
     uint32_t* pos;
     // insert: keys by range, hash table, dense distinct keys, raises
-    unsigned long long* key_data; unsigned int* key_cursor; uint32_t* key_roff; int key_B; int key_shift;
-    unsigned long long* tab_keys; unsigned int* tab_counts; int64_t T; int tab_shift;
+    unsigned long long* key_data; unsigned int* key_cursor; uint32_t* key_roff; int key_B; int key_shift;   // level 1: key_B ranges
+    unsigned long long* sub_data; unsigned int* sub_cursor; int sub_bits; uint32_t sub_cap;                   // level 2: key_B << sub_bits sub-ranges
     unsigned long long* dkey; unsigned int* dmult; unsigned int* n_distinct;
     uint32_t* raise_data; unsigned int* raise_cursor; uint32_t* raise_roff;
     int* chunk_prefix;
@@ -21,7 +21,7 @@ static void sliced_engine_free(rb_graph* g) {
     cudaStreamSynchronize(g->ctx->stream);
     cudaFree(e->probe_data); cudaFree(e->ans); cudaFree(e->probe_cursor); cudaFree(e->probe_roff); cudaFree(e->pos);
     cudaFree(e->key_data); cudaFree(e->key_cursor); cudaFree(e->key_roff);
-    cudaFree(e->tab_keys); cudaFree(e->tab_counts); cudaFree(e->dkey); cudaFree(e->dmult); cudaFree(e->n_distinct);
+    cudaFree(e->sub_data); cudaFree(e->sub_cursor); cudaFree(e->dkey); cudaFree(e->dmult); cudaFree(e->n_distinct);
     cudaFree(e->raise_data); cudaFree(e->raise_cursor); cudaFree(e->raise_roff);
     cudaFree(e->chunk_prefix); cudaFree(e->overflow);
     delete e;
@@ -35,8 +35,8 @@ static int env_int(const char* name, int dflt, int lo, int hi) {
 }
 // Consumers walk an arena region by region with a window of grid * chunk records in flight; the window has to stay a small
 // fraction of a region or several filter / table slices are live at once and fall out of L2.
-static int sl_chunk() { return env_int("RB_SLICED_CHUNK", 2048, 256, 1 << 16); }
-static int sl_consumer_occ() { return env_int("RB_SLICED_CONSUMER_OCC", 2, 1, 8); }
+static int sl_chunk() { return env_int("RB_SLICED_CHUNK", 4096, 256, 1 << 16); }
+static int sl_consumer_occ() { return env_int("RB_SLICED_CONSUMER_OCC", 4, 1, 8); }
 static int64_t sl_pow2_at_least(int64_t v) { int64_t p = 1024; while (p < v) p <<= 1; return p; }
 // capacity of a region that expects `expected` records from uniform hashes: 4 % + 8 sigma + a constant
 static int64_t sl_capacity(double expected) { return (int64_t)(expected * 1.04 + 8.0 * std::sqrt(expected + 1.0)) + 2048; }
@@ -71,8 +71,8 @@ static int32_t sliced_engine_get(rb_graph* g, int64_t n_round, SlicedEngine** ou
     SlGeom& sg = e->sg;
     sg.dbg_fm = make_fm(g->dbg->size); sg.cbf_fm = make_fm(g->cbf->size);
     sg.hd = g->hd; sg.hc = g->hc;
-    sg.dbg_log2 = env_int("RB_SLICE_BITS_LOG2", 29, 5, 31);     // 64 MiB of bits
-    sg.cbf_log2 = env_int("RB_SLICE_BYTES_LOG2", 26, 2, 31);    // 64 MiB of counters
+    sg.dbg_log2 = env_int("RB_SLICE_BITS_LOG2", 28, 5, 31);     // 32 MiB of bits
+    sg.cbf_log2 = env_int("RB_SLICE_BYTES_LOG2", 25, 2, 31);    // 32 MiB of counters
     for (;;) {
         sg.n_dbg = (int)std::min<int64_t>(div_up(g->dbg->size, 1LL << sg.dbg_log2), 1 << 20);
         sg.n_cbf = (int)std::min<int64_t>(div_up(g->cbf->size, 1LL << sg.cbf_log2), 1 << 20);
@@ -87,13 +87,15 @@ static int32_t sliced_engine_get(rb_graph* g, int64_t n_round, SlicedEngine** ou
     if (g->hd > kSlMaxH || g->hc > kSlMaxH || sg.n_dbg + sg.n_cbf > kSlMaxRegions || n_raise > kSlMaxRegions) { e->unsupported = true; return RB_OK; }
     const int64_t n_max = sl_pow2_at_least(n_round);
     e->n_max = n_max;
-    e->T = sl_pow2_at_least(2 * n_max);
-    int lgT = 0; while ((1LL << lgT) < e->T) ++lgT;
-    e->tab_shift = 64 - lgT;
-    const int lgRange = env_int("RB_SLICE_TABLE_LOG2", 21, 4, 30);   // table slots per key range (12 B each)
-    const int lgR = std::max(0, std::min(lgT - lgRange, 11));
-    e->key_B = 1 << lgR;
-    e->key_shift = 64 - lgR;
+    // duplicates of a key are found in sub-ranges of ~2^RB_SLICED_SUBRANGE_LOG2 keys (two tile sorts: key_B ranges x 2^sub_bits each)
+    const int lgSub = env_int("RB_SLICED_SUBRANGE_LOG2", 10, 4, 11);
+    int lgS = 0; while ((n_max >> lgSub) > (1LL << lgS)) ++lgS;
+    const int lg1 = std::min((lgS + 1) / 2, 11);
+    e->sub_bits = std::min(lgS - lg1, 11);
+    e->key_B = 1 << lg1;
+    e->key_shift = 64 - lg1;
+    e->sub_cap = (uint32_t)sl_capacity((double)n_max / (double)(1LL << (lg1 + e->sub_bits)));
+    if (e->sub_cap >= (uint32_t)kSlDedupSlots) { e->unsupported = true; return RB_OK; }   // cannot happen with lgSub <= 11, n_max <= 2^29
     e->probe_B = sg.n_dbg + sg.n_cbf;
     // ---- capacities ----
     const double dbg_slices = std::max(1.0, (double)g->dbg->size / (double)(1LL << sg.dbg_log2));
@@ -118,8 +120,10 @@ static int32_t sliced_engine_get(rb_graph* g, int64_t n_round, SlicedEngine** ou
     if (er == cudaSuccess) er = cudaMalloc(&e->pos, ((size_t)n_max + 8) * kSlNJ * 4);
     if (er == cudaSuccess) er = cudaMalloc(&e->key_data, (size_t)key_slots * 8 + 64);
     if (er == cudaSuccess) er = cudaMalloc(&e->key_cursor, (size_t)e->key_B * kSlPad * 4);
-    if (er == cudaSuccess) er = cudaMalloc(&e->tab_keys, (size_t)(e->T + 1) * 8);
-    if (er == cudaSuccess) er = cudaMalloc(&e->tab_counts, (size_t)(e->T + 1) * 4);
+    const int64_t n_sub_regions = (int64_t)e->key_B << e->sub_bits;
+    if (n_sub_regions * e->sub_cap >= (1LL << 32) - (1LL << 20)) { sliced_engine_free(g); return fail(ctx, RB_EINVAL, "sliced engine: round too large for 32-bit record positions"); }
+    if (er == cudaSuccess) er = cudaMalloc(&e->sub_data, (size_t)n_sub_regions * e->sub_cap * 8 + 64);
+    if (er == cudaSuccess) er = cudaMalloc(&e->sub_cursor, (size_t)n_sub_regions * 4 + 64);
     if (er == cudaSuccess) er = cudaMalloc(&e->dkey, ((size_t)n_max + 8) * 8);
     if (er == cudaSuccess) er = cudaMalloc(&e->dmult, ((size_t)n_max + 8) * 4);
     if (er == cudaSuccess) er = cudaMalloc(&e->n_distinct, 64);
@@ -162,7 +166,40 @@ static int32_t sl_chunk_prefix(rb_ctx* ctx, SlicedEngine* e, const SlArena& a) {
     LAUNCH_CHECK();
     return RB_OK;
 }
-static SlArena sl_probe_arena(SlicedEngine* e) { SlArena a; a.data = e->probe_data; a.cursor = e->probe_cursor; a.roff = e->probe_roff; a.B = e->probe_B; a.chunk = sl_chunk(); return a; }
+static int sl_rank_mode() { const char* v = getenv("RB_SLICED_RANK"); return (v && !strcmp(v, "atoms")) ? SL_RANK_ATOMS : SL_RANK_BALLOT; }
+static SlArena sl_arena(void* data, unsigned int* cursor, const uint32_t* roff, int B, int chunk) {
+    SlArena a;
+    a.data = data; a.cursor = cursor; a.roff = roff; a.B = B; a.chunk = chunk; a.cap = 0; a.cursor_stride = kSlPad; a.rank_mode = sl_rank_mode();
+    return a;
+}
+static SlArena sl_probe_arena(SlicedEngine* e) { return sl_arena(e->probe_data, e->probe_cursor, e->probe_roff, e->probe_B, sl_chunk()); }
+
+// the prefix k-merizer covers a CTA's 1024 positions with one span of at most kPfxSpan bases of the packed stream (uniform layout only)
+static bool sl_uniform_fast(const Ingest& ing, int k) {
+    const char* v = getenv("RB_SLICED_KMERIZER");
+    if (v && !strcmp(v, "walker")) return false;
+    if (ing.pos_off || ing.uniform_npos <= 0) return false;
+    const int64_t span = ((int64_t)(kSlTile - 1) / ing.uniform_npos + 1) * ing.uniform_stride + ing.uniform_npos - 1 + k;
+    return span <= kPfxSpan;
+}
+// grid of a kernel that streams over an arena with no residency window to respect
+template <typename K>
+static int32_t sl_stream_grid(rb_ctx* ctx, K kernel, size_t smem, int* grid) {
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kSlThreads, smem));
+    if (occ < 1) return fail(ctx, RB_ECUDA, "sliced engine: kernel does not fit on an SM");
+    *grid = ctx->sm_count * std::min(occ, 8);
+    return RB_OK;
+}
+#define SL_LAUNCH(name, kern, grid, smem, ...)                                   \
+    do {                                                                         \
+        rc = sl_allow_smem(ctx, kern, smem);                                     \
+        if (rc) return rc;                                                       \
+        PROF(name);                                                              \
+        RB_LAUNCH(grid, kSlThreads, smem, ctx->stream, kern)(__VA_ARGS__);       \
+        LAUNCH_CHECK();                                                          \
+    } while (0)
 
 // S1..S3
 static int32_t sliced_count_round(rb_graph* g, const Ingest& ing, int mode, float* counts, int64_t* fh, int64_t* rh, bool* fell_back) {
@@ -174,18 +211,19 @@ static int32_t sliced_count_round(rb_graph* g, const Ingest& ing, int mode, floa
     const HashMults hm = make_hm(g->k);
     const SlArena probes = sl_probe_arena(e);
     CK(cudaMemsetAsync(probes.cursor, 0, (size_t)probes.B * kSlPad * 4, ctx->stream));
-    const int grid_pos = (int)div_up(ing.n_pos, (int64_t)kSlThreads * kChunk);
     const size_t sm_sort = TileSort<uint32_t, kSlRoundKmers * kSlNJ>::smem_bytes(probes.B);
-    if (mode == RB_MODE_FWD) {
-        rc = sl_allow_smem(ctx, ks_route_lookup<0>, sm_sort); if (rc) return rc;
-        PROF("ks_route_lookup<0>");
-        RB_LAUNCH(grid_pos, kSlThreads, sm_sort, ctx->stream, ks_route_lookup<0>)(ing, g->k, hm, e->sg, probes, e->pos, fh, rh, e->overflow);
+    const bool fast = sl_uniform_fast(ing, g->k);
+    int grid_pos;
+    if (fast) {
+        grid_pos = (int)div_up(ing.n_pos, (int64_t)kSlTile);
+        const size_t sm = std::max(sm_sort, PrefixKmerizer::smem_bytes());
+        if (mode == RB_MODE_FWD) SL_LAUNCH("ks_route_lookup_u<0>", ks_route_lookup_u<0>, grid_pos, sm, ing, g->k, hm, e->sg, probes, e->pos, fh, rh, e->overflow);
+        else SL_LAUNCH("ks_route_lookup_u<2>", ks_route_lookup_u<2>, grid_pos, sm, ing, g->k, hm, e->sg, probes, e->pos, fh, rh, e->overflow);
     } else {
-        rc = sl_allow_smem(ctx, ks_route_lookup<2>, sm_sort); if (rc) return rc;
-        PROF("ks_route_lookup<2>");
-        RB_LAUNCH(grid_pos, kSlThreads, sm_sort, ctx->stream, ks_route_lookup<2>)(ing, g->k, hm, e->sg, probes, e->pos, fh, rh, e->overflow);
+        grid_pos = (int)div_up(ing.n_pos, (int64_t)kSlThreads * kChunk);
+        if (mode == RB_MODE_FWD) SL_LAUNCH("ks_route_lookup<0>", ks_route_lookup<0>, grid_pos, sm_sort, ing, g->k, hm, e->sg, probes, e->pos, fh, rh, e->overflow);
+        else SL_LAUNCH("ks_route_lookup<2>", ks_route_lookup<2>, grid_pos, sm_sort, ing, g->k, hm, e->sg, probes, e->pos, fh, rh, e->overflow);
     }
-    LAUNCH_CHECK();
     int flag = 0;
     rc = sl_read_flag(ctx, e->overflow, &flag);
     if (rc) return rc;
@@ -196,13 +234,10 @@ static int32_t sliced_count_round(rb_graph* g, const Ingest& ing, int mode, floa
     int grid = 0;
     rc = sl_persistent_grid(ctx, ks_apply_probes<0>, sm_pre, &grid);
     if (rc) return rc;
-    PROF("ks_apply_probes<0>");
-    RB_LAUNCH(grid, kSlThreads, sm_pre, ctx->stream, ks_apply_probes<0>)(probes, e->chunk_prefix, e->sg, g->dbg->dev, g->cbf->dev, e->ans);
-    LAUNCH_CHECK();
-    const int grid_c = (int)div_up(ing.n_pos, (int64_t)kSlThreads * kSlRoundKmers);
-    PROF("ks_combine_lookup");
-    RB_LAUNCH(grid_c, kSlThreads, 0, ctx->stream, ks_combine_lookup)(e->pos, e->ans, ing.n_pos, g->hd, g->hc, counts, ing.out_base);
-    LAUNCH_CHECK();
+    SL_LAUNCH("ks_apply_probes<0>", ks_apply_probes<0>, grid, sm_pre, probes, e->chunk_prefix, e->sg, g->dbg->dev, g->cbf->dev, e->ans);
+    // same CTA -> k-mer mapping as the route kernel
+    if (fast) SL_LAUNCH("ks_combine_lookup<1>", ks_combine_lookup<1>, grid_pos, 0, e->pos, e->ans, ing.n_pos, g->hd, g->hc, counts, ing.out_base);
+    else SL_LAUNCH("ks_combine_lookup<0>", ks_combine_lookup<0>, grid_pos, 0, e->pos, e->ans, ing.n_pos, g->hd, g->hc, counts, ing.out_base);
     return RB_OK;
 }
 
@@ -215,59 +250,51 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     if (e->unsupported) { *fell_back = true; return RB_OK; }
     const HashMults hm = make_hm(g->k);
     // I1 keys by range
-    SlArena keys; keys.data = e->key_data; keys.cursor = e->key_cursor; keys.roff = e->key_roff; keys.B = e->key_B; keys.chunk = sl_chunk();
+    const SlArena keys = sl_arena(e->key_data, e->key_cursor, e->key_roff, e->key_B, kSlThreads * kSlRoundKmers);
     CK(cudaMemsetAsync(keys.cursor, 0, (size_t)keys.B * kSlPad * 4, ctx->stream));
-    const int grid_pos = (int)div_up(ing.n_pos, (int64_t)kSlThreads * kChunk);
-    const size_t sm_keys = TileSort<unsigned long long, kChunk>::smem_bytes(keys.B);
-    if (mode == RB_MODE_FWD) {
-        rc = sl_allow_smem(ctx, ks_route_keys<0>, sm_keys); if (rc) return rc;
-        PROF("ks_route_keys<0>");
-        RB_LAUNCH(grid_pos, kSlThreads, sm_keys, ctx->stream, ks_route_keys<0>)(ing, g->k, e->key_B, e->key_shift, keys, e->overflow);
-    } else if (mode == RB_MODE_RC) {
-        rc = sl_allow_smem(ctx, ks_route_keys<1>, sm_keys); if (rc) return rc;
-        PROF("ks_route_keys<1>");
-        RB_LAUNCH(grid_pos, kSlThreads, sm_keys, ctx->stream, ks_route_keys<1>)(ing, g->k, e->key_B, e->key_shift, keys, e->overflow);
+    if (sl_uniform_fast(ing, g->k)) {
+        const int grid_pos = (int)div_up(ing.n_pos, (int64_t)kSlTile);
+        const size_t sm = std::max(TileSort<unsigned long long, kSlRoundKmers>::smem_bytes(keys.B), PrefixKmerizer::smem_bytes());
+        if (mode == RB_MODE_FWD) SL_LAUNCH("ks_route_keys_u<0>", ks_route_keys_u<0>, grid_pos, sm, ing, g->k, e->key_B, e->key_shift, keys, e->overflow);
+        else if (mode == RB_MODE_RC) SL_LAUNCH("ks_route_keys_u<1>", ks_route_keys_u<1>, grid_pos, sm, ing, g->k, e->key_B, e->key_shift, keys, e->overflow);
+        else SL_LAUNCH("ks_route_keys_u<2>", ks_route_keys_u<2>, grid_pos, sm, ing, g->k, e->key_B, e->key_shift, keys, e->overflow);
     } else {
-        rc = sl_allow_smem(ctx, ks_route_keys<2>, sm_keys); if (rc) return rc;
-        PROF("ks_route_keys<2>");
-        RB_LAUNCH(grid_pos, kSlThreads, sm_keys, ctx->stream, ks_route_keys<2>)(ing, g->k, e->key_B, e->key_shift, keys, e->overflow);
+        const int grid_pos = (int)div_up(ing.n_pos, (int64_t)kSlThreads * kChunk);
+        const size_t sm_keys = TileSort<unsigned long long, kChunk>::smem_bytes(keys.B);
+        if (mode == RB_MODE_FWD) SL_LAUNCH("ks_route_keys<0>", ks_route_keys<0>, grid_pos, sm_keys, ing, g->k, e->key_B, e->key_shift, keys, e->overflow);
+        else if (mode == RB_MODE_RC) SL_LAUNCH("ks_route_keys<1>", ks_route_keys<1>, grid_pos, sm_keys, ing, g->k, e->key_B, e->key_shift, keys, e->overflow);
+        else SL_LAUNCH("ks_route_keys<2>", ks_route_keys<2>, grid_pos, sm_keys, ing, g->k, e->key_B, e->key_shift, keys, e->overflow);
     }
-    LAUNCH_CHECK();
-    int flag = 0;
-    rc = sl_read_flag(ctx, e->overflow, &flag);
-    if (rc) return rc;
-    if (flag) { *fell_back = true; return RB_OK; }   // extreme key skew: nothing modified yet
-    // I2 aggregate
-    SlTable t; t.keys = e->tab_keys; t.counts = e->tab_counts; t.n_slots = (uint64_t)e->T; t.shift = e->tab_shift;
-    PROF("memset(table)");
-    CK(cudaMemsetAsync(t.keys, 0, (size_t)(e->T + 1) * 8, ctx->stream));
-    CK(cudaMemsetAsync(t.counts, 0, (size_t)(e->T + 1) * 4, ctx->stream));
-    if (ctx->prof_pending) prof_end(ctx);
+    // I2 second-level split (no flag read in between: an overflow of level 1 only drops keys, level 2 then sees fewer)
+    const int n_sub = 1 << e->sub_bits;
+    const int n_sub_regions = e->key_B << e->sub_bits;
+    SlArena subs = sl_arena(e->sub_data, e->sub_cursor, nullptr, n_sub_regions, 0);
+    subs.cap = e->sub_cap; subs.cursor_stride = 1;
+    CK(cudaMemsetAsync(subs.cursor, 0, (size_t)n_sub_regions * 4, ctx->stream));
     rc = sl_chunk_prefix(ctx, e, keys);
     if (rc) return rc;
     int grid = 0;
-    rc = sl_persistent_grid(ctx, ks_aggregate, (size_t)(keys.B + 1) * 4, &grid);
+    const size_t sm_split = TileSort<unsigned long long, kSlRoundKmers>::smem_bytes(n_sub) + (size_t)(keys.B + 1) * 4;
+    rc = sl_stream_grid(ctx, ks_split_keys, sm_split, &grid);
     if (rc) return rc;
-    PROF("ks_aggregate");
-    RB_LAUNCH(grid, kSlThreads, (size_t)(keys.B + 1) * 4, ctx->stream, ks_aggregate)(keys, e->chunk_prefix, t);
-    LAUNCH_CHECK();
-    // I3 dense distinct keys
+    SL_LAUNCH("ks_split_keys", ks_split_keys, grid, sm_split, keys, e->chunk_prefix, e->sub_bits, 64 - (64 - e->key_shift) - e->sub_bits, subs, e->overflow);
+    int flag = 0;
+    rc = sl_read_flag(ctx, e->overflow, &flag);
+    if (rc) return rc;
+    if (flag) { *fell_back = true; return RB_OK; }   // key skew (one k-mer dominating the batch): nothing modified yet
+    // I3 distinct keys and their multiplicities
     CK(cudaMemsetAsync(e->n_distinct, 0, 4, ctx->stream));
-    const int grid_t = (int)div_up(e->T + 1, (int64_t)kSlThreads * kSlCompactPer);
-    PROF("ks_compact_table");
-    RB_LAUNCH(grid_t, kSlThreads, 0, ctx->stream, ks_compact_table)(t, e->dkey, e->dmult, e->n_distinct);
-    LAUNCH_CHECK();
+    const size_t sm_dedup = (size_t)kSlDedupSlots * 12;
+    rc = sl_stream_grid(ctx, ks_dedup, sm_dedup, &grid);
+    if (rc) return rc;
+    SL_LAUNCH("ks_dedup", ks_dedup, std::min(grid, n_sub_regions), sm_dedup, subs, n_sub_regions, (64 - e->key_shift) + e->sub_bits, e->dkey, e->dmult, e->n_distinct);
     // I4 probes by filter slice
     const SlArena probes = sl_probe_arena(e);
     CK(cudaMemsetAsync(probes.cursor, 0, (size_t)probes.B * kSlPad * 4, ctx->stream));
     const int with_cbf = policy != POLICY_DBG_ONLY;
     const size_t sm_sort = TileSort<uint32_t, kSlRoundKmers * kSlNJ>::smem_bytes(probes.B);
-    rc = sl_allow_smem(ctx, ks_emit_probes, sm_sort);
-    if (rc) return rc;
     const int grid_d = (int)div_up(ing.n_pos, (int64_t)kSlThreads * kSlRoundKmers);   // distinct keys <= instances
-    PROF("ks_emit_probes");
-    RB_LAUNCH(grid_d, kSlThreads, sm_sort, ctx->stream, ks_emit_probes)(e->dkey, e->n_distinct, hm, e->sg, with_cbf, probes, e->pos, e->overflow);
-    LAUNCH_CHECK();
+    SL_LAUNCH("ks_emit_probes", ks_emit_probes, grid_d, sm_sort, e->dkey, e->n_distinct, hm, e->sg, with_cbf, probes, e->pos, e->overflow);
     rc = sl_read_flag(ctx, e->overflow, &flag);
     if (rc) return rc;
     if (flag) { *fell_back = true; return RB_OK; }   // still nothing modified
@@ -277,34 +304,24 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     const size_t sm_pre = (size_t)(probes.B + 1) * 4;
     if (policy != POLICY_COUNT_IF_PRESENT) {
         rc = sl_persistent_grid(ctx, ks_apply_probes<1>, sm_pre, &grid); if (rc) return rc;
-        PROF("ks_apply_probes<1>");
-        RB_LAUNCH(grid, kSlThreads, sm_pre, ctx->stream, ks_apply_probes<1>)(probes, e->chunk_prefix, e->sg, g->dbg->dev, g->cbf->dev, e->ans);
+        SL_LAUNCH("ks_apply_probes<1>", ks_apply_probes<1>, grid, sm_pre, probes, e->chunk_prefix, e->sg, g->dbg->dev, g->cbf->dev, e->ans);
     } else {
         rc = sl_persistent_grid(ctx, ks_apply_probes<0>, sm_pre, &grid); if (rc) return rc;
-        PROF("ks_apply_probes<0>");
-        RB_LAUNCH(grid, kSlThreads, sm_pre, ctx->stream, ks_apply_probes<0>)(probes, e->chunk_prefix, e->sg, g->dbg->dev, g->cbf->dev, e->ans);
+        SL_LAUNCH("ks_apply_probes<0>", ks_apply_probes<0>, grid, sm_pre, probes, e->chunk_prefix, e->sg, g->dbg->dev, g->cbf->dev, e->ans);
     }
-    LAUNCH_CHECK();
     if (with_cbf) {
         // I6 + I7
-        SlArena raises; raises.data = e->raise_data; raises.cursor = e->raise_cursor; raises.roff = e->raise_roff; raises.B = e->sg.n_raise; raises.chunk = sl_chunk();
+        const SlArena raises = sl_arena(e->raise_data, e->raise_cursor, e->raise_roff, e->sg.n_raise, sl_chunk());
         CK(cudaMemsetAsync(raises.cursor, 0, (size_t)raises.B * kSlPad * 4, ctx->stream));
         const uint64_t seed = ctx->rng_seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(ctx->launches + 1);
         const size_t sm_r = TileSort<uint32_t, kSlRoundKmers * kSlMaxH>::smem_bytes(raises.B);
-        rc = sl_allow_smem(ctx, ks_combine_insert, sm_r);
-        if (rc) return rc;
-        PROF("ks_combine_insert");
-        RB_LAUNCH(grid_d, kSlThreads, sm_r, ctx->stream, ks_combine_insert)(e->dkey, e->dmult, e->n_distinct, e->pos, e->ans, hm, e->sg, policy, seed, raises,
-                                                                         e->overflow);
-        LAUNCH_CHECK();
+        SL_LAUNCH("ks_combine_insert", ks_combine_insert, grid_d, sm_r, e->dkey, e->dmult, e->n_distinct, e->pos, e->ans, hm, e->sg, policy, seed, raises, e->overflow);
         rc = sl_chunk_prefix(ctx, e, raises);
         if (rc) return rc;
         const size_t sm_rp = (size_t)(raises.B + 1) * 4;
         rc = sl_persistent_grid(ctx, ks_apply_raises, sm_rp, &grid);
         if (rc) return rc;
-        PROF("ks_apply_raises");
-        RB_LAUNCH(grid, kSlThreads, sm_rp, ctx->stream, ks_apply_raises)(raises, e->chunk_prefix, e->sg, g->cbf->dev);
-        LAUNCH_CHECK();
+        SL_LAUNCH("ks_apply_raises", ks_apply_raises, grid, sm_rp, raises, e->chunk_prefix, e->sg, g->cbf->dev);
         rc = sl_read_flag(ctx, e->overflow, &flag);
         if (rc) return rc;
         if (flag) return fail(ctx, RB_ESTATE, "sliced engine: a raise region overflowed after filters were modified (hash skew beyond the slack)");

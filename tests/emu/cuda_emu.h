@@ -112,6 +112,22 @@ static inline T emu_shfl(T v, int src_lane) {
 template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_shfl(v, (int)((threadIdx.x & 31) ^ (unsigned)m)); }
 template <typename T> static inline T __shfl_up_sync(unsigned, T v, int d) { const int l = (int)(threadIdx.x & 31); const T o = emu_shfl(v, l >= d ? l - d : l); return l >= d ? o : v; }
 template <typename T> static inline T __shfl_sync(unsigned, T v, int src) { return emu_shfl(v, src); }
+static inline unsigned __ballot_sync(unsigned, int pred) {   // every lane of the warp must call it (full mask)
+    const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    emu::g_warp_xchg[w][l] = pred ? 1ULL : 0ULL;
+    emu::g_warp_barrier[w]->arrive_and_wait();
+    unsigned m = 0;
+    const unsigned lanes = std::min(32u, blockDim.x - w * 32);
+    for (unsigned i = 0; i < lanes; ++i) m |= (unsigned)emu::g_warp_xchg[w][i] << i;
+    emu::g_warp_barrier[w]->arrive_and_wait();
+    return m;
+}
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline void __syncwarp() {   // every lane of the warp must call it
+    const unsigned w = threadIdx.x >> 5;
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+    emu::g_warp_barrier[w]->arrive_and_wait();
+}
 
 // ---- atomics -----------------------------------------------------------------------------------------------------------
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }

@@ -45,23 +45,34 @@ def ctx(emu_lib):
     c.close()
 
 
-SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_RAISE_LOG2": "14", "RB_SLICE_TABLE_LOG2": "10"}
+SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_RAISE_LOG2": "14", "RB_SLICED_SUBRANGE_LOG2": "6"}
+# The emulated warp ballots cost two OS-level barriers each, so the ballot ranking of the tile sort runs on a few tests only and the
+# shared-memory-atomic ranking (same results, RB_SLICED_RANK=atoms) carries the rest of the matrix; "direct" is here to validate
+# the emulation itself (that engine is verified on the GPU).
+ONLY = {
+    "sliced-small-ballot": ("test_getkmers_with_invalid_nucleotides", "test_duplicates_inside_one_batch_are_linearised",
+                            "test_uniform_layout_graph_matches_oracle"),
+    "sliced-default-atoms": ("test_getkmers_with_invalid_nucleotides", "test_insert_policies_and_pair_filters",
+                             "test_uniform_layout_graph_matches_oracle"),
+    "direct": ("test_getkmers_with_invalid_nucleotides", "test_insert_policies_and_pair_filters"),
+}
 
 
-@pytest.fixture(autouse=True, params=["sliced", "sliced-default-slices", "direct"])
+@pytest.fixture(autouse=True, params=["sliced-small-atoms", "sliced-small-ballot", "sliced-default-atoms", "direct"])
 def engine(request):
-    """sliced: tiny slices so that the small test filters span hundreds of regions; sliced-default-slices: the production geometry."""
+    """small: tiny slices / sub-ranges so that the small test filters span hundreds of regions; default: the production geometry."""
     name = request.node.originalname or request.node.name
-    if request.param == "direct" and name not in ("test_getkmers_with_invalid_nucleotides", "test_insert_policies_and_pair_filters"):
-        pytest.skip("the direct engine is only here to validate the emulation itself (it is verified on the GPU)")
-    keys = ["RB_ENGINE"] + list(SLICE_ENV)
+    if request.param in ONLY and name not in ONLY[request.param]:
+        pytest.skip("not in the reduced matrix of this variant")
+    keys = ["RB_ENGINE", "RB_SLICED_RANK"] + list(SLICE_ENV)
     old = {k: os.environ.get(k) for k in keys}
     os.environ["RB_ENGINE"] = request.param.split("-")[0]
-    if request.param == "sliced":
+    for k in keys[1:]:
+        os.environ.pop(k, None)
+    if "small" in request.param:
         os.environ.update(SLICE_ENV)
-    else:
-        for k in SLICE_ENV:
-            os.environ.pop(k, None)
+    if "atoms" in request.param:
+        os.environ["RB_SLICED_RANK"] = "atoms"
     yield request.param
     for k, v in old.items():
         if v is None:
@@ -77,6 +88,14 @@ test_insert_policies_and_pair_filters = G.test_insert_policies_and_pair_filters
 test_loaded_filter_dbgbf_exact_cbf_within_envelope = G.test_loaded_filter_dbgbf_exact_cbf_within_envelope
 
 
-@pytest.mark.parametrize("stranded,k,hd,hc,n_reads", [(False, 25, 3, 3, 800), (True, 25, 3, 3, 120), (False, 17, 3, 2, 120), (True, 64, 1, 4, 120)])
+@pytest.mark.parametrize("stranded,k,hd,hc,n_reads", [(False, 25, 3, 3, 800), (True, 25, 3, 3, 120), (True, 64, 1, 4, 120)])
 def test_graph_add_collision_free_is_bit_exact(ctx, orc, stranded, k, hd, hc, n_reads):
     G.test_graph_add_collision_free_is_bit_exact(ctx, orc, stranded, k, hd, hc, n_reads)
+
+
+
+# the uniform-layout cases that exercise distinct code paths (tile ends inside a read, read longer than a tile, walker fallback)
+@pytest.mark.parametrize("L,stride,k,n_reads,stranded", [(150, 160, 25, 300, False), (150, 192, 25, 120, True), (3000, 3008, 25, 3, False),
+                                                         (40, 64, 25, 200, False)])
+def test_uniform_layout_graph_matches_oracle(ctx, orc, L, stride, k, n_reads, stranded):
+    G.test_uniform_layout_graph_matches_oracle(ctx, orc, L, stride, k, n_reads, stranded)

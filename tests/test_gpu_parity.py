@@ -23,10 +23,10 @@ ENGINE_TESTS = {"test_graph_add_collision_free_is_bit_exact", "test_duplicates_i
                 "test_loaded_filter_dbgbf_exact_cbf_within_envelope", "test_insert_policies_and_pair_filters", "test_pairs_existing_only",
                 "test_fastq_ascii_ingest_matches_regex_segmentation", "test_getkmers_with_invalid_nucleotides",
                 "test_subbatching_and_claim_table_recycling_do_not_change_results", "test_full_size_filters_properties",
-                "test_upload_download_save_load_roundtrip"}
+                "test_upload_download_save_load_roundtrip", "test_uniform_layout_graph_matches_oracle"}
 # "sliced-small": slices of 16 KiB / 32 KiB so that the small test filters span hundreds of regions (the default 64 MiB slices
 # would put every test filter into one or two regions and leave the multi-region paths to the full-size test alone)
-SMALL_SLICES = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_RAISE_LOG2": "14", "RB_SLICE_TABLE_LOG2": "10"}
+SMALL_SLICES = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_RAISE_LOG2": "14", "RB_SLICED_SUBRANGE_LOG2": "6"}
 
 
 @pytest.fixture(autouse=True, params=["direct", "bucketed", "sliced", "sliced-small"])
@@ -450,6 +450,65 @@ def test_subbatching_and_claim_table_recycling_do_not_change_results(ctx, orc):
         ctx.set_subbatch_kmers(1 << 25)
     c0 = np.concatenate([og.count_seq(s)[0] for s in seqs[:50]])
     assert (counts == c0).all()
+    g.destroy(), og.close()
+
+
+@pytest.mark.parametrize("L,stride,k,n_reads,stranded", [(150, 160, 25, 900, False), (150, 192, 25, 300, True), (100, 128, 31, 500, False),
+                                                         (3000, 3008, 25, 4, False), (40, 64, 25, 700, False), (151, 160, 17, 300, False)])
+def test_uniform_layout_graph_matches_oracle(ctx, orc, L, stride, k, n_reads, stranded):
+    """Uniform (fixed-length, strided) ingest: the sliced engine hashes it through XOR-prefix arrays instead of the rolling walker.
+    Masked bases, padding between reads, tiles that end inside a read, reads longer than a tile, duplicates inside a batch."""
+    rng = np.random.default_rng(L * 7 + k)
+    reads = orc.synth_reads(L + k, max(n_reads * L * 2 // 3, 2 * L), 0, n_reads, L, 6000)   # ~1.5x coverage, twice: counts stay in the exact MiniFloat range
+    code = np.zeros(256, dtype=np.uint8)
+    code[list(b"ACGT")] = [0, 1, 2, 3]
+    codes = code[reads]
+    pr = rb.pack_uniform(codes, stride=stride)
+    # unusable bases: a few random ones plus one read that is mostly masked
+    bad = rng.random((n_reads, L)) < 0.002
+    bad[min(3, n_reads - 1), : L // 2] = True
+    m = np.zeros((n_reads, stride), dtype=np.uint64)
+    m[:, :L] = bad
+    m[:, L:] = 1
+    mask_words = np.bitwise_or.reduce((m << (np.arange(stride) % 32).astype(np.uint64)).reshape(n_reads, stride // 32, 32), axis=2)
+    pr.mask = np.ascontiguousarray(mask_words.reshape(-1).astype(np.uint32))
+    seqs = []
+    for i in range(n_reads):
+        r = bytearray(bytes(reads[i]))
+        for j in np.nonzero(bad[i])[0]:
+            r[j] = ord("N")
+        seqs.append(bytes(r))
+    dbg_bits, cbf_bytes = (1 << 29) + 3, (1 << 27) + 1
+    g, og = make_graphs(ctx, orc, dbg_bits, cbf_bytes, 64, 3, 3, 1, k, stranded, False)
+    for s_ in seqs:
+        og.add_read(s_)
+    n = g.addReads(pr)
+    assert n == n_reads * (L - k + 1)
+    bases = all_bases(orc, [x.replace(b"N", b"A") for x in seqs], k, [MODE_FWD, MODE_RC] if stranded else [MODE_CANON])
+    assert_same_state(g, og, bases=bases)
+    if stranded:
+        for s_ in seqs[: n_reads // 2]:
+            og.add_read(s_, flags=F_REVCOMP)
+        half = rb.PackedReads(pr.packed, pr.mask, None, None, n_reads // 2, L, stride)
+        g.addReads(half, flags=rb.REVCOMP)
+    else:
+        for s_ in seqs:
+            og.add_read(s_)
+        g.addReads(pr)                      # every k-mer again: multiplicities inside and across rounds
+    assert og.cbf().max() <= 16, "fixture reached the probabilistic MiniFloat range"
+    assert_same_state(g, og, bases=bases)
+    counts, fh, rh = g.getKmers(pr)
+    off, exact = 0, not len(np.nonzero(g.getCbf().download() != og.cbf())[0])
+    for s_ in seqs:
+        c, f, r = og.count_seq(s_)
+        mlen = len(c)
+        assert (fh[off:off + mlen] == f).all()
+        if not stranded:
+            assert (rh[off:off + mlen] == r).all()
+        if exact:
+            assert (counts[off:off + mlen] == c).all()
+        off += mlen
+    assert off == len(counts)
     g.destroy(), og.close()
 
 
