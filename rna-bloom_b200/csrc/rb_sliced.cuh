@@ -181,6 +181,7 @@ struct TileSort {
                 if (run) at[q] = atomicAdd(&out.cursor[(size_t)(region0 + b) * out.cursor_stride], run);
             }
         }
+        __syncthreads();   // start[] was written with a thread-strided mapping, the scan reads it in contiguous pieces
         const uint32_t total = cta_exclusive_scan(start, B, scratch);   // start[b] = staging position of the bucket's first record
 #pragma unroll
         for (int e = 0; e < E; ++e) {
@@ -202,7 +203,7 @@ struct TileSort {
                 const uint32_t lo = sl_region_lo(out, region0 + b), hi = sl_region_hi(out, region0 + b);
                 uint32_t a = at[q];
                 if (a > hi - lo) a = hi - lo;
-                if (cnt && a + cnt > hi - lo) *overflow = 1;
+                if (cnt && a + cnt > hi - lo) atomicOr(reinterpret_cast<unsigned int*>(overflow), 1u);
                 gdst[b] = lo + a;
                 glim[b] = hi;
             }

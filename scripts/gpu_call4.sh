@@ -1,0 +1,32 @@
+#!/bin/bash
+# round-1 GPU call 3: prefix k-merizer + ballot tile sort + shared-memory dedup: parity, sweep, ncu details as CSV
+cd "$(dirname "$0")/.." || exit 1
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+echo "== pytest sliced subset" ; date +%s
+timeout 400 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "sliced and (uniform or duplicates or collision_free or getkmers or policies or full_size or subbatching)" > gpurun_out/c4_pytest_sliced.log 2>&1; echo "pytest exit $?" >> gpurun_out/c4_pytest_sliced.log
+tail -3 gpurun_out/c4_pytest_sliced.log
+echo "== sweep (bits bytes round chunk occ rank)" ; date +%s
+for cfg in "28 25 28 4096 4 ballot" "28 25 28 4096 4 atoms" "28 25 28 4096 8 ballot" "28 25 29 4096 4 ballot" "29 26 28 4096 4 ballot" "28 25 28 2048 8 ballot"; do
+  set -- $cfg
+  f=gpurun_out/c4_sweep_$1_$2_$3_$4_$5_$6
+  RB_SLICE_BITS_LOG2=$1 RB_SLICE_BYTES_LOG2=$2 RB_SLICED_ROUND_LOG2=$3 RB_SLICED_CHUNK=$4 RB_SLICED_CONSUMER_OCC=$5 RB_SLICED_RANK=$6 timeout 200 python bench.py --engine sliced --steps 4 --warmup 3 --no-cpu-baseline --no-e2e > $f.json 2> $f.err
+  python - <<PY
+import json
+try:
+    d = json.load(open("$f.json"))
+    r = d["roofline"]
+    print("$cfg", "value %.3f ins %.3f look %.3f" % (d["value"]/1e9, r["insert_gkmers_s"], r["lookup_gkmers_s"]), {k: round(v, 1) for k, v in r["kernels_ms_per_step"].items()})
+except Exception as e:
+    print("$cfg failed", e)
+PY
+done
+echo "== ncu full, one round" ; date +%s
+timeout 500 ncu --set full --clock-control none --import-source on -k regex:ks_ -s 42 -c 14 -o /tmp/r01_sliced_full python bench.py --engine sliced --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --reads-per-step 2000000 > gpurun_out/c4_ncu_full.log 2>&1; echo "ncu exit $?"
+ls -la /tmp/r01_sliced_full.ncu-rep
+ncu -i /tmp/r01_sliced_full.ncu-rep --page details --csv > gpurun_out/r01_sliced_details.csv 2> gpurun_out/c4_ncu_export.err
+ncu -i /tmp/r01_sliced_full.ncu-rep --page raw --csv > gpurun_out/r01_sliced_raw.csv 2>> gpurun_out/c4_ncu_export.err
+sz=$(stat -c %s /tmp/r01_sliced_full.ncu-rep 2>/dev/null || echo 0)
+if [ "$sz" -gt 0 ] && [ "$sz" -lt 40000000 ]; then cp /tmp/r01_sliced_full.ncu-rep gpurun_out/; fi
+du -sh gpurun_out
+date +%s

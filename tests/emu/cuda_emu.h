@@ -141,7 +141,7 @@ static inline unsigned long long atomicExch(unsigned long long* p, unsigned long
 
 // ---- loads / stores / integer intrinsics ---------------------------------------------------------------------------------
 template <typename T> static inline T __ldg(const T* p) { return *p; }
-template <typename T> static inline T __ldcg(const T* p) { return *(const volatile T*)p; }
+template <typename T> static inline T __ldcg(const T* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }   // ld.global.cg: coherent at L2, may race with atomics by design
 template <typename T> static inline T __ldcs(const T* p) { return *p; }
 template <typename T> static inline void __stcs(T* p, T v) { *p = v; }
 static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) { return (unsigned long long)(((unsigned __int128)a * b) >> 64); }

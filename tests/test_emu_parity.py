@@ -99,3 +99,20 @@ def test_graph_add_collision_free_is_bit_exact(ctx, orc, stranded, k, hd, hc, n_
                                                          (40, 64, 25, 200, False)])
 def test_uniform_layout_graph_matches_oracle(ctx, orc, L, stride, k, n_reads, stranded):
     G.test_uniform_layout_graph_matches_oracle(ctx, orc, L, stride, k, n_reads, stranded)
+
+
+def test_kernels_are_race_free_under_tsan(tmp_path):
+    """The emulated kernels (sliced engine: uniform + variable layout, insert twice + lookup) under ThreadSanitizer.  A missing
+    __syncthreads() does not change the results of the emulation (OS threads rarely interleave badly) but corrupts a full-size GPU
+    run; TSan sees the unordered shared-memory accesses directly (checked: removing one barrier of TileSort::run is reported)."""
+    exe = os.path.join(EMU_DIR, "race_check")
+    srcs = [os.path.join(CSRC, n) for n in os.listdir(CSRC)] + [os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(EMU_DIR, "race_check.cpp")]
+    if not os.path.exists(exe) or any(os.path.getmtime(s) > os.path.getmtime(exe) for s in srcs):
+        subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-DRB_EMU", "-I", EMU_DIR, "-pthread",
+                               os.path.join(EMU_DIR, "race_check.cpp"), "-o", exe])
+    env = dict(os.environ, **SLICE_ENV)
+    env.pop("RB_SLICED_RANK", None)
+    env["RB_ENGINE"] = "sliced"
+    p = subprocess.run([exe, "120"], env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "race_check ok" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
+    assert "WARNING: ThreadSanitizer" not in p.stderr, p.stderr[:6000]
