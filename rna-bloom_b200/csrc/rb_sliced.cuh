@@ -51,7 +51,6 @@ struct SlArena {
     int chunk;                // records per work item of the kernels that consume the arena region by region
     uint32_t cap;             // roff == nullptr: every region holds cap records, region b = [b * cap, (b + 1) * cap)
     int cursor_stride;        // cursor of region b = cursor[b * cursor_stride] (kSlPad when the regions are few and hot)
-    int rank_mode;            // SL_RANK_BALLOT / SL_RANK_ATOMS (TileSort)
 };
 struct SlGeom {
     FastMod dbg_fm, cbf_fm;   // global index arithmetic (reference semantics)
@@ -93,106 +92,62 @@ __device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t* v, int n, uint3
 }
 
 // ---- CTA-wide multisplit of up to 256 * E records into the regions of an arena -------------------------------------------------
-// Ranking (which place a record takes inside its (tile, bucket) run):
-//   ballot (default)  the 32 lanes of a warp find their same-bucket peers with one __ballot_sync per bucket-id bit (what
-//                     cub::BlockRadixRank's match path does); the first peer bumps a warp-private 16-bit counter, no atomics.
-//                     ~45 issue slots per row of 32 records.
-//   atoms             shared-memory atomicAdd whose return value is the rank; ATOMS costs 1-2 cycles per *lane* on this part
-//                     (B300_MICROARCH.md "Atomics"; measured here: ks_route_lookup 19 cycles per k-mer and SM, 6 ATOMS each).
-// Then: per-bucket totals, one global cursor bump per (tile, bucket) -- issued early, consumed after the scan and the staging so
-// its ~1 us round trip overlaps them --, records staged in bucket order, copied out so that consecutive threads write
-// consecutive addresses.
-enum { SL_RANK_BALLOT = 0, SL_RANK_ATOMS = 1 };
+// rank     shared-memory atomicAdd on the bucket's counter; its return value is the record's place inside the (tile, bucket) run.
+//          (A warp-ballot ranking -- one __ballot_sync per bucket-id bit, warp-private counters, no atomics -- was measured too:
+//          30.4 against 23.1 ms per 504 M k-mers in ks_route_lookup_u; ATOMS is the cheaper instruction mix on this part.)
+// reserve  one global cursor bump per (tile, bucket), issued before the scan and consumed after the staging, so its ~1 us round trip
+//          is overlapped
+// stage    records + their bucket ids in bucket order in shared memory
+// copy     consecutive threads write consecutive addresses inside a bucket's run
+// A run that does not fit its region sets *overflow and is written past the region's end (at most one tile of records: the arenas
+// are allocated with that much slack); the host discards the round, so what it overwrites does not matter.
 constexpr int kSlWarps = kSlThreads / 32;
 constexpr int kSlBucketsPerThread = kSlMaxRegions / kSlThreads;
+constexpr int kSlSpill = 8192;   // records of slack behind every arena (>= the largest tile)
 __device__ __forceinline__ uint32_t sl_region_lo(const SlArena& a, int region) { return a.roff ? __ldg(&a.roff[region]) : (uint32_t)region * a.cap; }
 __device__ __forceinline__ uint32_t sl_region_hi(const SlArena& a, int region) { return a.roff ? __ldg(&a.roff[region + 1]) : (uint32_t)(region + 1) * a.cap; }
 template <typename REC, int E>
 struct TileSort {
-    uint32_t *start, *gdst, *glim, *scratch;   // [B] [B] [B] [296]
-    uint16_t* whist;                           // [8 * B] per-warp counters, then per-warp offsets inside the (tile, bucket) run
-    REC* stage;                                // [256 * E] records in bucket order
-    uint16_t* tag;                             // [256 * E] bucket of each staged record
-    int B, nbits;
-    static __host__ __device__ size_t words_of(int B) { return ((size_t)3 * B + 296 + (size_t)kSlWarps * B / 2 + 4 + 3) & ~(size_t)3; }
+    uint32_t *start, *delta, *scratch;   // [B] [B] [296]
+    REC* stage;                          // [256 * E] records in bucket order
+    uint16_t* tag;                       // [256 * E] bucket of each staged record
+    int B;
+    static __host__ __device__ size_t words_of(int B) { return ((size_t)2 * B + 296 + 3) & ~(size_t)3; }
     static __host__ __device__ size_t smem_bytes(int B) { return words_of(B) * 4 + (size_t)kSlThreads * E * sizeof(REC) + (size_t)kSlThreads * E * 2; }
     __device__ __forceinline__ void init(unsigned char* smem, int B_) {
         B = B_;
-        nbits = 0;
-        while ((1 << nbits) < B) ++nbits;
         start = reinterpret_cast<uint32_t*>(smem);
-        gdst = start + B;
-        glim = gdst + B;
-        scratch = glim + B;
-        whist = reinterpret_cast<uint16_t*>(scratch + 296);
-        const size_t words = ((size_t)3 * B + 296 + (size_t)kSlWarps * B / 2 + 4 + 3) & ~(size_t)3;
-        stage = reinterpret_cast<REC*>(smem + words * 4);
-        tag = reinterpret_cast<uint16_t*>(smem + words * 4 + (size_t)kSlThreads * E * sizeof(REC));
+        delta = start + B;
+        scratch = delta + B;
+        stage = reinterpret_cast<REC*>(smem + words_of(B) * 4);
+        tag = reinterpret_cast<uint16_t*>(smem + words_of(B) * 4 + (size_t)kSlThreads * E * sizeof(REC));
     }
-    // bkt[e] < 0: no record, else the record goes to region region0 + bkt[e] of `out`.  slot[e] receives the arena position it was
-    // written to (kNoSlot: none, or dropped because its region is full -- *overflow is set then).  Every thread of the CTA calls it.
-    __device__ __forceinline__ void run(const SlArena& out, int region0, const int (&bkt)[E], const REC (&rec)[E], uint32_t (&slot)[E], int* overflow) {
-        const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-        uint32_t br[E];   // bucket | place inside the (tile, bucket) run << 12
+    // bkt[e] < 0: no record, else the record goes to region region0 + bkt[e] of `out`.  place[e] = bucket | rank inside the
+    // (tile, bucket) run << 12 (kNoSlot: no record).  meta (nullable, B + 1 entries): x = arena position of the bucket's run,
+    // y = position of the run inside the tile's bucket-ordered sequence; entry B: y = number of records of the tile.  With them a
+    // later kernel finds the tile's answers again: answer of a record = ans[meta[b].x + rank].  Every thread of the CTA calls it.
+    __device__ __forceinline__ void run(const SlArena& out, int region0, const int (&bkt)[E], const REC (&rec)[E], uint32_t (&place)[E], int* overflow,
+                                        uint2* __restrict__ meta) {
+        const int t = threadIdx.x;
+        for (int b = t; b < B; b += kSlThreads) start[b] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < E; ++e) place[e] = bkt[e] >= 0 ? ((uint32_t)bkt[e] | (atomicAdd(&start[bkt[e]], 1u) << 12)) : kNoSlot;
+        __syncthreads();
         uint32_t at[kSlBucketsPerThread];
-        if (out.rank_mode == SL_RANK_ATOMS) {
-            for (int b = t; b < B; b += kSlThreads) start[b] = 0;
-            __syncthreads();
-#pragma unroll
-            for (int e = 0; e < E; ++e) br[e] = bkt[e] >= 0 ? ((uint32_t)bkt[e] | (atomicAdd(&start[bkt[e]], 1u) << 12)) : 0xFFFu;
-            __syncthreads();
-        } else {
-            uint32_t* wz = reinterpret_cast<uint32_t*>(whist);
-            for (int i = t; i < (kSlWarps * B + 1) / 2; i += kSlThreads) wz[i] = 0;
-            __syncthreads();
-            uint16_t* mine = whist + warp * B;
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const bool valid = bkt[e] >= 0;
-                const uint32_t b = valid ? (uint32_t)bkt[e] : 0u;
-                uint32_t peers = __ballot_sync(0xffffffffu, valid);
-                for (int bit = 0; bit < nbits; ++bit) {
-                    const uint32_t one = (b >> bit) & 1u;
-                    const uint32_t v = __ballot_sync(0xffffffffu, one);
-                    peers &= one ? v : ~v;
-                }
-                const int leader = __ffs(peers) - 1;   // a valid lane is its own peer, so peers != 0 there
-                uint32_t base = 0;
-                if (valid && lane == leader) { base = mine[b]; mine[b] = (uint16_t)(base + __popc(peers)); }
-                __syncwarp();
-                base = __shfl_sync(0xffffffffu, base, valid ? leader : lane);
-                br[e] = valid ? (b | ((base + __popc(peers & ((1u << lane) - 1u))) << 12)) : 0xFFFu;
-            }
-            __syncthreads();
-        }
-        // per-bucket totals; warp counters become warp offsets; the cursor bumps go out now and are consumed after the staging
 #pragma unroll
         for (int q = 0; q < kSlBucketsPerThread; ++q) {
             const int b = t + q * kSlThreads;
             at[q] = 0;
-            if (b < B) {
-                uint32_t run = start[b];
-                if (out.rank_mode != SL_RANK_ATOMS) {
-                    run = 0;
-#pragma unroll
-                    for (int w = 0; w < kSlWarps; ++w) { const uint32_t c = whist[w * B + b]; whist[w * B + b] = (uint16_t)run; run += c; }
-                    start[b] = run;
-                }
-                if (run) at[q] = atomicAdd(&out.cursor[(size_t)(region0 + b) * out.cursor_stride], run);
-            }
+            if (b < B) { const uint32_t cnt = start[b]; if (cnt) at[q] = atomicAdd(&out.cursor[(size_t)(region0 + b) * out.cursor_stride], cnt); }
         }
-        __syncthreads();   // start[] was written with a thread-strided mapping, the scan reads it in contiguous pieces
         const uint32_t total = cta_exclusive_scan(start, B, scratch);   // start[b] = staging position of the bucket's first record
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            if ((br[e] & 0xFFFu) != 0xFFFu) {
-                const uint32_t b = br[e] & 0xFFFu;
-                uint32_t r = br[e] >> 12;
-                if (out.rank_mode != SL_RANK_ATOMS) r += whist[warp * B + b];
-                const uint32_t p = start[b] + r;
+            if (place[e] != kNoSlot) {
+                const uint32_t b = place[e] & 0xFFFu, p = start[b] + (place[e] >> 12);
                 stage[p] = rec[e];
                 tag[p] = (uint16_t)b;
-                br[e] = b | (r << 12);
             }
         }
 #pragma unroll
@@ -200,29 +155,17 @@ struct TileSort {
             const int b = t + q * kSlThreads;
             if (b < B) {
                 const uint32_t cnt = (b + 1 < B ? start[b + 1] : total) - start[b];
-                const uint32_t lo = sl_region_lo(out, region0 + b), hi = sl_region_hi(out, region0 + b);
-                uint32_t a = at[q];
-                if (a > hi - lo) a = hi - lo;
-                if (cnt && a + cnt > hi - lo) atomicOr(reinterpret_cast<unsigned int*>(overflow), 1u);
-                gdst[b] = lo + a;
-                glim[b] = hi;
+                const uint32_t lo = sl_region_lo(out, region0 + b), cap = sl_region_hi(out, region0 + b) - lo;
+                const uint32_t a = min(at[q], cap);
+                if (cnt && a + cnt > cap) atomicOr(reinterpret_cast<unsigned int*>(overflow), 1u);
+                delta[b] = lo + a - start[b];
+                if (meta) meta[b] = make_uint2(lo + a, start[b]);
             }
         }
+        if (meta && t == 0) meta[B] = make_uint2(0u, total);
         __syncthreads();
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            slot[e] = kNoSlot;
-            if ((br[e] & 0xFFFu) != 0xFFFu) {
-                const uint32_t b = br[e] & 0xFFFu, d = gdst[b] + (br[e] >> 12);
-                if (d < glim[b]) slot[e] = d;
-            }
-        }
         REC* data = reinterpret_cast<REC*>(out.data);
-        for (uint32_t p = t; p < total; p += kSlThreads) {   // consecutive threads -> consecutive addresses inside a bucket's run
-            const uint32_t b = tag[p];
-            const uint32_t d = gdst[b] + (p - start[b]);
-            if (d < glim[b]) data[d] = stage[p];
-        }
+        for (uint32_t p = t; p < total; p += kSlThreads) data[delta[tag[p]] + p] = stage[p];
         __syncthreads();
     }
 };
@@ -243,22 +186,46 @@ __device__ __forceinline__ void sl_probes(const SlGeom& sg, const HashMults& hm,
         }
     }
 }
-// a thread's 4 k-mers x 6 positions are 96 contiguous, 16-byte aligned bytes of the position array
-__device__ __forceinline__ void sl_store_positions(uint32_t* pos, int64_t first, const uint32_t (&slot)[kSlRoundKmers * kSlNJ]) {
+// a thread's 4 k-mers x 6 places are 96 contiguous, 16-byte aligned bytes of the position array
+__device__ __forceinline__ void sl_store_positions(uint32_t* pos, int64_t first, const uint32_t (&place)[kSlRoundKmers * kSlNJ]) {
     uint4* dst = reinterpret_cast<uint4*>(pos + first * kSlNJ);
 #pragma unroll
-    for (int q = 0; q < kSlNJ; ++q) dst[q] = make_uint4(slot[4 * q], slot[4 * q + 1], slot[4 * q + 2], slot[4 * q + 3]);
+    for (int q = 0; q < kSlNJ; ++q) dst[q] = make_uint4(place[4 * q], place[4 * q + 1], place[4 * q + 2], place[4 * q + 3]);
 }
-__device__ __forceinline__ void sl_load_answers(const uint32_t* pos, int64_t first, const uint8_t* __restrict__ ans, uint32_t (&slot)[kSlRoundKmers * kSlNJ],
-                                                uint32_t (&a)[kSlRoundKmers * kSlNJ]) {
+// The answers of a tile: its records sit in one run per bucket of the answer array (where the tile sort put them); the runs are
+// copied into shared memory in bucket order -- one warp per run, consecutive lanes read consecutive bytes -- and every thread
+// then picks its answers up at start[bucket] + rank.  (A per-record gather from global memory costs ~2 L1TEX cycles per
+// answer: 20 ms per 504 M k-mers in ks_combine_lookup; the runs of a tile are a few hundred sectors.)
+struct TileAnswers {
+    uint32_t* start;   // [B + 1]
+    uint8_t* bytes;    // [tile records]
+    static __host__ __device__ size_t smem_bytes(int B, int tile_records) { return ((size_t)(B + 1) * 4 + (size_t)tile_records + 15) & ~(size_t)15; }
+    // every thread of the CTA calls it; meta = the tile's B + 1 entries written by TileSort::run
+    __device__ __forceinline__ void load(unsigned char* smem, int B, const uint2* __restrict__ meta, const uint8_t* __restrict__ ans) {
+        start = reinterpret_cast<uint32_t*>(smem);
+        bytes = smem + (size_t)(B + 1) * 4;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int b = threadIdx.x; b <= B; b += kSlThreads) start[b] = __ldg(&meta[b]).y;
+        __syncthreads();
+#pragma unroll 4
+        for (int b = warp; b < B; b += kSlThreads / 32) {
+            const uint32_t lo = start[b], n = start[b + 1] - lo;
+            if (n) {
+                const uint32_t g = __ldg(&meta[b]).x;
+                for (uint32_t i = lane; i < n; i += 32) bytes[lo + i] = __ldg(ans + g + i);
+            }
+        }
+        __syncthreads();
+    }
+    __device__ __forceinline__ uint32_t get(uint32_t place) const { return place != kNoSlot ? (uint32_t)bytes[start[place & 0xFFFu] + (place >> 12)] : 0u; }
+};
+__device__ __forceinline__ void sl_load_places(const uint32_t* pos, int64_t first, uint32_t (&place)[kSlRoundKmers * kSlNJ]) {
     const uint4* src = reinterpret_cast<const uint4*>(pos + first * kSlNJ);
 #pragma unroll
     for (int q = 0; q < kSlNJ; ++q) {
         const uint4 v = __ldg(src + q);
-        slot[4 * q] = v.x; slot[4 * q + 1] = v.y; slot[4 * q + 2] = v.z; slot[4 * q + 3] = v.w;
+        place[4 * q] = v.x; place[4 * q + 1] = v.y; place[4 * q + 2] = v.z; place[4 * q + 3] = v.w;
     }
-#pragma unroll
-    for (int e = 0; e < kSlRoundKmers * kSlNJ; ++e) a[e] = slot[e] != kNoSlot ? (uint32_t)__ldg(ans + slot[e]) : 0u;
 }
 
 // ---- prefix k-merizer (uniform read layout) ----------------------------------------------------------------------------------------------
@@ -353,8 +320,8 @@ struct PrefixKmerizer {
 // ---- S1 (uniform layout): one CTA = 1024 consecutive k-mer positions, hashed through the prefix arrays, one tile sort -------------------
 template <int MODE>
 __global__ void __launch_bounds__(kSlThreads) ks_route_lookup_u(const Ingest g, int k, const HashMults hm, const SlGeom sg, const SlArena arena,
-                                                               uint32_t* __restrict__ pos, int64_t* __restrict__ fhash, int64_t* __restrict__ rhash,
-                                                               int* overflow) {
+                                                               uint32_t* __restrict__ pos, uint2* __restrict__ tile_meta, int64_t* __restrict__ fhash,
+                                                               int64_t* __restrict__ rhash, int* overflow) {
     RB_DYN_SMEM(unsigned char, sl_smem);
     const int64_t tile0 = (int64_t)blockIdx.x * kSlTile;
     PrefixKmerizer pk;
@@ -377,7 +344,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_route_lookup_u(const Ingest g, 
     __syncthreads();   // the tile sort reuses the shared memory of the prefix arrays
     TileSort<uint32_t, kSlRoundKmers * kSlNJ> ts;
     ts.init(sl_smem, arena.B);
-    ts.run(arena, 0, bkt, rec, slot, overflow);
+    ts.run(arena, 0, bkt, rec, slot, overflow, tile_meta + (size_t)blockIdx.x * (arena.B + 1));
     if (p0 < g.n_pos) sl_store_positions(pos, p0, slot);
 }
 // ---- I1 (uniform layout) -------------------------------------------------------------------------------------------------------------------
@@ -407,14 +374,14 @@ __global__ void __launch_bounds__(kSlThreads) ks_route_keys_u(const Ingest g, in
     __syncthreads();
     TileSort<unsigned long long, kSlRoundKmers> ts;
     ts.init(sl_smem, arena.B);
-    ts.run(arena, 0, bkt, rec, slot, overflow);
+    ts.run(arena, 0, bkt, rec, slot, overflow, nullptr);
 }
 
 // ---- S1: k-merise, tile-sort the probes of every usable k-mer instance by filter slice --------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(kSlThreads) ks_route_lookup(const Ingest g, int k, const HashMults hm, const SlGeom sg, const SlArena arena,
-                                                             uint32_t* __restrict__ pos, int64_t* __restrict__ fhash, int64_t* __restrict__ rhash,
-                                                             int* overflow) {
+                                                             uint32_t* __restrict__ pos, uint2* __restrict__ tile_meta, int64_t* __restrict__ fhash,
+                                                             int64_t* __restrict__ rhash, int* overflow) {
     RB_DYN_SMEM(unsigned char, sl_smem);
     __shared__ RollLut lut;
     build_lut(&lut, k);
@@ -440,7 +407,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_route_lookup(const Ingest g, in
                 if (pw.wk.bad == 0) sl_probes(sg, hm, pw.wk.base(), true, &bkt[i * kSlNJ], &rec[i * kSlNJ]);
             }
         }
-        ts.run(arena, 0, bkt, rec, slot, overflow);
+        ts.run(arena, 0, bkt, rec, slot, overflow, tile_meta + ((size_t)blockIdx.x * (kChunk / kSlRoundKmers) + r0 / kSlRoundKmers) * (arena.B + 1));
         if (r0 < n) sl_store_positions(pos, pos0 + r0, slot);
     }
 }
@@ -458,14 +425,22 @@ __global__ void __launch_bounds__(kSlThreads) ks_chunk_prefix(const SlArena aren
     __syncthreads();
     const uint32_t total = cta_exclusive_scan(v, arena.B, scratch);
     for (int b = threadIdx.x; b < arena.B; b += kSlThreads) chunk_prefix[b] = (int)v[b];
-    if (threadIdx.x == 0) chunk_prefix[arena.B] = (int)total;
+    if (threadIdx.x == 0) { chunk_prefix[arena.B] = (int)total; chunk_prefix[arena.B + 1] = 0; }   // [B + 1]: the consumers' work counter
 }
-// Work items are dealt round-robin in region order, so at any moment the whole grid works inside a window of gridDim.x * chunk
-// records.  The window must be a small fraction of a region (the host sizes grid and chunk for that): then one, at region
-// boundaries two, filter slices are live and they stay L2-resident without any grid barrier.  (Measured with a window as large
-// as a region: 109 B of DRAM reads per probe, i.e. no residency at all -- profiles/r01_notes.md section 6.)
+// Work items are handed out in region order through one global counter: every CTA takes the lowest unclaimed chunk, so the records
+// in flight are always one contiguous window of gridDim.x chunks.  The window must be a fraction of a region (the host sizes grid
+// and chunk for that): then one, at region boundaries two, filter slices are live and they stay L2-resident without any grid
+// barrier.  Measured: window as large as a region -> 109 B of DRAM reads per probe (no residency at all); static round-robin
+// (chunk c to CTA c % grid) -> the CTAs of the test-and-set kernel drift apart by several windows and every filter line is
+// fetched ~6 times (106 GB instead of 23 GB per round).
+__device__ __forceinline__ int sl_next_chunk(int* counter, int* s_c) {
+    __syncthreads();   // everybody is done with the previous chunk and has read *s_c
+    if (threadIdx.x == 0) *s_c = atomicAdd(counter, 1);
+    __syncthreads();
+    return *s_c;
+}
 struct SlWork { int b; uint32_t first, n; };
-__device__ __forceinline__ void sl_load_prefix(int* pre, const int* __restrict__ chunk_prefix, int B) {
+__device__ __forceinline__ void sl_load_prefix(int* pre, const int* chunk_prefix, int B) {
     for (int i = threadIdx.x; i <= B; i += kSlThreads) pre[i] = chunk_prefix[i];
     __syncthreads();
 }
@@ -484,7 +459,7 @@ __device__ __forceinline__ SlWork sl_work_item(const SlArena& arena, const int* 
 
 // ---- S2 / I5: apply the probes.  SET = 1: dbgbf probes are test-and-set (graph.add / addDbgOnly) -------------------------------------
 template <int SET>
-__global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena arena, const int* __restrict__ chunk_prefix, const SlGeom sg,
+__global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena arena, int* chunk_prefix, const SlGeom sg,
                                                              uint32_t* __restrict__ dbg_words, const uint32_t* __restrict__ cbf_words,
                                                              uint8_t* __restrict__ ans) {
     RB_DYN_SMEM(unsigned char, sl_smem);
@@ -493,7 +468,8 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
     const int total = pre[arena.B];
     const uint32_t* rec = reinterpret_cast<const uint32_t*>(arena.data);
     constexpr int U = 8;   // probes in flight per thread
-    for (int c = blockIdx.x; c < total; c += gridDim.x) {
+    __shared__ int s_c;
+    for (int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c); c < total; c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c)) {
         const SlWork w = sl_work_item(arena, pre, c);
         const bool is_dbg = w.b < sg.n_dbg;
         const int64_t word0 = is_dbg ? ((int64_t)w.b << (sg.dbg_log2 - 5)) : ((int64_t)(w.b - sg.n_dbg) << (sg.cbf_log2 - 2));
@@ -529,39 +505,46 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
 // k-mers per CTA; FLAT = 0: ks_route_lookup, 16 consecutive k-mers per thread in 4 rounds): the answers of a CTA round sit in
 // the few hundred runs its tile sort wrote, so the 32 B sectors a CTA gathers from are shared by its own threads (L1 hits)
 // instead of being fetched again by CTAs on other SMs (measured with mismatched mappings: 43 ms per 504 M k-mers).
-__device__ __forceinline__ void sl_counts_of_group(const uint32_t* __restrict__ pos, const uint8_t* __restrict__ ans, int64_t i0, int64_t n_inst, int hd, int hc,
+__device__ __forceinline__ void sl_counts_of_group(const uint32_t* __restrict__ pos, const TileAnswers& ta, int64_t i0, int64_t n_inst, int hd, int hc,
                                                    float* __restrict__ counts, int64_t out_base) {
-    uint32_t slot[kSlRoundKmers * kSlNJ], a[kSlRoundKmers * kSlNJ];
-    sl_load_answers(pos, i0, ans, slot, a);
+    uint32_t place[kSlRoundKmers * kSlNJ];
+    sl_load_places(pos, i0, place);
 #pragma unroll
     for (int i = 0; i < kSlRoundKmers; ++i) {
         if (i0 + i < n_inst) {
             float c = 0.f;
-            bool all = slot[i * kSlNJ] != kNoSlot;   // unusable k-mers (masked base in the window) made no probes
+            bool all = place[i * kSlNJ] != kNoSlot;   // unusable k-mers (masked base in the window) made no probes
 #pragma unroll
-            for (int h = 0; h < kSlMaxH; ++h) if (h < hd) all = all && (a[i * kSlNJ + h] & 1u);
+            for (int h = 0; h < kSlMaxH; ++h) if (h < hd) all = all && (ta.get(place[i * kSlNJ + h]) & 1u);
             if (all) {
                 int mn = 127;
 #pragma unroll
-                for (int h = 0; h < kSlMaxH; ++h) if (h < hc) { const int v = (int)(int8_t)a[i * kSlNJ + kSlMaxH + h]; mn = v < mn ? v : mn; }
+                for (int h = 0; h < kSlMaxH; ++h) if (h < hc) { const int v = (int)(int8_t)ta.get(place[i * kSlNJ + kSlMaxH + h]); mn = v < mn ? v : mn; }
                 c = minifloat_to_float(mn) + 1.f;
             }
             counts[out_base + i0 + i] = c;
         }
     }
 }
+// FLAT = 1: tiles of ks_route_lookup_u (1024 consecutive k-mers per CTA); FLAT = 0: tiles of ks_route_lookup (16 consecutive k-mers
+// per thread, four tile sorts per CTA).  Same grid as the route kernel.
 template <int FLAT>
-__global__ void __launch_bounds__(kSlThreads) ks_combine_lookup(const uint32_t* __restrict__ pos, const uint8_t* __restrict__ ans, int64_t n_inst, int hd,
-                                                               int hc, float* __restrict__ counts, int64_t out_base) {
+__global__ void __launch_bounds__(kSlThreads) ks_combine_lookup(const uint32_t* __restrict__ pos, const uint2* __restrict__ tile_meta, int B,
+                                                               const uint8_t* __restrict__ ans, int64_t n_inst, int hd, int hc,
+                                                               float* __restrict__ counts, int64_t out_base) {
+    RB_DYN_SMEM(unsigned char, sl_smem);
+    TileAnswers ta;
     if (FLAT) {
+        ta.load(sl_smem, B, tile_meta + (size_t)blockIdx.x * (B + 1), ans);
         const int64_t i0 = ((int64_t)blockIdx.x * kSlThreads + threadIdx.x) * kSlRoundKmers;
-        if (i0 < n_inst) sl_counts_of_group(pos, ans, i0, n_inst, hd, hc, counts, out_base);
+        if (i0 < n_inst) sl_counts_of_group(pos, ta, i0, n_inst, hd, hc, counts, out_base);
     } else {
         const int64_t pos0 = ((int64_t)blockIdx.x * kSlThreads + threadIdx.x) * kChunk;
 #pragma unroll 1
         for (int r0 = 0; r0 < kChunk; r0 += kSlRoundKmers) {
-            if (pos0 + r0 >= n_inst) return;
-            sl_counts_of_group(pos, ans, pos0 + r0, n_inst, hd, hc, counts, out_base);
+            ta.load(sl_smem, B, tile_meta + ((size_t)blockIdx.x * (kChunk / kSlRoundKmers) + r0 / kSlRoundKmers) * (B + 1), ans);
+            if (pos0 + r0 < n_inst) sl_counts_of_group(pos, ta, pos0 + r0, n_inst, hd, hc, counts, out_base);
+            __syncthreads();   // the next round overwrites the staged answers
         }
     }
 }
@@ -593,13 +576,13 @@ __global__ void __launch_bounds__(kSlThreads) ks_route_keys(const Ingest g, int 
             }
         }
     }
-    ts.run(arena, 0, bkt, rec, slot, overflow);
+    ts.run(arena, 0, bkt, rec, slot, overflow, nullptr);
 }
 
 // ---- I2: second-level split: the keys of every range are tile-sorted again by their next hash bits ------------------------------------------
 // After it a sub-range holds ~1 Ki keys: small enough for a shared-memory hash table, so no global table is ever touched
 // (the L2-sliced global table this replaces ran at 4-9 G keys/s: one CAS + one add per key against ~24 B of table per key).
-__global__ void __launch_bounds__(kSlThreads) ks_split_keys(const SlArena in, const int* __restrict__ chunk_prefix, int sub_bits, int sub_shift,
+__global__ void __launch_bounds__(kSlThreads) ks_split_keys(const SlArena in, int* chunk_prefix, int sub_bits, int sub_shift,
                                                            const SlArena out, int* overflow) {
     RB_DYN_SMEM(unsigned char, sl_smem);
     TileSort<unsigned long long, kSlRoundKmers> ts;
@@ -609,7 +592,8 @@ __global__ void __launch_bounds__(kSlThreads) ks_split_keys(const SlArena in, co
     sl_load_prefix(pre, chunk_prefix, in.B);
     const int total = pre[in.B];
     const unsigned long long* rec_in = reinterpret_cast<const unsigned long long*>(in.data);
-    for (int c = blockIdx.x; c < total; c += gridDim.x) {
+    __shared__ int s_c;
+    for (int c = sl_next_chunk(chunk_prefix + in.B + 1, &s_c); c < total; c = sl_next_chunk(chunk_prefix + in.B + 1, &s_c)) {
         const SlWork w = sl_work_item(in, pre, c);   // in.chunk <= 256 * kSlRoundKmers keys
         int bkt[kSlRoundKmers];
         unsigned long long rec[kSlRoundKmers];
@@ -623,12 +607,12 @@ __global__ void __launch_bounds__(kSlThreads) ks_split_keys(const SlArena in, co
                 bkt[i] = n_sub > 1 ? (int)((sl_mixkey(rec[i]) >> sub_shift) & (uint64_t)(n_sub - 1)) : 0;
             }
         }
-        ts.run(out, w.b * n_sub, bkt, rec, slot, overflow);
+        ts.run(out, w.b * n_sub, bkt, rec, slot, overflow, nullptr);
     }
 }
 
 // ---- I3: one CTA per sub-range: (key -> multiplicity) in a shared-memory hash table, distinct keys appended to the dense arrays ----------------
-constexpr int kSlDedupSlots = 8192;   // 64 KiB of keys + 32 KiB of counters; a sub-range holds fewer keys than that (host: cap < slots)
+constexpr int kSlDedupSlots = 4096;   // 32 KiB of keys + 16 KiB of counters; a sub-range holds fewer keys than that (host: cap < slots)
 __global__ void __launch_bounds__(kSlThreads) ks_dedup(const SlArena in, int n_regions, int hash_shift, unsigned long long* __restrict__ dkey,
                                                       unsigned int* __restrict__ dmult, unsigned int* n_distinct) {
     RB_DYN_SMEM(unsigned char, sl_smem);
@@ -657,7 +641,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_dedup(const SlArena in, int n_r
         }
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < T; i += kSlThreads)
-            if (tcnt[i]) tcnt[i] |= atomicAdd(&n_occ, 1u) << 16;   // multiplicity (< 2^16: a sub-range holds < 8192 keys) | dense rank
+            if (tcnt[i]) tcnt[i] |= atomicAdd(&n_occ, 1u) << 16;   // multiplicity (< 2^16: a sub-range holds < 4096 keys) | dense rank
         __syncthreads();
         if (threadIdx.x == 0) out_base = atomicAdd(n_distinct, n_occ + (n_zero ? 1u : 0u));
         __syncthreads();
@@ -671,7 +655,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_dedup(const SlArena in, int n_r
 // ---- I4: the probes of every distinct key, tile-sorted by filter slice ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSlThreads) ks_emit_probes(const unsigned long long* __restrict__ dkey, const unsigned int* __restrict__ n_distinct,
                                                             const HashMults hm, const SlGeom sg, int with_cbf, const SlArena arena,
-                                                            uint32_t* __restrict__ pos, int* overflow) {
+                                                            uint32_t* __restrict__ pos, uint2* __restrict__ tile_meta, int* overflow) {
     const int64_t nd = (int64_t)*n_distinct;
     if ((int64_t)blockIdx.x * (kSlThreads * kSlRoundKmers) >= nd) return;   // whole CTA
     RB_DYN_SMEM(unsigned char, sl_smem);
@@ -686,28 +670,37 @@ __global__ void __launch_bounds__(kSlThreads) ks_emit_probes(const unsigned long
         for (int j = 0; j < kSlNJ; ++j) { bkt[i * kSlNJ + j] = -1; rec[i * kSlNJ + j] = 0; }
         if (d0 + i < nd) sl_probes(sg, hm, (uint64_t)dkey[d0 + i], with_cbf != 0, &bkt[i * kSlNJ], &rec[i * kSlNJ]);
     }
-    ts.run(arena, 0, bkt, rec, slot, overflow);
+    ts.run(arena, 0, bkt, rec, slot, overflow, tile_meta + (size_t)blockIdx.x * (arena.B + 1));
     if (d0 < nd) sl_store_positions(pos, d0, slot);
 }
 
 // ---- I6: per distinct key: present?, replay the increments, emit one raise per counter that grew ----------------------------------------------
 __global__ void __launch_bounds__(kSlThreads) ks_combine_insert(const unsigned long long* __restrict__ dkey, const unsigned int* __restrict__ dmult,
                                                                const unsigned int* __restrict__ n_distinct, const uint32_t* __restrict__ pos,
-                                                               const uint8_t* __restrict__ ans, const HashMults hm, const SlGeom sg, int policy,
-                                                               uint64_t rng_seed, const SlArena raises, int* overflow) {
+                                                               const uint2* __restrict__ tile_meta, int probe_B, const uint8_t* __restrict__ ans,
+                                                               const HashMults hm, const SlGeom sg, int policy, uint64_t rng_seed, const SlArena raises,
+                                                               int* overflow) {
     const int64_t nd = (int64_t)*n_distinct;
     if ((int64_t)blockIdx.x * (kSlThreads * kSlRoundKmers) >= nd) return;   // whole CTA
     RB_DYN_SMEM(unsigned char, sl_smem);
-    TileSort<uint32_t, kSlRoundKmers * kSlMaxH> ts;
-    ts.init(sl_smem, raises.B);
     const int64_t d0 = ((int64_t)blockIdx.x * kSlThreads + threadIdx.x) * kSlRoundKmers;
     int bkt[kSlRoundKmers * kSlMaxH];
     uint32_t rec[kSlRoundKmers * kSlMaxH], rslot[kSlRoundKmers * kSlMaxH];
 #pragma unroll
     for (int e = 0; e < kSlRoundKmers * kSlMaxH; ++e) { bkt[e] = -1; rec[e] = 0; }
+    TileAnswers ta;   // the tile of ks_emit_probes with the same block index
+    ta.load(sl_smem, probe_B, tile_meta + (size_t)blockIdx.x * (probe_B + 1), ans);
+    uint32_t a[kSlRoundKmers * kSlNJ];
     if (d0 < nd) {
-        uint32_t slot[kSlRoundKmers * kSlNJ], a[kSlRoundKmers * kSlNJ];
-        sl_load_answers(pos, d0, ans, slot, a);
+        uint32_t place[kSlRoundKmers * kSlNJ];
+        sl_load_places(pos, d0, place);
+#pragma unroll
+        for (int e = 0; e < kSlRoundKmers * kSlNJ; ++e) a[e] = ta.get(place[e]);
+    }
+    __syncthreads();   // the tile sort of the raises reuses the shared memory
+    TileSort<uint32_t, kSlRoundKmers * kSlMaxH> ts;
+    ts.init(sl_smem, raises.B);
+    if (d0 < nd) {
 #pragma unroll
         for (int i = 0; i < kSlRoundKmers; ++i) {
             if (d0 + i < nd) {
@@ -758,18 +751,19 @@ __global__ void __launch_bounds__(kSlThreads) ks_combine_insert(const unsigned l
             }
         }
     }
-    ts.run(raises, 0, bkt, rec, rslot, overflow);
+    ts.run(raises, 0, bkt, rec, rslot, overflow, nullptr);
 }
 
 // ---- I7: raise the counters slice by slice ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSlThreads) ks_apply_raises(const SlArena arena, const int* __restrict__ chunk_prefix, const SlGeom sg,
+__global__ void __launch_bounds__(kSlThreads) ks_apply_raises(const SlArena arena, int* chunk_prefix, const SlGeom sg,
                                                              uint32_t* __restrict__ cbf_words) {
     RB_DYN_SMEM(unsigned char, sl_smem);
     int* pre = reinterpret_cast<int*>(sl_smem);
     sl_load_prefix(pre, chunk_prefix, arena.B);
     const int total = pre[arena.B];
     const uint32_t* rec = reinterpret_cast<const uint32_t*>(arena.data);
-    for (int c = blockIdx.x; c < total; c += gridDim.x) {
+    __shared__ int s_c;
+    for (int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c); c < total; c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c)) {
         const SlWork w = sl_work_item(arena, pre, c);
         const int64_t word0 = (int64_t)w.b << (sg.raise_log2 - 2);
         for (uint32_t i = threadIdx.x; i < w.n; i += kSlThreads) {

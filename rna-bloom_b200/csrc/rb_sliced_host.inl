@@ -7,6 +7,7 @@ struct SlicedEngine {
     // probes: 4-byte slice-local indices, one answer byte per probe, 6 remembered positions per k-mer (or distinct key)
     uint32_t* probe_data; uint8_t* ans; unsigned int* probe_cursor; uint32_t* probe_roff; int probe_B;
     uint32_t* pos;
+    uint2* tile_meta;             // per tile sort of probes: where each bucket's run went (TileSort::run), B + 1 entries per tile
     // insert: keys by range, hash table, dense distinct keys, raises
     unsigned long long* key_data; unsigned int* key_cursor; uint32_t* key_roff; int key_B; int key_shift;   // level 1: key_B ranges
     unsigned long long* sub_data; unsigned int* sub_cursor; int sub_bits; uint32_t sub_cap;                   // level 2: key_B << sub_bits sub-ranges
@@ -19,7 +20,7 @@ static void sliced_engine_free(rb_graph* g) {
     SlicedEngine* e = g->se;
     if (!e) return;
     cudaStreamSynchronize(g->ctx->stream);
-    cudaFree(e->probe_data); cudaFree(e->ans); cudaFree(e->probe_cursor); cudaFree(e->probe_roff); cudaFree(e->pos);
+    cudaFree(e->probe_data); cudaFree(e->ans); cudaFree(e->probe_cursor); cudaFree(e->probe_roff); cudaFree(e->pos); cudaFree(e->tile_meta);
     cudaFree(e->key_data); cudaFree(e->key_cursor); cudaFree(e->key_roff);
     cudaFree(e->sub_data); cudaFree(e->sub_cursor); cudaFree(e->dkey); cudaFree(e->dmult); cudaFree(e->n_distinct);
     cudaFree(e->raise_data); cudaFree(e->raise_cursor); cudaFree(e->raise_roff);
@@ -114,22 +115,24 @@ static int32_t sliced_engine_get(rb_graph* g, int64_t n_round, SlicedEngine** ou
     rc = sl_make_roff(ctx, caps, &e->raise_roff, &raise_slots);
     if (rc) { sliced_engine_free(g); return rc; }
     const int maxB = std::max(std::max(e->probe_B, e->key_B), sg.n_raise);
-    cudaError_t er = cudaMalloc(&e->probe_data, (size_t)probe_slots * 4 + 64);
-    if (er == cudaSuccess) er = cudaMalloc(&e->ans, (size_t)probe_slots + 64);
+    const int64_t n_tiles = n_max / kSlTile + 8;
+    cudaError_t er = cudaMalloc(&e->probe_data, ((size_t)probe_slots + kSlSpill) * 4);
+    if (er == cudaSuccess) er = cudaMalloc(&e->ans, (size_t)probe_slots + kSlSpill);
+    if (er == cudaSuccess) er = cudaMalloc(&e->tile_meta, (size_t)n_tiles * (e->probe_B + 1) * 8);
     if (er == cudaSuccess) er = cudaMalloc(&e->probe_cursor, (size_t)e->probe_B * kSlPad * 4);
     if (er == cudaSuccess) er = cudaMalloc(&e->pos, ((size_t)n_max + 8) * kSlNJ * 4);
-    if (er == cudaSuccess) er = cudaMalloc(&e->key_data, (size_t)key_slots * 8 + 64);
+    if (er == cudaSuccess) er = cudaMalloc(&e->key_data, ((size_t)key_slots + kSlSpill) * 8);
     if (er == cudaSuccess) er = cudaMalloc(&e->key_cursor, (size_t)e->key_B * kSlPad * 4);
     const int64_t n_sub_regions = (int64_t)e->key_B << e->sub_bits;
     if (n_sub_regions * e->sub_cap >= (1LL << 32) - (1LL << 20)) { sliced_engine_free(g); return fail(ctx, RB_EINVAL, "sliced engine: round too large for 32-bit record positions"); }
-    if (er == cudaSuccess) er = cudaMalloc(&e->sub_data, (size_t)n_sub_regions * e->sub_cap * 8 + 64);
+    if (er == cudaSuccess) er = cudaMalloc(&e->sub_data, ((size_t)n_sub_regions * e->sub_cap + kSlSpill) * 8);
     if (er == cudaSuccess) er = cudaMalloc(&e->sub_cursor, (size_t)n_sub_regions * 4 + 64);
     if (er == cudaSuccess) er = cudaMalloc(&e->dkey, ((size_t)n_max + 8) * 8);
     if (er == cudaSuccess) er = cudaMalloc(&e->dmult, ((size_t)n_max + 8) * 4);
     if (er == cudaSuccess) er = cudaMalloc(&e->n_distinct, 64);
-    if (er == cudaSuccess) er = cudaMalloc(&e->raise_data, (size_t)raise_slots * 4 + 64);
+    if (er == cudaSuccess) er = cudaMalloc(&e->raise_data, ((size_t)raise_slots + kSlSpill) * 4);
     if (er == cudaSuccess) er = cudaMalloc(&e->raise_cursor, (size_t)sg.n_raise * kSlPad * 4);
-    if (er == cudaSuccess) er = cudaMalloc(&e->chunk_prefix, (size_t)(maxB + 1) * 4);
+    if (er == cudaSuccess) er = cudaMalloc(&e->chunk_prefix, (size_t)(maxB + 2) * 4 + 64);
     if (er == cudaSuccess) er = cudaMalloc(&e->overflow, 64);
     if (er == cudaSuccess) er = cudaMemsetAsync(e->overflow, 0, 4, ctx->stream);
     if (er != cudaSuccess) { sliced_engine_free(g); return fail(ctx, RB_ENOMEM, std::string("sliced engine buffers: ") + cudaGetErrorString(er)); }
@@ -166,10 +169,9 @@ static int32_t sl_chunk_prefix(rb_ctx* ctx, SlicedEngine* e, const SlArena& a) {
     LAUNCH_CHECK();
     return RB_OK;
 }
-static int sl_rank_mode() { const char* v = getenv("RB_SLICED_RANK"); return (v && !strcmp(v, "atoms")) ? SL_RANK_ATOMS : SL_RANK_BALLOT; }
 static SlArena sl_arena(void* data, unsigned int* cursor, const uint32_t* roff, int B, int chunk) {
     SlArena a;
-    a.data = data; a.cursor = cursor; a.roff = roff; a.B = B; a.chunk = chunk; a.cap = 0; a.cursor_stride = kSlPad; a.rank_mode = sl_rank_mode();
+    a.data = data; a.cursor = cursor; a.roff = roff; a.B = B; a.chunk = chunk; a.cap = 0; a.cursor_stride = kSlPad;
     return a;
 }
 static SlArena sl_probe_arena(SlicedEngine* e) { return sl_arena(e->probe_data, e->probe_cursor, e->probe_roff, e->probe_B, sl_chunk()); }
@@ -217,12 +219,12 @@ static int32_t sliced_count_round(rb_graph* g, const Ingest& ing, int mode, floa
     if (fast) {
         grid_pos = (int)div_up(ing.n_pos, (int64_t)kSlTile);
         const size_t sm = std::max(sm_sort, PrefixKmerizer::smem_bytes());
-        if (mode == RB_MODE_FWD) SL_LAUNCH("ks_route_lookup_u<0>", ks_route_lookup_u<0>, grid_pos, sm, ing, g->k, hm, e->sg, probes, e->pos, fh, rh, e->overflow);
-        else SL_LAUNCH("ks_route_lookup_u<2>", ks_route_lookup_u<2>, grid_pos, sm, ing, g->k, hm, e->sg, probes, e->pos, fh, rh, e->overflow);
+        if (mode == RB_MODE_FWD) SL_LAUNCH("ks_route_lookup_u<0>", ks_route_lookup_u<0>, grid_pos, sm, ing, g->k, hm, e->sg, probes, e->pos, e->tile_meta, fh, rh, e->overflow);
+        else SL_LAUNCH("ks_route_lookup_u<2>", ks_route_lookup_u<2>, grid_pos, sm, ing, g->k, hm, e->sg, probes, e->pos, e->tile_meta, fh, rh, e->overflow);
     } else {
         grid_pos = (int)div_up(ing.n_pos, (int64_t)kSlThreads * kChunk);
-        if (mode == RB_MODE_FWD) SL_LAUNCH("ks_route_lookup<0>", ks_route_lookup<0>, grid_pos, sm_sort, ing, g->k, hm, e->sg, probes, e->pos, fh, rh, e->overflow);
-        else SL_LAUNCH("ks_route_lookup<2>", ks_route_lookup<2>, grid_pos, sm_sort, ing, g->k, hm, e->sg, probes, e->pos, fh, rh, e->overflow);
+        if (mode == RB_MODE_FWD) SL_LAUNCH("ks_route_lookup<0>", ks_route_lookup<0>, grid_pos, sm_sort, ing, g->k, hm, e->sg, probes, e->pos, e->tile_meta, fh, rh, e->overflow);
+        else SL_LAUNCH("ks_route_lookup<2>", ks_route_lookup<2>, grid_pos, sm_sort, ing, g->k, hm, e->sg, probes, e->pos, e->tile_meta, fh, rh, e->overflow);
     }
     int flag = 0;
     rc = sl_read_flag(ctx, e->overflow, &flag);
@@ -236,8 +238,9 @@ static int32_t sliced_count_round(rb_graph* g, const Ingest& ing, int mode, floa
     if (rc) return rc;
     SL_LAUNCH("ks_apply_probes<0>", ks_apply_probes<0>, grid, sm_pre, probes, e->chunk_prefix, e->sg, g->dbg->dev, g->cbf->dev, e->ans);
     // same CTA -> k-mer mapping as the route kernel
-    if (fast) SL_LAUNCH("ks_combine_lookup<1>", ks_combine_lookup<1>, grid_pos, 0, e->pos, e->ans, ing.n_pos, g->hd, g->hc, counts, ing.out_base);
-    else SL_LAUNCH("ks_combine_lookup<0>", ks_combine_lookup<0>, grid_pos, 0, e->pos, e->ans, ing.n_pos, g->hd, g->hc, counts, ing.out_base);
+    const size_t sm_ans = TileAnswers::smem_bytes(probes.B, kSlTile * kSlNJ);
+    if (fast) SL_LAUNCH("ks_combine_lookup<1>", ks_combine_lookup<1>, grid_pos, sm_ans, e->pos, e->tile_meta, probes.B, e->ans, ing.n_pos, g->hd, g->hc, counts, ing.out_base);
+    else SL_LAUNCH("ks_combine_lookup<0>", ks_combine_lookup<0>, grid_pos, sm_ans, e->pos, e->tile_meta, probes.B, e->ans, ing.n_pos, g->hd, g->hc, counts, ing.out_base);
     return RB_OK;
 }
 
@@ -294,7 +297,7 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     const int with_cbf = policy != POLICY_DBG_ONLY;
     const size_t sm_sort = TileSort<uint32_t, kSlRoundKmers * kSlNJ>::smem_bytes(probes.B);
     const int grid_d = (int)div_up(ing.n_pos, (int64_t)kSlThreads * kSlRoundKmers);   // distinct keys <= instances
-    SL_LAUNCH("ks_emit_probes", ks_emit_probes, grid_d, sm_sort, e->dkey, e->n_distinct, hm, e->sg, with_cbf, probes, e->pos, e->overflow);
+    SL_LAUNCH("ks_emit_probes", ks_emit_probes, grid_d, sm_sort, e->dkey, e->n_distinct, hm, e->sg, with_cbf, probes, e->pos, e->tile_meta, e->overflow);
     rc = sl_read_flag(ctx, e->overflow, &flag);
     if (rc) return rc;
     if (flag) { *fell_back = true; return RB_OK; }   // still nothing modified
@@ -314,8 +317,9 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
         const SlArena raises = sl_arena(e->raise_data, e->raise_cursor, e->raise_roff, e->sg.n_raise, sl_chunk());
         CK(cudaMemsetAsync(raises.cursor, 0, (size_t)raises.B * kSlPad * 4, ctx->stream));
         const uint64_t seed = ctx->rng_seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(ctx->launches + 1);
-        const size_t sm_r = TileSort<uint32_t, kSlRoundKmers * kSlMaxH>::smem_bytes(raises.B);
-        SL_LAUNCH("ks_combine_insert", ks_combine_insert, grid_d, sm_r, e->dkey, e->dmult, e->n_distinct, e->pos, e->ans, hm, e->sg, policy, seed, raises, e->overflow);
+        const size_t sm_r = std::max(TileSort<uint32_t, kSlRoundKmers * kSlMaxH>::smem_bytes(raises.B), TileAnswers::smem_bytes(probes.B, kSlTile * kSlNJ));
+        SL_LAUNCH("ks_combine_insert", ks_combine_insert, grid_d, sm_r, e->dkey, e->dmult, e->n_distinct, e->pos, e->tile_meta, probes.B, e->ans, hm, e->sg, policy, seed,
+                  raises, e->overflow);
         rc = sl_chunk_prefix(ctx, e, raises);
         if (rc) return rc;
         const size_t sm_rp = (size_t)(raises.B + 1) * 4;

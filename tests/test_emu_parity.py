@@ -46,33 +46,27 @@ def ctx(emu_lib):
 
 
 SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_RAISE_LOG2": "14", "RB_SLICED_SUBRANGE_LOG2": "6"}
-# The emulated warp ballots cost two OS-level barriers each, so the ballot ranking of the tile sort runs on a few tests only and the
-# shared-memory-atomic ranking (same results, RB_SLICED_RANK=atoms) carries the rest of the matrix; "direct" is here to validate
-# the emulation itself (that engine is verified on the GPU).
+# "direct" is here to validate the emulation itself (that engine is verified on the GPU); "default" = production slice geometry
 ONLY = {
-    "sliced-small-ballot": ("test_getkmers_with_invalid_nucleotides", "test_duplicates_inside_one_batch_are_linearised",
-                            "test_uniform_layout_graph_matches_oracle"),
-    "sliced-default-atoms": ("test_getkmers_with_invalid_nucleotides", "test_insert_policies_and_pair_filters",
-                             "test_uniform_layout_graph_matches_oracle"),
+    "sliced-default": ("test_getkmers_with_invalid_nucleotides", "test_insert_policies_and_pair_filters",
+                       "test_uniform_layout_graph_matches_oracle"),
     "direct": ("test_getkmers_with_invalid_nucleotides", "test_insert_policies_and_pair_filters"),
 }
 
 
-@pytest.fixture(autouse=True, params=["sliced-small-atoms", "sliced-small-ballot", "sliced-default-atoms", "direct"])
+@pytest.fixture(autouse=True, params=["sliced-small-atoms", "sliced-small-bigtable", "sliced-default-atoms", "direct"])
 def engine(request):
     """small: tiny slices / sub-ranges so that the small test filters span hundreds of regions; default: the production geometry."""
     name = request.node.originalname or request.node.name
     if request.param in ONLY and name not in ONLY[request.param]:
         pytest.skip("not in the reduced matrix of this variant")
-    keys = ["RB_ENGINE", "RB_SLICED_RANK"] + list(SLICE_ENV)
+    keys = ["RB_ENGINE"] + list(SLICE_ENV)
     old = {k: os.environ.get(k) for k in keys}
     os.environ["RB_ENGINE"] = request.param.split("-")[0]
     for k in keys[1:]:
         os.environ.pop(k, None)
     if "small" in request.param:
         os.environ.update(SLICE_ENV)
-    if "atoms" in request.param:
-        os.environ["RB_SLICED_RANK"] = "atoms"
     yield request.param
     for k, v in old.items():
         if v is None:
@@ -111,7 +105,6 @@ def test_kernels_are_race_free_under_tsan(tmp_path):
         subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-DRB_EMU", "-I", EMU_DIR, "-pthread",
                                os.path.join(EMU_DIR, "race_check.cpp"), "-o", exe])
     env = dict(os.environ, **SLICE_ENV)
-    env.pop("RB_SLICED_RANK", None)
     env["RB_ENGINE"] = "sliced"
     p = subprocess.run([exe, "120"], env=env, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0 and "race_check ok" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
