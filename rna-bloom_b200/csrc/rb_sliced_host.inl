@@ -147,7 +147,7 @@ static int32_t sl_read_flag(rb_ctx* ctx, int* dev_flag, int* host) {
 }
 template <typename K>
 static int32_t sl_persistent_grid(rb_ctx* ctx, K kernel, size_t smem, int* grid) {
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 32 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kSlThreads, smem));
     if (occ < 1) return fail(ctx, RB_ECUDA, "sliced engine: kernel does not fit on an SM");
@@ -156,7 +156,7 @@ static int32_t sl_persistent_grid(rb_ctx* ctx, K kernel, size_t smem, int* grid)
 }
 template <typename K>
 static int32_t sl_allow_smem(rb_ctx* ctx, K kernel, size_t smem) {
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 32 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return RB_OK;
 }
 // work list of an arena (one small CTA)
@@ -187,7 +187,7 @@ static bool sl_uniform_fast(const Ingest& ing, int k) {
 // grid of a kernel that streams over an arena with no residency window to respect
 template <typename K>
 static int32_t sl_stream_grid(rb_ctx* ctx, K kernel, size_t smem, int* grid) {
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 32 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kSlThreads, smem));
     if (occ < 1) return fail(ctx, RB_ECUDA, "sliced engine: kernel does not fit on an SM");
