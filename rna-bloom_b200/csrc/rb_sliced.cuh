@@ -51,6 +51,7 @@ struct SlArena {
     int chunk;                // records per work item of the kernels that consume the arena region by region
     uint32_t cap;             // roff == nullptr: every region holds cap records, region b = [b * cap, (b + 1) * cap)
     int cursor_stride;        // cursor of region b = cursor[b * cursor_stride] (kSlPad when the regions are few and hot)
+    int rank_mode;            // TileSort ranking: SL_RANK_ATOMS (default) / SL_RANK_MATCH
 };
 struct SlGeom {
     FastMod dbg_fm, cbf_fm;   // global index arithmetic (reference semantics)
@@ -101,6 +102,7 @@ __device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t* v, int n, uint3
 // copy     consecutive threads write consecutive addresses inside a bucket's run
 // A run that does not fit its region sets *overflow and is written past the region's end (at most one tile of records: the arenas
 // are allocated with that much slack); the host discards the round, so what it overwrites does not matter.
+enum { SL_RANK_ATOMS = 0, SL_RANK_MATCH = 1 };
 constexpr int kSlWarps = kSlThreads / 32;
 constexpr int kSlBucketsPerThread = kSlMaxRegions / kSlThreads;
 constexpr int kSlSpill = 8192;   // records of slack behind every arena (>= the largest tile)
@@ -109,16 +111,18 @@ __device__ __forceinline__ uint32_t sl_region_hi(const SlArena& a, int region) {
 template <typename REC, int E>
 struct TileSort {
     uint32_t *start, *delta, *scratch;   // [B] [B] [296]
+    uint16_t* whist;                     // [8 * B] SL_RANK_MATCH: per-warp counters, then per-warp offsets inside the (tile, bucket) run
     REC* stage;                          // [256 * E] records in bucket order
     uint16_t* tag;                       // [256 * E] bucket of each staged record
     int B;
-    static __host__ __device__ size_t words_of(int B) { return ((size_t)2 * B + 296 + 3) & ~(size_t)3; }
+    static __host__ __device__ size_t words_of(int B) { return ((size_t)2 * B + 296 + (size_t)kSlWarps * B / 2 + 4 + 3) & ~(size_t)3; }
     static __host__ __device__ size_t smem_bytes(int B) { return words_of(B) * 4 + (size_t)kSlThreads * E * sizeof(REC) + (size_t)kSlThreads * E * 2; }
     __device__ __forceinline__ void init(unsigned char* smem, int B_) {
         B = B_;
         start = reinterpret_cast<uint32_t*>(smem);
         delta = start + B;
         scratch = delta + B;
+        whist = reinterpret_cast<uint16_t*>(scratch + 296);
         stage = reinterpret_cast<REC*>(smem + words_of(B) * 4);
         tag = reinterpret_cast<uint16_t*>(smem + words_of(B) * 4 + (size_t)kSlThreads * E * sizeof(REC));
     }
@@ -128,24 +132,57 @@ struct TileSort {
     // later kernel finds the tile's answers again: answer of a record = ans[meta[b].x + rank].  Every thread of the CTA calls it.
     __device__ __forceinline__ void run(const SlArena& out, int region0, const int (&bkt)[E], const REC (&rec)[E], uint32_t (&place)[E], int* overflow,
                                         uint2* __restrict__ meta) {
-        const int t = threadIdx.x;
-        for (int b = t; b < B; b += kSlThreads) start[b] = 0;
-        __syncthreads();
+        const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+        const bool match = out.rank_mode == SL_RANK_MATCH;
+        if (match) {   // experiment: one match.any per row of 32 records, warp-private counters, no shared-memory atomics
+            uint32_t* wz = reinterpret_cast<uint32_t*>(whist);
+            for (int i = t; i < (kSlWarps * B + 1) / 2; i += kSlThreads) wz[i] = 0;
+            __syncthreads();
+            uint16_t* mine = whist + warp * B;
 #pragma unroll
-        for (int e = 0; e < E; ++e) place[e] = bkt[e] >= 0 ? ((uint32_t)bkt[e] | (atomicAdd(&start[bkt[e]], 1u) << 12)) : kNoSlot;
-        __syncthreads();
+            for (int e = 0; e < E; ++e) {
+                const bool valid = bkt[e] >= 0;
+                const uint32_t b = valid ? (uint32_t)bkt[e] : 0u;
+                const uint32_t peers = __match_any_sync(0xffffffffu, valid ? b : (0x80000000u | (uint32_t)lane));
+                const int leader = __ffs(peers) - 1;
+                uint32_t base = 0;
+                if (valid && lane == leader) { base = mine[b]; mine[b] = (uint16_t)(base + __popc(peers)); }
+                __syncwarp();
+                base = __shfl_sync(0xffffffffu, base, leader);
+                place[e] = valid ? (b | ((base + __popc(peers & ((1u << lane) - 1u))) << 12)) : kNoSlot;
+            }
+            __syncthreads();
+        } else {
+            for (int b = t; b < B; b += kSlThreads) start[b] = 0;
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < E; ++e) place[e] = bkt[e] >= 0 ? ((uint32_t)bkt[e] | (atomicAdd(&start[bkt[e]], 1u) << 12)) : kNoSlot;
+            __syncthreads();
+        }
         uint32_t at[kSlBucketsPerThread];
 #pragma unroll
         for (int q = 0; q < kSlBucketsPerThread; ++q) {
             const int b = t + q * kSlThreads;
             at[q] = 0;
-            if (b < B) { const uint32_t cnt = start[b]; if (cnt) at[q] = atomicAdd(&out.cursor[(size_t)(region0 + b) * out.cursor_stride], cnt); }
+            if (b < B) {
+                uint32_t cnt = 0;
+                if (match) {   // warp counters -> warp offsets inside the run, and the run's length
+#pragma unroll
+                    for (int w = 0; w < kSlWarps; ++w) { const uint32_t c = whist[w * B + b]; whist[w * B + b] = (uint16_t)cnt; cnt += c; }
+                    start[b] = cnt;
+                } else cnt = start[b];
+                if (cnt) at[q] = atomicAdd(&out.cursor[(size_t)(region0 + b) * out.cursor_stride], cnt);
+            }
         }
+        if (match) __syncthreads();   // start[] was just written with a thread-strided mapping, the scan reads it in contiguous pieces
         const uint32_t total = cta_exclusive_scan(start, B, scratch);   // start[b] = staging position of the bucket's first record
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             if (place[e] != kNoSlot) {
-                const uint32_t b = place[e] & 0xFFFu, p = start[b] + (place[e] >> 12);
+                const uint32_t b = place[e] & 0xFFFu;
+                uint32_t r = place[e] >> 12;
+                if (match) { r += whist[warp * B + b]; place[e] = b | (r << 12); }
+                const uint32_t p = start[b] + r;
                 stage[p] = rec[e];
                 tag[p] = (uint16_t)b;
             }
@@ -186,47 +223,42 @@ __device__ __forceinline__ void sl_probes(const SlGeom& sg, const HashMults& hm,
         }
     }
 }
-// a thread's 4 k-mers x 6 places are 96 contiguous, 16-byte aligned bytes of the position array
-__device__ __forceinline__ void sl_store_positions(uint32_t* pos, int64_t first, const uint32_t (&place)[kSlRoundKmers * kSlNJ]) {
-    uint4* dst = reinterpret_cast<uint4*>(pos + first * kSlNJ);
+// the 6 places of one k-mer (or distinct key) are 24 contiguous, 8-byte aligned bytes of the position array
+__device__ __forceinline__ void sl_store_places(uint32_t* pos, int64_t item, const uint32_t* place) {
+    uint2* dst = reinterpret_cast<uint2*>(pos + item * kSlNJ);
 #pragma unroll
-    for (int q = 0; q < kSlNJ; ++q) dst[q] = make_uint4(place[4 * q], place[4 * q + 1], place[4 * q + 2], place[4 * q + 3]);
+    for (int q = 0; q < kSlNJ / 2; ++q) dst[q] = make_uint2(place[2 * q], place[2 * q + 1]);
+}
+__device__ __forceinline__ void sl_load_places(const uint32_t* pos, int64_t item, uint32_t* place) {
+    const uint2* src = reinterpret_cast<const uint2*>(pos + item * kSlNJ);
+#pragma unroll
+    for (int q = 0; q < kSlNJ / 2; ++q) { const uint2 v = __ldg(src + q); place[2 * q] = v.x; place[2 * q + 1] = v.y; }
 }
 // The answers of a tile: its records sit in one run per bucket of the answer array (where the tile sort put them); the runs are
 // copied into shared memory in bucket order -- one warp per run, consecutive lanes read consecutive bytes -- and every thread
 // then picks its answers up at start[bucket] + rank.  (A per-record gather from global memory costs ~2 L1TEX cycles per
 // answer: 20 ms per 504 M k-mers in ks_combine_lookup; the runs of a tile are a few hundred sectors.)
 struct TileAnswers {
-    uint32_t* start;   // [B + 1]
+    uint32_t* start;   // [B + 1] (+ [B + 1] arena positions of the runs while loading)
     uint8_t* bytes;    // [tile records]
-    static __host__ __device__ size_t smem_bytes(int B, int tile_records) { return ((size_t)(B + 1) * 4 + (size_t)tile_records + 15) & ~(size_t)15; }
-    // every thread of the CTA calls it; meta = the tile's B + 1 entries written by TileSort::run
+    static __host__ __device__ size_t smem_bytes(int B, int tile_records) { return ((size_t)(2 * B + 2) * 4 + (size_t)tile_records + 15) & ~(size_t)15; }
+    // every thread of the CTA calls it; meta = the tile's B + 1 entries written by TileSort::run.  Eight lanes copy one run (a run
+    // is ~12-24 bytes), 32 runs per CTA step, and nothing in a step depends on the step before: the loads of many runs overlap.
     __device__ __forceinline__ void load(unsigned char* smem, int B, const uint2* __restrict__ meta, const uint8_t* __restrict__ ans) {
         start = reinterpret_cast<uint32_t*>(smem);
-        bytes = smem + (size_t)(B + 1) * 4;
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        for (int b = threadIdx.x; b <= B; b += kSlThreads) start[b] = __ldg(&meta[b]).y;
+        uint32_t* gpos = start + (B + 1);
+        bytes = smem + (size_t)(2 * B + 2) * 4;
+        for (int b = threadIdx.x; b <= B; b += kSlThreads) { const uint2 m = __ldg(&meta[b]); start[b] = m.y; gpos[b] = m.x; }
         __syncthreads();
-#pragma unroll 4
-        for (int b = warp; b < B; b += kSlThreads / 32) {
-            const uint32_t lo = start[b], n = start[b + 1] - lo;
-            if (n) {
-                const uint32_t g = __ldg(&meta[b]).x;
-                for (uint32_t i = lane; i < n; i += 32) bytes[lo + i] = __ldg(ans + g + i);
-            }
+        const int grp = threadIdx.x >> 3, l8 = threadIdx.x & 7;
+        for (int b = grp; b < B; b += kSlThreads / 8) {
+            const uint32_t lo = start[b], n = start[b + 1] - lo, g = gpos[b];
+            for (uint32_t i = l8; i < n; i += 8) bytes[lo + i] = __ldg(ans + g + i);
         }
         __syncthreads();
     }
     __device__ __forceinline__ uint32_t get(uint32_t place) const { return place != kNoSlot ? (uint32_t)bytes[start[place & 0xFFFu] + (place >> 12)] : 0u; }
 };
-__device__ __forceinline__ void sl_load_places(const uint32_t* pos, int64_t first, uint32_t (&place)[kSlRoundKmers * kSlNJ]) {
-    const uint4* src = reinterpret_cast<const uint4*>(pos + first * kSlNJ);
-#pragma unroll
-    for (int q = 0; q < kSlNJ; ++q) {
-        const uint4 v = __ldg(src + q);
-        place[4 * q] = v.x; place[4 * q + 1] = v.y; place[4 * q + 2] = v.z; place[4 * q + 3] = v.w;
-    }
-}
 
 // ---- prefix k-merizer (uniform read layout) ----------------------------------------------------------------------------------------------
 // ntHash is a XOR of rotated per-base seeds (bloom/hash/NTHash.java:332-373), so with x = index of a base in the CTA's span of the
@@ -326,18 +358,20 @@ __global__ void __launch_bounds__(kSlThreads) ks_route_lookup_u(const Ingest g, 
     const int64_t tile0 = (int64_t)blockIdx.x * kSlTile;
     PrefixKmerizer pk;
     pk.build<MODE>(sl_smem, g, k, tile0);
-    const int64_t p0 = tile0 + (int64_t)threadIdx.x * kSlRoundKmers;
+    // item i of thread t = position tile0 + i * 256 + t: consecutive lanes read consecutive prefix entries (no bank conflicts) and
+    // write consecutive 24-byte place records
     int bkt[kSlRoundKmers * kSlNJ];
     uint32_t rec[kSlRoundKmers * kSlNJ], slot[kSlRoundKmers * kSlNJ];
 #pragma unroll
     for (int i = 0; i < kSlRoundKmers; ++i) {
+        const int64_t p = tile0 + i * kSlThreads + threadIdx.x;
 #pragma unroll
         for (int j = 0; j < kSlNJ; ++j) { bkt[i * kSlNJ + j] = -1; rec[i * kSlNJ + j] = 0; }
-        if (p0 + i < g.n_pos) {
+        if (p < g.n_pos) {
             uint64_t f, r; int bad;
-            pk.eval<MODE>(g, k, p0 + i, f, r, bad);
-            if (fhash) fhash[g.out_base + p0 + i] = (int64_t)f;
-            if (rhash) rhash[g.out_base + p0 + i] = (int64_t)r;
+            pk.eval<MODE>(g, k, p, f, r, bad);
+            if (fhash) fhash[g.out_base + p] = (int64_t)f;
+            if (rhash) rhash[g.out_base + p] = (int64_t)r;
             if (bad == 0) sl_probes(sg, hm, PrefixKmerizer::base_of<MODE>(f, r), true, &bkt[i * kSlNJ], &rec[i * kSlNJ]);
         }
     }
@@ -345,7 +379,11 @@ __global__ void __launch_bounds__(kSlThreads) ks_route_lookup_u(const Ingest g, 
     TileSort<uint32_t, kSlRoundKmers * kSlNJ> ts;
     ts.init(sl_smem, arena.B);
     ts.run(arena, 0, bkt, rec, slot, overflow, tile_meta + (size_t)blockIdx.x * (arena.B + 1));
-    if (p0 < g.n_pos) sl_store_positions(pos, p0, slot);
+#pragma unroll
+    for (int i = 0; i < kSlRoundKmers; ++i) {
+        const int64_t p = tile0 + i * kSlThreads + threadIdx.x;
+        if (p < g.n_pos) sl_store_places(pos, p, &slot[i * kSlNJ]);
+    }
 }
 // ---- I1 (uniform layout) -------------------------------------------------------------------------------------------------------------------
 template <int MODE>
@@ -354,16 +392,16 @@ __global__ void __launch_bounds__(kSlThreads) ks_route_keys_u(const Ingest g, in
     const int64_t tile0 = (int64_t)blockIdx.x * kSlTile;
     PrefixKmerizer pk;
     pk.build<MODE>(sl_smem, g, k, tile0);
-    const int64_t p0 = tile0 + (int64_t)threadIdx.x * kSlRoundKmers;
     int bkt[kSlRoundKmers];
     unsigned long long rec[kSlRoundKmers];
     uint32_t slot[kSlRoundKmers];
 #pragma unroll
     for (int i = 0; i < kSlRoundKmers; ++i) {
+        const int64_t p = tile0 + i * kSlThreads + threadIdx.x;
         bkt[i] = -1; rec[i] = 0;
-        if (p0 + i < g.n_pos) {
+        if (p < g.n_pos) {
             uint64_t f, r; int bad;
-            pk.eval<MODE>(g, k, p0 + i, f, r, bad);
+            pk.eval<MODE>(g, k, p, f, r, bad);
             if (bad == 0) {
                 const uint64_t b = PrefixKmerizer::base_of<MODE>(f, r);
                 rec[i] = b;
@@ -408,7 +446,8 @@ __global__ void __launch_bounds__(kSlThreads) ks_route_lookup(const Ingest g, in
             }
         }
         ts.run(arena, 0, bkt, rec, slot, overflow, tile_meta + ((size_t)blockIdx.x * (kChunk / kSlRoundKmers) + r0 / kSlRoundKmers) * (arena.B + 1));
-        if (r0 < n) sl_store_positions(pos, pos0 + r0, slot);
+#pragma unroll
+        for (int i = 0; i < kSlRoundKmers; ++i) if (r0 + i < n) sl_store_places(pos, pos0 + r0 + i, &slot[i * kSlNJ]);
     }
 }
 
@@ -505,29 +544,24 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
 // k-mers per CTA; FLAT = 0: ks_route_lookup, 16 consecutive k-mers per thread in 4 rounds): the answers of a CTA round sit in
 // the few hundred runs its tile sort wrote, so the 32 B sectors a CTA gathers from are shared by its own threads (L1 hits)
 // instead of being fetched again by CTAs on other SMs (measured with mismatched mappings: 43 ms per 504 M k-mers).
-__device__ __forceinline__ void sl_counts_of_group(const uint32_t* __restrict__ pos, const TileAnswers& ta, int64_t i0, int64_t n_inst, int hd, int hc,
-                                                   float* __restrict__ counts, int64_t out_base) {
-    uint32_t place[kSlRoundKmers * kSlNJ];
-    sl_load_places(pos, i0, place);
+__device__ __forceinline__ void sl_count_of_kmer(const uint32_t* __restrict__ pos, const TileAnswers& ta, int64_t inst, int hd, int hc,
+                                                 float* __restrict__ counts, int64_t out_base) {
+    uint32_t place[kSlNJ];
+    sl_load_places(pos, inst, place);
+    float c = 0.f;
+    bool all = place[0] != kNoSlot;   // unusable k-mers (masked base in the window) made no probes
 #pragma unroll
-    for (int i = 0; i < kSlRoundKmers; ++i) {
-        if (i0 + i < n_inst) {
-            float c = 0.f;
-            bool all = place[i * kSlNJ] != kNoSlot;   // unusable k-mers (masked base in the window) made no probes
+    for (int h = 0; h < kSlMaxH; ++h) if (h < hd) all = all && (ta.get(place[h]) & 1u);
+    if (all) {
+        int mn = 127;
 #pragma unroll
-            for (int h = 0; h < kSlMaxH; ++h) if (h < hd) all = all && (ta.get(place[i * kSlNJ + h]) & 1u);
-            if (all) {
-                int mn = 127;
-#pragma unroll
-                for (int h = 0; h < kSlMaxH; ++h) if (h < hc) { const int v = (int)(int8_t)ta.get(place[i * kSlNJ + kSlMaxH + h]); mn = v < mn ? v : mn; }
-                c = minifloat_to_float(mn) + 1.f;
-            }
-            counts[out_base + i0 + i] = c;
-        }
+        for (int h = 0; h < kSlMaxH; ++h) if (h < hc) { const int v = (int)(int8_t)ta.get(place[kSlMaxH + h]); mn = v < mn ? v : mn; }
+        c = minifloat_to_float(mn) + 1.f;
     }
+    counts[out_base + inst] = c;
 }
-// FLAT = 1: tiles of ks_route_lookup_u (1024 consecutive k-mers per CTA); FLAT = 0: tiles of ks_route_lookup (16 consecutive k-mers
-// per thread, four tile sorts per CTA).  Same grid as the route kernel.
+// FLAT = 1: tiles of ks_route_lookup_u (1024 consecutive k-mers per CTA, item i of thread t = k-mer i * 256 + t);
+// FLAT = 0: tiles of ks_route_lookup (16 consecutive k-mers per thread, four tile sorts per CTA).  Same grid as the route kernel.
 template <int FLAT>
 __global__ void __launch_bounds__(kSlThreads) ks_combine_lookup(const uint32_t* __restrict__ pos, const uint2* __restrict__ tile_meta, int B,
                                                                const uint8_t* __restrict__ ans, int64_t n_inst, int hd, int hc,
@@ -536,14 +570,18 @@ __global__ void __launch_bounds__(kSlThreads) ks_combine_lookup(const uint32_t* 
     TileAnswers ta;
     if (FLAT) {
         ta.load(sl_smem, B, tile_meta + (size_t)blockIdx.x * (B + 1), ans);
-        const int64_t i0 = ((int64_t)blockIdx.x * kSlThreads + threadIdx.x) * kSlRoundKmers;
-        if (i0 < n_inst) sl_counts_of_group(pos, ta, i0, n_inst, hd, hc, counts, out_base);
+#pragma unroll
+        for (int i = 0; i < kSlRoundKmers; ++i) {
+            const int64_t inst = (int64_t)blockIdx.x * kSlTile + i * kSlThreads + threadIdx.x;
+            if (inst < n_inst) sl_count_of_kmer(pos, ta, inst, hd, hc, counts, out_base);
+        }
     } else {
         const int64_t pos0 = ((int64_t)blockIdx.x * kSlThreads + threadIdx.x) * kChunk;
 #pragma unroll 1
         for (int r0 = 0; r0 < kChunk; r0 += kSlRoundKmers) {
             ta.load(sl_smem, B, tile_meta + ((size_t)blockIdx.x * (kChunk / kSlRoundKmers) + r0 / kSlRoundKmers) * (B + 1), ans);
-            if (pos0 + r0 < n_inst) sl_counts_of_group(pos, ta, pos0 + r0, n_inst, hd, hc, counts, out_base);
+#pragma unroll
+            for (int i = 0; i < kSlRoundKmers; ++i) if (pos0 + r0 + i < n_inst) sl_count_of_kmer(pos, ta, pos0 + r0 + i, hd, hc, counts, out_base);
             __syncthreads();   // the next round overwrites the staged answers
         }
     }
@@ -661,17 +699,18 @@ __global__ void __launch_bounds__(kSlThreads) ks_emit_probes(const unsigned long
     RB_DYN_SMEM(unsigned char, sl_smem);
     TileSort<uint32_t, kSlRoundKmers * kSlNJ> ts;
     ts.init(sl_smem, arena.B);
-    const int64_t d0 = ((int64_t)blockIdx.x * kSlThreads + threadIdx.x) * kSlRoundKmers;
+    const int64_t d0 = (int64_t)blockIdx.x * kSlTile + threadIdx.x;   // item i of the thread = distinct key d0 + i * 256
     int bkt[kSlRoundKmers * kSlNJ];
     uint32_t rec[kSlRoundKmers * kSlNJ], slot[kSlRoundKmers * kSlNJ];
 #pragma unroll
     for (int i = 0; i < kSlRoundKmers; ++i) {
 #pragma unroll
         for (int j = 0; j < kSlNJ; ++j) { bkt[i * kSlNJ + j] = -1; rec[i * kSlNJ + j] = 0; }
-        if (d0 + i < nd) sl_probes(sg, hm, (uint64_t)dkey[d0 + i], with_cbf != 0, &bkt[i * kSlNJ], &rec[i * kSlNJ]);
+        if (d0 + i * kSlThreads < nd) sl_probes(sg, hm, (uint64_t)dkey[d0 + i * kSlThreads], with_cbf != 0, &bkt[i * kSlNJ], &rec[i * kSlNJ]);
     }
     ts.run(arena, 0, bkt, rec, slot, overflow, tile_meta + (size_t)blockIdx.x * (arena.B + 1));
-    if (d0 < nd) sl_store_positions(pos, d0, slot);
+#pragma unroll
+    for (int i = 0; i < kSlRoundKmers; ++i) if (d0 + i * kSlThreads < nd) sl_store_places(pos, d0 + i * kSlThreads, &slot[i * kSlNJ]);
 }
 
 // ---- I6: per distinct key: present?, replay the increments, emit one raise per counter that grew ----------------------------------------------
@@ -683,7 +722,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_combine_insert(const unsigned l
     const int64_t nd = (int64_t)*n_distinct;
     if ((int64_t)blockIdx.x * (kSlThreads * kSlRoundKmers) >= nd) return;   // whole CTA
     RB_DYN_SMEM(unsigned char, sl_smem);
-    const int64_t d0 = ((int64_t)blockIdx.x * kSlThreads + threadIdx.x) * kSlRoundKmers;
+    const int64_t d0 = (int64_t)blockIdx.x * kSlTile + threadIdx.x;   // item i of the thread = distinct key d0 + i * 256 (as in ks_emit_probes)
     int bkt[kSlRoundKmers * kSlMaxH];
     uint32_t rec[kSlRoundKmers * kSlMaxH], rslot[kSlRoundKmers * kSlMaxH];
 #pragma unroll
@@ -691,21 +730,24 @@ __global__ void __launch_bounds__(kSlThreads) ks_combine_insert(const unsigned l
     TileAnswers ta;   // the tile of ks_emit_probes with the same block index
     ta.load(sl_smem, probe_B, tile_meta + (size_t)blockIdx.x * (probe_B + 1), ans);
     uint32_t a[kSlRoundKmers * kSlNJ];
-    if (d0 < nd) {
-        uint32_t place[kSlRoundKmers * kSlNJ];
-        sl_load_places(pos, d0, place);
 #pragma unroll
-        for (int e = 0; e < kSlRoundKmers * kSlNJ; ++e) a[e] = ta.get(place[e]);
+    for (int i = 0; i < kSlRoundKmers; ++i) {
+        uint32_t place[kSlNJ];
+#pragma unroll
+        for (int j = 0; j < kSlNJ; ++j) place[j] = kNoSlot;
+        if (d0 + i * kSlThreads < nd) sl_load_places(pos, d0 + i * kSlThreads, place);
+#pragma unroll
+        for (int j = 0; j < kSlNJ; ++j) a[i * kSlNJ + j] = ta.get(place[j]);
     }
     __syncthreads();   // the tile sort of the raises reuses the shared memory
     TileSort<uint32_t, kSlRoundKmers * kSlMaxH> ts;
     ts.init(sl_smem, raises.B);
-    if (d0 < nd) {
+    {
 #pragma unroll
         for (int i = 0; i < kSlRoundKmers; ++i) {
-            if (d0 + i < nd) {
-                const uint64_t key = (uint64_t)dkey[d0 + i];
-                const unsigned int m = dmult[d0 + i];
+            if (d0 + i * kSlThreads < nd) {
+                const uint64_t key = (uint64_t)dkey[d0 + i * kSlThreads];
+                const unsigned int m = dmult[d0 + i * kSlThreads];
                 bool present = true;
 #pragma unroll
                 for (int h = 0; h < kSlMaxH; ++h) if (h < sg.hd) present = present && (a[i * kSlNJ + h] & 1u);

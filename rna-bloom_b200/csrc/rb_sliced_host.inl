@@ -172,6 +172,7 @@ static int32_t sl_chunk_prefix(rb_ctx* ctx, SlicedEngine* e, const SlArena& a) {
 static SlArena sl_arena(void* data, unsigned int* cursor, const uint32_t* roff, int B, int chunk) {
     SlArena a;
     a.data = data; a.cursor = cursor; a.roff = roff; a.B = B; a.chunk = chunk; a.cap = 0; a.cursor_stride = kSlPad;
+    { const char* v = getenv("RB_SLICED_RANK"); a.rank_mode = (v && !strcmp(v, "match")) ? SL_RANK_MATCH : SL_RANK_ATOMS; }
     return a;
 }
 static SlArena sl_probe_arena(SlicedEngine* e) { return sl_arena(e->probe_data, e->probe_cursor, e->probe_roff, e->probe_B, sl_chunk()); }

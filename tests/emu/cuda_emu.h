@@ -122,6 +122,16 @@ static inline unsigned __ballot_sync(unsigned, int pred) {   // every lane of th
     emu::g_warp_barrier[w]->arrive_and_wait();
     return m;
 }
+static inline unsigned __match_any_sync(unsigned, unsigned value) {   // every lane of the warp must call it (full mask)
+    const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    emu::g_warp_xchg[w][l] = value;
+    emu::g_warp_barrier[w]->arrive_and_wait();
+    unsigned m = 0;
+    const unsigned lanes = std::min(32u, blockDim.x - w * 32);
+    for (unsigned i = 0; i < lanes; ++i) if ((unsigned)emu::g_warp_xchg[w][i] == value) m |= 1u << i;
+    emu::g_warp_barrier[w]->arrive_and_wait();
+    return m;
+}
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline void __syncwarp() {   // every lane of the warp must call it
     const unsigned w = threadIdx.x >> 5;

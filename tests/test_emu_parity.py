@@ -48,6 +48,8 @@ def ctx(emu_lib):
 SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_RAISE_LOG2": "14", "RB_SLICED_SUBRANGE_LOG2": "6"}
 # "direct" is here to validate the emulation itself (that engine is verified on the GPU); "default" = production slice geometry
 ONLY = {
+    "sliced-small-match": ("test_getkmers_with_invalid_nucleotides", "test_duplicates_inside_one_batch_are_linearised",
+                           "test_uniform_layout_graph_matches_oracle"),
     "sliced-default": ("test_getkmers_with_invalid_nucleotides", "test_insert_policies_and_pair_filters",
                        "test_uniform_layout_graph_matches_oracle"),
     "direct": ("test_getkmers_with_invalid_nucleotides", "test_insert_policies_and_pair_filters"),
@@ -60,13 +62,15 @@ def engine(request):
     name = request.node.originalname or request.node.name
     if request.param in ONLY and name not in ONLY[request.param]:
         pytest.skip("not in the reduced matrix of this variant")
-    keys = ["RB_ENGINE"] + list(SLICE_ENV)
+    keys = ["RB_ENGINE", "RB_SLICED_RANK"] + list(SLICE_ENV)
     old = {k: os.environ.get(k) for k in keys}
     os.environ["RB_ENGINE"] = request.param.split("-")[0]
     for k in keys[1:]:
         os.environ.pop(k, None)
     if "small" in request.param:
         os.environ.update(SLICE_ENV)
+    if "match" in request.param:
+        os.environ["RB_SLICED_RANK"] = "match"   # experimental ranking of the tile sort (warp match.any instead of shared-memory atomics)
     yield request.param
     for k, v in old.items():
         if v is None:
