@@ -167,7 +167,7 @@ def main():
     ap.add_argument("--subbatch-kmers", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--engine", default=os.environ.get("RB_ENGINE", "direct"), choices=["direct", "bucketed", "sliced"])
+    ap.add_argument("--engine", default=os.environ.get("RB_ENGINE", "sliced"), choices=["direct", "sliced", "auto"])
     ap.add_argument("--sharded", action="store_true", help="experiments only: run the sharded pipeline even on one GPU")
     ap.add_argument("--genome", type=int, default=GENOME, help="experiments only: virtual genome length (coverage knob)")
     args = ap.parse_args()
@@ -276,20 +276,21 @@ def main():
     top = max(prof.items(), key=lambda kv: kv[1][0]) if prof else ("?", (0.0, 1))
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     traffic_tab = json.load(open(tp)) if os.path.exists(tp) else {}
-    if args.engine == "direct":
+    if args.engine == "direct" or not any(k_.startswith("ks_") for k_ in prof):
         name = "k_graph_insert" if ins_dominant else "k_graph_count"
         ms_sum, calls = prof.get(name, (t_ins if ins_dominant else t_look, args.steps))
         kmers_per_launch = kmers_total / calls
         ms_per_launch = ms_sum / calls
         traffic = traffic_tab.get(name)
     else:
-        # a phase of the sliced / bucketed engine is a chain of kernels over one round; the sector model prices the phase (the k-mer
-        # operation), so the roofline line is the whole chain: every launch between the phase's first and last kernel, memsets included
-        name = ("insert" if ins_dominant else "lookup") + " round of the %s engine (kernel chain, see kernels_ms_per_step)" % args.engine
-        rounds = max(1, prof.get("ks_route_keys<2>" if ins_dominant else "ks_route_lookup<2>", (0.0, args.steps))[1])
+        # a phase of the sliced engine is a chain of kernels over one round; the sector model prices the phase (the k-mer operation),
+        # so the roofline line is the whole chain: everything between the phase's first and last kernel, memsets and syncs included
+        name = ("insert" if ins_dominant else "lookup") + " round of the sliced engine (kernel chain, see kernels_ms_per_step)"
+        first = "ks_route_keys" if ins_dominant else "ks_route_lookup"
+        rounds = max([v[1] for k_, v in prof.items() if k_.startswith(first)] + [args.steps])
         kmers_per_launch = kmers_total / rounds
         ms_per_launch = (t_ins if ins_dominant else t_look) / rounds
-        traffic = traffic_tab.get(args.engine + ("_insert_round" if ins_dominant else "_lookup_round"))
+        traffic = traffic_tab.get("sliced_insert_round" if ins_dominant else "sliced_lookup_round")
     achieved = kmers_per_launch * a_k / (ms_per_launch * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": hbm,
                 "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic, "peak_source": peak_src,

@@ -164,12 +164,13 @@ RB_API int32_t rb_graph_set_distances(rb_graph* g, int32_t d_read, int32_t d_fra
 RB_API int32_t rb_graph_filter(rb_graph* g, int32_t which, rb_filter** out); /* borrowed handle; NULL if absent */
 RB_API int32_t rb_graph_clear(rb_graph* g);
 /* Execution engine of the read-level insert/lookup calls (same results, different HBM schedule):
- *   RB_ENGINE_DIRECT   one fused kernel, every probe an isolated HBM sector access (bounded by DRAM row activations)
- *   RB_ENGINE_BUCKETED probes partitioned by 32 MiB filter slice and applied slice by slice out of L2 (needs numHash(dbgbf)+numHash(cbf) <= 8)
- *   RB_ENGINE_SLICED   probes tile-sorted by 64 MiB filter slice, applied slice by slice out of L2, answers gathered through
- *                      remembered positions; rounds of up to 2^29 k-mers (needs numHash(dbgbf) <= 3 and numHash(cbf) <= 3,
- *                      otherwise the direct engine serves the call) */
-enum { RB_ENGINE_DIRECT = 0, RB_ENGINE_BUCKETED = 1, RB_ENGINE_SLICED = 2 };
+ *   RB_ENGINE_DIRECT  one fused kernel, every probe an isolated random HBM access (one DRAM line request per probe)
+ *   RB_ENGINE_SLICED  probes tile-sorted by 64 MiB filter slice, applied slice by slice out of L2, answers picked up per tile;
+ *                     rounds of up to 2^29 k-mers.  Needs numHash(dbgbf) <= 3 and numHash(cbf) <= 3 and un-skewed hashes; a
+ *                     round it cannot take is done by the direct engine (before anything was modified)
+ *   RB_ENGINE_AUTO    (default) sliced for rounds of at least 2^20 k-mers, direct below
+ * The environment variable RB_ENGINE = direct | sliced | auto sets the engine of graphs created afterwards. */
+enum { RB_ENGINE_DIRECT = 0, RB_ENGINE_SLICED = 2, RB_ENGINE_AUTO = 3 };
 RB_API int32_t rb_graph_set_engine(rb_graph* g, int32_t engine);                                 /* clearDbgbf/Cbf/Rpkbf/Fpkbf :211-245 */
 
 /* Bulk insert = the body of the five live insert workers (RNABloom.java:364-732,1463-1539): for every usable k-mer of

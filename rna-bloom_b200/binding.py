@@ -7,7 +7,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 _SO = os.path.join(_HERE, "librnabloom_gpu.so")
-_SRC = [os.path.join(_HERE, "csrc", n) for n in ("rnabloom_gpu.cu", "rb_kernels.cuh", "rb_device.cuh", "rb_shard.cuh", "rb_bucket.cuh", "rb_sliced.cuh",
+_SRC = [os.path.join(_HERE, "csrc", n) for n in ("rnabloom_gpu.cu", "rb_kernels.cuh", "rb_device.cuh", "rb_shard.cuh", "rb_sliced.cuh",
                                                  "rb_sliced_host.inl")] + [
     os.path.join(_ROOT, "include", "rnabloom_gpu.h")]
 

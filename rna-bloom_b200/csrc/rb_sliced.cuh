@@ -51,7 +51,6 @@ struct SlArena {
     int chunk;                // records per work item of the kernels that consume the arena region by region
     uint32_t cap;             // roff == nullptr: every region holds cap records, region b = [b * cap, (b + 1) * cap)
     int cursor_stride;        // cursor of region b = cursor[b * cursor_stride] (kSlPad when the regions are few and hot)
-    int rank_mode;            // TileSort ranking: SL_RANK_ATOMS (default) / SL_RANK_MATCH
 };
 struct SlGeom {
     FastMod dbg_fm, cbf_fm;   // global index arithmetic (reference semantics)
@@ -94,15 +93,15 @@ __device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t* v, int n, uint3
 
 // ---- CTA-wide multisplit of up to 256 * E records into the regions of an arena -------------------------------------------------
 // rank     shared-memory atomicAdd on the bucket's counter; its return value is the record's place inside the (tile, bucket) run.
-//          (A warp-ballot ranking -- one __ballot_sync per bucket-id bit, warp-private counters, no atomics -- was measured too:
-//          30.4 against 23.1 ms per 504 M k-mers in ks_route_lookup_u; ATOMS is the cheaper instruction mix on this part.)
+//          (Warp-level rankings with warp-private counters and no atomics were measured too -- one __ballot_sync per bucket-id
+//          bit: 30.4 ms, one __match_any_sync per row: 31.1 ms, against 21-23 ms per 504 M k-mers in ks_route_lookup_u with
+//          ATOMS -- the atomic is the cheaper instruction mix on this part; git history has both variants.)
 // reserve  one global cursor bump per (tile, bucket), issued before the scan and consumed after the staging, so its ~1 us round trip
 //          is overlapped
 // stage    records + their bucket ids in bucket order in shared memory
 // copy     consecutive threads write consecutive addresses inside a bucket's run
 // A run that does not fit its region sets *overflow and is written past the region's end (at most one tile of records: the arenas
 // are allocated with that much slack); the host discards the round, so what it overwrites does not matter.
-enum { SL_RANK_ATOMS = 0, SL_RANK_MATCH = 1 };
 constexpr int kSlWarps = kSlThreads / 32;
 constexpr int kSlBucketsPerThread = kSlMaxRegions / kSlThreads;
 constexpr int kSlSpill = 8192;   // records of slack behind every arena (>= the largest tile)
@@ -111,18 +110,16 @@ __device__ __forceinline__ uint32_t sl_region_hi(const SlArena& a, int region) {
 template <typename REC, int E>
 struct TileSort {
     uint32_t *start, *delta, *scratch;   // [B] [B] [296]
-    uint16_t* whist;                     // [8 * B] SL_RANK_MATCH: per-warp counters, then per-warp offsets inside the (tile, bucket) run
     REC* stage;                          // [256 * E] records in bucket order
     uint16_t* tag;                       // [256 * E] bucket of each staged record
     int B;
-    static __host__ __device__ size_t words_of(int B) { return ((size_t)2 * B + 296 + (size_t)kSlWarps * B / 2 + 4 + 3) & ~(size_t)3; }
+    static __host__ __device__ size_t words_of(int B) { return ((size_t)2 * B + 296 + 3) & ~(size_t)3; }
     static __host__ __device__ size_t smem_bytes(int B) { return words_of(B) * 4 + (size_t)kSlThreads * E * sizeof(REC) + (size_t)kSlThreads * E * 2; }
     __device__ __forceinline__ void init(unsigned char* smem, int B_) {
         B = B_;
         start = reinterpret_cast<uint32_t*>(smem);
         delta = start + B;
         scratch = delta + B;
-        whist = reinterpret_cast<uint16_t*>(scratch + 296);
         stage = reinterpret_cast<REC*>(smem + words_of(B) * 4);
         tag = reinterpret_cast<uint16_t*>(smem + words_of(B) * 4 + (size_t)kSlThreads * E * sizeof(REC));
     }
@@ -132,57 +129,24 @@ struct TileSort {
     // later kernel finds the tile's answers again: answer of a record = ans[meta[b].x + rank].  Every thread of the CTA calls it.
     __device__ __forceinline__ void run(const SlArena& out, int region0, const int (&bkt)[E], const REC (&rec)[E], uint32_t (&place)[E], int* overflow,
                                         uint2* __restrict__ meta) {
-        const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-        const bool match = out.rank_mode == SL_RANK_MATCH;
-        if (match) {   // experiment: one match.any per row of 32 records, warp-private counters, no shared-memory atomics
-            uint32_t* wz = reinterpret_cast<uint32_t*>(whist);
-            for (int i = t; i < (kSlWarps * B + 1) / 2; i += kSlThreads) wz[i] = 0;
-            __syncthreads();
-            uint16_t* mine = whist + warp * B;
+        const int t = threadIdx.x;
+        for (int b = t; b < B; b += kSlThreads) start[b] = 0;
+        __syncthreads();
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const bool valid = bkt[e] >= 0;
-                const uint32_t b = valid ? (uint32_t)bkt[e] : 0u;
-                const uint32_t peers = __match_any_sync(0xffffffffu, valid ? b : (0x80000000u | (uint32_t)lane));
-                const int leader = __ffs(peers) - 1;
-                uint32_t base = 0;
-                if (valid && lane == leader) { base = mine[b]; mine[b] = (uint16_t)(base + __popc(peers)); }
-                __syncwarp();
-                base = __shfl_sync(0xffffffffu, base, leader);
-                place[e] = valid ? (b | ((base + __popc(peers & ((1u << lane) - 1u))) << 12)) : kNoSlot;
-            }
-            __syncthreads();
-        } else {
-            for (int b = t; b < B; b += kSlThreads) start[b] = 0;
-            __syncthreads();
-#pragma unroll
-            for (int e = 0; e < E; ++e) place[e] = bkt[e] >= 0 ? ((uint32_t)bkt[e] | (atomicAdd(&start[bkt[e]], 1u) << 12)) : kNoSlot;
-            __syncthreads();
-        }
+        for (int e = 0; e < E; ++e) place[e] = bkt[e] >= 0 ? ((uint32_t)bkt[e] | (atomicAdd(&start[bkt[e]], 1u) << 12)) : kNoSlot;
+        __syncthreads();
         uint32_t at[kSlBucketsPerThread];
 #pragma unroll
         for (int q = 0; q < kSlBucketsPerThread; ++q) {
             const int b = t + q * kSlThreads;
             at[q] = 0;
-            if (b < B) {
-                uint32_t cnt = 0;
-                if (match) {   // warp counters -> warp offsets inside the run, and the run's length
-#pragma unroll
-                    for (int w = 0; w < kSlWarps; ++w) { const uint32_t c = whist[w * B + b]; whist[w * B + b] = (uint16_t)cnt; cnt += c; }
-                    start[b] = cnt;
-                } else cnt = start[b];
-                if (cnt) at[q] = atomicAdd(&out.cursor[(size_t)(region0 + b) * out.cursor_stride], cnt);
-            }
+            if (b < B) { const uint32_t cnt = start[b]; if (cnt) at[q] = atomicAdd(&out.cursor[(size_t)(region0 + b) * out.cursor_stride], cnt); }
         }
-        if (match) __syncthreads();   // start[] was just written with a thread-strided mapping, the scan reads it in contiguous pieces
         const uint32_t total = cta_exclusive_scan(start, B, scratch);   // start[b] = staging position of the bucket's first record
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             if (place[e] != kNoSlot) {
-                const uint32_t b = place[e] & 0xFFFu;
-                uint32_t r = place[e] >> 12;
-                if (match) { r += whist[warp * B + b]; place[e] = b | (r << 12); }
-                const uint32_t p = start[b] + r;
+                const uint32_t b = place[e] & 0xFFFu, p = start[b] + (place[e] >> 12);
                 stage[p] = rec[e];
                 tag[p] = (uint16_t)b;
             }

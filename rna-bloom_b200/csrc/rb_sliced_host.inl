@@ -36,14 +36,18 @@ static int env_int(const char* name, int dflt, int lo, int hi) {
 }
 // Consumers walk an arena region by region with a window of grid * chunk records in flight; the window has to stay a small
 // fraction of a region or several filter / table slices are live at once and fall out of L2.
-static int sl_chunk() { return env_int("RB_SLICED_CHUNK", 4096, 256, 1 << 16); }
-static int sl_consumer_occ() { return env_int("RB_SLICED_CONSUMER_OCC", 4, 1, 8); }
+static bool sliced_supports(const rb_graph* g) { return g->hd <= kSlMaxH && g->hc <= kSlMaxH && !(g->se && g->se->unsupported); }
+static int sl_chunk() { return env_int("RB_SLICED_CHUNK", 2048, 256, 1 << 16); }
+static int sl_consumer_occ() { return env_int("RB_SLICED_CONSUMER_OCC", 8, 1, 8); }
 static int64_t sl_pow2_at_least(int64_t v) { int64_t p = 1024; while (p < v) p <<= 1; return p; }
 // capacity of a region that expects `expected` records from uniform hashes: 4 % + 8 sigma + a constant
 static int64_t sl_capacity(double expected) { return (int64_t)(expected * 1.04 + 8.0 * std::sqrt(expected + 1.0)) + 2048; }
-static int64_t sliced_round_kmers(const rb_ctx* ctx) {
+// Rounds are as large as the 32-bit record positions allow (one sweep of the filters is amortised over the round); look-ups whose
+// results go back to host memory use smaller rounds so that the D2H copy of one round overlaps the kernels of the next.
+static int64_t sliced_round_kmers(const rb_ctx* ctx, bool host_results) {
     if (ctx->subbatch_user_set) return std::min<int64_t>(ctx->subbatch_kmers, 1LL << 29);
-    return 1LL << env_int("RB_SLICED_ROUND_LOG2", 28, 10, 29);
+    if (host_results) return 1LL << env_int("RB_SLICED_HOST_ROUND_LOG2", 27, 10, 29);
+    return 1LL << env_int("RB_SLICED_ROUND_LOG2", 29, 10, 29);
 }
 
 // Uploads region offsets (B + 1 values) for uniform or two-kind capacities; returns the total number of records.
@@ -72,8 +76,8 @@ static int32_t sliced_engine_get(rb_graph* g, int64_t n_round, SlicedEngine** ou
     SlGeom& sg = e->sg;
     sg.dbg_fm = make_fm(g->dbg->size); sg.cbf_fm = make_fm(g->cbf->size);
     sg.hd = g->hd; sg.hc = g->hc;
-    sg.dbg_log2 = env_int("RB_SLICE_BITS_LOG2", 28, 5, 31);     // 32 MiB of bits
-    sg.cbf_log2 = env_int("RB_SLICE_BYTES_LOG2", 25, 2, 31);    // 32 MiB of counters
+    sg.dbg_log2 = env_int("RB_SLICE_BITS_LOG2", 29, 5, 31);     // 64 MiB of bits
+    sg.cbf_log2 = env_int("RB_SLICE_BYTES_LOG2", 26, 2, 31);    // 64 MiB of counters
     for (;;) {
         sg.n_dbg = (int)std::min<int64_t>(div_up(g->dbg->size, 1LL << sg.dbg_log2), 1 << 20);
         sg.n_cbf = (int)std::min<int64_t>(div_up(g->cbf->size, 1LL << sg.cbf_log2), 1 << 20);
@@ -172,7 +176,6 @@ static int32_t sl_chunk_prefix(rb_ctx* ctx, SlicedEngine* e, const SlArena& a) {
 static SlArena sl_arena(void* data, unsigned int* cursor, const uint32_t* roff, int B, int chunk) {
     SlArena a;
     a.data = data; a.cursor = cursor; a.roff = roff; a.B = B; a.chunk = chunk; a.cap = 0; a.cursor_stride = kSlPad;
-    { const char* v = getenv("RB_SLICED_RANK"); a.rank_mode = (v && !strcmp(v, "match")) ? SL_RANK_MATCH : SL_RANK_ATOMS; }
     return a;
 }
 static SlArena sl_probe_arena(SlicedEngine* e) { return sl_arena(e->probe_data, e->probe_cursor, e->probe_roff, e->probe_B, sl_chunk()); }

@@ -4,9 +4,8 @@
 #include "../../include/rnabloom_gpu.h"
 #include "rb_kernels.cuh"
 #include "rb_sliced.cuh"
-#ifndef RB_EMU   // the host emulation (tests/emu) covers the direct and the sliced engine only
+#ifndef RB_EMU   // the host emulation (tests/emu) covers the direct and the sliced engine, not the sharded pipeline
 #include "rb_shard.cuh"
-#include "rb_bucket.cuh"
 #endif
 
 #include <algorithm>
@@ -62,15 +61,13 @@ struct rb_filter {
     uint32_t* dev;
     bool in_graph;
 };
-struct BucketEngine;
 struct SlicedEngine;
 struct rb_graph {
     rb_ctx* ctx;
     rb_filter *dbg, *cbf, *rpk, *fpk;
     int k, stranded, hd, hc, hp, hmax;
     int d_read, d_frag;
-    int engine;            // RB_ENGINE_DIRECT / RB_ENGINE_BUCKETED
-    BucketEngine* be;      // lazily built
+    int engine;            // RB_ENGINE_AUTO / RB_ENGINE_DIRECT / RB_ENGINE_SLICED
     SlicedEngine* se;      // lazily built
 };
 
@@ -838,14 +835,13 @@ extern "C" int32_t rb_graph_create(rb_ctx* ctx, int64_t dbg_bits, int64_t cbf_by
     g->dbg->in_graph = g->cbf->in_graph = true;
     if (g->rpk) g->rpk->in_graph = true;
     const char* eng = getenv("RB_ENGINE");
-    g->engine = (eng && !strcmp(eng, "bucketed")) ? RB_ENGINE_BUCKETED : (eng && !strcmp(eng, "sliced")) ? RB_ENGINE_SLICED : RB_ENGINE_DIRECT;
+    g->engine = (eng && !strcmp(eng, "direct")) ? RB_ENGINE_DIRECT : (eng && !strcmp(eng, "sliced")) ? RB_ENGINE_SLICED : RB_ENGINE_AUTO;
     *out = g;
     return RB_OK;
 }
-static void bucket_engine_free(rb_graph* g);
 static void sliced_engine_free(rb_graph* g);
 extern "C" int32_t rb_graph_set_engine(rb_graph* g, int32_t engine) {
-    if (!g || (engine != RB_ENGINE_DIRECT && engine != RB_ENGINE_BUCKETED && engine != RB_ENGINE_SLICED)) return RB_EINVAL;
+    if (!g || (engine != RB_ENGINE_DIRECT && engine != RB_ENGINE_SLICED && engine != RB_ENGINE_AUTO)) return RB_EINVAL;
     LOCK(g->ctx);
     g->engine = engine;
     return RB_OK;
@@ -853,7 +849,6 @@ extern "C" int32_t rb_graph_set_engine(rb_graph* g, int32_t engine) {
 extern "C" int32_t rb_graph_destroy(rb_graph* g) {
     if (!g) return RB_EINVAL;
     LOCK(g->ctx);
-    bucket_engine_free(g);
     sliced_engine_free(g);
     if (g->dbg) filter_free(g->dbg);
     if (g->cbf) filter_free(g->cbf);
@@ -909,26 +904,29 @@ static void launch_insert_mode(int mode, int policy, int grid, cudaStream_t s, c
     else launch_insert<2, MAXH>(policy, grid, s, ing, gd);
 }
 struct InsertUser { rb_graph* g; int mode, policy; };
-static int32_t bucket_insert_round(rb_graph* g, const Ingest& ing, int mode, int policy, bool* fell_back);
 static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int policy, bool* fell_back);
 static int32_t sliced_count_round(rb_graph* g, const Ingest& ing, int mode, float* counts, int64_t* fh, int64_t* rh, bool* fell_back);
-static int64_t sliced_round_kmers(const rb_ctx* ctx);
+static int64_t sliced_round_kmers(const rb_ctx* ctx, bool host_results);
+static bool sliced_supports(const rb_graph* g);
+constexpr int64_t kAutoSlicedMinKmers = 1LL << 20;   // RB_ENGINE_AUTO: rounds smaller than this go to the direct kernels (14 launches and
+                                                     // 3 stream syncs per sliced round only pay off on large rounds)
+static bool use_sliced(const rb_graph* g, int64_t n_pos) {
+    if (g->engine == RB_ENGINE_SLICED) return true;
+    return g->engine == RB_ENGINE_AUTO && n_pos >= kAutoSlicedMinKmers && sliced_supports(g);
+}
 // the sliced engine amortises one sweep of the filters over a whole round, so its rounds are much larger than the direct launches
 struct RoundSize {
     rb_ctx* c; int64_t keep;
-    RoundSize(rb_graph* g) : c(g->ctx), keep(g->ctx->subbatch_kmers) { if (g->engine == RB_ENGINE_SLICED) c->subbatch_kmers = sliced_round_kmers(c); }
+    RoundSize(rb_graph* g, bool host_results) : c(g->ctx), keep(g->ctx->subbatch_kmers) {
+        if (g->engine != RB_ENGINE_DIRECT && sliced_supports(g)) c->subbatch_kmers = sliced_round_kmers(c, host_results);
+    }
     ~RoundSize() { c->subbatch_kmers = keep; }
 };
 static int32_t insert_launch(rb_ctx* ctx, const Ingest& ing, void* user) {
     InsertUser* u = (InsertUser*)user;
-    if (u->g->engine == RB_ENGINE_SLICED) {
+    if (use_sliced(u->g, ing.n_pos)) {
         bool fell_back = false;
         const int32_t rc = sliced_insert_round(u->g, ing, u->mode, u->policy, &fell_back);
-        if (rc || !fell_back) return rc;
-    }
-    if (u->g->engine == RB_ENGINE_BUCKETED && u->g->hd + u->g->hc <= 8) {
-        bool fell_back = false;
-        const int32_t rc = bucket_insert_round(u->g, ing, u->mode, u->policy, &fell_back);
         if (rc || !fell_back) return rc;
     }
     GraphDev gd = graph_view(u->g);
@@ -978,7 +976,7 @@ static int32_t graph_add_reads(rb_graph* g, const ReadsArg& ra, uint32_t flags, 
     int64_t total = 0;
     if (!(flags & RB_PAIRS_EXISTING_ONLY)) {
         InsertUser u{g, mode, (flags & RB_DBG_ONLY) ? POLICY_DBG_ONLY : (flags & RB_ADD_COUNT_IF_PRESENT) ? POLICY_COUNT_IF_PRESENT : POLICY_ADD};
-        RoundSize rs(g);
+        RoundSize rs(g, false);
         const int32_t rc = for_each_launch(ctx, ra, g->k, insert_launch, &u, &total);
         if (rc) return rc;
     }
@@ -1075,7 +1073,6 @@ static void launch_count_mode(int mode, int grid, cudaStream_t s, const Ingest& 
     if (mode == RB_MODE_FWD) RB_LAUNCH(grid, kThreads, 0, s, k_graph_count<0, MAXH>)(ing, gd, c, f, r);
     else RB_LAUNCH(grid, kThreads, 0, s, k_graph_count<2, MAXH>)(ing, gd, c, f, r);
 }
-static int32_t bucket_count_round(rb_graph* g, const Ingest& ing, int mode, float* counts, int64_t* fh, int64_t* rh, bool* fell_back);
 static int32_t count_launch(rb_ctx* ctx, const Ingest& ing_in, void* user) {
     CountUser* u = (CountUser*)user;
     const GraphDev gd = graph_view(u->g);
@@ -1092,28 +1089,22 @@ static int32_t count_launch(rb_ctx* ctx, const Ingest& ing_in, void* user) {
         if (u->rh) { rc = stage_get(ctx, s0 + 2, ing.n_pos * 8, &p); if (rc) return rc; dr = (int64_t*)p; }
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[par], 0));   // the previous D2H out of this staging set is done
     }
-    bool bucketed_done = false;
-    if (u->g->engine == RB_ENGINE_SLICED && dc) {
+    bool sliced_done = false;
+    if (dc && use_sliced(u->g, ing.n_pos)) {
         bool fell_back = false;
         const int32_t rc = sliced_count_round(u->g, ing, u->mode, dc, df, dr, &fell_back);
         if (rc) return rc;
-        bucketed_done = !fell_back;
-    }
-    if (u->g->engine == RB_ENGINE_BUCKETED && u->g->hd + u->g->hc <= 8 && dc) {
-        bool fell_back = false;
-        const int32_t rc = bucket_count_round(u->g, ing, u->mode, dc, df, dr, &fell_back);
-        if (rc) return rc;
-        bucketed_done = !fell_back;
+        sliced_done = !fell_back;
     }
     const int grid = (int)div_up(div_up(ing.n_pos, kChunk), kThreads);
     const int maxh = u->g->hmax;
-    if (!bucketed_done) PROF("k_graph_count");
-    if (bucketed_done) { /* counts are already in dc */ }
+    if (!sliced_done) PROF("k_graph_count");
+    if (sliced_done) { /* counts are already in dc */ }
     else if (maxh <= 2) launch_count_mode<2>(u->mode, grid, ctx->stream, ing, gd, dc, df, dr);
     else if (maxh <= 3) launch_count_mode<3>(u->mode, grid, ctx->stream, ing, gd, dc, df, dr);
     else if (maxh <= 4) launch_count_mode<4>(u->mode, grid, ctx->stream, ing, gd, dc, df, dr);
     else launch_count_mode<8>(u->mode, grid, ctx->stream, ing, gd, dc, df, dr);
-    if (!bucketed_done) LAUNCH_CHECK();
+    if (!sliced_done) LAUNCH_CHECK();
     if (!u->on_device) {   // D2H on the copy stream: overlaps the next launch's kernel
         CK(cudaEventRecord(ctx->ev_kernel[par], ctx->stream));
         CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kernel[par], 0));
@@ -1126,7 +1117,7 @@ static int32_t count_launch(rb_ctx* ctx, const Ingest& ing_in, void* user) {
 }
 static int32_t graph_count_reads(rb_graph* g, const ReadsArg& ra, float* counts, int64_t* fh, int64_t* rh, int64_t* n_out) {
     CountUser u{g, g->stranded ? RB_MODE_FWD : RB_MODE_CANON, counts, fh, g->stranded ? nullptr : rh, ra.on_device};
-    RoundSize rs(g);
+    RoundSize rs(g, !ra.on_device);
     return for_each_launch(g->ctx, ra, g->k, count_launch, &u, n_out);
 }
 extern "C" int32_t rb_graph_count_reads(rb_graph* g, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
@@ -1245,11 +1236,7 @@ extern "C" int32_t rb_synth_reads_dev(rb_ctx* ctx, uint64_t seed, uint64_t genom
 
 #include "rb_sliced_host.inl"
 
-#ifdef RB_EMU
-static void bucket_engine_free(rb_graph*) {}
-static int32_t bucket_insert_round(rb_graph*, const Ingest&, int, int, bool* fell_back) { *fell_back = true; return RB_OK; }
-static int32_t bucket_count_round(rb_graph*, const Ingest&, int, float*, int64_t*, int64_t*, bool* fell_back) { *fell_back = true; return RB_OK; }
-#else
+#ifndef RB_EMU
 // ---- hash-sharded graph (one rank's share; phases of rb_shard.cuh) ---------------------------------------------------------------
 struct rb_shard {
     rb_ctx* ctx;
@@ -1507,272 +1494,4 @@ extern "C" int32_t rb_shard_combine_lookup(rb_shard* sh, const uint8_t* reply_ho
     return RB_OK;
 }
 
-// ---- bucketed engine (rb_bucket.cuh): buffers, geometry, round drivers ------------------------------------------------------------
-struct BucketEngine {
-    int64_t n_max;                      // instances per round the buffers were sized for
-    int64_t T;                          // table slots (power of two) for n_max
-    unsigned long long* tab_keys; unsigned int* tab_counts;
-    Regions keys, raises;               // cursor-scattered
-    SortPlan probes, answers;           // counting-sorted
-    int64_t* tot;                       // scan scratch
-    uint8_t* usable;
-    unsigned int* done;                 // loose-barrier counters
-    int* overflow;
-    int n_dbg_slices, n_cbf_slices, max_regions;
-};
-static void bucket_engine_free(rb_graph* g) {
-    BucketEngine* e = g->be;
-    if (!e) return;
-    cudaStreamSynchronize(g->ctx->stream);
-    cudaFree(e->tab_keys); cudaFree(e->tab_counts);
-    cudaFree(e->keys.data); cudaFree(e->keys.count); cudaFree(e->raises.data); cudaFree(e->raises.count);
-    cudaFree(e->probes.hist); cudaFree(e->probes.cursor); cudaFree(e->probes.roff); cudaFree(e->probes.data);
-    cudaFree(e->answers.hist); cudaFree(e->answers.cursor); cudaFree(e->answers.roff); cudaFree(e->answers.data);
-    cudaFree(e->tot); cudaFree(e->usable); cudaFree(e->done); cudaFree(e->overflow);
-    delete e;
-    g->be = nullptr;
-}
-static int64_t pow2_at_least(int64_t v) { int64_t p = 1024; while (p < v) p <<= 1; return p; }
-static constexpr int kPersistMax = 8;   // persistent CTAs per SM (upper bound; the occupancy of each kernel may lower it)
-static constexpr int kWriterCursors = 16384;   // target number of (region, writer group) cursors of a counting sort
-
-static int32_t bucket_engine_get(rb_graph* g, int64_t n_round, BucketEngine** out) {
-    rb_ctx* ctx = g->ctx;
-    if (g->be && g->be->n_max >= n_round) { *out = g->be; return RB_OK; }
-    bucket_engine_free(g);
-    BucketEngine* e = new BucketEngine();
-    memset(e, 0, sizeof *e);
-    g->be = e;
-    const int64_t n_max = std::max<int64_t>(n_round, std::min<int64_t>(ctx->subbatch_kmers, 1LL << 28));
-    e->n_max = n_max;
-    e->T = pow2_at_least(2 * n_max);
-    const int nj = g->hd + g->hc;
-    e->n_dbg_slices = (int)div_up(g->dbg->size, 1LL << kSliceBitsLog2);
-    e->n_cbf_slices = (int)div_up(g->cbf->size, 1LL << kSliceBytesLog2);
-    const int n_key_ranges = (int)std::max<int64_t>(1, e->T >> kTableRangeLog2);
-    const int n_probe_regions = e->n_dbg_slices + e->n_cbf_slices;
-    const int n_id_ranges = (int)(div_up(std::max<int64_t>(e->T + 1, n_max), 1LL << kIdRangeLog2)) + 1;
-    e->max_regions = std::max(std::max(n_probe_regions, n_id_ranges), n_key_ranges) + 2;
-    if (n_probe_regions > 16384 || n_id_ranges > 49152 || n_key_ranges > kMaxCursorRegions || e->n_cbf_slices > kMaxCursorRegions)
-        return fail(ctx, RB_EINVAL, "bucketed engine: too many regions for this filter size / round size");
-    const int C = 64;   // upper bound of writer groups per region
-    auto alloc_regions = [&](Regions* r, int n, int64_t cap, int rec_bytes) -> cudaError_t {
-        r->n = n; r->cap = cap / kSub + 4096;   // capacity of each of the kSub sub-regions
-        cudaError_t er = cudaMalloc(&r->data, (size_t)n * kSub * (size_t)r->cap * rec_bytes);
-        if (er == cudaSuccess) er = cudaMalloc(&r->count, (size_t)kMaxCursorRegions * kSub * kCursorPad * 4);
-        return er;
-    };
-    auto alloc_plan = [&](SortPlan* p, int R, int64_t records) -> cudaError_t {
-        p->R = R; p->C = C;
-        cudaError_t er = cudaMalloc(&p->hist, (size_t)R * C * 4);
-        if (er == cudaSuccess) er = cudaMalloc(&p->cursor, (size_t)R * C * 4 * kCursorPad);
-        if (er == cudaSuccess) er = cudaMalloc(&p->roff, (size_t)(R + 2) * 8);
-        if (er == cudaSuccess) er = cudaMalloc(&p->data, (size_t)records * 8 + 64);
-        return er;
-    };
-    const int64_t cap_keys = (int64_t)((double)n_max / n_key_ranges * 1.3) + 8192;
-    const int64_t cap_raises = (int64_t)((double)n_max * g->hc / e->n_cbf_slices * 1.15) + 16384;
-    cudaError_t er = cudaMalloc(&e->tab_keys, (size_t)(e->T + 1) * 8);
-    if (er == cudaSuccess) er = cudaMalloc(&e->tab_counts, (size_t)(e->T + 1) * 4);
-    if (er == cudaSuccess) er = alloc_regions(&e->keys, n_key_ranges, cap_keys, 8);
-    if (er == cudaSuccess) er = alloc_regions(&e->raises, e->n_cbf_slices, cap_raises, 4);
-    if (er == cudaSuccess) er = alloc_plan(&e->probes, n_probe_regions, n_max * nj);
-    if (er == cudaSuccess) er = alloc_plan(&e->answers, n_id_ranges, n_max * nj);
-    if (er == cudaSuccess) er = cudaMalloc(&e->tot, (size_t)e->max_regions * 8);
-    if (er == cudaSuccess) er = cudaMalloc(&e->usable, (size_t)n_max + 64);
-    if (er == cudaSuccess) er = cudaMalloc(&e->done, (size_t)e->max_regions * 4);
-    if (er == cudaSuccess) er = cudaMalloc(&e->overflow, 4);
-    if (er == cudaSuccess) er = cudaMemsetAsync(e->overflow, 0, 4, ctx->stream);
-    if (er != cudaSuccess) { bucket_engine_free(g); return fail(ctx, RB_ENOMEM, std::string("bucketed engine buffers: ") + cudaGetErrorString(er)); }
-    *out = e;
-    return RB_OK;
-}
-static int32_t read_flag(rb_ctx* ctx, int* dev_flag, int* host) {
-    CK(cudaMemcpyAsync(host, dev_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (*host) CK(cudaMemsetAsync(dev_flag, 0, 4, ctx->stream));
-    return RB_OK;
-}
-// geometry of one round of n instances: table and ranges are sized by the round, not by the buffers, so small rounds stay cheap
-static BucketGeom round_geom(const rb_graph* g, const BucketEngine* e, int64_t n, int64_t* T_out) {
-    BucketGeom bg;
-    memset(&bg, 0, sizeof bg);
-    bg.dbg_fm = make_fm(g->dbg->size); bg.cbf_fm = make_fm(g->cbf->size);
-    bg.hd = g->hd; bg.hc = g->hc;
-    bg.n_dbg_slices = e->n_dbg_slices; bg.n_cbf_slices = e->n_cbf_slices;
-    const int64_t T = std::min<int64_t>(e->T, pow2_at_least(2 * n));
-    int lgT = 0; while ((1LL << lgT) < T) ++lgT;
-    const int lgR = std::max(0, lgT - kTableRangeLog2);
-    bg.n_key_ranges = 1 << lgR;
-    bg.key_range_shift = 64 - lgR;
-    bg.n_id_ranges = (int)div_up(T + 1, 1LL << kIdRangeLog2);
-    *T_out = T;
-    return bg;
-}
-template <typename K>
-static int32_t persistent_grid(rb_ctx* ctx, K kernel, int threads, size_t smem, int* grid) {
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
-    if (occ < 1) return fail(ctx, RB_ECUDA, "bucketed engine: kernel does not fit on an SM");
-    *grid = ctx->sm_count * std::min(occ, kPersistMax);
-    return RB_OK;
-}
-static int writer_groups(int R) { int c = kWriterCursors / std::max(R, 1); return std::max(1, std::min(64, c)); }
-static int32_t scan_plan(rb_ctx* ctx, BucketEngine* e, const SortPlan& p) {
-    RB_LAUNCH(p.R, 1024, 0, ctx->stream, kb_scan_regions)(p.hist, p.C, e->tot);
-    LAUNCH_CHECK();
-    RB_LAUNCH(1, 1024, 0, ctx->stream, kb_scan_totals)(e->tot, p.R, p.roff);
-    LAUNCH_CHECK();
-    RB_LAUNCH((int)div_up((int64_t)p.R * p.C, 256), 256, 0, ctx->stream, kb_spread_cursors)(p.hist, p.R * p.C, p.cursor);
-    LAUNCH_CHECK();
-    return RB_OK;
-}
-
-// B4 (+ its histogram pass): probes -> filters -> answers sorted by id range
-template <int SET>
-static int32_t bucket_apply(rb_graph* g, BucketEngine* e, const BucketGeom& bg, SortPlan in, int want_answers, SortPlan* answers_out) {
-    rb_ctx* ctx = g->ctx;
-    SortPlan out = e->answers;
-    out.R = bg.n_id_ranges;
-    const size_t sm = want_answers ? (size_t)out.R * 4 : 0;
-    int grid = 0;
-    int32_t rc = persistent_grid(ctx, kb_apply_probes<1, SET>, kThreads, sm, &grid);
-    if (rc) return rc;
-    if (sm > 48 * 1024) CK(cudaFuncSetAttribute(kb_apply_probes<0, SET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    out.C = writer_groups(out.R);
-    if (want_answers) {
-        CK(cudaMemsetAsync(out.hist, 0, (size_t)out.R * out.C * 4, ctx->stream));
-        RB_LAUNCH(grid, kThreads, sm, ctx->stream, kb_apply_probes<0, SET>)(in, bg, g->dbg->dev, g->cbf->dev, g->dbg->nbytes, g->cbf->nbytes, 1, out, e->done);
-        LAUNCH_CHECK();
-        rc = scan_plan(ctx, e, out);
-        if (rc) return rc;
-    }
-    CK(cudaMemsetAsync(e->done, 0, (size_t)(in.R + 2) * 4, ctx->stream));
-    RB_LAUNCH(grid, kThreads, sm, ctx->stream, kb_apply_probes<1, SET>)(in, bg, g->dbg->dev, g->cbf->dev, g->dbg->nbytes, g->cbf->nbytes, want_answers, out, e->done);
-    LAUNCH_CHECK();
-    *answers_out = out;
-    return RB_OK;
-}
-
-static int32_t bucket_insert_round(rb_graph* g, const Ingest& ing, int mode, int policy, bool* fell_back) {
-    rb_ctx* ctx = g->ctx;
-    BucketEngine* e = nullptr;
-    int32_t rc = bucket_engine_get(g, ing.n_pos, &e);
-    if (rc) return rc;
-    int64_t T;
-    const BucketGeom bg = round_geom(g, e, ing.n_pos, &T);
-    const HashMults hm = make_hm(g->k);
-    // B1 keys by range (cursor scatter)
-    Regions keys = e->keys; keys.n = bg.n_key_ranges;
-    CK(cudaMemsetAsync(keys.count, 0, (size_t)keys.n * kSub * kCursorPad * 4, ctx->stream));
-    const int grid_pos = (int)div_up(div_up(ing.n_pos, kChunk), kThreads);
-    const size_t sm_keys = (size_t)keys.n * 8;
-    if (mode == RB_MODE_FWD) RB_LAUNCH(grid_pos, kThreads, sm_keys, ctx->stream, kb_route_keys<0>)(ing, g->k, bg, keys, e->overflow);
-    else if (mode == RB_MODE_RC) RB_LAUNCH(grid_pos, kThreads, sm_keys, ctx->stream, kb_route_keys<1>)(ing, g->k, bg, keys, e->overflow);
-    else RB_LAUNCH(grid_pos, kThreads, sm_keys, ctx->stream, kb_route_keys<2>)(ing, g->k, bg, keys, e->overflow);
-    LAUNCH_CHECK();
-    int flag = 0;
-    rc = read_flag(ctx, e->overflow, &flag);
-    if (rc) return rc;
-    if (flag) { *fell_back = true; return RB_OK; }   // extreme key skew (one k-mer dominating the batch): nothing modified yet
-    // B2 aggregate
-    AggTable2 t;
-    t.keys = e->tab_keys; t.counts = e->tab_counts; t.n_slots = (uint64_t)T; t.zero_slot = (uint64_t)T;
-    int lgT = 0; while ((1LL << lgT) < T) ++lgT;
-    t.shift = 64 - lgT;
-    CK(cudaMemsetAsync(t.keys, 0, (size_t)(T + 1) * 8, ctx->stream));
-    CK(cudaMemsetAsync(t.counts, 0, (size_t)(T + 1) * 4, ctx->stream));
-    CK(cudaMemsetAsync(e->done, 0, (size_t)(keys.n + 2) * 4, ctx->stream));
-    int grid = 0;
-    rc = persistent_grid(ctx, kb_aggregate, kThreads, 0, &grid);
-    if (rc) return rc;
-    RB_LAUNCH(grid, kThreads, 0, ctx->stream, kb_aggregate)(keys, t, e->done);
-    LAUNCH_CHECK();
-    // B3 probes sorted by filter slice
-    SortPlan probes = e->probes;
-    probes.R = bg.n_dbg_slices + bg.n_cbf_slices;
-    const int with_cbf = policy != POLICY_DBG_ONLY;
-    const size_t sm_p = (size_t)probes.R * 4;
-    const bool small = g->hd + g->hc <= 6;
-    if (small) rc = persistent_grid(ctx, kb_emit_probes<6, 1>, kThreads, sm_p, &grid); else rc = persistent_grid(ctx, kb_emit_probes<8, 1>, kThreads, sm_p, &grid);
-    if (rc) return rc;
-    if (sm_p > 48 * 1024) {
-        CK(cudaFuncSetAttribute(kb_emit_probes<6, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_p));
-        CK(cudaFuncSetAttribute(kb_emit_probes<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_p));
-    }
-    probes.C = writer_groups(probes.R);
-    CK(cudaMemsetAsync(probes.hist, 0, (size_t)probes.R * probes.C * 4, ctx->stream));
-    if (small) RB_LAUNCH(grid, kThreads, sm_p, ctx->stream, kb_emit_probes<6, 0>)(t, hm, bg, with_cbf, probes);
-    else RB_LAUNCH(grid, kThreads, sm_p, ctx->stream, kb_emit_probes<8, 0>)(t, hm, bg, with_cbf, probes);
-    LAUNCH_CHECK();
-    rc = scan_plan(ctx, e, probes);
-    if (rc) return rc;
-    if (small) RB_LAUNCH(grid, kThreads, sm_p, ctx->stream, kb_emit_probes<6, 1>)(t, hm, bg, with_cbf, probes);
-    else RB_LAUNCH(grid, kThreads, sm_p, ctx->stream, kb_emit_probes<8, 1>)(t, hm, bg, with_cbf, probes);
-    LAUNCH_CHECK();
-    // B4
-    SortPlan answers;
-    if (policy != POLICY_COUNT_IF_PRESENT) rc = bucket_apply<1>(g, e, bg, probes, with_cbf, &answers);
-    else rc = bucket_apply<0>(g, e, bg, probes, with_cbf, &answers);
-    if (rc) return rc;
-    if (with_cbf) {
-        // B5 + B6
-        Regions raises = e->raises; raises.n = bg.n_cbf_slices;
-        CK(cudaMemsetAsync(raises.count, 0, (size_t)raises.n * kSub * kCursorPad * 4, ctx->stream));
-        const uint64_t seed = ctx->rng_seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(ctx->launches + 1);
-        const size_t sm_c = ((size_t)1 << kIdRangeLog2) * 8 + (size_t)raises.n * 8;
-        if (g->hc <= 4) {
-            CK(cudaFuncSetAttribute(kb_combine_insert<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
-            RB_LAUNCH(ctx->sm_count, kCombineThreads, sm_c, ctx->stream, kb_combine_insert<4>)(answers, t, hm, bg, policy, seed, raises, e->overflow);
-        } else {
-            CK(cudaFuncSetAttribute(kb_combine_insert<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
-            RB_LAUNCH(ctx->sm_count, kCombineThreads, sm_c, ctx->stream, kb_combine_insert<8>)(answers, t, hm, bg, policy, seed, raises, e->overflow);
-        }
-        LAUNCH_CHECK();
-        CK(cudaMemsetAsync(e->done, 0, (size_t)(raises.n + 2) * 4, ctx->stream));
-        rc = persistent_grid(ctx, kb_apply_raises, kThreads, 0, &grid);
-        if (rc) return rc;
-        RB_LAUNCH(grid, kThreads, 0, ctx->stream, kb_apply_raises)(raises, g->cbf->dev, g->cbf->nbytes, e->done);
-        LAUNCH_CHECK();
-    }
-    rc = read_flag(ctx, e->overflow, &flag);
-    if (rc) return rc;
-    if (flag) return fail(ctx, RB_ESTATE, "bucketed engine: a raise region overflowed after filters were modified (hash skew beyond the slack)");
-    claim_invalidate(ctx);   // bits were set without going through the claim table
-    return RB_OK;
-}
-
-static int32_t bucket_count_round(rb_graph* g, const Ingest& ing, int mode, float* counts, int64_t* fh, int64_t* rh, bool* fell_back) {
-    (void)fell_back;   // counting sort: exact sizes, nothing can overflow
-    rb_ctx* ctx = g->ctx;
-    BucketEngine* e = nullptr;
-    int32_t rc = bucket_engine_get(g, ing.n_pos, &e);
-    if (rc) return rc;
-    int64_t T;
-    BucketGeom bg = round_geom(g, e, ing.n_pos, &T);
-    bg.n_id_ranges = (int)div_up(ing.n_pos, 1LL << kIdRangeLog2);
-    const HashMults hm = make_hm(g->k);
-    SortPlan probes = e->probes;
-    probes.R = bg.n_dbg_slices + bg.n_cbf_slices;
-    const size_t sm_p = (size_t)probes.R * 4;
-    const bool small = g->hd + g->hc <= 6;
-    int grid = 0;
-#define RL(MODE, MAXJ, PASS) RB_LAUNCH(grid, kThreads, sm_p, ctx->stream, kb_route_lookup<MODE, MAXJ, PASS>)(ing, g->k, hm, bg, probes, e->usable, fh, rh)
-#define RLA(MODE, MAXJ) { rc = persistent_grid(ctx, kb_route_lookup<MODE, MAXJ, 1>, kThreads, sm_p, &grid); if (rc) return rc; \
-        if (sm_p > 48 * 1024) CK(cudaFuncSetAttribute(kb_route_lookup<MODE, MAXJ, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_p)); \
-        probes.C = writer_groups(probes.R); CK(cudaMemsetAsync(probes.hist, 0, (size_t)probes.R * probes.C * 4, ctx->stream)); RL(MODE, MAXJ, 0); LAUNCH_CHECK(); rc = scan_plan(ctx, e, probes); if (rc) return rc; RL(MODE, MAXJ, 1); LAUNCH_CHECK(); }
-    if (mode == RB_MODE_FWD) { if (small) RLA(0, 6) else RLA(0, 8) }
-    else { if (small) RLA(2, 6) else RLA(2, 8) }
-#undef RLA
-#undef RL
-    SortPlan answers;
-    rc = bucket_apply<0>(g, e, bg, probes, 1, &answers);
-    if (rc) return rc;
-    const size_t sm_c = ((size_t)1 << kIdRangeLog2) * 8;
-    CK(cudaFuncSetAttribute(kb_combine_lookup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
-    RB_LAUNCH(ctx->sm_count, kCombineThreads, sm_c, ctx->stream, kb_combine_lookup)(answers, ing.n_pos, g->hd, g->hc, e->usable, counts, ing.out_base);
-    LAUNCH_CHECK();
-    return RB_OK;
-}
 #endif  // !RB_EMU

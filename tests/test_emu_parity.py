@@ -46,31 +46,29 @@ def ctx(emu_lib):
 
 
 SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_RAISE_LOG2": "14", "RB_SLICED_SUBRANGE_LOG2": "6"}
-# "direct" is here to validate the emulation itself (that engine is verified on the GPU); "default" = production slice geometry
+# sliced-small: tiny slices / sub-ranges so that the small test filters span hundreds of regions (every test);
+# sliced-default: the production geometry; direct: validates the emulation itself (that engine is verified on the GPU)
 ONLY = {
-    "sliced-small-match": ("test_getkmers_with_invalid_nucleotides", "test_duplicates_inside_one_batch_are_linearised",
-                           "test_uniform_layout_graph_matches_oracle"),
-    "sliced-default": ("test_getkmers_with_invalid_nucleotides", "test_insert_policies_and_pair_filters",
-                       "test_uniform_layout_graph_matches_oracle"),
-    "direct": ("test_getkmers_with_invalid_nucleotides", "test_insert_policies_and_pair_filters"),
+    "sliced-default": ("test_getkmers_with_invalid_nucleotides", "test_insert_policies_and_pair_filters"),
+    "direct": ("test_getkmers_with_invalid_nucleotides",),
 }
+SKIP = {"sliced-small": ("test_kernels_are_race_free_under_tsan",)}   # sets its own environment; runs once (under "sliced-default")
+ONLY["sliced-default"] += ("test_kernels_are_race_free_under_tsan",)
 
 
-@pytest.fixture(autouse=True, params=["sliced-small-atoms", "sliced-small-bigtable", "sliced-default-atoms", "direct"])
+@pytest.fixture(autouse=True, params=["sliced-small", "sliced-default", "direct"])
 def engine(request):
-    """small: tiny slices / sub-ranges so that the small test filters span hundreds of regions; default: the production geometry."""
     name = request.node.originalname or request.node.name
-    if request.param in ONLY and name not in ONLY[request.param]:
+    if (request.param in ONLY and name not in ONLY[request.param]) or name in SKIP.get(request.param, ()):
         pytest.skip("not in the reduced matrix of this variant")
-    keys = ["RB_ENGINE", "RB_SLICED_RANK"] + list(SLICE_ENV)
+    keys = ["RB_ENGINE", "RB_SLICED_CHUNK"] + list(SLICE_ENV)
     old = {k: os.environ.get(k) for k in keys}
     os.environ["RB_ENGINE"] = request.param.split("-")[0]
     for k in keys[1:]:
         os.environ.pop(k, None)
+    os.environ["RB_SLICED_CHUNK"] = "8192"   # fewer work items = fewer emulated barriers; the logic is the same
     if "small" in request.param:
         os.environ.update(SLICE_ENV)
-    if "match" in request.param:
-        os.environ["RB_SLICED_RANK"] = "match"   # experimental ranking of the tile sort (warp match.any instead of shared-memory atomics)
     yield request.param
     for k, v in old.items():
         if v is None:
@@ -81,9 +79,7 @@ def engine(request):
 
 test_duplicates_inside_one_batch_are_linearised = G.test_duplicates_inside_one_batch_are_linearised
 test_getkmers_with_invalid_nucleotides = G.test_getkmers_with_invalid_nucleotides
-test_subbatching_and_claim_table_recycling_do_not_change_results = G.test_subbatching_and_claim_table_recycling_do_not_change_results
 test_insert_policies_and_pair_filters = G.test_insert_policies_and_pair_filters
-test_loaded_filter_dbgbf_exact_cbf_within_envelope = G.test_loaded_filter_dbgbf_exact_cbf_within_envelope
 
 
 @pytest.mark.parametrize("stranded,k,hd,hc,n_reads", [(False, 25, 3, 3, 800), (True, 25, 3, 3, 120), (True, 64, 1, 4, 120)])

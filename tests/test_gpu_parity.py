@@ -29,7 +29,7 @@ ENGINE_TESTS = {"test_graph_add_collision_free_is_bit_exact", "test_duplicates_i
 SMALL_SLICES = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_RAISE_LOG2": "14", "RB_SLICED_SUBRANGE_LOG2": "6"}
 
 
-@pytest.fixture(autouse=True, params=["direct", "bucketed", "sliced", "sliced-small"])
+@pytest.fixture(autouse=True, params=["direct", "sliced", "sliced-small"])
 def engine(request):
     """Engine-dependent tests run once per execution engine of the read-level calls (RB_ENGINE is read when a graph is created)."""
     name = request.node.originalname or request.node.name
