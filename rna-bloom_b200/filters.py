@@ -332,6 +332,12 @@ class BloomFilterDeBruijnGraph:
                     g.stranded = val == "true"
         return g
 
+    ENGINE_DIRECT, ENGINE_SLICED, ENGINE_AUTO = 0, 2, 3
+
+    def setEngine(self, engine):
+        """Execution engine of the read-level calls (include/rnabloom_gpu.h RB_ENGINE_*): same results, different HBM schedule."""
+        self.ctx.check(self.ctx.L.rb_graph_set_engine(self.h, int(engine)))
+
     def destroy(self):
         if self.h:
             self.ctx.check(self.ctx.L.rb_graph_destroy(self.h))
