@@ -16,7 +16,7 @@ import bench as single
 
 def run_sharded(args, rank, world, local_rank):
     import rnabloom_b200 as rb
-    from rnabloom_b200.sharded import GpuBackend, ShardedGraph
+    from rnabloom_b200.sharded import GpuBackend, ShardedGraph, SlicedBackend, SlicedShardedGraph
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     args.warmup = max(args.warmup, 3)
@@ -24,12 +24,19 @@ def run_sharded(args, rank, world, local_rank):
     kpr = single.KMERS_PER_READ
     dbg_bits, cbf_bytes = single.DBG_BITS * world, single.CBF_BYTES * world
     genome = args.genome * world
-    reads_per_round = 500_000                               # 63 M k-mers per rank per round
+    sliced = getattr(args, "sharded_engine", "sliced") == "sliced"
+    # sliced: rounds of 126 M k-mers per rank (the tile sort of the sliced engine routes; equal-split all-to-all of whole regions);
+    # legacy: the first-generation pipeline (per-record cursor scatter), 63 M k-mers per round
+    reads_per_round = min(args.reads_per_step, 1_000_000 if sliced else 500_000)
     rounds = max(1, args.reads_per_step // reads_per_round)
     n_reads = rounds * reads_per_round
     ctx = rb.Context(local_rank)
-    be = GpuBackend(ctx, world, rank, dbg_bits, cbf_bytes, single.HD, single.HC, K, False, reads_per_round * kpr)
-    sg = ShardedGraph(be, rank, world)
+    if sliced:
+        be = SlicedBackend(ctx, world, rank, dbg_bits, cbf_bytes, single.HD, single.HC, K, False, reads_per_round * kpr)
+        sg = SlicedShardedGraph(be, rank, world)
+    else:
+        be = GpuBackend(ctx, world, rank, dbg_bits, cbf_bytes, single.HD, single.HC, K, False, reads_per_round * kpr)
+        sg = ShardedGraph(be, rank, world)
     total_steps = args.warmup + args.steps
     n_batches = min(total_steps, max(1, 100_000_000 // n_reads))
     words = n_reads * STRIDE // 32
@@ -123,7 +130,8 @@ def run_sharded(args, rank, world, local_rank):
         cfg.update({"dbgbf_bits": dbg_bits, "cbf_bytes": cbf_bytes, "genome_len": genome,
                     "workload": "BASELINE.json configs[2] shape, weak-scaled: %d x %d reads/step, k=25, dbgbf %d GiB + cbf %d GiB sharded by index range over %d GPUs"
                                 % (world, n_reads, dbg_bits >> 33, cbf_bytes >> 30, world),
-                    "exchange": "NCCL all-to-all (torch.distributed), %.0f MB per rank per step" % (xbytes / 1e6)})
+                    "exchange": "NCCL all-to-all (torch.distributed), %.0f MB per rank per step" % (xbytes / 1e6),
+                    "sharded_engine": "sliced" if sliced else "legacy", "kmers_per_round_per_gpu": reads_per_round * kpr})
         line = {"metric": "k-mers/s (insert+lookup) at k=25, 2x150 bp reads", "value": value, "unit": "k-mers/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e,

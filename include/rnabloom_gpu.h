@@ -249,6 +249,39 @@ RB_API int32_t rb_shard_combine_lookup(rb_shard* sh, const uint8_t* reply_home, 
 RB_API int32_t rb_synth_reads_dev(rb_ctx* ctx, uint64_t seed, uint64_t genome_len, uint64_t first_read, int64_t n_reads,
                                   int32_t L, uint32_t err_ppm, int64_t stride_bases, uint64_t* packed_dev);
 
+/* ---- hash-sharded graph on the sliced engine (one process per GPU) ------------------------------------------
+ * The filters of BloomFilterDeBruijnGraph (graph/BloomFilterDeBruijnGraph.java:75-104) are split by index range over n_ranks GPUs
+ * (whole 64 MiB slices per rank; the concatenation of the ranks' shares is the array a single GPU or the JVM produces).  Every call
+ * below is one rank's phase between two equal-split all-to-all exchanges that the caller performs (torch.distributed / NCCL in
+ * rna-bloom_b200/sharded.py); buffers that travel belong to the caller and are laid out [destination or source rank][region][records]:
+ *   probes  uint32  n_ranks * geom[0] regions of geom[1] records      answers uint8, same shape
+ *   keys    uint64  n_ranks * geom[2] regions of geom[3] records
+ *   raises  uint32  n_ranks * geom[4] regions of geom[5] records      counts  uint32, one per region
+ * plus geom[10] records of slack behind every buffer.  A device flag (rb_sshard_overflow) reports regions that did not fit: the
+ * caller must all-reduce it and abandon the round before the first apply (nothing has been modified until then). */
+typedef struct rb_sshard rb_sshard;
+RB_API int32_t rb_sshard_create(rb_ctx* ctx, int32_t n_ranks, int32_t rank, int64_t dbgbf_bits, int64_t cbf_bytes, int32_t dbgbf_num_hash,
+                                int32_t cbf_num_hash, int32_t k, int32_t stranded, int64_t max_kmers_per_round, rb_sshard** out);
+RB_API int32_t rb_sshard_destroy(rb_sshard* sh);
+RB_API int32_t rb_sshard_geometry(rb_sshard* sh, int64_t* geom11);
+RB_API int32_t rb_sshard_filter(rb_sshard* sh, int32_t which, rb_filter** out);   /* this rank's share (borrowed) */
+RB_API int32_t rb_sshard_overflow(rb_sshard* sh, int32_t* flag);                   /* reads and clears the flag */
+/* lookup round (graph.getKmers :562-570): route -> [probes] -> apply(set_bits = 0) -> [answers back] -> combine */
+RB_API int32_t rb_sshard_route_lookup(rb_sshard* sh, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off,
+                                      const int32_t* read_len, int64_t n_reads, int32_t uniform_len, int64_t uniform_stride,
+                                      uint32_t* send_probes, uint32_t* send_cnt, int64_t* fhash, int64_t* rhash, int64_t* n_kmers_out);
+RB_API int32_t rb_sshard_apply(rb_sshard* sh, const uint32_t* recv_probes, const uint32_t* recv_cnt, uint8_t* recv_answers, int32_t set_bits);
+RB_API int32_t rb_sshard_combine_lookup(rb_sshard* sh, const uint8_t* home_answers, float* counts);
+/* insert round (graph.add :405-412 and its policies): route_keys -> [keys] -> dedup -> emit_probes -> [probes] -> apply(set_bits) ->
+ * [answers back] -> combine_insert -> [raises] -> apply_raises */
+RB_API int32_t rb_sshard_route_keys(rb_sshard* sh, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off,
+                                    const int32_t* read_len, int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, uint32_t flags,
+                                    unsigned long long* send_keys, uint32_t* send_cnt, int64_t* n_kmers_out);
+RB_API int32_t rb_sshard_dedup(rb_sshard* sh, const unsigned long long* recv_keys, const uint32_t* recv_cnt);
+RB_API int32_t rb_sshard_emit_probes(rb_sshard* sh, int32_t with_cbf, uint32_t* send_probes, uint32_t* send_cnt);
+RB_API int32_t rb_sshard_combine_insert(rb_sshard* sh, const uint8_t* home_answers, int32_t policy, uint32_t* send_raises, uint32_t* send_cnt);
+RB_API int32_t rb_sshard_apply_raises(rb_sshard* sh, const uint32_t* recv_raises, const uint32_t* recv_cnt);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 _SO = os.path.join(_HERE, "librnabloom_gpu.so")
 _SRC = [os.path.join(_HERE, "csrc", n) for n in ("rnabloom_gpu.cu", "rb_kernels.cuh", "rb_device.cuh", "rb_shard.cuh", "rb_sliced.cuh",
-                                                 "rb_sliced_host.inl")] + [
+                                                 "rb_sliced_host.inl", "rb_sshard_host.inl")] + [
     os.path.join(_ROOT, "include", "rnabloom_gpu.h")]
 
 RB_BLOOM, RB_COUNTING = 0, 1
@@ -149,6 +149,19 @@ def bind(path, allow_missing=False):
         "rb_shard_apply_lookup": (i32, [vp, vp, vp, vp]),
         "rb_shard_combine_lookup": (i32, [vp, vp, vp]),
         "rb_synth_reads_dev": (i32, [vp, u64, u64, u64, i64, i32, u32, i64, vp]),
+        "rb_sshard_create": (i32, [vp, i32, i32, i64, i64, i32, i32, i32, i32, i64, C.POINTER(vp)]),
+        "rb_sshard_destroy": (i32, [vp]),
+        "rb_sshard_geometry": (i32, [vp, C.POINTER(i64)]),
+        "rb_sshard_filter": (i32, [vp, i32, C.POINTER(vp)]),
+        "rb_sshard_overflow": (i32, [vp, C.POINTER(i32)]),
+        "rb_sshard_route_lookup": (i32, [vp] + reads + [vp, vp, vp, vp, C.POINTER(i64)]),
+        "rb_sshard_apply": (i32, [vp, vp, vp, vp, i32]),
+        "rb_sshard_combine_lookup": (i32, [vp, vp, vp]),
+        "rb_sshard_route_keys": (i32, [vp] + reads + [u32, vp, vp, C.POINTER(i64)]),
+        "rb_sshard_dedup": (i32, [vp, vp, vp]),
+        "rb_sshard_emit_probes": (i32, [vp, i32, vp, vp]),
+        "rb_sshard_combine_insert": (i32, [vp, vp, i32, vp, vp]),
+        "rb_sshard_apply_raises": (i32, [vp, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         if allow_missing and not hasattr(L, name):

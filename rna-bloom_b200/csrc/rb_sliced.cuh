@@ -47,6 +47,7 @@ struct SlArena {
     void* data;               // records; region b = [roff[b], roff[b+1])
     unsigned int* cursor;     // [B * cursor_stride] records appended to region b so far (may pass the capacity: overflow)
     const uint32_t* roff;     // [B + 1] region offsets in records (the whole arena holds < 2^32 records), or nullptr (see cap)
+    const uint32_t* rlo;      // [B] or nullptr: explicit region starts (regions of cap records in an order of the consumer's choosing)
     int B;
     int chunk;                // records per work item of the kernels that consume the arena region by region
     uint32_t cap;             // roff == nullptr: every region holds cap records, region b = [b * cap, (b + 1) * cap)
@@ -58,7 +59,24 @@ struct SlGeom {
     int dbg_log2, cbf_log2;   // slice sizes: 2^dbg_log2 bits, 2^cbf_log2 bytes
     int n_dbg, n_cbf;         // probe region = dbgbf slice, or n_dbg + cbf slice
     int raise_log2, n_raise;  // counter raises: record = slice-local byte index | value << raise_log2 (raise_log2 <= 25)
+    // hash-sharded graph (rb_sshard_*, one process per GPU): rank r owns dbgbf slices [r * shard_d, (r+1) * shard_d) and cbf slices
+    // [r * shard_c, ...); a producer's probe region = owner * (shard_d + shard_c) + (local dbgbf slice | shard_d + local cbf slice),
+    // raise region = owner * shard_r + local raise slice.  A consumer sees the regions it received ordered by local region first,
+    // source rank second: region / region_div = local region.  Single GPU: shard_d = 0, region_div = 1.
+    int shard_d, shard_c, shard_r, region_div;
 };
+__device__ __forceinline__ int sl_dbg_region(const SlGeom& sg, uint64_t gi) {
+    const int s = (int)(gi >> sg.dbg_log2);
+    return sg.shard_d ? (s / sg.shard_d) * (sg.shard_d + sg.shard_c) + s % sg.shard_d : s;
+}
+__device__ __forceinline__ int sl_cbf_region(const SlGeom& sg, uint64_t gi) {
+    const int s = (int)(gi >> sg.cbf_log2);
+    return sg.shard_d ? (s / sg.shard_c) * (sg.shard_d + sg.shard_c) + sg.shard_d + s % sg.shard_c : sg.n_dbg + s;
+}
+__device__ __forceinline__ int sl_raise_region(const SlGeom& sg, uint64_t gi) {
+    const int s = (int)(gi >> sg.raise_log2);
+    return sg.shard_d ? (s / sg.shard_r) * sg.shard_r + s % sg.shard_r : s;
+}
 __device__ __forceinline__ uint64_t sl_mixkey(uint64_t key) { return key * 0x9E3779B97F4A7C15ULL; }
 
 // Exclusive prefix sum of v[0..n) in shared memory, in place.  Every thread of the (256-thread) CTA calls it; returns the total.
@@ -105,8 +123,12 @@ __device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t* v, int n, uint3
 constexpr int kSlWarps = kSlThreads / 32;
 constexpr int kSlBucketsPerThread = kSlMaxRegions / kSlThreads;
 constexpr int kSlSpill = 8192;   // records of slack behind every arena (>= the largest tile)
-__device__ __forceinline__ uint32_t sl_region_lo(const SlArena& a, int region) { return a.roff ? __ldg(&a.roff[region]) : (uint32_t)region * a.cap; }
-__device__ __forceinline__ uint32_t sl_region_hi(const SlArena& a, int region) { return a.roff ? __ldg(&a.roff[region + 1]) : (uint32_t)(region + 1) * a.cap; }
+__device__ __forceinline__ uint32_t sl_region_lo(const SlArena& a, int region) {
+    return a.rlo ? __ldg(&a.rlo[region]) : a.roff ? __ldg(&a.roff[region]) : (uint32_t)region * a.cap;
+}
+__device__ __forceinline__ uint32_t sl_region_hi(const SlArena& a, int region) {
+    return a.rlo ? __ldg(&a.rlo[region]) + a.cap : a.roff ? __ldg(&a.roff[region + 1]) : (uint32_t)(region + 1) * a.cap;
+}
 template <typename REC, int E>
 struct TileSort {
     uint32_t *start, *delta, *scratch;   // [B] [B] [296]
@@ -177,12 +199,12 @@ __device__ __forceinline__ void sl_probes(const SlGeom& sg, const HashMults& hm,
     for (int j = 0; j < kSlMaxH; ++j) {
         if (j < sg.hd) {
             const uint64_t gi = fm_index(expand_hash(base, j, hm), sg.dbg_fm);
-            bkt[j] = (int)(gi >> sg.dbg_log2);
+            bkt[j] = sl_dbg_region(sg, gi);
             rec[j] = (uint32_t)(gi & ((1ULL << sg.dbg_log2) - 1));
         }
         if (with_cbf && j < sg.hc) {
             const uint64_t gi = fm_index(expand_hash(base, j, hm), sg.cbf_fm);
-            bkt[kSlMaxH + j] = sg.n_dbg + (int)(gi >> sg.cbf_log2);
+            bkt[kSlMaxH + j] = sl_cbf_region(sg, gi);
             rec[kSlMaxH + j] = (uint32_t)(gi & ((1ULL << sg.cbf_log2) - 1));
         }
     }
@@ -474,8 +496,9 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
     __shared__ int s_c;
     for (int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c); c < total; c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c)) {
         const SlWork w = sl_work_item(arena, pre, c);
-        const bool is_dbg = w.b < sg.n_dbg;
-        const int64_t word0 = is_dbg ? ((int64_t)w.b << (sg.dbg_log2 - 5)) : ((int64_t)(w.b - sg.n_dbg) << (sg.cbf_log2 - 2));
+        const int lr = w.b / sg.region_div;   // local region: dbgbf slices first, then cbf slices
+        const bool is_dbg = lr < sg.n_dbg;
+        const int64_t word0 = is_dbg ? ((int64_t)lr << (sg.dbg_log2 - 5)) : ((int64_t)(lr - sg.n_dbg) << (sg.cbf_log2 - 2));
         for (uint32_t i0 = threadIdx.x; i0 < w.n; i0 += kSlThreads * U) {
             uint32_t li[U], wd[U];
 #pragma unroll
@@ -584,7 +607,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_route_keys(const Ingest g, int 
 // ---- I2: second-level split: the keys of every range are tile-sorted again by their next hash bits ------------------------------------------
 // After it a sub-range holds ~1 Ki keys: small enough for a shared-memory hash table, so no global table is ever touched
 // (the L2-sliced global table this replaces ran at 4-9 G keys/s: one CAS + one add per key against ~24 B of table per key).
-__global__ void __launch_bounds__(kSlThreads) ks_split_keys(const SlArena in, int* chunk_prefix, int sub_bits, int sub_shift,
+__global__ void __launch_bounds__(kSlThreads) ks_split_keys(const SlArena in, int* chunk_prefix, int sub_bits, int sub_shift, int region_div,
                                                            const SlArena out, int* overflow) {
     RB_DYN_SMEM(unsigned char, sl_smem);
     TileSort<unsigned long long, kSlRoundKmers> ts;
@@ -609,14 +632,14 @@ __global__ void __launch_bounds__(kSlThreads) ks_split_keys(const SlArena in, in
                 bkt[i] = n_sub > 1 ? (int)((sl_mixkey(rec[i]) >> sub_shift) & (uint64_t)(n_sub - 1)) : 0;
             }
         }
-        ts.run(out, w.b * n_sub, bkt, rec, slot, overflow, nullptr);
+        ts.run(out, (w.b / region_div) * n_sub, bkt, rec, slot, overflow, nullptr);
     }
 }
 
 // ---- I3: one CTA per sub-range: (key -> multiplicity) in a shared-memory hash table, distinct keys appended to the dense arrays ----------------
 constexpr int kSlDedupSlots = 4096;   // 32 KiB of keys + 16 KiB of counters; a sub-range holds fewer keys than that (host: cap < slots)
 __global__ void __launch_bounds__(kSlThreads) ks_dedup(const SlArena in, int n_regions, int hash_shift, unsigned long long* __restrict__ dkey,
-                                                      unsigned int* __restrict__ dmult, unsigned int* n_distinct) {
+                                                      unsigned int* __restrict__ dmult, unsigned int* n_distinct, unsigned int dense_cap, int* overflow) {
     RB_DYN_SMEM(unsigned char, sl_smem);
     unsigned long long* tkeys = reinterpret_cast<unsigned long long*>(sl_smem);
     unsigned int* tcnt = reinterpret_cast<unsigned int*>(tkeys + kSlDedupSlots);
@@ -647,9 +670,13 @@ __global__ void __launch_bounds__(kSlThreads) ks_dedup(const SlArena in, int n_r
         __syncthreads();
         if (threadIdx.x == 0) out_base = atomicAdd(n_distinct, n_occ + (n_zero ? 1u : 0u));
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < T; i += kSlThreads)
-            if (tcnt[i]) { const uint32_t d = out_base + (tcnt[i] >> 16); dkey[d] = tkeys[i]; dmult[d] = tcnt[i] & 0xFFFFu; }
-        if (threadIdx.x == 0 && n_zero) { dkey[out_base + n_occ] = 0ULL; dmult[out_base + n_occ] = n_zero; }
+        if (out_base + n_occ + 1u > dense_cap) {   // more distinct keys than the dense arrays hold (sharded graph: key ranges out of balance)
+            if (threadIdx.x == 0) atomicOr(reinterpret_cast<unsigned int*>(overflow), 1u);
+        } else {
+            for (uint32_t i = threadIdx.x; i < T; i += kSlThreads)
+                if (tcnt[i]) { const uint32_t d = out_base + (tcnt[i] >> 16); dkey[d] = tkeys[i]; dmult[d] = tcnt[i] & 0xFFFFu; }
+            if (threadIdx.x == 0 && n_zero) { dkey[out_base + n_occ] = 0ULL; dmult[out_base + n_occ] = n_zero; }
+        }
         __syncthreads();
     }
 }
@@ -750,7 +777,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_combine_insert(const unsigned l
 #pragma unroll
                     for (int h2 = 0; h2 < kSlMaxH; ++h2) if (h2 < h && gi[h2] == gi[h]) dup = true;   // one raise per distinct counter
                     if (h < sg.hc && !dup && v[h] > v0[h]) {
-                        bkt[i * kSlMaxH + h] = (int)(gi[h] >> sg.raise_log2);
+                        bkt[i * kSlMaxH + h] = sl_raise_region(sg, gi[h]);
                         rec[i * kSlMaxH + h] = (uint32_t)(gi[h] & ((1ULL << sg.raise_log2) - 1)) | ((uint32_t)v[h] << sg.raise_log2);
                     }
                 }
@@ -771,13 +798,30 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_raises(const SlArena aren
     __shared__ int s_c;
     for (int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c); c < total; c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c)) {
         const SlWork w = sl_work_item(arena, pre, c);
-        const int64_t word0 = (int64_t)w.b << (sg.raise_log2 - 2);
+        const int64_t word0 = (int64_t)(w.b / sg.region_div) << (sg.raise_log2 - 2);
         for (uint32_t i = threadIdx.x; i < w.n; i += kSlThreads) {
             const uint32_t a = __ldcs(rec + w.first + i);
             const uint32_t li = a & ((1u << sg.raise_log2) - 1u);
             uint32_t* wp = cbf_words + word0 + (li >> 2);
             byte_raise(wp, (int)(li & 3) * 8, a >> sg.raise_log2, ld_cg(wp));
         }
+    }
+}
+
+// ---- exchange helpers of the hash-sharded graph ----------------------------------------------------------------------------------------------
+// padded cursors of a producer arena -> dense counts (what travels with the regions)
+__global__ void __launch_bounds__(kSlThreads) ks_pack_counts(const unsigned int* __restrict__ cursor, int stride, uint32_t cap, int n, uint32_t* __restrict__ dense) {
+    const int i = blockIdx.x * kSlThreads + threadIdx.x;
+    if (i < n) dense[i] = min(cursor[(size_t)i * stride], cap);
+}
+// received counts [source rank][local region] -> consumer order [local region][source rank], and the region starts in that order
+__global__ void __launch_bounds__(kSlThreads) ks_order_counts(const uint32_t* __restrict__ recv, int n_ranks, int per_rank, uint32_t cap,
+                                                             unsigned int* __restrict__ cursor, uint32_t* __restrict__ rlo) {
+    const int i = blockIdx.x * kSlThreads + threadIdx.x;   // consumer region
+    if (i < n_ranks * per_rank) {
+        const int lr = i / n_ranks, src = i % n_ranks;
+        cursor[i] = recv[src * per_rank + lr];
+        rlo[i] = (uint32_t)(src * per_rank + lr) * cap;
     }
 }
 

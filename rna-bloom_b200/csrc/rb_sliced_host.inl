@@ -86,6 +86,7 @@ static int32_t sliced_engine_get(rb_graph* g, int64_t n_round, SlicedEngine** ou
         else if (sg.cbf_log2 < 31) ++sg.cbf_log2;
         else break;
     }
+    sg.shard_d = sg.shard_c = sg.shard_r = 0; sg.region_div = 1;
     sg.raise_log2 = std::min(sg.cbf_log2, env_int("RB_SLICE_RAISE_LOG2", 25, 2, 25));
     const int64_t n_raise = div_up(g->cbf->size, 1LL << sg.raise_log2);
     sg.n_raise = (int)std::min<int64_t>(n_raise, 1 << 20);
@@ -175,7 +176,7 @@ static int32_t sl_chunk_prefix(rb_ctx* ctx, SlicedEngine* e, const SlArena& a) {
 }
 static SlArena sl_arena(void* data, unsigned int* cursor, const uint32_t* roff, int B, int chunk) {
     SlArena a;
-    a.data = data; a.cursor = cursor; a.roff = roff; a.B = B; a.chunk = chunk; a.cap = 0; a.cursor_stride = kSlPad;
+    a.data = data; a.cursor = cursor; a.roff = roff; a.B = B; a.chunk = chunk; a.cap = 0; a.cursor_stride = kSlPad; a.rlo = nullptr;
     return a;
 }
 static SlArena sl_probe_arena(SlicedEngine* e) { return sl_arena(e->probe_data, e->probe_cursor, e->probe_roff, e->probe_B, sl_chunk()); }
@@ -284,7 +285,7 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     const size_t sm_split = TileSort<unsigned long long, kSlRoundKmers>::smem_bytes(n_sub) + (size_t)(keys.B + 1) * 4;
     rc = sl_stream_grid(ctx, ks_split_keys, sm_split, &grid);
     if (rc) return rc;
-    SL_LAUNCH("ks_split_keys", ks_split_keys, grid, sm_split, keys, e->chunk_prefix, e->sub_bits, 64 - (64 - e->key_shift) - e->sub_bits, subs, e->overflow);
+    SL_LAUNCH("ks_split_keys", ks_split_keys, grid, sm_split, keys, e->chunk_prefix, e->sub_bits, 64 - (64 - e->key_shift) - e->sub_bits, 1, subs, e->overflow);
     int flag = 0;
     rc = sl_read_flag(ctx, e->overflow, &flag);
     if (rc) return rc;
@@ -294,7 +295,8 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     const size_t sm_dedup = (size_t)kSlDedupSlots * 12;
     rc = sl_stream_grid(ctx, ks_dedup, sm_dedup, &grid);
     if (rc) return rc;
-    SL_LAUNCH("ks_dedup", ks_dedup, std::min(grid, n_sub_regions), sm_dedup, subs, n_sub_regions, (64 - e->key_shift) + e->sub_bits, e->dkey, e->dmult, e->n_distinct);
+    SL_LAUNCH("ks_dedup", ks_dedup, std::min(grid, n_sub_regions), sm_dedup, subs, n_sub_regions, (64 - e->key_shift) + e->sub_bits, e->dkey, e->dmult, e->n_distinct,
+              (unsigned int)std::min<int64_t>(e->n_max + 8, 0xFFFFFFFFLL), e->overflow);
     // I4 probes by filter slice
     const SlArena probes = sl_probe_arena(e);
     CK(cudaMemsetAsync(probes.cursor, 0, (size_t)probes.B * kSlPad * 4, ctx->stream));

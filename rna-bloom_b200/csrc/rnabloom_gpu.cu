@@ -1235,6 +1235,7 @@ extern "C" int32_t rb_synth_reads_dev(rb_ctx* ctx, uint64_t seed, uint64_t genom
 }
 
 #include "rb_sliced_host.inl"
+#include "rb_sshard_host.inl"
 
 #ifndef RB_EMU
 // ---- hash-sharded graph (one rank's share; phases of rb_shard.cuh) ---------------------------------------------------------------

@@ -716,3 +716,51 @@ def test_sharded_pipeline_single_rank_matches_oracle(orc, stranded, hd, hc):
     assert (counts.cpu().numpy() == want).mean() > 0.999 and (fh.cpu().numpy() == wantf).all()
     dr.free()
     be.close(), og.close(), ctx.close()
+
+
+@pytest.mark.parametrize("stranded,hd,hc", [(False, 3, 3), (True, 2, 3)])
+def test_sharded_sliced_graph_single_rank_matches_oracle(orc, stranded, hd, hc):
+    """rb_sshard_* phase by phase on one GPU (world = 1 makes every exchange the identity); tests/test_sharded_sliced_gloo.py runs the same
+    orchestrator at world sizes 2 and 4 over the host emulation of the kernels."""
+    import torch
+    from rnabloom_b200.sharded import SlicedBackend, SlicedShardedGraph
+    from parity_util import all_bases, assert_cbf_close
+    ctx = rb.Context(0)
+    k, dbg_bits, cbf_bytes = 25, (1 << 30) + 77, (1 << 28) + 13
+    reads = orc.synth_reads(61, 90000, 0, 1200, 150, 6000)  # 2x coverage: counters stay in the exact MiniFloat range
+    seqs = [bytes(r).decode() for r in reads]
+    seqs[3] = seqs[3][:70] + "N" + seqs[3][71:]
+    be = SlicedBackend(ctx, 1, 0, dbg_bits, cbf_bytes, hd, hc, k, stranded, 80000)
+    sg = SlicedShardedGraph(be, 0, 1)
+    og = OracleGraph(orc, dbg_bits, cbf_bytes, 64, hd, hc, 1, k, stranded, False)
+    for r in range(3):
+        chunk = seqs[r * 400:(r + 1) * 400]
+        dr = DevReads(ctx, rb.pack_reads(chunk))
+        assert sg.add_round(dr.args, 0) == sum(max(0, len(s) - k + 1) for s in chunk)
+        dr.free()
+        for s in chunk:
+            og.add_read(s)
+    dr = DevReads(ctx, rb.pack_reads(seqs[:400] + seqs[:200]))   # every k-mer present now, with multiplicities inside one round
+    sg.add_round(dr.args, 0)
+    dr.free()
+    for s in seqs[:400] + seqs[:200]:
+        og.add_read(s)
+    dr = DevReads(ctx, rb.pack_reads(seqs[100:300]))
+    sg.add_round(dr.args, rb.ADD_COUNT_IF_PRESENT)
+    sg.add_round(dr.args, rb.DBG_ONLY)
+    sg.check_overflow()
+    for s in seqs[100:300]:
+        og.add_read(s, flags=F_ADD_COUNT_IF_PRESENT)
+    assert (sg.gather_filter(rb.RB_DBGBF, (dbg_bits + 7) // 8) == og.dbgbf()).all()
+    bases = all_bases(orc, seqs, k, [MODE_FWD if stranded else MODE_CANON])
+    assert_cbf_close(sg.gather_filter(rb.RB_CBF, cbf_bytes), og.cbf(), bases, k, hc, cbf_bytes)
+    n_inst = sum(max(0, len(s) - k + 1) for s in seqs[100:300])
+    counts = torch.zeros(n_inst, dtype=torch.float32, device="cuda")
+    fh = torch.zeros(n_inst, dtype=torch.int64, device="cuda")
+    sg.count_round(dr.args, counts, fh)
+    ctx.sync()
+    want = np.concatenate([og.count_seq(s)[0] for s in seqs[100:300]])
+    wantf = np.concatenate([og.count_seq(s)[1] for s in seqs[100:300]])
+    assert (counts.cpu().numpy() == want).mean() > 0.999 and (fh.cpu().numpy() == wantf).all()
+    dr.free()
+    be.close(), og.close(), ctx.close()

@@ -1,0 +1,110 @@
+"""The hash-sharded graph on the sliced engine (rb_sshard_*, rna-bloom_b200/sharded.py SlicedShardedGraph) at world sizes 2 and 4 on
+CPU: gloo all-to-all exchanges between processes that each run the *real* kernel sources through the host emulation of
+tests/emu (test infrastructure, see tests/test_emu_parity.py).  Checks that probes reach the owner of their filter slice, answers come
+back to the right k-mer, duplicates of a k-mer that live on different ranks are aggregated at the key's home rank, and the
+concatenated shares equal the sequential oracle's single arrays."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, HERE):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+K, HD, HC = 25, 3, 2
+DBG_BITS, CBF_BYTES = 3_000_017, 1_000_003
+SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_RAISE_LOG2": "14", "RB_SLICED_SUBRANGE_LOG2": "6",
+             "RB_SLICED_CHUNK": "8192"}
+
+
+def _reads():
+    from oracle.binding import Oracle
+    orc = Oracle()
+    reads = [bytes(r).decode() for r in orc.synth_reads(13, 9000, 0, 240, 100, 8000)]   # ~2.7x coverage: counters stay exact
+    reads[5] = reads[5][:40] + "N" + reads[5][41:]
+    reads[17] = "ACGT"          # shorter than k
+    return reads
+
+
+def _worker(rank, world, port, stranded, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), **SLICE_ENV)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import rnabloom_b200 as rb
+        from rnabloom_b200 import binding as B
+        from rnabloom_b200.sharded import SlicedBackend, SlicedShardedGraph
+        from test_emu_parity import EMU_SO
+        B._lib = B.bind(EMU_SO, allow_missing=True)   # the emulated kernels: "device memory" is host memory
+        reads = _reads()
+        mine = reads[rank::world]
+        ctx = rb.Context(0)
+        be = SlicedBackend(ctx, world, rank, DBG_BITS, CBF_BYTES, HD, HC, K, stranded, 8000, device=torch.device("cpu"))
+        sg = SlicedShardedGraph(be, rank, world)
+        per_round = 40
+        n_rounds = -(-max(len(reads[r::world]) for r in range(world)) // per_round)
+        total = 0
+        keep = []
+        for r in range(n_rounds):
+            pr = rb.pack_reads(mine[r * per_round:(r + 1) * per_round])
+            keep.append(pr)
+            total += sg.add_round(pr.args(), 0)
+        sg.check_overflow()
+        for chunk, flags in ((mine[:30], 2), (mine[30:60], 4)):   # addCountIfPresent, addDbgOnly
+            pr = rb.pack_reads(chunk)
+            keep.append(pr)
+            sg.add_round(pr.args(), flags)
+        q = rb.pack_reads(mine[:per_round])
+        n_inst = sum(max(0, len(s) - K + 1) for s in mine[:per_round])
+        counts = torch.zeros(n_inst + 8, dtype=torch.float32)
+        fh = torch.zeros(n_inst + 8, dtype=torch.int64)
+        assert sg.count_round(q.args(), counts, fh) == n_inst
+        sg.check_overflow()
+        dbg = sg.gather_filter(0, (DBG_BITS + 7) // 8)
+        cbf = sg.gather_filter(1, CBF_BYTES)
+        if rank == 0:
+            np.save(os.path.join(out, "dbg.npy"), dbg), np.save(os.path.join(out, "cbf.npy"), cbf)
+        np.save(os.path.join(out, "counts%d.npy" % rank), counts.numpy()[:n_inst])
+        np.save(os.path.join(out, "fh%d.npy" % rank), fh.numpy()[:n_inst])
+        assert sg.exchanged_bytes > 0
+        be.close(), ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,stranded", [(2, False), (2, True), (4, False)])
+def test_sharded_sliced_graph_matches_oracle(tmp_path, orc, world, stranded):
+    from oracle.binding import MODE_CANON, MODE_FWD, OracleGraph
+    from parity_util import all_bases, assert_cbf_close
+    from test_emu_parity import build_emu
+    build_emu()
+    port = 31500 + os.getpid() % 2000 + world * 3 + (1 if stranded else 0)
+    mp.spawn(_worker, args=(world, port, stranded, str(tmp_path)), nprocs=world, join=True)
+    reads = _reads()
+    og = OracleGraph(orc, DBG_BITS, CBF_BYTES, 64, HD, HC, 1, K, stranded, False)
+    for s in reads:
+        og.add_read(s)
+    for r in range(world):
+        mine = reads[r::world]
+        for s in mine[:30]:
+            og.add_read(s, flags=2)
+        for s in mine[30:60]:
+            og.add_read(s, flags=4)
+    assert og.cbf().max() <= 16, "fixture reached the probabilistic MiniFloat range"
+    assert (np.load(tmp_path / "dbg.npy") == og.dbgbf()).all()
+    bases = all_bases(orc, reads, K, [MODE_FWD if stranded else MODE_CANON])
+    assert_cbf_close(np.load(tmp_path / "cbf.npy"), og.cbf(), bases, K, HC, CBF_BYTES, max_frac=0.05)
+    for r in range(world):
+        mine = reads[r::world][:40]
+        want = np.concatenate([og.count_seq(s)[0] for s in mine if len(s) >= K])
+        wantf = np.concatenate([og.count_seq(s)[1] for s in mine if len(s) >= K])
+        got = np.load(tmp_path / ("counts%d.npy" % r))
+        assert (np.load(tmp_path / ("fh%d.npy" % r)) == wantf).all()
+        # counts are read from the gathered state, which may differ from the oracle only on shared counters
+        assert len(got) == len(want) and (got == want).mean() > 0.99
