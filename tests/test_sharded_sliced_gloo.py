@@ -1,4 +1,4 @@
-"""The hash-sharded graph on the sliced engine (rb_sshard_*, rna-bloom_b200/sharded.py SlicedShardedGraph) at world sizes 2 and 4 on
+"""The hash-sharded graph on the sliced engine (rb_sshard_*, rna-bloom_b200/sharded.py SlicedShardedGraph) at world sizes 2, 4 and 8 on
 CPU: gloo all-to-all exchanges between processes that each run the *real* kernel sources through the host emulation of
 tests/emu (test infrastructure, see tests/test_emu_parity.py).  Checks that probes reach the owner of their filter slice, answers come
 back to the right k-mer, duplicates of a k-mer that live on different ranks are aggregated at the key's home rank, and the
@@ -78,7 +78,7 @@ def _worker(rank, world, port, stranded, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,stranded", [(2, False), (2, True), (4, False)])
+@pytest.mark.parametrize("world,stranded", [(2, False), (2, True), (4, False), (8, False)])
 def test_sharded_sliced_graph_matches_oracle(tmp_path, orc, world, stranded):
     from oracle.binding import MODE_CANON, MODE_FWD, OracleGraph
     from parity_util import all_bases, assert_cbf_close
