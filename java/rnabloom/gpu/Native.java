@@ -23,6 +23,8 @@ public final class Native {
                                           int cbfNumHash, int pkbfNumHash, int k, boolean stranded, boolean useReadPairedKmers);
     public static native void graphDestroy(long graph);
     public static native void graphSetDistances(long ctx, long graph, int readPairedKmersDistance, int fragPairedKmersDistance);
+    /** RB_ENGINE_DIRECT = 0, RB_ENGINE_SLICED = 2, RB_ENGINE_AUTO = 3 (default): same results, different HBM schedule. */
+    public static native void graphSetEngine(long ctx, long graph, int engine);
     public static native void graphInitFpkbf(long ctx, long graph, long numBits, int numHash);
     public static native long graphAddReadsAscii(long ctx, long graph, ByteBuffer bases, ByteBuffer quals, ByteBuffer offsets,
                                                  long numReads, int minBaseQual, int flags);

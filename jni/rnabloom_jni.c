@@ -49,6 +49,9 @@ JNIEXPORT void JNICALL Java_rnabloom_gpu_Native_graphSetDistances(JNIEnv* env, j
     (void)cls;
     check(env, (rb_ctx*)(intptr_t)ctx, rb_graph_set_distances((rb_graph*)(intptr_t)g, dRead, dFrag));
 }
+JNIEXPORT void JNICALL Java_rnabloom_gpu_Native_graphSetEngine(JNIEnv* env, jclass cls, jlong ctx, jlong g, jint engine) {
+    check(env, (rb_ctx*)(intptr_t)ctx, rb_graph_set_engine((rb_graph*)(intptr_t)g, engine));
+}
 JNIEXPORT void JNICALL Java_rnabloom_gpu_Native_graphInitFpkbf(JNIEnv* env, jclass cls, jlong ctx, jlong g, jlong bits, jint numHash) {
     (void)cls;
     check(env, (rb_ctx*)(intptr_t)ctx, rb_graph_init_fpkbf((rb_graph*)(intptr_t)g, bits, numHash));
