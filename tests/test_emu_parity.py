@@ -102,8 +102,11 @@ def test_kernels_are_race_free_under_tsan(tmp_path):
     exe = os.path.join(EMU_DIR, "race_check")
     srcs = [os.path.join(CSRC, n) for n in os.listdir(CSRC)] + [os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(EMU_DIR, "race_check.cpp")]
     if not os.path.exists(exe) or any(os.path.getmtime(s) > os.path.getmtime(exe) for s in srcs):
-        subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-DRB_EMU", "-I", EMU_DIR, "-pthread",
-                               os.path.join(EMU_DIR, "race_check.cpp"), "-o", exe])
+        b = subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-DRB_EMU", "-I", EMU_DIR, "-pthread",
+                            os.path.join(EMU_DIR, "race_check.cpp"), "-o", exe], capture_output=True, text=True)
+        if b.returncode != 0 and "tsan" in b.stderr.lower():
+            pytest.skip("this toolchain has no ThreadSanitizer runtime")
+        assert b.returncode == 0, b.stderr[-3000:]
     env = dict(os.environ, **SLICE_ENV)
     env["RB_ENGINE"] = "sliced"
     p = subprocess.run([exe, "120"], env=env, capture_output=True, text=True, timeout=900)
