@@ -83,8 +83,10 @@ extern "C" int32_t rb_sshard_create(rb_ctx* ctx, int32_t n_ranks, int32_t rank, 
     const int64_t local_d = std::max<int64_t>(0, std::min<int64_t>(share_d, dbg_bits - share_d * rank));
     const int64_t local_c = std::max<int64_t>(0, std::min<int64_t>(share_c, cbf_bytes - share_c * rank));
     // rounds: keys
-    const int64_t n_max = sl_pow2_at_least(max_kmers);
-    sh->n_max = n_max; sh->n_dense = n_max + n_max / 4 + 4096;
+    // capacities follow the caller's round size (no power-of-two rounding: every record of slack travels through the exchanges); the
+    // distinct keys a home rank can see exceed its share of the instances only by the imbalance of the hash ranges (~1e-4 at 10^8 keys)
+    const int64_t n_max = div_up(std::max<int64_t>(max_kmers, 1024), 4096) * 4096;
+    sh->n_max = n_max; sh->n_dense = n_max + n_max / 32 + 4096;
     const int lgSub = env_int("RB_SLICED_SUBRANGE_LOG2", 10, 4, 11);
     int lgW = 0; while ((1 << lgW) < W) ++lgW;
     int lgS = 0; while (((n_max * W) >> lgSub) > (1LL << lgS)) ++lgS;       // sub-ranges over all ranks
