@@ -88,6 +88,7 @@ static int32_t sliced_engine_get(rb_graph* g, int64_t n_round, SlicedEngine** ou
     }
     sg.shard_d = sg.shard_c = sg.shard_r = 0; sg.region_div = 1;
     sg.raise_log2 = std::min(sg.cbf_log2, env_int("RB_SLICE_RAISE_LOG2", 25, 2, 25));
+    while (div_up(g->cbf->size, 1LL << sg.raise_log2) > kSlMaxRegions && sg.raise_log2 < std::min(sg.cbf_log2, 25)) ++sg.raise_log2;
     const int64_t n_raise = div_up(g->cbf->size, 1LL << sg.raise_log2);
     sg.n_raise = (int)std::min<int64_t>(n_raise, 1 << 20);
     if (g->hd > kSlMaxH || g->hc > kSlMaxH || sg.n_dbg + sg.n_cbf > kSlMaxRegions || n_raise > kSlMaxRegions) { e->unsupported = true; return RB_OK; }

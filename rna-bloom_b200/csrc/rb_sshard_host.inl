@@ -70,6 +70,7 @@ extern "C" int32_t rb_sshard_create(rb_ctx* ctx, int32_t n_ranks, int32_t rank, 
     }
     sg.shard_d = (int)div_up(tot_d, W); sg.shard_c = (int)div_up(tot_c, W);
     sg.raise_log2 = std::min(sg.cbf_log2, env_int("RB_SLICE_RAISE_LOG2", 25, 2, 25));
+    while (((int64_t)sg.shard_c << (sg.cbf_log2 - sg.raise_log2)) * W > kSlMaxRegions && sg.raise_log2 < std::min(sg.cbf_log2, 25)) ++sg.raise_log2;
     sg.shard_r = sg.shard_c << (sg.cbf_log2 - sg.raise_log2);
     sg.region_div = 1;
     sh->R = sg.shard_d + sg.shard_c; sh->SR = sg.shard_r;

@@ -82,6 +82,13 @@ test_getkmers_with_invalid_nucleotides = G.test_getkmers_with_invalid_nucleotide
 test_insert_policies_and_pair_filters = G.test_insert_policies_and_pair_filters
 
 
+def test_skewed_batch_is_redone_by_the_direct_engine(ctx, orc, monkeypatch):
+    monkeypatch.setattr(G, "SKEW_COPIES", 2500)   # enough for the 2179-key sub-ranges of the small test geometry, cheaper to emulate
+    G.test_skewed_batch_is_redone_by_the_direct_engine(ctx, orc)
+
+
+
+
 @pytest.mark.parametrize("stranded,k,hd,hc,n_reads", [(False, 25, 3, 3, 800), (True, 25, 3, 3, 120), (True, 64, 1, 4, 120)])
 def test_graph_add_collision_free_is_bit_exact(ctx, orc, stranded, k, hd, hc, n_reads):
     G.test_graph_add_collision_free_is_bit_exact(ctx, orc, stranded, k, hd, hc, n_reads)

@@ -23,7 +23,7 @@ ENGINE_TESTS = {"test_graph_add_collision_free_is_bit_exact", "test_duplicates_i
                 "test_loaded_filter_dbgbf_exact_cbf_within_envelope", "test_insert_policies_and_pair_filters", "test_pairs_existing_only",
                 "test_fastq_ascii_ingest_matches_regex_segmentation", "test_getkmers_with_invalid_nucleotides",
                 "test_subbatching_and_claim_table_recycling_do_not_change_results", "test_full_size_filters_properties",
-                "test_upload_download_save_load_roundtrip", "test_uniform_layout_graph_matches_oracle"}
+                "test_upload_download_save_load_roundtrip", "test_uniform_layout_graph_matches_oracle", "test_skewed_batch_is_redone_by_the_direct_engine"}
 # "sliced-small": slices of 16 KiB / 32 KiB so that the small test filters span hundreds of regions (the default 64 MiB slices
 # would put every test filter into one or two regions and leave the multi-region paths to the full-size test alone)
 SMALL_SLICES = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_RAISE_LOG2": "14", "RB_SLICED_SUBRANGE_LOG2": "6"}
@@ -509,6 +509,32 @@ def test_uniform_layout_graph_matches_oracle(ctx, orc, L, stride, k, n_reads, st
             assert (counts[off:off + mlen] == c).all()
         off += mlen
     assert off == len(counts)
+    g.destroy(), og.close()
+
+
+SKEW_COPIES = 4000   # more copies of a k-mer in one round than a key sub-range holds (3369 with the production geometry)
+
+
+def test_skewed_batch_is_redone_by_the_direct_engine(ctx, orc):
+    """One read repeated thousands of times: every k-mer has thousands of copies inside one round, which no fixed-capacity region of
+    the sliced engine holds.  The overflow is detected before any filter is modified and the round is redone by the direct engine:
+    same filters, same answers (addDbgOnly keeps the counters out of the probabilistic MiniFloat range)."""
+    rng = np.random.default_rng(53)
+    base = rand_reads(rng, 3, 150, 150)
+    seqs = base * SKEW_COPIES + rand_reads(rng, 200, 150, 150)
+    g, og = make_graphs(ctx, orc, (1 << 27) + 9, (1 << 24) + 3, 64, 3, 3, 1, 25, False, False)
+    for s_ in base + seqs[-200:]:
+        og.add_read(s_, flags=F_DBG_ONLY)
+    n = g.addReads(rb.pack_reads(seqs), flags=rb.DBG_ONLY)
+    assert n == len(seqs) * 126
+    assert_same_state(g, og)
+    for s_ in seqs[-200:]:                      # an ordinary batch afterwards goes through the sliced engine again
+        og.add_read(s_)
+    g.addReads(rb.pack_reads(seqs[-200:]))
+    assert_same_state(g, og)
+    counts, fh, _ = g.getKmers(rb.pack_reads(seqs[:6000:7] + seqs[-50:]))   # skewed look-up batch as well
+    want = np.concatenate([og.count_seq(s_)[0] for s_ in seqs[:6000:7] + seqs[-50:]])
+    assert (counts == want).all()
     g.destroy(), og.close()
 
 
