@@ -2,17 +2,19 @@
 //
 // Why (profiles/r01_notes.md): an isolated probe costs one 128 B DRAM line request whatever it uses of it, and the part serves
 // ~47.5 G of those per second -- 23 % of the 32 B-per-probe roofline.  The same probe against an L2-resident slice of the filter
-// costs one L1TEX wavefront (~280 G/s), and streaming runs at ~6 TB/s.  So every probe is first written, as a 4-byte slice-local
-// index, into the region of the filter slice it falls into; then the regions are visited in order by all CTAs together, so
-// that only a few slices are live in L2 at any time; the answer to a probe is one byte at the probe's own position in a
-// parallel array, and the k-mer picks its answers up through the positions it remembered (a gather, no second sort).
-// The logical bit / byte arrays are untouched: this is a schedule, not a blocked Bloom filter.
+// costs one L1TEX wavefront (measured ~1.4 cycles per lane, ~200 G/s), and streaming runs at ~6 TB/s.  So every probe is first
+// written, as a 4-byte slice-local index, into the region of the filter slice it falls into; then the regions are consumed in
+// order by all CTAs together (work handed out by one in-order counter), so that only one or two slices are live in L2 at any
+// time; the answer to a probe is one byte at the probe's own position in a parallel array, and a tile picks the answers of
+// its k-mers up through the run positions its sort recorded (coalesced copies of whole runs into shared memory, no second sort).
+// The logical bit / byte arrays are untouched: this is a schedule, not a blocked Bloom filter.  The same kernels run the
+// hash-sharded multi-GPU graph (rb_sshard_host.inl): there the tile sort's regions are (owner rank, slice) and travel by all-to-all.
 //
 //   lookup (graph.getKmers / getCount, graph/BloomFilterDeBruijnGraph.java:562-570)
 //     S1 ks_route_lookup    hash every k-mer, tile-sort its h_d + h_c probes by filter slice, remember the positions
 //        (_u: uniform read layout -- the k-mers of a CTA are hashed through XOR-prefix arrays of rotated base seeds)
 //     S2 ks_apply_probes<0> slice by slice: read bit / counter, write the answer byte
-//     S3 ks_combine_lookup  gather the answers: count = MiniFloat(min counter) + 1 if all bits are set
+//     S3 ks_combine_lookup  stage the tile's answer runs in shared memory: count = MiniFloat(min counter) + 1 if all bits are set
 //   insert (graph.add, :405-412; addCountIfPresent :424-428; addDbgOnly :430-436)
 //     I1 ks_route_keys      tile-sort the base hashes by key range (top bits of a multiplicative hash of the key)
 //     I2 ks_split_keys      tile-sort every range again by the next hash bits: sub-ranges of ~1 Ki keys
