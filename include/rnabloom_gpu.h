@@ -249,6 +249,15 @@ RB_API int32_t rb_shard_combine_lookup(rb_shard* sh, const uint8_t* reply_home, 
 RB_API int32_t rb_synth_reads_dev(rb_ctx* ctx, uint64_t seed, uint64_t genome_len, uint64_t first_read, int64_t n_reads,
                                   int32_t L, uint32_t err_ppm, int64_t stride_bases, uint64_t* packed_dev);
 
+/* ---- neighbour query -------------------------------------------------------------------------------------
+ * Kmer.getSuccessors / getPredecessors (graph/Kmer.java:213-253) and CanonicalKmer's (graph/CanonicalKmer.java:232-271), batched: for
+ * every k-mer i (forward hash, reverse hash for an unstranded graph, 2-bit codes A0 C1 G2 T3 of its first and last base) the
+ * graph.getCount of its four candidate successors then its four candidate predecessors (candidate order A, C, G, T), and their
+ * hashes: counts / nbr_fhash / nbr_rhash are [n][2][4]; the caller keeps the candidates with count >= minKmerCov (the hash arrays
+ * are nullable; rhash and nbr_rhash are ignored for a stranded graph). */
+RB_API int32_t rb_graph_neighbor_counts(rb_graph* g, const int64_t* fhash, const int64_t* rhash, const uint8_t* first_base,
+                                        const uint8_t* last_base, int64_t n, float* counts, int64_t* nbr_fhash, int64_t* nbr_rhash);
+
 /* ---- hash-sharded graph on the sliced engine (one process per GPU) ------------------------------------------
  * The filters of BloomFilterDeBruijnGraph (graph/BloomFilterDeBruijnGraph.java:75-104) are split by index range over n_ranks GPUs
  * (whole 64 MiB slices per rank; the concatenation of the ranks' shares is the array a single GPU or the JVM produces).  Every call

@@ -92,6 +92,7 @@ def load():
         "orc_graph_add_dbg_only": (None, [vp, vp]),
         "orc_graph_contains": (i32, [vp, vp]),
         "orc_graph_get_count": (f32, [vp, vp]),
+        "orc_graph_neighbors": (None, [vp, i64, i64, i32, i32, vp, vp, vp]),
         "orc_segment": (i32, [vp, vp, i32, i32, i32, vp, vp]),
         "orc_graph_add_segment": (i64, [vp, vp, i32, i32, i32]),
         "orc_graph_add_read": (i64, [vp, vp, vp, i32, i32, i32]),
@@ -222,6 +223,14 @@ class OracleGraph:
         rh = np.zeros(n, dtype=np.int64)
         self.lib.orc_graph_count_seq(self.g, b.ctypes.data, start, end, counts.ctypes.data, fh.ctypes.data, rh.ctypes.data)
         return counts, fh, rh
+
+    def neighbors(self, fh, rh, char_out, successors):
+        """counts, forward and reverse hashes of the 4 candidate neighbours (A, C, G, T) of one k-mer (graph/Kmer.java:213-253)."""
+        c = np.zeros(4, dtype=np.float32)
+        f = np.zeros(4, dtype=np.int64)
+        r = np.zeros(4, dtype=np.int64)
+        self.lib.orc_graph_neighbors(self.g, int(fh), int(rh), int(char_out), int(successors), c.ctypes.data, f.ctypes.data, r.ctypes.data)
+        return c, f, r
 
     def dbgbf(self):
         return self.o.bf_array(self.lib.orc_graph_dbgbf(self.g))

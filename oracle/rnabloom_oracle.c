@@ -421,6 +421,43 @@ ORC_API float orc_graph_get_count(const orc_graph* g, const int64_t* hv) {   /* 
 }
 
 /* ------------------------------------------------------------------------------------------
+ * f1  neighbours of a k-mer      graph/Kmer.java:213-253 (getPredecessors / getSuccessors), graph/CanonicalKmer.java:232-271;
+ *     hash side: bloom/hash/SuccessorsNTHashIterator.java:52-63, PredecessorsNTHashIterator.java:54-65,
+ *     CanonicalSuccessorsNTHashIterator.java:56-72, CanonicalPredecessorsNTHashIterator.java:56-72
+ * For the four candidate bases A,C,G,T (SeqUtils.NUCLEOTIDES_BYTES): the neighbour's forward / reverse hash and graph.getCount of it.
+ * char_out = bytes[0] for successors, bytes[k-1] for predecessors.  The caller applies "count >= minKmerCov".
+ * ---------------------------------------------------------------------------------------- */
+ORC_API void orc_graph_neighbors(const orc_graph* g, int64_t fh, int64_t rh, int char_out, int successors, float* counts4, int64_t* f4,
+                                 int64_t* r4) {
+    static const uint8_t nt[4] = {'A', 'C', 'G', 'T'};
+    init_tables();
+    const int k = g->k, km1 = (k - 1) % 64;
+    const uint8_t co = (uint8_t)char_out;
+    uint64_t tf, tr = 0;
+    if (successors) {
+        tf = rotl64((uint64_t)fh, 1) ^ ms_tab[co][k % 64];
+        if (!g->stranded) tr = rotr64((uint64_t)rh, 1) ^ ms_tab[co & CP_OFF][63];
+    } else {
+        tf = rotr64((uint64_t)fh, 1) ^ ms_tab[co][63];
+        if (!g->stranded) tr = rotl64((uint64_t)rh, 1) ^ ms_tab[co & CP_OFF][k % 64];
+    }
+    for (int i = 0; i < 4; ++i) {
+        const uint8_t ci = nt[i];
+        const uint64_t f = tf ^ (successors ? ms_tab[ci][0] : ms_tab[ci][km1]);
+        uint64_t r = 0, b = f;
+        if (!g->stranded) {
+            r = tr ^ (successors ? ms_tab[ci & CP_OFF][km1] : ms_tab[ci & CP_OFF][0]);
+            b = ((int64_t)r < (int64_t)f) ? r : f;           /* Math.min on long */
+        }
+        int64_t hv[ORC_MAX_HASH];
+        orc_ntm64((int64_t)b, hv, k, g->hmax);
+        counts4[i] = orc_graph_get_count(g, hv);
+        if (f4) f4[i] = (int64_t)f;
+        if (r4) r4[i] = (int64_t)r;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * a20 segmentation              RNABloom.java:567-595 (FASTQ), :677-716 (FASTA); util/SeqUtils.java:1430-1438
  *   qualPattern = [chars >= '!'+minQual .. '~']{k,}   seqPattern = [ACGTUacgtu]{k,}
  *   -> maximal runs of length >= k; the sequence pattern is searched inside every quality run.

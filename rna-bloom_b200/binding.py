@@ -130,6 +130,7 @@ def bind(path, allow_missing=False):
         "rb_graph_count_hashes": (i32, [vp, vp, i64, vp]),
         "rb_graph_add_pair_hashes": (i32, [vp, i32, vp, i64]),
         "rb_graph_lookup_pair_hashes": (i32, [vp, i32, vp, i64, vp]),
+        "rb_graph_neighbor_counts": (i32, [vp, vp, vp, vp, vp, i64, vp, vp, vp]),
         "rb_graph_save": (i32, [vp, cp]),
         "rb_graph_load": (i32, [vp, cp, i32, i32, C.POINTER(vp)]),
         "rb_shard_create": (i32, [vp, i32, i32, i64, i64, i32, i32, i32, i32, i64, C.POINTER(vp)]),

@@ -399,6 +399,53 @@ __global__ void __launch_bounds__(kThreads) k_hash_op(const int64_t* __restrict_
     }
 }
 
+// ---- f1 neighbours of a k-mer: Kmer.getSuccessors / getPredecessors (graph/Kmer.java:213-253), CanonicalKmer (:232-271) ----------------
+// Hash side: bloom/hash/SuccessorsNTHashIterator.java:52-63, PredecessorsNTHashIterator.java:54-65 and the Canonical twins (:56-72).
+// One thread per (k-mer, direction): the hashes of the 4 candidate neighbours (A,C,G,T) and graph.getCount of each, all
+// 4 * (h_d + h_c) probes in flight before any is consumed.  out code = first base (successors) / last base (predecessors).
+template <int MAXH>
+__global__ void __launch_bounds__(kThreads) k_neighbors(const int64_t* __restrict__ fhash, const int64_t* __restrict__ rhash,
+                                                       const uint8_t* __restrict__ first_code, const uint8_t* __restrict__ last_code, int64_t n,
+                                                       const GraphDev gd, int canonical, float* __restrict__ counts, int64_t* __restrict__ nf,
+                                                       int64_t* __restrict__ nr) {
+    const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (t >= 2 * n) return;
+    const int64_t q = t >> 1;
+    const bool succ = (t & 1) == 0;   // outputs: [q][0] successors, [q][1] predecessors, 4 entries each
+    const int k = gd.k;
+    const int out = (int)(succ ? first_code[q] : last_code[q]) & 3;
+    const uint64_t f = (uint64_t)fhash[q], r = canonical ? (uint64_t)rhash[q] : 0ULL;
+    const uint64_t tf = succ ? (rotl1(f) ^ rotl64(seed_of_code(out), k)) : (rotr1(f) ^ rotl64(seed_of_code(out), 63));
+    const uint64_t tr = succ ? (rotr1(r) ^ rotl64(seed_of_code(3 - out), 63)) : (rotl1(r) ^ rotl64(seed_of_code(3 - out), k));
+    uint64_t base[4], fn[4], rn[4];
+    uint32_t wd[4][MAXH], wc[4][MAXH];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        fn[c] = tf ^ (succ ? seed_of_code(c) : rotl64(seed_of_code(c), k - 1));
+        rn[c] = canonical ? (tr ^ (succ ? rotl64(seed_of_code(3 - c), k - 1) : seed_of_code(3 - c))) : 0ULL;
+        base[c] = (canonical && (int64_t)rn[c] < (int64_t)fn[c]) ? rn[c] : fn[c];
+#pragma unroll
+        for (int h = 0; h < MAXH; ++h) {
+            if (h < gd.dbg.num_hash) wd[c][h] = ld_cg(&gd.dbg.words[fm_index(expand_hash(base[c], h, gd.hm), gd.dbg.fm) >> 5]);
+            if (h < gd.cbf.num_hash) wc[c][h] = ld_cg(&gd.cbf.words[fm_index(expand_hash(base[c], h, gd.hm), gd.cbf.fm) >> 2]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        bool all = true;
+        int mn = 127;
+#pragma unroll
+        for (int h = 0; h < MAXH; ++h) {
+            if (h < gd.dbg.num_hash) { const uint64_t idx = fm_index(expand_hash(base[c], h, gd.hm), gd.dbg.fm); all = all && ((wd[c][h] >> (idx & 31)) & 1u); }
+            if (h < gd.cbf.num_hash) { const uint64_t idx = fm_index(expand_hash(base[c], h, gd.hm), gd.cbf.fm); const int v = byte_of(wc[c][h], (int)(idx & 3) * 8); mn = v < mn ? v : mn; }
+        }
+        const int64_t o = t * 4 + c;
+        counts[o] = all ? minifloat_to_float(mn) + 1.f : 0.f;   // graph.getCount :562-570
+        if (nf) nf[o] = (int64_t)fn[c];
+        if (nr) nr[o] = (int64_t)rn[c];
+    }
+}
+
 // ---- a8 getIndex exposed on its own (bloom/BloomFilter.java:108-111) -------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) k_index(const int64_t* __restrict__ hash, int64_t n, const FastMod fm, int64_t* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;

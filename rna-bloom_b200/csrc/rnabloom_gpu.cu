@@ -1166,6 +1166,44 @@ extern "C" int32_t rb_graph_lookup_pair_hashes(rb_graph* g, int32_t which, const
     return rb_filter_lookup_hashes(f, pair_hash, n, out);
 }
 
+// ---- f1: batched neighbour query (graph/Kmer.java:213-253, graph/CanonicalKmer.java:232-271) ------------------------------------------------
+// out arrays: [n][2][4] -- per k-mer the 4 successors (A,C,G,T) then the 4 predecessors
+extern "C" int32_t rb_graph_neighbor_counts(rb_graph* g, const int64_t* fhash, const int64_t* rhash, const uint8_t* first_base, const uint8_t* last_base,
+                                            int64_t n, float* counts, int64_t* nbr_fhash, int64_t* nbr_rhash) {
+    if (!g || n < 0 || (n > 0 && (!fhash || !first_base || !last_base || !counts))) return RB_EINVAL;
+    rb_ctx* ctx = g->ctx;
+    LOCK(ctx);
+    const int canonical = g->stranded ? 0 : 1;
+    if (canonical && n > 0 && !rhash) return fail(ctx, RB_EINVAL, "neighbours of canonical k-mers need the reverse-strand hashes");
+    const GraphDev gd = graph_view(g);
+    const int64_t step = std::max<int64_t>(1024, ctx->subbatch_kmers / 8);
+    for (int64_t i0 = 0; i0 < n; i0 += step) {
+        const int64_t m = std::min(step, n - i0);
+        void *df, *dr = nullptr, *d1, *d2, *dc, *dnf = nullptr, *dnr = nullptr;
+        int32_t rc = stage_get(ctx, 0, m * 8, &df); if (rc) return rc;
+        if (canonical) { rc = stage_get(ctx, 1, m * 8, &dr); if (rc) return rc; }
+        rc = stage_get(ctx, 2, m, &d1); if (rc) return rc;
+        rc = stage_get(ctx, 3, m, &d2); if (rc) return rc;
+        rc = stage_get(ctx, 5, m * 32, &dc); if (rc) return rc;
+        if (nbr_fhash) { rc = stage_get(ctx, 6, m * 64, &dnf); if (rc) return rc; }
+        if (nbr_rhash && canonical) { rc = stage_get(ctx, 7, m * 64, &dnr); if (rc) return rc; }
+        CK(cudaMemcpyAsync(df, fhash + i0, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (canonical) CK(cudaMemcpyAsync(dr, rhash + i0, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d1, first_base + i0, (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d2, last_base + i0, (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        const int grid = (int)div_up(2 * m, kThreads);
+        PROF("k_neighbors");
+        if (g->hmax <= 3) RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_neighbors<3>)((const int64_t*)df, (const int64_t*)dr, (const uint8_t*)d1, (const uint8_t*)d2, m, gd, canonical, (float*)dc, (int64_t*)dnf, (int64_t*)dnr);
+        else RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_neighbors<8>)((const int64_t*)df, (const int64_t*)dr, (const uint8_t*)d1, (const uint8_t*)d2, m, gd, canonical, (float*)dc, (int64_t*)dnf, (int64_t*)dnr);
+        LAUNCH_CHECK();
+        CK(cudaMemcpyAsync(counts + i0 * 8, dc, (size_t)m * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        if (dnf) CK(cudaMemcpyAsync(nbr_fhash + i0 * 8, dnf, (size_t)m * 64, cudaMemcpyDeviceToHost, ctx->stream));
+        if (dnr) CK(cudaMemcpyAsync(nbr_rhash + i0 * 8, dnr, (size_t)m * 64, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return RB_OK;
+}
+
 // ---- persistence (graph :297-339, file ctor :121-189) -------------------------------------------------------------------------
 extern "C" int32_t rb_graph_save(rb_graph* g, const char* path) {
     if (!g || !path) return RB_EINVAL;

@@ -430,6 +430,21 @@ class BloomFilterDeBruijnGraph:
     def contains(self, hashVals):
         return self.getDbgbf().lookup(hashVals)
 
+    def getNeighborCounts(self, fHashVals, rHashVals, firstBases, lastBases, with_hashes=True):
+        """Batched Kmer.getSuccessors / getPredecessors (graph/Kmer.java:213-253, CanonicalKmer.java:232-271): for every k-mer the
+        graph.getCount of its 4 candidate successors and 4 candidate predecessors (A, C, G, T) -> counts[n, 2, 4] (and the candidates'
+        forward / reverse hashes).  Bases are 2-bit codes A0 C1 G2 T3 of the k-mer's first and last base."""
+        f = _hashes(fHashVals)
+        r = None if rHashVals is None else _hashes(rHashVals)
+        b0 = np.ascontiguousarray(firstBases, dtype=np.uint8)
+        b1 = np.ascontiguousarray(lastBases, dtype=np.uint8)
+        n = f.size
+        counts = np.zeros((n, 2, 4), dtype=np.float32)
+        nf = np.zeros((n, 2, 4), dtype=np.int64) if with_hashes else None
+        nr = np.zeros((n, 2, 4), dtype=np.int64) if with_hashes and not self.stranded else None
+        self.ctx.check(self.ctx.L.rb_graph_neighbor_counts(self.h, _ptr(f), _ptr(r), _ptr(b0), _ptr(b1), n, _ptr(counts), _ptr(nf), _ptr(nr)))
+        return counts, nf, nr
+
     def addReadSingleKmerPair(self, pairHashVals):
         a = _hashes(pairHashVals)
         self.ctx.check(self.ctx.L.rb_graph_add_pair_hashes(self.h, B.RB_RPKBF, _ptr(a), a.size))

@@ -50,9 +50,9 @@ SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_
 # sliced-default: the production geometry; direct: validates the emulation itself (that engine is verified on the GPU)
 ONLY = {
     "sliced-default": ("test_getkmers_with_invalid_nucleotides", "test_insert_policies_and_pair_filters"),
-    "direct": ("test_getkmers_with_invalid_nucleotides",),
+    "direct": ("test_getkmers_with_invalid_nucleotides", "test_neighbor_counts_match_oracle"),
 }
-SKIP = {"sliced-small": ("test_kernels_are_race_free_under_tsan",)}   # sets its own environment; runs once (under "sliced-default")
+SKIP = {"sliced-small": ("test_kernels_are_race_free_under_tsan", "test_neighbor_counts_match_oracle")}   # sets its own environment; runs once (under "sliced-default")
 ONLY["sliced-default"] += ("test_kernels_are_race_free_under_tsan",)
 
 
@@ -80,6 +80,7 @@ def engine(request):
 test_duplicates_inside_one_batch_are_linearised = G.test_duplicates_inside_one_batch_are_linearised
 test_getkmers_with_invalid_nucleotides = G.test_getkmers_with_invalid_nucleotides
 test_insert_policies_and_pair_filters = G.test_insert_policies_and_pair_filters
+test_neighbor_counts_match_oracle = G.test_neighbor_counts_match_oracle
 
 
 def test_skewed_batch_is_redone_by_the_direct_engine(ctx, orc, monkeypatch):

@@ -538,6 +538,45 @@ def test_skewed_batch_is_redone_by_the_direct_engine(ctx, orc):
     g.destroy(), og.close()
 
 
+# ---- f1: neighbour queries ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("stranded,k", [(False, 25), (True, 25), (False, 64), (True, 17)])
+def test_neighbor_counts_match_oracle(ctx, orc, stranded, k):
+    """Kmer.getSuccessors / getPredecessors batched (graph/Kmer.java:213-253, CanonicalKmer.java:232-271): counts and hashes of the 8
+    candidate neighbours of every k-mer of some reads, against the oracle's restatement of the four *NTHashIterator classes; and the
+    internal consistency the iterators imply: the true next k-mer of a read is among the successors with the read's own hashes."""
+    reads = orc.synth_reads(71 + k, 30000, 0, 300, 150, 6000)
+    seqs = [bytes(r_) for r_ in reads]
+    g, og = make_graphs(ctx, orc, (1 << 27) + 5, (1 << 24) + 3, 64, 3, 3, 1, k, stranded, False)
+    for s_ in seqs:
+        og.add_read(s_)
+    g.addReads(rb.pack_reads(seqs))
+    assert_same_state(g, og, bases=all_bases(orc, seqs, k, [MODE_FWD] if stranded else [MODE_CANON]))
+    code = np.zeros(256, dtype=np.uint8)
+    code[list(b"ACGT")] = [0, 1, 2, 3]
+    fh, rh, first, last, chars = [], [], [], [], []
+    for s_ in seqs[:40]:
+        f, r, _ = orc.kmer_hashes(s_, k, MODE_CANON)
+        a = np.frombuffer(s_, dtype=np.uint8)
+        n = len(f)
+        fh.append(f), rh.append(r), first.append(code[a[:n]]), last.append(code[a[k - 1:k - 1 + n]])
+        chars.append(np.stack([a[:n], a[k - 1:k - 1 + n]], axis=1))
+    fh, rh, first, last, chars = np.concatenate(fh), np.concatenate(rh), np.concatenate(first), np.concatenate(last), np.concatenate(chars)
+    counts, nf, nr = g.getNeighborCounts(fh, None if stranded else rh, first, last)
+    for i in range(0, len(fh), 7):
+        for d, succ in ((0, 1), (1, 0)):
+            c, f, r = og.neighbors(fh[i], rh[i], chars[i][0] if succ else chars[i][1], succ)
+            assert (counts[i, d] == c).all() and (nf[i, d] == f).all()
+            if not stranded:
+                assert (nr[i, d] == r).all()
+    # the k-mer that follows in the read is the successor with base = that k-mer's last base, and it was inserted: count >= 1
+    n0 = 150 - k + 1
+    nxt = last[1:n0]
+    assert (nf[np.arange(n0 - 1), 0, nxt] == fh[1:n0]).all() and (counts[np.arange(n0 - 1), 0, nxt] >= 1).all()
+    prv = first[:n0 - 1]
+    assert (nf[np.arange(1, n0), 1, prv] == fh[:n0 - 1]).all() and (counts[np.arange(1, n0), 1, prv] >= 1).all()
+    g.destroy(), og.close()
+
+
 # ---- per-hash operators ---------------------------------------------------------------------------------------------------
 def test_filter_hash_operators(ctx, orc):
     rng = np.random.default_rng(43)
