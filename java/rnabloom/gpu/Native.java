@@ -34,6 +34,9 @@ public final class Native {
                                               ByteBuffer readLen, long numReads, ByteBuffer counts, ByteBuffer fHash, ByteBuffer rHash);
     public static native void graphAddHashes(long ctx, long graph, ByteBuffer hashes, long n, int flags);
     public static native void graphCountHashes(long ctx, long graph, ByteBuffer hashes, long n, ByteBuffer counts);
+    /** Batched Kmer.getSuccessors/getPredecessors: counts[n][2][4] (successors A,C,G,T then predecessors), optional neighbour hashes. */
+    public static native void graphNeighborCounts(long ctx, long graph, ByteBuffer fHashVals, ByteBuffer rHashVals, ByteBuffer firstBases,
+                                                  ByteBuffer lastBases, long n, ByteBuffer counts, ByteBuffer nbrFHashVals, ByteBuffer nbrRHashVals);
     public static native void graphAddPairHashes(long ctx, long graph, int which, ByteBuffer hashes, long n);
     public static native void graphLookupPairHashes(long ctx, long graph, int which, ByteBuffer hashes, long n, ByteBuffer out);
     public static native long graphFilter(long ctx, long graph, int which);

@@ -95,6 +95,14 @@ JNIEXPORT void JNICALL Java_rnabloom_gpu_Native_graphCountHashes(JNIEnv* env, jc
     (void)cls;
     check(env, (rb_ctx*)(intptr_t)ctx, rb_graph_count_hashes((rb_graph*)(intptr_t)g, (const int64_t*)addr(env, hashes), n, (float*)addr(env, counts)));
 }
+/* Kmer.getSuccessors / getPredecessors for a batch of k-mers (graph/Kmer.java:213-253): counts (and hashes) of the 4 + 4 candidates */
+JNIEXPORT void JNICALL Java_rnabloom_gpu_Native_graphNeighborCounts(JNIEnv* env, jclass cls, jlong ctx, jlong g, jobject fhash, jobject rhash, jobject firstBases,
+                                                                    jobject lastBases, jlong n, jobject counts, jobject nbrF, jobject nbrR) {
+    (void)cls;
+    check(env, (rb_ctx*)(intptr_t)ctx,
+          rb_graph_neighbor_counts((rb_graph*)(intptr_t)g, (const int64_t*)addr(env, fhash), (const int64_t*)addr(env, rhash), (const uint8_t*)addr(env, firstBases),
+                                   (const uint8_t*)addr(env, lastBases), n, (float*)addr(env, counts), (int64_t*)addr(env, nbrF), (int64_t*)addr(env, nbrR)));
+}
 JNIEXPORT void JNICALL Java_rnabloom_gpu_Native_graphAddPairHashes(JNIEnv* env, jclass cls, jlong ctx, jlong g, jint which, jobject hashes, jlong n) {
     (void)cls;
     check(env, (rb_ctx*)(intptr_t)ctx, rb_graph_add_pair_hashes((rb_graph*)(intptr_t)g, which, (const int64_t*)addr(env, hashes), n));
