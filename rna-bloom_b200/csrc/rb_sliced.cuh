@@ -54,6 +54,10 @@ struct SlArena {
     int chunk;                // records per work item of the kernels that consume the arena region by region
     uint32_t cap;             // roff == nullptr: every region holds cap records, region b = [b * cap, (b + 1) * cap)
     int cursor_stride;        // cursor of region b = cursor[b * cursor_stride] (kSlPad when the regions are few and hot)
+    // TileSort<.., SPILL = true> only: records that do not fit their region go here instead of failing the round (nullptr: fail)
+    void* spill_data;
+    unsigned int* spill_cursor;
+    uint32_t spill_cap;
 };
 struct SlGeom {
     FastMod dbg_fm, cbf_fm;   // global index arithmetic (reference semantics)
@@ -131,19 +135,22 @@ __device__ __forceinline__ uint32_t sl_region_lo(const SlArena& a, int region) {
 __device__ __forceinline__ uint32_t sl_region_hi(const SlArena& a, int region) {
     return a.rlo ? __ldg(&a.rlo[region]) + a.cap : a.roff ? __ldg(&a.roff[region + 1]) : (uint32_t)(region + 1) * a.cap;
 }
-template <typename REC, int E>
+template <typename REC, int E, bool SPILL = false>
 struct TileSort {
     uint32_t *start, *delta, *scratch;   // [B] [B] [296]
+    uint32_t *thresh, *delta2;           // SPILL: [B] staged positions from thresh[b] on go to the spill list, at delta2[b] + position
     REC* stage;                          // [256 * E] records in bucket order
     uint16_t* tag;                       // [256 * E] bucket of each staged record
     int B;
-    static __host__ __device__ size_t words_of(int B) { return ((size_t)2 * B + 296 + 3) & ~(size_t)3; }
+    static __host__ __device__ size_t words_of(int B) { return ((size_t)(SPILL ? 4 : 2) * B + 296 + 3) & ~(size_t)3; }
     static __host__ __device__ size_t smem_bytes(int B) { return words_of(B) * 4 + (size_t)kSlThreads * E * sizeof(REC) + (size_t)kSlThreads * E * 2; }
     __device__ __forceinline__ void init(unsigned char* smem, int B_) {
         B = B_;
         start = reinterpret_cast<uint32_t*>(smem);
         delta = start + B;
         scratch = delta + B;
+        thresh = scratch + 296;
+        delta2 = thresh + B;
         stage = reinterpret_cast<REC*>(smem + words_of(B) * 4);
         tag = reinterpret_cast<uint16_t*>(smem + words_of(B) * 4 + (size_t)kSlThreads * E * sizeof(REC));
     }
@@ -182,15 +189,32 @@ struct TileSort {
                 const uint32_t cnt = (b + 1 < B ? start[b + 1] : total) - start[b];
                 const uint32_t lo = sl_region_lo(out, region0 + b), cap = sl_region_hi(out, region0 + b) - lo;
                 const uint32_t a = min(at[q], cap);
-                if (cnt && a + cnt > cap) atomicOr(reinterpret_cast<unsigned int*>(overflow), 1u);
                 delta[b] = lo + a - start[b];
                 if (meta) meta[b] = make_uint2(lo + a, start[b]);
+                bool failed = cnt && a + cnt > cap;
+                if (SPILL) {
+                    thresh[b] = 0xFFFFFFFFu; delta2[b] = 0;
+                    if (failed && out.spill_data) {   // the part of the run that does not fit goes to the spill list
+                        const uint32_t keep = cap - a, over = cnt - keep;
+                        const uint32_t so = atomicAdd(out.spill_cursor, over);
+                        if (so + over <= out.spill_cap) { thresh[b] = start[b] + keep; delta2[b] = so - (start[b] + keep); failed = false; }
+                    }
+                }
+                if (failed) atomicOr(reinterpret_cast<unsigned int*>(overflow), 1u);
             }
         }
         if (meta && t == 0) meta[B] = make_uint2(0u, total);
         __syncthreads();
         REC* data = reinterpret_cast<REC*>(out.data);
-        for (uint32_t p = t; p < total; p += kSlThreads) data[delta[tag[p]] + p] = stage[p];
+        if (SPILL) {
+            REC* spill = reinterpret_cast<REC*>(out.spill_data);
+            for (uint32_t p = t; p < total; p += kSlThreads) {
+                const uint32_t b = tag[p];
+                if (p < thresh[b]) data[delta[b] + p] = stage[p]; else spill[delta2[b] + p] = stage[p];
+            }
+        } else {
+            for (uint32_t p = t; p < total; p += kSlThreads) data[delta[tag[p]] + p] = stage[p];
+        }
         __syncthreads();
     }
 };
@@ -398,7 +422,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_route_keys_u(const Ingest g, in
         }
     }
     __syncthreads();
-    TileSort<unsigned long long, kSlRoundKmers> ts;
+    TileSort<unsigned long long, kSlRoundKmers, true> ts;
     ts.init(sl_smem, arena.B);
     ts.run(arena, 0, bkt, rec, slot, overflow, nullptr);
 }
@@ -582,7 +606,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_route_keys(const Ingest g, int 
     RB_DYN_SMEM(unsigned char, sl_smem);
     __shared__ RollLut lut;
     build_lut(&lut, k);
-    TileSort<unsigned long long, kChunk> ts;
+    TileSort<unsigned long long, kChunk, true> ts;
     ts.init(sl_smem, arena.B);
     const int64_t pos0 = ((int64_t)blockIdx.x * kSlThreads + threadIdx.x) * kChunk;
     const int n = pos0 < g.n_pos ? (int)min((int64_t)kChunk, g.n_pos - pos0) : 0;
@@ -612,10 +636,10 @@ __global__ void __launch_bounds__(kSlThreads) ks_route_keys(const Ingest g, int 
 __global__ void __launch_bounds__(kSlThreads) ks_split_keys(const SlArena in, int* chunk_prefix, int sub_bits, int sub_shift, int region_div,
                                                            const SlArena out, int* overflow) {
     RB_DYN_SMEM(unsigned char, sl_smem);
-    TileSort<unsigned long long, kSlRoundKmers> ts;
+    TileSort<unsigned long long, kSlRoundKmers, true> ts;
     const int n_sub = 1 << sub_bits;
     ts.init(sl_smem, n_sub);
-    int* pre = reinterpret_cast<int*>(sl_smem + TileSort<unsigned long long, kSlRoundKmers>::smem_bytes(n_sub));
+    int* pre = reinterpret_cast<int*>(sl_smem + TileSort<unsigned long long, kSlRoundKmers, true>::smem_bytes(n_sub));
     sl_load_prefix(pre, chunk_prefix, in.B);
     const int total = pre[in.B];
     const unsigned long long* rec_in = reinterpret_cast<const unsigned long long*>(in.data);
@@ -639,9 +663,53 @@ __global__ void __launch_bounds__(kSlThreads) ks_split_keys(const SlArena in, in
 }
 
 // ---- I3: one CTA per sub-range: (key -> multiplicity) in a shared-memory hash table, distinct keys appended to the dense arrays ----------------
+// keys that did not fit their range / sub-range (heavy hitters: one k-mer with thousands of copies in a round): aggregated here first,
+// then merged into the multiplicities ks_dedup finds, and what ks_dedup never saw is appended afterwards (ks_spill_append)
+struct SpillTable {
+    unsigned long long* keys;   // n_slots + 1; 0 = empty; slot n_slots stands for key 0
+    unsigned int* counts;
+    uint64_t n_slots;           // power of two; nullptr keys = no spill this round
+    int shift;
+};
+__device__ __forceinline__ unsigned int spill_take(const SpillTable& h, unsigned long long key) {
+    if (key == 0ULL) return atomicExch(&h.counts[h.n_slots], 0u);
+    uint64_t s = sl_mixkey(key) >> h.shift;
+    for (;;) {
+        const unsigned long long k = h.keys[s];
+        if (k == key) return atomicExch(&h.counts[s], 0u);
+        if (k == 0ULL) return 0u;
+        s = (s + 1) & (h.n_slots - 1);
+    }
+}
+__global__ void __launch_bounds__(kSlThreads) ks_spill_aggregate(const unsigned long long* __restrict__ spill, const unsigned int* __restrict__ n_spill,
+                                                                uint32_t cap, const SpillTable h) {
+    const uint32_t n = min(*n_spill, cap);
+    for (uint32_t i = blockIdx.x * kSlThreads + threadIdx.x; i < n; i += gridDim.x * kSlThreads) {
+        const unsigned long long key = spill[i];
+        if (key == 0ULL) { atomicAdd(&h.counts[h.n_slots], 1u); continue; }
+        uint64_t s = sl_mixkey(key) >> h.shift;
+        for (;;) {
+            const unsigned long long old = atomicCAS(&h.keys[s], 0ULL, key);
+            if (old == 0ULL || old == key) { atomicAdd(&h.counts[s], 1u); break; }
+            s = (s + 1) & (h.n_slots - 1);
+        }
+    }
+}
+__global__ void __launch_bounds__(kSlThreads) ks_spill_append(const SpillTable h, unsigned long long* __restrict__ dkey, unsigned int* __restrict__ dmult,
+                                                             unsigned int* n_distinct, unsigned int dense_cap, int* overflow) {
+    for (uint64_t s = (uint64_t)blockIdx.x * kSlThreads + threadIdx.x; s <= h.n_slots; s += (uint64_t)gridDim.x * kSlThreads) {
+        const unsigned int c = h.counts[s];
+        if (c) {   // ks_dedup did not meet this key in its sub-range: every copy of it was spilled
+            const unsigned int d = atomicAdd(n_distinct, 1u);
+            if (d < dense_cap) { dkey[d] = s == h.n_slots ? 0ULL : h.keys[s]; dmult[d] = c; }
+            else atomicOr(reinterpret_cast<unsigned int*>(overflow), 1u);
+        }
+    }
+}
 constexpr int kSlDedupSlots = 4096;   // 32 KiB of keys + 16 KiB of counters; a sub-range holds fewer keys than that (host: cap < slots)
 __global__ void __launch_bounds__(kSlThreads) ks_dedup(const SlArena in, int n_regions, int hash_shift, unsigned long long* __restrict__ dkey,
-                                                      unsigned int* __restrict__ dmult, unsigned int* n_distinct, unsigned int dense_cap, int* overflow) {
+                                                      unsigned int* __restrict__ dmult, unsigned int* n_distinct, unsigned int dense_cap, int* overflow,
+                                                      const SpillTable spill) {
     RB_DYN_SMEM(unsigned char, sl_smem);
     unsigned long long* tkeys = reinterpret_cast<unsigned long long*>(sl_smem);
     unsigned int* tcnt = reinterpret_cast<unsigned int*>(tkeys + kSlDedupSlots);
@@ -676,8 +744,12 @@ __global__ void __launch_bounds__(kSlThreads) ks_dedup(const SlArena in, int n_r
             if (threadIdx.x == 0) atomicOr(reinterpret_cast<unsigned int*>(overflow), 1u);
         } else {
             for (uint32_t i = threadIdx.x; i < T; i += kSlThreads)
-                if (tcnt[i]) { const uint32_t d = out_base + (tcnt[i] >> 16); dkey[d] = tkeys[i]; dmult[d] = tcnt[i] & 0xFFFFu; }
-            if (threadIdx.x == 0 && n_zero) { dkey[out_base + n_occ] = 0ULL; dmult[out_base + n_occ] = n_zero; }
+                if (tcnt[i]) {
+                    const uint32_t d = out_base + (tcnt[i] >> 16);
+                    dkey[d] = tkeys[i];
+                    dmult[d] = (tcnt[i] & 0xFFFFu) + (spill.keys ? spill_take(spill, tkeys[i]) : 0u);
+                }
+            if (threadIdx.x == 0 && n_zero) { dkey[out_base + n_occ] = 0ULL; dmult[out_base + n_occ] = n_zero + (spill.keys ? spill_take(spill, 0ULL) : 0u); }
         }
         __syncthreads();
     }

@@ -12,6 +12,9 @@ struct SlicedEngine {
     unsigned long long* key_data; unsigned int* key_cursor; uint32_t* key_roff; int key_B; int key_shift;   // level 1: key_B ranges
     unsigned long long* sub_data; unsigned int* sub_cursor; int sub_bits; uint32_t sub_cap;                   // level 2: key_B << sub_bits sub-ranges
     unsigned long long* dkey; unsigned int* dmult; unsigned int* n_distinct;
+    // heavy hitters (RB_SLICED_SPILL=1, off by default until it has been measured): keys that overflow their range / sub-range
+    bool spill_on; unsigned long long* spill_keys; unsigned int* spill_cursor; uint32_t spill_cap;
+    unsigned long long* htab_keys; unsigned int* htab_counts; int64_t htab_slots; int htab_shift;
     uint32_t* raise_data; unsigned int* raise_cursor; uint32_t* raise_roff;
     int* chunk_prefix;
     int* overflow;
@@ -22,6 +25,7 @@ static void sliced_engine_free(rb_graph* g) {
     cudaStreamSynchronize(g->ctx->stream);
     cudaFree(e->probe_data); cudaFree(e->ans); cudaFree(e->probe_cursor); cudaFree(e->probe_roff); cudaFree(e->pos); cudaFree(e->tile_meta);
     cudaFree(e->key_data); cudaFree(e->key_cursor); cudaFree(e->key_roff);
+    cudaFree(e->spill_keys); cudaFree(e->spill_cursor); cudaFree(e->htab_keys); cudaFree(e->htab_counts);
     cudaFree(e->sub_data); cudaFree(e->sub_cursor); cudaFree(e->dkey); cudaFree(e->dmult); cudaFree(e->n_distinct);
     cudaFree(e->raise_data); cudaFree(e->raise_cursor); cudaFree(e->raise_roff);
     cudaFree(e->chunk_prefix); cudaFree(e->overflow);
@@ -102,6 +106,11 @@ static int32_t sliced_engine_get(rb_graph* g, int64_t n_round, SlicedEngine** ou
     e->key_B = 1 << lg1;
     e->key_shift = 64 - lg1;
     e->sub_cap = (uint32_t)sl_capacity((double)n_max / (double)(1LL << (lg1 + e->sub_bits)));
+    if (getenv("RB_SLICED_SUBCAP")) e->sub_cap = (uint32_t)env_int("RB_SLICED_SUBCAP", (int)e->sub_cap, 8, kSlDedupSlots - 1);   // tests: force spills
+    e->spill_on = env_int("RB_SLICED_SPILL", 0, 0, 1) != 0;
+    e->spill_cap = (uint32_t)std::min<int64_t>(n_max / 8 + 65536, 1LL << 30);
+    e->htab_slots = sl_pow2_at_least(2 * (int64_t)e->spill_cap);
+    { int lg = 0; while ((1LL << lg) < e->htab_slots) ++lg; e->htab_shift = 64 - lg; }
     if (e->sub_cap >= (uint32_t)kSlDedupSlots) { e->unsupported = true; return RB_OK; }   // cannot happen with lgSub <= 11, n_max <= 2^29
     e->probe_B = sg.n_dbg + sg.n_cbf;
     // ---- capacities ----
@@ -114,7 +123,7 @@ static int32_t sliced_engine_get(rb_graph* g, int64_t n_round, SlicedEngine** ou
     int64_t probe_slots = 0, key_slots = 0, raise_slots = 0;
     int32_t rc = sl_make_roff(ctx, caps, &e->probe_roff, &probe_slots);
     if (rc) { sliced_engine_free(g); return rc; }
-    caps.assign((size_t)e->key_B, sl_capacity((double)n_max / e->key_B));
+    caps.assign((size_t)e->key_B, getenv("RB_SLICED_KEYCAP") ? (int64_t)env_int("RB_SLICED_KEYCAP", 1 << 20, 8, 1 << 30) : sl_capacity((double)n_max / e->key_B));
     rc = sl_make_roff(ctx, caps, &e->key_roff, &key_slots);
     if (rc) { sliced_engine_free(g); return rc; }
     caps.assign((size_t)sg.n_raise, sl_capacity((double)n_max * g->hc / raise_slices));
@@ -133,6 +142,12 @@ static int32_t sliced_engine_get(rb_graph* g, int64_t n_round, SlicedEngine** ou
     if (n_sub_regions * e->sub_cap >= (1LL << 32) - (1LL << 20)) { sliced_engine_free(g); return fail(ctx, RB_EINVAL, "sliced engine: round too large for 32-bit record positions"); }
     if (er == cudaSuccess) er = cudaMalloc(&e->sub_data, ((size_t)n_sub_regions * e->sub_cap + kSlSpill) * 8);
     if (er == cudaSuccess) er = cudaMalloc(&e->sub_cursor, (size_t)n_sub_regions * 4 + 64);
+    if (er == cudaSuccess && e->spill_on) {
+        er = cudaMalloc(&e->spill_keys, ((size_t)e->spill_cap + kSlSpill) * 8);
+        if (er == cudaSuccess) er = cudaMalloc(&e->spill_cursor, 64);
+        if (er == cudaSuccess) er = cudaMalloc(&e->htab_keys, (size_t)(e->htab_slots + 1) * 8);
+        if (er == cudaSuccess) er = cudaMalloc(&e->htab_counts, (size_t)(e->htab_slots + 1) * 4);
+    }
     if (er == cudaSuccess) er = cudaMalloc(&e->dkey, ((size_t)n_max + 8) * 8);
     if (er == cudaSuccess) er = cudaMalloc(&e->dmult, ((size_t)n_max + 8) * 4);
     if (er == cudaSuccess) er = cudaMalloc(&e->n_distinct, 64);
@@ -178,6 +193,7 @@ static int32_t sl_chunk_prefix(rb_ctx* ctx, SlicedEngine* e, const SlArena& a) {
 static SlArena sl_arena(void* data, unsigned int* cursor, const uint32_t* roff, int B, int chunk) {
     SlArena a;
     a.data = data; a.cursor = cursor; a.roff = roff; a.B = B; a.chunk = chunk; a.cap = 0; a.cursor_stride = kSlPad; a.rlo = nullptr;
+    a.spill_data = nullptr; a.spill_cursor = nullptr; a.spill_cap = 0;
     return a;
 }
 static SlArena sl_probe_arena(SlicedEngine* e) { return sl_arena(e->probe_data, e->probe_cursor, e->probe_roff, e->probe_B, sl_chunk()); }
@@ -259,17 +275,21 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     if (e->unsupported) { *fell_back = true; return RB_OK; }
     const HashMults hm = make_hm(g->k);
     // I1 keys by range
-    const SlArena keys = sl_arena(e->key_data, e->key_cursor, e->key_roff, e->key_B, kSlThreads * kSlRoundKmers);
+    SlArena keys = sl_arena(e->key_data, e->key_cursor, e->key_roff, e->key_B, kSlThreads * kSlRoundKmers);
     CK(cudaMemsetAsync(keys.cursor, 0, (size_t)keys.B * kSlPad * 4, ctx->stream));
+    if (e->spill_on) {
+        keys.spill_data = e->spill_keys; keys.spill_cursor = e->spill_cursor; keys.spill_cap = e->spill_cap;
+        CK(cudaMemsetAsync(e->spill_cursor, 0, 4, ctx->stream));
+    }
     if (sl_uniform_fast(ing, g->k)) {
         const int grid_pos = (int)div_up(ing.n_pos, (int64_t)kSlTile);
-        const size_t sm = std::max(TileSort<unsigned long long, kSlRoundKmers>::smem_bytes(keys.B), PrefixKmerizer::smem_bytes());
+        const size_t sm = std::max(TileSort<unsigned long long, kSlRoundKmers, true>::smem_bytes(keys.B), PrefixKmerizer::smem_bytes());
         if (mode == RB_MODE_FWD) SL_LAUNCH("ks_route_keys_u<0>", ks_route_keys_u<0>, grid_pos, sm, ing, g->k, e->key_B, e->key_shift, keys, e->overflow);
         else if (mode == RB_MODE_RC) SL_LAUNCH("ks_route_keys_u<1>", ks_route_keys_u<1>, grid_pos, sm, ing, g->k, e->key_B, e->key_shift, keys, e->overflow);
         else SL_LAUNCH("ks_route_keys_u<2>", ks_route_keys_u<2>, grid_pos, sm, ing, g->k, e->key_B, e->key_shift, keys, e->overflow);
     } else {
         const int grid_pos = (int)div_up(ing.n_pos, (int64_t)kSlThreads * kChunk);
-        const size_t sm_keys = TileSort<unsigned long long, kChunk>::smem_bytes(keys.B);
+        const size_t sm_keys = TileSort<unsigned long long, kChunk, true>::smem_bytes(keys.B);
         if (mode == RB_MODE_FWD) SL_LAUNCH("ks_route_keys<0>", ks_route_keys<0>, grid_pos, sm_keys, ing, g->k, e->key_B, e->key_shift, keys, e->overflow);
         else if (mode == RB_MODE_RC) SL_LAUNCH("ks_route_keys<1>", ks_route_keys<1>, grid_pos, sm_keys, ing, g->k, e->key_B, e->key_shift, keys, e->overflow);
         else SL_LAUNCH("ks_route_keys<2>", ks_route_keys<2>, grid_pos, sm_keys, ing, g->k, e->key_B, e->key_shift, keys, e->overflow);
@@ -279,11 +299,12 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     const int n_sub_regions = e->key_B << e->sub_bits;
     SlArena subs = sl_arena(e->sub_data, e->sub_cursor, nullptr, n_sub_regions, 0);
     subs.cap = e->sub_cap; subs.cursor_stride = 1;
+    subs.spill_data = keys.spill_data; subs.spill_cursor = keys.spill_cursor; subs.spill_cap = keys.spill_cap;
     CK(cudaMemsetAsync(subs.cursor, 0, (size_t)n_sub_regions * 4, ctx->stream));
     rc = sl_chunk_prefix(ctx, e, keys);
     if (rc) return rc;
     int grid = 0;
-    const size_t sm_split = TileSort<unsigned long long, kSlRoundKmers>::smem_bytes(n_sub) + (size_t)(keys.B + 1) * 4;
+    const size_t sm_split = TileSort<unsigned long long, kSlRoundKmers, true>::smem_bytes(n_sub) + (size_t)(keys.B + 1) * 4;
     rc = sl_stream_grid(ctx, ks_split_keys, sm_split, &grid);
     if (rc) return rc;
     SL_LAUNCH("ks_split_keys", ks_split_keys, grid, sm_split, keys, e->chunk_prefix, e->sub_bits, 64 - (64 - e->key_shift) - e->sub_bits, 1, subs, e->overflow);
@@ -291,13 +312,32 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     rc = sl_read_flag(ctx, e->overflow, &flag);
     if (rc) return rc;
     if (flag) { *fell_back = true; return RB_OK; }   // key skew (one k-mer dominating the batch): nothing modified yet
+    // heavy hitters: what did not fit its range / sub-range is aggregated in a global table that ks_dedup merges from
+    SpillTable spill;
+    memset(&spill, 0, sizeof spill);
+    if (e->spill_on) {
+        unsigned int n_spill = 0;
+        CK(cudaMemcpyAsync(&n_spill, e->spill_cursor, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (n_spill) {
+            spill.keys = e->htab_keys; spill.counts = e->htab_counts; spill.n_slots = (uint64_t)e->htab_slots; spill.shift = e->htab_shift;
+            CK(cudaMemsetAsync(spill.keys, 0, (size_t)(e->htab_slots + 1) * 8, ctx->stream));
+            CK(cudaMemsetAsync(spill.counts, 0, (size_t)(e->htab_slots + 1) * 4, ctx->stream));
+            const int grid_s = (int)std::min<int64_t>(div_up((int64_t)n_spill, kSlThreads), (int64_t)ctx->sm_count * 8);
+            SL_LAUNCH("ks_spill_aggregate", ks_spill_aggregate, grid_s, 0, e->spill_keys, e->spill_cursor, e->spill_cap, spill);
+        }
+    }
     // I3 distinct keys and their multiplicities
     CK(cudaMemsetAsync(e->n_distinct, 0, 4, ctx->stream));
     const size_t sm_dedup = (size_t)kSlDedupSlots * 12;
     rc = sl_stream_grid(ctx, ks_dedup, sm_dedup, &grid);
     if (rc) return rc;
     SL_LAUNCH("ks_dedup", ks_dedup, std::min(grid, n_sub_regions), sm_dedup, subs, n_sub_regions, (64 - e->key_shift) + e->sub_bits, e->dkey, e->dmult, e->n_distinct,
-              (unsigned int)std::min<int64_t>(e->n_max + 8, 0xFFFFFFFFLL), e->overflow);
+              (unsigned int)std::min<int64_t>(e->n_max + 8, 0xFFFFFFFFLL), e->overflow, spill);
+    if (spill.keys) {
+        const int grid_a = (int)std::min<int64_t>(div_up(e->htab_slots + 1, kSlThreads), (int64_t)ctx->sm_count * 8);
+        SL_LAUNCH("ks_spill_append", ks_spill_append, grid_a, 0, spill, e->dkey, e->dmult, e->n_distinct, (unsigned int)std::min<int64_t>(e->n_max + 8, 0xFFFFFFFFLL), e->overflow);
+    }
     // I4 probes by filter slice
     const SlArena probes = sl_probe_arena(e);
     CK(cudaMemsetAsync(probes.cursor, 0, (size_t)probes.B * kSlPad * 4, ctx->stream));

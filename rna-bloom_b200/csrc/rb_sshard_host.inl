@@ -219,13 +219,13 @@ static int32_t ss_route_launch(rb_ctx* ctx, const Ingest& ing_in, void* user) {
         const int n_ranges = 1 << sh->lg1, shift = 64 - sh->lg1;
         if (fast) {
             const int grid = (int)div_up(ing.n_pos, (int64_t)kSlTile);
-            const size_t sm = std::max(TileSort<unsigned long long, kSlRoundKmers>::smem_bytes(keys.B), PrefixKmerizer::smem_bytes());
+            const size_t sm = std::max(TileSort<unsigned long long, kSlRoundKmers, true>::smem_bytes(keys.B), PrefixKmerizer::smem_bytes());
             if (u->mode == RB_MODE_FWD) SL_LAUNCH("ks_route_keys_u<0>", ks_route_keys_u<0>, grid, sm, ing, sh->k, n_ranges, shift, keys, sh->overflow);
             else if (u->mode == RB_MODE_RC) SL_LAUNCH("ks_route_keys_u<1>", ks_route_keys_u<1>, grid, sm, ing, sh->k, n_ranges, shift, keys, sh->overflow);
             else SL_LAUNCH("ks_route_keys_u<2>", ks_route_keys_u<2>, grid, sm, ing, sh->k, n_ranges, shift, keys, sh->overflow);
         } else {
             const int grid = (int)div_up(ing.n_pos, (int64_t)kSlThreads * kChunk);
-            const size_t sm = TileSort<unsigned long long, kChunk>::smem_bytes(keys.B);
+            const size_t sm = TileSort<unsigned long long, kChunk, true>::smem_bytes(keys.B);
             if (u->mode == RB_MODE_FWD) SL_LAUNCH("ks_route_keys<0>", ks_route_keys<0>, grid, sm, ing, sh->k, n_ranges, shift, keys, sh->overflow);
             else if (u->mode == RB_MODE_RC) SL_LAUNCH("ks_route_keys<1>", ks_route_keys<1>, grid, sm, ing, sh->k, n_ranges, shift, keys, sh->overflow);
             else SL_LAUNCH("ks_route_keys<2>", ks_route_keys<2>, grid, sm, ing, sh->k, n_ranges, shift, keys, sh->overflow);
@@ -314,7 +314,7 @@ extern "C" int32_t rb_sshard_dedup(rb_sshard* sh, const unsigned long long* recv
     subs.cap = sh->sub_cap; subs.cursor_stride = 1;
     CK(cudaMemsetAsync(subs.cursor, 0, (size_t)n_sub_regions * 4, ctx->stream));
     int grid = 0;
-    const size_t sm_split = TileSort<unsigned long long, kSlRoundKmers>::smem_bytes(n_sub) + (size_t)(keys.B + 1) * 4;
+    const size_t sm_split = TileSort<unsigned long long, kSlRoundKmers, true>::smem_bytes(n_sub) + (size_t)(keys.B + 1) * 4;
     rc = sl_stream_grid(ctx, ks_split_keys, sm_split, &grid);
     if (rc) return rc;
     SL_LAUNCH("ks_split_keys", ks_split_keys, grid, sm_split, keys, sh->chunk_prefix, sh->sub_bits, 64 - sh->lg1 - sh->sub_bits, sh->W, subs, sh->overflow);
@@ -323,7 +323,7 @@ extern "C" int32_t rb_sshard_dedup(rb_sshard* sh, const unsigned long long* recv
     rc = sl_stream_grid(ctx, ks_dedup, sm_dedup, &grid);
     if (rc) return rc;
     SL_LAUNCH("ks_dedup", ks_dedup, std::min(grid, n_sub_regions), sm_dedup, subs, n_sub_regions, sh->lg1 + sh->sub_bits, sh->dkey, sh->dmult, sh->n_distinct,
-              (unsigned int)sh->n_dense, sh->overflow);
+              (unsigned int)sh->n_dense, sh->overflow, SpillTable{nullptr, nullptr, 0, 0});
     return RB_OK;
 }
 extern "C" int32_t rb_sshard_emit_probes(rb_sshard* sh, int32_t with_cbf, uint32_t* send_probes, uint32_t* send_cnt) {

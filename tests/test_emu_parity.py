@@ -48,7 +48,12 @@ def ctx(emu_lib):
 SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_RAISE_LOG2": "14", "RB_SLICED_SUBRANGE_LOG2": "6"}
 # sliced-small: tiny slices / sub-ranges so that the small test filters span hundreds of regions (every test);
 # sliced-default: the production geometry; direct: validates the emulation itself (that engine is verified on the GPU)
+# sliced-small-spill: RB_SLICED_SPILL=1 with region capacities far below the expected load, so that a large part of the keys takes
+# the heavy-hitter path (spill list -> global table -> merged by ks_dedup / appended afterwards); off by default in the product
+SPILL_ENV = {"RB_SLICED_SPILL": "1", "RB_SLICED_SUBCAP": "40", "RB_SLICED_KEYCAP": "1500"}
 ONLY = {
+    "sliced-small-spill": ("test_graph_add_collision_free_is_bit_exact", "test_duplicates_inside_one_batch_are_linearised",
+                           "test_skewed_batch_is_redone_by_the_direct_engine", "test_insert_policies_and_pair_filters"),
     "sliced-default": ("test_getkmers_with_invalid_nucleotides", "test_insert_policies_and_pair_filters"),
     "direct": ("test_getkmers_with_invalid_nucleotides", "test_neighbor_counts_match_oracle"),
 }
@@ -56,12 +61,12 @@ SKIP = {"sliced-small": ("test_kernels_are_race_free_under_tsan", "test_neighbor
 ONLY["sliced-default"] += ("test_kernels_are_race_free_under_tsan",)
 
 
-@pytest.fixture(autouse=True, params=["sliced-small", "sliced-default", "direct"])
+@pytest.fixture(autouse=True, params=["sliced-small", "sliced-small-spill", "sliced-default", "direct"])
 def engine(request):
     name = request.node.originalname or request.node.name
     if (request.param in ONLY and name not in ONLY[request.param]) or name in SKIP.get(request.param, ()):
         pytest.skip("not in the reduced matrix of this variant")
-    keys = ["RB_ENGINE", "RB_SLICED_CHUNK"] + list(SLICE_ENV)
+    keys = ["RB_ENGINE", "RB_SLICED_CHUNK"] + list(SLICE_ENV) + list(SPILL_ENV)
     old = {k: os.environ.get(k) for k in keys}
     os.environ["RB_ENGINE"] = request.param.split("-")[0]
     for k in keys[1:]:
@@ -69,6 +74,8 @@ def engine(request):
     os.environ["RB_SLICED_CHUNK"] = "8192"   # fewer work items = fewer emulated barriers; the logic is the same
     if "small" in request.param:
         os.environ.update(SLICE_ENV)
+    if "spill" in request.param:
+        os.environ.update(SPILL_ENV)
     yield request.param
     for k, v in old.items():
         if v is None:
