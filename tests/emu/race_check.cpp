@@ -2,7 +2,8 @@
 // A missing __syncthreads() is invisible to the parity tests of the emulation (OS threads rarely interleave badly) and only
 // shows up on the GPU at full size; TSan sees the unordered shared-memory accesses directly.  Built and run by
 // tests/test_emu_parity.py::test_kernels_are_race_free_under_tsan:
-//   g++ -std=c++20 -O1 -g -fsanitize=thread -DRB_EMU -I tests/emu -pthread tests/emu/race_check.cpp -o tests/emu/race_check
+//   g++ -std=c++20 -O1 -g -fsanitize=thread -DRB_EMU -DRB_EMU_THREADS -I tests/emu -pthread tests/emu/race_check.cpp -o tests/emu/race_check
+// (RB_EMU_THREADS: one OS thread per CUDA thread; the default fiber mode of cuda_emu.h is sequential and would hide every race)
 #include "../../rna-bloom_b200/csrc/rnabloom_gpu.cu"
 
 #include <cstdio>
