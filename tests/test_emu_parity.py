@@ -8,6 +8,7 @@ engines are caught in the container instead of on the (scarce) GPU box.
 import os
 import subprocess
 
+import numpy as np
 import pytest
 
 import rnabloom_b200 as rb
@@ -54,11 +55,13 @@ SPILL_ENV = {"RB_SLICED_SPILL": "1", "RB_SLICED_SUBCAP": "40", "RB_SLICED_KEYCAP
 ONLY = {
     "sliced-small-spill": ("test_duplicates_inside_one_batch_are_linearised", "test_skewed_batch_is_redone_by_the_direct_engine",
                            "test_insert_policies_and_pair_filters"),
-    "sliced-default": ("test_getkmers_with_invalid_nucleotides", "test_insert_policies_and_pair_filters"),
     "direct": ("test_getkmers_with_invalid_nucleotides", "test_neighbor_counts_match_oracle"),
+    "sliced-default": ("test_getkmers_with_invalid_nucleotides", "test_insert_policies_and_pair_filters", "test_kernels_are_race_free_under_tsan",
+                       "test_random_geometry_matches_oracle", "test_random_uniform_layout_matches_oracle"),
 }
-SKIP = {"sliced-small": ("test_kernels_are_race_free_under_tsan", "test_neighbor_counts_match_oracle")}   # sets its own environment; runs once (under "sliced-default")
-ONLY["sliced-default"] += ("test_kernels_are_race_free_under_tsan",)
+SKIP = {"sliced-small": ("test_kernels_are_race_free_under_tsan", "test_neighbor_counts_match_oracle", "test_random_geometry_matches_oracle",
+                         "test_random_uniform_layout_matches_oracle"),
+        "sliced-small-spill": ("test_random_geometry_matches_oracle", "test_random_uniform_layout_matches_oracle")}   # the random test sets its own geometry: it runs once, under "sliced-default"   # sets its own environment; runs once (under "sliced-default")
 
 
 @pytest.fixture(autouse=True, params=["sliced-small", "sliced-small-spill", "sliced-default", "direct"])
@@ -126,3 +129,78 @@ def test_kernels_are_race_free_under_tsan(tmp_path):
     p = subprocess.run([exe, "120"], env=env, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0 and "race_check ok" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
     assert "WARNING: ThreadSanitizer" not in p.stderr, p.stderr[:6000]
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("RB_FUZZ_SEEDS", "10"))))
+def test_random_geometry_matches_oracle(ctx, orc, seed, monkeypatch):
+    """Seeded random configurations of the sliced engine against the oracle: filter sizes that are no multiple of the slice size (or
+    smaller than one slice), 1..3 hashes per filter, k from 9 to 70, ragged reads with unusable bases, random slice / sub-range
+    geometry, spill path on or off; insert (twice: every k-mer present the second time), look-up of every k-mer, one more policy."""
+    rng = np.random.default_rng(1000 + seed)
+    k = int(rng.integers(9, 71))
+    hd, hc = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+    stranded = bool(rng.integers(0, 2))
+    dbg_bits = int(rng.integers(1 << 16, 1 << 25)) | 1
+    cbf_bytes = int(rng.integers(1 << 20, 1 << 23)) | 1       # roomy: counters of distinct k-mers rarely collide, the comparison stays tight
+    for name, lo, hi in (("RB_SLICE_BITS_LOG2", 12, 22), ("RB_SLICE_BYTES_LOG2", 10, 20), ("RB_SLICE_RAISE_LOG2", 8, 18),
+                         ("RB_SLICED_SUBRANGE_LOG2", 4, 9)):
+        monkeypatch.setenv(name, str(int(rng.integers(lo, hi + 1))))
+    if rng.integers(0, 2):
+        monkeypatch.setenv("RB_SLICED_SPILL", "1")
+        monkeypatch.setenv("RB_SLICED_SUBCAP", str(int(rng.integers(8, 200))))
+    monkeypatch.setenv("RB_ENGINE", "sliced")
+    n_reads = int(rng.integers(60, 260))
+    genome = "".join(rng.choice(list("ACGT"), size=max(4 * k, n_reads * 40)))
+    seqs = []
+    for _ in range(n_reads):
+        L = int(rng.integers(1, 260))
+        p = int(rng.integers(0, max(1, len(genome) - L)))
+        s = list(genome[p:p + L])
+        for j in np.nonzero(rng.random(len(s)) < 0.004)[0]:
+            s[j] = "N"
+        seqs.append("".join(s))
+    g, og = G.make_graphs(ctx, orc, dbg_bits, cbf_bytes, 64, hd, hc, 1, k, stranded, False)
+    modes = [G.MODE_FWD, G.MODE_RC] if stranded else [G.MODE_CANON]
+    bases = G.all_bases(orc, [s.replace("N", "A") for s in seqs], k, modes)
+    half = n_reads // 2
+    for rnd, (chunk, flags, oflags) in enumerate(((seqs, 0, 0), (seqs[:half], rb.REVCOMP if stranded else 0, G.F_REVCOMP if stranded else 0),
+                                                   (seqs[half:], rb.ADD_COUNT_IF_PRESENT, G.F_ADD_COUNT_IF_PRESENT), (seqs[:20], rb.DBG_ONLY, G.F_DBG_ONLY))):
+        for s in chunk:
+            og.add_read(s, flags=oflags)
+        g.addReads(rb.pack_reads(chunk), flags=flags)
+        assert (g.getDbgbf().download() == og.dbgbf()).all(), "dbgbf differs after round %d" % rnd
+    if og.cbf().max() <= 16:      # inside the deterministic MiniFloat range
+        diff = np.nonzero(g.getCbf().download() != og.cbf())[0]
+        if len(diff):
+            # order dependence the reference has itself: k-mers that share a counter, and k-mers that share a dbgbf bit with another
+            # k-mer (whether such a k-mer is "present" the first time it is seen depends on which of the two came first)
+            allowed, _ = G.counters_that_may_differ(bases, k, hc, cbf_bytes)
+            bits = G.np_slots(bases, k, hd, dbg_bits)
+            uniq, cnt = np.unique(bits.reshape(-1), return_counts=True)
+            fp_prone = np.isin(bits, uniq[cnt > 1]).any(axis=1)
+            allowed |= set(int(x) for x in G.np_slots(bases[fp_prone], k, hc, cbf_bytes).reshape(-1))
+            assert set(diff.tolist()) <= allowed, "cbf differs on counters of k-mers that share neither a counter nor a dbgbf bit"
+        counts, fh, rh = g.getKmers(rb.pack_reads(seqs))
+        want = [og.count_seq(s) for s in seqs]
+        assert (fh == np.concatenate([w[1] for w in want])).all()
+        if not stranded:
+            assert (rh == np.concatenate([w[2] for w in want])).all()
+        if not len(diff):
+            assert (counts == np.concatenate([w[0] for w in want])).all()
+    g.destroy(), og.close()
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("RB_FUZZ_SEEDS", "4"))))
+def test_random_uniform_layout_matches_oracle(ctx, orc, seed, monkeypatch):
+    """The uniform (fixed-length, strided) ingest with random read length, stride, k and engine geometry: the XOR-prefix k-merizer's
+    tile / span arithmetic (tiles ending inside reads, reads longer than a tile, layouts it must hand to the rolling walker)."""
+    rng = np.random.default_rng(5000 + seed)
+    k = int(rng.integers(15, 66))   # shorter k-mers repeat by chance in the synthetic genome and push counters to 16, where MiniFloat flips coins
+    L = int(rng.integers(k, k + 500))
+    stride = ((L + 31) // 32 + int(rng.integers(0, 3))) * 32
+    n_reads = max(2, int(rng.integers(20000, 90000)) // (L - k + 1))
+    for name, lo, hi in (("RB_SLICE_BITS_LOG2", 14, 22), ("RB_SLICE_BYTES_LOG2", 12, 20), ("RB_SLICE_RAISE_LOG2", 10, 18),
+                         ("RB_SLICED_SUBRANGE_LOG2", 4, 9)):
+        monkeypatch.setenv(name, str(int(rng.integers(lo, hi + 1))))
+    monkeypatch.setenv("RB_ENGINE", "sliced")
+    G.test_uniform_layout_graph_matches_oracle(ctx, orc, L, stride, k, n_reads, bool(rng.integers(0, 2)))
