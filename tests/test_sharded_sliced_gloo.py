@@ -24,17 +24,20 @@ SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_
              "RB_SLICED_CHUNK": "8192"}
 
 
-def _reads():
+def _reads(seed=13):
     from oracle.binding import Oracle
     orc = Oracle()
-    reads = [bytes(r).decode() for r in orc.synth_reads(13, 9000, 0, 240, 100, 8000)]   # ~2.7x coverage: counters stay exact
+    reads = [bytes(r).decode() for r in orc.synth_reads(seed, 9000, 0, 240, 100, 8000)]   # ~2.7x coverage: counters stay exact
     reads[5] = reads[5][:40] + "N" + reads[5][41:]
     reads[17] = "ACGT"          # shorter than k
     return reads
 
 
-def _worker(rank, world, port, stranded, out):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), **SLICE_ENV)
+def _worker(rank, world, port, stranded, out, cfg=None):
+    cfg = cfg or {}
+    K, HD, HC = cfg.get("k", globals()["K"]), cfg.get("hd", globals()["HD"]), cfg.get("hc", globals()["HC"])
+    DBG_BITS, CBF_BYTES = cfg.get("dbg_bits", globals()["DBG_BITS"]), cfg.get("cbf_bytes", globals()["CBF_BYTES"])
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), **dict(SLICE_ENV, **cfg.get("env", {})))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         import rnabloom_b200 as rb
@@ -42,7 +45,7 @@ def _worker(rank, world, port, stranded, out):
         from rnabloom_b200.sharded import SlicedBackend, SlicedShardedGraph
         from test_emu_parity import EMU_SO
         B._lib = B.bind(EMU_SO, allow_missing=True)   # the emulated kernels: "device memory" is host memory
-        reads = _reads()
+        reads = _reads(cfg.get("seed", 13))
         mine = reads[rank::world]
         ctx = rb.Context(0)
         be = SlicedBackend(ctx, world, rank, DBG_BITS, CBF_BYTES, HD, HC, K, stranded, 8000, device=torch.device("cpu"))
@@ -108,3 +111,49 @@ def test_sharded_sliced_graph_matches_oracle(tmp_path, orc, world, stranded):
         assert (np.load(tmp_path / ("fh%d.npy" % r)) == wantf).all()
         # counts are read from the gathered state, which may differ from the oracle only on shared counters
         assert len(got) == len(want) and (got == want).mean() > 0.99
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("RB_FUZZ_SEEDS", "3"))))
+def test_sharded_sliced_graph_random_configurations(tmp_path, orc, seed):
+    """Seeded random world size, k, hash counts, filter sizes and slice geometry through the same protocol."""
+    from oracle.binding import MODE_CANON, MODE_FWD, OracleGraph
+    from parity_util import all_bases, assert_cbf_close
+    from test_emu_parity import build_emu
+    build_emu()
+    rng = np.random.default_rng(9000 + seed)
+    world = int(rng.choice([2, 4, 8]))
+    stranded = bool(rng.integers(0, 2))
+    cfg = {"k": int(rng.integers(15, 61)), "hd": int(rng.integers(1, 4)), "hc": int(rng.integers(1, 4)), "seed": 100 + seed,
+           "dbg_bits": int(rng.integers(1 << 22, 1 << 25)) | 1, "cbf_bytes": int(rng.integers(1 << 19, 1 << 22)) | 1,
+           "env": {"RB_SLICE_BITS_LOG2": str(int(rng.integers(15, 21))), "RB_SLICE_BYTES_LOG2": str(int(rng.integers(13, 19))),
+                   "RB_SLICE_RAISE_LOG2": str(int(rng.integers(10, 16))), "RB_SLICED_SUBRANGE_LOG2": str(int(rng.integers(4, 8)))}}
+    port = 33500 + os.getpid() % 2000 + seed
+    mp.spawn(_worker, args=(world, port, stranded, str(tmp_path), cfg), nprocs=world, join=True)
+    k, hd, hc, dbg_bits, cbf_bytes = cfg["k"], cfg["hd"], cfg["hc"], cfg["dbg_bits"], cfg["cbf_bytes"]
+    reads = _reads(cfg["seed"])
+    og = OracleGraph(orc, dbg_bits, cbf_bytes, 64, hd, hc, 1, k, stranded, False)
+    for s in reads:
+        og.add_read(s)
+    for r in range(world):
+        mine = reads[r::world]
+        for s in mine[:30]:
+            og.add_read(s, flags=2)
+        for s in mine[30:60]:
+            og.add_read(s, flags=4)
+    assert (np.load(tmp_path / "dbg.npy") == og.dbgbf()).all()
+    if og.cbf().max() <= 15:
+        # allowed differences = the order dependence the reference has itself: k-mers that share a counter, and k-mers that share a
+        # dbgbf bit with another k-mer (whether such a k-mer counts as present at its first sighting depends on which came first)
+        from parity_util import counters_that_may_differ, np_slots
+        bases = all_bases(orc, reads, k, [MODE_FWD if stranded else MODE_CANON])
+        allowed, _ = counters_that_may_differ(bases, k, hc, cbf_bytes)
+        bits = np_slots(bases, k, hd, dbg_bits)
+        uniq, cnt = np.unique(bits.reshape(-1), return_counts=True)
+        fp_prone = np.isin(bits, uniq[cnt > 1]).any(axis=1)
+        allowed |= set(int(x) for x in np_slots(bases[fp_prone], k, hc, cbf_bytes).reshape(-1))
+        diff = np.nonzero(np.load(tmp_path / "cbf.npy") != og.cbf())[0]
+        assert set(diff.tolist()) <= allowed, "cbf differs on counters of k-mers that share neither a counter nor a dbgbf bit"
+    for r in range(world):
+        mine = reads[r::world][:40]
+        wantf = np.concatenate([og.count_seq(s)[1] for s in mine if len(s) >= k])
+        assert (np.load(tmp_path / ("fh%d.npy" % r)) == wantf).all()
