@@ -169,7 +169,7 @@ def test_random_geometry_matches_oracle(ctx, orc, seed, monkeypatch):
             og.add_read(s, flags=oflags)
         g.addReads(rb.pack_reads(chunk), flags=flags)
         assert (g.getDbgbf().download() == og.dbgbf()).all(), "dbgbf differs after round %d" % rnd
-    if og.cbf().max() <= 16:      # inside the deterministic MiniFloat range
+    if og.cbf().max() <= 15:      # strictly inside the deterministic MiniFloat range (an increment attempted at 16 is already a coin flip)
         diff = np.nonzero(g.getCbf().download() != og.cbf())[0]
         if len(diff):
             # order dependence the reference has itself: k-mers that share a counter, and k-mers that share a dbgbf bit with another
