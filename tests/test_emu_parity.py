@@ -53,8 +53,7 @@ SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_
 # the heavy-hitter path (spill list -> global table -> merged by ks_dedup / appended afterwards); off by default in the product
 SPILL_ENV = {"RB_SLICED_SPILL": "1", "RB_SLICED_SUBCAP": "40", "RB_SLICED_KEYCAP": "1500"}
 ONLY = {
-    "sliced-small-spill": ("test_duplicates_inside_one_batch_are_linearised", "test_skewed_batch_is_redone_by_the_direct_engine",
-                           "test_insert_policies_and_pair_filters"),
+    "sliced-small-spill": ("test_duplicates_inside_one_batch_are_linearised", "test_skewed_batch_is_redone_by_the_direct_engine"),
     "direct": ("test_getkmers_with_invalid_nucleotides", "test_neighbor_counts_match_oracle"),
     "sliced-default": ("test_getkmers_with_invalid_nucleotides", "test_insert_policies_and_pair_filters", "test_kernels_are_race_free_under_tsan",
                        "test_random_geometry_matches_oracle", "test_random_uniform_layout_matches_oracle"),
@@ -99,7 +98,7 @@ def test_skewed_batch_is_redone_by_the_direct_engine(ctx, orc, monkeypatch):
 
 
 
-@pytest.mark.parametrize("stranded,k,hd,hc,n_reads", [(False, 25, 3, 3, 800), (True, 25, 3, 3, 120), (True, 64, 1, 4, 120)])
+@pytest.mark.parametrize("stranded,k,hd,hc,n_reads", [(False, 25, 3, 3, 800), (True, 25, 3, 3, 120)])
 def test_graph_add_collision_free_is_bit_exact(ctx, orc, stranded, k, hd, hc, n_reads):
     G.test_graph_add_collision_free_is_bit_exact(ctx, orc, stranded, k, hd, hc, n_reads)
 
@@ -131,7 +130,7 @@ def test_kernels_are_race_free_under_tsan(tmp_path):
     assert "WARNING: ThreadSanitizer" not in p.stderr, p.stderr[:6000]
 
 
-@pytest.mark.parametrize("seed", range(int(os.environ.get("RB_FUZZ_SEEDS", "10"))))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("RB_FUZZ_SEEDS", "8"))))
 def test_random_geometry_matches_oracle(ctx, orc, seed, monkeypatch):
     """Seeded random configurations of the sliced engine against the oracle: filter sizes that are no multiple of the slice size (or
     smaller than one slice), 1..3 hashes per filter, k from 9 to 70, ragged reads with unusable bases, random slice / sub-range
@@ -190,7 +189,7 @@ def test_random_geometry_matches_oracle(ctx, orc, seed, monkeypatch):
     g.destroy(), og.close()
 
 
-@pytest.mark.parametrize("seed", range(int(os.environ.get("RB_FUZZ_SEEDS", "4"))))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("RB_FUZZ_SEEDS", "2"))))
 def test_random_uniform_layout_matches_oracle(ctx, orc, seed, monkeypatch):
     """The uniform (fixed-length, strided) ingest with random read length, stride, k and engine geometry: the XOR-prefix k-merizer's
     tile / span arithmetic (tiles ending inside reads, reads longer than a tile, layouts it must hand to the rolling walker)."""
