@@ -167,7 +167,7 @@ static HashMults make_hm(int k) {
 static inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- context ---------------------------------------------------------------------------------------------------------
-extern "C" int32_t rb_version(void) { return 100; }
+extern "C" int32_t rb_version(void) { return 110; }   // 110: sliced engine, rb_sshard_*, neighbour query, profile spans
 
 extern "C" int32_t rb_ctx_create(int32_t device, rb_ctx** out) {
     if (!out) return fail(nullptr, RB_EINVAL, "rb_ctx_create: out is NULL");
