@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--subbatch-kmers", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="N>1: skip the oracle comparison of the sharded path after the timed region")
     ap.add_argument("--engine", default=os.environ.get("RB_ENGINE", "sliced"), choices=["direct", "sliced", "auto"])
     ap.add_argument("--sharded", action="store_true", help="experiments only: run the sharded pipeline even on one GPU")
     ap.add_argument("--sharded-engine", default="sliced", choices=["sliced", "legacy"], help="N>1: pipeline generation (DESIGN.md section 8)")

@@ -14,6 +14,146 @@ import torch.distributed as dist
 import bench as single
 
 
+class _DevReads:
+    """ASCII reads -> packed -> device tensors; .args is the raw-pointer tuple the sharded calls take."""
+
+    def __init__(self, rb, seqs, device):
+        import ctypes as C
+        pr = rb.pack_reads(seqs)
+        self.keep = []
+
+        def up(a):
+            if a is None:
+                return None
+            t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).copy()).to(device)
+            pad = torch.zeros(64, dtype=torch.uint8, device=device)
+            t = torch.cat([t, pad])
+            self.keep.append(t)
+            return C.c_void_p(t.data_ptr())
+        self.args = (up(pr.packed), up(pr.mask), up(pr.read_off), up(pr.read_len), pr.n_reads, pr.uniform_len, pr.uniform_stride)
+
+
+def sharded_parity_check(make_graph, rank, world, device, full_dbg_bits=None, full_cbf_bytes=None, full_graph=None,
+                         small=((1 << 30) + 77, (1 << 28) + 13, 2000, 500), n_full=20000):
+    """Correctness of the N-rank data path against the CPU oracle, on the very box and process group the numbers come from
+    (graph/BloomFilterDeBruijnGraph.java:405-412 add, :562-570 getCount).  The oracle is the checker here, never the thing timed.
+
+    A  small odd-sized filters (no power of two, shares of unequal length): every rank inserts its own reads in several rounds, then
+       re-inserts some (multiplicities inside a round, k-mers present before the round), then addCountIfPresent / addDbgOnly; all
+       shares are gathered and compared with the sequential oracle: dbgbf byte-equal, cbf equal except on counters that two distinct
+       k-mers share, getKmers counts of every rank's query equal to the oracle's.
+    B  the production shard geometry (`full_graph`, the graph the bench just timed, emptied first): a fixture sparse enough that no
+       two k-mers share a bit or counter, so the expected state follows from the k-mer multiplicities alone: popcount of all dbgbf
+       shares == distinct probe indices, non-zero counters == distinct counter indices of repeated k-mers, count of every queried
+       k-mer == its multiplicity.
+    Returns the dict that goes into the bench line; raises AssertionError on any difference."""
+    import rnabloom_b200 as rb
+    sys_path_tests = os.path.join(single.ROOT, "tests")
+    import sys
+    if sys_path_tests not in sys.path:
+        sys.path.insert(0, sys_path_tests)
+    from oracle.binding import MODE_CANON, Oracle, OracleGraph
+    from parity_util import all_bases, assert_cbf_close, np_slots
+    orc = Oracle()
+    k, hd, hc = single.K, single.HD, single.HC
+    out = {"n_ranks": world}
+    alive = []   # device buffers of every round stay allocated until the check is over (the calls only take raw pointers)
+
+    def dev(seqs):
+        alive.append(_DevReads(rb, seqs, device))
+        return alive[-1]
+    # ---- A ---------------------------------------------------------------------------------------------------------------------
+    dbg_bits, cbf_bytes, per_rank, per_round = small
+    q0, q1 = per_rank // 20, per_rank // 20 + per_rank // 10           # the queried / re-inserted reads
+    reads = [bytes(r).decode() for r in orc.synth_reads(71, 75 * per_rank * world // 2, 0, per_rank * world, 150, 6000)]
+    reads[3] = reads[3][:70] + "N" + reads[3][71:]
+    mine = reads[rank::world]
+    sg = make_graph(dbg_bits, cbf_bytes, per_round * 126)
+    for r in range(0, per_rank, per_round):
+        sg.add_round(dev(mine[r:r + per_round]).args, 0)
+    again = mine[:q1] + mine[:q1 // 2]
+    for r in range(0, len(again), per_round):
+        sg.add_round(dev(again[r:r + per_round]).args, 0)
+    dq = dev(mine[q0:q1])
+    sg.add_round(dq.args, rb.ADD_COUNT_IF_PRESENT)
+    sg.add_round(dq.args, rb.DBG_ONLY)
+    sg.check_overflow()
+    n_inst = sum(max(0, len(s) - k + 1) for s in mine[q0:q1])
+    counts = torch.zeros(n_inst, dtype=torch.float32, device=device)
+    fh = torch.zeros(n_inst, dtype=torch.int64, device=device)
+    assert sg.count_round(dq.args, counts, fh) == n_inst
+    sg.check_overflow()
+    if device.type == "cuda":
+        torch.cuda.synchronize()
+    dbg = sg.gather_filter(rb.RB_DBGBF, (dbg_bits + 7) // 8)
+    cbf = sg.gather_filter(rb.RB_CBF, cbf_bytes)
+    og = OracleGraph(orc, dbg_bits, cbf_bytes, 64, hd, hc, 1, k, False, False)
+    for s in reads:
+        og.add_read(s)
+    for r in range(world):
+        m = reads[r::world]
+        for s in m[:q1] + m[:q1 // 2]:
+            og.add_read(s)
+    for r in range(world):
+        for s in reads[r::world][q0:q1]:
+            og.add_read(s, flags=2)
+    assert og.cbf().max() <= 16, "parity fixture reached the probabilistic MiniFloat range"
+    assert (dbg == og.dbgbf()).all(), "rank %d: gathered dbgbf differs from the oracle" % rank
+    assert_cbf_close(cbf, og.cbf(), all_bases(orc, reads, k, [MODE_CANON]), k, hc, cbf_bytes)
+    want = np.concatenate([og.count_seq(s)[0] for s in mine[q0:q1]])
+    wantf = np.concatenate([og.count_seq(s)[1] for s in mine[q0:q1]])
+    got = counts.cpu().numpy()
+    assert (fh.cpu().numpy() == wantf).all(), "rank %d: forward hashes differ" % rank
+    frac = float((got == want).mean())
+    assert frac > 0.999, "rank %d: getKmers counts differ from the oracle (%.5f equal)" % (rank, frac)
+    out.update({"dbgbf": "equal", "cbf": "equal up to shared counters (%d of %d bytes differ)" % (int((cbf != og.cbf()).sum()), cbf_bytes),
+                "counts_equal_frac": frac, "small": {"dbgbf_bits": dbg_bits, "cbf_bytes": cbf_bytes, "reads_per_rank": per_rank + len(again) + 2 * (q1 - q0)}})
+    og.close()
+    sg.close()
+    # ---- B ---------------------------------------------------------------------------------------------------------------------
+    if full_graph is not None:
+        fg = full_graph
+        fg.clear()
+        n_b = n_full
+        n_r, n_qr = n_b // 4, (3 * n_b) // 10
+        reads = [bytes(r).decode() for r in orc.synth_reads(73, 50 * n_b * world, 0, n_b * world, 150, 4000)]
+        mine = reads[rank::world]
+        dr = dev(mine)
+        fg.add_round(dr.args, 0)
+        dr2 = dev(mine[:n_r])
+        fg.add_round(dr2.args, 0)
+        fg.check_overflow()
+        n_q = sum(max(0, len(s) - k + 1) for s in mine[:n_qr])
+        counts = torch.zeros(n_q, dtype=torch.float32, device=device)
+        dq = dev(mine[:n_qr])
+        assert fg.count_round(dq.args, counts) == n_q
+        fg.check_overflow()
+        pops = torch.tensor([fg.popcount(rb.RB_DBGBF), fg.popcount(rb.RB_CBF)], dtype=torch.int64, device=device)
+        dist.all_reduce(pops)
+        bases = np.concatenate([orc.kmer_hashes(s, k, MODE_CANON)[2] for s in reads] +
+                               [orc.kmer_hashes(s, k, MODE_CANON)[2] for r in range(world) for s in reads[r::world][:n_r]])
+        keys, mult = np.unique(bases, return_counts=True)
+        assert mult.max() <= 17
+        sd = np_slots(keys, k, hd, full_dbg_bits)
+        sc = np_slots(keys, k, hc, full_cbf_bytes)
+        # sparse fixture: k-mers that share a bit or a counter with another k-mer are vanishingly few; they only loosen the bounds
+        n_bits = len(np.unique(sd.reshape(-1)))
+        rep = sc[mult >= 2].reshape(-1)
+        n_cnt = len(np.unique(rep))
+        shared_c = sc.size - len(np.unique(sc.reshape(-1)))
+        assert int(pops[0]) == n_bits, "dbgbf popcount over all shares %d != distinct probe indices %d" % (int(pops[0]), n_bits)
+        assert abs(int(pops[1]) - n_cnt) <= shared_c, "cbf non-zero counters %d != %d" % (int(pops[1]), n_cnt)
+        mq = np.concatenate([orc.kmer_hashes(s, k, MODE_CANON)[2] for s in mine[:n_qr]])
+        want = mult[np.searchsorted(keys, mq)].astype(np.float32)
+        got = counts.cpu().numpy()
+        frac_b = float((got == want).mean())
+        assert frac_b > 0.9999, "full geometry: counts differ from the k-mer multiplicities (%.6f equal)" % frac_b
+        out["full_geometry"] = {"dbgbf_bits": full_dbg_bits, "cbf_bytes": full_cbf_bytes, "reads": (n_b + n_r) * world,
+                                "dbgbf_popcount": int(pops[0]), "expected": n_bits, "cbf_nonzero": int(pops[1]), "expected_cbf": n_cnt,
+                                "counts_equal_frac": frac_b}
+    return out
+
+
 def run_sharded(args, rank, world, local_rank):
     import rnabloom_b200 as rb
     from rnabloom_b200.sharded import GpuBackend, ShardedGraph, SlicedBackend, SlicedShardedGraph
@@ -125,6 +265,26 @@ def run_sharded(args, rank, world, local_rank):
         e2e = {"value": nk_rank * world * e_steps / float(te.item()), "unit": "k-mers/s", "h2d_bytes_per_step": words * 8 * world,
                "d2h_bytes_per_step": nk_rank * 4 * world, "steps": e_steps}
 
+    # ---- correctness of the path that was just timed: oracle comparison over NCCL (all ranks; a difference fails the run) -----------------
+    parity = None
+    if sliced and not getattr(args, "no_parity", False):
+        def make_graph(db, cb, max_kmers):
+            b2 = SlicedBackend(ctx, world, rank, db, cb, single.HD, single.HC, K, False, max_kmers)
+            return SlicedShardedGraph(b2, rank, world)
+        try:
+            parity = sharded_parity_check(make_graph, rank, world, torch.device("cuda", local_rank), dbg_bits, cbf_bytes, sg)
+            ok = 1
+        except AssertionError as e:
+            parity = {"n_ranks": world, "error": str(e)}
+            ok = 0
+        okt = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        if not int(okt.item()) and ok:
+            parity = {"n_ranks": world, "error": "another rank reported a difference"}
+        parity_ok = bool(int(okt.item()))
+    else:
+        parity_ok = True
+
     if rank == 0:
         clocks = sampler.stop()
         hbm, peak_src = single.peaks()
@@ -142,8 +302,13 @@ def run_sharded(args, rank, world, local_rank):
                              "peak": hbm, "unit": "GB/s", "frac": value / world * single.A_STEP / 1e9 / hbm, "traffic": None,
                              "peak_source": peak_src, "insert_gkmers_s": nk_rank * world * args.steps / t_ins / 1e6,
                              "lookup_gkmers_s": nk_rank * world * args.steps / t_look / 1e6},
-                "cpu_baseline": None, "wall_s_timed_region": wall_ms / 1e3}
+                "cpu_baseline": None, "wall_s_timed_region": wall_ms / 1e3, "parity_check": parity}
         print(json.dumps(line), flush=True)
+    elif parity is not None and "error" in parity:
+        import sys
+        print("rank %d parity: %s" % (rank, parity["error"]), file=sys.stderr, flush=True)
     be.close()
     ctx.close()
     dist.destroy_process_group()
+    if not parity_ok:
+        raise SystemExit(3)

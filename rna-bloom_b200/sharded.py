@@ -278,12 +278,16 @@ class SlicedBackend:
         self.ctx.check(self.L.rb_sshard_overflow(self.h, C.byref(f)))
         return bool(f.value)
 
-    def download(self, which):
+    def share(self, which):
+        """This rank's share of a filter as a (non-owning) BloomFilter / CountingBloomFilter."""
         from .filters import BloomFilter, CountingBloomFilter
         h = C.c_void_p()
         self.ctx.check(self.L.rb_sshard_filter(self.h, which, C.byref(h)))
         cls = BloomFilter if which == B.RB_DBGBF else CountingBloomFilter
-        return cls(self.ctx, 0, 0, 0, _handle=h).download()
+        return cls(self.ctx, 0, 0, 0, _handle=h)
+
+    def download(self, which):
+        return self.share(which).download()
 
 
 class SlicedShardedGraph:
@@ -371,6 +375,18 @@ class SlicedShardedGraph:
             dist.all_reduce(self.flag, op=dist.ReduceOp.MAX, group=self.group)
         if int(self.flag.item()):
             raise RBError(-6, "sharded graph: a raise region overflowed; lower max_kmers_per_round")
+
+    def close(self):
+        self.be.close()
+
+    def clear(self):
+        """graph.clearDbgbf + clearCbf (graph :211-230) on this rank's shares."""
+        self.be.share(B.RB_DBGBF).empty()
+        self.be.share(B.RB_CBF).empty()
+
+    def popcount(self, which):
+        """Set bits (dbgbf) / non-zero counters (cbf) of this rank's share; the caller sums over the ranks."""
+        return self.be.share(which).getPopCount()
 
     def gather_filter(self, which, total_bytes):
         """Concatenate the ranks' shares -> the reference's single byte array (valid on every rank)."""

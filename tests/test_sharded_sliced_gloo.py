@@ -157,3 +157,42 @@ def test_sharded_sliced_graph_random_configurations(tmp_path, orc, seed):
         mine = reads[r::world][:40]
         wantf = np.concatenate([og.count_seq(s)[1] for s in mine if len(s) >= k])
         assert (np.load(tmp_path / ("fh%d.npy" % r)) == wantf).all()
+
+
+def _parity_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), **SLICE_ENV)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import rnabloom_b200 as rb
+        from rnabloom_b200 import binding as B
+        from rnabloom_b200.sharded import SlicedBackend, SlicedShardedGraph
+        from test_emu_parity import EMU_SO
+        import bench_multi
+        B._lib = B.bind(EMU_SO, allow_missing=True)
+        ctx = rb.Context(0)
+        cpu = torch.device("cpu")
+
+        def make_graph(db, cb, max_kmers):
+            return SlicedShardedGraph(SlicedBackend(ctx, world, rank, db, cb, 3, 3, 25, False, max_kmers, device=cpu), rank, world)
+        full_d, full_c = 1 << 27, 1 << 24
+        full = make_graph(full_d, full_c, 40000)
+        res = bench_multi.sharded_parity_check(make_graph, rank, world, cpu, full_d, full_c, full, small=(3_000_017, 1_000_003, 120, 40), n_full=120)
+        if rank == 0:
+            import json
+            with open(os.path.join(out, "parity.json"), "w") as fh:
+                json.dump(res, fh)
+        full.close(), ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bench_parity_check_runs_at_world_2(tmp_path):
+    """bench_multi.sharded_parity_check -- the oracle comparison `bench.py --gpus N` runs after its timed region -- on 2 gloo ranks over
+    the emulated kernels: the checker itself is exercised without a GPU (fixtures scaled down, same code path)."""
+    import json
+    from test_emu_parity import build_emu
+    build_emu()
+    port = 35500 + os.getpid() % 2000
+    mp.spawn(_parity_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    res = json.load(open(tmp_path / "parity.json"))
+    assert res["dbgbf"] == "equal" and res["counts_equal_frac"] > 0.999 and res["full_geometry"]["counts_equal_frac"] > 0.9999
