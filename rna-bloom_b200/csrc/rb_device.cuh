@@ -212,8 +212,9 @@ __device__ __forceinline__ int cbf_increment(const ByteFilter& cbf, uint64_t bas
     }
 }
 
-// a11 getCount (bloom/CountingBloomFilter.java:235-251): MiniFloat of the minimum slot
-template <int MAXH>
+// a11 getCount (bloom/CountingBloomFilter.java:235-251): MiniFloat of the minimum slot.  IGNORE_LOCK: called from a kernel that also
+// increments (slots may carry the transient lock bit of another thread's increment): compare the 7 value bits only.
+template <int MAXH, bool IGNORE_LOCK = false>
 __device__ __forceinline__ int cbf_min(const ByteFilter& cbf, uint64_t base, const HashMults& hm) {
     uint32_t w[MAXH];
     uint64_t idx[MAXH];
@@ -223,7 +224,11 @@ __device__ __forceinline__ int cbf_min(const ByteFilter& cbf, uint64_t base, con
     int mn = 127;
 #pragma unroll
     for (int h = 0; h < MAXH; ++h)
-        if (h < cbf.num_hash) { const int v = byte_of(w[h], (int)(idx[h] & 3) * 8); mn = v < mn ? v : mn; }
+        if (h < cbf.num_hash) {
+            int v = byte_of(w[h], (int)(idx[h] & 3) * 8);
+            if (IGNORE_LOCK) v &= 0x7F;
+            mn = v < mn ? v : mn;
+        }
     return mn;
 }
 

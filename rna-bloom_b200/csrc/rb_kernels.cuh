@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(kThreads) k_hash_op(const int64_t* __restrict_
     else if (OP == OP_GRAPH_ADD) {
         if (bf_lookup_then_add<MAXH>(gd.dbg, gd.ct, b, gd.hm)) cbf_increment<MAXH>(gd.cbf, b, gd.hm, (mix64(b ^ gd.rng_seed) + (uint64_t)i * 0x632BE59BD9B4E019ULL), nullptr);
     } else if (OP == OP_GRAPH_COUNT_IF_PRESENT) {
-        if (bf_lookup<MAXH>(gd.dbg, b, gd.hm) && minifloat_to_float(cbf_min<MAXH>(gd.cbf, b, gd.hm) & 0x7F) > 0.f)
+        if (bf_lookup<MAXH>(gd.dbg, b, gd.hm) && cbf_min<MAXH, true>(gd.cbf, b, gd.hm) > 0)   // graph :424-428; a locked slot is not a smaller one
             cbf_increment<MAXH>(gd.cbf, b, gd.hm, (mix64(b ^ gd.rng_seed) + (uint64_t)i * 0x632BE59BD9B4E019ULL), nullptr);
     } else if (OP == OP_GRAPH_COUNT) {
         outf[i] = bf_lookup<MAXH>(gd.dbg, b, gd.hm) ? minifloat_to_float(cbf_min<MAXH>(gd.cbf, b, gd.hm)) + 1.f : 0.f;

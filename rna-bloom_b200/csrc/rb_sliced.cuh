@@ -39,8 +39,21 @@ namespace rb {
 
 constexpr int kSlThreads = 256;        // every kernel here runs 256-thread CTAs (cta_exclusive_scan relies on it)
 constexpr int kSlMaxH = 3;             // hashes per filter the engine is built for
-constexpr int kSlNJ = 2 * kSlMaxH;     // probe slots per k-mer: dbgbf hashes at 0..2, cbf hashes at 3..5
-constexpr int kSlRoundKmers = 4;       // k-mers per thread and sort round
+constexpr int kSlNJ = 2 * kSlMaxH;     // probe slots per k-mer, separate records: dbgbf hashes at 0..2, cbf hashes at 3..5
+constexpr int kSlRoundKmers = 4;       // k-mers per thread and sort round (key sorts; probe sorts: SlShape<NJ>::KPT)
+constexpr int kSlTileRecords = 24;     // probe records per thread and tile sort
+// Probe records per k-mer.  NJ = 6: one record per probe (any filter sizes).  NJ = 3 ("paired"): hash j of a k-mer indexes both
+// filters -- (h_j >>> 1) % dbg_bits and (h_j >>> 1) % cbf_bytes (bloom/BloomFilter.java:108-111, bloom/CountingBloomFilter.java:101-104) --
+// so when cbf_bytes is a power of two that divides dbg_bits the counter index is the bit index mod cbf_bytes, and ONE record per
+// hash serves both filters if a slice is cut as {counters [s*W, (s+1)*W)} + {bits whose index mod cbf_bytes falls in that range}
+// (dbg_bits / cbf_bytes chunks of W bits).  The answer byte carries both: bit 7 = the dbgbf bit, bits 0..6 = the counter (<= 127).
+// Half the records to sort, move and answer; the logical arrays are untouched.
+template <int NJ>
+struct SlShape {
+    static constexpr int KPT = kSlTileRecords / NJ;      // k-mers per thread and tile: 4 (NJ = 6) or 8 (NJ = 3)
+    static constexpr int TILE = kSlThreads * KPT;        // k-mers per tile: 1024 or 2048
+    static constexpr int PFX_PER = NJ == 3 ? 12 : 8;     // bases per thread of the prefix k-merizer's span
+};
 constexpr int kSlPad = 32;             // one cursor per 128 B line (atomics to one line serialise in L2)
 constexpr int kSlMaxRegions = 2048;    // bucket ids are kept in 12 bits, 0xFFF = no record
 constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
@@ -65,6 +78,11 @@ struct SlGeom {
     int dbg_log2, cbf_log2;   // slice sizes: 2^dbg_log2 bits, 2^cbf_log2 bytes
     int n_dbg, n_cbf;         // probe region = dbgbf slice, or n_dbg + cbf slice
     int raise_log2, n_raise;  // counter raises: record = slice-local byte index | value << raise_log2 (raise_log2 <= 25)
+    // paired records (NJ = 3): slice s = counters [s << pair_log2, (s + 1) << pair_log2) and, for every chunk c < dbg_bits / cbf_bytes,
+    // the bits c * cbf_bytes + the same range; record = chunk << pair_log2 | offset inside the slice.  n_dbg = n_cbf = 0, n_pair regions.
+    int paired, pair_log2, cbf_size_log2, n_pair;
+    uint64_t pair_local_c;    // counters (= bits per chunk) of the consumer's share: cbf_bytes on one GPU, shard_p << pair_log2 when sharded
+    int shard_p;              // paired slices per rank (sharded graph): region = global slice, owner = slice / shard_p
     // hash-sharded graph (rb_sshard_*, one process per GPU): rank r owns dbgbf slices [r * shard_d, (r+1) * shard_d) and cbf slices
     // [r * shard_c, ...); a producer's probe region = owner * (shard_d + shard_c) + (local dbgbf slice | shard_d + local cbf slice),
     // raise region = owner * shard_r + local raise slice.  A consumer sees the regions it received ordered by local region first,
@@ -219,33 +237,60 @@ struct TileSort {
     }
 };
 
-// the probes of one k-mer: slots 0..2 dbgbf, 3..5 cbf (bloom/hash/NTHash.java:518-527 + bloom/BloomFilter.java:108-111)
+// the probes of one k-mer (bloom/hash/NTHash.java:518-527 + bloom/BloomFilter.java:108-111).  NJ = 6: slots 0..2 dbgbf, 3..5 cbf;
+// NJ = 3: slot j = hash j against both filters (slots >= hc: the counter half of the answer is ignored)
+template <int NJ>
 __device__ __forceinline__ void sl_probes(const SlGeom& sg, const HashMults& hm, uint64_t base, bool with_cbf, int* bkt, uint32_t* rec) {
 #pragma unroll
     for (int j = 0; j < kSlMaxH; ++j) {
-        if (j < sg.hd) {
-            const uint64_t gi = fm_index(expand_hash(base, j, hm), sg.dbg_fm);
-            bkt[j] = sl_dbg_region(sg, gi);
-            rec[j] = (uint32_t)(gi & ((1ULL << sg.dbg_log2) - 1));
-        }
-        if (with_cbf && j < sg.hc) {
-            const uint64_t gi = fm_index(expand_hash(base, j, hm), sg.cbf_fm);
-            bkt[kSlMaxH + j] = sl_cbf_region(sg, gi);
-            rec[kSlMaxH + j] = (uint32_t)(gi & ((1ULL << sg.cbf_log2) - 1));
+        if (NJ == 3) {
+            if (j < sg.hd) {
+                const uint64_t gd = fm_index(expand_hash(base, j, hm), sg.dbg_fm);
+                const uint64_t gc = gd & sg.cbf_fm.mask;   // == (h_j >>> 1) % cbf_bytes: cbf_bytes is a power of two dividing dbg_bits
+                bkt[j] = (int)(gc >> sg.pair_log2);
+                rec[j] = (uint32_t)((gd >> sg.cbf_size_log2) << sg.pair_log2) | (uint32_t)(gc & ((1ULL << sg.pair_log2) - 1));
+            }
+        } else {
+            if (j < sg.hd) {
+                const uint64_t gi = fm_index(expand_hash(base, j, hm), sg.dbg_fm);
+                bkt[j] = sl_dbg_region(sg, gi);
+                rec[j] = (uint32_t)(gi & ((1ULL << sg.dbg_log2) - 1));
+            }
+            if (with_cbf && j < sg.hc) {
+                const uint64_t gi = fm_index(expand_hash(base, j, hm), sg.cbf_fm);
+                bkt[kSlMaxH + j] = sl_cbf_region(sg, gi);
+                rec[kSlMaxH + j] = (uint32_t)(gi & ((1ULL << sg.cbf_log2) - 1));
+            }
         }
     }
 }
-// the 6 places of one k-mer (or distinct key) are 24 contiguous, 8-byte aligned bytes of the position array
+// the NJ places of one k-mer (or distinct key) are 4 * NJ contiguous bytes of the position array
+template <int NJ>
 __device__ __forceinline__ void sl_store_places(uint32_t* pos, int64_t item, const uint32_t* place) {
-    uint2* dst = reinterpret_cast<uint2*>(pos + item * kSlNJ);
+    if (NJ % 2 == 0) {
+        uint2* dst = reinterpret_cast<uint2*>(pos + item * NJ);
 #pragma unroll
-    for (int q = 0; q < kSlNJ / 2; ++q) dst[q] = make_uint2(place[2 * q], place[2 * q + 1]);
+        for (int q = 0; q < NJ / 2; ++q) dst[q] = make_uint2(place[2 * q], place[2 * q + 1]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < NJ; ++q) pos[item * NJ + q] = place[q];
+    }
 }
+template <int NJ>
 __device__ __forceinline__ void sl_load_places(const uint32_t* pos, int64_t item, uint32_t* place) {
-    const uint2* src = reinterpret_cast<const uint2*>(pos + item * kSlNJ);
+    if (NJ % 2 == 0) {
+        const uint2* src = reinterpret_cast<const uint2*>(pos + item * NJ);
 #pragma unroll
-    for (int q = 0; q < kSlNJ / 2; ++q) { const uint2 v = __ldg(src + q); place[2 * q] = v.x; place[2 * q + 1] = v.y; }
+        for (int q = 0; q < NJ / 2; ++q) { const uint2 v = __ldg(src + q); place[2 * q] = v.x; place[2 * q + 1] = v.y; }
+    } else {
+#pragma unroll
+        for (int q = 0; q < NJ; ++q) place[q] = __ldg(pos + item * NJ + q);
+    }
 }
+// answer byte of a probe: bit 7 = the dbgbf bit (old value when test-and-set), bits 0..6 = the counter
+__device__ __forceinline__ bool sl_ans_bit(uint32_t a) { return (a & 0x80u) != 0; }
+template <int NJ>
+__device__ __forceinline__ int sl_ans_counter(const uint32_t* a, int h) { return (int)((NJ == 3 ? a[h] : a[kSlMaxH + h]) & 0x7Fu); }
 // The answers of a tile: its records sit in one run per bucket of the answer array (where the tile sort put them); the runs are
 // copied into shared memory in bucket order -- one warp per run, consecutive lanes read consecutive bytes -- and every thread
 // then picks its answers up at start[bucket] + rank.  (A per-record gather from global memory costs ~2 L1TEX cycles per
@@ -280,14 +325,14 @@ struct TileAnswers {
 // this sum evaluated incrementally).  Masked / non-ACGT bases contribute 0 exactly as in the walker (NTHash.java:39-43 "N" seed),
 // and a prefix count of them gives the number of unusable bases in any window.  The span (garbage between reads included:
 // it cancels in Pf(x+k) ^ Pf(x)) is scanned once per CTA: 8 bases per thread, warp-shuffle XOR-scan of the thread totals.
-constexpr int kPfxPer = 8;
-constexpr int kPfxSpan = kSlThreads * kPfxPer;   // bases a CTA can cover
-constexpr int kSlTile = kSlThreads * kSlRoundKmers;   // k-mer positions per CTA of the uniform-layout kernels
+constexpr int kSlTile = kSlThreads * kSlRoundKmers;   // k-mer positions per CTA of the uniform-layout key kernel
+template <int PER, int TILE>   // PER bases per thread of the span, TILE k-mer positions per CTA
 struct PrefixKmerizer {
-    unsigned long long *lf, *lr, *of, *orv;   // [kPfxSpan + 8] thread-local exclusive prefixes, [257] thread offsets
+    static constexpr int kSpan = kSlThreads * PER;   // bases a CTA can cover
+    unsigned long long *lf, *lr, *of, *orv;   // [kSpan + 8] thread-local exclusive prefixes, [257] thread offsets
     uint16_t* lb; uint32_t* ob;               // masked-base counts
     int64_t abs_lo;
-    static size_t smem_bytes() { return (size_t)(kPfxSpan + 8) * 16 + 264 * 16 + (size_t)(kPfxSpan + 8) * 2 + 264 * 4 + 3 * kSlWarps * 8; }
+    static __host__ __device__ size_t smem_bytes() { return (size_t)(kSpan + 8) * 16 + 264 * 16 + (size_t)(kSpan + 8) * 2 + 264 * 4 + 3 * kSlWarps * 8; }
     __device__ __forceinline__ int64_t abs_of(const Ingest& g, int64_t p) const {   // first base of launch-local position p
         const int64_t read = p / g.uniform_npos;
         return g.first_base + read * g.uniform_stride + (p - read * g.uniform_npos);
@@ -296,23 +341,23 @@ struct PrefixKmerizer {
     template <int MODE>
     __device__ __forceinline__ void build(unsigned char* smem, const Ingest& g, int k, int64_t tile0) {
         lf = reinterpret_cast<unsigned long long*>(smem);
-        lr = lf + (kPfxSpan + 8);
-        of = lr + (kPfxSpan + 8);
+        lr = lf + (kSpan + 8);
+        of = lr + (kSpan + 8);
         orv = of + 264;
         unsigned long long* wtot = orv + 264;                     // [3 * kSlWarps]
         lb = reinterpret_cast<uint16_t*>(wtot + 3 * kSlWarps);
-        ob = reinterpret_cast<uint32_t*>(lb + (kPfxSpan + 8));
+        ob = reinterpret_cast<uint32_t*>(lb + (kSpan + 8));
         const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-        const int64_t last = min(tile0 + kSlTile, g.n_pos) - 1;
+        const int64_t last = min(tile0 + TILE, g.n_pos) - 1;
         abs_lo = abs_of(g, tile0);
-        const int span = (int)(abs_of(g, last) + k - abs_lo);   // <= kPfxSpan (the host checks the layout)
+        const int span = (int)(abs_of(g, last) + k - abs_lo);   // <= kSpan (the host checks the layout)
         BaseCursor cur;
-        cur.seek(g.packed, g.mask, abs_lo + (int64_t)t * kPfxPer);
+        cur.seek(g.packed, g.mask, abs_lo + (int64_t)t * PER);
         unsigned long long xf = 0, xr = 0;
         uint32_t xb = 0;
 #pragma unroll
-        for (int i = 0; i < kPfxPer; ++i) {
-            const int x = t * kPfxPer + i;
+        for (int i = 0; i < PER; ++i) {
+            const int x = t * PER + i;
             lf[x] = xf; lr[x] = xr; lb[x] = (uint16_t)xb;
             if (x < span) {
                 const int c = cur.next();
@@ -340,7 +385,7 @@ struct PrefixKmerizer {
         of[t] = ef; orv[t] = er; ob[t] = eb;
         if (t == kSlThreads - 1) {
             of[kSlThreads] = ef ^ xf; orv[kSlThreads] = er ^ xr; ob[kSlThreads] = eb + xb;
-            lf[kPfxSpan] = 0; lr[kPfxSpan] = 0; lb[kPfxSpan] = 0;
+            lf[kSpan] = 0; lr[kSpan] = 0; lb[kSpan] = 0;
         }
         __syncthreads();
     }
@@ -348,10 +393,11 @@ struct PrefixKmerizer {
     template <int MODE>
     __device__ __forceinline__ void eval(const Ingest& g, int k, int64_t p, uint64_t& f, uint64_t& r, int& bad) const {
         const int x = (int)(abs_of(g, p) - abs_lo), y = x + k;
+        const int tx = x / PER, ty = y / PER;
         f = 0; r = 0;
-        if (MODE != 1) f = rotl64((lf[y] ^ of[y >> 3]) ^ (lf[x] ^ of[x >> 3]), (y - 1) & 63);
-        if (MODE != 0) r = rotr64((lr[y] ^ orv[y >> 3]) ^ (lr[x] ^ orv[x >> 3]), x & 63);
-        bad = (int)((lb[y] + ob[y >> 3]) - (lb[x] + ob[x >> 3]));
+        if (MODE != 1) f = rotl64((lf[y] ^ of[ty]) ^ (lf[x] ^ of[tx]), (y - 1) & 63);
+        if (MODE != 0) r = rotr64((lr[y] ^ orv[ty]) ^ (lr[x] ^ orv[tx]), x & 63);
+        bad = (int)((lb[y] + ob[ty]) - (lb[x] + ob[tx]));
     }
     template <int MODE>
     static __device__ __forceinline__ uint64_t base_of(uint64_t f, uint64_t r) {
@@ -360,106 +406,123 @@ struct PrefixKmerizer {
         return ((int64_t)r < (int64_t)f) ? r : f;   // canonical: signed min (NTHash.java:494)
     }
 };
+using KeyKmerizer = PrefixKmerizer<8, kSlTile>;
 
-// ---- S1 (uniform layout): one CTA = 1024 consecutive k-mer positions, hashed through the prefix arrays, one tile sort -------------------
-template <int MODE>
+// ---- S1 (uniform layout): one CTA = SlShape<NJ>::TILE consecutive k-mer positions, hashed through the prefix arrays, one tile sort ------
+template <int MODE, int NJ>
 __global__ void __launch_bounds__(kSlThreads) ks_route_lookup_u(const Ingest g, int k, const HashMults hm, const SlGeom sg, const SlArena arena,
                                                                uint32_t* __restrict__ pos, uint2* __restrict__ tile_meta, int64_t* __restrict__ fhash,
                                                                int64_t* __restrict__ rhash, int* overflow) {
     RB_DYN_SMEM(unsigned char, sl_smem);
-    const int64_t tile0 = (int64_t)blockIdx.x * kSlTile;
-    PrefixKmerizer pk;
-    pk.build<MODE>(sl_smem, g, k, tile0);
+    constexpr int KPT = SlShape<NJ>::KPT, TILE = SlShape<NJ>::TILE;
+    using PK = PrefixKmerizer<SlShape<NJ>::PFX_PER, TILE>;
+    const int64_t tile0 = (int64_t)blockIdx.x * TILE;
+    PK pk;
+    pk.template build<MODE>(sl_smem, g, k, tile0);
     // item i of thread t = position tile0 + i * 256 + t: consecutive lanes read consecutive prefix entries (no bank conflicts) and
-    // write consecutive 24-byte place records
-    int bkt[kSlRoundKmers * kSlNJ];
-    uint32_t rec[kSlRoundKmers * kSlNJ], slot[kSlRoundKmers * kSlNJ];
+    // write consecutive place records
+    int bkt[KPT * NJ];
+    uint32_t rec[KPT * NJ], slot[KPT * NJ];
 #pragma unroll
-    for (int i = 0; i < kSlRoundKmers; ++i) {
+    for (int i = 0; i < KPT; ++i) {
         const int64_t p = tile0 + i * kSlThreads + threadIdx.x;
 #pragma unroll
-        for (int j = 0; j < kSlNJ; ++j) { bkt[i * kSlNJ + j] = -1; rec[i * kSlNJ + j] = 0; }
+        for (int j = 0; j < NJ; ++j) { bkt[i * NJ + j] = -1; rec[i * NJ + j] = 0; }
         if (p < g.n_pos) {
             uint64_t f, r; int bad;
-            pk.eval<MODE>(g, k, p, f, r, bad);
+            pk.template eval<MODE>(g, k, p, f, r, bad);
             if (fhash) fhash[g.out_base + p] = (int64_t)f;
             if (rhash) rhash[g.out_base + p] = (int64_t)r;
-            if (bad == 0) sl_probes(sg, hm, PrefixKmerizer::base_of<MODE>(f, r), true, &bkt[i * kSlNJ], &rec[i * kSlNJ]);
+            if (bad == 0) sl_probes<NJ>(sg, hm, PK::template base_of<MODE>(f, r), true, &bkt[i * NJ], &rec[i * NJ]);
         }
     }
     __syncthreads();   // the tile sort reuses the shared memory of the prefix arrays
-    TileSort<uint32_t, kSlRoundKmers * kSlNJ> ts;
+    TileSort<uint32_t, KPT * NJ> ts;
     ts.init(sl_smem, arena.B);
     ts.run(arena, 0, bkt, rec, slot, overflow, tile_meta + (size_t)blockIdx.x * (arena.B + 1));
 #pragma unroll
-    for (int i = 0; i < kSlRoundKmers; ++i) {
+    for (int i = 0; i < KPT; ++i) {
         const int64_t p = tile0 + i * kSlThreads + threadIdx.x;
-        if (p < g.n_pos) sl_store_places(pos, p, &slot[i * kSlNJ]);
+        if (p < g.n_pos) sl_store_places<NJ>(pos, p, &slot[i * NJ]);
     }
 }
 // ---- I1 (uniform layout) -------------------------------------------------------------------------------------------------------------------
+// One CTA = kKeyTile consecutive positions: kKeySub passes of the prefix k-merizer (1024 positions each, 4 keys per thread kept in
+// registers), then ONE tile sort of 16 keys per thread -- the per-bucket work of a sort (zeroing, scan, one global cursor bump per
+// bucket) is as large as its per-record work when a tile holds about as many keys as there are ranges.
+constexpr int kKeySub = 4;
+constexpr int kKeyE = kSlRoundKmers * kKeySub;    // keys per thread and tile sort
+constexpr int kKeyTile = kSlTile * kKeySub;       // 4096
 template <int MODE>
 __global__ void __launch_bounds__(kSlThreads) ks_route_keys_u(const Ingest g, int k, int n_ranges, int range_shift, const SlArena arena, int* overflow) {
     RB_DYN_SMEM(unsigned char, sl_smem);
-    const int64_t tile0 = (int64_t)blockIdx.x * kSlTile;
-    PrefixKmerizer pk;
-    pk.build<MODE>(sl_smem, g, k, tile0);
-    int bkt[kSlRoundKmers];
-    unsigned long long rec[kSlRoundKmers];
-    uint32_t slot[kSlRoundKmers];
+    const int64_t tile0 = (int64_t)blockIdx.x * kKeyTile;
+    int bkt[kKeyE];
+    unsigned long long rec[kKeyE];
+    uint32_t slot[kKeyE];
 #pragma unroll
-    for (int i = 0; i < kSlRoundKmers; ++i) {
-        const int64_t p = tile0 + i * kSlThreads + threadIdx.x;
-        bkt[i] = -1; rec[i] = 0;
-        if (p < g.n_pos) {
-            uint64_t f, r; int bad;
-            pk.eval<MODE>(g, k, p, f, r, bad);
-            if (bad == 0) {
-                const uint64_t b = PrefixKmerizer::base_of<MODE>(f, r);
-                rec[i] = b;
-                bkt[i] = n_ranges > 1 ? (int)(sl_mixkey(b) >> range_shift) : 0;
+    for (int s = 0; s < kKeySub; ++s) {
+        const int64_t sub0 = tile0 + (int64_t)s * kSlTile;
+#pragma unroll
+        for (int i = 0; i < kSlRoundKmers; ++i) { bkt[s * kSlRoundKmers + i] = -1; rec[s * kSlRoundKmers + i] = 0; }
+        if (sub0 < g.n_pos) {   // the whole CTA
+            KeyKmerizer pk;
+            pk.build<MODE>(sl_smem, g, k, sub0);
+#pragma unroll
+            for (int i = 0; i < kSlRoundKmers; ++i) {
+                const int64_t p = sub0 + i * kSlThreads + threadIdx.x;
+                if (p < g.n_pos) {
+                    uint64_t f, r; int bad;
+                    pk.eval<MODE>(g, k, p, f, r, bad);
+                    if (bad == 0) {
+                        const uint64_t b = KeyKmerizer::base_of<MODE>(f, r);
+                        rec[s * kSlRoundKmers + i] = b;
+                        bkt[s * kSlRoundKmers + i] = n_ranges > 1 ? (int)(sl_mixkey(b) >> range_shift) : 0;
+                    }
+                }
             }
+            __syncthreads();   // the next pass (or the tile sort) reuses the shared memory of the prefix arrays
         }
     }
-    __syncthreads();
-    TileSort<unsigned long long, kSlRoundKmers, true> ts;
+    TileSort<unsigned long long, kKeyE, true> ts;
     ts.init(sl_smem, arena.B);
     ts.run(arena, 0, bkt, rec, slot, overflow, nullptr);
 }
 
 // ---- S1: k-merise, tile-sort the probes of every usable k-mer instance by filter slice --------------------------------------------
-template <int MODE>
+template <int MODE, int NJ>
 __global__ void __launch_bounds__(kSlThreads) ks_route_lookup(const Ingest g, int k, const HashMults hm, const SlGeom sg, const SlArena arena,
                                                              uint32_t* __restrict__ pos, uint2* __restrict__ tile_meta, int64_t* __restrict__ fhash,
                                                              int64_t* __restrict__ rhash, int* overflow) {
     RB_DYN_SMEM(unsigned char, sl_smem);
+    constexpr int KPT = SlShape<NJ>::KPT;
     __shared__ RollLut lut;
     build_lut(&lut, k);
-    TileSort<uint32_t, kSlRoundKmers * kSlNJ> ts;
+    TileSort<uint32_t, KPT * NJ> ts;
     ts.init(sl_smem, arena.B);
     const int64_t pos0 = ((int64_t)blockIdx.x * kSlThreads + threadIdx.x) * kChunk;
     const int n = pos0 < g.n_pos ? (int)min((int64_t)kChunk, g.n_pos - pos0) : 0;
     PositionWalker<MODE> pw;
     if (n) pw.start(g, pos0, k, lut);
 #pragma unroll 1
-    for (int r0 = 0; r0 < kChunk; r0 += kSlRoundKmers) {
-        int bkt[kSlRoundKmers * kSlNJ];
-        uint32_t rec[kSlRoundKmers * kSlNJ], slot[kSlRoundKmers * kSlNJ];
+    for (int r0 = 0; r0 < kChunk; r0 += KPT) {
+        int bkt[KPT * NJ];
+        uint32_t rec[KPT * NJ], slot[KPT * NJ];
 #pragma unroll
-        for (int i = 0; i < kSlRoundKmers; ++i) {
+        for (int i = 0; i < KPT; ++i) {
 #pragma unroll
-            for (int j = 0; j < kSlNJ; ++j) { bkt[i * kSlNJ + j] = -1; rec[i * kSlNJ + j] = 0; }
+            for (int j = 0; j < NJ; ++j) { bkt[i * NJ + j] = -1; rec[i * NJ + j] = 0; }
             if (r0 + i < n) {
                 pw.advance(g, k, lut);
                 const int64_t o = g.out_base + pos0 + r0 + i;
                 if (fhash) fhash[o] = (int64_t)pw.wk.f;
                 if (rhash) rhash[o] = (int64_t)pw.wk.r;
-                if (pw.wk.bad == 0) sl_probes(sg, hm, pw.wk.base(), true, &bkt[i * kSlNJ], &rec[i * kSlNJ]);
+                if (pw.wk.bad == 0) sl_probes<NJ>(sg, hm, pw.wk.base(), true, &bkt[i * NJ], &rec[i * NJ]);
             }
         }
-        ts.run(arena, 0, bkt, rec, slot, overflow, tile_meta + ((size_t)blockIdx.x * (kChunk / kSlRoundKmers) + r0 / kSlRoundKmers) * (arena.B + 1));
+        ts.run(arena, 0, bkt, rec, slot, overflow, tile_meta + ((size_t)blockIdx.x * (kChunk / KPT) + r0 / KPT) * (arena.B + 1));
 #pragma unroll
-        for (int i = 0; i < kSlRoundKmers; ++i) if (r0 + i < n) sl_store_places(pos, pos0 + r0 + i, &slot[i * kSlNJ]);
+        for (int i = 0; i < KPT; ++i) if (r0 + i < n) sl_store_places<NJ>(pos, pos0 + r0 + i, &slot[i * NJ]);
     }
 }
 
@@ -522,7 +585,38 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
     __shared__ int s_c;
     for (int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c); c < total; c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c)) {
         const SlWork w = sl_work_item(arena, pre, c);
-        const int lr = w.b / sg.region_div;   // local region: dbgbf slices first, then cbf slices
+        const int lr = w.b / sg.region_div;   // local region: dbgbf slices first, then cbf slices -- or paired slices
+        if (sg.paired) {
+            // record = chunk << pair_log2 | offset: counter byte (lr << pair_log2) + offset, bit chunk * pair_local_c + the same
+            const uint64_t byte0 = (uint64_t)lr << sg.pair_log2;
+            const uint32_t off_mask = (1u << sg.pair_log2) - 1u;
+            for (uint32_t i0 = threadIdx.x; i0 < w.n; i0 += kSlThreads * U) {
+                uint32_t li[U], wd[U], wc[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) li[u] = (i0 + u * kSlThreads < w.n) ? __ldcs(rec + w.first + i0 + u * kSlThreads) : 0u;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    wd[u] = 0; wc[u] = 0;
+                    if (i0 + u * kSlThreads < w.n) {
+                        const uint64_t ci = byte0 + (li[u] & off_mask);
+                        const uint64_t bi = (uint64_t)(li[u] >> sg.pair_log2) * sg.pair_local_c + ci;
+                        wd[u] = ld_cg(dbg_words + (bi >> 5));
+                        wc[u] = ld_cg(cbf_words + (ci >> 2));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (i0 + u * kSlThreads < w.n) {
+                        const uint64_t ci = byte0 + (li[u] & off_mask);
+                        const uint64_t bi = (uint64_t)(li[u] >> sg.pair_log2) * sg.pair_local_c + ci;
+                        const uint32_t bit = 1u << (bi & 31);
+                        if (SET && !(wd[u] & bit)) wd[u] = atomicOr(dbg_words + (bi >> 5), bit);
+                        ans[w.first + i0 + u * kSlThreads] = (uint8_t)(((wd[u] & bit) ? 0x80u : 0u) | ((wc[u] >> ((ci & 3) * 8)) & 0x7Fu));
+                    }
+                }
+            }
+            continue;
+        }
         const bool is_dbg = lr < sg.n_dbg;
         const int64_t word0 = is_dbg ? ((int64_t)lr << (sg.dbg_log2 - 5)) : ((int64_t)(lr - sg.n_dbg) << (sg.cbf_log2 - 2));
         for (uint32_t i0 = threadIdx.x; i0 < w.n; i0 += kSlThreads * U) {
@@ -541,9 +635,9 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
                     if (is_dbg) {
                         const uint32_t bit = 1u << (li[u] & 31);
                         if (SET && !(wd[u] & bit)) wd[u] = atomicOr(dbg_words + word0 + (li[u] >> 5), bit);
-                        value = (wd[u] & bit) ? 1u : 0u;
+                        value = (wd[u] & bit) ? 0x80u : 0u;
                     } else {
-                        value = (wd[u] >> ((li[u] & 3) * 8)) & 0xFFu;
+                        value = (wd[u] >> ((li[u] & 3) * 8)) & 0x7Fu;
                     }
                     ans[w.first + i0 + u * kSlThreads] = (uint8_t)value;
                 }
@@ -557,44 +651,48 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
 // k-mers per CTA; FLAT = 0: ks_route_lookup, 16 consecutive k-mers per thread in 4 rounds): the answers of a CTA round sit in
 // the few hundred runs its tile sort wrote, so the 32 B sectors a CTA gathers from are shared by its own threads (L1 hits)
 // instead of being fetched again by CTAs on other SMs (measured with mismatched mappings: 43 ms per 504 M k-mers).
+template <int NJ>
 __device__ __forceinline__ void sl_count_of_kmer(const uint32_t* __restrict__ pos, const TileAnswers& ta, int64_t inst, int hd, int hc,
                                                  float* __restrict__ counts, int64_t out_base) {
-    uint32_t place[kSlNJ];
-    sl_load_places(pos, inst, place);
+    uint32_t place[NJ], a[NJ];
+    sl_load_places<NJ>(pos, inst, place);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) a[j] = ta.get(place[j]);
     float c = 0.f;
     bool all = place[0] != kNoSlot;   // unusable k-mers (masked base in the window) made no probes
 #pragma unroll
-    for (int h = 0; h < kSlMaxH; ++h) if (h < hd) all = all && (ta.get(place[h]) & 1u);
+    for (int h = 0; h < kSlMaxH; ++h) if (h < hd) all = all && sl_ans_bit(a[h]);
     if (all) {
         int mn = 127;
 #pragma unroll
-        for (int h = 0; h < kSlMaxH; ++h) if (h < hc) { const int v = (int)(int8_t)ta.get(place[kSlMaxH + h]); mn = v < mn ? v : mn; }
+        for (int h = 0; h < kSlMaxH; ++h) if (h < hc) { const int v = sl_ans_counter<NJ>(a, h); mn = v < mn ? v : mn; }
         c = minifloat_to_float(mn) + 1.f;
     }
     counts[out_base + inst] = c;
 }
-// FLAT = 1: tiles of ks_route_lookup_u (1024 consecutive k-mers per CTA, item i of thread t = k-mer i * 256 + t);
-// FLAT = 0: tiles of ks_route_lookup (16 consecutive k-mers per thread, four tile sorts per CTA).  Same grid as the route kernel.
-template <int FLAT>
+// FLAT = 1: tiles of ks_route_lookup_u (TILE consecutive k-mers per CTA, item i of thread t = k-mer i * 256 + t);
+// FLAT = 0: tiles of ks_route_lookup (16 consecutive k-mers per thread, 16 / KPT tile sorts per CTA).  Same grid as the route kernel.
+template <int FLAT, int NJ>
 __global__ void __launch_bounds__(kSlThreads) ks_combine_lookup(const uint32_t* __restrict__ pos, const uint2* __restrict__ tile_meta, int B,
                                                                const uint8_t* __restrict__ ans, int64_t n_inst, int hd, int hc,
                                                                float* __restrict__ counts, int64_t out_base) {
     RB_DYN_SMEM(unsigned char, sl_smem);
+    constexpr int KPT = SlShape<NJ>::KPT, TILE = SlShape<NJ>::TILE;
     TileAnswers ta;
     if (FLAT) {
         ta.load(sl_smem, B, tile_meta + (size_t)blockIdx.x * (B + 1), ans);
 #pragma unroll
-        for (int i = 0; i < kSlRoundKmers; ++i) {
-            const int64_t inst = (int64_t)blockIdx.x * kSlTile + i * kSlThreads + threadIdx.x;
-            if (inst < n_inst) sl_count_of_kmer(pos, ta, inst, hd, hc, counts, out_base);
+        for (int i = 0; i < KPT; ++i) {
+            const int64_t inst = (int64_t)blockIdx.x * TILE + i * kSlThreads + threadIdx.x;
+            if (inst < n_inst) sl_count_of_kmer<NJ>(pos, ta, inst, hd, hc, counts, out_base);
         }
     } else {
         const int64_t pos0 = ((int64_t)blockIdx.x * kSlThreads + threadIdx.x) * kChunk;
 #pragma unroll 1
-        for (int r0 = 0; r0 < kChunk; r0 += kSlRoundKmers) {
-            ta.load(sl_smem, B, tile_meta + ((size_t)blockIdx.x * (kChunk / kSlRoundKmers) + r0 / kSlRoundKmers) * (B + 1), ans);
+        for (int r0 = 0; r0 < kChunk; r0 += KPT) {
+            ta.load(sl_smem, B, tile_meta + ((size_t)blockIdx.x * (kChunk / KPT) + r0 / KPT) * (B + 1), ans);
 #pragma unroll
-            for (int i = 0; i < kSlRoundKmers; ++i) if (pos0 + r0 + i < n_inst) sl_count_of_kmer(pos, ta, pos0 + r0 + i, hd, hc, counts, out_base);
+            for (int i = 0; i < KPT; ++i) if (pos0 + r0 + i < n_inst) sl_count_of_kmer<NJ>(pos, ta, pos0 + r0 + i, hd, hc, counts, out_base);
             __syncthreads();   // the next round overwrites the staged answers
         }
     }
@@ -636,21 +734,21 @@ __global__ void __launch_bounds__(kSlThreads) ks_route_keys(const Ingest g, int 
 __global__ void __launch_bounds__(kSlThreads) ks_split_keys(const SlArena in, int* chunk_prefix, int sub_bits, int sub_shift, int region_div,
                                                            const SlArena out, int* overflow) {
     RB_DYN_SMEM(unsigned char, sl_smem);
-    TileSort<unsigned long long, kSlRoundKmers, true> ts;
+    TileSort<unsigned long long, kKeyE, true> ts;
     const int n_sub = 1 << sub_bits;
     ts.init(sl_smem, n_sub);
-    int* pre = reinterpret_cast<int*>(sl_smem + TileSort<unsigned long long, kSlRoundKmers, true>::smem_bytes(n_sub));
+    int* pre = reinterpret_cast<int*>(sl_smem + TileSort<unsigned long long, kKeyE, true>::smem_bytes(n_sub));
     sl_load_prefix(pre, chunk_prefix, in.B);
     const int total = pre[in.B];
     const unsigned long long* rec_in = reinterpret_cast<const unsigned long long*>(in.data);
     __shared__ int s_c;
     for (int c = sl_next_chunk(chunk_prefix + in.B + 1, &s_c); c < total; c = sl_next_chunk(chunk_prefix + in.B + 1, &s_c)) {
-        const SlWork w = sl_work_item(in, pre, c);   // in.chunk <= 256 * kSlRoundKmers keys
-        int bkt[kSlRoundKmers];
-        unsigned long long rec[kSlRoundKmers];
-        uint32_t slot[kSlRoundKmers];
+        const SlWork w = sl_work_item(in, pre, c);   // in.chunk <= 256 * kKeyE keys
+        int bkt[kKeyE];
+        unsigned long long rec[kKeyE];
+        uint32_t slot[kKeyE];
 #pragma unroll
-        for (int i = 0; i < kSlRoundKmers; ++i) {
+        for (int i = 0; i < kKeyE; ++i) {
             const uint32_t idx = threadIdx.x + i * kSlThreads;
             bkt[i] = -1; rec[i] = 0;
             if (idx < w.n) {
@@ -728,15 +826,16 @@ __global__ void __launch_bounds__(kSlThreads) ks_dedup(const SlArena in, int n_r
             const unsigned long long key = __ldcs(rec + lo + i);
             if (key == 0ULL) { atomicAdd(&n_zero, 1u); continue; }   // 0 marks an empty slot
             uint32_t s = (uint32_t)((sl_mixkey(key) << hash_shift) >> 40) & (T - 1);   // hash bits the two splits did not use
-            for (;;) {
+            for (;;) {   // the copy that claims the slot is counted by the slot being taken: one atomic per distinct key, two per duplicate
                 const unsigned long long old = atomicCAS(&tkeys[s], 0ULL, key);
-                if (old == 0ULL || old == key) { atomicAdd(&tcnt[s], 1u); break; }
+                if (old == 0ULL) break;
+                if (old == key) { atomicAdd(&tcnt[s], 1u); break; }
                 s = (s + 1) & (T - 1);
             }
         }
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < T; i += kSlThreads)
-            if (tcnt[i]) tcnt[i] |= atomicAdd(&n_occ, 1u) << 16;   // multiplicity (< 2^16: a sub-range holds < 4096 keys) | dense rank
+            if (tkeys[i]) tcnt[i] |= atomicAdd(&n_occ, 1u) << 16;   // extra copies (< 2^16: a sub-range holds < 4096 keys) | dense rank
         __syncthreads();
         if (threadIdx.x == 0) out_base = atomicAdd(n_distinct, n_occ + (n_zero ? 1u : 0u));
         __syncthreads();
@@ -744,10 +843,10 @@ __global__ void __launch_bounds__(kSlThreads) ks_dedup(const SlArena in, int n_r
             if (threadIdx.x == 0) atomicOr(reinterpret_cast<unsigned int*>(overflow), 1u);
         } else {
             for (uint32_t i = threadIdx.x; i < T; i += kSlThreads)
-                if (tcnt[i]) {
+                if (tkeys[i]) {
                     const uint32_t d = out_base + (tcnt[i] >> 16);
                     dkey[d] = tkeys[i];
-                    dmult[d] = (tcnt[i] & 0xFFFFu) + (spill.keys ? spill_take(spill, tkeys[i]) : 0u);
+                    dmult[d] = (tcnt[i] & 0xFFFFu) + 1u + (spill.keys ? spill_take(spill, tkeys[i]) : 0u);
                 }
             if (threadIdx.x == 0 && n_zero) { dkey[out_base + n_occ] = 0ULL; dmult[out_base + n_occ] = n_zero + (spill.keys ? spill_take(spill, 0ULL) : 0u); }
         }
@@ -756,66 +855,70 @@ __global__ void __launch_bounds__(kSlThreads) ks_dedup(const SlArena in, int n_r
 }
 
 // ---- I4: the probes of every distinct key, tile-sorted by filter slice ---------------------------------------------------------------------------
+template <int NJ>
 __global__ void __launch_bounds__(kSlThreads) ks_emit_probes(const unsigned long long* __restrict__ dkey, const unsigned int* __restrict__ n_distinct,
                                                             const HashMults hm, const SlGeom sg, int with_cbf, const SlArena arena,
                                                             uint32_t* __restrict__ pos, uint2* __restrict__ tile_meta, int* overflow) {
+    constexpr int KPT = SlShape<NJ>::KPT, TILE = SlShape<NJ>::TILE;
     const int64_t nd = (int64_t)*n_distinct;
-    if ((int64_t)blockIdx.x * (kSlThreads * kSlRoundKmers) >= nd) return;   // whole CTA
+    if ((int64_t)blockIdx.x * TILE >= nd) return;   // whole CTA
     RB_DYN_SMEM(unsigned char, sl_smem);
-    TileSort<uint32_t, kSlRoundKmers * kSlNJ> ts;
+    TileSort<uint32_t, KPT * NJ> ts;
     ts.init(sl_smem, arena.B);
-    const int64_t d0 = (int64_t)blockIdx.x * kSlTile + threadIdx.x;   // item i of the thread = distinct key d0 + i * 256
-    int bkt[kSlRoundKmers * kSlNJ];
-    uint32_t rec[kSlRoundKmers * kSlNJ], slot[kSlRoundKmers * kSlNJ];
+    const int64_t d0 = (int64_t)blockIdx.x * TILE + threadIdx.x;   // item i of the thread = distinct key d0 + i * 256
+    int bkt[KPT * NJ];
+    uint32_t rec[KPT * NJ], slot[KPT * NJ];
 #pragma unroll
-    for (int i = 0; i < kSlRoundKmers; ++i) {
+    for (int i = 0; i < KPT; ++i) {
 #pragma unroll
-        for (int j = 0; j < kSlNJ; ++j) { bkt[i * kSlNJ + j] = -1; rec[i * kSlNJ + j] = 0; }
-        if (d0 + i * kSlThreads < nd) sl_probes(sg, hm, (uint64_t)dkey[d0 + i * kSlThreads], with_cbf != 0, &bkt[i * kSlNJ], &rec[i * kSlNJ]);
+        for (int j = 0; j < NJ; ++j) { bkt[i * NJ + j] = -1; rec[i * NJ + j] = 0; }
+        if (d0 + i * kSlThreads < nd) sl_probes<NJ>(sg, hm, (uint64_t)dkey[d0 + i * kSlThreads], with_cbf != 0, &bkt[i * NJ], &rec[i * NJ]);
     }
     ts.run(arena, 0, bkt, rec, slot, overflow, tile_meta + (size_t)blockIdx.x * (arena.B + 1));
 #pragma unroll
-    for (int i = 0; i < kSlRoundKmers; ++i) if (d0 + i * kSlThreads < nd) sl_store_places(pos, d0 + i * kSlThreads, &slot[i * kSlNJ]);
+    for (int i = 0; i < KPT; ++i) if (d0 + i * kSlThreads < nd) sl_store_places<NJ>(pos, d0 + i * kSlThreads, &slot[i * NJ]);
 }
 
 // ---- I6: per distinct key: present?, replay the increments, emit one raise per counter that grew ----------------------------------------------
+template <int NJ>
 __global__ void __launch_bounds__(kSlThreads) ks_combine_insert(const unsigned long long* __restrict__ dkey, const unsigned int* __restrict__ dmult,
                                                                const unsigned int* __restrict__ n_distinct, const uint32_t* __restrict__ pos,
                                                                const uint2* __restrict__ tile_meta, int probe_B, const uint8_t* __restrict__ ans,
                                                                const HashMults hm, const SlGeom sg, int policy, uint64_t rng_seed, const SlArena raises,
                                                                int* overflow) {
+    constexpr int KPT = SlShape<NJ>::KPT, TILE = SlShape<NJ>::TILE;
     const int64_t nd = (int64_t)*n_distinct;
-    if ((int64_t)blockIdx.x * (kSlThreads * kSlRoundKmers) >= nd) return;   // whole CTA
+    if ((int64_t)blockIdx.x * TILE >= nd) return;   // whole CTA
     RB_DYN_SMEM(unsigned char, sl_smem);
-    const int64_t d0 = (int64_t)blockIdx.x * kSlTile + threadIdx.x;   // item i of the thread = distinct key d0 + i * 256 (as in ks_emit_probes)
-    int bkt[kSlRoundKmers * kSlMaxH];
-    uint32_t rec[kSlRoundKmers * kSlMaxH], rslot[kSlRoundKmers * kSlMaxH];
+    const int64_t d0 = (int64_t)blockIdx.x * TILE + threadIdx.x;   // item i of the thread = distinct key d0 + i * 256 (as in ks_emit_probes)
+    int bkt[KPT * kSlMaxH];
+    uint32_t rec[KPT * kSlMaxH], rslot[KPT * kSlMaxH];
 #pragma unroll
-    for (int e = 0; e < kSlRoundKmers * kSlMaxH; ++e) { bkt[e] = -1; rec[e] = 0; }
+    for (int e = 0; e < KPT * kSlMaxH; ++e) { bkt[e] = -1; rec[e] = 0; }
     TileAnswers ta;   // the tile of ks_emit_probes with the same block index
     ta.load(sl_smem, probe_B, tile_meta + (size_t)blockIdx.x * (probe_B + 1), ans);
-    uint32_t a[kSlRoundKmers * kSlNJ];
+    uint32_t a[KPT * NJ];
 #pragma unroll
-    for (int i = 0; i < kSlRoundKmers; ++i) {
-        uint32_t place[kSlNJ];
+    for (int i = 0; i < KPT; ++i) {
+        uint32_t place[NJ];
 #pragma unroll
-        for (int j = 0; j < kSlNJ; ++j) place[j] = kNoSlot;
-        if (d0 + i * kSlThreads < nd) sl_load_places(pos, d0 + i * kSlThreads, place);
+        for (int j = 0; j < NJ; ++j) place[j] = kNoSlot;
+        if (d0 + i * kSlThreads < nd) sl_load_places<NJ>(pos, d0 + i * kSlThreads, place);
 #pragma unroll
-        for (int j = 0; j < kSlNJ; ++j) a[i * kSlNJ + j] = ta.get(place[j]);
+        for (int j = 0; j < NJ; ++j) a[i * NJ + j] = ta.get(place[j]);
     }
     __syncthreads();   // the tile sort of the raises reuses the shared memory
-    TileSort<uint32_t, kSlRoundKmers * kSlMaxH> ts;
+    TileSort<uint32_t, KPT * kSlMaxH> ts;
     ts.init(sl_smem, raises.B);
     {
 #pragma unroll
-        for (int i = 0; i < kSlRoundKmers; ++i) {
+        for (int i = 0; i < KPT; ++i) {
             if (d0 + i * kSlThreads < nd) {
                 const uint64_t key = (uint64_t)dkey[d0 + i * kSlThreads];
                 const unsigned int m = dmult[d0 + i * kSlThreads];
                 bool present = true;
 #pragma unroll
-                for (int h = 0; h < kSlMaxH; ++h) if (h < sg.hd) present = present && (a[i * kSlNJ + h] & 1u);
+                for (int h = 0; h < kSlMaxH; ++h) if (h < sg.hd) present = present && sl_ans_bit(a[i * NJ + h]);
                 // graph.add :405-412 -- the first sighting of an absent k-mer only sets bits; addCountIfPresent :424-428 needs presence
                 unsigned int n_inc = (policy == POLICY_COUNT_IF_PRESENT) ? (present ? m : 0u) : (m - 1u + (present ? 1u : 0u));
                 int v0[kSlMaxH], v[kSlMaxH];
@@ -825,7 +928,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_combine_insert(const unsigned l
                 for (int h = 0; h < kSlMaxH; ++h) {
                     v0[h] = 127; gi[h] = ~0ULL;
                     if (h < sg.hc) {
-                        v0[h] = (int)(a[i * kSlNJ + kSlMaxH + h] & 0x7Fu);
+                        v0[h] = sl_ans_counter<NJ>(&a[i * NJ], h);
                         gi[h] = fm_index(expand_hash(key, h, hm), sg.cbf_fm);
                         mn0 = min(mn0, v0[h]);
                     }

@@ -4,6 +4,7 @@ struct SlicedEngine {
     int64_t n_max;                // k-mer instances per round the buffers hold
     SlGeom sg;
     bool unsupported;             // this graph cannot use the engine (hash counts / filter sizes): the direct engine serves it
+    bool paired;                  // one record per hash serves both filters (rb_sliced.cuh SlShape<3>); else one record per probe
     // probes: 4-byte slice-local indices, one answer byte per probe, 6 remembered positions per k-mer (or distinct key)
     uint32_t* probe_data; uint8_t* ans; unsigned int* probe_cursor; uint32_t* probe_roff; int probe_B;
     uint32_t* pos;
@@ -68,6 +69,29 @@ static int32_t sl_make_roff(rb_ctx* ctx, const std::vector<int64_t>& caps, uint3
     return RB_OK;
 }
 
+// Paired records need cbf_bytes = 2^c dividing dbg_bits and h_d >= h_c (a paired record always tests a bit).  A slice is W = 2^w
+// counters plus dbg_bits / cbf_bytes chunks of W bits; w is chosen so that one slice is about 64 MiB (it has to stay L2-resident
+// while it is consumed).  n_ranks > 1: every rank must own the same whole number of slices.  Fills the pair_* fields of sg.
+static bool sl_pair_geometry(int64_t dbg_bits, int64_t cbf_bytes, int hd, int hc, int n_ranks, SlGeom* sg) {
+    sg->paired = 0; sg->pair_log2 = 0; sg->cbf_size_log2 = 0; sg->n_pair = 0; sg->pair_local_c = 0; sg->shard_p = 0;
+    if (!env_int("RB_SLICED_PAIRED", 1, 0, 1)) return false;
+    if (hd < hc || cbf_bytes < 4 || (cbf_bytes & (cbf_bytes - 1)) != 0 || dbg_bits % cbf_bytes != 0) return false;
+    const int64_t q = dbg_bits / cbf_bytes;
+    int c = 0; while ((1LL << c) < cbf_bytes) ++c;
+    int w = 2;
+    while (w < c && (double)(1LL << (w + 1)) * (1.0 + (double)q / 8.0) <= 64.0 * 1024 * 1024) ++w;
+    w = env_int("RB_SLICE_PAIR_LOG2", w, 2, 31);
+    if (w > c) w = c;
+    while ((cbf_bytes >> w) > kSlMaxRegions && w < c) ++w;
+    if ((cbf_bytes >> w) > kSlMaxRegions || w > 31 || (w < 32 && (q - 1) >= (1LL << (32 - w)))) return false;
+    const int64_t n_pair = cbf_bytes >> w;
+    if (n_ranks > 1 && (n_pair % n_ranks) != 0) return false;
+    sg->paired = 1; sg->pair_log2 = w; sg->cbf_size_log2 = c; sg->n_pair = (int)n_pair;
+    sg->shard_p = n_ranks > 1 ? (int)(n_pair / n_ranks) : 0;
+    sg->pair_local_c = n_ranks > 1 ? (uint64_t)sg->shard_p << w : (uint64_t)cbf_bytes;
+    return true;
+}
+
 static int32_t sliced_engine_get(rb_graph* g, int64_t n_round, SlicedEngine** out) {
     rb_ctx* ctx = g->ctx;
     if (g->se && (g->se->unsupported || g->se->n_max >= n_round)) { *out = g->se; return RB_OK; }
@@ -91,6 +115,7 @@ static int32_t sliced_engine_get(rb_graph* g, int64_t n_round, SlicedEngine** ou
         else break;
     }
     sg.shard_d = sg.shard_c = sg.shard_r = 0; sg.region_div = 1;
+    e->paired = sl_pair_geometry(g->dbg->size, g->cbf->size, g->hd, g->hc, 1, &sg);
     sg.raise_log2 = std::min(sg.cbf_log2, env_int("RB_SLICE_RAISE_LOG2", 25, 2, 25));
     while (div_up(g->cbf->size, 1LL << sg.raise_log2) > kSlMaxRegions && sg.raise_log2 < std::min(sg.cbf_log2, 25)) ++sg.raise_log2;
     const int64_t n_raise = div_up(g->cbf->size, 1LL << sg.raise_log2);
@@ -99,7 +124,7 @@ static int32_t sliced_engine_get(rb_graph* g, int64_t n_round, SlicedEngine** ou
     const int64_t n_max = sl_pow2_at_least(n_round);
     e->n_max = n_max;
     // duplicates of a key are found in sub-ranges of ~2^RB_SLICED_SUBRANGE_LOG2 keys (two tile sorts: key_B ranges x 2^sub_bits each)
-    const int lgSub = env_int("RB_SLICED_SUBRANGE_LOG2", 10, 4, 11);
+    const int lgSub = env_int("RB_SLICED_SUBRANGE_LOG2", 11, 4, 11);
     int lgS = 0; while ((n_max >> lgSub) > (1LL << lgS)) ++lgS;
     const int lg1 = std::min((lgS + 1) / 2, 11);
     e->sub_bits = std::min(lgS - lg1, 11);
@@ -107,19 +132,26 @@ static int32_t sliced_engine_get(rb_graph* g, int64_t n_round, SlicedEngine** ou
     e->key_shift = 64 - lg1;
     e->sub_cap = (uint32_t)sl_capacity((double)n_max / (double)(1LL << (lg1 + e->sub_bits)));
     if (getenv("RB_SLICED_SUBCAP")) e->sub_cap = (uint32_t)env_int("RB_SLICED_SUBCAP", (int)e->sub_cap, 8, kSlDedupSlots - 1);   // tests: force spills
-    e->spill_on = env_int("RB_SLICED_SPILL", 0, 0, 1) != 0;
-    e->spill_cap = (uint32_t)std::min<int64_t>(n_max / 8 + 65536, 1LL << 30);
-    e->htab_slots = sl_pow2_at_least(2 * (int64_t)e->spill_cap);
+    // heavy hitters (one k-mer with thousands of copies in a round: poly-A, very highly expressed transcripts): the copies that do not
+    // fit their range / sub-range go to a spill list (up to half a round) and are aggregated in a global table of up to 2^26 slots;
+    // a round that exceeds either is handed to the direct engine before anything is modified
+    e->spill_on = env_int("RB_SLICED_SPILL", 1, 0, 1) != 0;
+    e->spill_cap = (uint32_t)std::min<int64_t>(n_max / 2 + 65536, 1LL << 30);
+    e->htab_slots = std::min<int64_t>(sl_pow2_at_least(2 * (int64_t)e->spill_cap), 1LL << 26);
     { int lg = 0; while ((1LL << lg) < e->htab_slots) ++lg; e->htab_shift = 64 - lg; }
     if (e->sub_cap >= (uint32_t)kSlDedupSlots) { e->unsupported = true; return RB_OK; }   // cannot happen with lgSub <= 11, n_max <= 2^29
-    e->probe_B = sg.n_dbg + sg.n_cbf;
+    e->probe_B = e->paired ? sg.n_pair : sg.n_dbg + sg.n_cbf;
     // ---- capacities ----
     const double dbg_slices = std::max(1.0, (double)g->dbg->size / (double)(1LL << sg.dbg_log2));
     const double cbf_slices = std::max(1.0, (double)g->cbf->size / (double)(1LL << sg.cbf_log2));
     const double raise_slices = std::max(1.0, (double)g->cbf->size / (double)(1LL << sg.raise_log2));
     std::vector<int64_t> caps;
-    for (int b = 0; b < sg.n_dbg; ++b) caps.push_back(sl_capacity((double)n_max * g->hd / dbg_slices));
-    for (int b = 0; b < sg.n_cbf; ++b) caps.push_back(sl_capacity((double)n_max * g->hc / cbf_slices));
+    if (e->paired) {
+        for (int b = 0; b < sg.n_pair; ++b) caps.push_back(sl_capacity((double)n_max * g->hd / (double)sg.n_pair));
+    } else {
+        for (int b = 0; b < sg.n_dbg; ++b) caps.push_back(sl_capacity((double)n_max * g->hd / dbg_slices));
+        for (int b = 0; b < sg.n_cbf; ++b) caps.push_back(sl_capacity((double)n_max * g->hc / cbf_slices));
+    }
     int64_t probe_slots = 0, key_slots = 0, raise_slots = 0;
     int32_t rc = sl_make_roff(ctx, caps, &e->probe_roff, &probe_slots);
     if (rc) { sliced_engine_free(g); return rc; }
@@ -130,12 +162,13 @@ static int32_t sliced_engine_get(rb_graph* g, int64_t n_round, SlicedEngine** ou
     rc = sl_make_roff(ctx, caps, &e->raise_roff, &raise_slots);
     if (rc) { sliced_engine_free(g); return rc; }
     const int maxB = std::max(std::max(e->probe_B, e->key_B), sg.n_raise);
-    const int64_t n_tiles = n_max / kSlTile + 8;
+    const int nj = e->paired ? 3 : kSlNJ;
+    const int64_t n_tiles = n_max / (e->paired ? SlShape<3>::TILE : SlShape<6>::TILE) + 8;
     cudaError_t er = cudaMalloc(&e->probe_data, ((size_t)probe_slots + kSlSpill) * 4);
     if (er == cudaSuccess) er = cudaMalloc(&e->ans, (size_t)probe_slots + kSlSpill);
     if (er == cudaSuccess) er = cudaMalloc(&e->tile_meta, (size_t)n_tiles * (e->probe_B + 1) * 8);
     if (er == cudaSuccess) er = cudaMalloc(&e->probe_cursor, (size_t)e->probe_B * kSlPad * 4);
-    if (er == cudaSuccess) er = cudaMalloc(&e->pos, ((size_t)n_max + 8) * kSlNJ * 4);
+    if (er == cudaSuccess) er = cudaMalloc(&e->pos, ((size_t)n_max + 8) * nj * 4);
     if (er == cudaSuccess) er = cudaMalloc(&e->key_data, ((size_t)key_slots + kSlSpill) * 8);
     if (er == cudaSuccess) er = cudaMalloc(&e->key_cursor, (size_t)e->key_B * kSlPad * 4);
     const int64_t n_sub_regions = (int64_t)e->key_B << e->sub_bits;
@@ -156,7 +189,17 @@ static int32_t sliced_engine_get(rb_graph* g, int64_t n_round, SlicedEngine** ou
     if (er == cudaSuccess) er = cudaMalloc(&e->chunk_prefix, (size_t)(maxB + 2) * 4 + 64);
     if (er == cudaSuccess) er = cudaMalloc(&e->overflow, 64);
     if (er == cudaSuccess) er = cudaMemsetAsync(e->overflow, 0, 4, ctx->stream);
-    if (er != cudaSuccess) { sliced_engine_free(g); return fail(ctx, RB_ENOMEM, std::string("sliced engine buffers: ") + cudaGetErrorString(er)); }
+    if (er != cudaSuccess) {
+        // not enough device memory for the work buffers of a round this large: the direct engine needs none and serves the graph
+        cudaGetLastError();
+        sliced_engine_free(g);
+        SlicedEngine* stub = new SlicedEngine();
+        memset(stub, 0, sizeof *stub);
+        stub->unsupported = true;
+        g->se = stub;
+        *out = stub;
+        return RB_OK;
+    }
     return RB_OK;
 }
 
@@ -199,12 +242,17 @@ static SlArena sl_arena(void* data, unsigned int* cursor, const uint32_t* roff, 
 static SlArena sl_probe_arena(SlicedEngine* e) { return sl_arena(e->probe_data, e->probe_cursor, e->probe_roff, e->probe_B, sl_chunk()); }
 
 // the prefix k-merizer covers a CTA's 1024 positions with one span of at most kPfxSpan bases of the packed stream (uniform layout only)
-static bool sl_uniform_fast(const Ingest& ing, int k) {
+static bool sl_uniform_fast(const Ingest& ing, int k, int tile, int span_cap) {
     const char* v = getenv("RB_SLICED_KMERIZER");
     if (v && !strcmp(v, "walker")) return false;
     if (ing.pos_off || ing.uniform_npos <= 0) return false;
-    const int64_t span = ((int64_t)(kSlTile - 1) / ing.uniform_npos + 1) * ing.uniform_stride + ing.uniform_npos - 1 + k;
-    return span <= kPfxSpan;
+    const int64_t span = ((int64_t)(tile - 1) / ing.uniform_npos + 1) * ing.uniform_stride + ing.uniform_npos - 1 + k;
+    return span <= span_cap;
+}
+static bool sl_uniform_fast_keys(const Ingest& ing, int k) { return sl_uniform_fast(ing, k, kSlTile, KeyKmerizer::kSpan); }
+template <int NJ>
+static bool sl_uniform_fast_probes(const Ingest& ing, int k) {
+    return sl_uniform_fast(ing, k, SlShape<NJ>::TILE, PrefixKmerizer<SlShape<NJ>::PFX_PER, SlShape<NJ>::TILE>::kSpan);
 }
 // grid of a kernel that streams over an arena with no residency window to respect
 template <typename K>
@@ -226,27 +274,30 @@ static int32_t sl_stream_grid(rb_ctx* ctx, K kernel, size_t smem, int* grid) {
     } while (0)
 
 // S1..S3
-static int32_t sliced_count_round(rb_graph* g, const Ingest& ing, int mode, float* counts, int64_t* fh, int64_t* rh, bool* fell_back) {
+template <int NJ>
+static int32_t sliced_count_round_t(rb_graph* g, SlicedEngine* e, const Ingest& ing, int mode, float* counts, int64_t* fh, int64_t* rh, bool* fell_back) {
     rb_ctx* ctx = g->ctx;
-    SlicedEngine* e = nullptr;
-    int32_t rc = sliced_engine_get(g, ing.n_pos, &e);
-    if (rc) return rc;
-    if (e->unsupported) { *fell_back = true; return RB_OK; }
+    int32_t rc;
+    constexpr int TILE = SlShape<NJ>::TILE, KPT = SlShape<NJ>::KPT;
     const HashMults hm = make_hm(g->k);
     const SlArena probes = sl_probe_arena(e);
     CK(cudaMemsetAsync(probes.cursor, 0, (size_t)probes.B * kSlPad * 4, ctx->stream));
-    const size_t sm_sort = TileSort<uint32_t, kSlRoundKmers * kSlNJ>::smem_bytes(probes.B);
-    const bool fast = sl_uniform_fast(ing, g->k);
+    const size_t sm_sort = TileSort<uint32_t, KPT * NJ>::smem_bytes(probes.B);
+    const bool fast = sl_uniform_fast_probes<NJ>(ing, g->k);
     int grid_pos;
     if (fast) {
-        grid_pos = (int)div_up(ing.n_pos, (int64_t)kSlTile);
-        const size_t sm = std::max(sm_sort, PrefixKmerizer::smem_bytes());
-        if (mode == RB_MODE_FWD) SL_LAUNCH("ks_route_lookup_u<0>", ks_route_lookup_u<0>, grid_pos, sm, ing, g->k, hm, e->sg, probes, e->pos, e->tile_meta, fh, rh, e->overflow);
-        else SL_LAUNCH("ks_route_lookup_u<2>", ks_route_lookup_u<2>, grid_pos, sm, ing, g->k, hm, e->sg, probes, e->pos, e->tile_meta, fh, rh, e->overflow);
+        grid_pos = (int)div_up(ing.n_pos, (int64_t)TILE);
+        const size_t sm = std::max(sm_sort, PrefixKmerizer<SlShape<NJ>::PFX_PER, TILE>::smem_bytes());
+        auto kf = ks_route_lookup_u<0, NJ>;
+        auto kc = ks_route_lookup_u<2, NJ>;
+        if (mode == RB_MODE_FWD) SL_LAUNCH("ks_route_lookup_u<0>", kf, grid_pos, sm, ing, g->k, hm, e->sg, probes, e->pos, e->tile_meta, fh, rh, e->overflow);
+        else SL_LAUNCH("ks_route_lookup_u<2>", kc, grid_pos, sm, ing, g->k, hm, e->sg, probes, e->pos, e->tile_meta, fh, rh, e->overflow);
     } else {
         grid_pos = (int)div_up(ing.n_pos, (int64_t)kSlThreads * kChunk);
-        if (mode == RB_MODE_FWD) SL_LAUNCH("ks_route_lookup<0>", ks_route_lookup<0>, grid_pos, sm_sort, ing, g->k, hm, e->sg, probes, e->pos, e->tile_meta, fh, rh, e->overflow);
-        else SL_LAUNCH("ks_route_lookup<2>", ks_route_lookup<2>, grid_pos, sm_sort, ing, g->k, hm, e->sg, probes, e->pos, e->tile_meta, fh, rh, e->overflow);
+        auto kf = ks_route_lookup<0, NJ>;
+        auto kc = ks_route_lookup<2, NJ>;
+        if (mode == RB_MODE_FWD) SL_LAUNCH("ks_route_lookup<0>", kf, grid_pos, sm_sort, ing, g->k, hm, e->sg, probes, e->pos, e->tile_meta, fh, rh, e->overflow);
+        else SL_LAUNCH("ks_route_lookup<2>", kc, grid_pos, sm_sort, ing, g->k, hm, e->sg, probes, e->pos, e->tile_meta, fh, rh, e->overflow);
     }
     int flag = 0;
     rc = sl_read_flag(ctx, e->overflow, &flag);
@@ -260,10 +311,19 @@ static int32_t sliced_count_round(rb_graph* g, const Ingest& ing, int mode, floa
     if (rc) return rc;
     SL_LAUNCH("ks_apply_probes<0>", ks_apply_probes<0>, grid, sm_pre, probes, e->chunk_prefix, e->sg, g->dbg->dev, g->cbf->dev, e->ans);
     // same CTA -> k-mer mapping as the route kernel
-    const size_t sm_ans = TileAnswers::smem_bytes(probes.B, kSlTile * kSlNJ);
-    if (fast) SL_LAUNCH("ks_combine_lookup<1>", ks_combine_lookup<1>, grid_pos, sm_ans, e->pos, e->tile_meta, probes.B, e->ans, ing.n_pos, g->hd, g->hc, counts, ing.out_base);
-    else SL_LAUNCH("ks_combine_lookup<0>", ks_combine_lookup<0>, grid_pos, sm_ans, e->pos, e->tile_meta, probes.B, e->ans, ing.n_pos, g->hd, g->hc, counts, ing.out_base);
+    const size_t sm_ans = TileAnswers::smem_bytes(probes.B, TILE * NJ);
+    auto k1 = ks_combine_lookup<1, NJ>;
+    auto k0 = ks_combine_lookup<0, NJ>;
+    if (fast) SL_LAUNCH("ks_combine_lookup<1>", k1, grid_pos, sm_ans, e->pos, e->tile_meta, probes.B, e->ans, ing.n_pos, g->hd, g->hc, counts, ing.out_base);
+    else SL_LAUNCH("ks_combine_lookup<0>", k0, grid_pos, sm_ans, e->pos, e->tile_meta, probes.B, e->ans, ing.n_pos, g->hd, g->hc, counts, ing.out_base);
     return RB_OK;
+}
+static int32_t sliced_count_round(rb_graph* g, const Ingest& ing, int mode, float* counts, int64_t* fh, int64_t* rh, bool* fell_back) {
+    SlicedEngine* e = nullptr;
+    int32_t rc = sliced_engine_get(g, ing.n_pos, &e);
+    if (rc) return rc;
+    if (e->unsupported) { *fell_back = true; return RB_OK; }
+    return e->paired ? sliced_count_round_t<3>(g, e, ing, mode, counts, fh, rh, fell_back) : sliced_count_round_t<6>(g, e, ing, mode, counts, fh, rh, fell_back);
 }
 
 // I1..I7
@@ -275,15 +335,15 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     if (e->unsupported) { *fell_back = true; return RB_OK; }
     const HashMults hm = make_hm(g->k);
     // I1 keys by range
-    SlArena keys = sl_arena(e->key_data, e->key_cursor, e->key_roff, e->key_B, kSlThreads * kSlRoundKmers);
+    SlArena keys = sl_arena(e->key_data, e->key_cursor, e->key_roff, e->key_B, kSlThreads * kKeyE);
     CK(cudaMemsetAsync(keys.cursor, 0, (size_t)keys.B * kSlPad * 4, ctx->stream));
     if (e->spill_on) {
         keys.spill_data = e->spill_keys; keys.spill_cursor = e->spill_cursor; keys.spill_cap = e->spill_cap;
         CK(cudaMemsetAsync(e->spill_cursor, 0, 4, ctx->stream));
     }
-    if (sl_uniform_fast(ing, g->k)) {
-        const int grid_pos = (int)div_up(ing.n_pos, (int64_t)kSlTile);
-        const size_t sm = std::max(TileSort<unsigned long long, kSlRoundKmers, true>::smem_bytes(keys.B), PrefixKmerizer::smem_bytes());
+    if (sl_uniform_fast_keys(ing, g->k)) {
+        const int grid_pos = (int)div_up(ing.n_pos, (int64_t)kKeyTile);
+        const size_t sm = std::max(TileSort<unsigned long long, kKeyE, true>::smem_bytes(keys.B), KeyKmerizer::smem_bytes());
         if (mode == RB_MODE_FWD) SL_LAUNCH("ks_route_keys_u<0>", ks_route_keys_u<0>, grid_pos, sm, ing, g->k, e->key_B, e->key_shift, keys, e->overflow);
         else if (mode == RB_MODE_RC) SL_LAUNCH("ks_route_keys_u<1>", ks_route_keys_u<1>, grid_pos, sm, ing, g->k, e->key_B, e->key_shift, keys, e->overflow);
         else SL_LAUNCH("ks_route_keys_u<2>", ks_route_keys_u<2>, grid_pos, sm, ing, g->k, e->key_B, e->key_shift, keys, e->overflow);
@@ -304,7 +364,7 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     rc = sl_chunk_prefix(ctx, e, keys);
     if (rc) return rc;
     int grid = 0;
-    const size_t sm_split = TileSort<unsigned long long, kSlRoundKmers, true>::smem_bytes(n_sub) + (size_t)(keys.B + 1) * 4;
+    const size_t sm_split = TileSort<unsigned long long, kKeyE, true>::smem_bytes(n_sub) + (size_t)(keys.B + 1) * 4;
     rc = sl_stream_grid(ctx, ks_split_keys, sm_split, &grid);
     if (rc) return rc;
     SL_LAUNCH("ks_split_keys", ks_split_keys, grid, sm_split, keys, e->chunk_prefix, e->sub_bits, 64 - (64 - e->key_shift) - e->sub_bits, 1, subs, e->overflow);
@@ -319,6 +379,7 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
         unsigned int n_spill = 0;
         CK(cudaMemcpyAsync(&n_spill, e->spill_cursor, 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        if ((int64_t)n_spill > e->htab_slots / 2) { *fell_back = true; return RB_OK; }   // more spilled copies than the table is sure to hold
         if (n_spill) {
             spill.keys = e->htab_keys; spill.counts = e->htab_counts; spill.n_slots = (uint64_t)e->htab_slots; spill.shift = e->htab_shift;
             CK(cudaMemsetAsync(spill.keys, 0, (size_t)(e->htab_slots + 1) * 8, ctx->stream));
@@ -342,9 +403,11 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     const SlArena probes = sl_probe_arena(e);
     CK(cudaMemsetAsync(probes.cursor, 0, (size_t)probes.B * kSlPad * 4, ctx->stream));
     const int with_cbf = policy != POLICY_DBG_ONLY;
-    const size_t sm_sort = TileSort<uint32_t, kSlRoundKmers * kSlNJ>::smem_bytes(probes.B);
-    const int grid_d = (int)div_up(ing.n_pos, (int64_t)kSlThreads * kSlRoundKmers);   // distinct keys <= instances
-    SL_LAUNCH("ks_emit_probes", ks_emit_probes, grid_d, sm_sort, e->dkey, e->n_distinct, hm, e->sg, with_cbf, probes, e->pos, e->tile_meta, e->overflow);
+    const size_t sm_sort = TileSort<uint32_t, kSlTileRecords>::smem_bytes(probes.B);
+    const int tile_d = e->paired ? SlShape<3>::TILE : SlShape<6>::TILE;
+    const int grid_d = (int)div_up(ing.n_pos, (int64_t)tile_d);   // distinct keys <= instances
+    if (e->paired) SL_LAUNCH("ks_emit_probes", ks_emit_probes<3>, grid_d, sm_sort, e->dkey, e->n_distinct, hm, e->sg, with_cbf, probes, e->pos, e->tile_meta, e->overflow);
+    else SL_LAUNCH("ks_emit_probes", ks_emit_probes<6>, grid_d, sm_sort, e->dkey, e->n_distinct, hm, e->sg, with_cbf, probes, e->pos, e->tile_meta, e->overflow);
     rc = sl_read_flag(ctx, e->overflow, &flag);
     if (rc) return rc;
     if (flag) { *fell_back = true; return RB_OK; }   // still nothing modified
@@ -364,9 +427,11 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
         const SlArena raises = sl_arena(e->raise_data, e->raise_cursor, e->raise_roff, e->sg.n_raise, sl_chunk());
         CK(cudaMemsetAsync(raises.cursor, 0, (size_t)raises.B * kSlPad * 4, ctx->stream));
         const uint64_t seed = ctx->rng_seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(ctx->launches + 1);
-        const size_t sm_r = std::max(TileSort<uint32_t, kSlRoundKmers * kSlMaxH>::smem_bytes(raises.B), TileAnswers::smem_bytes(probes.B, kSlTile * kSlNJ));
-        SL_LAUNCH("ks_combine_insert", ks_combine_insert, grid_d, sm_r, e->dkey, e->dmult, e->n_distinct, e->pos, e->tile_meta, probes.B, e->ans, hm, e->sg, policy, seed,
-                  raises, e->overflow);
+        const size_t sm_r = std::max(TileSort<uint32_t, kSlTileRecords>::smem_bytes(raises.B), TileAnswers::smem_bytes(probes.B, kSlThreads * kSlTileRecords));
+        if (e->paired) SL_LAUNCH("ks_combine_insert", ks_combine_insert<3>, grid_d, sm_r, e->dkey, e->dmult, e->n_distinct, e->pos, e->tile_meta, probes.B, e->ans, hm, e->sg, policy, seed,
+                                 raises, e->overflow);
+        else SL_LAUNCH("ks_combine_insert", ks_combine_insert<6>, grid_d, sm_r, e->dkey, e->dmult, e->n_distinct, e->pos, e->tile_meta, probes.B, e->ans, hm, e->sg, policy, seed,
+                       raises, e->overflow);
         rc = sl_chunk_prefix(ctx, e, raises);
         if (rc) return rc;
         const size_t sm_rp = (size_t)(raises.B + 1) * 4;

@@ -88,7 +88,7 @@ extern "C" int32_t rb_sshard_create(rb_ctx* ctx, int32_t n_ranks, int32_t rank, 
     // distinct keys a home rank can see exceed its share of the instances only by the imbalance of the hash ranges (~1e-4 at 10^8 keys)
     const int64_t n_max = div_up(std::max<int64_t>(max_kmers, 1024), 4096) * 4096;
     sh->n_max = n_max; sh->n_dense = n_max + n_max / 32 + 4096;
-    const int lgSub = env_int("RB_SLICED_SUBRANGE_LOG2", 10, 4, 11);
+    const int lgSub = env_int("RB_SLICED_SUBRANGE_LOG2", 11, 4, 11);
     int lgW = 0; while ((1 << lgW) < W) ++lgW;
     int lgS = 0; while (((n_max * W) >> lgSub) > (1LL << lgS)) ++lgS;       // sub-ranges over all ranks
     sh->lg1 = std::max(lgW, std::min((lgS + 1) / 2, 11));
@@ -112,7 +112,7 @@ extern "C" int32_t rb_sshard_create(rb_ctx* ctx, int32_t n_ranks, int32_t rank, 
     cudaError_t er = cudaSuccess;
     if (!rc) {
         const int maxB = std::max(std::max(sh->R, sh->SR), sh->KR) * W;
-        const int64_t n_tiles = sh->n_dense / kSlTile + 8;
+        const int64_t n_tiles = sh->n_dense / SlShape<6>::TILE + 8;
         er = cudaMalloc(&sh->probe_cursor, (size_t)sh->R * W * kSlPad * 4);
         if (er == cudaSuccess) er = cudaMalloc(&sh->key_cursor, (size_t)sh->KR * W * kSlPad * 4);
         if (er == cudaSuccess) er = cudaMalloc(&sh->raise_cursor, (size_t)sh->SR * W * kSlPad * 4);
@@ -196,7 +196,7 @@ static int32_t ss_route_launch(rb_ctx* ctx, const Ingest& ing_in, void* user) {
     Ingest ing = ing_in;
     ing.out_base = 0;
     const HashMults hm = make_hm(sh->k);
-    const bool fast = sl_uniform_fast(ing, sh->k);
+    const bool fast = u->lookup ? sl_uniform_fast_probes<6>(ing, sh->k) : sl_uniform_fast_keys(ing, sh->k);
     int32_t rc;
     if (u->lookup) {
         const SlArena probes = ss_producer(sh, u->send, sh->probe_cursor, sh->R, sh->probe_cap);
@@ -205,21 +205,23 @@ static int32_t ss_route_launch(rb_ctx* ctx, const Ingest& ing_in, void* user) {
         sh->n_items = ing.n_pos; sh->lookup_fast = fast;
         if (fast) {
             const int grid = (int)div_up(ing.n_pos, (int64_t)kSlTile);
-            const size_t sm = std::max(sm_sort, PrefixKmerizer::smem_bytes());
-            if (u->mode == RB_MODE_FWD) SL_LAUNCH("ks_route_lookup_u<0>", ks_route_lookup_u<0>, grid, sm, ing, sh->k, hm, sh->sg_route, probes, sh->pos, sh->tile_meta, u->fh, u->rh, sh->overflow);
-            else SL_LAUNCH("ks_route_lookup_u<2>", ks_route_lookup_u<2>, grid, sm, ing, sh->k, hm, sh->sg_route, probes, sh->pos, sh->tile_meta, u->fh, u->rh, sh->overflow);
+            const size_t sm = std::max(sm_sort, PrefixKmerizer<8, SlShape<6>::TILE>::smem_bytes());
+            auto kf = ks_route_lookup_u<0, 6>; auto kc = ks_route_lookup_u<2, 6>;
+            if (u->mode == RB_MODE_FWD) SL_LAUNCH("ks_route_lookup_u<0>", kf, grid, sm, ing, sh->k, hm, sh->sg_route, probes, sh->pos, sh->tile_meta, u->fh, u->rh, sh->overflow);
+            else SL_LAUNCH("ks_route_lookup_u<2>", kc, grid, sm, ing, sh->k, hm, sh->sg_route, probes, sh->pos, sh->tile_meta, u->fh, u->rh, sh->overflow);
         } else {
             const int grid = (int)div_up(ing.n_pos, (int64_t)kSlThreads * kChunk);
-            if (u->mode == RB_MODE_FWD) SL_LAUNCH("ks_route_lookup<0>", ks_route_lookup<0>, grid, sm_sort, ing, sh->k, hm, sh->sg_route, probes, sh->pos, sh->tile_meta, u->fh, u->rh, sh->overflow);
-            else SL_LAUNCH("ks_route_lookup<2>", ks_route_lookup<2>, grid, sm_sort, ing, sh->k, hm, sh->sg_route, probes, sh->pos, sh->tile_meta, u->fh, u->rh, sh->overflow);
+            auto kf = ks_route_lookup<0, 6>; auto kc = ks_route_lookup<2, 6>;
+            if (u->mode == RB_MODE_FWD) SL_LAUNCH("ks_route_lookup<0>", kf, grid, sm_sort, ing, sh->k, hm, sh->sg_route, probes, sh->pos, sh->tile_meta, u->fh, u->rh, sh->overflow);
+            else SL_LAUNCH("ks_route_lookup<2>", kc, grid, sm_sort, ing, sh->k, hm, sh->sg_route, probes, sh->pos, sh->tile_meta, u->fh, u->rh, sh->overflow);
         }
     } else {
         const SlArena keys = ss_producer(sh, u->send, sh->key_cursor, sh->KR, sh->key_cap);
         CK(cudaMemsetAsync(keys.cursor, 0, (size_t)keys.B * kSlPad * 4, ctx->stream));
         const int n_ranges = 1 << sh->lg1, shift = 64 - sh->lg1;
         if (fast) {
-            const int grid = (int)div_up(ing.n_pos, (int64_t)kSlTile);
-            const size_t sm = std::max(TileSort<unsigned long long, kSlRoundKmers, true>::smem_bytes(keys.B), PrefixKmerizer::smem_bytes());
+            const int grid = (int)div_up(ing.n_pos, (int64_t)kKeyTile);
+            const size_t sm = std::max(TileSort<unsigned long long, kKeyE, true>::smem_bytes(keys.B), KeyKmerizer::smem_bytes());
             if (u->mode == RB_MODE_FWD) SL_LAUNCH("ks_route_keys_u<0>", ks_route_keys_u<0>, grid, sm, ing, sh->k, n_ranges, shift, keys, sh->overflow);
             else if (u->mode == RB_MODE_RC) SL_LAUNCH("ks_route_keys_u<1>", ks_route_keys_u<1>, grid, sm, ing, sh->k, n_ranges, shift, keys, sh->overflow);
             else SL_LAUNCH("ks_route_keys_u<2>", ks_route_keys_u<2>, grid, sm, ing, sh->k, n_ranges, shift, keys, sh->overflow);
@@ -296,8 +298,9 @@ extern "C" int32_t rb_sshard_combine_lookup(rb_sshard* sh, const uint8_t* home_a
     int32_t rc;
     const int B = sh->R * sh->W;
     const size_t sm_ans = TileAnswers::smem_bytes(B, kSlTile * kSlNJ);
-    if (sh->lookup_fast) SL_LAUNCH("ks_combine_lookup<1>", ks_combine_lookup<1>, (int)div_up(sh->n_items, (int64_t)kSlTile), sm_ans, sh->pos, sh->tile_meta, B, home_ans, sh->n_items, sh->hd, sh->hc, counts, (int64_t)0);
-    else SL_LAUNCH("ks_combine_lookup<0>", ks_combine_lookup<0>, (int)div_up(sh->n_items, (int64_t)kSlThreads * kChunk), sm_ans, sh->pos, sh->tile_meta, B, home_ans, sh->n_items, sh->hd, sh->hc, counts, (int64_t)0);
+    auto k1 = ks_combine_lookup<1, 6>; auto k0 = ks_combine_lookup<0, 6>;
+    if (sh->lookup_fast) SL_LAUNCH("ks_combine_lookup<1>", k1, (int)div_up(sh->n_items, (int64_t)kSlTile), sm_ans, sh->pos, sh->tile_meta, B, home_ans, sh->n_items, sh->hd, sh->hc, counts, (int64_t)0);
+    else SL_LAUNCH("ks_combine_lookup<0>", k0, (int)div_up(sh->n_items, (int64_t)kSlThreads * kChunk), sm_ans, sh->pos, sh->tile_meta, B, home_ans, sh->n_items, sh->hd, sh->hc, counts, (int64_t)0);
     return RB_OK;
 }
 // home side: keys of this rank's hash ranges from every rank -> distinct keys with multiplicities
@@ -306,7 +309,7 @@ extern "C" int32_t rb_sshard_dedup(rb_sshard* sh, const unsigned long long* recv
     rb_ctx* ctx = sh->ctx;
     LOCK(ctx);
     SlArena keys;
-    int32_t rc = ss_consumer(sh, (void*)recv_keys, recv_cnt, sh->KR, sh->key_cap, kSlThreads * kSlRoundKmers, &keys);
+    int32_t rc = ss_consumer(sh, (void*)recv_keys, recv_cnt, sh->KR, sh->key_cap, kSlThreads * kKeyE, &keys);
     if (rc) return rc;
     const int n_sub = 1 << sh->sub_bits;
     const int n_sub_regions = sh->KR << sh->sub_bits;
@@ -314,7 +317,7 @@ extern "C" int32_t rb_sshard_dedup(rb_sshard* sh, const unsigned long long* recv
     subs.cap = sh->sub_cap; subs.cursor_stride = 1;
     CK(cudaMemsetAsync(subs.cursor, 0, (size_t)n_sub_regions * 4, ctx->stream));
     int grid = 0;
-    const size_t sm_split = TileSort<unsigned long long, kSlRoundKmers, true>::smem_bytes(n_sub) + (size_t)(keys.B + 1) * 4;
+    const size_t sm_split = TileSort<unsigned long long, kKeyE, true>::smem_bytes(n_sub) + (size_t)(keys.B + 1) * 4;
     rc = sl_stream_grid(ctx, ks_split_keys, sm_split, &grid);
     if (rc) return rc;
     SL_LAUNCH("ks_split_keys", ks_split_keys, grid, sm_split, keys, sh->chunk_prefix, sh->sub_bits, 64 - sh->lg1 - sh->sub_bits, sh->W, subs, sh->overflow);
@@ -336,7 +339,7 @@ extern "C" int32_t rb_sshard_emit_probes(rb_sshard* sh, int32_t with_cbf, uint32
     CK(cudaMemsetAsync(probes.cursor, 0, (size_t)probes.B * kSlPad * 4, ctx->stream));
     const size_t sm_sort = TileSort<uint32_t, kSlRoundKmers * kSlNJ>::smem_bytes(probes.B);
     const int grid_d = (int)div_up(sh->n_dense, (int64_t)kSlTile);
-    SL_LAUNCH("ks_emit_probes", ks_emit_probes, grid_d, sm_sort, sh->dkey, sh->n_distinct, hm, sh->sg_route, with_cbf, probes, sh->pos, sh->tile_meta, sh->overflow);
+    SL_LAUNCH("ks_emit_probes", ks_emit_probes<6>, grid_d, sm_sort, sh->dkey, sh->n_distinct, hm, sh->sg_route, with_cbf, probes, sh->pos, sh->tile_meta, sh->overflow);
     return ss_pack_counts(sh, probes, send_cnt);
 }
 extern "C" int32_t rb_sshard_combine_insert(rb_sshard* sh, const uint8_t* home_ans, int32_t policy, uint32_t* send_raises, uint32_t* send_cnt) {
@@ -351,7 +354,7 @@ extern "C" int32_t rb_sshard_combine_insert(rb_sshard* sh, const uint8_t* home_a
     const int B = sh->R * sh->W;
     const size_t sm_r = std::max(TileSort<uint32_t, kSlRoundKmers * kSlMaxH>::smem_bytes(raises.B), TileAnswers::smem_bytes(B, kSlTile * kSlNJ));
     const int grid_d = (int)div_up(sh->n_dense, (int64_t)kSlTile);
-    SL_LAUNCH("ks_combine_insert", ks_combine_insert, grid_d, sm_r, sh->dkey, sh->dmult, sh->n_distinct, sh->pos, sh->tile_meta, B, home_ans, hm, sh->sg_route, policy, seed,
+    SL_LAUNCH("ks_combine_insert", ks_combine_insert<6>, grid_d, sm_r, sh->dkey, sh->dmult, sh->n_distinct, sh->pos, sh->tile_meta, B, home_ans, hm, sh->sg_route, policy, seed,
               raises, sh->overflow);
     return ss_pack_counts(sh, raises, send_cnt);
 }

@@ -662,6 +662,7 @@ struct ReadsArg {
     const uint64_t* packed; const uint32_t* mask; const int64_t* read_off; const int32_t* read_len;
     int64_t n_reads; int32_t uniform_len; int64_t uniform_stride;
     bool on_device;
+    int64_t read0 = 0;   // uniform layout: index of the first read inside `packed` (a launch handed on as a ReadsArg of its own)
 };
 // One launch worth of reads, all pointers on the device.
 struct Launch { Ingest ing; int64_t n_pos; };
@@ -687,7 +688,7 @@ static int32_t for_each_launch(rb_ctx* ctx, const ReadsArg& ra, int span, Launch
                 memset(&ing, 0, sizeof ing);
                 ing.n_reads = nr; ing.n_pos = nr * npos; ing.out_base = r0 * npos;
                 ing.uniform_stride = ra.uniform_stride; ing.uniform_len = ra.uniform_len; ing.uniform_npos = npos;
-                const int64_t b_lo = r0 * ra.uniform_stride, b_hi = (r0 + nr - 1) * ra.uniform_stride + ra.uniform_len;
+                const int64_t b_lo = (ra.read0 + r0) * ra.uniform_stride, b_hi = (ra.read0 + r0 + nr - 1) * ra.uniform_stride + ra.uniform_len;
                 if (ra.on_device) { ing.packed = ra.packed; ing.mask = ra.mask; ing.first_base = b_lo; }
                 else {
                     const int64_t w_lo = b_lo >> 5, w_hi = (b_hi + 31) >> 5;
@@ -814,6 +815,10 @@ extern "C" int32_t rb_kmerize_pairs(rb_ctx* ctx, const uint64_t* packed, const u
 }
 
 // ---- graph ---------------------------------------------------------------------------------------------------------------
+static int engine_from_env() {   // RB_ENGINE = direct | sliced | (anything else) auto
+    const char* eng = getenv("RB_ENGINE");
+    return (eng && !strcmp(eng, "direct")) ? RB_ENGINE_DIRECT : (eng && !strcmp(eng, "sliced")) ? RB_ENGINE_SLICED : RB_ENGINE_AUTO;
+}
 extern "C" int32_t rb_graph_create(rb_ctx* ctx, int64_t dbg_bits, int64_t cbf_bytes, int64_t pkbf_bits, int32_t hd, int32_t hc, int32_t hp,
                                    int32_t k, int32_t stranded, int32_t use_pairs, rb_graph** out) {
     if (!ctx || !out) return RB_EINVAL;
@@ -834,8 +839,7 @@ extern "C" int32_t rb_graph_create(rb_ctx* ctx, int64_t dbg_bits, int64_t cbf_by
     }
     g->dbg->in_graph = g->cbf->in_graph = true;
     if (g->rpk) g->rpk->in_graph = true;
-    const char* eng = getenv("RB_ENGINE");
-    g->engine = (eng && !strcmp(eng, "direct")) ? RB_ENGINE_DIRECT : (eng && !strcmp(eng, "sliced")) ? RB_ENGINE_SLICED : RB_ENGINE_AUTO;
+    g->engine = engine_from_env();
     *out = g;
     return RB_OK;
 }
@@ -903,7 +907,7 @@ static void launch_insert_mode(int mode, int policy, int grid, cudaStream_t s, c
     else if (mode == RB_MODE_RC) launch_insert<1, MAXH>(policy, grid, s, ing, gd);
     else launch_insert<2, MAXH>(policy, grid, s, ing, gd);
 }
-struct InsertUser { rb_graph* g; int mode, policy; };
+struct InsertUser { rb_graph* g; int mode, policy; int64_t direct_subbatch; bool direct_only; };
 static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int policy, bool* fell_back);
 static int32_t sliced_count_round(rb_graph* g, const Ingest& ing, int mode, float* counts, int64_t* fh, int64_t* rh, bool* fell_back);
 static int64_t sliced_round_kmers(const rb_ctx* ctx, bool host_results);
@@ -922,12 +926,26 @@ struct RoundSize {
     }
     ~RoundSize() { c->subbatch_kmers = keep; }
 };
+static int32_t for_each_launch(rb_ctx* ctx, const ReadsArg& ra, int span, LaunchFn fn, void* user, int64_t* total_out);
 static int32_t insert_launch(rb_ctx* ctx, const Ingest& ing, void* user) {
     InsertUser* u = (InsertUser*)user;
-    if (use_sliced(u->g, ing.n_pos)) {
+    if (!u->direct_only && use_sliced(u->g, ing.n_pos)) {
         bool fell_back = false;
         const int32_t rc = sliced_insert_round(u->g, ing, u->mode, u->policy, &fell_back);
         if (rc || !fell_back) return rc;
+        if (ing.n_pos > u->direct_subbatch) {
+            // a sliced round handed back (skew beyond the spill path, or no memory for the work buffers) is as large as 2^29 k-mers: the
+            // direct engine takes it in launches of its own size, so that its claim table stays bounded (8 B x 2 x k-mers per launch)
+            ReadsArg sub{ing.packed, ing.mask, ing.read_off, ing.read_len, ing.n_reads, ing.uniform_len, ing.uniform_stride, true};
+            if (!ing.pos_off) sub.read0 = ing.first_base / ing.uniform_stride;
+            InsertUser u2 = *u;
+            u2.direct_only = true;
+            const int64_t keep = ctx->subbatch_kmers;
+            ctx->subbatch_kmers = u->direct_subbatch;
+            const int32_t rc2 = for_each_launch(ctx, sub, u->g->k, insert_launch, &u2, nullptr);
+            ctx->subbatch_kmers = keep;
+            return rc2;
+        }
     }
     GraphDev gd = graph_view(u->g);
     if (u->policy == POLICY_ADD) { const int32_t rc = claim_reserve(ctx, ing.n_pos, gd.dbg.words, &gd.ct); if (rc) return rc; }
@@ -975,7 +993,8 @@ static int32_t graph_add_reads(rb_graph* g, const ReadsArg& ra, uint32_t flags, 
     const int mode = graph_mode(g, flags);
     int64_t total = 0;
     if (!(flags & RB_PAIRS_EXISTING_ONLY)) {
-        InsertUser u{g, mode, (flags & RB_DBG_ONLY) ? POLICY_DBG_ONLY : (flags & RB_ADD_COUNT_IF_PRESENT) ? POLICY_COUNT_IF_PRESENT : POLICY_ADD};
+        InsertUser u{g, mode, (flags & RB_DBG_ONLY) ? POLICY_DBG_ONLY : (flags & RB_ADD_COUNT_IF_PRESENT) ? POLICY_COUNT_IF_PRESENT : POLICY_ADD,
+                     ctx->subbatch_kmers, false};
         RoundSize rs(g, false);
         const int32_t rc = for_each_launch(ctx, ra, g->k, insert_launch, &u, &total);
         if (rc) return rc;
@@ -1252,7 +1271,16 @@ extern "C" int32_t rb_graph_load(rb_ctx* ctx, const char* path, int32_t load_dbg
         return rc;
     }
     g->hd = g->dbg->num_hash; g->hc = g->cbf->num_hash; g->hp = g->rpk ? g->rpk->num_hash : (g->fpk ? g->fpk->num_hash : 0);
+    // the file's dbgbfCbfMaxNumHash is max(h_d, h_c) by construction (graph :83); a file that says otherwise is inconsistent
+    if (g->hmax != 0 && g->hmax != std::max(g->hd, g->hc)) {
+        filter_free(g->dbg); filter_free(g->cbf);
+        if (g->rpk) filter_free(g->rpk);
+        if (g->fpk) filter_free(g->fpk);
+        delete g;
+        return fail(ctx, RB_EIO, "graph desc: dbgbfCbfMaxNumHash does not match the filters' numhash");
+    }
     g->hmax = std::max(g->hd, g->hc);
+    g->engine = engine_from_env();
     g->dbg->in_graph = g->cbf->in_graph = true;
     if (g->rpk) g->rpk->in_graph = true;
     if (g->fpk) g->fpk->in_graph = true;

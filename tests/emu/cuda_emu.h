@@ -178,7 +178,7 @@ inline Launcher<K> launcher(long long grid, long long block, size_t smem, void*,
 
 #define blockDim emu::g_blockDim
 #define gridDim emu::g_gridDim
-#define RB_LAUNCH(grid, block, smem, stream, ...) emu::launcher((grid), (block), (smem), (void*)(stream), &__VA_ARGS__)
+#define RB_LAUNCH(grid, block, smem, stream, ...) emu::launcher((grid), (block), (smem), (void*)(stream), __VA_ARGS__)
 #define RB_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::g_dyn_smem)
 
 static inline void __syncthreads() { emu::cta_sync(); }

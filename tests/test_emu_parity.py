@@ -46,7 +46,8 @@ def ctx(emu_lib):
     c.close()
 
 
-SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_RAISE_LOG2": "14", "RB_SLICED_SUBRANGE_LOG2": "6"}
+SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_RAISE_LOG2": "14", "RB_SLICED_SUBRANGE_LOG2": "6",
+             "RB_SLICE_PAIR_LOG2": "13"}
 # sliced-small: tiny slices / sub-ranges so that the small test filters span hundreds of regions (every test);
 # sliced-default: the production geometry; direct: validates the emulation itself (that engine is verified on the GPU)
 # sliced-small-spill: RB_SLICED_SPILL=1 with region capacities far below the expected load, so that a large part of the keys takes
@@ -56,7 +57,7 @@ ONLY = {
     "sliced-small-spill": ("test_duplicates_inside_one_batch_are_linearised", "test_skewed_batch_is_redone_by_the_direct_engine"),
     "direct": ("test_getkmers_with_invalid_nucleotides", "test_neighbor_counts_match_oracle"),
     "sliced-default": ("test_getkmers_with_invalid_nucleotides", "test_insert_policies_and_pair_filters", "test_kernels_are_race_free_under_tsan",
-                       "test_random_geometry_matches_oracle", "test_random_uniform_layout_matches_oracle"),
+                       "test_random_geometry_matches_oracle", "test_random_uniform_layout_matches_oracle", "test_paired_slices_match_oracle"),
 }
 SKIP = {"sliced-small": ("test_kernels_are_race_free_under_tsan", "test_neighbor_counts_match_oracle", "test_random_geometry_matches_oracle",
                          "test_random_uniform_layout_matches_oracle"),
@@ -89,6 +90,15 @@ test_duplicates_inside_one_batch_are_linearised = G.test_duplicates_inside_one_b
 test_getkmers_with_invalid_nucleotides = G.test_getkmers_with_invalid_nucleotides
 test_insert_policies_and_pair_filters = G.test_insert_policies_and_pair_filters
 test_neighbor_counts_match_oracle = G.test_neighbor_counts_match_oracle
+
+
+# paired probe records (cbf_bytes a power of two dividing dbg_bits): q = 8, q = 5 (stranded), h_d > h_c, and the h_d < h_c case that must
+# stay unpaired; both read layouts
+@pytest.mark.parametrize("layout", ["ragged", "uniform"])
+@pytest.mark.parametrize("stranded,k,hd,hc,dbg_bits,cbf_bytes", [(False, 25, 3, 3, 1 << 29, 1 << 26), (True, 25, 3, 3, 5 << 24, 1 << 24),
+                                                                 (False, 31, 3, 2, 1 << 27, 1 << 27), (False, 25, 2, 3, 1 << 29, 1 << 26)])
+def test_paired_slices_match_oracle(ctx, orc, stranded, k, hd, hc, dbg_bits, cbf_bytes, layout):
+    G.test_paired_slices_match_oracle(ctx, orc, stranded, k, hd, hc, dbg_bits, cbf_bytes, layout)
 
 
 def test_skewed_batch_is_redone_by_the_direct_engine(ctx, orc, monkeypatch):
@@ -141,6 +151,10 @@ def test_random_geometry_matches_oracle(ctx, orc, seed, monkeypatch):
     stranded = bool(rng.integers(0, 2))
     dbg_bits = int(rng.integers(1 << 16, 1 << 25)) | 1
     cbf_bytes = int(rng.integers(1 << 20, 1 << 23)) | 1       # roomy: counters of distinct k-mers rarely collide, the comparison stays tight
+    if seed % 2:   # sizes the engine pairs the probe records for (when h_d >= h_c): cbf_bytes = 2^c, dbg_bits = q * cbf_bytes
+        cbf_bytes = 1 << int(rng.integers(20, 23))
+        dbg_bits = cbf_bytes * int(rng.integers(1, 17))
+        monkeypatch.setenv("RB_SLICE_PAIR_LOG2", str(int(rng.integers(8, 19))))
     for name, lo, hi in (("RB_SLICE_BITS_LOG2", 12, 22), ("RB_SLICE_BYTES_LOG2", 10, 20), ("RB_SLICE_RAISE_LOG2", 8, 18),
                          ("RB_SLICED_SUBRANGE_LOG2", 4, 9)):
         monkeypatch.setenv(name, str(int(rng.integers(lo, hi + 1))))

@@ -23,10 +23,12 @@ ENGINE_TESTS = {"test_graph_add_collision_free_is_bit_exact", "test_duplicates_i
                 "test_loaded_filter_dbgbf_exact_cbf_within_envelope", "test_insert_policies_and_pair_filters", "test_pairs_existing_only",
                 "test_fastq_ascii_ingest_matches_regex_segmentation", "test_getkmers_with_invalid_nucleotides",
                 "test_subbatching_and_claim_table_recycling_do_not_change_results", "test_full_size_filters_properties",
-                "test_upload_download_save_load_roundtrip", "test_uniform_layout_graph_matches_oracle", "test_skewed_batch_is_redone_by_the_direct_engine"}
+                "test_upload_download_save_load_roundtrip", "test_uniform_layout_graph_matches_oracle", "test_skewed_batch_is_redone_by_the_direct_engine",
+                "test_paired_slices_match_oracle"}
 # "sliced-small": slices of 16 KiB / 32 KiB so that the small test filters span hundreds of regions (the default 64 MiB slices
 # would put every test filter into one or two regions and leave the multi-region paths to the full-size test alone)
-SMALL_SLICES = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_RAISE_LOG2": "14", "RB_SLICED_SUBRANGE_LOG2": "6"}
+SMALL_SLICES = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_RAISE_LOG2": "14", "RB_SLICED_SUBRANGE_LOG2": "6",
+                "RB_SLICE_PAIR_LOG2": "13"}
 
 
 @pytest.fixture(autouse=True, params=["direct", "sliced", "sliced-small"])
@@ -264,6 +266,51 @@ def test_graph_add_collision_free_is_bit_exact(ctx, orc, stranded, k, hd, hc, n_
         off += m
     assert g.getDbgbf().getPopCount() == int(np.unpackbits(og.dbgbf()).sum())
     assert g.getCbf().getPopCount() == int((og.cbf() != 0).sum())
+    g.destroy(), og.close()
+
+
+@pytest.mark.parametrize("layout", ["ragged", "uniform"])
+@pytest.mark.parametrize("stranded,k,hd,hc,dbg_bits,cbf_bytes", [(False, 25, 3, 3, 1 << 29, 1 << 26), (True, 25, 3, 3, 5 << 24, 1 << 24),
+                                                                 (False, 31, 3, 2, 1 << 27, 1 << 27), (False, 21, 2, 2, 24 << 22, 1 << 22),
+                                                                 (False, 25, 2, 3, 1 << 29, 1 << 26)])
+def test_paired_slices_match_oracle(ctx, orc, stranded, k, hd, hc, dbg_bits, cbf_bytes, layout):
+    """Filter sizes where the sliced engine pairs the probes (cbf_bytes a power of two dividing dbg_bits, h_d >= h_c: one record per
+    hash serves both filters, rb_sliced.cuh SlShape<3>) -- and one (h_d < h_c) where it must not.  Same contract as everywhere:
+    dbgbf byte-identical, cbf identical except on shared counters, counts and hashes exact; ragged reads go through the rolling
+    walker kernels, the uniform layout through the prefix k-merizer."""
+    n_reads = 700
+    reads = orc.synth_reads(900 + k, 40000, 0, n_reads, 150, 7000)
+    seqs = [bytes(r) for r in reads]
+    if layout == "ragged":
+        seqs[5] = seqs[5][:60] + b"N" + seqs[5][61:]
+        seqs[9] = seqs[9][:97]
+    g, og = make_graphs(ctx, orc, dbg_bits, cbf_bytes, 64, hd, hc, 1, k, stranded, False)
+    for s in seqs + seqs[:150]:
+        og.add_read(s)
+    assert og.cbf().max() <= 16
+    if layout == "ragged":
+        g.addReads(rb.pack_reads(seqs))
+        g.addReads(rb.pack_reads(seqs[:150]))
+        q = rb.pack_reads(seqs[:200])
+    else:
+        code = np.zeros(256, dtype=np.uint8)
+        code[[ord(c) for c in "ACGT"]] = [0, 1, 2, 3]
+        arr = code[np.frombuffer(b"".join(seqs), dtype=np.uint8).reshape(n_reads, 150)]
+        g.addReads(rb.pack_uniform(arr, 160))
+        g.addReads(rb.pack_uniform(arr[:150], 160))
+        q = rb.pack_uniform(arr[:200], 160)
+    assert (g.getDbgbf().download() == og.dbgbf()).all(), "dbgbf differs"
+    bases = all_bases(orc, seqs, k, [MODE_FWD if stranded else MODE_CANON])
+    allowed, frac = counters_that_may_differ(bases, k, hc, cbf_bytes)
+    diff = np.nonzero(g.getCbf().download() != og.cbf())[0]
+    assert frac < 0.06 and set(diff.tolist()) <= allowed, "cbf differs on counters no other k-mer shares"
+    counts, fh, rh = g.getKmers(q)
+    want = [og.count_seq(s) for s in seqs[:200]]
+    assert (fh == np.concatenate([w[1] for w in want])).all()
+    if not stranded:
+        assert (rh == np.concatenate([w[2] for w in want])).all()
+    wc = np.concatenate([w[0] for w in want])
+    assert (counts == wc).mean() > (0.999 if len(diff) else 0.99999)
     g.destroy(), og.close()
 
 
