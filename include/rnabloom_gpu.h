@@ -208,41 +208,6 @@ RB_API int32_t rb_graph_lookup_pair_hashes(rb_graph* g, int32_t which, const int
 RB_API int32_t rb_graph_save(rb_graph* g, const char* path);
 RB_API int32_t rb_graph_load(rb_ctx* ctx, const char* path, int32_t load_dbgbf, int32_t load_fpkbf, rb_graph** out);
 
-/* ---- hash-sharded graph: one rank's share of filters that are split by index range over the GPUs of a box ----------------
- * The logical dbgbf / cbf stay the reference's single arrays (graph/BloomFilterDeBruijnGraph.java:75-104); rank r holds indices
- * [r*shard, (r+1)*shard).  A step is a fixed sequence of phases; between phases the caller exchanges the fixed-capacity send regions
- * ([n_ranks][cap] records + [n_ranks] counts) with an all-to-all (NCCL over NVLink; rna-bloom_b200/sharded.py is the orchestrator).
- * All pointers of the phase calls are DEVICE pointers; calls are stream-ordered on the context's stream.
- *   insert: route_keys -> a2a -> aggregate, emit_dbg -> a2a -> apply_dbg -> a2a back -> emit_cbf_reads -> a2a -> apply_cbf_read
- *           -> a2a back -> emit_cbf_raises -> a2a -> apply_cbf_raise
- *   lookup: route_lookup -> a2a -> apply_lookup -> a2a back -> combine_lookup
- * policy: 0 graph.add (:405-412), 1 addCountIfPresent (:424-428), 2 addDbgOnly (:430-436; stop after apply_dbg). */
-typedef struct rb_shard rb_shard;
-RB_API int32_t rb_shard_create(rb_ctx* ctx, int32_t n_ranks, int32_t rank, int64_t dbgbf_bits, int64_t cbf_bytes, int32_t dbgbf_num_hash,
-                               int32_t cbf_num_hash, int32_t k, int32_t stranded, int64_t max_kmers_per_round, rb_shard** out);
-RB_API int32_t rb_shard_destroy(rb_shard* sh);
-/* geom[0..9] = cap_keys, cap_dbg, cap_cbf, cap_lookup (records per send region), dbg_shard_bits, cbf_shard_bytes, local_dbg_bits,
- * local_cbf_bytes, regions_per_rank, count_stride.  A send buffer holds n_ranks * regions_per_rank regions of `cap` records, grouped by
- * destination rank; the count array holds one int32 per region, count_stride ints apart. */
-RB_API int32_t rb_shard_geometry(rb_shard* sh, int64_t* geom);
-RB_API int32_t rb_shard_filter(rb_shard* sh, int32_t which, rb_filter** out);   /* local share as a filter handle (download, popcount) */
-RB_API int32_t rb_shard_overflow(rb_shard* sh, int32_t* flag);                  /* 1 if any send region overflowed since the last call */
-RB_API int32_t rb_shard_route_keys(rb_shard* sh, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
-                                   int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, uint32_t flags, int64_t* send, int32_t* cnt,
-                                   int64_t* n_kmers_out);
-RB_API int32_t rb_shard_aggregate(rb_shard* sh, const int64_t* recv, const int32_t* recv_cnt);
-RB_API int32_t rb_shard_emit_dbg(rb_shard* sh, int64_t* send, int32_t* cnt);
-RB_API int32_t rb_shard_apply_dbg(rb_shard* sh, const int64_t* recv, const int32_t* recv_cnt, uint8_t* reply, int32_t set_bits);
-RB_API int32_t rb_shard_emit_cbf_reads(rb_shard* sh, const uint8_t* reply_home, int32_t policy, int64_t* send, int32_t* cnt);
-RB_API int32_t rb_shard_apply_cbf_read(rb_shard* sh, const int64_t* recv, const int32_t* recv_cnt, uint8_t* reply);
-RB_API int32_t rb_shard_emit_cbf_raises(rb_shard* sh, const uint8_t* reply_home, int32_t policy, int64_t* send, int32_t* cnt);
-RB_API int32_t rb_shard_apply_cbf_raise(rb_shard* sh, const int64_t* recv, const int32_t* recv_cnt);
-RB_API int32_t rb_shard_route_lookup(rb_shard* sh, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
-                                     int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, int64_t* send, int32_t* cnt, int64_t* fhash,
-                                     int64_t* rhash, int64_t* n_kmers_out);
-RB_API int32_t rb_shard_apply_lookup(rb_shard* sh, const int64_t* recv, const int32_t* recv_cnt, uint8_t* reply);
-RB_API int32_t rb_shard_combine_lookup(rb_shard* sh, const uint8_t* reply_home, float* counts);
-
 /* ---- synthetic workload generator (bench + fixtures; not a reference operator) ----------------------------------
  * Deterministic, counter-based: read r of a virtual genome (seed, genome_len), length L, err_ppm substitutions per
  * 1e6 bases; written in the uniform ingest layout (stride = stride_bases, multiple of 32) into device memory. */

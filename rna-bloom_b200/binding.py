@@ -7,7 +7,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 _SO = os.path.join(_HERE, "librnabloom_gpu.so")
-_SRC = [os.path.join(_HERE, "csrc", n) for n in ("rnabloom_gpu.cu", "rb_kernels.cuh", "rb_device.cuh", "rb_shard.cuh", "rb_sliced.cuh",
+_SRC = [os.path.join(_HERE, "csrc", n) for n in ("rnabloom_gpu.cu", "rb_kernels.cuh", "rb_device.cuh", "rb_sliced.cuh",
                                                  "rb_sliced_host.inl", "rb_sshard_host.inl")] + [
     os.path.join(_ROOT, "include", "rnabloom_gpu.h")]
 
@@ -133,22 +133,6 @@ def bind(path, allow_missing=False):
         "rb_graph_neighbor_counts": (i32, [vp, vp, vp, vp, vp, i64, vp, vp, vp]),
         "rb_graph_save": (i32, [vp, cp]),
         "rb_graph_load": (i32, [vp, cp, i32, i32, C.POINTER(vp)]),
-        "rb_shard_create": (i32, [vp, i32, i32, i64, i64, i32, i32, i32, i32, i64, C.POINTER(vp)]),
-        "rb_shard_destroy": (i32, [vp]),
-        "rb_shard_geometry": (i32, [vp, C.POINTER(i64)]),
-        "rb_shard_filter": (i32, [vp, i32, C.POINTER(vp)]),
-        "rb_shard_overflow": (i32, [vp, C.POINTER(i32)]),
-        "rb_shard_route_keys": (i32, [vp] + reads + [u32, vp, vp, C.POINTER(i64)]),
-        "rb_shard_aggregate": (i32, [vp, vp, vp]),
-        "rb_shard_emit_dbg": (i32, [vp, vp, vp]),
-        "rb_shard_apply_dbg": (i32, [vp, vp, vp, vp, i32]),
-        "rb_shard_emit_cbf_reads": (i32, [vp, vp, i32, vp, vp]),
-        "rb_shard_apply_cbf_read": (i32, [vp, vp, vp, vp]),
-        "rb_shard_emit_cbf_raises": (i32, [vp, vp, i32, vp, vp]),
-        "rb_shard_apply_cbf_raise": (i32, [vp, vp, vp]),
-        "rb_shard_route_lookup": (i32, [vp] + reads + [vp, vp, vp, vp, C.POINTER(i64)]),
-        "rb_shard_apply_lookup": (i32, [vp, vp, vp, vp]),
-        "rb_shard_combine_lookup": (i32, [vp, vp, vp]),
         "rb_synth_reads_dev": (i32, [vp, u64, u64, u64, i64, i32, u32, i64, vp]),
         "rb_sshard_create": (i32, [vp, i32, i32, i64, i64, i32, i32, i32, i32, i64, C.POINTER(vp)]),
         "rb_sshard_destroy": (i32, [vp]),

@@ -86,6 +86,34 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
 
 // ---- HBM access: filters are written by other SMs during a kernel, so loads go to L2 (ld.global.cg) ---------------
 __device__ __forceinline__ uint32_t ld_cg(const uint32_t* p) { return __ldcg(p); }
+// The sliced engine keeps one filter slice resident in L2 while records and answers stream past it: accesses to the slice carry an
+// L2 evict_last policy, the streams are read / written with .cs (evict first).  Without the hints the streams push slice lines out
+// (ncu: 49 GB of DRAM reads per look-up round where records + one sweep of the filters are 23 GB).
+#ifdef RB_EMU
+struct L2Keep { };
+__device__ __forceinline__ L2Keep l2_keep_policy() { return L2Keep(); }
+__device__ __forceinline__ uint32_t ld_cg_keep(const uint32_t* p, L2Keep) { return __ldcg(p); }
+__device__ __forceinline__ uint32_t atomic_or_keep(uint32_t* p, uint32_t v, L2Keep) { return atomicOr(p, v); }
+__device__ __forceinline__ uint32_t atomic_cas_keep(uint32_t* p, uint32_t cmp, uint32_t v, L2Keep) { return atomicCAS(p, cmp, v); }
+#else
+struct L2Keep { uint64_t pol; };
+__device__ __forceinline__ L2Keep l2_keep_policy() {
+    L2Keep k;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(k.pol));
+    return k;
+}
+__device__ __forceinline__ uint32_t ld_cg_keep(const uint32_t* p, L2Keep k) {
+    uint32_t v;
+    asm volatile("ld.global.cg.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(k.pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t atomic_or_keep(uint32_t* p, uint32_t v, L2Keep k) {
+    uint32_t old;
+    asm volatile("atom.global.or.L2::cache_hint.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(v), "l"(k.pol) : "memory");
+    return old;
+}
+__device__ __forceinline__ uint32_t atomic_cas_keep(uint32_t* p, uint32_t cmp, uint32_t v, L2Keep) { return atomicCAS(p, cmp, v); }   // PTX: atom.cas takes no cache hint
+#endif
 
 // ---- filter views ---------------------------------------------------------------------------------------------------
 struct BitFilter {    // BloomFilter over UnsafeBitBuffer: bit i = byte i/8, mask 1<<(i%8) == bit (i&31) of LE word i>>5
@@ -121,6 +149,16 @@ __device__ __forceinline__ void byte_raise(uint32_t* wp, int sh, uint32_t v, uin
         if (((old >> sh) & 0x7Fu) >= v) return;
         const uint32_t nw = (old & ~(0x7Fu << sh)) | (v << sh);
         const uint32_t got = atomicCAS(wp, old, nw);
+        if (got == old) return;
+        old = got;
+    }
+}
+
+__device__ __forceinline__ void byte_raise_keep(uint32_t* wp, int sh, uint32_t v, uint32_t old, L2Keep k) {
+    for (;;) {
+        if (((old >> sh) & 0x7Fu) >= v) return;
+        const uint32_t nw = (old & ~(0x7Fu << sh)) | (v << sh);
+        const uint32_t got = atomic_cas_keep(wp, old, nw, k);
         if (got == old) return;
         old = got;
     }

@@ -172,17 +172,17 @@ struct TileSort {
         stage = reinterpret_cast<REC*>(smem + words_of(B) * 4);
         tag = reinterpret_cast<uint16_t*>(smem + words_of(B) * 4 + (size_t)kSlThreads * E * sizeof(REC));
     }
-    // bkt[e] < 0: no record, else the record goes to region region0 + bkt[e] of `out`.  place[e] = bucket | rank inside the
-    // (tile, bucket) run << 12 (kNoSlot: no record).  meta (nullable, B + 1 entries): x = arena position of the bucket's run,
+    // In: place[e] = kNoSlot: no record, else the record goes to region region0 + place[e] of `out`.  Out: place[e] = bucket | rank inside
+    // the (tile, bucket) run << 12 (kNoSlot: no record).  meta (nullable, B + 1 entries): x = arena position of the bucket's run,
     // y = position of the run inside the tile's bucket-ordered sequence; entry B: y = number of records of the tile.  With them a
     // later kernel finds the tile's answers again: answer of a record = ans[meta[b].x + rank].  Every thread of the CTA calls it.
-    __device__ __forceinline__ void run(const SlArena& out, int region0, const int (&bkt)[E], const REC (&rec)[E], uint32_t (&place)[E], int* overflow,
+    __device__ __forceinline__ void run(const SlArena& out, int region0, uint32_t (&place)[E], const REC (&rec)[E], int* overflow,
                                         uint2* __restrict__ meta) {
         const int t = threadIdx.x;
         for (int b = t; b < B; b += kSlThreads) start[b] = 0;
         __syncthreads();
 #pragma unroll
-        for (int e = 0; e < E; ++e) place[e] = bkt[e] >= 0 ? ((uint32_t)bkt[e] | (atomicAdd(&start[bkt[e]], 1u) << 12)) : kNoSlot;
+        for (int e = 0; e < E; ++e) if (place[e] != kNoSlot) place[e] |= atomicAdd(&start[place[e]], 1u) << 12;
         __syncthreads();
         uint32_t at[kSlBucketsPerThread];
 #pragma unroll
@@ -240,25 +240,25 @@ struct TileSort {
 // the probes of one k-mer (bloom/hash/NTHash.java:518-527 + bloom/BloomFilter.java:108-111).  NJ = 6: slots 0..2 dbgbf, 3..5 cbf;
 // NJ = 3: slot j = hash j against both filters (slots >= hc: the counter half of the answer is ignored)
 template <int NJ>
-__device__ __forceinline__ void sl_probes(const SlGeom& sg, const HashMults& hm, uint64_t base, bool with_cbf, int* bkt, uint32_t* rec) {
+__device__ __forceinline__ void sl_probes(const SlGeom& sg, const HashMults& hm, uint64_t base, bool with_cbf, uint32_t* bkt, uint32_t* rec) {
 #pragma unroll
     for (int j = 0; j < kSlMaxH; ++j) {
         if (NJ == 3) {
             if (j < sg.hd) {
                 const uint64_t gd = fm_index(expand_hash(base, j, hm), sg.dbg_fm);
                 const uint64_t gc = gd & sg.cbf_fm.mask;   // == (h_j >>> 1) % cbf_bytes: cbf_bytes is a power of two dividing dbg_bits
-                bkt[j] = (int)(gc >> sg.pair_log2);
+                bkt[j] = (uint32_t)(gc >> sg.pair_log2);
                 rec[j] = (uint32_t)((gd >> sg.cbf_size_log2) << sg.pair_log2) | (uint32_t)(gc & ((1ULL << sg.pair_log2) - 1));
             }
         } else {
             if (j < sg.hd) {
                 const uint64_t gi = fm_index(expand_hash(base, j, hm), sg.dbg_fm);
-                bkt[j] = sl_dbg_region(sg, gi);
+                bkt[j] = (uint32_t)sl_dbg_region(sg, gi);
                 rec[j] = (uint32_t)(gi & ((1ULL << sg.dbg_log2) - 1));
             }
             if (with_cbf && j < sg.hc) {
                 const uint64_t gi = fm_index(expand_hash(base, j, hm), sg.cbf_fm);
-                bkt[kSlMaxH + j] = sl_cbf_region(sg, gi);
+                bkt[kSlMaxH + j] = (uint32_t)sl_cbf_region(sg, gi);
                 rec[kSlMaxH + j] = (uint32_t)(gi & ((1ULL << sg.cbf_log2) - 1));
             }
         }
@@ -410,7 +410,7 @@ using KeyKmerizer = PrefixKmerizer<8, kSlTile>;
 
 // ---- S1 (uniform layout): one CTA = SlShape<NJ>::TILE consecutive k-mer positions, hashed through the prefix arrays, one tile sort ------
 template <int MODE, int NJ>
-__global__ void __launch_bounds__(kSlThreads) ks_route_lookup_u(const Ingest g, int k, const HashMults hm, const SlGeom sg, const SlArena arena,
+__global__ void __launch_bounds__(kSlThreads, 3) ks_route_lookup_u(const Ingest g, int k, const HashMults hm, const SlGeom sg, const SlArena arena,
                                                                uint32_t* __restrict__ pos, uint2* __restrict__ tile_meta, int64_t* __restrict__ fhash,
                                                                int64_t* __restrict__ rhash, int* overflow) {
     RB_DYN_SMEM(unsigned char, sl_smem);
@@ -421,25 +421,24 @@ __global__ void __launch_bounds__(kSlThreads) ks_route_lookup_u(const Ingest g, 
     pk.template build<MODE>(sl_smem, g, k, tile0);
     // item i of thread t = position tile0 + i * 256 + t: consecutive lanes read consecutive prefix entries (no bank conflicts) and
     // write consecutive place records
-    int bkt[KPT * NJ];
     uint32_t rec[KPT * NJ], slot[KPT * NJ];
 #pragma unroll
     for (int i = 0; i < KPT; ++i) {
         const int64_t p = tile0 + i * kSlThreads + threadIdx.x;
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) { bkt[i * NJ + j] = -1; rec[i * NJ + j] = 0; }
+        for (int j = 0; j < NJ; ++j) { slot[i * NJ + j] = kNoSlot; rec[i * NJ + j] = 0; }
         if (p < g.n_pos) {
             uint64_t f, r; int bad;
             pk.template eval<MODE>(g, k, p, f, r, bad);
             if (fhash) fhash[g.out_base + p] = (int64_t)f;
             if (rhash) rhash[g.out_base + p] = (int64_t)r;
-            if (bad == 0) sl_probes<NJ>(sg, hm, PK::template base_of<MODE>(f, r), true, &bkt[i * NJ], &rec[i * NJ]);
+            if (bad == 0) sl_probes<NJ>(sg, hm, PK::template base_of<MODE>(f, r), true, &slot[i * NJ], &rec[i * NJ]);
         }
     }
     __syncthreads();   // the tile sort reuses the shared memory of the prefix arrays
     TileSort<uint32_t, KPT * NJ> ts;
     ts.init(sl_smem, arena.B);
-    ts.run(arena, 0, bkt, rec, slot, overflow, tile_meta + (size_t)blockIdx.x * (arena.B + 1));
+    ts.run(arena, 0, slot, rec, overflow, tile_meta + (size_t)blockIdx.x * (arena.B + 1));
 #pragma unroll
     for (int i = 0; i < KPT; ++i) {
         const int64_t p = tile0 + i * kSlThreads + threadIdx.x;
@@ -454,17 +453,16 @@ constexpr int kKeySub = 4;
 constexpr int kKeyE = kSlRoundKmers * kKeySub;    // keys per thread and tile sort
 constexpr int kKeyTile = kSlTile * kKeySub;       // 4096
 template <int MODE>
-__global__ void __launch_bounds__(kSlThreads) ks_route_keys_u(const Ingest g, int k, int n_ranges, int range_shift, const SlArena arena, int* overflow) {
+__global__ void __launch_bounds__(kSlThreads, 3) ks_route_keys_u(const Ingest g, int k, int n_ranges, int range_shift, const SlArena arena, int* overflow) {
     RB_DYN_SMEM(unsigned char, sl_smem);
     const int64_t tile0 = (int64_t)blockIdx.x * kKeyTile;
-    int bkt[kKeyE];
     unsigned long long rec[kKeyE];
     uint32_t slot[kKeyE];
 #pragma unroll
     for (int s = 0; s < kKeySub; ++s) {
         const int64_t sub0 = tile0 + (int64_t)s * kSlTile;
 #pragma unroll
-        for (int i = 0; i < kSlRoundKmers; ++i) { bkt[s * kSlRoundKmers + i] = -1; rec[s * kSlRoundKmers + i] = 0; }
+        for (int i = 0; i < kSlRoundKmers; ++i) { slot[s * kSlRoundKmers + i] = kNoSlot; rec[s * kSlRoundKmers + i] = 0; }
         if (sub0 < g.n_pos) {   // the whole CTA
             KeyKmerizer pk;
             pk.build<MODE>(sl_smem, g, k, sub0);
@@ -477,7 +475,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_route_keys_u(const Ingest g, in
                     if (bad == 0) {
                         const uint64_t b = KeyKmerizer::base_of<MODE>(f, r);
                         rec[s * kSlRoundKmers + i] = b;
-                        bkt[s * kSlRoundKmers + i] = n_ranges > 1 ? (int)(sl_mixkey(b) >> range_shift) : 0;
+                        slot[s * kSlRoundKmers + i] = n_ranges > 1 ? (uint32_t)(sl_mixkey(b) >> range_shift) : 0;
                     }
                 }
             }
@@ -486,7 +484,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_route_keys_u(const Ingest g, in
     }
     TileSort<unsigned long long, kKeyE, true> ts;
     ts.init(sl_smem, arena.B);
-    ts.run(arena, 0, bkt, rec, slot, overflow, nullptr);
+    ts.run(arena, 0, slot, rec, overflow, nullptr);
 }
 
 // ---- S1: k-merise, tile-sort the probes of every usable k-mer instance by filter slice --------------------------------------------
@@ -506,21 +504,20 @@ __global__ void __launch_bounds__(kSlThreads) ks_route_lookup(const Ingest g, in
     if (n) pw.start(g, pos0, k, lut);
 #pragma unroll 1
     for (int r0 = 0; r0 < kChunk; r0 += KPT) {
-        int bkt[KPT * NJ];
         uint32_t rec[KPT * NJ], slot[KPT * NJ];
 #pragma unroll
         for (int i = 0; i < KPT; ++i) {
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) { bkt[i * NJ + j] = -1; rec[i * NJ + j] = 0; }
+            for (int j = 0; j < NJ; ++j) { slot[i * NJ + j] = kNoSlot; rec[i * NJ + j] = 0; }
             if (r0 + i < n) {
                 pw.advance(g, k, lut);
                 const int64_t o = g.out_base + pos0 + r0 + i;
                 if (fhash) fhash[o] = (int64_t)pw.wk.f;
                 if (rhash) rhash[o] = (int64_t)pw.wk.r;
-                if (pw.wk.bad == 0) sl_probes<NJ>(sg, hm, pw.wk.base(), true, &bkt[i * NJ], &rec[i * NJ]);
+                if (pw.wk.bad == 0) sl_probes<NJ>(sg, hm, pw.wk.base(), true, &slot[i * NJ], &rec[i * NJ]);
             }
         }
-        ts.run(arena, 0, bkt, rec, slot, overflow, tile_meta + ((size_t)blockIdx.x * (kChunk / KPT) + r0 / KPT) * (arena.B + 1));
+        ts.run(arena, 0, slot, rec, overflow, tile_meta + ((size_t)blockIdx.x * (kChunk / KPT) + r0 / KPT) * (arena.B + 1));
 #pragma unroll
         for (int i = 0; i < KPT; ++i) if (r0 + i < n) sl_store_places<NJ>(pos, pos0 + r0 + i, &slot[i * NJ]);
     }
@@ -582,6 +579,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
     const int total = pre[arena.B];
     const uint32_t* rec = reinterpret_cast<const uint32_t*>(arena.data);
     constexpr int U = 8;   // probes in flight per thread
+    const L2Keep keep = l2_keep_policy();
     __shared__ int s_c;
     for (int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c); c < total; c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c)) {
         const SlWork w = sl_work_item(arena, pre, c);
@@ -600,8 +598,8 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
                     if (i0 + u * kSlThreads < w.n) {
                         const uint64_t ci = byte0 + (li[u] & off_mask);
                         const uint64_t bi = (uint64_t)(li[u] >> sg.pair_log2) * sg.pair_local_c + ci;
-                        wd[u] = ld_cg(dbg_words + (bi >> 5));
-                        wc[u] = ld_cg(cbf_words + (ci >> 2));
+                        wd[u] = ld_cg_keep(dbg_words + (bi >> 5), keep);
+                        wc[u] = ld_cg_keep(cbf_words + (ci >> 2), keep);
                     }
                 }
 #pragma unroll
@@ -610,8 +608,8 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
                         const uint64_t ci = byte0 + (li[u] & off_mask);
                         const uint64_t bi = (uint64_t)(li[u] >> sg.pair_log2) * sg.pair_local_c + ci;
                         const uint32_t bit = 1u << (bi & 31);
-                        if (SET && !(wd[u] & bit)) wd[u] = atomicOr(dbg_words + (bi >> 5), bit);
-                        ans[w.first + i0 + u * kSlThreads] = (uint8_t)(((wd[u] & bit) ? 0x80u : 0u) | ((wc[u] >> ((ci & 3) * 8)) & 0x7Fu));
+                        if (SET && !(wd[u] & bit)) wd[u] = atomic_or_keep(dbg_words + (bi >> 5), bit, keep);
+                        __stcs(ans + w.first + i0 + u * kSlThreads, (uint8_t)(((wd[u] & bit) ? 0x80u : 0u) | ((wc[u] >> ((ci & 3) * 8)) & 0x7Fu)));
                     }
                 }
             }
@@ -626,7 +624,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 wd[u] = 0;
-                if (i0 + u * kSlThreads < w.n) wd[u] = is_dbg ? ld_cg(dbg_words + word0 + (li[u] >> 5)) : ld_cg(cbf_words + word0 + (li[u] >> 2));
+                if (i0 + u * kSlThreads < w.n) wd[u] = is_dbg ? ld_cg_keep(dbg_words + word0 + (li[u] >> 5), keep) : ld_cg_keep(cbf_words + word0 + (li[u] >> 2), keep);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -634,12 +632,12 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
                     uint32_t value;
                     if (is_dbg) {
                         const uint32_t bit = 1u << (li[u] & 31);
-                        if (SET && !(wd[u] & bit)) wd[u] = atomicOr(dbg_words + word0 + (li[u] >> 5), bit);
+                        if (SET && !(wd[u] & bit)) wd[u] = atomic_or_keep(dbg_words + word0 + (li[u] >> 5), bit, keep);
                         value = (wd[u] & bit) ? 0x80u : 0u;
                     } else {
                         value = (wd[u] >> ((li[u] & 3) * 8)) & 0x7Fu;
                     }
-                    ans[w.first + i0 + u * kSlThreads] = (uint8_t)value;
+                    __stcs(ans + w.first + i0 + u * kSlThreads, (uint8_t)value);
                 }
             }
         }
@@ -710,28 +708,27 @@ __global__ void __launch_bounds__(kSlThreads) ks_route_keys(const Ingest g, int 
     const int n = pos0 < g.n_pos ? (int)min((int64_t)kChunk, g.n_pos - pos0) : 0;
     PositionWalker<MODE> pw;
     if (n) pw.start(g, pos0, k, lut);
-    int bkt[kChunk];
     unsigned long long rec[kChunk];
     uint32_t slot[kChunk];
 #pragma unroll
     for (int i = 0; i < kChunk; ++i) {
-        bkt[i] = -1; rec[i] = 0;
+        slot[i] = kNoSlot; rec[i] = 0;
         if (i < n) {
             pw.advance(g, k, lut);
             if (pw.wk.bad == 0) {
                 const uint64_t b = pw.wk.base();
                 rec[i] = b;
-                bkt[i] = n_ranges > 1 ? (int)(sl_mixkey(b) >> range_shift) : 0;
+                slot[i] = n_ranges > 1 ? (uint32_t)(sl_mixkey(b) >> range_shift) : 0;
             }
         }
     }
-    ts.run(arena, 0, bkt, rec, slot, overflow, nullptr);
+    ts.run(arena, 0, slot, rec, overflow, nullptr);
 }
 
 // ---- I2: second-level split: the keys of every range are tile-sorted again by their next hash bits ------------------------------------------
 // After it a sub-range holds ~1 Ki keys: small enough for a shared-memory hash table, so no global table is ever touched
 // (the L2-sliced global table this replaces ran at 4-9 G keys/s: one CAS + one add per key against ~24 B of table per key).
-__global__ void __launch_bounds__(kSlThreads) ks_split_keys(const SlArena in, int* chunk_prefix, int sub_bits, int sub_shift, int region_div,
+__global__ void __launch_bounds__(kSlThreads, 3) ks_split_keys(const SlArena in, int* chunk_prefix, int sub_bits, int sub_shift, int region_div,
                                                            const SlArena out, int* overflow) {
     RB_DYN_SMEM(unsigned char, sl_smem);
     TileSort<unsigned long long, kKeyE, true> ts;
@@ -744,19 +741,18 @@ __global__ void __launch_bounds__(kSlThreads) ks_split_keys(const SlArena in, in
     __shared__ int s_c;
     for (int c = sl_next_chunk(chunk_prefix + in.B + 1, &s_c); c < total; c = sl_next_chunk(chunk_prefix + in.B + 1, &s_c)) {
         const SlWork w = sl_work_item(in, pre, c);   // in.chunk <= 256 * kKeyE keys
-        int bkt[kKeyE];
         unsigned long long rec[kKeyE];
         uint32_t slot[kKeyE];
 #pragma unroll
         for (int i = 0; i < kKeyE; ++i) {
             const uint32_t idx = threadIdx.x + i * kSlThreads;
-            bkt[i] = -1; rec[i] = 0;
+            slot[i] = kNoSlot; rec[i] = 0;
             if (idx < w.n) {
                 rec[i] = __ldcs(rec_in + w.first + idx);
-                bkt[i] = n_sub > 1 ? (int)((sl_mixkey(rec[i]) >> sub_shift) & (uint64_t)(n_sub - 1)) : 0;
+                slot[i] = n_sub > 1 ? (uint32_t)((sl_mixkey(rec[i]) >> sub_shift) & (uint64_t)(n_sub - 1)) : 0;
             }
         }
-        ts.run(out, (w.b / region_div) * n_sub, bkt, rec, slot, overflow, nullptr);
+        ts.run(out, (w.b / region_div) * n_sub, slot, rec, overflow, nullptr);
     }
 }
 
@@ -866,15 +862,14 @@ __global__ void __launch_bounds__(kSlThreads) ks_emit_probes(const unsigned long
     TileSort<uint32_t, KPT * NJ> ts;
     ts.init(sl_smem, arena.B);
     const int64_t d0 = (int64_t)blockIdx.x * TILE + threadIdx.x;   // item i of the thread = distinct key d0 + i * 256
-    int bkt[KPT * NJ];
     uint32_t rec[KPT * NJ], slot[KPT * NJ];
 #pragma unroll
     for (int i = 0; i < KPT; ++i) {
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) { bkt[i * NJ + j] = -1; rec[i * NJ + j] = 0; }
-        if (d0 + i * kSlThreads < nd) sl_probes<NJ>(sg, hm, (uint64_t)dkey[d0 + i * kSlThreads], with_cbf != 0, &bkt[i * NJ], &rec[i * NJ]);
+        for (int j = 0; j < NJ; ++j) { slot[i * NJ + j] = kNoSlot; rec[i * NJ + j] = 0; }
+        if (d0 + i * kSlThreads < nd) sl_probes<NJ>(sg, hm, (uint64_t)dkey[d0 + i * kSlThreads], with_cbf != 0, &slot[i * NJ], &rec[i * NJ]);
     }
-    ts.run(arena, 0, bkt, rec, slot, overflow, tile_meta + (size_t)blockIdx.x * (arena.B + 1));
+    ts.run(arena, 0, slot, rec, overflow, tile_meta + (size_t)blockIdx.x * (arena.B + 1));
 #pragma unroll
     for (int i = 0; i < KPT; ++i) if (d0 + i * kSlThreads < nd) sl_store_places<NJ>(pos, d0 + i * kSlThreads, &slot[i * NJ]);
 }
@@ -891,10 +886,9 @@ __global__ void __launch_bounds__(kSlThreads) ks_combine_insert(const unsigned l
     if ((int64_t)blockIdx.x * TILE >= nd) return;   // whole CTA
     RB_DYN_SMEM(unsigned char, sl_smem);
     const int64_t d0 = (int64_t)blockIdx.x * TILE + threadIdx.x;   // item i of the thread = distinct key d0 + i * 256 (as in ks_emit_probes)
-    int bkt[KPT * kSlMaxH];
     uint32_t rec[KPT * kSlMaxH], rslot[KPT * kSlMaxH];
 #pragma unroll
-    for (int e = 0; e < KPT * kSlMaxH; ++e) { bkt[e] = -1; rec[e] = 0; }
+    for (int e = 0; e < KPT * kSlMaxH; ++e) { rslot[e] = kNoSlot; rec[e] = 0; }
     TileAnswers ta;   // the tile of ks_emit_probes with the same block index
     ta.load(sl_smem, probe_B, tile_meta + (size_t)blockIdx.x * (probe_B + 1), ans);
     uint32_t a[KPT * NJ];
@@ -954,14 +948,14 @@ __global__ void __launch_bounds__(kSlThreads) ks_combine_insert(const unsigned l
 #pragma unroll
                     for (int h2 = 0; h2 < kSlMaxH; ++h2) if (h2 < h && gi[h2] == gi[h]) dup = true;   // one raise per distinct counter
                     if (h < sg.hc && !dup && v[h] > v0[h]) {
-                        bkt[i * kSlMaxH + h] = sl_raise_region(sg, gi[h]);
+                        rslot[i * kSlMaxH + h] = (uint32_t)sl_raise_region(sg, gi[h]);
                         rec[i * kSlMaxH + h] = (uint32_t)(gi[h] & ((1ULL << sg.raise_log2) - 1)) | ((uint32_t)v[h] << sg.raise_log2);
                     }
                 }
             }
         }
     }
-    ts.run(raises, 0, bkt, rec, rslot, overflow, nullptr);
+    ts.run(raises, 0, rslot, rec, overflow, nullptr);
 }
 
 // ---- I7: raise the counters slice by slice ------------------------------------------------------------------------------------------------------
@@ -972,6 +966,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_raises(const SlArena aren
     sl_load_prefix(pre, chunk_prefix, arena.B);
     const int total = pre[arena.B];
     const uint32_t* rec = reinterpret_cast<const uint32_t*>(arena.data);
+    const L2Keep keep = l2_keep_policy();
     __shared__ int s_c;
     for (int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c); c < total; c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c)) {
         const SlWork w = sl_work_item(arena, pre, c);
@@ -980,7 +975,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_raises(const SlArena aren
             const uint32_t a = __ldcs(rec + w.first + i);
             const uint32_t li = a & ((1u << sg.raise_log2) - 1u);
             uint32_t* wp = cbf_words + word0 + (li >> 2);
-            byte_raise(wp, (int)(li & 3) * 8, a >> sg.raise_log2, ld_cg(wp));
+            byte_raise_keep(wp, (int)(li & 3) * 8, a >> sg.raise_log2, ld_cg_keep(wp, keep), keep);
         }
     }
 }

@@ -124,7 +124,7 @@ static int32_t sliced_engine_get(rb_graph* g, int64_t n_round, SlicedEngine** ou
     const int64_t n_max = sl_pow2_at_least(n_round);
     e->n_max = n_max;
     // duplicates of a key are found in sub-ranges of ~2^RB_SLICED_SUBRANGE_LOG2 keys (two tile sorts: key_B ranges x 2^sub_bits each)
-    const int lgSub = env_int("RB_SLICED_SUBRANGE_LOG2", 11, 4, 11);
+    const int lgSub = env_int("RB_SLICED_SUBRANGE_LOG2", 10, 4, 11);
     int lgS = 0; while ((n_max >> lgSub) > (1LL << lgS)) ++lgS;
     const int lg1 = std::min((lgS + 1) / 2, 11);
     e->sub_bits = std::min(lgS - lg1, 11);

@@ -88,7 +88,7 @@ extern "C" int32_t rb_sshard_create(rb_ctx* ctx, int32_t n_ranks, int32_t rank, 
     // distinct keys a home rank can see exceed its share of the instances only by the imbalance of the hash ranges (~1e-4 at 10^8 keys)
     const int64_t n_max = div_up(std::max<int64_t>(max_kmers, 1024), 4096) * 4096;
     sh->n_max = n_max; sh->n_dense = n_max + n_max / 32 + 4096;
-    const int lgSub = env_int("RB_SLICED_SUBRANGE_LOG2", 11, 4, 11);
+    const int lgSub = env_int("RB_SLICED_SUBRANGE_LOG2", 10, 4, 11);
     int lgW = 0; while ((1 << lgW) < W) ++lgW;
     int lgS = 0; while (((n_max * W) >> lgSub) > (1LL << lgS)) ++lgS;       // sub-ranges over all ranks
     sh->lg1 = std::max(lgW, std::min((lgS + 1) / 2, 11));

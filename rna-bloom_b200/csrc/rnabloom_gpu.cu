@@ -4,9 +4,6 @@
 #include "../../include/rnabloom_gpu.h"
 #include "rb_kernels.cuh"
 #include "rb_sliced.cuh"
-#ifndef RB_EMU   // the host emulation (tests/emu) covers the direct and the sliced engine, not the sharded pipeline
-#include "rb_shard.cuh"
-#endif
 
 #include <algorithm>
 #include <cmath>
@@ -1303,262 +1300,3 @@ extern "C" int32_t rb_synth_reads_dev(rb_ctx* ctx, uint64_t seed, uint64_t genom
 #include "rb_sliced_host.inl"
 #include "rb_sshard_host.inl"
 
-#ifndef RB_EMU
-// ---- hash-sharded graph (one rank's share; phases of rb_shard.cuh) ---------------------------------------------------------------
-struct rb_shard {
-    rb_ctx* ctx;
-    int n_ranks, rank, hd, hc, hmax, k, stranded;
-    int64_t dbg_bits, cbf_bytes;          // global sizes
-    uint64_t dbg_shard, cbf_shard;        // per-rank index range
-    int64_t max_kmers;
-    int64_t cap_keys, cap_dbg, cap_cbf, cap_lookup;
-    rb_filter *dbg, *cbf;                 // local shares
-    AggTable tab; int64_t tab_slots;      // slots incl. the extra one for key 0
-    int *pos_dbg, *pos_cbf, *pos_lookup;
-    unsigned int* inc;
-    int* overflow;                        // device flag
-    int64_t lookup_inst;                  // instances of the last route_lookup
-};
-
-static int64_t region_cap(int64_t total, int n_ranks) { return (int64_t)((double)total / (n_ranks * kShardSub) * 1.08) + 2048; }
-
-extern "C" int32_t rb_shard_create(rb_ctx* ctx, int32_t n_ranks, int32_t rank, int64_t dbg_bits, int64_t cbf_bytes, int32_t hd, int32_t hc, int32_t k,
-                                   int32_t stranded, int64_t max_kmers, rb_shard** out) {
-    if (!ctx || !out || n_ranks < 1 || rank < 0 || rank >= n_ranks || max_kmers < 1) return RB_EINVAL;
-    if (hd < 1 || hd > kMaxHash || hc < 1 || hc > kMaxHash || dbg_bits < 1 || cbf_bytes < 1) return fail(ctx, RB_EINVAL, "shard: bad sizes");
-    LOCK(ctx);
-    rb_shard* sh = new rb_shard();
-    memset(sh, 0, sizeof *sh);
-    sh->ctx = ctx; sh->n_ranks = n_ranks; sh->rank = rank; sh->hd = hd; sh->hc = hc; sh->hmax = std::max(hd, hc); sh->k = k; sh->stranded = stranded ? 1 : 0;
-    sh->dbg_bits = dbg_bits; sh->cbf_bytes = cbf_bytes; sh->max_kmers = max_kmers;
-    sh->dbg_shard = (uint64_t)(div_up(div_up(dbg_bits, n_ranks), 1024) * 1024);   // whole bytes/words per rank: shares concatenate to the global array
-    sh->cbf_shard = (uint64_t)(div_up(div_up(cbf_bytes, n_ranks), 4) * 4);
-    const int64_t lo_d = (int64_t)sh->dbg_shard * rank, lo_c = (int64_t)sh->cbf_shard * rank;
-    const int64_t local_d = std::max<int64_t>(0, std::min<int64_t>((int64_t)sh->dbg_shard, dbg_bits - lo_d));
-    const int64_t local_c = std::max<int64_t>(0, std::min<int64_t>((int64_t)sh->cbf_shard, cbf_bytes - lo_c));
-    // a home rank receives about max_kmers keys when every rank routes max_kmers; allow 25 % imbalance
-    const int64_t recv_keys = max_kmers + max_kmers / 4 + 4096;
-    sh->cap_keys = region_cap(recv_keys, n_ranks);
-    sh->cap_dbg = region_cap(recv_keys * hd, n_ranks);
-    sh->cap_cbf = region_cap(recv_keys * hc, n_ranks);
-    sh->cap_lookup = region_cap(max_kmers * (hd + hc), n_ranks);
-    if ((double)sh->cap_lookup * n_ranks * kShardSub > 2.0e9 || (double)sh->cap_dbg * n_ranks * kShardSub > 2.0e9)
-        { delete sh; return fail(ctx, RB_EINVAL, "shard: max_kmers_per_round too large for 32-bit reply positions"); }
-    int64_t T = 1024;
-    while ((double)T < 1.6 * (double)recv_keys) T <<= 1;   // linear probing at a load factor of at most 0.63
-    sh->tab_slots = T + 1;
-    int lg = 0; while ((1LL << lg) < T) ++lg;
-    sh->tab.mask = (uint64_t)T - 1; sh->tab.shift = 64 - lg;
-    int32_t rc = filter_alloc(ctx, RB_BLOOM, std::max<int64_t>(local_d, 32), hd, k, &sh->dbg);
-    if (!rc) rc = filter_alloc(ctx, RB_COUNTING, std::max<int64_t>(local_c, 4), hc, k, &sh->cbf);
-    cudaError_t e = cudaSuccess;
-    if (!rc) {
-        e = cudaMalloc(&sh->tab.keys, (size_t)sh->tab_slots * 8);
-        if (e == cudaSuccess) e = cudaMalloc(&sh->tab.counts, (size_t)sh->tab_slots * 4);
-        if (e == cudaSuccess) e = cudaMalloc(&sh->inc, (size_t)sh->tab_slots * 4);
-        if (e == cudaSuccess) e = cudaMalloc(&sh->pos_dbg, (size_t)sh->tab_slots * hd * 4);
-        if (e == cudaSuccess) e = cudaMalloc(&sh->pos_cbf, (size_t)sh->tab_slots * hc * 4);
-        if (e == cudaSuccess) e = cudaMalloc(&sh->pos_lookup, (size_t)max_kmers * (hd + hc) * 4);
-        if (e == cudaSuccess) e = cudaMalloc(&sh->overflow, 4);
-        if (e == cudaSuccess) e = cudaMemsetAsync(sh->overflow, 0, 4, ctx->stream);
-    }
-    if (rc || e != cudaSuccess) {
-        if (!rc) rc = fail(ctx, RB_ENOMEM, std::string("shard alloc: ") + cudaGetErrorString(e));
-        rb_shard_destroy(sh);
-        return rc;
-    }
-    sh->dbg->in_graph = sh->cbf->in_graph = true;
-    *out = sh;
-    return RB_OK;
-}
-extern "C" int32_t rb_shard_destroy(rb_shard* sh) {
-    if (!sh) return RB_EINVAL;
-    rb_ctx* ctx = sh->ctx;
-    LOCK(ctx);
-    cudaStreamSynchronize(ctx->stream);
-    if (sh->dbg) filter_free(sh->dbg);
-    if (sh->cbf) filter_free(sh->cbf);
-    cudaFree(sh->tab.keys); cudaFree(sh->tab.counts); cudaFree(sh->inc); cudaFree(sh->pos_dbg); cudaFree(sh->pos_cbf);
-    cudaFree(sh->pos_lookup); cudaFree(sh->overflow);
-    delete sh;
-    return RB_OK;
-}
-extern "C" int32_t rb_shard_geometry(rb_shard* sh, int64_t* geom) {
-    if (!sh || !geom) return RB_EINVAL;
-    geom[0] = sh->cap_keys; geom[1] = sh->cap_dbg; geom[2] = sh->cap_cbf; geom[3] = sh->cap_lookup;
-    geom[4] = (int64_t)sh->dbg_shard; geom[5] = (int64_t)sh->cbf_shard; geom[6] = sh->dbg->size; geom[7] = sh->cbf->size; geom[8] = kShardSub; geom[9] = kCntStride;
-    return RB_OK;
-}
-extern "C" int32_t rb_shard_filter(rb_shard* sh, int32_t which, rb_filter** out) {
-    if (!sh || !out) return RB_EINVAL;
-    *out = which == RB_DBGBF ? sh->dbg : which == RB_CBF ? sh->cbf : nullptr;
-    return RB_OK;
-}
-extern "C" int32_t rb_shard_overflow(rb_shard* sh, int32_t* flag) {
-    if (!sh || !flag) return RB_EINVAL;
-    rb_ctx* ctx = sh->ctx;
-    LOCK(ctx);
-    CK(cudaMemcpyAsync(flag, sh->overflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (*flag) CK(cudaMemsetAsync(sh->overflow, 0, 4, ctx->stream));
-    return RB_OK;
-}
-static ShardGeom shard_geom(const rb_shard* sh, int64_t cap) { ShardGeom g; g.n_ranks = sh->n_ranks; g.cap = cap; g.dbg_shard = sh->dbg_shard; g.cbf_shard = sh->cbf_shard; return g; }
-static int slot_grid(const rb_shard* sh) { return (int)div_up(sh->tab_slots, kThreads); }
-static int region_grid(const rb_shard* sh, int64_t cap) { return (int)div_up(cap * sh->n_ranks * kShardSub, kThreads); }
-
-struct RouteUser { rb_shard* sh; int mode; int64_t* send; int* cnt; int64_t *fh, *rh; bool lookup; int launches; };
-static int32_t route_launch(rb_ctx* ctx, const Ingest& ing, void* user) {
-    RouteUser* u = (RouteUser*)user;
-    rb_shard* sh = u->sh;
-    if (++u->launches > 1) return fail(ctx, RB_EINVAL, "shard: reads exceed max_kmers_per_round");
-    if (ing.n_pos > sh->max_kmers) return fail(ctx, RB_EINVAL, "shard: reads exceed max_kmers_per_round");
-    const int grid = (int)div_up(div_up(ing.n_pos, kChunk), kThreads);
-    Ingest g = ing;
-    g.out_base = 0;
-    if (!u->lookup) {
-        const ShardGeom sg = shard_geom(sh, sh->cap_keys);
-        if (u->mode == RB_MODE_FWD) RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_route_keys<0>)(g, sh->k, sg, u->send, u->cnt, sh->overflow);
-        else if (u->mode == RB_MODE_RC) RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_route_keys<1>)(g, sh->k, sg, u->send, u->cnt, sh->overflow);
-        else RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_route_keys<2>)(g, sh->k, sg, u->send, u->cnt, sh->overflow);
-    } else {
-        const ShardGeom sg = shard_geom(sh, sh->cap_lookup);
-        const HashMults hm = make_hm(sh->k);
-        const FastMod fd = make_fm(sh->dbg_bits), fc = make_fm(sh->cbf_bytes);
-        sh->lookup_inst = ing.n_pos;
-#define RL(MODE, MAXH) RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_route_lookup<MODE, MAXH>)(g, sh->k, hm, fd, fc, sh->hd, sh->hc, sg, u->send, u->cnt, sh->pos_lookup, u->fh, u->rh, sh->overflow)
-        if (u->mode == RB_MODE_FWD) { if (sh->hmax <= 3) RL(0, 3); else if (sh->hmax <= 4) RL(0, 4); else RL(0, 8); }
-        else { if (sh->hmax <= 3) RL(2, 3); else if (sh->hmax <= 4) RL(2, 4); else RL(2, 8); }
-#undef RL
-    }
-    LAUNCH_CHECK();
-    return RB_OK;
-}
-static int32_t shard_route(rb_shard* sh, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len, int64_t n_reads,
-                           int32_t uniform_len, int64_t uniform_stride, int mode, bool lookup, int64_t* send, int32_t* cnt, int64_t* fh, int64_t* rh,
-                           int64_t* n_out) {
-    rb_ctx* ctx = sh->ctx;
-    CK(cudaMemsetAsync(cnt, 0, (size_t)sh->n_ranks * kShardSub * kCntStride * 4, ctx->stream));
-    ReadsArg ra{packed, mask, read_off, read_len, n_reads, uniform_len, uniform_stride, true};
-    RouteUser u{sh, mode, send, cnt, fh, rh, lookup, 0};
-    const int64_t keep = ctx->subbatch_kmers;
-    ctx->subbatch_kmers = INT64_MAX / 4;      // one round = one launch
-    const int32_t rc = for_each_launch(ctx, ra, sh->k, route_launch, &u, n_out);
-    ctx->subbatch_kmers = keep;
-    if (lookup && u.launches == 0) sh->lookup_inst = 0;
-    return rc;
-}
-extern "C" int32_t rb_shard_route_keys(rb_shard* sh, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
-                                       int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, uint32_t flags, int64_t* send, int32_t* cnt,
-                                       int64_t* n_out) {
-    if (!sh || !send || !cnt) return RB_EINVAL;
-    LOCK(sh->ctx);
-    const int mode = !sh->stranded ? RB_MODE_CANON : ((flags & RB_REVCOMP) ? RB_MODE_RC : RB_MODE_FWD);
-    return shard_route(sh, packed, mask, read_off, read_len, n_reads, uniform_len, uniform_stride, mode, false, send, cnt, nullptr, nullptr, n_out);
-}
-extern "C" int32_t rb_shard_route_lookup(rb_shard* sh, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
-                                         int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, int64_t* send, int32_t* cnt, int64_t* fhash,
-                                         int64_t* rhash, int64_t* n_out) {
-    if (!sh || !send || !cnt) return RB_EINVAL;
-    LOCK(sh->ctx);
-    const int mode = sh->stranded ? RB_MODE_FWD : RB_MODE_CANON;
-    return shard_route(sh, packed, mask, read_off, read_len, n_reads, uniform_len, uniform_stride, mode, true, send, cnt, fhash,
-                       sh->stranded ? nullptr : rhash, n_out);
-}
-extern "C" int32_t rb_shard_aggregate(rb_shard* sh, const int64_t* recv, const int32_t* recv_cnt) {
-    if (!sh || !recv || !recv_cnt) return RB_EINVAL;
-    rb_ctx* ctx = sh->ctx;
-    LOCK(ctx);
-    CK(cudaMemsetAsync(sh->tab.keys, 0, (size_t)sh->tab_slots * 8, ctx->stream));
-    CK(cudaMemsetAsync(sh->tab.counts, 0, (size_t)sh->tab_slots * 4, ctx->stream));
-    RB_LAUNCH(region_grid(sh, sh->cap_keys), kThreads, 0, ctx->stream, k_agg_insert)(recv, recv_cnt, shard_geom(sh, sh->cap_keys), sh->tab);
-    LAUNCH_CHECK();
-    return RB_OK;
-}
-extern "C" int32_t rb_shard_emit_dbg(rb_shard* sh, int64_t* send, int32_t* cnt) {
-    if (!sh || !send || !cnt) return RB_EINVAL;
-    rb_ctx* ctx = sh->ctx;
-    LOCK(ctx);
-    CK(cudaMemsetAsync(cnt, 0, (size_t)sh->n_ranks * kShardSub * kCntStride * 4, ctx->stream));
-    const HashMults hm = make_hm(sh->k);
-    const FastMod fm = make_fm(sh->dbg_bits);
-    const ShardGeom sg = shard_geom(sh, sh->cap_dbg);
-    if (sh->hd <= 3) RB_LAUNCH(slot_grid(sh), kThreads, 0, ctx->stream, k_emit_dbg<3>)(sh->tab, hm, fm, sh->hd, sg, send, cnt, sh->pos_dbg, sh->overflow);
-    else if (sh->hd <= 4) RB_LAUNCH(slot_grid(sh), kThreads, 0, ctx->stream, k_emit_dbg<4>)(sh->tab, hm, fm, sh->hd, sg, send, cnt, sh->pos_dbg, sh->overflow);
-    else RB_LAUNCH(slot_grid(sh), kThreads, 0, ctx->stream, k_emit_dbg<8>)(sh->tab, hm, fm, sh->hd, sg, send, cnt, sh->pos_dbg, sh->overflow);
-    LAUNCH_CHECK();
-    return RB_OK;
-}
-extern "C" int32_t rb_shard_apply_dbg(rb_shard* sh, const int64_t* recv, const int32_t* recv_cnt, uint8_t* reply, int32_t set_bits) {
-    if (!sh || !recv || !recv_cnt || !reply) return RB_EINVAL;
-    rb_ctx* ctx = sh->ctx;
-    LOCK(ctx);
-    if (set_bits) RB_LAUNCH(region_grid(sh, sh->cap_dbg), kThreads, 0, ctx->stream, k_apply_dbg<1>)(recv, recv_cnt, shard_geom(sh, sh->cap_dbg), sh->dbg->dev, reply);
-    else RB_LAUNCH(region_grid(sh, sh->cap_dbg), kThreads, 0, ctx->stream, k_apply_dbg<0>)(recv, recv_cnt, shard_geom(sh, sh->cap_dbg), sh->dbg->dev, reply);
-    LAUNCH_CHECK();
-    return RB_OK;
-}
-extern "C" int32_t rb_shard_emit_cbf_reads(rb_shard* sh, const uint8_t* reply_home, int32_t policy, int64_t* send, int32_t* cnt) {
-    if (!sh || !reply_home || !send || !cnt) return RB_EINVAL;
-    rb_ctx* ctx = sh->ctx;
-    LOCK(ctx);
-    CK(cudaMemsetAsync(cnt, 0, (size_t)sh->n_ranks * kShardSub * kCntStride * 4, ctx->stream));
-    const HashMults hm = make_hm(sh->k);
-    const FastMod fm = make_fm(sh->cbf_bytes);
-    const ShardGeom sg = shard_geom(sh, sh->cap_cbf);
-#define EC(MAXH) RB_LAUNCH(slot_grid(sh), kThreads, 0, ctx->stream, k_combine_dbg_emit_cbf<MAXH>)(sh->tab, hm, fm, sh->hd, sh->hc, sg, sh->pos_dbg, reply_home, policy, sh->inc, send, cnt, sh->pos_cbf, sh->overflow)
-    if (sh->hc <= 3) EC(3); else if (sh->hc <= 4) EC(4); else EC(8);
-#undef EC
-    LAUNCH_CHECK();
-    return RB_OK;
-}
-extern "C" int32_t rb_shard_apply_cbf_read(rb_shard* sh, const int64_t* recv, const int32_t* recv_cnt, uint8_t* reply) {
-    if (!sh || !recv || !recv_cnt || !reply) return RB_EINVAL;
-    rb_ctx* ctx = sh->ctx;
-    LOCK(ctx);
-    RB_LAUNCH(region_grid(sh, sh->cap_cbf), kThreads, 0, ctx->stream, k_apply_cbf_read)(recv, recv_cnt, shard_geom(sh, sh->cap_cbf), sh->cbf->dev, reply);
-    LAUNCH_CHECK();
-    return RB_OK;
-}
-extern "C" int32_t rb_shard_emit_cbf_raises(rb_shard* sh, const uint8_t* reply_home, int32_t policy, int64_t* send, int32_t* cnt) {
-    if (!sh || !reply_home || !send || !cnt) return RB_EINVAL;
-    rb_ctx* ctx = sh->ctx;
-    LOCK(ctx);
-    CK(cudaMemsetAsync(cnt, 0, (size_t)sh->n_ranks * kShardSub * kCntStride * 4, ctx->stream));
-    const HashMults hm = make_hm(sh->k);
-    const FastMod fm = make_fm(sh->cbf_bytes);
-    const ShardGeom sg = shard_geom(sh, sh->cap_cbf);
-    const uint64_t seed = ctx->rng_seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(ctx->launches + 1);
-#define ER(MAXH) RB_LAUNCH(slot_grid(sh), kThreads, 0, ctx->stream, k_combine_cbf_emit_raise<MAXH>)(sh->tab, hm, fm, sh->hc, sg, sh->inc, sh->pos_cbf, reply_home, policy, seed, send, cnt, sh->overflow)
-    if (sh->hc <= 3) ER(3); else if (sh->hc <= 4) ER(4); else ER(8);
-#undef ER
-    LAUNCH_CHECK();
-    return RB_OK;
-}
-extern "C" int32_t rb_shard_apply_cbf_raise(rb_shard* sh, const int64_t* recv, const int32_t* recv_cnt) {
-    if (!sh || !recv || !recv_cnt) return RB_EINVAL;
-    rb_ctx* ctx = sh->ctx;
-    LOCK(ctx);
-    RB_LAUNCH(region_grid(sh, sh->cap_cbf), kThreads, 0, ctx->stream, k_apply_cbf_raise)(recv, recv_cnt, shard_geom(sh, sh->cap_cbf), sh->cbf->dev);
-    LAUNCH_CHECK();
-    return RB_OK;
-}
-extern "C" int32_t rb_shard_apply_lookup(rb_shard* sh, const int64_t* recv, const int32_t* recv_cnt, uint8_t* reply) {
-    if (!sh || !recv || !recv_cnt || !reply) return RB_EINVAL;
-    rb_ctx* ctx = sh->ctx;
-    LOCK(ctx);
-    RB_LAUNCH(region_grid(sh, sh->cap_lookup), kThreads, 0, ctx->stream, k_apply_lookup)(recv, recv_cnt, shard_geom(sh, sh->cap_lookup), sh->dbg->dev, sh->cbf->dev, reply);
-    LAUNCH_CHECK();
-    return RB_OK;
-}
-extern "C" int32_t rb_shard_combine_lookup(rb_shard* sh, const uint8_t* reply_home, float* counts) {
-    if (!sh || !reply_home || !counts) return RB_EINVAL;
-    rb_ctx* ctx = sh->ctx;
-    LOCK(ctx);
-    if (sh->lookup_inst == 0) return RB_OK;
-    RB_LAUNCH((int)div_up(sh->lookup_inst, kThreads), kThreads, 0, ctx->stream, k_combine_lookup)(sh->lookup_inst, sh->hd, sh->hc, sh->pos_lookup, reply_home, counts);
-    LAUNCH_CHECK();
-    return RB_OK;
-}
-
-#endif  // !RB_EMU

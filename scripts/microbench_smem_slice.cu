@@ -28,13 +28,26 @@ __global__ void k_fill(uint32_t* rec, uint64_t n, int bits_log2, uint64_t seed) 
 }
 
 // ---- L2-resident slices (the engine's apply kernel, reduced to its memory behaviour) -----------------------------------------------
-template <int SET>
+__device__ __forceinline__ uint32_t ld_keep(const uint32_t* p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.cg.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t or_keep(uint32_t* p, uint32_t b, uint64_t pol) {
+    uint32_t v;
+    asm volatile("atom.global.or.L2::cache_hint.b32 %0, [%1], %2, %3;" : "=r"(v) : "l"(p), "r"(b), "l"(pol) : "memory");
+    return v;
+}
+// HINT = 1: slice accesses carry an L2 evict_last policy, the answer stream is written with st.cs
+template <int SET, int HINT>
 __global__ void __launch_bounds__(256) k_apply_l2(const uint32_t* __restrict__ rec, uint64_t per_region, int n_regions, int slice_log2, int chunk,
                                                   uint32_t* __restrict__ words, uint8_t* __restrict__ ans, int* counter) {
     __shared__ int s_c;
     const int chunks_per_region = (int)((per_region + chunk - 1) / chunk);
     const int total = chunks_per_region * n_regions;
     constexpr int U = 8;
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_c = atomicAdd(counter, 1);
@@ -50,13 +63,14 @@ __global__ void __launch_bounds__(256) k_apply_l2(const uint32_t* __restrict__ r
 #pragma unroll
             for (int u = 0; u < U; ++u) li[u] = (i0 + u * 256 < n) ? __ldcs(rec + first + i0 + u * 256) : 0u;
 #pragma unroll
-            for (int u = 0; u < U; ++u) wd[u] = (i0 + u * 256 < n) ? __ldcg(w0 + (li[u] >> 5)) : 0u;
+            for (int u = 0; u < U; ++u) wd[u] = (i0 + u * 256 < n) ? (HINT ? ld_keep(w0 + (li[u] >> 5), pol) : __ldcg(w0 + (li[u] >> 5))) : 0u;
 #pragma unroll
             for (int u = 0; u < U; ++u)
                 if (i0 + u * 256 < n) {
                     const uint32_t bit = 1u << (li[u] & 31);
-                    if (SET && !(wd[u] & bit)) wd[u] = atomicOr(w0 + (li[u] >> 5), bit);
-                    ans[first + i0 + u * 256] = (wd[u] & bit) ? 0x80 : 0;
+                    if (SET && !(wd[u] & bit)) wd[u] = HINT ? or_keep(w0 + (li[u] >> 5), bit, pol) : atomicOr(w0 + (li[u] >> 5), bit);
+                    if (HINT) __stcs(ans + first + i0 + u * 256, (uint8_t)((wd[u] & bit) ? 0x80 : 0));
+                    else ans[first + i0 + u * 256] = (wd[u] & bit) ? 0x80 : 0;
                 }
         }
     }
@@ -165,21 +179,24 @@ int main(int argc, char** argv) {
     // ---- L2 variant: 64 MiB slices
     {
         const int slice_log2 = 29;
-        const int n_regions = (int)(filter_bytes >> 23);
+        const int n_regions = (int)(filter_bytes >> (slice_log2 - 3));
         const uint64_t per = n_probes / n_regions;
         k_fill<<<sms * 8, 256>>>(rec, per * n_regions, slice_log2, 1);
+        for (int hint = 0; hint < 2; ++hint)
         for (int set = 0; set < 2; ++set)
             for (int rep = 0; rep < 2; ++rep) {   // rep 0: bits clear (insert: every probe sets); rep 1: bits set
                 if (rep == 0) CK(cudaMemset(words, 0, filter_bytes));
                 CK(cudaMemset(counter, 0, 4));
                 CK(cudaEventRecord(e0));
-                if (set) k_apply_l2<1><<<sms * 6, 256>>>(rec, per, n_regions, slice_log2, 2048, words, ans, counter);
-                else k_apply_l2<0><<<sms * 6, 256>>>(rec, per, n_regions, slice_log2, 2048, words, ans, counter);
+                if (set && hint) k_apply_l2<1, 1><<<sms * 6, 256>>>(rec, per, n_regions, slice_log2, 2048, words, ans, counter);
+                else if (set) k_apply_l2<1, 0><<<sms * 6, 256>>>(rec, per, n_regions, slice_log2, 2048, words, ans, counter);
+                else if (hint) k_apply_l2<0, 1><<<sms * 6, 256>>>(rec, per, n_regions, slice_log2, 2048, words, ans, counter);
+                else k_apply_l2<0, 0><<<sms * 6, 256>>>(rec, per, n_regions, slice_log2, 2048, words, ans, counter);
                 CK(cudaEventRecord(e1));
                 CK(cudaEventSynchronize(e1));
                 CK(cudaEventElapsedTime(&ms, e0, e1));
-                printf("L2   slices 64 MiB  %-7s %-10s %8.3f ms  %7.1f G probes/s\n", set ? "set" : "lookup", rep ? "(bits set)" : "(clear)", ms,
-                       per * n_regions / ms / 1e6);
+                printf("L2   slices 64 MiB %s %-7s %-10s %8.3f ms  %7.1f G probes/s\n", hint ? "evict_last+st.cs" : "no hints        ", set ? "set" : "lookup",
+                       rep ? "(bits set)" : "(clear)", ms, per * n_regions / ms / 1e6);
             }
     }
     // ---- SMEM variant: 64 KiB sub-slices, 3-stage bulk-copy pipeline

@@ -585,15 +585,14 @@ def test_skewed_batch_is_redone_by_the_direct_engine(ctx, orc):
     g.destroy(), og.close()
 
 
-@pytest.mark.skipif(os.environ.get("RB_TEST_SPILL") != "1", reason="the heavy-hitter spill path is off by default until measured (RB_TEST_SPILL=1)")
 def test_heavy_hitters_take_the_spill_path(ctx, orc, monkeypatch):
-    """RB_SLICED_SPILL=1: the skewed batch stays on the sliced engine (spill list -> table -> merged multiplicities)."""
+    """The skewed batch stays on the sliced engine (spill list -> table -> merged multiplicities); the spill path is on by default."""
     monkeypatch.setenv("RB_SLICED_SPILL", "1")
     monkeypatch.setenv("RB_ENGINE", "sliced")
     rng = np.random.default_rng(59)
     base = rand_reads(rng, 3, 150, 150)
     seqs = base * SKEW_COPIES + rand_reads(rng, 2000, 150, 150)
-    g, og = make_graphs(ctx, orc, (1 << 27) + 9, (1 << 24) + 3, 64, 3, 3, 1, 25, False, False)
+    g, og = make_graphs(ctx, orc, (1 << 30) + 9, (1 << 28) + 3, 64, 3, 3, 1, 25, False, False)   # roomy: few shared counters
     for s_ in base + seqs[-2000:]:
         og.add_read(s_, flags=F_DBG_ONLY)
     l0 = ctx.kernel_launches()
