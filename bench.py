@@ -170,7 +170,6 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="N>1: skip the oracle comparison of the sharded path after the timed region")
     ap.add_argument("--engine", default=os.environ.get("RB_ENGINE", "sliced"), choices=["direct", "sliced", "auto"])
     ap.add_argument("--sharded", action="store_true", help="experiments only: run the sharded pipeline even on one GPU")
-    ap.add_argument("--sharded-engine", default="sliced", choices=["sliced", "legacy"], help="N>1: pipeline generation (DESIGN.md section 8)")
     ap.add_argument("--genome", type=int, default=GENOME, help="experiments only: virtual genome length (coverage knob)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

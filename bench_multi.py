@@ -59,8 +59,13 @@ def sharded_parity_check(make_graph, rank, world, device, full_dbg_bits=None, fu
     out = {"n_ranks": world}
     alive = []   # device buffers of every round stay allocated until the check is over (the calls only take raw pointers)
 
+    def sync():
+        if device.type == "cuda":   # torch allocates / fills on its own stream, the library works on the context's stream
+            torch.cuda.synchronize()
+
     def dev(seqs):
         alive.append(_DevReads(rb, seqs, device))
+        sync()
         return alive[-1]
     # ---- A ---------------------------------------------------------------------------------------------------------------------
     dbg_bits, cbf_bytes, per_rank, per_round = small
@@ -81,10 +86,10 @@ def sharded_parity_check(make_graph, rank, world, device, full_dbg_bits=None, fu
     n_inst = sum(max(0, len(s) - k + 1) for s in mine[q0:q1])
     counts = torch.zeros(n_inst, dtype=torch.float32, device=device)
     fh = torch.zeros(n_inst, dtype=torch.int64, device=device)
+    sync()
     assert sg.count_round(dq.args, counts, fh) == n_inst
     sg.check_overflow()
-    if device.type == "cuda":
-        torch.cuda.synchronize()
+    sync()
     dbg = sg.gather_filter(rb.RB_DBGBF, (dbg_bits + 7) // 8)
     cbf = sg.gather_filter(rb.RB_CBF, cbf_bytes)
     og = OracleGraph(orc, dbg_bits, cbf_bytes, 64, hd, hc, 1, k, False, False)
@@ -126,6 +131,7 @@ def sharded_parity_check(make_graph, rank, world, device, full_dbg_bits=None, fu
         n_q = sum(max(0, len(s) - k + 1) for s in mine[:n_qr])
         counts = torch.zeros(n_q, dtype=torch.float32, device=device)
         dq = dev(mine[:n_qr])
+        sync()
         assert fg.count_round(dq.args, counts) == n_q
         fg.check_overflow()
         pops = torch.tensor([fg.popcount(rb.RB_DBGBF), fg.popcount(rb.RB_CBF)], dtype=torch.int64, device=device)
@@ -156,7 +162,7 @@ def sharded_parity_check(make_graph, rank, world, device, full_dbg_bits=None, fu
 
 def run_sharded(args, rank, world, local_rank):
     import rnabloom_b200 as rb
-    from rnabloom_b200.sharded import GpuBackend, ShardedGraph, SlicedBackend, SlicedShardedGraph
+    from rnabloom_b200.sharded import ShardedGraph, broadcast_nccl_id
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":   # its banner goes to stdout, where the bench contract wants one JSON line
         os.environ["NCCL_DEBUG"] = "WARN"
     torch.cuda.set_device(local_rank)
@@ -166,19 +172,17 @@ def run_sharded(args, rank, world, local_rank):
     kpr = single.KMERS_PER_READ
     dbg_bits, cbf_bytes = single.DBG_BITS * world, single.CBF_BYTES * world
     genome = args.genome * world
-    sliced = getattr(args, "sharded_engine", "sliced") == "sliced"
-    # sliced: rounds of 252 M k-mers per rank (the tile sort of the sliced engine routes; equal-split all-to-all of whole regions);
-    # legacy: the first-generation pipeline (per-record cursor scatter), 63 M k-mers per round
-    reads_per_round = min(args.reads_per_step, 2_000_000 if sliced else 500_000)
+    # rounds of up to 504 M k-mers per rank, as on one GPU (one sweep of the local 16 GiB per phase is amortised over the round)
+    reads_per_round = min(args.reads_per_step, int(os.environ.get("RB_BENCH_READS_PER_ROUND", "4000000")))
     rounds = max(1, args.reads_per_step // reads_per_round)
     n_reads = rounds * reads_per_round
     ctx = rb.Context(local_rank)
-    if sliced:
-        be = SlicedBackend(ctx, world, rank, dbg_bits, cbf_bytes, single.HD, single.HC, K, False, reads_per_round * kpr)
-        sg = SlicedShardedGraph(be, rank, world)
-    else:
-        be = GpuBackend(ctx, world, rank, dbg_bits, cbf_bytes, single.HD, single.HC, K, False, reads_per_round * kpr)
-        sg = ShardedGraph(be, rank, world)
+    dev = torch.device("cuda", local_rank)
+    # the library owns the exchange: its own NCCL communicator on its own stream; torch.distributed only carries the 128-byte id,
+    # the barriers and the max-over-ranks of the timings
+    stream = torch.cuda.Stream(device=dev)
+    ctx.set_stream(stream.cuda_stream)
+    sg = ShardedGraph(ctx, world, rank, dbg_bits, cbf_bytes, single.HD, single.HC, K, False, reads_per_round * kpr, nccl_id=broadcast_nccl_id(dev))
     total_steps = args.warmup + args.steps
     n_batches = min(total_steps, max(1, 100_000_000 // n_reads))
     words = n_reads * STRIDE // 32
@@ -194,8 +198,6 @@ def run_sharded(args, rank, world, local_rank):
     def reads_of(t, r):
         base = t.data_ptr() + r * reads_per_round * (STRIDE // 4)
         return (C.c_void_p(base), None, None, None, reads_per_round, L, STRIDE)
-
-    stream = be.stream
 
     def step(t):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -267,10 +269,9 @@ def run_sharded(args, rank, world, local_rank):
 
     # ---- correctness of the path that was just timed: oracle comparison over NCCL (all ranks; a difference fails the run) -----------------
     parity = None
-    if sliced and not getattr(args, "no_parity", False):
+    if not getattr(args, "no_parity", False):
         def make_graph(db, cb, max_kmers):
-            b2 = SlicedBackend(ctx, world, rank, db, cb, single.HD, single.HC, K, False, max_kmers)
-            return SlicedShardedGraph(b2, rank, world)
+            return ShardedGraph(ctx, world, rank, db, cb, single.HD, single.HC, K, False, max_kmers, nccl_id=broadcast_nccl_id(dev))
         try:
             parity = sharded_parity_check(make_graph, rank, world, torch.device("cuda", local_rank), dbg_bits, cbf_bytes, sg)
             ok = 1
@@ -292,8 +293,8 @@ def run_sharded(args, rank, world, local_rank):
         cfg.update({"dbgbf_bits": dbg_bits, "cbf_bytes": cbf_bytes, "genome_len": genome,
                     "workload": "BASELINE.json configs[2] shape, weak-scaled: %d x %d reads/step, k=25, dbgbf %d GiB + cbf %d GiB sharded by index range over %d GPUs"
                                 % (world, n_reads, dbg_bits >> 33, cbf_bytes >> 30, world),
-                    "exchange": "NCCL all-to-all (torch.distributed), %.0f MB per rank per step" % (xbytes / 1e6),
-                    "sharded_engine": "sliced" if sliced else "legacy", "kmers_per_round_per_gpu": reads_per_round * kpr})
+                    "exchange": "library-owned NCCL all-to-all (rb_mgraph_*), %.0f MB per rank per step" % (xbytes / 1e6),
+                    "paired_probe_records": bool(sg.paired), "kmers_per_round_per_gpu": reads_per_round * kpr})
         line = {"metric": "k-mers/s (insert+lookup) at k=25, 2x150 bp reads", "value": value, "unit": "k-mers/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e,
@@ -307,7 +308,7 @@ def run_sharded(args, rank, world, local_rank):
     elif parity is not None and "error" in parity:
         import sys
         print("rank %d parity: %s" % (rank, parity["error"]), file=sys.stderr, flush=True)
-    be.close()
+    sg.close()
     ctx.close()
     dist.destroy_process_group()
     if not parity_ok:

@@ -45,7 +45,7 @@ enum {
     RB_EINVAL = -1,  /* bad argument */
     RB_ENOMEM = -2,  /* host or device allocation failed */
     RB_ECUDA = -3,   /* CUDA runtime error (text in rb_last_error) */
-    RB_ENCCL = -4,   /* reserved for the multi-GPU exchange */
+    RB_ENCCL = -4,   /* multi-GPU exchange: NCCL missing or an NCCL / transport call failed */
     RB_EIO = -5,     /* file I/O */
     RB_ESTATE = -6   /* object not in a state that allows the call (e.g. no rpkbf) */
 };
@@ -203,6 +203,13 @@ RB_API int32_t rb_graph_count_hashes(rb_graph* g, const int64_t* base, int64_t n
  * pair_hash[i] is Kmer.getKmerPairHashValue (graph/Kmer.java:65-67, CanonicalKmer.java:69-72) */
 RB_API int32_t rb_graph_add_pair_hashes(rb_graph* g, int32_t which, const int64_t* pair_hash, int64_t n);
 RB_API int32_t rb_graph_lookup_pair_hashes(rb_graph* g, int32_t which, const int64_t* pair_hash, int64_t n, uint8_t* out);
+/* Barrier, and barrier + refresh of the HOST MIRROR.  The assembler's per-k-mer calls (graph.getCount(long[]), contains, the neighbour
+ * iterators: hundreds of latency-bound call sites in util/GraphUtils.java) must not cross the FFI; they keep reading the Unsafe buffers
+ * of the inherited filters (bloom/buffer/UnsafeByteBuffer.java:30 `start`, UnsafeBitBuffer.java:31 `backingByteBuffer`), which this call
+ * makes byte-identical to the device arrays.  Destinations are host addresses of rb_filter_num_bytes() bytes each; NULL skips a filter.
+ * Call before FPR checks on the host, graph.save by the JVM, and stage 2. */
+RB_API int32_t rb_graph_sync(rb_graph* g);
+RB_API int32_t rb_graph_sync_to_host(rb_graph* g, void* dbgbf, void* cbf, void* rpkbf, void* fpkbf);
 /* save / file constructor: graph :297-339,121-189.  Writes <path>, <path>.dbgbf[.desc], <path>.cbf[.desc], <path>.rpkbf[.desc]
  * (if present) and <path>.fpkbf[.desc] (if present) in the reference's format, so the unmodified JAR can restoreGraph() them. */
 RB_API int32_t rb_graph_save(rb_graph* g, const char* path);
@@ -223,38 +230,48 @@ RB_API int32_t rb_synth_reads_dev(rb_ctx* ctx, uint64_t seed, uint64_t genome_le
 RB_API int32_t rb_graph_neighbor_counts(rb_graph* g, const int64_t* fhash, const int64_t* rhash, const uint8_t* first_base,
                                         const uint8_t* last_base, int64_t n, float* counts, int64_t* nbr_fhash, int64_t* nbr_rhash);
 
-/* ---- hash-sharded graph on the sliced engine (one process per GPU) ------------------------------------------
- * The filters of BloomFilterDeBruijnGraph (graph/BloomFilterDeBruijnGraph.java:75-104) are split by index range over n_ranks GPUs
- * (whole 64 MiB slices per rank; the concatenation of the ranks' shares is the array a single GPU or the JVM produces).  Every call
- * below is one rank's phase between two equal-split all-to-all exchanges that the caller performs (torch.distributed / NCCL in
- * rna-bloom_b200/sharded.py); buffers that travel belong to the caller and are laid out [destination or source rank][region][records]:
- *   probes  uint32  n_ranks * geom[0] regions of geom[1] records      answers uint8, same shape
- *   keys    uint64  n_ranks * geom[2] regions of geom[3] records
- *   raises  uint32  n_ranks * geom[4] regions of geom[5] records      counts  uint32, one per region
- * plus geom[10] records of slack behind every buffer.  A device flag (rb_sshard_overflow) reports regions that did not fit: the
- * caller must all-reduce it and abandon the round before the first apply (nothing has been modified until then). */
-typedef struct rb_sshard rb_sshard;
-RB_API int32_t rb_sshard_create(rb_ctx* ctx, int32_t n_ranks, int32_t rank, int64_t dbgbf_bits, int64_t cbf_bytes, int32_t dbgbf_num_hash,
-                                int32_t cbf_num_hash, int32_t k, int32_t stranded, int64_t max_kmers_per_round, rb_sshard** out);
-RB_API int32_t rb_sshard_destroy(rb_sshard* sh);
-RB_API int32_t rb_sshard_geometry(rb_sshard* sh, int64_t* geom11);
-RB_API int32_t rb_sshard_filter(rb_sshard* sh, int32_t which, rb_filter** out);   /* this rank's share (borrowed) */
-RB_API int32_t rb_sshard_overflow(rb_sshard* sh, int32_t* flag);                   /* reads and clears the flag */
-/* lookup round (graph.getKmers :562-570): route -> [probes] -> apply(set_bits = 0) -> [answers back] -> combine */
-RB_API int32_t rb_sshard_route_lookup(rb_sshard* sh, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off,
-                                      const int32_t* read_len, int64_t n_reads, int32_t uniform_len, int64_t uniform_stride,
-                                      uint32_t* send_probes, uint32_t* send_cnt, int64_t* fhash, int64_t* rhash, int64_t* n_kmers_out);
-RB_API int32_t rb_sshard_apply(rb_sshard* sh, const uint32_t* recv_probes, const uint32_t* recv_cnt, uint8_t* recv_answers, int32_t set_bits);
-RB_API int32_t rb_sshard_combine_lookup(rb_sshard* sh, const uint8_t* home_answers, float* counts);
-/* insert round (graph.add :405-412 and its policies): route_keys -> [keys] -> dedup -> emit_probes -> [probes] -> apply(set_bits) ->
- * [answers back] -> combine_insert -> [raises] -> apply_raises */
-RB_API int32_t rb_sshard_route_keys(rb_sshard* sh, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off,
-                                    const int32_t* read_len, int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, uint32_t flags,
-                                    unsigned long long* send_keys, uint32_t* send_cnt, int64_t* n_kmers_out);
-RB_API int32_t rb_sshard_dedup(rb_sshard* sh, const unsigned long long* recv_keys, const uint32_t* recv_cnt);
-RB_API int32_t rb_sshard_emit_probes(rb_sshard* sh, int32_t with_cbf, uint32_t* send_probes, uint32_t* send_cnt);
-RB_API int32_t rb_sshard_combine_insert(rb_sshard* sh, const uint8_t* home_answers, int32_t policy, uint32_t* send_raises, uint32_t* send_cnt);
-RB_API int32_t rb_sshard_apply_raises(rb_sshard* sh, const uint32_t* recv_raises, const uint32_t* recv_cnt);
+/* ---- hash-sharded graph (one process per GPU) ------------------------------------------------
+ * The filters of BloomFilterDeBruijnGraph (graph/BloomFilterDeBruijnGraph.java:75-104) are split by index range over n_ranks GPUs; the
+ * ranks' shares reassemble to exactly the arrays a single GPU or the JVM produces (rb_mgraph_layout).  Reads are data-parallel: every
+ * rank feeds its own reads, the library routes every probe to the owner of its index and the answers back.  The exchange belongs to
+ * the library: rb_mgraph_create_nccl drives NCCL itself (libnccl.so.2 is bound at run time; all ranks pass the 128-byte id that rank 0
+ * obtained from rb_nccl_unique_id and distributed over any host-side channel), rb_mgraph_create takes a transport of two functions
+ * instead (MPI, gloo, a test double ...).  A transport works on DEVICE pointers and is ordered on the given stream.
+ *
+ * A round is collective: every rank calls rb_mgraph_add_round_dev / rb_mgraph_count_round_dev the same number of times (with zero
+ * reads if it has none left); one round holds at most max_kmers_per_round k-mers per rank.  Pointers of the round calls are DEVICE
+ * pointers.  insert = graph.add (:405-412) and its policies via the RB_* flags; count = graph.getKmers counts (:562-570).
+ * Errors: a hash skew that overflows the fixed-capacity regions of a round is detected on the device, agreed between the ranks and
+ * reported as RB_ESTATE with NOTHING modified (retry with smaller rounds); overflowing counter-raise regions are retried internally. */
+typedef struct rb_mgraph rb_mgraph;
+typedef struct rb_transport {
+    void* user;
+    /* equal-split all-to-all: piece p (bytes_per_rank bytes) of `send` on rank r arrives as piece r of `recv` on rank p */
+    int32_t (*all_to_all)(void* user, const void* send, void* recv, int64_t bytes_per_rank, void* stream);
+    /* element-wise maximum of n int32 over all ranks, in place */
+    int32_t (*all_reduce_max)(void* user, int32_t* buf, int64_t n, void* stream);
+} rb_transport;
+RB_API int32_t rb_nccl_unique_id(void* id128, int64_t len);   /* ncclGetUniqueId; len >= 128 */
+RB_API int32_t rb_mgraph_create_nccl(rb_ctx* ctx, int32_t n_ranks, int32_t rank, const void* nccl_unique_id, int64_t dbgbf_bits, int64_t cbf_bytes,
+                                     int32_t dbgbf_num_hash, int32_t cbf_num_hash, int32_t k, int32_t stranded, int64_t max_kmers_per_round,
+                                     rb_mgraph** out);
+RB_API int32_t rb_mgraph_create(rb_ctx* ctx, int32_t n_ranks, int32_t rank, const rb_transport* transport, int64_t dbgbf_bits, int64_t cbf_bytes,
+                                int32_t dbgbf_num_hash, int32_t cbf_num_hash, int32_t k, int32_t stranded, int64_t max_kmers_per_round,
+                                rb_mgraph** out);
+RB_API int32_t rb_mgraph_destroy(rb_mgraph* mg);
+/* layout[0] paired slices (0/1)  [1] dbgbf bits of a full share  [2] cbf bytes of a full share  [3] local dbgbf bits  [4] local cbf bytes
+ * [5] chunks = dbgbf_bits / cbf_bytes (paired)  [6] max k-mers per round and rank  [7] / [8] bytes one insert / lookup round sends per rank.
+ * unpaired: rank r holds dbgbf bits [r * layout[1], ...) and cbf bytes [r * layout[2], ...);
+ * paired:   rank r holds cbf bytes [r * layout[2], ...) and, for every chunk c, the global bits c * cbf_bytes + r * layout[2] + x
+ *           (x < layout[2]) as its local bits c * layout[2] + x. */
+RB_API int32_t rb_mgraph_layout(rb_mgraph* mg, int64_t* layout9);
+RB_API int32_t rb_mgraph_filter(rb_mgraph* mg, int32_t which, rb_filter** out);   /* this rank's share (borrowed): popcount, download, empty */
+RB_API int32_t rb_mgraph_stats(rb_mgraph* mg, int64_t* exchanged_bytes, int64_t* rounds);
+RB_API int32_t rb_mgraph_add_round_dev(rb_mgraph* mg, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
+                                       int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, uint32_t flags, int64_t* n_kmers_out);
+RB_API int32_t rb_mgraph_count_round_dev(rb_mgraph* mg, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
+                                         int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, float* counts, int64_t* fhash, int64_t* rhash,
+                                         int64_t* n_kmers_out);
 
 #ifdef __cplusplus
 }

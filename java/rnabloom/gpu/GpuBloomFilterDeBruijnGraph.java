@@ -49,10 +49,21 @@ public class GpuBloomFilterDeBruijnGraph extends BloomFilterDeBruijnGraph {
         return Native.graphAddReadsAscii(ctx, handle, bases, q, off, seqs.size(), minBaseQual, flags);
     }
 
-    /** Copies dbgbf / cbf / rpkbf / fpkbf from HBM into the inherited Unsafe buffers (call before FPR checks, save, stage 2). */
+    /**
+     * Copies dbgbf / cbf / rpkbf / fpkbf from HBM into the inherited Unsafe buffers (call before FPR checks on the host, save by the JVM,
+     * and stage 2).  Needs the four one-line getters of INTEGRATION.md edit 4 in the reference:
+     *   UnsafeByteBuffer.getAddress()      { return start; }                          (bloom/buffer/UnsafeByteBuffer.java:30)
+     *   UnsafeBitBuffer.getAddress()       { return backingByteBuffer.getAddress(); } (bloom/buffer/UnsafeBitBuffer.java:31)
+     *   BloomFilter.getBufferAddress()     { return ((UnsafeBitBuffer) bitArray).getAddress(); }   (bloom/BloomFilter.java:41)
+     *   CountingBloomFilter.getBufferAddress() { return ((UnsafeByteBuffer) counts).getAddress(); } (bloom/CountingBloomFilter.java:42)
+     * The device arrays have exactly the Unsafe layout (bit i = byte i/8, mask 1 << (i % 8); one byte per counter), so this is a copy.
+     */
     public void syncToHost() {
-        // e.g. Native.filterDownload(ctx, Native.graphFilter(ctx, handle, Native.DBGBF), <address of dbgbf's UnsafeByteBuffer>, numBytes);
-        // UnsafeByteBuffer keeps `start` private (bloom/buffer/UnsafeByteBuffer.java:30); expose it with a package-private getter.
+        Native.graphSyncToHost(ctx, handle,
+                               getDbgbf().getBufferAddress(),
+                               getCbf().getBufferAddress(),
+                               getRpkbf() == null ? 0L : getRpkbf().getBufferAddress(),
+                               getFpkbf() == null ? 0L : getFpkbf().getBufferAddress());
     }
 
     @Override

@@ -40,6 +40,9 @@ public final class Native {
     public static native void graphAddPairHashes(long ctx, long graph, int which, ByteBuffer hashes, long n);
     public static native void graphLookupPairHashes(long ctx, long graph, int which, ByteBuffer hashes, long n, ByteBuffer out);
     public static native long graphFilter(long ctx, long graph, int which);
+    /** Barrier + refresh of the host mirror: native addresses of the Unsafe buffers behind the inherited filters (0 = skip). */
+    public static native void graphSyncToHost(long ctx, long graph, long dbgbfAddress, long cbfAddress, long rpkbfAddress, long fpkbfAddress);
+    public static native void graphSync(long ctx, long graph);
     public static native void graphSave(long ctx, long graph, String path);
     public static native long graphLoad(long ctx, String path, boolean loadDbgbf, boolean loadFpkbf);
     public static native long filterCreate(long ctx, int kind, long size, int numHash, int k);

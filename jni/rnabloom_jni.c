@@ -118,6 +118,17 @@ JNIEXPORT jlong JNICALL Java_rnabloom_gpu_Native_graphFilter(JNIEnv* env, jclass
     check(env, (rb_ctx*)(intptr_t)ctx, rb_graph_filter((rb_graph*)(intptr_t)g, which, &f));
     return (jlong)(intptr_t)f;
 }
+/* barrier + host mirror refresh: destinations are the native addresses of the inherited filters' Unsafe buffers (0 = skip) */
+JNIEXPORT void JNICALL Java_rnabloom_gpu_Native_graphSyncToHost(JNIEnv* env, jclass cls, jlong ctx, jlong g, jlong dbgbfAddr, jlong cbfAddr, jlong rpkbfAddr,
+                                                                jlong fpkbfAddr) {
+    (void)cls;
+    check(env, (rb_ctx*)(intptr_t)ctx, rb_graph_sync_to_host((rb_graph*)(intptr_t)g, (void*)(intptr_t)dbgbfAddr, (void*)(intptr_t)cbfAddr,
+                                                             (void*)(intptr_t)rpkbfAddr, (void*)(intptr_t)fpkbfAddr));
+}
+JNIEXPORT void JNICALL Java_rnabloom_gpu_Native_graphSync(JNIEnv* env, jclass cls, jlong ctx, jlong g) {
+    (void)cls;
+    check(env, (rb_ctx*)(intptr_t)ctx, rb_graph_sync((rb_graph*)(intptr_t)g));
+}
 JNIEXPORT void JNICALL Java_rnabloom_gpu_Native_graphSave(JNIEnv* env, jclass cls, jlong ctx, jlong g, jstring path) {
     const char* p = (*env)->GetStringUTFChars(env, path, NULL);
     (void)cls;

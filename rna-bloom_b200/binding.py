@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 _SO = os.path.join(_HERE, "librnabloom_gpu.so")
 _SRC = [os.path.join(_HERE, "csrc", n) for n in ("rnabloom_gpu.cu", "rb_kernels.cuh", "rb_device.cuh", "rb_sliced.cuh",
-                                                 "rb_sliced_host.inl", "rb_sshard_host.inl")] + [
+                                                 "rb_sliced_host.inl", "rb_mgraph_host.inl")] + [
     os.path.join(_ROOT, "include", "rnabloom_gpu.h")]
 
 RB_BLOOM, RB_COUNTING = 0, 1
@@ -114,6 +114,15 @@ def bind(path, allow_missing=False):
         "rb_index_hashes": (i32, [vp, vp, i64, i64, vp]),
         "rb_kmerize": (i32, [vp] + reads + [i32, i32, vp, vp, vp]),
         "rb_kmerize_pairs": (i32, [vp] + reads + [i32, i32, i32, vp]),
+        "rb_nccl_unique_id": (i32, [vp, i64]),
+        "rb_mgraph_create_nccl": (i32, [vp, i32, i32, vp, i64, i64, i32, i32, i32, i32, i64, C.POINTER(vp)]),
+        "rb_mgraph_create": (i32, [vp, i32, i32, vp, i64, i64, i32, i32, i32, i32, i64, C.POINTER(vp)]),
+        "rb_mgraph_destroy": (i32, [vp]),
+        "rb_mgraph_layout": (i32, [vp, C.POINTER(i64)]),
+        "rb_mgraph_filter": (i32, [vp, i32, C.POINTER(vp)]),
+        "rb_mgraph_stats": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
+        "rb_mgraph_add_round_dev": (i32, [vp] + reads + [u32, C.POINTER(i64)]),
+        "rb_mgraph_count_round_dev": (i32, [vp] + reads + [vp, vp, vp, C.POINTER(i64)]),
         "rb_graph_create": (i32, [vp, i64, i64, i64, i32, i32, i32, i32, i32, i32, C.POINTER(vp)]),
         "rb_graph_destroy": (i32, [vp]),
         "rb_graph_init_fpkbf": (i32, [vp, i64, i32]),
@@ -131,22 +140,11 @@ def bind(path, allow_missing=False):
         "rb_graph_add_pair_hashes": (i32, [vp, i32, vp, i64]),
         "rb_graph_lookup_pair_hashes": (i32, [vp, i32, vp, i64, vp]),
         "rb_graph_neighbor_counts": (i32, [vp, vp, vp, vp, vp, i64, vp, vp, vp]),
+        "rb_graph_sync": (i32, [vp]),
+        "rb_graph_sync_to_host": (i32, [vp, vp, vp, vp, vp]),
         "rb_graph_save": (i32, [vp, cp]),
         "rb_graph_load": (i32, [vp, cp, i32, i32, C.POINTER(vp)]),
         "rb_synth_reads_dev": (i32, [vp, u64, u64, u64, i64, i32, u32, i64, vp]),
-        "rb_sshard_create": (i32, [vp, i32, i32, i64, i64, i32, i32, i32, i32, i64, C.POINTER(vp)]),
-        "rb_sshard_destroy": (i32, [vp]),
-        "rb_sshard_geometry": (i32, [vp, C.POINTER(i64)]),
-        "rb_sshard_filter": (i32, [vp, i32, C.POINTER(vp)]),
-        "rb_sshard_overflow": (i32, [vp, C.POINTER(i32)]),
-        "rb_sshard_route_lookup": (i32, [vp] + reads + [vp, vp, vp, vp, C.POINTER(i64)]),
-        "rb_sshard_apply": (i32, [vp, vp, vp, vp, i32]),
-        "rb_sshard_combine_lookup": (i32, [vp, vp, vp]),
-        "rb_sshard_route_keys": (i32, [vp] + reads + [u32, vp, vp, C.POINTER(i64)]),
-        "rb_sshard_dedup": (i32, [vp, vp, vp]),
-        "rb_sshard_emit_probes": (i32, [vp, i32, vp, vp]),
-        "rb_sshard_combine_insert": (i32, [vp, vp, i32, vp, vp]),
-        "rb_sshard_apply_raises": (i32, [vp, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         if allow_missing and not hasattr(L, name):

@@ -572,7 +572,8 @@ __device__ __forceinline__ SlWork sl_work_item(const SlArena& arena, const int* 
 template <int SET>
 __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena arena, int* chunk_prefix, const SlGeom sg,
                                                              uint32_t* __restrict__ dbg_words, const uint32_t* __restrict__ cbf_words,
-                                                             uint8_t* __restrict__ ans) {
+                                                             uint8_t* __restrict__ ans, const int* abort) {
+    if (abort && *abort) return;   // a region overflowed while the round was routed (on this or another rank): nothing may be modified
     RB_DYN_SMEM(unsigned char, sl_smem);
     int* pre = reinterpret_cast<int*>(sl_smem);
     sl_load_prefix(pre, chunk_prefix, arena.B);
@@ -880,8 +881,9 @@ __global__ void __launch_bounds__(kSlThreads) ks_combine_insert(const unsigned l
                                                                const unsigned int* __restrict__ n_distinct, const uint32_t* __restrict__ pos,
                                                                const uint2* __restrict__ tile_meta, int probe_B, const uint8_t* __restrict__ ans,
                                                                const HashMults hm, const SlGeom sg, int policy, uint64_t rng_seed, const SlArena raises,
-                                                               int* overflow) {
+                                                               int* overflow, const int* abort, int pass, int n_pass) {
     constexpr int KPT = SlShape<NJ>::KPT, TILE = SlShape<NJ>::TILE;
+    if (abort && *abort) return;
     const int64_t nd = (int64_t)*n_distinct;
     if ((int64_t)blockIdx.x * TILE >= nd) return;   // whole CTA
     RB_DYN_SMEM(unsigned char, sl_smem);
@@ -947,7 +949,10 @@ __global__ void __launch_bounds__(kSlThreads) ks_combine_insert(const unsigned l
                     bool dup = false;
 #pragma unroll
                     for (int h2 = 0; h2 < kSlMaxH; ++h2) if (h2 < h && gi[h2] == gi[h]) dup = true;   // one raise per distinct counter
-                    if (h < sg.hc && !dup && v[h] > v0[h]) {
+                    // n_pass > 1: the raise regions of an earlier attempt overflowed (hash skew); the keys are spread over n_pass passes.
+                    // A raise is a max: applying one twice, or the passes in any order, gives the same counters.
+                    const bool mine = n_pass <= 1 || (int)((sl_mixkey(key) >> 20) % (uint64_t)n_pass) == pass;
+                    if (h < sg.hc && !dup && mine && v[h] > v0[h]) {
                         rslot[i * kSlMaxH + h] = (uint32_t)sl_raise_region(sg, gi[h]);
                         rec[i * kSlMaxH + h] = (uint32_t)(gi[h] & ((1ULL << sg.raise_log2) - 1)) | ((uint32_t)v[h] << sg.raise_log2);
                     }
@@ -960,7 +965,8 @@ __global__ void __launch_bounds__(kSlThreads) ks_combine_insert(const unsigned l
 
 // ---- I7: raise the counters slice by slice ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSlThreads) ks_apply_raises(const SlArena arena, int* chunk_prefix, const SlGeom sg,
-                                                             uint32_t* __restrict__ cbf_words) {
+                                                             uint32_t* __restrict__ cbf_words, const int* abort) {
+    if (abort && *abort) return;   // a raise region overflowed (on this or another rank): the pass is repeated with the keys spread wider
     RB_DYN_SMEM(unsigned char, sl_smem);
     int* pre = reinterpret_cast<int*>(sl_smem);
     sl_load_prefix(pre, chunk_prefix, arena.B);

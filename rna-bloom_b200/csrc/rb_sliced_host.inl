@@ -309,7 +309,7 @@ static int32_t sliced_count_round_t(rb_graph* g, SlicedEngine* e, const Ingest& 
     int grid = 0;
     rc = sl_persistent_grid(ctx, ks_apply_probes<0>, sm_pre, &grid);
     if (rc) return rc;
-    SL_LAUNCH("ks_apply_probes<0>", ks_apply_probes<0>, grid, sm_pre, probes, e->chunk_prefix, e->sg, g->dbg->dev, g->cbf->dev, e->ans);
+    SL_LAUNCH("ks_apply_probes<0>", ks_apply_probes<0>, grid, sm_pre, probes, e->chunk_prefix, e->sg, g->dbg->dev, g->cbf->dev, e->ans, (const int*)nullptr);
     // same CTA -> k-mer mapping as the route kernel
     const size_t sm_ans = TileAnswers::smem_bytes(probes.B, TILE * NJ);
     auto k1 = ks_combine_lookup<1, NJ>;
@@ -417,10 +417,10 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     const size_t sm_pre = (size_t)(probes.B + 1) * 4;
     if (policy != POLICY_COUNT_IF_PRESENT) {
         rc = sl_persistent_grid(ctx, ks_apply_probes<1>, sm_pre, &grid); if (rc) return rc;
-        SL_LAUNCH("ks_apply_probes<1>", ks_apply_probes<1>, grid, sm_pre, probes, e->chunk_prefix, e->sg, g->dbg->dev, g->cbf->dev, e->ans);
+        SL_LAUNCH("ks_apply_probes<1>", ks_apply_probes<1>, grid, sm_pre, probes, e->chunk_prefix, e->sg, g->dbg->dev, g->cbf->dev, e->ans, (const int*)nullptr);
     } else {
         rc = sl_persistent_grid(ctx, ks_apply_probes<0>, sm_pre, &grid); if (rc) return rc;
-        SL_LAUNCH("ks_apply_probes<0>", ks_apply_probes<0>, grid, sm_pre, probes, e->chunk_prefix, e->sg, g->dbg->dev, g->cbf->dev, e->ans);
+        SL_LAUNCH("ks_apply_probes<0>", ks_apply_probes<0>, grid, sm_pre, probes, e->chunk_prefix, e->sg, g->dbg->dev, g->cbf->dev, e->ans, (const int*)nullptr);
     }
     if (with_cbf) {
         // I6 + I7
@@ -428,19 +428,30 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
         CK(cudaMemsetAsync(raises.cursor, 0, (size_t)raises.B * kSlPad * 4, ctx->stream));
         const uint64_t seed = ctx->rng_seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(ctx->launches + 1);
         const size_t sm_r = std::max(TileSort<uint32_t, kSlTileRecords>::smem_bytes(raises.B), TileAnswers::smem_bytes(probes.B, kSlThreads * kSlTileRecords));
-        if (e->paired) SL_LAUNCH("ks_combine_insert", ks_combine_insert<3>, grid_d, sm_r, e->dkey, e->dmult, e->n_distinct, e->pos, e->tile_meta, probes.B, e->ans, hm, e->sg, policy, seed,
-                                 raises, e->overflow);
-        else SL_LAUNCH("ks_combine_insert", ks_combine_insert<6>, grid_d, sm_r, e->dkey, e->dmult, e->n_distinct, e->pos, e->tile_meta, probes.B, e->ans, hm, e->sg, policy, seed,
-                       raises, e->overflow);
-        rc = sl_chunk_prefix(ctx, e, raises);
-        if (rc) return rc;
-        const size_t sm_rp = (size_t)(raises.B + 1) * 4;
-        rc = sl_persistent_grid(ctx, ks_apply_raises, sm_rp, &grid);
-        if (rc) return rc;
-        SL_LAUNCH("ks_apply_raises", ks_apply_raises, grid, sm_rp, raises, e->chunk_prefix, e->sg, g->cbf->dev);
-        rc = sl_read_flag(ctx, e->overflow, &flag);
-        if (rc) return rc;
-        if (flag) return fail(ctx, RB_ESTATE, "sliced engine: a raise region overflowed after filters were modified (hash skew beyond the slack)");
+        // A raise region that overflows (hash skew beyond the slack) is only seen after the dbgbf bits were set -- but the answers of
+        // the round are still there and a raise is a max, so the raise phase can simply be repeated with the keys spread over more
+        // passes: an aborted pass applies nothing (ks_apply_raises sees the flag), a repeated raise changes nothing.
+        for (int n_pass = 1;; n_pass *= 2) {
+            if (n_pass > 256) return fail(ctx, RB_ESTATE, "sliced engine: raise regions overflow even with the keys spread over 256 passes");
+            bool over = false;
+            for (int pass = 0; pass < n_pass && !over; ++pass) {
+                CK(cudaMemsetAsync(raises.cursor, 0, (size_t)raises.B * kSlPad * 4, ctx->stream));
+                if (e->paired) SL_LAUNCH("ks_combine_insert", ks_combine_insert<3>, grid_d, sm_r, e->dkey, e->dmult, e->n_distinct, e->pos, e->tile_meta, probes.B, e->ans, hm, e->sg,
+                                         policy, seed, raises, e->overflow, (const int*)nullptr, pass, n_pass);
+                else SL_LAUNCH("ks_combine_insert", ks_combine_insert<6>, grid_d, sm_r, e->dkey, e->dmult, e->n_distinct, e->pos, e->tile_meta, probes.B, e->ans, hm, e->sg,
+                               policy, seed, raises, e->overflow, (const int*)nullptr, pass, n_pass);
+                rc = sl_chunk_prefix(ctx, e, raises);
+                if (rc) return rc;
+                const size_t sm_rp = (size_t)(raises.B + 1) * 4;
+                rc = sl_persistent_grid(ctx, ks_apply_raises, sm_rp, &grid);
+                if (rc) return rc;
+                SL_LAUNCH("ks_apply_raises", ks_apply_raises, grid, sm_rp, raises, e->chunk_prefix, e->sg, g->cbf->dev, (const int*)e->overflow);
+                rc = sl_read_flag(ctx, e->overflow, &flag);
+                if (rc) return rc;
+                over = flag != 0;
+            }
+            if (!over) break;
+        }
     }
     claim_invalidate(ctx);   // bits were set without going through the claim table
     return RB_OK;

@@ -1285,6 +1285,31 @@ extern "C" int32_t rb_graph_load(rb_ctx* ctx, const char* path, int32_t load_dbg
     return RB_OK;
 }
 
+// ---- host mirror: per-k-mer Java calls (GraphUtils: getCount, contains, neighbour iterators ...) keep running on the host
+// buffers of the inherited BloomFilter / CountingBloomFilter objects, which are byte-identical to the device arrays after this call
+extern "C" int32_t rb_graph_sync(rb_graph* g) {
+    if (!g) return RB_EINVAL;
+    rb_ctx* ctx = g->ctx;
+    LOCK(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    return RB_OK;
+}
+extern "C" int32_t rb_graph_sync_to_host(rb_graph* g, void* dbgbf, void* cbf, void* rpkbf, void* fpkbf) {
+    if (!g) return RB_EINVAL;
+    rb_ctx* ctx = g->ctx;
+    LOCK(ctx);
+    if ((rpkbf && !g->rpk) || (fpkbf && !g->fpk)) return fail(ctx, RB_ESTATE, "sync_to_host: the graph has no such pair filter");
+    // the four copies are queued back to back (pageable destinations are staged by the driver; pinned ones run at PCIe speed)
+    if (dbgbf) CK(cudaMemcpyAsync(dbgbf, g->dbg->dev, (size_t)g->dbg->nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cbf) CK(cudaMemcpyAsync(cbf, g->cbf->dev, (size_t)g->cbf->nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rpkbf) CK(cudaMemcpyAsync(rpkbf, g->rpk->dev, (size_t)g->rpk->nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (fpkbf) CK(cudaMemcpyAsync(fpkbf, g->fpk->dev, (size_t)g->fpk->nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    return RB_OK;
+}
+
 // ---- synthetic workload ----------------------------------------------------------------------------------------------------
 extern "C" int32_t rb_synth_reads_dev(rb_ctx* ctx, uint64_t seed, uint64_t genome_len, uint64_t first_read, int64_t n_reads, int32_t L,
                                       uint32_t err_ppm, int64_t stride_bases, uint64_t* packed_dev) {
@@ -1298,5 +1323,5 @@ extern "C" int32_t rb_synth_reads_dev(rb_ctx* ctx, uint64_t seed, uint64_t genom
 }
 
 #include "rb_sliced_host.inl"
-#include "rb_sshard_host.inl"
+#include "rb_mgraph_host.inl"
 

@@ -366,6 +366,14 @@ class BloomFilterDeBruijnGraph:
     def setPairedKmerDistances(self, readPairedKmersDistance, fragmentPairedKmersDistance=-1):
         self.ctx.check(self.ctx.L.rb_graph_set_distances(self.h, readPairedKmersDistance, fragmentPairedKmersDistance))
 
+    def syncToHost(self, dbgbf=None, cbf=None, rpkbf=None, fpkbf=None):
+        """Barrier + refresh of host mirrors (numpy uint8 arrays of the filters' byte lengths; None skips a filter): the host side of
+        java/rnabloom/gpu/GpuBloomFilterDeBruijnGraph.syncToHost()."""
+        self.ctx.check(self.ctx.L.rb_graph_sync_to_host(self.h, _ptr(dbgbf), _ptr(cbf), _ptr(rpkbf), _ptr(fpkbf)))
+
+    def sync(self):
+        self.ctx.check(self.ctx.L.rb_graph_sync(self.h))
+
     def clear(self):
         self.ctx.check(self.ctx.L.rb_graph_clear(self.h))
 

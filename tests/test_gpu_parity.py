@@ -701,6 +701,12 @@ def test_upload_download_save_load_roundtrip(ctx, orc, tmp_path):
     for s in seqs:
         og.add_read(s, flags=F_STORE_READ_PAIRS | F_STORE_FRAG_PAIRS)
     g.addReads(rb.pack_reads(seqs), flags=rb.STORE_READ_PAIRS | rb.STORE_FRAG_PAIRS)
+    # host mirror (rb_graph_sync_to_host): what the JVM's Unsafe buffers hold after syncToHost() is the oracle's arrays, byte for byte
+    mirror = [np.full(f.num_bytes, 0xAA, dtype=np.uint8) for f in (g.getDbgbf(), g.getCbf(), g.getRpkbf(), g.getFpkbf())]
+    g.syncToHost(*mirror)
+    assert (mirror[0] == og.dbgbf()).all() and (mirror[2] == og.rpkbf()).all() and (mirror[3] == og.fpkbf()).all()
+    assert (mirror[1] == g.getCbf().download()).all()
+    g.syncToHost(None, mirror[1], None, None)   # NULL skips a filter
     path = tmp_path / "rnabloom.graph"
     g.save(path)
     # raw dumps are the byte arrays themselves (UnsafeByteBuffer.write :160-183); desc grammar BloomFilter.java:113-124
@@ -802,69 +808,21 @@ class DevReads:
             self.ctx.dev_free(p)
 
 
-@pytest.mark.parametrize("stranded,hd,hc", [(False, 3, 3), (True, 2, 4)])
-def test_sharded_pipeline_single_rank_matches_oracle(orc, stranded, hd, hc):
+@pytest.mark.parametrize("stranded,hd,hc,dbg_bits,cbf_bytes", [(False, 3, 3, (1 << 30) + 77, (1 << 28) + 13), (True, 2, 3, (1 << 30) + 77, (1 << 28) + 13),
+                                                                 (False, 3, 3, 1 << 31, 1 << 28)])
+def test_sharded_graph_single_rank_matches_oracle(orc, stranded, hd, hc, dbg_bits, cbf_bytes):
+    """rb_mgraph_* on one GPU (world = 1 makes every exchange the identity; the last case has paired probe records);
+    tests/test_sharded_sliced_gloo.py runs the same library orchestrator at world sizes 2, 4 and 8 over the host emulation of the kernels,
+    `bench.py --gpus N` and scripts/check_sharded_nccl.py compare it with the oracle over NCCL on real GPUs."""
     import torch
-    from rnabloom_b200.sharded import GpuBackend, ShardedGraph
+    from rnabloom_b200.sharded import ShardedGraph
     from parity_util import all_bases, assert_cbf_close
     ctx = rb.Context(0)
-    k, dbg_bits, cbf_bytes = 25, (1 << 30) + 77, (1 << 28) + 13
+    k = 25
     reads = orc.synth_reads(61, 90000, 0, 1200, 150, 6000)  # 2x coverage: counters stay in the exact MiniFloat range
     seqs = [bytes(r).decode() for r in reads]
     seqs[3] = seqs[3][:70] + "N" + seqs[3][71:]
-    be = GpuBackend(ctx, 1, 0, dbg_bits, cbf_bytes, hd, hc, k, stranded, max_kmers_per_round=80000)
-    sg = ShardedGraph(be, 0, 1)
-    og = OracleGraph(orc, dbg_bits, cbf_bytes, 64, hd, hc, 1, k, stranded, False)
-    per_round = 400
-    for r in range(3):
-        chunk = seqs[r * per_round:(r + 1) * per_round]
-        dr = DevReads(ctx, rb.pack_reads(chunk))
-        n = sg.add_round(dr.args, 0)
-        sg.check_overflow()
-        assert n == sum(max(0, len(s) - k + 1) for s in chunk)
-        dr.free()
-        for s in chunk:
-            og.add_read(s)
-    # the same reads again: every k-mer is present now, with multiplicities inside one round
-    dr = DevReads(ctx, rb.pack_reads(seqs[:400] + seqs[:200]))
-    sg.add_round(dr.args, 0)
-    dr.free()
-    for s in seqs[:400] + seqs[:200]:
-        og.add_read(s)
-    dr = DevReads(ctx, rb.pack_reads(seqs[100:300]))
-    sg.add_round(dr.args, rb.ADD_COUNT_IF_PRESENT)
-    sg.add_round(dr.args, rb.DBG_ONLY)
-    for s in seqs[100:300]:
-        og.add_read(s, flags=F_ADD_COUNT_IF_PRESENT)
-    assert (sg.gather_filter(rb.RB_DBGBF, (dbg_bits + 7) // 8) == og.dbgbf()).all()
-    bases = all_bases(orc, seqs, k, [MODE_FWD if stranded else MODE_CANON])
-    assert_cbf_close(sg.gather_filter(rb.RB_CBF, cbf_bytes), og.cbf(), bases, k, hc, cbf_bytes)
-    n_inst = sum(max(0, len(s) - k + 1) for s in seqs[100:300])
-    counts = torch.zeros(n_inst, dtype=torch.float32, device="cuda")
-    fh = torch.zeros(n_inst, dtype=torch.int64, device="cuda")
-    sg.count_round(dr.args, counts, fh)
-    ctx.sync()
-    want = np.concatenate([og.count_seq(s)[0] for s in seqs[100:300]])
-    wantf = np.concatenate([og.count_seq(s)[1] for s in seqs[100:300]])
-    assert (counts.cpu().numpy() == want).mean() > 0.999 and (fh.cpu().numpy() == wantf).all()
-    dr.free()
-    be.close(), og.close(), ctx.close()
-
-
-@pytest.mark.parametrize("stranded,hd,hc", [(False, 3, 3), (True, 2, 3)])
-def test_sharded_sliced_graph_single_rank_matches_oracle(orc, stranded, hd, hc):
-    """rb_sshard_* phase by phase on one GPU (world = 1 makes every exchange the identity); tests/test_sharded_sliced_gloo.py runs the same
-    orchestrator at world sizes 2 and 4 over the host emulation of the kernels."""
-    import torch
-    from rnabloom_b200.sharded import SlicedBackend, SlicedShardedGraph
-    from parity_util import all_bases, assert_cbf_close
-    ctx = rb.Context(0)
-    k, dbg_bits, cbf_bytes = 25, (1 << 30) + 77, (1 << 28) + 13
-    reads = orc.synth_reads(61, 90000, 0, 1200, 150, 6000)  # 2x coverage: counters stay in the exact MiniFloat range
-    seqs = [bytes(r).decode() for r in reads]
-    seqs[3] = seqs[3][:70] + "N" + seqs[3][71:]
-    be = SlicedBackend(ctx, 1, 0, dbg_bits, cbf_bytes, hd, hc, k, stranded, 80000)
-    sg = SlicedShardedGraph(be, 0, 1)
+    sg = ShardedGraph(ctx, 1, 0, dbg_bits, cbf_bytes, hd, hc, k, stranded, 80000)
     og = OracleGraph(orc, dbg_bits, cbf_bytes, 64, hd, hc, 1, k, stranded, False)
     for r in range(3):
         chunk = seqs[r * 400:(r + 1) * 400]
@@ -896,4 +854,4 @@ def test_sharded_sliced_graph_single_rank_matches_oracle(orc, stranded, hd, hc):
     wantf = np.concatenate([og.count_seq(s)[1] for s in seqs[100:300]])
     assert (counts.cpu().numpy() == want).mean() > 0.999 and (fh.cpu().numpy() == wantf).all()
     dr.free()
-    be.close(), og.close(), ctx.close()
+    sg.close(), og.close(), ctx.close()

@@ -1,6 +1,6 @@
-"""The hash-sharded graph on the sliced engine (rb_sshard_*, rna-bloom_b200/sharded.py SlicedShardedGraph) at world sizes 2, 4 and 8 on
-CPU: gloo all-to-all exchanges between processes that each run the *real* kernel sources through the host emulation of
-tests/emu (test infrastructure, see tests/test_emu_parity.py).  Checks that probes reach the owner of their filter slice, answers come
+"""The hash-sharded graph (rb_mgraph_*, csrc/rb_mgraph_host.inl; host mirror rna-bloom_b200/sharded.py ShardedGraph) at world sizes 2, 4
+and 8 on CPU: the library's own round orchestrator with a gloo transport plugged in, between processes that each run the *real* kernel
+sources through the host emulation of tests/emu (test infrastructure, see tests/test_emu_parity.py).  Checks that probes reach the owner of their filter slice, answers come
 back to the right k-mer, duplicates of a k-mer that live on different ranks are aggregated at the key's home rank, and the
 concatenated shares equal the sequential oracle's single arrays."""
 import os
@@ -42,14 +42,13 @@ def _worker(rank, world, port, stranded, out, cfg=None):
     try:
         import rnabloom_b200 as rb
         from rnabloom_b200 import binding as B
-        from rnabloom_b200.sharded import SlicedBackend, SlicedShardedGraph
+        from rnabloom_b200.sharded import GlooTransport, ShardedGraph
         from test_emu_parity import EMU_SO
         B._lib = B.bind(EMU_SO, allow_missing=True)   # the emulated kernels: "device memory" is host memory
         reads = _reads(cfg.get("seed", 13))
         mine = reads[rank::world]
         ctx = rb.Context(0)
-        be = SlicedBackend(ctx, world, rank, DBG_BITS, CBF_BYTES, HD, HC, K, stranded, 8000, device=torch.device("cpu"))
-        sg = SlicedShardedGraph(be, rank, world)
+        sg = ShardedGraph(ctx, world, rank, DBG_BITS, CBF_BYTES, HD, HC, K, stranded, 8000, transport=GlooTransport(), device=torch.device("cpu"))
         per_round = 40
         n_rounds = -(-max(len(reads[r::world]) for r in range(world)) // per_round)
         total = 0
@@ -76,20 +75,29 @@ def _worker(rank, world, port, stranded, out, cfg=None):
         np.save(os.path.join(out, "counts%d.npy" % rank), counts.numpy()[:n_inst])
         np.save(os.path.join(out, "fh%d.npy" % rank), fh.numpy()[:n_inst])
         assert sg.exchanged_bytes > 0
-        be.close(), ctx.close()
+        sg.close(), ctx.close()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,stranded", [(2, False), (2, True), (4, False), (8, False)])
-def test_sharded_sliced_graph_matches_oracle(tmp_path, orc, world, stranded):
+# paired: cbf_bytes = 2^c dividing dbg_bits and h_d >= h_c -> one probe record per hash, a rank owns paired slices (its bits are a
+# range inside every chunk of cbf_bytes bits: gather_filter reassembles them)
+PAIRED = {"dbg_bits": 5 << 22, "cbf_bytes": 1 << 22, "hd": 3, "hc": 3, "env": {"RB_SLICE_PAIR_LOG2": "13"}}
+
+
+@pytest.mark.parametrize("world,stranded,paired", [(2, False, False), (2, True, False), (4, False, False), (8, False, False), (2, False, True),
+                                                   (4, True, True)])
+def test_sharded_sliced_graph_matches_oracle(tmp_path, orc, world, stranded, paired):
     from oracle.binding import MODE_CANON, MODE_FWD, OracleGraph
     from parity_util import all_bases, assert_cbf_close
     from test_emu_parity import build_emu
     build_emu()
-    port = 31500 + os.getpid() % 2000 + world * 3 + (1 if stranded else 0)
-    mp.spawn(_worker, args=(world, port, stranded, str(tmp_path)), nprocs=world, join=True)
+    port = 31500 + os.getpid() % 2000 + world * 3 + (1 if stranded else 0) + (40 if paired else 0)
+    cfg = PAIRED if paired else None
+    mp.spawn(_worker, args=(world, port, stranded, str(tmp_path), cfg), nprocs=world, join=True)
     reads = _reads()
+    DBG_BITS, CBF_BYTES, HD, HC = ((cfg["dbg_bits"], cfg["cbf_bytes"], cfg["hd"], cfg["hc"]) if paired else
+                                   (globals()["DBG_BITS"], globals()["CBF_BYTES"], globals()["HD"], globals()["HC"]))
     og = OracleGraph(orc, DBG_BITS, CBF_BYTES, 64, HD, HC, 1, K, stranded, False)
     for s in reads:
         og.add_read(s)
@@ -165,7 +173,7 @@ def _parity_worker(rank, world, port, out):
     try:
         import rnabloom_b200 as rb
         from rnabloom_b200 import binding as B
-        from rnabloom_b200.sharded import SlicedBackend, SlicedShardedGraph
+        from rnabloom_b200.sharded import GlooTransport, ShardedGraph
         from test_emu_parity import EMU_SO
         import bench_multi
         B._lib = B.bind(EMU_SO, allow_missing=True)
@@ -173,7 +181,7 @@ def _parity_worker(rank, world, port, out):
         cpu = torch.device("cpu")
 
         def make_graph(db, cb, max_kmers):
-            return SlicedShardedGraph(SlicedBackend(ctx, world, rank, db, cb, 3, 3, 25, False, max_kmers, device=cpu), rank, world)
+            return ShardedGraph(ctx, world, rank, db, cb, 3, 3, 25, False, max_kmers, transport=GlooTransport(), device=cpu)
         full_d, full_c = 1 << 27, 1 << 24
         full = make_graph(full_d, full_c, 40000)
         res = bench_multi.sharded_parity_check(make_graph, rank, world, cpu, full_d, full_c, full, small=(3_000_017, 1_000_003, 120, 40), n_full=120)
