@@ -171,12 +171,21 @@ def main():
     ap.add_argument("--engine", default=os.environ.get("RB_ENGINE", "sliced"), choices=["direct", "sliced", "auto"])
     ap.add_argument("--sharded", action="store_true", help="experiments only: run the sharded pipeline even on one GPU")
     ap.add_argument("--genome", type=int, default=GENOME, help="experiments only: virtual genome length (coverage knob)")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 3, 4],
+                    help="BASELINE.json configs[i]: 1 = the headline workload (default), 3 = stranded k=35 + read paired k-mers, 4 = ONT-like long reads k=17 "
+                         "(single GPU; bench_configs.py)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.config != 1:
+        if world > 1:
+            raise SystemExit("--config 3 / 4 are single-GPU workloads")
+        import bench_configs
+        (bench_configs.run_config3 if args.config == 3 else bench_configs.run_config4)(args)
         return
     if world > 1 or args.sharded:
         if world == 1:

@@ -192,7 +192,7 @@ def run_sharded(args, rank, world, local_rank):
         first = (s * world + rank) * n_reads                   # disjoint read ids per rank and step
         ctx.synth_reads_dev(single.SEED, genome, first, n_reads, L, single.ERR_PPM, STRIDE, t.data_ptr())
         batches.append(t)
-    counts = torch.empty(reads_per_round * kpr, dtype=torch.float32, device="cuda")
+    counts = torch.empty(n_reads * kpr, dtype=torch.float32, device="cuda")   # one step's counts; round r writes its own slice
     import ctypes as C
 
     def reads_of(t, r):
@@ -206,7 +206,7 @@ def run_sharded(args, rank, world, local_rank):
             sg.add_round(reads_of(t, r), 0)
         e[1].record(stream)
         for r in range(rounds):
-            sg.count_round(reads_of(t, r), counts)
+            sg.count_round(reads_of(t, r), counts[r * reads_per_round * kpr:])
         e[2].record(stream)
         return e
 
@@ -221,6 +221,8 @@ def run_sharded(args, rank, world, local_rank):
     l0 = ctx.kernel_launches()
     x0 = sg.exchanged_bytes
     evs = []
+    ctx.profile_enable(True)   # CUDA-event spans around every kernel and every exchange of the timed region (library side)
+    ctx.profile_read()
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -229,7 +231,8 @@ def run_sharded(args, rank, world, local_rank):
     torch.cuda.synchronize()
     dist.barrier()
     wall = time.perf_counter() - t0
-    sg.check_overflow()
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
     t_ins = sum(e[0].elapsed_time(e[1]) for e in evs)
     t_look = sum(e[1].elapsed_time(e[2]) for e in evs)
     tt = torch.tensor([t_ins + t_look, t_ins, t_look, wall * 1e3], dtype=torch.float64, device="cuda")
@@ -239,33 +242,50 @@ def run_sharded(args, rank, world, local_rank):
     value = nk_rank * world * args.steps / (t_total * 1e-3)
     launches = ctx.kernel_launches() - l0
     xbytes = (sg.exchanged_bytes - x0) / args.steps
+    # per-phase device time of THIS rank (rank 0 reports its own; an exchange span includes waiting for the slowest peer)
+    kern_ms = {k_: round(v[0] / args.steps, 4) for k_, v in prof.items() if k_ != "exchange"}
+    exch_ms = round(prof.get("exchange", (0.0, 0))[0] / args.steps, 4)
 
-    # end to end at N GPUs: packed reads start in pinned host memory, counts end there
+    # end to end at N GPUs: packed reads start in pinned host memory, counts end there.  The D2H of a step's counts runs on a copy
+    # stream out of one of two count buffers, so it overlaps the next step's insert rounds (as the single-GPU host-pointer calls do)
     e2e = None
     if not args.no_e2e:
-        e_steps = 2
+        e_steps = 3
         h_in = torch.empty(words + 8, dtype=torch.int64).pin_memory()
         h_in.copy_(batches[0].cpu())
-        h_out = torch.empty(reads_per_round * kpr, dtype=torch.float32).pin_memory()
+        h_out = torch.empty(n_reads * kpr, dtype=torch.float32).pin_memory()
         d_in = torch.empty_like(batches[0])
+        cbuf = [counts, torch.empty_like(counts)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        copied = [None, None]
+        torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(e_steps):
+        for i in range(e_steps):
+            c = cbuf[i % 2]
             with torch.cuda.stream(stream):
                 d_in.copy_(h_in, non_blocking=True)
             for r in range(rounds):
                 sg.add_round(reads_of(d_in, r), 0)
+            if copied[i % 2] is not None:
+                stream.wait_event(copied[i % 2])      # the D2H that last read this count buffer is done
             for r in range(rounds):
-                sg.count_round(reads_of(d_in, r), counts)
-                with torch.cuda.stream(stream):
-                    h_out.copy_(counts, non_blocking=True)
-            torch.cuda.synchronize()
+                sg.count_round(reads_of(d_in, r), c[r * reads_per_round * kpr:])
+            done = torch.cuda.Event()
+            done.record(stream)
+            copy_stream.wait_event(done)
+            with torch.cuda.stream(copy_stream):
+                h_out.copy_(c, non_blocking=True)
+                copied[i % 2] = torch.cuda.Event()
+                copied[i % 2].record(copy_stream)
+        torch.cuda.synchronize()
         dist.barrier()
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": nk_rank * world * e_steps / float(te.item()), "unit": "k-mers/s", "h2d_bytes_per_step": words * 8 * world,
                "d2h_bytes_per_step": nk_rank * 4 * world, "steps": e_steps}
+        del cbuf, h_out, h_in
 
     # ---- correctness of the path that was just timed: oracle comparison over NCCL (all ranks; a difference fails the run) -----------------
     parity = None
@@ -293,7 +313,8 @@ def run_sharded(args, rank, world, local_rank):
         cfg.update({"dbgbf_bits": dbg_bits, "cbf_bytes": cbf_bytes, "genome_len": genome,
                     "workload": "BASELINE.json configs[2] shape, weak-scaled: %d x %d reads/step, k=25, dbgbf %d GiB + cbf %d GiB sharded by index range over %d GPUs"
                                 % (world, n_reads, dbg_bits >> 33, cbf_bytes >> 30, world),
-                    "exchange": "library-owned NCCL all-to-all (rb_mgraph_*), %.0f MB per rank per step" % (xbytes / 1e6),
+                    "exchange": ("peer-to-peer: consumer kernels read the producers' arenas over NVLink (CUDA IPC), NCCL only for barriers"
+                                 if sg.peer_to_peer else "library-owned NCCL all-to-all (rb_mgraph_*), %.0f MB per rank per step" % (xbytes / 1e6)),
                     "paired_probe_records": bool(sg.paired), "kmers_per_round_per_gpu": reads_per_round * kpr})
         line = {"metric": "k-mers/s (insert+lookup) at k=25, 2x150 bp reads", "value": value, "unit": "k-mers/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -302,7 +323,9 @@ def run_sharded(args, rank, world, local_rank):
                 "roofline": {"bound": "hbm", "kernel": "sharded pipeline (whole step, per GPU)", "achieved": value / world * single.A_STEP / 1e9,
                              "peak": hbm, "unit": "GB/s", "frac": value / world * single.A_STEP / 1e9 / hbm, "traffic": None,
                              "peak_source": peak_src, "insert_gkmers_s": nk_rank * world * args.steps / t_ins / 1e6,
-                             "lookup_gkmers_s": nk_rank * world * args.steps / t_look / 1e6},
+                             "lookup_gkmers_s": nk_rank * world * args.steps / t_look / 1e6,
+                             "kernels_ms_per_step": kern_ms, "exchange_ms_per_step": exch_ms,
+                             "exchange_gb_per_rank_per_step": xbytes / 1e9},
                 "cpu_baseline": None, "wall_s_timed_region": wall_ms / 1e3, "parity_check": parity}
         print(json.dumps(line), flush=True)
     elif parity is not None and "error" in parity:

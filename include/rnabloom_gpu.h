@@ -250,6 +250,10 @@ typedef struct rb_transport {
     int32_t (*all_to_all)(void* user, const void* send, void* recv, int64_t bytes_per_rank, void* stream);
     /* element-wise maximum of n int32 over all ranks, in place */
     int32_t (*all_reduce_max)(void* user, int32_t* buf, int64_t n, void* stream);
+    /* optional (may be NULL): every rank contributes `bytes` bytes, recv holds the contributions in rank order.  With it, ranks on one box
+     * exchange CUDA IPC handles at creation and the round kernels then read each other's arenas directly over NVLink (peer-to-peer mode:
+     * no staged exchange, the transport is only used for barriers); without it every exchange is a staged all_to_all. */
+    int32_t (*all_gather)(void* user, const void* send, void* recv, int64_t bytes, void* stream);
 } rb_transport;
 RB_API int32_t rb_nccl_unique_id(void* id128, int64_t len);   /* ncclGetUniqueId; len >= 128 */
 RB_API int32_t rb_mgraph_create_nccl(rb_ctx* ctx, int32_t n_ranks, int32_t rank, const void* nccl_unique_id, int64_t dbgbf_bits, int64_t cbf_bytes,
@@ -267,11 +271,19 @@ RB_API int32_t rb_mgraph_destroy(rb_mgraph* mg);
 RB_API int32_t rb_mgraph_layout(rb_mgraph* mg, int64_t* layout9);
 RB_API int32_t rb_mgraph_filter(rb_mgraph* mg, int32_t which, rb_filter** out);   /* this rank's share (borrowed): popcount, download, empty */
 RB_API int32_t rb_mgraph_stats(rb_mgraph* mg, int64_t* exchanged_bytes, int64_t* rounds);
+RB_API int32_t rb_mgraph_peer_to_peer(rb_mgraph* mg);   /* 1: the round kernels read / write peer memory over NVLink (CUDA IPC); 0: staged all_to_all */
 RB_API int32_t rb_mgraph_add_round_dev(rb_mgraph* mg, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
                                        int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, uint32_t flags, int64_t* n_kmers_out);
 RB_API int32_t rb_mgraph_count_round_dev(rb_mgraph* mg, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
                                          int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, float* counts, int64_t* fhash, int64_t* rhash,
                                          int64_t* n_kmers_out);
+
+/* Long reads for BASELINE configs[4] (ONT-like): read r has rb_synth_long_read_len(seed, r) bases (500..3497, mean ~2 kb) with
+ * substitutions, insertions and deletions at the given rates per 1e6 emitted bases; ragged layout: read i of the call starts at base
+ * read_off_dev[i] (a multiple of 32) of packed_dev.  Same generator, bit for bit, in the CPU checker. */
+RB_API int32_t rb_synth_long_read_len(uint64_t seed, uint64_t read);
+RB_API int32_t rb_synth_long_reads_dev(rb_ctx* ctx, uint64_t seed, uint64_t genome_len, uint64_t first_read, int64_t n_reads, uint32_t sub_ppm,
+                                       uint32_t ins_ppm, uint32_t del_ppm, const int64_t* read_off_dev, uint64_t* packed_dev);
 
 #ifdef __cplusplus
 }

@@ -100,6 +100,10 @@ def load():
         "orc_synth_read": (None, [u64, u64, u64, i32, C.c_uint32, vp]),
         "orc_synth_reads": (None, [u64, u64, u64, u64, i32, C.c_uint32, vp]),
         "orc_graph_run_mt": (i64, [vp, vp, i64, i32, i32, i32, i32, vp]),
+        "orc_graph_run_mt_ragged": (i64, [vp, vp, vp, i64, i32, i32, i32, i32, vp]),
+        "orc_synth_long_len": (i32, [u64, u64]),
+        "orc_synth_long_read": (i32, [u64, u64, u64, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
+        "orc_synth_long_reads": (i64, [u64, u64, u64, u64, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -175,6 +179,14 @@ class Oracle:
         self.lib.orc_synth_reads(seed, genome_len, first, n, L, err_ppm, out.ctypes.data)
         return out
 
+    def synth_long_reads(self, seed, genome_len, first, n, sub_ppm, ins_ppm, del_ppm):
+        """ONT-like ragged reads (BASELINE configs[4]): (ASCII bases concatenated, offsets[n + 1])."""
+        lens = np.array([self.lib.orc_synth_long_len(seed, first + r) for r in range(n)], dtype=np.int64)
+        out = np.zeros(int(lens.sum()) + 8, dtype=np.uint8)
+        off = np.zeros(n + 1, dtype=np.int64)
+        total = self.lib.orc_synth_long_reads(seed, genome_len, first, n, sub_ppm, ins_ppm, del_ppm, out.ctypes.data, off.ctypes.data)
+        return out[:total], off
+
     # ---- raw buffer views ----------------------------------------------------------------
     def bf_array(self, bf):
         n = self.lib.orc_bf_nbytes(bf)
@@ -243,6 +255,15 @@ class OracleGraph:
 
     def fpkbf(self):
         return self.o.bf_array(self.lib.orc_graph_fpkbf(self.g))
+
+    def run_mt_ragged(self, bases, off, flags, lookup, nthreads):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        cs = C.c_double(0)
+        max_len = int(np.diff(off).max()) if len(off) > 1 else 0
+        km = self.lib.orc_graph_run_mt_ragged(self.g, bases.ctypes.data, off.ctypes.data, len(off) - 1, max_len, flags, int(lookup), nthreads,
+                                              C.addressof(cs))
+        return km, cs.value
 
     def run_mt(self, reads, flags, lookup, nthreads):
         reads = np.ascontiguousarray(reads, dtype=np.uint8)

@@ -601,6 +601,37 @@ ORC_API void orc_synth_reads(uint64_t seed, uint64_t genome_len, uint64_t first,
     for (uint64_t r = 0; r < n; ++r) orc_synth_read(seed, genome_len, first + r, L, err_ppm, out + r * (uint64_t)L);
 }
 
+/* long reads (BASELINE configs[4]): the twin of k_synth_long_reads (rna-bloom_b200/csrc/rb_kernels.cuh), integer arithmetic only */
+ORC_API int orc_synth_long_len(uint64_t seed, uint64_t r) {
+    uint64_t h = splitmix64(seed * 0x100000001B3ULL + 2 * r);
+    return 500 + (int)(h % 1000u) + (int)((h >> 20) % 1000u) + (int)((h >> 40) % 1000u);
+}
+ORC_API int orc_synth_long_read(uint64_t seed, uint64_t genome_len, uint64_t r, uint32_t sub_ppm, uint32_t ins_ppm, uint32_t del_ppm, uint8_t* out) {
+    static const char NT[4] = {'A', 'C', 'G', 'T'};
+    int L = orc_synth_long_len(seed, r);
+    uint64_t h = splitmix64(seed * 0x100000001B3ULL + 2 * r + 1);
+    uint64_t span = (uint64_t)(2 * L + 64);
+    uint64_t p0 = (h >> 1) % (genome_len - span + 1);
+    int rc = (int)(h & 1);
+    uint64_t gpos = 0;
+    for (int i = 0; i < L; ++i) {
+        int b;
+        for (int tries = 0;; ++tries) {
+            uint64_t e = splitmix64((seed + 0x5851F42D4C957F2DULL) ^ splitmix64(r * 8192 + (uint64_t)i * 4 + (uint64_t)(tries < 3 ? tries : 3)));
+            uint32_t u = (uint32_t)(e % 1000000u);
+            if (u < del_ppm && tries < 3 && gpos + 1 < span) { ++gpos; continue; }
+            int gb = rc ? 3 - genome_base(seed, p0 + span - 1 - gpos) : genome_base(seed, p0 + gpos);
+            if (u < del_ppm + ins_ppm) { b = (int)((e >> 40) & 3); break; }
+            b = gb;
+            if (u < del_ppm + ins_ppm + sub_ppm) b = (gb + 1 + (int)((e >> 40) % 3)) & 3;
+            if (gpos + 1 < span) ++gpos;
+            break;
+        }
+        out[i] = (uint8_t)NT[b];
+    }
+    return L;
+}
+
 /* ------------------------------------------------------------------------------------------
  * CPU baseline: reference-faithful threaded insert / lookup (RNABloom.java:1189-1205 thread model:
  * N workers share one graph and pull reads from one synchronized reader, io/FastqReader.java:140-151;
@@ -609,6 +640,7 @@ ORC_API void orc_synth_reads(uint64_t seed, uint64_t genome_len, uint64_t first,
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
     orc_graph* g; const uint8_t* reads; int64_t n; int L; int flags; int lookup;
+    const int64_t* off;   /* ragged reads: read r = reads[off[r], off[r+1]); NULL: fixed length L */
     int64_t cursor; pthread_mutex_t mu; int64_t kmers; double checksum;
 } mt_job;
 
@@ -622,13 +654,14 @@ static void* mt_worker(void* arg) {
         int64_t r = j->cursor++;
         pthread_mutex_unlock(&j->mu);
         if (r >= j->n) break;
-        const uint8_t* s = j->reads + r * (int64_t)j->L;
+        const uint8_t* s = j->off ? j->reads + j->off[r] : j->reads + r * (int64_t)j->L;
+        const int len = j->off ? (int)(j->off[r + 1] - j->off[r]) : j->L;
         if (j->lookup) {
-            int64_t nk = orc_graph_count_seq(j->g, s, 0, j->L, counts, NULL, NULL);
+            int64_t nk = orc_graph_count_seq(j->g, s, 0, len, counts, NULL, NULL);
             for (int64_t i = 0; i < nk; ++i) cs += counts[i];
             kmers += nk;
         } else {
-            kmers += orc_graph_add_read(j->g, s, NULL, j->L, 0, j->flags);
+            kmers += orc_graph_add_read(j->g, s, NULL, len, 0, j->flags);
         }
     }
     free(counts);
@@ -638,11 +671,27 @@ static void* mt_worker(void* arg) {
     return NULL;
 }
 
+static int64_t run_mt(orc_graph* g, const uint8_t* reads, const int64_t* off, int64_t n, int L, int flags, int lookup, int nthreads, double* checksum);
 ORC_API int64_t orc_graph_run_mt(orc_graph* g, const uint8_t* reads, int64_t n, int L, int flags,
                                  int lookup, int nthreads, double* checksum) {
+    return run_mt(g, reads, NULL, n, L, flags, lookup, nthreads, checksum);
+}
+/* ragged reads: off has n + 1 entries; max_len bounds the longest read */
+ORC_API int64_t orc_graph_run_mt_ragged(orc_graph* g, const uint8_t* bases, const int64_t* off, int64_t n, int max_len, int flags,
+                                        int lookup, int nthreads, double* checksum) {
+    return run_mt(g, bases, off, n, max_len, flags, lookup, nthreads, checksum);
+}
+ORC_API int64_t orc_synth_long_reads(uint64_t seed, uint64_t genome_len, uint64_t first, uint64_t n, uint32_t sub_ppm, uint32_t ins_ppm,
+                                     uint32_t del_ppm, uint8_t* out, int64_t* off) {
+    int64_t at = 0;
+    for (uint64_t r = 0; r < n; ++r) { off[r] = at; at += orc_synth_long_read(seed, genome_len, first + r, sub_ppm, ins_ppm, del_ppm, out + at); }
+    off[n] = at;
+    return at;
+}
+static int64_t run_mt(orc_graph* g, const uint8_t* reads, const int64_t* off, int64_t n, int L, int flags, int lookup, int nthreads, double* checksum) {
     init_tables();
     mt_job j; memset(&j, 0, sizeof j);
-    j.g = g; j.reads = reads; j.n = n; j.L = L; j.flags = flags; j.lookup = lookup;
+    j.g = g; j.reads = reads; j.n = n; j.L = L; j.flags = flags; j.lookup = lookup; j.off = off;
     pthread_mutex_init(&j.mu, NULL);
     if (nthreads < 1) nthreads = 1;
     pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)nthreads);

@@ -121,6 +121,7 @@ def bind(path, allow_missing=False):
         "rb_mgraph_layout": (i32, [vp, C.POINTER(i64)]),
         "rb_mgraph_filter": (i32, [vp, i32, C.POINTER(vp)]),
         "rb_mgraph_stats": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
+        "rb_mgraph_peer_to_peer": (i32, [vp]),
         "rb_mgraph_add_round_dev": (i32, [vp] + reads + [u32, C.POINTER(i64)]),
         "rb_mgraph_count_round_dev": (i32, [vp] + reads + [vp, vp, vp, C.POINTER(i64)]),
         "rb_graph_create": (i32, [vp, i64, i64, i64, i32, i32, i32, i32, i32, i32, C.POINTER(vp)]),
@@ -145,6 +146,8 @@ def bind(path, allow_missing=False):
         "rb_graph_save": (i32, [vp, cp]),
         "rb_graph_load": (i32, [vp, cp, i32, i32, C.POINTER(vp)]),
         "rb_synth_reads_dev": (i32, [vp, u64, u64, u64, i64, i32, u32, i64, vp]),
+        "rb_synth_long_read_len": (i32, [u64, u64]),
+        "rb_synth_long_reads_dev": (i32, [vp, u64, u64, u64, i64, u32, u32, u32, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         if allow_missing and not hasattr(L, name):

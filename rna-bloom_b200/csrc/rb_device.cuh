@@ -77,7 +77,7 @@ __device__ __forceinline__ int minifloat_increment(int b, uint64_t rnd) {
     }
     return b;
 }
-__device__ __forceinline__ uint64_t mix64(uint64_t x) {  // splitmix64 finaliser: counter-based RNG and table hashing
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {  // splitmix64 finaliser: counter-based RNG and table hashing
     x += 0x9E3779B97F4A7C15ULL;
     x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;

@@ -492,6 +492,46 @@ __global__ void __launch_bounds__(kThreads) k_synth_reads(uint64_t seed, uint64_
     packed[rl * words_per_read + wi] = w;
 }
 
+// Long reads (BASELINE configs[4]: ONT-like, ~2 kb, substitutions + insertions + deletions).  Integer-only, so that the CPU checker's
+// twin (oracle/rnabloom_oracle.c orc_synth_long_read) produces the same bases: read r has length 500 + three draws of [0, 1000)
+// (mean ~2 kb) and walks the virtual genome from a random start on a random strand; per emitted base one draw decides
+// deletion (skip genome bases first) / insertion (random base, genome does not advance) / substitution / match.
+__host__ __device__ __forceinline__ int synth_long_len(uint64_t seed, uint64_t r) {
+    const uint64_t h = mix64(seed * 0x100000001B3ULL + 2 * r);
+    return 500 + (int)(h % 1000u) + (int)((h >> 20) % 1000u) + (int)((h >> 40) % 1000u);
+}
+__global__ void __launch_bounds__(kThreads) k_synth_long_reads(uint64_t seed, uint64_t genome_len, uint64_t first_read, int64_t n_reads, uint32_t sub_ppm,
+                                                              uint32_t ins_ppm, uint32_t del_ppm, const int64_t* __restrict__ read_off,
+                                                              uint64_t* __restrict__ packed) {
+    const int64_t rl = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (rl >= n_reads) return;
+    const uint64_t r = first_read + (uint64_t)rl;
+    const int L = synth_long_len(seed, r);
+    const uint64_t h = mix64(seed * 0x100000001B3ULL + 2 * r + 1);
+    const uint64_t span = (uint64_t)(2 * L + 64);                       // genome bases a read can consume at most (deletions)
+    const uint64_t p0 = (h >> 1) % (genome_len - span + 1);
+    const int rc = (int)(h & 1);
+    uint64_t gpos = 0;                                                  // genome bases consumed so far
+    uint64_t* out = packed + (read_off[rl] >> 5);
+    uint64_t w = 0;
+    for (int i = 0; i < L; ++i) {
+        int b;
+        for (int tries = 0;; ++tries) {
+            const uint64_t e = mix64((seed + 0x5851F42D4C957F2DULL) ^ mix64(r * 8192 + (uint64_t)i * 4 + (uint64_t)min(tries, 3)));
+            const uint32_t u = (uint32_t)(e % 1000000u);
+            if (u < del_ppm && tries < 3 && gpos + 1 < span) { ++gpos; continue; }      // deletion: the genome base is skipped
+            const int gb = rc ? 3 - synth_genome_base(seed, p0 + span - 1 - gpos) : synth_genome_base(seed, p0 + gpos);
+            if (u < del_ppm + ins_ppm) { b = (int)((e >> 40) & 3); break; }             // insertion: the genome does not advance
+            b = gb;
+            if (u < del_ppm + ins_ppm + sub_ppm) b = (gb + 1 + (int)((e >> 40) % 3)) & 3;
+            if (gpos + 1 < span) ++gpos;
+            break;
+        }
+        w |= (uint64_t)b << (2 * (i & 31));
+        if ((i & 31) == 31 || i == L - 1) { out[i >> 5] = w; w = 0; }
+    }
+}
+
 // ---- FASTQ/FASTA front end: ASCII (+PHRED33) -> 2-bit codes + usable-base mask ------------------------------------------
 // One thread per 32-base output word.  Replaces the host regex pre-pass (util/SeqUtils.java:1430-1438, RNABloom.java:567-577).
 __global__ void __launch_bounds__(kThreads) k_pack_ascii(const char* __restrict__ bases, const char* __restrict__ quals,

@@ -34,6 +34,7 @@ struct NcclApi {
     const char* (*GetErrorString)(int) = nullptr;
     int (*AlltoAll)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;   // NCCL >= 2.28
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
@@ -58,7 +59,7 @@ static bool nccl_load(std::string* why) {
 #define NCCL_SYM(field, name) a.field = reinterpret_cast<decltype(a.field)>(dlsym(h, name))
     NCCL_SYM(GetVersion, "ncclGetVersion"); NCCL_SYM(GetUniqueId, "ncclGetUniqueId"); NCCL_SYM(CommInitRank, "ncclCommInitRank");
     NCCL_SYM(CommDestroy, "ncclCommDestroy"); NCCL_SYM(GetErrorString, "ncclGetErrorString"); NCCL_SYM(AlltoAll, "ncclAlltoAll");
-    NCCL_SYM(AllReduce, "ncclAllReduce"); NCCL_SYM(GroupStart, "ncclGroupStart"); NCCL_SYM(GroupEnd, "ncclGroupEnd");
+    NCCL_SYM(AllReduce, "ncclAllReduce"); NCCL_SYM(AllGather, "ncclAllGather"); NCCL_SYM(GroupStart, "ncclGroupStart"); NCCL_SYM(GroupEnd, "ncclGroupEnd");
     NCCL_SYM(Send, "ncclSend"); NCCL_SYM(Recv, "ncclRecv");
 #undef NCCL_SYM
     if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce || !a.GroupStart || !a.GroupEnd || !a.Send || !a.Recv) {
@@ -106,6 +107,13 @@ static int32_t nccl_all_reduce_max(void* user, int32_t* buf, int64_t n, void* st
     return r ? nccl_fail(t->ctx, "ncclAllReduce", r) : RB_OK;
 }
 
+static int32_t nccl_all_gather(void* user, const void* send, void* recv, int64_t bytes, void* stream) {
+    NcclTransport* t = (NcclTransport*)user;
+    if (!g_nccl.AllGather) return fail(t->ctx, RB_ENCCL, "libnccl has no ncclAllGather");
+    const int r = g_nccl.AllGather(send, recv, (size_t)bytes, kNcclUint8, t->comm, (cudaStream_t)stream);
+    return r ? nccl_fail(t->ctx, "ncclAllGather", r) : RB_OK;
+}
+
 // ---- the sharded graph --------------------------------------------------------------------------------------------------------------------------
 struct rb_mgraph {
     rb_ctx* ctx;
@@ -136,6 +144,13 @@ struct rb_mgraph {
     uint8_t *ans, *home_ans;
     int64_t n_probe, n_key, n_raise;  // records of one send buffer (all destinations)
     int64_t exchanged_bytes, rounds;
+    // peer-to-peer mode (GPUs of one box, CUDA IPC): a consumer kernel reads the producers' send arenas directly over NVLink and writes
+    // its answers straight into the producers' answer arrays -- the transfer overlaps the filter work tile by tile and no separate
+    // exchange step (nor a receive buffer) exists; the transport is only used for barriers / flag agreement
+    bool p2p;
+    uint32_t* cnt_k;                  // packed key-range counts (its own array: peers may still read it while the probes are counted)
+    void** peer_open;                 // host: W * 5 pointers opened with cudaIpcOpenMemHandle (nullptr for this rank's own)
+    void **d_peer32, **d_peer64, **d_peer_ans, **d_peer_cnt, **d_peer_cntk;   // device tables [W]
 };
 
 extern "C" int32_t rb_mgraph_destroy(rb_mgraph* mg) {
@@ -151,9 +166,72 @@ extern "C" int32_t rb_mgraph_destroy(rb_mgraph* mg) {
     cudaFree(mg->probe_cursor); cudaFree(mg->key_cursor); cudaFree(mg->raise_cursor); cudaFree(mg->cons_cursor); cudaFree(mg->sub_cursor);
     cudaFree(mg->n_distinct); cudaFree(mg->cons_rlo); cudaFree(mg->pos); cudaFree(mg->tile_meta); cudaFree(mg->sub_data); cudaFree(mg->dkey);
     cudaFree(mg->dmult); cudaFree(mg->chunk_prefix); cudaFree(mg->flags);
-    cudaFree(mg->send32); cudaFree(mg->send64); cudaFree(mg->ans); cudaFree(mg->cnt_s);
-    if (mg->W > 1) { cudaFree(mg->recv32); cudaFree(mg->recv64); cudaFree(mg->home_ans); cudaFree(mg->cnt_r); }
+#ifndef RB_EMU
+    if (mg->peer_open) {
+        for (int i = 0; i < mg->W * 5; ++i) if (mg->peer_open[i]) cudaIpcCloseMemHandle(mg->peer_open[i]);
+        free(mg->peer_open);
+    }
+#endif
+    cudaFree(mg->d_peer32); cudaFree(mg->d_peer64); cudaFree(mg->d_peer_ans); cudaFree(mg->d_peer_cnt); cudaFree(mg->d_peer_cntk);
+    cudaFree(mg->send32); cudaFree(mg->send64); cudaFree(mg->home_ans); cudaFree(mg->cnt_s); cudaFree(mg->cnt_k);
+    if (mg->W > 1 && !mg->p2p) { cudaFree(mg->recv32); cudaFree(mg->recv64); cudaFree(mg->ans); cudaFree(mg->cnt_r); }
     delete mg;
+    return RB_OK;
+}
+
+// Peer-to-peer mode: every rank exports its send arenas, its answer array and its count arrays with CUDA IPC, the handles travel through
+// the transport's all_gather, every rank maps the others'.  All ranks agree (max-reduce of a failure flag) so that a box without
+// peer access falls back to the staged exchange everywhere.  RB_MGRAPH_P2P=0 forces the staged exchange.
+static int32_t mg_setup_p2p(rb_mgraph* mg) {
+    mg->p2p = false;
+#ifndef RB_EMU
+    rb_ctx* ctx = mg->ctx;
+    const int W = mg->W;
+    if (W == 1 || !mg->tr.all_gather || !env_int("RB_MGRAPH_P2P", 1, 0, 1)) return RB_OK;
+    void* mine[5] = {mg->send32, mg->send64, mg->home_ans, mg->cnt_s, mg->cnt_k};
+    std::vector<cudaIpcMemHandle_t> hs(5), all((size_t)W * 5);
+    int failed = 0;
+    for (int i = 0; i < 5; ++i) if (cudaIpcGetMemHandle(&hs[i], mine[i]) != cudaSuccess) failed = 1;
+    cudaGetLastError();
+    void *d_h = nullptr, *d_all = nullptr;
+    int* d_flag = nullptr;
+    const size_t hb = sizeof(cudaIpcMemHandle_t) * 5;
+    CK(cudaMalloc(&d_h, hb)); CK(cudaMalloc(&d_all, hb * W)); CK(cudaMalloc(&d_flag, 64));
+    CK(cudaMemcpyAsync(d_h, hs.data(), hb, cudaMemcpyHostToDevice, ctx->stream));
+    int32_t rc = mg->tr.all_gather(mg->tr.user, d_h, d_all, (int64_t)hb, ctx->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(all.data(), d_all, hb * W, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    mg->peer_open = (void**)calloc((size_t)W * 5, sizeof(void*));
+    std::vector<void*> tab((size_t)W * 5, nullptr);
+    for (int p = 0; p < W && !failed; ++p)
+        for (int i = 0; i < 5; ++i) {
+            if (p == mg->rank) { tab[(size_t)p * 5 + i] = mine[i]; continue; }
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[(size_t)p * 5 + i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { failed = 1; cudaGetLastError(); break; }
+            mg->peer_open[(size_t)p * 5 + i] = ptr;
+            tab[(size_t)p * 5 + i] = ptr;
+        }
+    CK(cudaMemcpyAsync(d_flag, &failed, 4, cudaMemcpyHostToDevice, ctx->stream));
+    rc = mg->tr.all_reduce_max(mg->tr.user, d_flag, 1, ctx->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(&failed, d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_h); cudaFree(d_all); cudaFree(d_flag);
+    if (failed) {   // somewhere a mapping failed: nobody uses peer memory
+        for (int i = 0; i < W * 5; ++i) if (mg->peer_open[i]) { cudaIpcCloseMemHandle(mg->peer_open[i]); mg->peer_open[i] = nullptr; }
+        return RB_OK;
+    }
+    void*** dst[5] = {&mg->d_peer32, &mg->d_peer64, &mg->d_peer_ans, &mg->d_peer_cnt, &mg->d_peer_cntk};
+    for (int i = 0; i < 5; ++i) {
+        std::vector<void*> col((size_t)W);
+        for (int p = 0; p < W; ++p) col[(size_t)p] = tab[(size_t)p * 5 + i];
+        CK(cudaMalloc(dst[i], sizeof(void*) * W));
+        CK(cudaMemcpyAsync(*dst[i], col.data(), sizeof(void*) * W, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    mg->p2p = true;
+#endif
     return RB_OK;
 }
 
@@ -267,16 +345,10 @@ static int32_t mgraph_create(rb_ctx* ctx, int32_t n_ranks, int32_t rank, const r
         if (er == cudaSuccess) er = cudaMemsetAsync(mg->flags, 0, 64, ctx->stream);
         if (er == cudaSuccess) er = cudaMalloc(&mg->send32, n32 * 4);
         if (er == cudaSuccess) er = cudaMalloc(&mg->send64, ((size_t)mg->n_key + kSlSpill) * 8);
-        if (er == cudaSuccess) er = cudaMalloc(&mg->ans, (size_t)mg->n_probe + kSlSpill);
+        if (er == cudaSuccess) er = cudaMalloc(&mg->home_ans, (size_t)mg->n_probe + kSlSpill);
         if (er == cudaSuccess) er = cudaMalloc(&mg->cnt_s, (size_t)maxB * 4 + 64);
-        if (W > 1) {
-            if (er == cudaSuccess) er = cudaMalloc(&mg->recv32, n32 * 4);
-            if (er == cudaSuccess) er = cudaMalloc(&mg->recv64, ((size_t)mg->n_key + kSlSpill) * 8);
-            if (er == cudaSuccess) er = cudaMalloc(&mg->home_ans, (size_t)mg->n_probe + kSlSpill);
-            if (er == cudaSuccess) er = cudaMalloc(&mg->cnt_r, (size_t)maxB * 4 + 64);
-        } else {
-            mg->recv32 = mg->send32; mg->recv64 = mg->send64; mg->home_ans = mg->ans; mg->cnt_r = mg->cnt_s;
-        }
+        if (er == cudaSuccess) er = cudaMalloc(&mg->cnt_k, (size_t)maxB * 4 + 64);
+        mg->recv32 = mg->send32; mg->recv64 = mg->send64; mg->ans = mg->home_ans; mg->cnt_r = mg->cnt_s;   // W == 1, and until decided otherwise
     }
     if (rc || er != cudaSuccess) {
         if (!rc) rc = fail(ctx, RB_ENOMEM, std::string("mgraph alloc: ") + cudaGetErrorString(er));
@@ -284,6 +356,8 @@ static int32_t mgraph_create(rb_ctx* ctx, int32_t n_ranks, int32_t rank, const r
         return rc;
     }
     mg->dbg->in_graph = mg->cbf->in_graph = true;
+    const int maxB_all = std::max(std::max(mg->R, mg->SR), mg->KR) * W;
+    const size_t n32_all = (size_t)std::max(mg->n_probe, mg->n_raise) + kSlSpill;
     if (tr) mg->tr = *tr;
     else if (W > 1) {
 #ifdef RB_EMU
@@ -299,8 +373,20 @@ static int32_t mgraph_create(rb_ctx* ctx, int32_t n_ranks, int32_t rank, const r
         if (r != 0) { rb_mgraph_destroy(mg); return nccl_fail(ctx, "ncclCommInitRank", r); }
         mg->nccl.comm = comm; mg->nccl.W = W; mg->nccl.rank = rank; mg->nccl.ctx = ctx;
         mg->own_comm = true;
-        mg->tr.user = &mg->nccl; mg->tr.all_to_all = nccl_all_to_all; mg->tr.all_reduce_max = nccl_all_reduce_max;
+        mg->tr.user = &mg->nccl; mg->tr.all_to_all = nccl_all_to_all; mg->tr.all_reduce_max = nccl_all_reduce_max; mg->tr.all_gather = nccl_all_gather;
 #endif
+    }
+    if (W > 1) {
+        rc = mg_setup_p2p(mg);
+        if (rc) { rb_mgraph_destroy(mg); return rc; }
+        if (!mg->p2p) {   // staged exchange: receive buffers and an owner-side answer array
+            mg->recv32 = nullptr; mg->recv64 = nullptr; mg->ans = nullptr; mg->cnt_r = nullptr;   // they aliased the send side until here
+            er = cudaMalloc(&mg->recv32, n32_all * 4);
+            if (er == cudaSuccess) er = cudaMalloc(&mg->recv64, ((size_t)mg->n_key + kSlSpill) * 8);
+            if (er == cudaSuccess) er = cudaMalloc(&mg->ans, (size_t)mg->n_probe + kSlSpill);
+            if (er == cudaSuccess) er = cudaMalloc(&mg->cnt_r, (size_t)maxB_all * 4 + 64);
+            if (er != cudaSuccess) { rb_mgraph_destroy(mg); return fail(ctx, RB_ENOMEM, std::string("mgraph exchange buffers: ") + cudaGetErrorString(er)); }
+        }
     }
     *out = mg;
     return RB_OK;
@@ -340,6 +426,7 @@ extern "C" int32_t rb_mgraph_filter(rb_mgraph* mg, int32_t which, rb_filter** ou
     *out = which == RB_DBGBF ? mg->dbg : which == RB_CBF ? mg->cbf : nullptr;
     return RB_OK;
 }
+extern "C" int32_t rb_mgraph_peer_to_peer(rb_mgraph* mg) { return mg && mg->p2p ? 1 : 0; }
 extern "C" int32_t rb_mgraph_stats(rb_mgraph* mg, int64_t* exchanged_bytes, int64_t* rounds) {
     if (!mg) return RB_EINVAL;
     if (exchanged_bytes) *exchanged_bytes = mg->exchanged_bytes;
@@ -354,13 +441,18 @@ static SlArena mg_producer(rb_mgraph* mg, void* data, unsigned int* cursor, int 
     return a;
 }
 // regions received from every rank, in the consumer's order (local region first, source rank second)
-static int32_t mg_consumer(rb_mgraph* mg, void* data, const uint32_t* recv_cnt, int per_rank, uint32_t cap, int chunk, SlArena* out) {
+// p2p mode: peer_data / peer_cnt are the device tables of the producers' arenas / packed counts (data and recv_cnt are not used)
+static int32_t mg_consumer(rb_mgraph* mg, void* data, const uint32_t* recv_cnt, void** peer_data, void** peer_cnt, int per_rank, uint32_t cap, int chunk,
+                           SlArena* out) {
     rb_ctx* ctx = mg->ctx;
     const int n = per_rank * mg->W;
-    RB_LAUNCH((int)div_up(n, kSlThreads), kSlThreads, 0, ctx->stream, ks_order_counts)(recv_cnt, mg->W, per_rank, cap, mg->cons_cursor, mg->cons_rlo);
+    if (mg->p2p) RB_LAUNCH((int)div_up(n, kSlThreads), kSlThreads, 0, ctx->stream, ks_order_counts_p2p)((const uint32_t* const*)peer_cnt, mg->W, mg->rank, per_rank, cap,
+                                                                                                      mg->cons_cursor, mg->cons_rlo);
+    else RB_LAUNCH((int)div_up(n, kSlThreads), kSlThreads, 0, ctx->stream, ks_order_counts)(recv_cnt, mg->W, per_rank, cap, mg->cons_cursor, mg->cons_rlo);
     LAUNCH_CHECK();
     SlArena a = sl_arena(data, mg->cons_cursor, nullptr, n, chunk);
     a.cap = cap; a.cursor_stride = 1; a.rlo = mg->cons_rlo;
+    if (mg->p2p) { a.data = nullptr; a.peer_data = peer_data; a.n_peers = mg->W; }
     *out = a;
     RB_LAUNCH(1, kSlThreads, ((size_t)((a.B + 3) & ~3) + 296) * 4, ctx->stream, ks_chunk_prefix)(a, mg->chunk_prefix);
     LAUNCH_CHECK();
@@ -373,8 +465,10 @@ static int32_t mg_pack_counts(rb_mgraph* mg, const SlArena& a, uint32_t* dense) 
     return RB_OK;
 }
 // one exchange: the counts of the regions, then the regions (equal split: every rank sends `per_rank` regions of `cap` records to every rank)
+static int32_t mg_barrier(rb_mgraph* mg);
 static int32_t mg_exchange(rb_mgraph* mg, const void* send, void* recv, int per_rank, uint32_t cap, int rec_bytes, bool with_counts) {
     if (mg->W == 1) return RB_OK;   // recv aliases send
+    if (mg->p2p) return mg_barrier(mg);   // the consumer reads the producers' arenas in place: it only has to know that they are complete
     rb_ctx* ctx = mg->ctx;
     int32_t rc;
     if (with_counts) {
@@ -397,6 +491,15 @@ static int32_t mg_agree(rb_mgraph* mg, int first, int n) {   // every rank learn
     return mg->tr.all_reduce_max(mg->tr.user, mg->flags + first, n, mg->ctx->stream);
 }
 
+// flags[2] is never set: its max-reduction is a barrier on the streams of all ranks (the collective completes on a rank only after every
+// rank has reached it in stream order)
+static int32_t mg_barrier(rb_mgraph* mg) {
+    rb_ctx* ctx = mg->ctx;
+    PROF("barrier");
+    const int32_t rc = mg->tr.all_reduce_max(mg->tr.user, mg->flags + 2, 1, ctx->stream);
+    if (ctx->prof_pending) prof_end(ctx);
+    return rc;
+}
 struct MgRouteUser { rb_mgraph* mg; int mode; bool lookup; int64_t *fh, *rh; int launches; };
 template <int NJ>
 static int32_t mg_route_lookup_t(rb_mgraph* mg, const Ingest& ing, int mode, int64_t* fh, int64_t* rh) {
@@ -465,14 +568,15 @@ static int32_t mg_route(rb_mgraph* mg, const ReadsArg& ra, int mode, bool lookup
         CK(cudaMemsetAsync(a.cursor, 0, (size_t)a.B * kSlPad * 4, ctx->stream));
         if (lookup) mg->n_items = 0;
     }
-    return mg_pack_counts(mg, a, mg->cnt_s);
+    return mg_pack_counts(mg, a, (!lookup && mg->p2p) ? mg->cnt_k : mg->cnt_s);
 }
 // owner side: probes received from every rank -> answers at the same positions of `ans`
 static int32_t mg_apply(rb_mgraph* mg, bool set_bits) {
     rb_ctx* ctx = mg->ctx;
     SlArena a;
-    int32_t rc = mg_consumer(mg, mg->recv32, mg->cnt_r, mg->R, mg->probe_cap, sl_chunk(), &a);
+    int32_t rc = mg_consumer(mg, mg->recv32, mg->cnt_r, mg->d_peer32, mg->d_peer_cnt, mg->R, mg->probe_cap, sl_chunk(), &a);
     if (rc) return rc;
+    if (mg->p2p) a.peer_ans = (uint8_t* const*)mg->d_peer_ans;
     const size_t sm_pre = (size_t)(a.B + 1) * 4;
     int grid = 0;
     if (set_bits) {
@@ -488,7 +592,7 @@ static int32_t mg_apply(rb_mgraph* mg, bool set_bits) {
 static int32_t mg_dedup_emit(rb_mgraph* mg, bool with_cbf) {
     rb_ctx* ctx = mg->ctx;
     SlArena keys;
-    int32_t rc = mg_consumer(mg, mg->recv64, mg->cnt_r, mg->KR, mg->key_cap, kSlThreads * kKeyE, &keys);
+    int32_t rc = mg_consumer(mg, mg->recv64, mg->cnt_r, mg->d_peer64, mg->d_peer_cntk, mg->KR, mg->key_cap, kSlThreads * kKeyE, &keys);
     if (rc) return rc;
     const int n_sub = 1 << mg->sub_bits;
     const int n_sub_regions = mg->KR << mg->sub_bits;
@@ -550,12 +654,11 @@ static int32_t mg_raise_pass(rb_mgraph* mg, int policy, uint64_t seed, int pass,
                    policy, seed, raises, mg->flags + 1, (const int*)mg->flags, pass, n_pass);
     rc = mg_pack_counts(mg, raises, mg->cnt_s);
     if (rc) return rc;
-    rc = mg_agree(mg, 1, 1);
+    rc = mg_agree(mg, 1, 1);   // p2p mode: also the barrier after which the raise arenas are complete everywhere
     if (rc) return rc;
-    rc = mg_exchange(mg, mg->send32, mg->recv32, mg->SR, mg->raise_cap, 4, true);
-    if (rc) return rc;
+    if (!mg->p2p) { rc = mg_exchange(mg, mg->send32, mg->recv32, mg->SR, mg->raise_cap, 4, true); if (rc) return rc; }
     SlArena a;
-    rc = mg_consumer(mg, mg->recv32, mg->cnt_r, mg->SR, mg->raise_cap, sl_chunk(), &a);
+    rc = mg_consumer(mg, mg->recv32, mg->cnt_r, mg->d_peer32, mg->d_peer_cnt, mg->SR, mg->raise_cap, sl_chunk(), &a);
     if (rc) return rc;
     const size_t sm_rp = (size_t)(a.B + 1) * 4;
     int grid = 0;
@@ -583,16 +686,17 @@ extern "C" int32_t rb_mgraph_add_round_dev(rb_mgraph* mg, const uint64_t* packed
     const int mode = !mg->stranded ? RB_MODE_CANON : ((flags & RB_REVCOMP) ? RB_MODE_RC : RB_MODE_FWD);
     const int policy = (flags & RB_DBG_ONLY) ? POLICY_DBG_ONLY : (flags & RB_ADD_COUNT_IF_PRESENT) ? POLICY_COUNT_IF_PRESENT : POLICY_ADD;
     ReadsArg ra{packed, mask, read_off, read_len, n_reads, uniform_len, uniform_stride, true};
-    int32_t rc = mg_route(mg, ra, mode, false, nullptr, nullptr, n_kmers_out);
+    int32_t rc = RB_OK;
+    if (mg->p2p) { rc = mg_barrier(mg); if (rc) return rc; }   // every rank is done reading this rank's arenas of the previous round
+    rc = mg_route(mg, ra, mode, false, nullptr, nullptr, n_kmers_out);
     if (rc) return rc;
     rc = mg_exchange(mg, mg->send64, mg->recv64, mg->KR, mg->key_cap, 8, true);
     if (rc) return rc;
     rc = mg_dedup_emit(mg, policy != POLICY_DBG_ONLY);
     if (rc) return rc;
-    rc = mg_agree(mg, 0, 1);
+    rc = mg_agree(mg, 0, 1);   // p2p mode: also the barrier after which the probe arenas are complete everywhere
     if (rc) return rc;
-    rc = mg_exchange(mg, mg->send32, mg->recv32, mg->R, mg->probe_cap, 4, true);
-    if (rc) return rc;
+    if (!mg->p2p) { rc = mg_exchange(mg, mg->send32, mg->recv32, mg->R, mg->probe_cap, 4, true); if (rc) return rc; }
     rc = mg_apply(mg, policy != POLICY_COUNT_IF_PRESENT);
     if (rc) return rc;
     ++mg->rounds;
@@ -632,12 +736,13 @@ extern "C" int32_t rb_mgraph_count_round_dev(rb_mgraph* mg, const uint64_t* pack
     rb_ctx* ctx = mg->ctx;
     LOCK(ctx);
     ReadsArg ra{packed, mask, read_off, read_len, n_reads, uniform_len, uniform_stride, true};
-    int32_t rc = mg_route(mg, ra, mg->stranded ? RB_MODE_FWD : RB_MODE_CANON, true, fhash, mg->stranded ? nullptr : rhash, n_kmers_out);
+    int32_t rc = RB_OK;
+    if (mg->p2p) { rc = mg_barrier(mg); if (rc) return rc; }
+    rc = mg_route(mg, ra, mg->stranded ? RB_MODE_FWD : RB_MODE_CANON, true, fhash, mg->stranded ? nullptr : rhash, n_kmers_out);
     if (rc) return rc;
     rc = mg_agree(mg, 0, 1);
     if (rc) return rc;
-    rc = mg_exchange(mg, mg->send32, mg->recv32, mg->R, mg->probe_cap, 4, true);
-    if (rc) return rc;
+    if (!mg->p2p) { rc = mg_exchange(mg, mg->send32, mg->recv32, mg->R, mg->probe_cap, 4, true); if (rc) return rc; }
     rc = mg_apply(mg, false);
     if (rc) return rc;
     rc = mg_exchange(mg, mg->ans, mg->home_ans, mg->R, mg->probe_cap, 1, false);

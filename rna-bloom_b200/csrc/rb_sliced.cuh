@@ -71,7 +71,17 @@ struct SlArena {
     void* spill_data;
     unsigned int* spill_cursor;
     uint32_t spill_cap;
+    // consumer of a sharded round in peer-to-peer mode: region b lives in the arena of source rank b % n_peers, which this GPU reads
+    // directly over NVLink (peer_data[src] = that rank's send arena, mapped with CUDA IPC); answers are written straight into the
+    // source's answer array peer_ans[src].  nullptr: one local arena (`data`).
+    void* const* peer_data;
+    uint8_t* const* peer_ans;
+    int n_peers;
 };
+template <typename REC>
+__device__ __forceinline__ const REC* sl_region_records(const SlArena& a, int region) {
+    return reinterpret_cast<const REC*>(a.peer_data ? a.peer_data[region % a.n_peers] : a.data);
+}
 struct SlGeom {
     FastMod dbg_fm, cbf_fm;   // global index arithmetic (reference semantics)
     int hd, hc;
@@ -578,13 +588,14 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
     int* pre = reinterpret_cast<int*>(sl_smem);
     sl_load_prefix(pre, chunk_prefix, arena.B);
     const int total = pre[arena.B];
-    const uint32_t* rec = reinterpret_cast<const uint32_t*>(arena.data);
     constexpr int U = 8;   // probes in flight per thread
     const L2Keep keep = l2_keep_policy();
     __shared__ int s_c;
     for (int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c); c < total; c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c)) {
         const SlWork w = sl_work_item(arena, pre, c);
         const int lr = w.b / sg.region_div;   // local region: dbgbf slices first, then cbf slices -- or paired slices
+        const uint32_t* rec = sl_region_records<uint32_t>(arena, w.b);                      // local, or the source rank's arena over NVLink
+        uint8_t* ans_out = arena.peer_ans ? arena.peer_ans[w.b % arena.n_peers] : ans;  // answers land where the producer will look
         if (sg.paired) {
             // record = chunk << pair_log2 | offset: counter byte (lr << pair_log2) + offset, bit chunk * pair_local_c + the same
             const uint64_t byte0 = (uint64_t)lr << sg.pair_log2;
@@ -610,7 +621,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
                         const uint64_t bi = (uint64_t)(li[u] >> sg.pair_log2) * sg.pair_local_c + ci;
                         const uint32_t bit = 1u << (bi & 31);
                         if (SET && !(wd[u] & bit)) wd[u] = atomic_or_keep(dbg_words + (bi >> 5), bit, keep);
-                        __stcs(ans + w.first + i0 + u * kSlThreads, (uint8_t)(((wd[u] & bit) ? 0x80u : 0u) | ((wc[u] >> ((ci & 3) * 8)) & 0x7Fu)));
+                        __stcs(ans_out + w.first + i0 + u * kSlThreads, (uint8_t)(((wd[u] & bit) ? 0x80u : 0u) | ((wc[u] >> ((ci & 3) * 8)) & 0x7Fu)));
                     }
                 }
             }
@@ -638,7 +649,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
                     } else {
                         value = (wd[u] >> ((li[u] & 3) * 8)) & 0x7Fu;
                     }
-                    __stcs(ans + w.first + i0 + u * kSlThreads, (uint8_t)value);
+                    __stcs(ans_out + w.first + i0 + u * kSlThreads, (uint8_t)value);
                 }
             }
         }
@@ -738,10 +749,10 @@ __global__ void __launch_bounds__(kSlThreads, 3) ks_split_keys(const SlArena in,
     int* pre = reinterpret_cast<int*>(sl_smem + TileSort<unsigned long long, kKeyE, true>::smem_bytes(n_sub));
     sl_load_prefix(pre, chunk_prefix, in.B);
     const int total = pre[in.B];
-    const unsigned long long* rec_in = reinterpret_cast<const unsigned long long*>(in.data);
     __shared__ int s_c;
     for (int c = sl_next_chunk(chunk_prefix + in.B + 1, &s_c); c < total; c = sl_next_chunk(chunk_prefix + in.B + 1, &s_c)) {
         const SlWork w = sl_work_item(in, pre, c);   // in.chunk <= 256 * kKeyE keys
+        const unsigned long long* rec_in = sl_region_records<unsigned long long>(in, w.b);
         unsigned long long rec[kKeyE];
         uint32_t slot[kKeyE];
 #pragma unroll
@@ -971,11 +982,11 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_raises(const SlArena aren
     int* pre = reinterpret_cast<int*>(sl_smem);
     sl_load_prefix(pre, chunk_prefix, arena.B);
     const int total = pre[arena.B];
-    const uint32_t* rec = reinterpret_cast<const uint32_t*>(arena.data);
     const L2Keep keep = l2_keep_policy();
     __shared__ int s_c;
     for (int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c); c < total; c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c)) {
         const SlWork w = sl_work_item(arena, pre, c);
+        const uint32_t* rec = sl_region_records<uint32_t>(arena, w.b);
         const int64_t word0 = (int64_t)(w.b / sg.region_div) << (sg.raise_log2 - 2);
         for (uint32_t i = threadIdx.x; i < w.n; i += kSlThreads) {
             const uint32_t a = __ldcs(rec + w.first + i);
@@ -1000,6 +1011,18 @@ __global__ void __launch_bounds__(kSlThreads) ks_order_counts(const uint32_t* __
         const int lr = i / n_ranks, src = i % n_ranks;
         cursor[i] = recv[src * per_rank + lr];
         rlo[i] = (uint32_t)(src * per_rank + lr) * cap;
+    }
+}
+
+// the same in peer-to-peer mode: the counts are read from the source ranks' packed count arrays, the regions stay where they are
+// (source src's arena holds the regions for this rank at (me * per_rank + local region) * cap)
+__global__ void __launch_bounds__(kSlThreads) ks_order_counts_p2p(const uint32_t* const* __restrict__ peer_cnt, int n_ranks, int me, int per_rank, uint32_t cap,
+                                                                 unsigned int* __restrict__ cursor, uint32_t* __restrict__ rlo) {
+    const int i = blockIdx.x * kSlThreads + threadIdx.x;   // consumer region
+    if (i < n_ranks * per_rank) {
+        const int lr = i / n_ranks, src = i % n_ranks;
+        cursor[i] = peer_cnt[src][me * per_rank + lr];
+        rlo[i] = (uint32_t)(me * per_rank + lr) * cap;
     }
 }
 

@@ -237,6 +237,7 @@ static SlArena sl_arena(void* data, unsigned int* cursor, const uint32_t* roff, 
     SlArena a;
     a.data = data; a.cursor = cursor; a.roff = roff; a.B = B; a.chunk = chunk; a.cap = 0; a.cursor_stride = kSlPad; a.rlo = nullptr;
     a.spill_data = nullptr; a.spill_cursor = nullptr; a.spill_cap = 0;
+    a.peer_data = nullptr; a.peer_ans = nullptr; a.n_peers = 1;
     return a;
 }
 static SlArena sl_probe_arena(SlicedEngine* e) { return sl_arena(e->probe_data, e->probe_cursor, e->probe_roff, e->probe_B, sl_chunk()); }

@@ -1322,6 +1322,18 @@ extern "C" int32_t rb_synth_reads_dev(rb_ctx* ctx, uint64_t seed, uint64_t genom
     return RB_OK;
 }
 
+extern "C" int32_t rb_synth_long_read_len(uint64_t seed, uint64_t read) { return synth_long_len(seed, read); }
+extern "C" int32_t rb_synth_long_reads_dev(rb_ctx* ctx, uint64_t seed, uint64_t genome_len, uint64_t first_read, int64_t n_reads, uint32_t sub_ppm,
+                                           uint32_t ins_ppm, uint32_t del_ppm, const int64_t* read_off_dev, uint64_t* packed_dev) {
+    if (!ctx || !packed_dev || !read_off_dev || n_reads < 0 || genome_len < 16384) return RB_EINVAL;
+    LOCK(ctx);
+    if (n_reads == 0) return RB_OK;
+    RB_LAUNCH((int)div_up(n_reads, kThreads), kThreads, 0, ctx->stream, k_synth_long_reads)(seed, genome_len, first_read, n_reads, sub_ppm, ins_ppm, del_ppm,
+                                                                                        read_off_dev, packed_dev);
+    LAUNCH_CHECK();
+    return RB_OK;
+}
+
 #include "rb_sliced_host.inl"
 #include "rb_mgraph_host.inl"
 

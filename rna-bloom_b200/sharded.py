@@ -25,10 +25,11 @@ POLICY_ADD, POLICY_COUNT_IF_PRESENT, POLICY_DBG_ONLY = 0, 1, 2
 
 _A2A = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 _ARM = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
+_AG = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 
 
 class _Transport(C.Structure):
-    _fields_ = [("user", C.c_void_p), ("all_to_all", _A2A), ("all_reduce_max", _ARM)]
+    _fields_ = [("user", C.c_void_p), ("all_to_all", _A2A), ("all_reduce_max", _ARM), ("all_gather", _AG)]
 
 
 def nccl_unique_id(lib=None):
@@ -79,7 +80,7 @@ class GlooTransport:
                 return -4
 
         self._a2a, self._arm = _A2A(a2a), _ARM(arm)   # keep the callbacks alive
-        self.struct = _Transport(None, self._a2a, self._arm)
+        self.struct = _Transport(None, self._a2a, self._arm, _AG())   # no all_gather: host memory has no peer-to-peer mode
 
 
 class ShardedGraph:
@@ -115,6 +116,10 @@ class ShardedGraph:
     @staticmethod
     def _p(t):
         return None if t is None else C.c_void_p(t.data_ptr())
+
+    @property
+    def peer_to_peer(self):
+        return bool(self.L.rb_mgraph_peer_to_peer(self.h))
 
     @property
     def exchanged_bytes(self):

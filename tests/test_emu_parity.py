@@ -57,7 +57,8 @@ ONLY = {
     "sliced-small-spill": ("test_duplicates_inside_one_batch_are_linearised", "test_skewed_batch_is_redone_by_the_direct_engine"),
     "direct": ("test_getkmers_with_invalid_nucleotides", "test_neighbor_counts_match_oracle"),
     "sliced-default": ("test_getkmers_with_invalid_nucleotides", "test_insert_policies_and_pair_filters", "test_kernels_are_race_free_under_tsan",
-                       "test_random_geometry_matches_oracle", "test_random_uniform_layout_matches_oracle", "test_paired_slices_match_oracle"),
+                       "test_random_geometry_matches_oracle", "test_random_uniform_layout_matches_oracle", "test_paired_slices_match_oracle",
+                       "test_config3_settings_match_oracle", "test_config4_long_reads_match_oracle"),
 }
 SKIP = {"sliced-small": ("test_kernels_are_race_free_under_tsan", "test_neighbor_counts_match_oracle", "test_random_geometry_matches_oracle",
                          "test_random_uniform_layout_matches_oracle"),
@@ -99,6 +100,16 @@ test_neighbor_counts_match_oracle = G.test_neighbor_counts_match_oracle
                                                                  (False, 31, 3, 2, 1 << 27, 1 << 27), (False, 25, 2, 3, 1 << 29, 1 << 26)])
 def test_paired_slices_match_oracle(ctx, orc, stranded, k, hd, hc, dbg_bits, cbf_bytes, layout):
     G.test_paired_slices_match_oracle(ctx, orc, stranded, k, hd, hc, dbg_bits, cbf_bytes, layout)
+
+
+def test_config3_settings_match_oracle(ctx, orc, monkeypatch):
+    monkeypatch.setattr(G, "N_CFG3_READS", 1200)
+    G.test_config3_settings_match_oracle(ctx, orc)
+
+
+def test_config4_long_reads_match_oracle(ctx, orc, monkeypatch):
+    monkeypatch.setattr(G, "N_CFG4_READS", 60)
+    G.test_config4_long_reads_match_oracle(ctx, orc)
 
 
 def test_skewed_batch_is_redone_by_the_direct_engine(ctx, orc, monkeypatch):

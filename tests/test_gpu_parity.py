@@ -24,7 +24,8 @@ ENGINE_TESTS = {"test_graph_add_collision_free_is_bit_exact", "test_duplicates_i
                 "test_fastq_ascii_ingest_matches_regex_segmentation", "test_getkmers_with_invalid_nucleotides",
                 "test_subbatching_and_claim_table_recycling_do_not_change_results", "test_full_size_filters_properties",
                 "test_upload_download_save_load_roundtrip", "test_uniform_layout_graph_matches_oracle", "test_skewed_batch_is_redone_by_the_direct_engine",
-                "test_paired_slices_match_oracle"}
+                "test_paired_slices_match_oracle", "test_full_size_filters_match_oracle", "test_config3_settings_match_oracle",
+                "test_config4_long_reads_match_oracle"}
 # "sliced-small": slices of 16 KiB / 32 KiB so that the small test filters span hundreds of regions (the default 64 MiB slices
 # would put every test filter into one or two regions and leave the multi-region paths to the full-size test alone)
 SMALL_SLICES = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_RAISE_LOG2": "14", "RB_SLICED_SUBRANGE_LOG2": "6",
@@ -37,7 +38,7 @@ def engine(request):
     name = request.node.originalname or request.node.name
     if request.param != "direct" and name not in ENGINE_TESTS:
         pytest.skip("engine independent")
-    if request.param == "sliced-small" and name == "test_full_size_filters_properties":
+    if request.param == "sliced-small" and name in ("test_full_size_filters_properties", "test_full_size_filters_match_oracle"):
         pytest.skip("full-size filters use the production slice geometry")
     keys = ["RB_ENGINE"] + list(SMALL_SLICES)
     old = {k: os.environ.get(k) for k in keys}
@@ -52,6 +53,10 @@ def engine(request):
             os.environ.pop(k, None)
         else:
             os.environ[k] = v
+
+
+def engine_name():
+    return os.environ.get("RB_ENGINE", "auto")
 
 
 @pytest.fixture(scope="module")
@@ -787,7 +792,143 @@ def test_full_size_filters_properties(ctx):
     g.destroy()
 
 
-# ---- sharded pipeline (rb_shard_* phase kernels) on one GPU: world = 1 makes every exchange the identity ---------------------------
+N_CFG3_READS = 1_000_000     # the emulated run of this test (tests/test_emu_parity.py) lowers it
+N_CFG4_READS = 40_000
+
+
+def test_config3_settings_match_oracle(ctx, orc):
+    """BASELINE configs[3] settings at scale: STRANDED, k=35, read paired k-mers at d = 105 (RNABloom.java:1022), left mates forward and
+    right mates through the reverse-complement iterators, >= 10^6 reads of 150 bp in the uniform layout against the sequential oracle
+    (1 GiB dbgbf + 1 GiB cbf + 256 MiB rpkbf): dbgbf and rpkbf byte-identical, cbf identical except on shared counters, counts of
+    sampled reads equal."""
+    k, d, L = 35, 105, 150
+    dbg_bits, cbf_bytes, pk_bits = 1 << 33, 1 << 30, 1 << 31
+    n = N_CFG3_READS
+    half = n // 2
+    reads = orc.synth_reads(333, max(40 * n, 100000), 0, n, L, 5000)
+    g, og = make_graphs(ctx, orc, dbg_bits, cbf_bytes, pk_bits, 3, 3, 3, k, True, True)
+    g.setPairedKmerDistances(d, -1), og.set_distances(d, -1)
+    og.run_mt(reads[:half], F_STORE_READ_PAIRS, False, 1)
+    og.run_mt(reads[half:], F_STORE_READ_PAIRS | F_REVCOMP, False, 1)
+    code = np.zeros(256, dtype=np.uint8)
+    code[[ord(c) for c in "ACGT"]] = [0, 1, 2, 3]
+    g.addReads(rb.pack_uniform(code[reads[:half]], 160), flags=rb.STORE_READ_PAIRS)
+    g.addReads(rb.pack_uniform(code[reads[half:]], 160), flags=rb.REVCOMP | rb.STORE_READ_PAIRS)
+    assert og.cbf().max() <= 16
+    assert np.array_equal(g.getDbgbf().download(), og.dbgbf()), "dbgbf differs"
+    assert np.array_equal(g.getRpkbf().download(), og.rpkbf()), "rpkbf differs"
+    diff = np.nonzero(g.getCbf().download() != og.cbf())[0]
+    if len(diff):
+        sub = [bytes(r) for r in reads]
+        allowed, frac = counters_that_may_differ(all_bases(orc, sub, k, [MODE_FWD, MODE_RC]), k, 3, cbf_bytes)
+        assert frac < 0.2 and set(diff.tolist()) <= allowed, "cbf differs on counters no other k-mer shares"
+    q = reads[:half:50]
+    counts, fh, _ = g.getKmers(rb.pack_uniform(code[q], 160))
+    want = [og.count_seq(bytes(r)) for r in q]
+    assert (fh == np.concatenate([w[1] for w in want])).all()
+    assert (counts == np.concatenate([w[0] for w in want])).mean() > (0.999 if len(diff) else 0.999999)
+    g.destroy(), og.close()
+
+
+def test_config4_long_reads_match_oracle(ctx, orc):
+    """BASELINE configs[4] settings: ONT-like ragged reads (500..3.5 kb; substitutions, insertions, deletions), k=17, canonical.  The device
+    generator must produce the oracle twin's bases exactly (checked through the hashes of every k-mer), and graph.add / getKmers of the
+    ragged layout must match the sequential oracle."""
+    import ctypes as C
+    from bench_configs import long_read_lengths
+    k, n = 17, N_CFG4_READS
+    seed, genome, rates = 4242, 30 * n * 2000 // 10, (20000, 15000, 15000)
+    bases, off = orc.synth_long_reads(seed, genome, 0, n, *rates)
+    lens = np.diff(off)
+    assert (lens == long_read_lengths(seed, 0, n)).all() and 500 <= lens.min() and lens.max() <= 3497
+    words = (lens + 31) // 32
+    roff = np.zeros(n, dtype=np.int64)
+    roff[1:] = np.cumsum(words[:-1]) * 32
+    d_off, d_len, d_packed = ctx.dev_alloc(n * 8 + 64), ctx.dev_alloc(n * 4 + 64), ctx.dev_alloc(int(words.sum()) * 8 + 64)
+    ctx.h2d(d_off, roff), ctx.h2d(d_len, lens.astype(np.int32))
+    ctx.check(ctx.L.rb_synth_long_reads_dev(ctx.h, seed, genome, 0, n, *rates, C.c_void_p(d_off), C.c_void_p(d_packed)))
+    dbg_bits, cbf_bytes = 1 << 34, 1 << 31
+    g, og = make_graphs(ctx, orc, dbg_bits, cbf_bytes, 64, 3, 3, 1, k, False, False)
+    og.run_mt_ragged(bases, off, 0, False, 1)
+    nk = int(np.maximum(lens - k + 1, 0).sum())
+    reads = (C.c_void_p(d_packed), None, C.c_void_p(d_off), C.c_void_p(d_len), n, 0, 0)
+    got = C.c_int64()
+    ctx.check(ctx.L.rb_graph_add_reads_dev(g.h, *reads, 0, C.byref(got)))
+    assert got.value == nk
+    assert np.array_equal(g.getDbgbf().download(), og.dbgbf()), "dbgbf differs (generator or ragged k-merizer)"
+    cbf = g.getCbf().download()
+    if og.cbf().max() <= 15:
+        assert (cbf != og.cbf()).mean() < 1e-4
+    d_counts, d_fh = ctx.dev_alloc(nk * 4 + 64), ctx.dev_alloc(nk * 8 + 64)
+    ctx.check(ctx.L.rb_graph_count_reads_dev(g.h, *reads, C.c_void_p(d_counts), C.c_void_p(d_fh), None, C.byref(got)))
+    ctx.sync()
+    fh = np.zeros(nk, dtype=np.int64)
+    counts = np.zeros(nk, dtype=np.float32)
+    ctx.d2h(fh, d_fh), ctx.d2h(counts, d_counts)
+    m = min(n, 400)
+    want = [og.count_seq(bytes(bases[off[i]:off[i + 1]])) for i in range(m)]
+    n_m = int(np.maximum(lens[:m] - k + 1, 0).sum())
+    assert (fh[:n_m] == np.concatenate([w[1] for w in want])).all(), "device long-read generator differs from the oracle twin"
+    assert (counts[:n_m] == np.concatenate([w[0] for w in want])).mean() > 0.999
+    for p in (d_off, d_len, d_packed, d_counts, d_fh):
+        ctx.dev_free(p)
+    g.destroy(), og.close()
+
+
+def _host_ram_gib():
+    try:
+        return int(next(line.split()[1] for line in open("/proc/meminfo") if line.startswith("MemAvailable"))) / (1 << 20)
+    except Exception:
+        return 0.0
+
+
+@pytest.mark.skipif(os.environ.get("RB_SKIP_FULLSIZE") == "1", reason="full-size filters skipped")
+def test_full_size_filters_match_oracle(ctx, orc):
+    """The production geometry against the ORACLE, not against itself: configs[1] filter sizes (2^36-bit dbgbf, 2^33-byte cbf; paired
+    probe records, 256 slices of 32 MiB + 8 x 4 MiB), 400 k synthetic 150 bp reads inserted by the sliced engine in two calls (the
+    second repeats a quarter of the reads: multiplicities inside and across rounds), the same reads through the sequential oracle with
+    16 GiB of host filters.  dbgbf: every one of the 8 Gi bytes equal.  cbf: equal except on counters that two distinct k-mers share
+    (computed from the fixture; a handful at this load).  Counts and hashes of 50 k sampled reads: equal."""
+    if _host_ram_gib() < 48:
+        pytest.skip("needs ~40 GiB of host memory for the oracle's filters and the downloads")
+    if engine_name() == "direct":
+        pytest.skip("the production geometry belongs to the sliced engine")
+    k, dbg_bits, cbf_bytes = 25, 1 << 36, 1 << 33
+    n_reads = 400_000
+    reads = orc.synth_reads(20261017, 20_000_000, 0, n_reads, 150, 3000)        # 3x coverage of a 20 Mb genome
+    again = reads[: n_reads // 4]
+    g, og = make_graphs(ctx, orc, dbg_bits, cbf_bytes, 64, 3, 3, 1, k, False, False)
+    og.run_mt(reads, 0, False, 1)                                                # one thread = the sequential reference order
+    og.run_mt(again, 0, False, 1)
+    code = np.zeros(256, dtype=np.uint8)
+    code[[ord(c) for c in "ACGT"]] = [0, 1, 2, 3]
+    g.addReads(rb.pack_uniform(code[reads], 160))
+    g.addReads(rb.pack_uniform(code[again], 160))
+    assert og.cbf().max() <= 16, "fixture reached the probabilistic MiniFloat range"
+    got = g.getDbgbf().download()
+    want = og.dbgbf()
+    for lo in range(0, len(want), 1 << 30):                                      # 1 GiB at a time: no 8 GiB temporaries
+        assert np.array_equal(got[lo:lo + (1 << 30)], want[lo:lo + (1 << 30)]), "dbgbf differs in GiB %d" % (lo >> 30)
+    del got
+    got = g.getCbf().download()
+    want = og.cbf()
+    diff = np.concatenate([lo + np.nonzero(got[lo:lo + (1 << 30)] != want[lo:lo + (1 << 30)])[0] for lo in range(0, len(want), 1 << 30)])
+    if len(diff):
+        seqs = [bytes(r) for r in reads]
+        bases = all_bases(orc, seqs, k, [MODE_CANON])
+        allowed, frac = counters_that_may_differ(bases, k, 3, cbf_bytes)
+        assert frac < 0.05 and set(diff.tolist()) <= allowed, "cbf differs on %d counters that no other k-mer shares" % len(diff)
+    del got
+    q = reads[::8]
+    counts, fh, rh = g.getKmers(rb.pack_uniform(code[q], 160))
+    want = [og.count_seq(bytes(r)) for r in q]
+    assert (fh == np.concatenate([w[1] for w in want])).all() and (rh == np.concatenate([w[2] for w in want])).all()
+    wc = np.concatenate([w[0] for w in want])
+    assert (counts == wc).mean() > (0.9999 if len(diff) else 0.999999)
+    g.destroy(), og.close()
+
+
+# ---- sharded graph (rb_mgraph_*) on one GPU: world = 1 makes every exchange the identity -------------------------------------------------
 class DevReads:
     """Packed reads uploaded to the GPU, as the raw-pointer tuple the rb_shard_* calls take."""
 
