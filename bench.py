@@ -278,6 +278,35 @@ def main():
         e2e = {"value": nk * e_steps / te, "unit": "k-mers/s", "h2d_bytes_per_step": 2 * words * 8, "d2h_bytes_per_step": nk * 4,
                "steps": e_steps, "ms_per_step": 1e3 * te / e_steps}
 
+        # the same through the ASCII entry points -- what the Java insert workers and graph.getKmers(String) call (RNABloom.java:551-634,
+        # graph :1224-1234): ASCII bases in host memory in, segmentation + 2-bit packing on the GPU, counts back to host memory
+        n_a = min(n_reads, 1_000_000)
+        w_a = n_a * STRIDE // 32
+        pk = np.zeros(w_a, dtype=np.uint64)
+        tmp = ctx.dev_alloc(w_a * 8 + 64)
+        ctx.synth_reads_dev(SEED, args.genome, (total_steps + e_steps + 2) * n_reads, n_a, READ_LEN, ERR_PPM, STRIDE, tmp)
+        ctx.sync()
+        ctx.d2h(pk, tmp)
+        ctx.dev_free(tmp)
+        codes = ((pk[:, None] >> (2 * np.arange(32, dtype=np.uint64))[None, :]) & np.uint64(3)).astype(np.uint8).reshape(n_a, STRIDE)[:, :READ_LEN]
+        ascii_bases = np.ascontiguousarray(np.frombuffer(b"ACGT", dtype=np.uint8)[codes]).reshape(-1)
+        ascii_off = np.arange(n_a + 1, dtype=np.int64) * READ_LEN
+        a_counts = ctx.host_alloc(n_a * KMERS_PER_READ * 4, np.float32)
+        na = C.c_int64()
+
+        def ascii_step():
+            ctx.check(ctx.L.rb_graph_add_reads_ascii(g.h, _ptr(ascii_bases), None, _ptr(ascii_off), n_a, 0, 0, C.byref(na)))
+            ctx.check(ctx.L.rb_graph_count_reads_ascii(g.h, _ptr(ascii_bases), _ptr(ascii_off), n_a, _ptr(a_counts), None, None, C.byref(na)))
+        ascii_step()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            ascii_step()
+        ta = time.perf_counter() - t0
+        assert na.value == n_a * KMERS_PER_READ and float(a_counts[:1024].min()) >= 1.0
+        e2e["ascii"] = {"value": n_a * KMERS_PER_READ * 2 / ta, "unit": "k-mers/s", "reads_per_call": n_a, "h2d_bytes_per_step": 2 * (n_a * READ_LEN + 8 * (n_a + 1)),
+                        "d2h_bytes_per_step": n_a * KMERS_PER_READ * 4,
+                        "note": "rb_graph_add_reads_ascii + rb_graph_count_reads_ascii: ASCII records in pageable host memory, packed on the GPU"}
+
     # ---- roofline (live CUDA-event times of the timed region; algorithmic bytes = SURVEY 8d sector model, 192.15 B per k-mer and phase)
     kmers_total = nk * args.steps
     ins_dominant = t_ins >= t_look

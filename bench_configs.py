@@ -125,6 +125,9 @@ def run_config3(args):
         threads = os.cpu_count() or 1
         og = OracleGraph(orc, DBG, CBF, PK, H, H, H, K, True, True)
         og.set_distances(D, -1)
+        for f in (orc.lib.orc_graph_dbgbf(og.g), orc.lib.orc_graph_rpkbf(og.g)):   # touch every page before timing
+            orc.lib.orc_bf_empty(f)
+        orc.lib.orc_cbf_empty(orc.lib.orc_graph_cbf(og.g))
         sample = 200_000
         reads = orc.synth_reads(SEED + 3, B1.GENOME, 0, sample, L, B1.ERR_PPM)
         t0 = time.perf_counter()
@@ -221,6 +224,8 @@ def run_config4(args):
         orc = Oracle()
         threads = os.cpu_count() or 1
         og = OracleGraph(orc, DBG, CBF, 64, H, H, 1, K, False, False)
+        orc.lib.orc_bf_empty(orc.lib.orc_graph_dbgbf(og.g))   # touch every page before timing
+        orc.lib.orc_cbf_empty(orc.lib.orc_graph_cbf(og.g))
         bases, off = orc.synth_long_reads(SEED + 4, GENOME, 0, 15000, SUB, INS, DEL)
         t0 = time.perf_counter()
         km, _ = og.run_mt_ragged(bases, off, 0, False, threads)

@@ -70,7 +70,8 @@ def sharded_parity_check(make_graph, rank, world, device, full_dbg_bits=None, fu
     # ---- A ---------------------------------------------------------------------------------------------------------------------
     dbg_bits, cbf_bytes, per_rank, per_round = small
     q0, q1 = per_rank // 20, per_rank // 20 + per_rank // 10           # the queried / re-inserted reads
-    reads = [bytes(r).decode() for r in orc.synth_reads(71, 75 * per_rank * world, 0, per_rank * world, 150, 6000)]
+    # ~1.3x coverage: counters stay in the exact MiniFloat range at any world size
+    reads = [bytes(r).decode() for r in orc.synth_reads(71, 120 * per_rank * world, 0, per_rank * world, 150, 6000)]
     reads[3] = reads[3][:70] + "N" + reads[3][71:]
     mine = reads[rank::world]
     sg = make_graph(dbg_bits, cbf_bytes, per_round * 126)

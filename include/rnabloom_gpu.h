@@ -137,12 +137,25 @@ RB_API int32_t rb_filter_load(rb_ctx* ctx, int32_t kind, const char* desc_path, 
 
 /* getIndex(hashVal, size) = (hashVal >>> 1) % size for an arbitrary positive 63-bit size (bloom/BloomFilter.java:108-111,
  * CountingBloomFilter.java:101-104): the device index arithmetic exposed for parity checks. */
+/* ---- CascadingBloomFilter (bloom/CascadingBloomFilter.java:34-100): num_levels Bloom filters of size / num_levels bits each ------------
+ * add (:66-72): lookupThenAdd level by level until a level did not have the key yet; lookup (:79-85): the top level;
+ * lookupThenAdd (:93-100): 1 iff every level already had the key.  rb_cascade_level lends a level as a filter (popcount, FPR, download). */
+typedef struct rb_cascade rb_cascade;
+RB_API int32_t rb_cascade_create(rb_ctx* ctx, int64_t size, int32_t num_hash, int32_t k, int32_t num_levels, rb_cascade** out);
+RB_API int32_t rb_cascade_destroy(rb_cascade* c);
+RB_API int32_t rb_cascade_level(rb_cascade* c, int32_t level, rb_filter** out);
+RB_API int32_t rb_cascade_add_hashes(rb_cascade* c, const int64_t* base, int64_t n);
+RB_API int32_t rb_cascade_lookup_hashes(rb_cascade* c, const int64_t* base, int64_t n, uint8_t* out);
+RB_API int32_t rb_cascade_lookup_then_add_hashes(rb_cascade* c, const int64_t* base, int64_t n, uint8_t* out);
+
 RB_API int32_t rb_index_hashes(rb_ctx* ctx, const int64_t* hash, int64_t n, int64_t size, int64_t* index_out);
 
 /* ---- k-merizer alone (hash parity, and the "hash only" operator) --------------------------------------------
  * NTHashIterator / CanonicalNTHashIterator / ReverseComplementNTHashIterator (bloom/hash/ *NTHashIterator.java): for every k-mer
  * position of every read writes fhash, rhash, base (= hVals[0]) at rb_kmer_offsets()[read] + pos.  Outputs may be NULL.
- * Masked bases hash as seed 0 (like 'N', NTHash.java:135-168). */
+ * Masked bases hash as seed 0 on both strands (like 'N', NTHash.java:135-168); that is exact for N and for every k-mer that is inserted or
+ * counted (> 0), but not for the reverse-strand hash of windows over other non-ACGTU characters: rb_kmerize_ascii /
+ * rb_graph_count_reads_ascii carry the c & 0x07 row of NTHash.java:367-373 as well. */
 RB_API int32_t rb_kmerize(rb_ctx* ctx, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off,
                           const int32_t* read_len, int64_t n_reads, int32_t uniform_len, int64_t uniform_stride,
                           int32_t k, int32_t mode, int64_t* fhash, int64_t* rhash, int64_t* base);
@@ -186,6 +199,23 @@ RB_API int32_t rb_graph_add_reads_dev(rb_graph* g, const uint64_t* packed, const
  * Segmentation and 2-bit packing run on the GPU. */
 RB_API int32_t rb_graph_add_reads_ascii(rb_graph* g, const char* bases, const char* quals, const int64_t* ascii_off,
                                         int64_t n_reads, int32_t min_qual, uint32_t flags, int64_t* n_kmers_out);
+/* ---- the reference's packed fragment records ("2bit": io/NucleotideBitsWriter.java:24-31, io/NucleotideBitsReader.java:39-49,
+ * util/SeqBitsUtils.java:138-262): 4-byte big-endian length + ceil(len/4) bytes, each (b0*64 + b1*16 + b2*4 + b3) - 128 with the first base
+ * in the top bits.  rb_graph_add_reads_2bit takes a buffer of such records in host memory (what FragmentsToGraphWorker reads for the stage-3
+ * graph rebuild, RNABloom.java:1489-1516) and re-packs them on the GPU; the host helpers are the codec itself. */
+RB_API int64_t rb_2bit_record_bytes(int32_t seq_len);
+RB_API int64_t rb_2bit_encode_records(const char* bases, const int64_t* ascii_off, int64_t n_reads, uint8_t* out /* NULL: size only */);
+RB_API int64_t rb_2bit_index_records(const uint8_t* records, int64_t n_bytes, int64_t* data_off, int32_t* read_len, int64_t max_reads);
+RB_API int32_t rb_graph_add_reads_2bit(rb_graph* g, const uint8_t* records, int64_t n_bytes, uint32_t flags, int64_t* n_reads_out, int64_t* n_kmers_out);
+/* graph.getKmers(String) over a chunk of sequences (graph :1224-1234, bloom/hash/HashFunction.java:55-85, CanonicalHashFunction.java:46-78):
+ * count (0 for windows over a non-ACGTU character), forward and reverse hash of every window, results in host memory.  Unlike the
+ * packed entry points (whose unusable bases hash as 0 on both strands, like 'N'), the ASCII entry points reproduce NTHash for every
+ * byte value: the reverse strand reads msTab row c & 0x07 (NTHash.java:100-101,367-373), so IUPAC codes such as Y K M S W D and '-'
+ * contribute a seed there. */
+RB_API int32_t rb_graph_count_reads_ascii(rb_graph* g, const char* bases, const int64_t* ascii_off, int64_t n_reads, float* counts, int64_t* fhash,
+                                          int64_t* rhash, int64_t* n_kmers_out);
+RB_API int32_t rb_kmerize_ascii(rb_ctx* ctx, const char* bases, const int64_t* ascii_off, int64_t n_reads, int32_t k, int32_t mode, int64_t* fhash,
+                                int64_t* rhash, int64_t* base);
 
 /* Bulk lookup = graph.getKmers(seq) (graph :1224-1226 -> HashFunction.java:55-85 / CanonicalHashFunction.java:46-78):
  * per k-mer position count = dbgbf.lookup ? cbf.getCount + 1 : 0 (graph :562-570), 0 when the k-mer covers a masked base;
@@ -229,6 +259,20 @@ RB_API int32_t rb_synth_reads_dev(rb_ctx* ctx, uint64_t seed, uint64_t genome_le
  * are nullable; rhash and nbr_rhash are ignored for a stranded graph). */
 RB_API int32_t rb_graph_neighbor_counts(rb_graph* g, const int64_t* fhash, const int64_t* rhash, const uint8_t* first_base,
                                         const uint8_t* last_base, int64_t n, float* counts, int64_t* nbr_fhash, int64_t* nbr_rhash);
+/* Kmer.getLeftVariants / getRightVariants (graph/Kmer.java:357-405, CanonicalKmer.java:381-519; bloom/hash/LeftVariantsNTHashIterator.java:40-46,
+ * RightVariantsNTHashIterator.java:38-44, Canonical*VariantsNTHashIterator.java:42-52) for a batch: counts / hashes [n][2][4] = the k-mers that
+ * carry base A, C, G, T in the FIRST position, then in the LAST position (the entry of the k-mer's own base is the k-mer itself). */
+RB_API int32_t rb_graph_variant_counts(rb_graph* g, const int64_t* fhash, const int64_t* rhash, const uint8_t* first_base, const uint8_t* last_base,
+                                       int64_t n, float* counts, int64_t* var_fhash, int64_t* var_rhash);
+/* Kmer.getMaxCovSuccessor / getMaxCovPredecessor (graph/Kmer.java:301-355): best[n][2] = base code of the successor / predecessor with the
+ * largest count >= min_cov (first of equal ones in A,C,G,T order), -1 if none; optional count and hashes of it. */
+RB_API int32_t rb_graph_max_cov_neighbors(rb_graph* g, const int64_t* fhash, const int64_t* rhash, const uint8_t* first_base, const uint8_t* last_base,
+                                          int64_t n, float min_cov, int8_t* best, float* best_count, int64_t* best_fhash, int64_t* best_rhash);
+/* GraphUtils.greedyExtendRight / greedyExtendLeft with lookahead <= 1 (util/GraphUtils.java:501-527,1961-1976) for a batch of start k-mers, one
+ * GPU thread per walk: kmer_bits = 2 x uint64 per k-mer (2-bit codes, base i at bits 2 * (i & 31) of word i >> 5; k <= 64); up to `bound`
+ * k-mers are added, each the max-count neighbour >= min_cov; ext_codes[n][bound] = the added bases in walking order, ext_len[n] their number. */
+RB_API int32_t rb_graph_greedy_extend(rb_graph* g, const uint64_t* kmer_bits, const int64_t* fhash, const int64_t* rhash, int64_t n, int32_t right,
+                                      int32_t bound, float min_cov, int32_t* ext_len, uint8_t* ext_codes, float* ext_counts);
 
 /* ---- hash-sharded graph (one process per GPU) ------------------------------------------------
  * The filters of BloomFilterDeBruijnGraph (graph/BloomFilterDeBruijnGraph.java:75-104) are split by index range over n_ranks GPUs; the

@@ -32,6 +32,9 @@ public final class Native {
                                                   ByteBuffer readLen, long numReads, int flags);
     public static native long graphCountReads(long ctx, long graph, ByteBuffer packed, ByteBuffer mask, ByteBuffer readOff,
                                               ByteBuffer readLen, long numReads, ByteBuffer counts, ByteBuffer fHash, ByteBuffer rHash);
+    /** graph.getKmers(String) for a chunk of sequences: counts + forward / reverse hashes of every window, exact for every character. */
+    public static native long graphCountReadsAscii(long ctx, long graph, ByteBuffer bases, ByteBuffer offsets, long numReads, ByteBuffer counts,
+                                                   ByteBuffer fHash, ByteBuffer rHash);
     public static native void graphAddHashes(long ctx, long graph, ByteBuffer hashes, long n, int flags);
     public static native void graphCountHashes(long ctx, long graph, ByteBuffer hashes, long n, ByteBuffer counts);
     /** Batched Kmer.getSuccessors/getPredecessors: counts[n][2][4] (successors A,C,G,T then predecessors), optional neighbour hashes. */

@@ -86,6 +86,15 @@ JNIEXPORT jlong JNICALL Java_rnabloom_gpu_Native_graphCountReads(JNIEnv* env, jc
                                                             (float*)addr(env, counts), (int64_t*)addr(env, fHash), (int64_t*)addr(env, rHash), &n));
     return n;
 }
+/* graph.getKmers(String) over a chunk of sequences: counts + hashes, bit-exact for every byte value (graph :1224-1234) */
+JNIEXPORT jlong JNICALL Java_rnabloom_gpu_Native_graphCountReadsAscii(JNIEnv* env, jclass cls, jlong ctx, jlong g, jobject bases, jobject offsets, jlong nReads,
+                                                                     jobject counts, jobject fHash, jobject rHash) {
+    int64_t n = 0;
+    (void)cls;
+    check(env, (rb_ctx*)(intptr_t)ctx, rb_graph_count_reads_ascii((rb_graph*)(intptr_t)g, (const char*)addr(env, bases), (const int64_t*)addr(env, offsets), nReads,
+                                                                  (float*)addr(env, counts), (int64_t*)addr(env, fHash), (int64_t*)addr(env, rHash), &n));
+    return n;
+}
 /* graph.add(long[]) / addCountIfPresent / addDbgOnly for an array of hVals[0] (graph :405-436) */
 JNIEXPORT void JNICALL Java_rnabloom_gpu_Native_graphAddHashes(JNIEnv* env, jclass cls, jlong ctx, jlong g, jobject hashes, jlong n, jint flags) {
     (void)cls;

@@ -93,6 +93,8 @@ def load():
         "orc_graph_contains": (i32, [vp, vp]),
         "orc_graph_get_count": (f32, [vp, vp]),
         "orc_graph_neighbors": (None, [vp, i64, i64, i32, i32, vp, vp, vp]),
+        "orc_graph_variants": (None, [vp, vp, i32, vp, vp, vp]),
+        "orc_graph_greedy_extend": (i32, [vp, vp, i32, i32, f32, vp]),
         "orc_segment": (i32, [vp, vp, i32, i32, i32, vp, vp]),
         "orc_graph_add_segment": (i64, [vp, vp, i32, i32, i32]),
         "orc_graph_add_read": (i64, [vp, vp, vp, i32, i32, i32]),
@@ -101,6 +103,8 @@ def load():
         "orc_synth_reads": (None, [u64, u64, u64, u64, i32, C.c_uint32, vp]),
         "orc_graph_run_mt": (i64, [vp, vp, i64, i32, i32, i32, i32, vp]),
         "orc_graph_run_mt_ragged": (i64, [vp, vp, vp, i64, i32, i32, i32, i32, vp]),
+        "orc_2bit_record": (i64, [vp, i32, vp]),
+        "orc_2bit_decode": (None, [vp, i32, vp]),
         "orc_synth_long_len": (i32, [u64, u64]),
         "orc_synth_long_read": (i32, [u64, u64, u64, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
         "orc_synth_long_reads": (i64, [u64, u64, u64, u64, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]),
@@ -243,6 +247,22 @@ class OracleGraph:
         r = np.zeros(4, dtype=np.int64)
         self.lib.orc_graph_neighbors(self.g, int(fh), int(rh), int(char_out), int(successors), c.ctypes.data, f.ctypes.data, r.ctypes.data)
         return c, f, r
+
+    def variants(self, kmer, side):
+        """counts, forward and reverse hashes of the 4 k-mers with A, C, G, T in the first (side 0) / last (side 1) position."""
+        b = _buf(kmer)
+        c = np.zeros(4, dtype=np.float32)
+        f = np.zeros(4, dtype=np.int64)
+        r = np.zeros(4, dtype=np.int64)
+        self.lib.orc_graph_variants(self.g, b.ctypes.data, int(side), c.ctypes.data, f.ctypes.data, r.ctypes.data)
+        return c, f, r
+
+    def greedy_extend(self, kmer, right=True, bound=100, min_cov=1.0):
+        b = _buf(kmer)
+        out = np.zeros(bound, dtype=np.uint8)
+        n = self.lib.orc_graph_greedy_extend(self.g, b.ctypes.data, int(right), bound, min_cov, out.ctypes.data)
+        s = bytes(out[:n]).decode()
+        return s if right else s[::-1]
 
     def dbgbf(self):
         return self.o.bf_array(self.lib.orc_graph_dbgbf(self.g))

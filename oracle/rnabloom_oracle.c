@@ -457,6 +457,53 @@ ORC_API void orc_graph_neighbors(const orc_graph* g, int64_t fh, int64_t rh, int
     }
 }
 
+/* Kmer.getLeftVariants / getRightVariants (graph/Kmer.java:357-405): counts of the k-mers that differ in the first (side 0) / last (side 1)
+ * base, computed here from the SEQUENCE (NTP64 / NTP64RC of the edited k-mer), not incrementally: an independent check of the variant
+ * iterators' algebra.  counts4[c] = graph.getCount of the k-mer with base "ACGT"[c] there (own base: the k-mer itself). */
+ORC_API void orc_graph_variants(const orc_graph* g, const uint8_t* kmer, int side, float* counts4, int64_t* f4, int64_t* r4) {
+    static const uint8_t nt[4] = {'A', 'C', 'G', 'T'};
+    init_tables();
+    const int k = g->k;
+    uint8_t* tmp = (uint8_t*)malloc((size_t)k);
+    memcpy(tmp, kmer, (size_t)k);
+    for (int c = 0; c < 4; ++c) {
+        tmp[side ? k - 1 : 0] = nt[c];
+        const int64_t f = orc_ntp64(tmp, k, 0), r = orc_ntp64rc(tmp, k, 0);
+        const int64_t b = g->stranded ? f : (r < f ? r : f);
+        int64_t hv[ORC_MAX_HASH];
+        orc_ntm64(b, hv, k, g->hmax);
+        counts4[c] = orc_graph_get_count(g, hv);
+        if (f4) f4[c] = f;
+        if (r4) r4[c] = g->stranded ? 0 : r;
+    }
+    free(tmp);
+}
+/* GraphUtils.greedyExtendRight / greedyExtendLeft (util/GraphUtils.java:1961-1976, :1925-1958) with lookahead <= 1, where
+ * greedyExtendRightOnce (:501-527) reduces to: no candidate -> stop; otherwise the candidate (getSuccessors: count > 0, A C G T order,
+ * graph/Kmer.java:213-231) with the largest count, the first one winning ties.  kmer: k ASCII bases; out: up to `bound` added bases in
+ * walking order.  Returns the number of k-mers added. */
+ORC_API int orc_graph_greedy_extend(const orc_graph* g, const uint8_t* kmer, int right, int bound, float min_cov, uint8_t* out) {
+    static const uint8_t nt[4] = {'A', 'C', 'G', 'T'};
+    init_tables();
+    const int k = g->k;
+    uint8_t* cur = (uint8_t*)malloc((size_t)k);
+    memcpy(cur, kmer, (size_t)k);
+    int n = 0;
+    for (; n < bound; ++n) {
+        const int64_t fh = orc_ntp64(cur, k, 0), rh = orc_ntp64rc(cur, k, 0);
+        float c4[4];
+        orc_graph_neighbors(g, fh, rh, right ? cur[0] : cur[k - 1], right, c4, NULL, NULL);
+        float best = -1.f; int bi = -1;
+        for (int c = 0; c < 4; ++c) if (c4[c] >= min_cov && c4[c] > best) { best = c4[c]; bi = c; }
+        if (bi < 0) break;
+        out[n] = nt[bi];
+        if (right) { memmove(cur, cur + 1, (size_t)(k - 1)); cur[k - 1] = nt[bi]; }
+        else { memmove(cur + 1, cur, (size_t)(k - 1)); cur[0] = nt[bi]; }
+    }
+    free(cur);
+    return n;
+}
+
 /* ------------------------------------------------------------------------------------------
  * a20 segmentation              RNABloom.java:567-595 (FASTQ), :677-716 (FASTA); util/SeqUtils.java:1430-1438
  *   qualPattern = [chars >= '!'+minQual .. '~']{k,}   seqPattern = [ACGTUacgtu]{k,}
@@ -599,6 +646,37 @@ ORC_API void orc_synth_read(uint64_t seed, uint64_t genome_len, uint64_t r, int 
 }
 ORC_API void orc_synth_reads(uint64_t seed, uint64_t genome_len, uint64_t first, uint64_t n, int L, uint32_t err_ppm, uint8_t* out) {
     for (uint64_t r = 0; r < n; ++r) orc_synth_read(seed, genome_len, first + r, L, err_ppm, out + r * (uint64_t)L);
+}
+
+/* util/SeqBitsUtils.java:138-247 + io/NucleotideBitsWriter.java:24-31: one record = intToFourBytes(len) (big endian, :209) + seqToBits(seq):
+ * getByte(i,j,k,l) = i*64 + j*16 + k*4 + l - 128 (:158-160), missing bases of the last tetramer = 0 (:236-243).  ACGTU only (anything else is
+ * a random base in the reference).  Returns the record's size; out may be NULL. */
+ORC_API int64_t orc_2bit_record(const uint8_t* seq, int len, uint8_t* out) {
+    int64_t at = 0;
+    if (out) { out[0] = (uint8_t)(len >> 24); out[1] = (uint8_t)(len >> 16); out[2] = (uint8_t)(len >> 8); out[3] = (uint8_t)len; }
+    at = 4;
+    for (int i = 0; i < len; i += 4) {
+        int idx[4] = {0, 0, 0, 0};
+        for (int j = 0; j < 4 && i + j < len; ++j) {
+            switch (seq[i + j]) {
+                case 'A': case 'a': idx[j] = 0; break;
+                case 'C': case 'c': idx[j] = 1; break;
+                case 'G': case 'g': idx[j] = 2; break;
+                default: idx[j] = 3;   /* T t U u */
+            }
+        }
+        if (out) out[at] = (uint8_t)(int8_t)(idx[0] * 64 + idx[1] * 16 + idx[2] * 4 + idx[3] - 128);
+        ++at;
+    }
+    return at;
+}
+/* bitsToSeq (:249-262): tetramer lookup by byte + 128 */
+ORC_API void orc_2bit_decode(const uint8_t* bytes, int len, uint8_t* seq) {
+    static const char NT[4] = {'A', 'C', 'G', 'T'};
+    for (int i = 0; i < len; ++i) {
+        int v = (int)(int8_t)bytes[i / 4] + 128;
+        seq[i] = (uint8_t)NT[(v >> (2 * (3 - (i & 3)))) & 3];
+    }
 }
 
 /* long reads (BASELINE configs[4]): the twin of k_synth_long_reads (rna-bloom_b200/csrc/rb_kernels.cuh), integer arithmetic only */

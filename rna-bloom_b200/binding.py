@@ -111,6 +111,12 @@ def bind(path, allow_missing=False):
         "rb_filter_upload": (i32, [vp, vp, i64]),
         "rb_filter_save": (i32, [vp, cp, cp]),
         "rb_filter_load": (i32, [vp, i32, cp, cp, i32, i32, C.POINTER(vp)]),
+        "rb_cascade_create": (i32, [vp, i64, i32, i32, i32, C.POINTER(vp)]),
+        "rb_cascade_destroy": (i32, [vp]),
+        "rb_cascade_level": (i32, [vp, i32, C.POINTER(vp)]),
+        "rb_cascade_add_hashes": (i32, [vp, vp, i64]),
+        "rb_cascade_lookup_hashes": (i32, [vp, vp, i64, vp]),
+        "rb_cascade_lookup_then_add_hashes": (i32, [vp, vp, i64, vp]),
         "rb_index_hashes": (i32, [vp, vp, i64, i64, vp]),
         "rb_kmerize": (i32, [vp] + reads + [i32, i32, vp, vp, vp]),
         "rb_kmerize_pairs": (i32, [vp] + reads + [i32, i32, i32, vp]),
@@ -135,12 +141,21 @@ def bind(path, allow_missing=False):
         "rb_graph_add_reads_dev": (i32, [vp] + reads + [u32, C.POINTER(i64)]),
         "rb_graph_add_reads_ascii": (i32, [vp, vp, vp, vp, i64, i32, u32, C.POINTER(i64)]),
         "rb_graph_count_reads": (i32, [vp] + reads + [vp, vp, vp, C.POINTER(i64)]),
+        "rb_2bit_record_bytes": (i64, [i32]),
+        "rb_2bit_encode_records": (i64, [vp, vp, i64, vp]),
+        "rb_2bit_index_records": (i64, [vp, i64, vp, vp, i64]),
+        "rb_graph_add_reads_2bit": (i32, [vp, vp, i64, u32, C.POINTER(i64), C.POINTER(i64)]),
+        "rb_graph_count_reads_ascii": (i32, [vp, vp, vp, i64, vp, vp, vp, C.POINTER(i64)]),
+        "rb_kmerize_ascii": (i32, [vp, vp, vp, i64, i32, i32, vp, vp, vp]),
         "rb_graph_count_reads_dev": (i32, [vp] + reads + [vp, vp, vp, C.POINTER(i64)]),
         "rb_graph_add_hashes": (i32, [vp, vp, i64, u32]),
         "rb_graph_count_hashes": (i32, [vp, vp, i64, vp]),
         "rb_graph_add_pair_hashes": (i32, [vp, i32, vp, i64]),
         "rb_graph_lookup_pair_hashes": (i32, [vp, i32, vp, i64, vp]),
         "rb_graph_neighbor_counts": (i32, [vp, vp, vp, vp, vp, i64, vp, vp, vp]),
+        "rb_graph_variant_counts": (i32, [vp, vp, vp, vp, vp, i64, vp, vp, vp]),
+        "rb_graph_max_cov_neighbors": (i32, [vp, vp, vp, vp, vp, i64, f32, vp, vp, vp, vp]),
+        "rb_graph_greedy_extend": (i32, [vp, vp, vp, vp, i64, i32, i32, f32, vp, vp, vp]),
         "rb_graph_sync": (i32, [vp]),
         "rb_graph_sync_to_host": (i32, [vp, vp, vp, vp, vp]),
         "rb_graph_save": (i32, [vp, cp]),

@@ -320,6 +320,9 @@ __device__ __forceinline__ bool bf_lookup_then_add(const BitFilter& bf, const Cl
 struct Ingest {
     const uint64_t* packed;   // 2-bit codes, base b at bits 2*(b&31) of word b>>5
     const uint32_t* mask;     // nullable; bit (b&31) of word b>>5 set = unusable base
+    const uint32_t* rcm;      // nullable; set only together with mask: the unusable base still contributes to the REVERSE-strand hash
+                              // with the seed of its 2-bit code (NTHash.java:367-373 indexes msTab with c & 0x07, so e.g. 'Y' = 0x59
+                              // hashes like the complement of 'A' on the reverse strand and as 0 on the forward strand)
     const int64_t* read_off;  // nullable (uniform layout)
     const int32_t* read_len;  // nullable (uniform layout)
     const int64_t* pos_off;   // exclusive prefix of per-read position counts (n_reads+1), nullable for uniform
@@ -340,12 +343,15 @@ struct RollLut {
     uint64_t c[4];      // S[3-c]                     complement seed
     uint64_t cr1[4];    // rotr(S[3-c], 1)            out-term of the reverse strand
     uint64_t ck1[4];    // rotl(S[3-c], k-1)          in-term of the reverse strand
+    uint64_t sr1[4];    // rotr(S[c], 1)              out-term of the reverse strand for an unusable base with a reverse seed (Ingest::rcm)
+    uint64_t sk1[4];    // rotl(S[c], k-1)            in-term of the same
 };
 __device__ __forceinline__ void build_lut(RollLut* lut, int k) {
     if (threadIdx.x < 4) {
         const int c = threadIdx.x;
         const uint64_t s = seed_of_code(c), sc = seed_of_code(3 - c);
         lut->s[c] = s; lut->sk[c] = rotl64(s, k); lut->c[c] = sc; lut->cr1[c] = rotr64(sc, 1); lut->ck1[c] = rotl64(sc, k - 1);
+        lut->sr1[c] = rotr64(s, 1); lut->sk1[c] = rotl64(s, k - 1);
     }
     __syncthreads();
 }
@@ -355,24 +361,26 @@ __device__ __forceinline__ void build_lut(RollLut* lut, int k) {
 struct BaseCursor {
     const uint64_t* packed;
     const uint32_t* mask;
+    const uint32_t* rcm;
     int64_t b;        // absolute index of the next base
     int64_t widx;     // index of the cached words
     uint64_t w;
-    uint32_t m;
-    __device__ __forceinline__ void seek(const uint64_t* p, const uint32_t* mk, int64_t base) {
-        packed = p; mask = mk; b = base; widx = -1; w = 0; m = 0;
+    uint32_t m, rm;
+    __device__ __forceinline__ void seek(const uint64_t* p, const uint32_t* mk, int64_t base, const uint32_t* rc = nullptr) {
+        packed = p; mask = mk; rcm = rc; b = base; widx = -1; w = 0; m = 0; rm = 0;
     }
-    // returns code | (masked << 2) and advances
+    // returns code | (masked << 2) | (masked base with a reverse-strand seed << 3) and advances
     __device__ __forceinline__ int next() {
         const int64_t wi = b >> 5;
         if (wi != widx) {
             widx = wi;
             w = __ldg(&packed[wi]);
             m = mask ? __ldg(&mask[wi]) : 0u;
+            rm = (mask && rcm) ? __ldg(&rcm[wi]) : 0u;
         }
         const int sh = (int)(b & 31);
         ++b;
-        return (int)((w >> (2 * sh)) & 3) | (int)(((m >> sh) & 1u) << 2);
+        return (int)((w >> (2 * sh)) & 3) | (int)(((m >> sh) & 1u) << 2) | (int)(((rm >> sh) & 1u) << 3);
     }
 };
 
@@ -384,23 +392,23 @@ struct KmerWalker {
     int bad;
     // position the window on bases [start, start+k)
     __device__ __forceinline__ void init(const Ingest& g, int64_t start, int k, const RollLut& lut) {
-        out.seek(g.packed, g.mask, start);
-        in.seek(g.packed, g.mask, start);
+        out.seek(g.packed, g.mask, start, g.rcm);
+        in.seek(g.packed, g.mask, start, g.rcm);
         f = 0; r = 0; bad = 0;
         for (int j = 0; j < k; ++j) {
             const int c = in.next();
             const bool ok = !(c & 4);
-            bad += (c >> 2);
+            bad += (c >> 2) & 1;
             if (MODE != 1) f = rotl1(f) ^ (ok ? lut.s[c & 3] : 0ULL);
-            if (MODE != 0) r ^= ok ? rotl64(lut.c[c & 3], j) : 0ULL;
+            if (MODE != 0) r ^= ok ? rotl64(lut.c[c & 3], j) : ((c & 8) ? rotl64(lut.s[c & 3], j) : 0ULL);
         }
     }
     __device__ __forceinline__ void roll(const RollLut& lut) {
         const int co = out.next(), ci = in.next();
         const bool oko = !(co & 4), oki = !(ci & 4);
-        bad += (ci >> 2) - (co >> 2);
+        bad += ((ci >> 2) & 1) - ((co >> 2) & 1);
         if (MODE != 1) f = rotl1(f) ^ (oko ? lut.sk[co & 3] : 0ULL) ^ (oki ? lut.s[ci & 3] : 0ULL);
-        if (MODE != 0) r = rotr1(r) ^ (oko ? lut.cr1[co & 3] : 0ULL) ^ (oki ? lut.ck1[ci & 3] : 0ULL);
+        if (MODE != 0) r = rotr1(r) ^ (oko ? lut.cr1[co & 3] : ((co & 8) ? lut.sr1[co & 3] : 0ULL)) ^ (oki ? lut.ck1[ci & 3] : ((ci & 8) ? lut.sk1[ci & 3] : 0ULL));
     }
     // hVals[0]: NTHashIterator / ReverseComplementNTHashIterator / CanonicalNTHashIterator (signed min, NTHash.java:494)
     __device__ __forceinline__ uint64_t base() const {

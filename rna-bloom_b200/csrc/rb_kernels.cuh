@@ -399,6 +399,46 @@ __global__ void __launch_bounds__(kThreads) k_hash_op(const int64_t* __restrict_
     }
 }
 
+// ---- the reference's packed fragment records (io/NucleotideBitsWriter.java:24-31, util/SeqBitsUtils.java:138-262) -> ingest layout -------
+// A record = 4-byte big-endian length + ceil(len / 4) tetramer bytes; a tetramer byte = (b0 * 64 + b1 * 16 + b2 * 4 + b3) - 128, first base in
+// the top two bits.  One thread per 32-base output word: 8 tetramer bytes -> one 64-bit word with base b at bits 2 * (b & 31).
+__global__ void __launch_bounds__(kThreads) k_unpack_2bit(const uint8_t* __restrict__ records, const int64_t* __restrict__ data_off /* first tetramer byte of read r */,
+                                                         const int32_t* __restrict__ read_len, const int64_t* __restrict__ word_off, int64_t n_reads,
+                                                         int64_t n_words, uint64_t* __restrict__ packed) {
+    const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (t >= n_words) return;
+    int64_t lo = 0, hi = n_reads;  // read whose word range contains t
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(&word_off[mid]) <= t) lo = mid; else hi = mid;
+    }
+    const int len = __ldg(&read_len[lo]);
+    const int first = (int)(t - __ldg(&word_off[lo])) * 32;          // first base of this word inside the read
+    const uint8_t* src = records + __ldg(&data_off[lo]) + first / 4;
+    const int n_bytes = min(8, (len - first + 3) / 4);
+    uint64_t w = 0;
+    for (int j = 0; j < n_bytes; ++j) {
+        const uint32_t v = (uint32_t)src[j] ^ 0x80u;                  // + 128 (BYTE_OFFSET, SeqBitsUtils.java:35)
+        const uint64_t four = (uint64_t)((v >> 6) & 3) | (uint64_t)((v >> 4) & 3) << 2 | (uint64_t)((v >> 2) & 3) << 4 | (uint64_t)(v & 3) << 6;
+        w |= four << (8 * j);
+    }
+    packed[t] = w;
+}
+
+// ---- CascadingBloomFilter (bloom/CascadingBloomFilter.java:66-100): the keys a level reported as already present move on to the next one
+__global__ void __launch_bounds__(kThreads) k_cascade_survivors(const int64_t* __restrict__ keys, const int32_t* __restrict__ idx, const uint8_t* __restrict__ found,
+                                                               int64_t n, int64_t* __restrict__ keys_out, int32_t* __restrict__ idx_out, unsigned int* n_out) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n || !found[i]) return;
+    const unsigned int o = atomicAdd(n_out, 1u);
+    keys_out[o] = keys[i];
+    idx_out[o] = idx ? idx[i] : (int32_t)i;
+}
+__global__ void __launch_bounds__(kThreads) k_scatter_ones(const int32_t* __restrict__ idx, int64_t n, uint8_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i < n) out[idx[i]] = 1;
+}
+
 // ---- f1 neighbours of a k-mer: Kmer.getSuccessors / getPredecessors (graph/Kmer.java:213-253), CanonicalKmer (:232-271) ----------------
 // Hash side: bloom/hash/SuccessorsNTHashIterator.java:52-63, PredecessorsNTHashIterator.java:54-65 and the Canonical twins (:56-72).
 // One thread per (k-mer, direction): the hashes of the 4 candidate neighbours (A,C,G,T) and graph.getCount of each, all
@@ -444,6 +484,108 @@ __global__ void __launch_bounds__(kThreads) k_neighbors(const int64_t* __restric
         if (nf) nf[o] = (int64_t)fn[c];
         if (nr) nr[o] = (int64_t)rn[c];
     }
+}
+
+// graph.getCount (:562-570) of one base hash: every probe in flight before any is consumed
+template <int MAXH>
+__device__ __forceinline__ float graph_count_of(const GraphDev& gd, uint64_t base) {
+    uint32_t wd[MAXH], wc[MAXH];
+    uint64_t id[MAXH], ic[MAXH];
+#pragma unroll
+    for (int h = 0; h < MAXH; ++h) {
+        if (h < gd.dbg.num_hash) { id[h] = fm_index(expand_hash(base, h, gd.hm), gd.dbg.fm); wd[h] = ld_cg(&gd.dbg.words[id[h] >> 5]); }
+        if (h < gd.cbf.num_hash) { ic[h] = fm_index(expand_hash(base, h, gd.hm), gd.cbf.fm); wc[h] = ld_cg(&gd.cbf.words[ic[h] >> 2]); }
+    }
+    bool all = true;
+    int mn = 127;
+#pragma unroll
+    for (int h = 0; h < MAXH; ++h) {
+        if (h < gd.dbg.num_hash) all = all && ((wd[h] >> (id[h] & 31)) & 1u);
+        if (h < gd.cbf.num_hash) { const int v = byte_of(wc[h], (int)(ic[h] & 3) * 8); mn = v < mn ? v : mn; }
+    }
+    return all ? minifloat_to_float(mn) + 1.f : 0.f;
+}
+
+// ---- f1 variants: Kmer.getLeftVariants / getRightVariants (graph/Kmer.java:357-405), CanonicalKmer (:381-519); hash side
+// bloom/hash/LeftVariantsNTHashIterator.java:40-46, RightVariantsNTHashIterator.java:38-44 and the Canonical twins (:42-52): the k-mers that
+// differ from the query in its FIRST (side 0) or LAST (side 1) base.  One thread per (k-mer, side); entry c of the 4 outputs is the variant
+// with base c there (c == the k-mer's own base: the k-mer itself); the caller drops that entry and applies "count >= minKmerCov".
+template <int MAXH>
+__global__ void __launch_bounds__(kThreads) k_variants(const int64_t* __restrict__ fhash, const int64_t* __restrict__ rhash, const uint8_t* __restrict__ first_code,
+                                                      const uint8_t* __restrict__ last_code, int64_t n, const GraphDev gd, int canonical,
+                                                      float* __restrict__ counts, int64_t* __restrict__ vf, int64_t* __restrict__ vr) {
+    const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (t >= 2 * n) return;
+    const int64_t q = t >> 1;
+    const bool left = (t & 1) == 0;   // outputs: [q][0] left variants, [q][1] right variants, 4 entries each
+    const int k = gd.k;
+    const int out = (int)(left ? first_code[q] : last_code[q]) & 3;
+    const uint64_t f = (uint64_t)fhash[q], r = canonical ? (uint64_t)rhash[q] : 0ULL;
+    // f = xor_i rotl(S[s_i], k-1-i),  r = xor_i rotl(S[3-s_i], i): base 0 sits at rotation k-1 (forward) / 0 (reverse), base k-1 the other way
+    const int rot_f = left ? k - 1 : 0, rot_r = left ? 0 : k - 1;
+    const uint64_t tf = f ^ rotl64(seed_of_code(out), rot_f), tr = r ^ rotl64(seed_of_code(3 - out), rot_r);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const uint64_t fn = tf ^ rotl64(seed_of_code(c), rot_f);
+        const uint64_t rn = canonical ? (tr ^ rotl64(seed_of_code(3 - c), rot_r)) : 0ULL;
+        const uint64_t base = (canonical && (int64_t)rn < (int64_t)fn) ? rn : fn;
+        const int64_t o = t * 4 + c;
+        counts[o] = graph_count_of<MAXH>(gd, base);
+        if (vf) vf[o] = (int64_t)fn;
+        if (vr) vr[o] = (int64_t)rn;
+    }
+}
+
+// ---- f1 batched greedy extension: GraphUtils.greedyExtendRight / greedyExtendLeft with lookahead <= 1 (util/GraphUtils.java:501-527,
+// 1961-1976): at every step the successor (predecessor) with the largest count >= min_cov, the first of equal ones in A, C, G, T order
+// (Kmer.getMaxCovSuccessor, graph/Kmer.java:301-327), until there is none or `bound` k-mers were added.  One thread per start k-mer;
+// the k-mer (k <= 64) travels as 2-bit codes in two 64-bit words, base i at bits 2 * (i & 31) of word i >> 5.
+template <int MAXH>
+__global__ void __launch_bounds__(kThreads) k_greedy_extend(const uint64_t* __restrict__ kmer_bits, const int64_t* __restrict__ fhash, const int64_t* __restrict__ rhash,
+                                                           int64_t n, const GraphDev gd, int canonical, int right, int bound, float min_cov,
+                                                           int32_t* __restrict__ ext_len, uint8_t* __restrict__ ext_codes, float* __restrict__ ext_counts) {
+    const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (t >= n) return;
+    const int k = gd.k;
+    uint64_t w0 = kmer_bits[2 * t], w1 = kmer_bits[2 * t + 1];
+    uint64_t f = (uint64_t)fhash[t], r = canonical ? (uint64_t)rhash[t] : 0ULL;
+    int len = 0;
+    for (; len < bound; ++len) {
+        // the base that leaves: the first one when extending to the right, the last one to the left
+        const int po = right ? 0 : k - 1;
+        const int out = (int)(((po < 32 ? w0 : w1) >> (2 * (po & 31))) & 3);
+        const uint64_t tf = right ? (rotl1(f) ^ rotl64(seed_of_code(out), k)) : (rotr1(f) ^ rotl64(seed_of_code(out), 63));
+        const uint64_t tr = right ? (rotr1(r) ^ rotl64(seed_of_code(3 - out), 63)) : (rotl1(r) ^ rotl64(seed_of_code(3 - out), k));
+        float best = -1.f;
+        int best_c = -1;
+        uint64_t best_f = 0, best_r = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint64_t fn = tf ^ (right ? seed_of_code(c) : rotl64(seed_of_code(c), k - 1));
+            const uint64_t rn = canonical ? (tr ^ (right ? rotl64(seed_of_code(3 - c), k - 1) : seed_of_code(3 - c))) : 0ULL;
+            const uint64_t base = (canonical && (int64_t)rn < (int64_t)fn) ? rn : fn;
+            const float cnt = graph_count_of<MAXH>(gd, base);
+            if (cnt >= min_cov && cnt > best) { best = cnt; best_c = c; best_f = fn; best_r = rn; }
+        }
+        if (best_c < 0) break;
+        ext_codes[t * bound + len] = (uint8_t)best_c;
+        if (ext_counts) ext_counts[t * bound + len] = best;
+        f = best_f; r = best_r;
+        if (right) {            // shift the window one base to the right: drop base 0, append at k - 1
+            w0 = (w0 >> 2) | (w1 << 62);
+            w1 >>= 2;
+            const int pi = k - 1;
+            if (pi < 32) w0 = (w0 & ~(3ULL << (2 * pi))) | ((uint64_t)best_c << (2 * pi));
+            else w1 = (w1 & ~(3ULL << (2 * (pi & 31)))) | ((uint64_t)best_c << (2 * (pi & 31)));
+        } else {                // to the left: prepend at 0, drop base k - 1
+            w1 = (w1 << 2) | (w0 >> 62);
+            w0 = (w0 << 2) | (uint64_t)best_c;
+            const int pd = k;   // the base that fell off now sits at position k: clear it
+            if (pd < 32) w0 &= ~(3ULL << (2 * pd));
+            else if (pd < 64) w1 &= ~(3ULL << (2 * (pd & 31)));
+        }
+    }
+    ext_len[t] = len;
 }
 
 // ---- a8 getIndex exposed on its own (bloom/BloomFilter.java:108-111) -------------------------------------------------------
@@ -493,7 +635,7 @@ __global__ void __launch_bounds__(kThreads) k_synth_reads(uint64_t seed, uint64_
 }
 
 // Long reads (BASELINE configs[4]: ONT-like, ~2 kb, substitutions + insertions + deletions).  Integer-only, so that the CPU checker's
-// twin (oracle/rnabloom_oracle.c orc_synth_long_read) produces the same bases: read r has length 500 + three draws of [0, 1000)
+// twin (in oracle/rnabloom_oracle.c) produces the same bases: read r has length 500 + three draws of [0, 1000)
 // (mean ~2 kb) and walks the virtual genome from a random start on a random strand; per emitted base one draw decides
 // deletion (skip genome bases first) / insertion (random base, genome does not advance) / substitution / match.
 __host__ __device__ __forceinline__ int synth_long_len(uint64_t seed, uint64_t r) {
@@ -537,7 +679,7 @@ __global__ void __launch_bounds__(kThreads) k_synth_long_reads(uint64_t seed, ui
 __global__ void __launch_bounds__(kThreads) k_pack_ascii(const char* __restrict__ bases, const char* __restrict__ quals,
                                                         const int64_t* __restrict__ ascii_off, const int64_t* __restrict__ word_off,
                                                         int64_t n_reads, int64_t n_words, int min_qual, uint64_t* __restrict__ packed,
-                                                        uint32_t* __restrict__ mask) {
+                                                        uint32_t* __restrict__ mask, uint32_t* __restrict__ rcm) {
     const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (t >= n_words) return;
     int64_t lo = 0, hi = n_reads;  // read whose word range contains t
@@ -549,7 +691,7 @@ __global__ void __launch_bounds__(kThreads) k_pack_ascii(const char* __restrict_
     const int len = (int)(__ldg(&ascii_off[lo + 1]) - a0);
     const int first = (int)(t - __ldg(&word_off[lo])) * 32;
     uint64_t w = 0;
-    uint32_t m = 0;
+    uint32_t m = 0, rm = 0;
     const int qlo = '!' + min_qual;
     for (int j = 0; j < 32; ++j) {
         const int i = first + j;
@@ -562,7 +704,14 @@ __global__ void __launch_bounds__(kThreads) k_pack_ascii(const char* __restrict_
             case 'C': case 'c': code = 1; break;
             case 'G': case 'g': code = 2; break;
             case 'T': case 't': case 'U': case 'u': code = 3; break;
-            default: ok = false;
+            default: {
+                // not a nucleotide: 0 on the forward strand (msTab row c), but the reverse strand reads msTab row c & 0x07
+                // (NTHash.java:100-101 rows 0..7 = N T N G A A N C): the code field carries the base whose FORWARD seed that row holds
+                ok = false;
+                const int row = c & 7;
+                const int rc_code = row == 1 ? 3 : row == 3 ? 2 : (row == 4 || row == 5) ? 0 : row == 7 ? 1 : -1;
+                if (rc_code >= 0) { code = rc_code; rm |= 1u << j; }
+            }
         }
         if (quals) { const unsigned char q = (unsigned char)quals[a0 + i]; if (q < qlo || q > '~') ok = false; }
         w |= (uint64_t)code << (2 * j);
@@ -570,6 +719,7 @@ __global__ void __launch_bounds__(kThreads) k_pack_ascii(const char* __restrict_
     }
     packed[t] = w;
     mask[t] = m;
+    if (rcm) rcm[t] = rm;
 }
 
 }  // namespace rb

@@ -261,6 +261,8 @@ static int32_t mgraph_create(rb_ctx* ctx, int32_t n_ranks, int32_t rank, const r
     }
     sg.shard_d = (int)div_up(tot_d, W); sg.shard_c = (int)div_up(tot_c, W);
     if (mg->paired) {   // the counters of a rank are its paired slices: the raise slices subdivide exactly that range
+        sg.shard_p = sg.n_pair / W;                                   // also for one rank (sl_pair_geometry leaves it 0 there)
+        sg.pair_local_c = (uint64_t)sg.shard_p << sg.pair_log2;
         sg.cbf_log2 = sg.pair_log2;
         sg.shard_c = sg.shard_p;
         sg.shard_d = 0;   // unused: a paired region is the global slice number
@@ -443,7 +445,7 @@ static SlArena mg_producer(rb_mgraph* mg, void* data, unsigned int* cursor, int 
 // regions received from every rank, in the consumer's order (local region first, source rank second)
 // p2p mode: peer_data / peer_cnt are the device tables of the producers' arenas / packed counts (data and recv_cnt are not used)
 static int32_t mg_consumer(rb_mgraph* mg, void* data, const uint32_t* recv_cnt, void** peer_data, void** peer_cnt, int per_rank, uint32_t cap, int chunk,
-                           SlArena* out) {
+                           SlArena* out, int passes = 1) {
     rb_ctx* ctx = mg->ctx;
     const int n = per_rank * mg->W;
     if (mg->p2p) RB_LAUNCH((int)div_up(n, kSlThreads), kSlThreads, 0, ctx->stream, ks_order_counts_p2p)((const uint32_t* const*)peer_cnt, mg->W, mg->rank, per_rank, cap,
@@ -453,6 +455,7 @@ static int32_t mg_consumer(rb_mgraph* mg, void* data, const uint32_t* recv_cnt, 
     SlArena a = sl_arena(data, mg->cons_cursor, nullptr, n, chunk);
     a.cap = cap; a.cursor_stride = 1; a.rlo = mg->cons_rlo;
     if (mg->p2p) { a.data = nullptr; a.peer_data = peer_data; a.n_peers = mg->W; }
+    a.passes = passes;
     *out = a;
     RB_LAUNCH(1, kSlThreads, ((size_t)((a.B + 3) & ~3) + 296) * 4, ctx->stream, ks_chunk_prefix)(a, mg->chunk_prefix);
     LAUNCH_CHECK();
@@ -574,7 +577,8 @@ static int32_t mg_route(rb_mgraph* mg, const ReadsArg& ra, int mode, bool lookup
 static int32_t mg_apply(rb_mgraph* mg, bool set_bits) {
     rb_ctx* ctx = mg->ctx;
     SlArena a;
-    int32_t rc = mg_consumer(mg, mg->recv32, mg->cnt_r, mg->d_peer32, mg->d_peer_cnt, mg->R, mg->probe_cap, sl_chunk(), &a);
+    int32_t rc = mg_consumer(mg, mg->recv32, mg->cnt_r, mg->d_peer32, mg->d_peer_cnt, mg->R, mg->probe_cap, sl_chunk(), &a,
+                             mg->paired ? 1 << mg->sg_apply.pair_sub_log2 : 1);
     if (rc) return rc;
     if (mg->p2p) a.peer_ans = (uint8_t* const*)mg->d_peer_ans;
     const size_t sm_pre = (size_t)(a.B + 1) * 4;

@@ -77,6 +77,9 @@ struct SlArena {
     void* const* peer_data;
     uint8_t* const* peer_ans;
     int n_peers;
+    // consumer: every region is walked `passes` times (work items of pass 0 first, then pass 1 ...): a paired region may span several
+    // L2-resident sub-slices, pass i handles the records of sub-slice i (SlGeom::pair_sub_log2).  1 everywhere else.
+    int passes;
 };
 template <typename REC>
 __device__ __forceinline__ const REC* sl_region_records(const SlArena& a, int region) {
@@ -91,6 +94,10 @@ struct SlGeom {
     // paired records (NJ = 3): slice s = counters [s << pair_log2, (s + 1) << pair_log2) and, for every chunk c < dbg_bits / cbf_bytes,
     // the bits c * cbf_bytes + the same range; record = chunk << pair_log2 | offset inside the slice.  n_dbg = n_cbf = 0, n_pair regions.
     int paired, pair_log2, cbf_size_log2, n_pair;
+    // A region of 2^pair_log2 counters is consumed in 2^pair_sub_log2 passes over sub-slices of 2^(pair_log2 - pair_sub_log2) counters:
+    // only the sub-slice has to stay L2-resident, so a producer with many owners / slices can sort into fewer, wider regions (the tile
+    // sort's cost per tile grows with the number of regions) at the price of streaming the region's records once per pass.
+    int pair_sub_log2;
     uint64_t pair_local_c;    // counters (= bits per chunk) of the consumer's share: cbf_bytes on one GPU, shard_p << pair_log2 when sharded
     int shard_p;              // paired slices per rank (sharded graph): region = global slice, owner = slice / shard_p
     // hash-sharded graph (rb_sshard_*, one process per GPU): rank r owns dbgbf slices [r * shard_d, (r+1) * shard_d) and cbf slices
@@ -362,7 +369,7 @@ struct PrefixKmerizer {
         abs_lo = abs_of(g, tile0);
         const int span = (int)(abs_of(g, last) + k - abs_lo);   // <= kSpan (the host checks the layout)
         BaseCursor cur;
-        cur.seek(g.packed, g.mask, abs_lo + (int64_t)t * PER);
+        cur.seek(g.packed, g.mask, abs_lo + (int64_t)t * PER, g.rcm);
         unsigned long long xf = 0, xr = 0;
         uint32_t xb = 0;
 #pragma unroll
@@ -371,8 +378,10 @@ struct PrefixKmerizer {
             lf[x] = xf; lr[x] = xr; lb[x] = (uint16_t)xb;
             if (x < span) {
                 const int c = cur.next();
-                if (c & 4) ++xb;
-                else {
+                if (c & 4) {
+                    ++xb;
+                    if ((c & 8) && MODE != 0) xr ^= rotl64(seed_of_code(c & 3), x & 63);   // unusable base with a reverse-strand seed (Ingest::rcm)
+                } else {
                     if (MODE != 1) xf ^= rotl64(seed_of_code(c & 3), 64 - (x & 63));
                     if (MODE != 0) xr ^= rotl64(seed_of_code(3 - (c & 3)), x & 63);
                 }
@@ -499,7 +508,7 @@ __global__ void __launch_bounds__(kSlThreads, 3) ks_route_keys_u(const Ingest g,
 
 // ---- S1: k-merise, tile-sort the probes of every usable k-mer instance by filter slice --------------------------------------------
 template <int MODE, int NJ>
-__global__ void __launch_bounds__(kSlThreads) ks_route_lookup(const Ingest g, int k, const HashMults hm, const SlGeom sg, const SlArena arena,
+__global__ void __launch_bounds__(kSlThreads, 2) ks_route_lookup(const Ingest g, int k, const HashMults hm, const SlGeom sg, const SlArena arena,
                                                              uint32_t* __restrict__ pos, uint2* __restrict__ tile_meta, int64_t* __restrict__ fhash,
                                                              int64_t* __restrict__ rhash, int* overflow) {
     RB_DYN_SMEM(unsigned char, sl_smem);
@@ -541,7 +550,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_chunk_prefix(const SlArena aren
     for (int b = threadIdx.x; b < arena.B; b += kSlThreads) {
         const uint32_t cap = sl_region_hi(arena, b) - sl_region_lo(arena, b);
         const uint32_t cnt = min(arena.cursor[(size_t)b * arena.cursor_stride], cap);
-        v[b] = (cnt + (uint32_t)arena.chunk - 1) / (uint32_t)arena.chunk;
+        v[b] = (cnt + (uint32_t)arena.chunk - 1) / (uint32_t)arena.chunk * (uint32_t)max(arena.passes, 1);
     }
     __syncthreads();
     const uint32_t total = cta_exclusive_scan(v, arena.B, scratch);
@@ -560,7 +569,7 @@ __device__ __forceinline__ int sl_next_chunk(int* counter, int* s_c) {
     __syncthreads();
     return *s_c;
 }
-struct SlWork { int b; uint32_t first, n; };
+struct SlWork { int b; uint32_t first, n; int pass; };
 __device__ __forceinline__ void sl_load_prefix(int* pre, const int* chunk_prefix, int B) {
     for (int i = threadIdx.x; i <= B; i += kSlThreads) pre[i] = chunk_prefix[i];
     __syncthreads();
@@ -572,7 +581,14 @@ __device__ __forceinline__ SlWork sl_work_item(const SlArena& arena, const int* 
     w.b = lo;
     const uint32_t r_lo = sl_region_lo(arena, lo), cap = sl_region_hi(arena, lo) - r_lo;
     const uint32_t cnt = min(arena.cursor[(size_t)lo * arena.cursor_stride], cap);
-    const uint32_t off = (uint32_t)(c - pre[lo]) * (uint32_t)arena.chunk;
+    uint32_t local = (uint32_t)(c - pre[lo]);
+    w.pass = 0;
+    if (arena.passes > 1) {
+        const uint32_t per_pass = (cnt + (uint32_t)arena.chunk - 1) / (uint32_t)arena.chunk;
+        w.pass = (int)(local / per_pass);
+        local -= (uint32_t)w.pass * per_pass;
+    }
+    const uint32_t off = local * (uint32_t)arena.chunk;
     w.first = r_lo + off;
     w.n = min((uint32_t)arena.chunk, cnt - off);
     return w;
@@ -600,14 +616,20 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
             // record = chunk << pair_log2 | offset: counter byte (lr << pair_log2) + offset, bit chunk * pair_local_c + the same
             const uint64_t byte0 = (uint64_t)lr << sg.pair_log2;
             const uint32_t off_mask = (1u << sg.pair_log2) - 1u;
+            const int sub_shift = sg.pair_log2 - sg.pair_sub_log2;
             for (uint32_t i0 = threadIdx.x; i0 < w.n; i0 += kSlThreads * U) {
                 uint32_t li[U], wd[U], wc[U];
+                bool act[U];   // in range and in the sub-slice of this pass
 #pragma unroll
-                for (int u = 0; u < U; ++u) li[u] = (i0 + u * kSlThreads < w.n) ? __ldcs(rec + w.first + i0 + u * kSlThreads) : 0u;
+                for (int u = 0; u < U; ++u) {
+                    const bool in = i0 + u * kSlThreads < w.n;
+                    li[u] = in ? __ldcs(rec + w.first + i0 + u * kSlThreads) : 0u;
+                    act[u] = in && (int)((li[u] & off_mask) >> sub_shift) == w.pass;
+                }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     wd[u] = 0; wc[u] = 0;
-                    if (i0 + u * kSlThreads < w.n) {
+                    if (act[u]) {
                         const uint64_t ci = byte0 + (li[u] & off_mask);
                         const uint64_t bi = (uint64_t)(li[u] >> sg.pair_log2) * sg.pair_local_c + ci;
                         wd[u] = ld_cg_keep(dbg_words + (bi >> 5), keep);
@@ -616,7 +638,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    if (i0 + u * kSlThreads < w.n) {
+                    if (act[u]) {
                         const uint64_t ci = byte0 + (li[u] & off_mask);
                         const uint64_t bi = (uint64_t)(li[u] >> sg.pair_log2) * sg.pair_local_c + ci;
                         const uint32_t bit = 1u << (bi & 31);

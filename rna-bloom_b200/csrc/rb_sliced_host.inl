@@ -73,7 +73,7 @@ static int32_t sl_make_roff(rb_ctx* ctx, const std::vector<int64_t>& caps, uint3
 // counters plus dbg_bits / cbf_bytes chunks of W bits; w is chosen so that one slice is about 64 MiB (it has to stay L2-resident
 // while it is consumed).  n_ranks > 1: every rank must own the same whole number of slices.  Fills the pair_* fields of sg.
 static bool sl_pair_geometry(int64_t dbg_bits, int64_t cbf_bytes, int hd, int hc, int n_ranks, SlGeom* sg) {
-    sg->paired = 0; sg->pair_log2 = 0; sg->cbf_size_log2 = 0; sg->n_pair = 0; sg->pair_local_c = 0; sg->shard_p = 0;
+    sg->paired = 0; sg->pair_log2 = 0; sg->pair_sub_log2 = 0; sg->cbf_size_log2 = 0; sg->n_pair = 0; sg->pair_local_c = 0; sg->shard_p = 0;
     if (!env_int("RB_SLICED_PAIRED", 1, 0, 1)) return false;
     if (hd < hc || cbf_bytes < 4 || (cbf_bytes & (cbf_bytes - 1)) != 0 || dbg_bits % cbf_bytes != 0) return false;
     const int64_t q = dbg_bits / cbf_bytes;
@@ -82,11 +82,19 @@ static bool sl_pair_geometry(int64_t dbg_bits, int64_t cbf_bytes, int hd, int hc
     while (w < c && (double)(1LL << (w + 1)) * (1.0 + (double)q / 8.0) <= 64.0 * 1024 * 1024) ++w;
     w = env_int("RB_SLICE_PAIR_LOG2", w, 2, 31);
     if (w > c) w = c;
+    // RB_SLICE_REGION_TARGET < the number of slices: widen the regions to 2^p sub-slices each, consumed in 2^p passes
+    // (SlGeom::pair_sub_log2).  Measured at N = 4 / 8 (profiles/r02_notes.md): the tile sorts do get cheaper with fewer regions, but the
+    // consumer streams every region's records once per pass -- over NVLink in peer-to-peer mode -- and loses far more (N = 8: 26.2 ->
+    // 16.3 G k-mers/s with 4 passes), so the default keeps one pass; the mechanism stays for geometries that need it (> 2048 slices).
+    const int64_t target = env_int("RB_SLICE_REGION_TARGET", kSlMaxRegions, 1, kSlMaxRegions);
+    int p = 0;
+    while ((cbf_bytes >> (w + p)) > target && p < 3 && w + p < c && (q - 1) < (1LL << (32 - (w + p + 1)))) ++p;
+    w += p;
     while ((cbf_bytes >> w) > kSlMaxRegions && w < c) ++w;
     if ((cbf_bytes >> w) > kSlMaxRegions || w > 31 || (w < 32 && (q - 1) >= (1LL << (32 - w)))) return false;
     const int64_t n_pair = cbf_bytes >> w;
     if (n_ranks > 1 && (n_pair % n_ranks) != 0) return false;
-    sg->paired = 1; sg->pair_log2 = w; sg->cbf_size_log2 = c; sg->n_pair = (int)n_pair;
+    sg->paired = 1; sg->pair_log2 = w; sg->pair_sub_log2 = p; sg->cbf_size_log2 = c; sg->n_pair = (int)n_pair;
     sg->shard_p = n_ranks > 1 ? (int)(n_pair / n_ranks) : 0;
     sg->pair_local_c = n_ranks > 1 ? (uint64_t)sg->shard_p << w : (uint64_t)cbf_bytes;
     return true;
@@ -237,10 +245,14 @@ static SlArena sl_arena(void* data, unsigned int* cursor, const uint32_t* roff, 
     SlArena a;
     a.data = data; a.cursor = cursor; a.roff = roff; a.B = B; a.chunk = chunk; a.cap = 0; a.cursor_stride = kSlPad; a.rlo = nullptr;
     a.spill_data = nullptr; a.spill_cursor = nullptr; a.spill_cap = 0;
-    a.peer_data = nullptr; a.peer_ans = nullptr; a.n_peers = 1;
+    a.peer_data = nullptr; a.peer_ans = nullptr; a.n_peers = 1; a.passes = 1;
     return a;
 }
-static SlArena sl_probe_arena(SlicedEngine* e) { return sl_arena(e->probe_data, e->probe_cursor, e->probe_roff, e->probe_B, sl_chunk()); }
+static SlArena sl_probe_arena(SlicedEngine* e) {
+    SlArena a = sl_arena(e->probe_data, e->probe_cursor, e->probe_roff, e->probe_B, sl_chunk());
+    if (e->paired) a.passes = 1 << e->sg.pair_sub_log2;
+    return a;
+}
 
 // the prefix k-merizer covers a CTA's 1024 positions with one span of at most kPfxSpan bases of the packed stream (uniform layout only)
 static bool sl_uniform_fast(const Ingest& ing, int k, int tile, int span_cap) {

@@ -32,8 +32,8 @@ struct rb_ctx {
     int64_t claim_cap = 0, claim_used = 0;
     const void* claim_owner = nullptr;  // the bit array the current claims refer to
     // staging (host-pointer entry points)
-    void* stage[16] = {};
-    int64_t stage_bytes[16] = {};
+    void* stage[32] = {};
+    int64_t stage_bytes[32] = {};
     cudaStream_t copy_stream = nullptr;             // D2H of lookup results overlaps the next launch
     cudaEvent_t ev_kernel[2] = {nullptr, nullptr};  // kernel of parity p finished (results ready in staging p)
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};    // D2H out of staging p finished (staging p reusable)
@@ -208,7 +208,7 @@ extern "C" int32_t rb_ctx_destroy(rb_ctx* ctx) {
         LOCK(ctx);
         cudaStreamSynchronize(ctx->stream);
         if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-        for (int i = 0; i < 16; ++i) if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+        for (int i = 0; i < 32; ++i) if (ctx->stage[i]) cudaFree(ctx->stage[i]);
         for (int i = 0; i < 2; ++i) { if (ctx->ev_kernel[i]) cudaEventDestroy(ctx->ev_kernel[i]); if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]); }
         if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
         if (ctx->claim) cudaFree(ctx->claim);
@@ -545,6 +545,85 @@ extern "C" int32_t rb_filter_upload(rb_filter* f, const void* src, int64_t nbyte
     return RB_OK;
 }
 
+// ---- CascadingBloomFilter (bloom/CascadingBloomFilter.java:34-100): L plain Bloom filters of size / L bits each ---------------------------------
+// add: walk the levels with lookupThenAdd, stop at the first level where the key was not already present; lookup: the top level;
+// lookupThenAdd: true iff every level already had the key.  A batch goes level by level: the instances a level reports as present
+// (duplicates inside the batch included: the claim table makes exactly one instance of a key the first sighting per level) are
+// compacted and handed to the next level -- the same final state as the sequential loop for any order of the batch.
+struct rb_cascade { rb_ctx* ctx; int levels; std::vector<rb_filter*> bf; };
+extern "C" int32_t rb_cascade_create(rb_ctx* ctx, int64_t size, int32_t num_hash, int32_t k, int32_t num_levels, rb_cascade** out) {
+    if (!ctx || !out || num_levels < 1 || num_levels > 64) return RB_EINVAL;
+    LOCK(ctx);
+    rb_cascade* c = new rb_cascade();
+    c->ctx = ctx; c->levels = num_levels;
+    for (int i = 0; i < num_levels; ++i) {
+        rb_filter* f = nullptr;
+        const int32_t rc = filter_alloc(ctx, RB_BLOOM, size / num_levels, num_hash, k, &f);   // partitionSize = size / numLevels (:38)
+        if (rc) { for (rb_filter* x : c->bf) filter_free(x); delete c; return rc; }
+        f->in_graph = true;
+        c->bf.push_back(f);
+    }
+    *out = c;
+    return RB_OK;
+}
+extern "C" int32_t rb_cascade_destroy(rb_cascade* c) {
+    if (!c) return RB_EINVAL;
+    { LOCK(c->ctx); for (rb_filter* f : c->bf) filter_free(f); }
+    delete c;
+    return RB_OK;
+}
+extern "C" int32_t rb_cascade_level(rb_cascade* c, int32_t level, rb_filter** out) {
+    if (!c || !out || level < 0 || level >= c->levels) return RB_EINVAL;
+    *out = c->bf[(size_t)level];
+    return RB_OK;
+}
+extern "C" int32_t rb_cascade_lookup_hashes(rb_cascade* c, const int64_t* base, int64_t n, uint8_t* out) {   // :79-85: the top level answers
+    if (!c) return RB_EINVAL;
+    return rb_filter_lookup_hashes(c->bf.back(), base, n, out);
+}
+// out (nullable): lookupThenAdd's answer per key (:93-100); add (:66-72) is the same walk without the answer
+extern "C" int32_t rb_cascade_lookup_then_add_hashes(rb_cascade* c, const int64_t* base, int64_t n, uint8_t* out) {
+    if (!c || n < 0 || (n > 0 && !base)) return RB_EINVAL;
+    rb_ctx* ctx = c->ctx;
+    LOCK(ctx);
+    if (n > INT32_MAX) return fail(ctx, RB_EINVAL, "cascade: at most 2^31-1 keys per call");
+    if (n == 0) return RB_OK;
+    void *k0, *k1, *i0, *i1, *fl, *res = nullptr;
+    int32_t rc;
+    if ((rc = stage_get(ctx, 0, n * 8, &k0)) || (rc = stage_get(ctx, 1, n * 8, &k1)) || (rc = stage_get(ctx, 2, n * 4, &i0)) ||
+        (rc = stage_get(ctx, 3, n * 4, &i1)) || (rc = stage_get(ctx, 4, n, &fl))) return rc;
+    if (out && (rc = stage_get(ctx, 5, n, &res))) return rc;
+    CK(cudaMemcpyAsync(k0, base, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (out) CK(cudaMemsetAsync(res, 0, (size_t)n, ctx->stream));
+    int64_t m = n;
+    int64_t *kin = (int64_t*)k0, *kout = (int64_t*)k1;
+    int32_t *iin = nullptr, *iout = (int32_t*)i0, *ispare = (int32_t*)i1;
+    for (int lv = 0; lv < c->levels && m > 0; ++lv) {
+        GraphDev gd = filter_view(c->bf[(size_t)lv]);
+        rc = claim_reserve(ctx, m, gd.dbg.words, &gd.ct);
+        if (rc) return rc;
+        dispatch_hash_op(OP_BF_LTA, c->bf[(size_t)lv]->num_hash, m, ctx->stream, kin, gd, (uint8_t*)fl, nullptr);
+        LAUNCH_CHECK();
+        CK(cudaMemsetAsync(ctx->scratch, 0, 8, ctx->stream));
+        RB_LAUNCH((int)div_up(m, kThreads), kThreads, 0, ctx->stream, k_cascade_survivors)(kin, iin, (const uint8_t*)fl, m, kout, iout, (unsigned int*)ctx->scratch);
+        LAUNCH_CHECK();
+        unsigned int next = 0;
+        CK(cudaMemcpyAsync(&next, ctx->scratch, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        m = next;
+        std::swap(kin, kout);
+        int32_t* t = iin ? iin : ispare;
+        iin = iout; iout = t;
+    }
+    if (out) {   // the survivors of the last level were present everywhere
+        if (m > 0) { RB_LAUNCH((int)div_up(m, kThreads), kThreads, 0, ctx->stream, k_scatter_ones)(iin, m, (uint8_t*)res); LAUNCH_CHECK(); }
+        CK(cudaMemcpyAsync(out, res, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return RB_OK;
+}
+extern "C" int32_t rb_cascade_add_hashes(rb_cascade* c, const int64_t* base, int64_t n) { return rb_cascade_lookup_then_add_hashes(c, base, n, nullptr); }
+
 // Float.toString look-alike for the "fpr:" line of the .desc files (value is informational: the reader skips it,
 // bloom/BloomFilter.java:73-88)
 static std::string java_float(float v) {
@@ -660,6 +739,7 @@ struct ReadsArg {
     int64_t n_reads; int32_t uniform_len; int64_t uniform_stride;
     bool on_device;
     int64_t read0 = 0;   // uniform layout: index of the first read inside `packed` (a launch handed on as a ReadsArg of its own)
+    const uint32_t* rcm = nullptr;   // device reads only: reverse-strand seed plane of unusable bases (Ingest::rcm; the ASCII entry points make it)
 };
 // One launch worth of reads, all pointers on the device.
 struct Launch { Ingest ing; int64_t n_pos; };
@@ -686,7 +766,7 @@ static int32_t for_each_launch(rb_ctx* ctx, const ReadsArg& ra, int span, Launch
                 ing.n_reads = nr; ing.n_pos = nr * npos; ing.out_base = r0 * npos;
                 ing.uniform_stride = ra.uniform_stride; ing.uniform_len = ra.uniform_len; ing.uniform_npos = npos;
                 const int64_t b_lo = (ra.read0 + r0) * ra.uniform_stride, b_hi = (ra.read0 + r0 + nr - 1) * ra.uniform_stride + ra.uniform_len;
-                if (ra.on_device) { ing.packed = ra.packed; ing.mask = ra.mask; ing.first_base = b_lo; }
+                if (ra.on_device) { ing.packed = ra.packed; ing.mask = ra.mask; ing.rcm = ra.rcm; ing.first_base = b_lo; }
                 else {
                     const int64_t w_lo = b_lo >> 5, w_hi = (b_hi + 31) >> 5;
                     void* dp; int32_t rc = stage_get(ctx, 0, (w_hi - w_lo) * 8, &dp); if (rc) return rc;
@@ -730,7 +810,7 @@ static int32_t for_each_launch(rb_ctx* ctx, const ReadsArg& ra, int span, Launch
                 int32_t rc = stage_get(ctx, 2, (nr + 1) * 8, &d_po); if (rc) return rc;
                 CK(cudaMemcpyAsync(d_po, pos_off.data() + r0, (size_t)(nr + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
                 ing.pos_off = (const int64_t*)d_po;
-                if (ra.on_device) { ing.packed = ra.packed; ing.mask = ra.mask; ing.read_off = ra.read_off + r0; ing.read_len = ra.read_len + r0; }
+                if (ra.on_device) { ing.packed = ra.packed; ing.mask = ra.mask; ing.rcm = ra.rcm; ing.read_off = ra.read_off + r0; ing.read_len = ra.read_len + r0; }
                 else {
                     int64_t b_lo = INT64_MAX, b_hi = 0;
                     for (int64_t i = r0; i < r1; ++i) if (len[i] > 0) { b_lo = std::min(b_lo, off[i]); b_hi = std::max(b_hi, off[i] + len[i]); }
@@ -934,6 +1014,7 @@ static int32_t insert_launch(rb_ctx* ctx, const Ingest& ing, void* user) {
             // a sliced round handed back (skew beyond the spill path, or no memory for the work buffers) is as large as 2^29 k-mers: the
             // direct engine takes it in launches of its own size, so that its claim table stays bounded (8 B x 2 x k-mers per launch)
             ReadsArg sub{ing.packed, ing.mask, ing.read_off, ing.read_len, ing.n_reads, ing.uniform_len, ing.uniform_stride, true};
+            sub.rcm = ing.rcm;
             if (!ing.pos_off) sub.read0 = ing.first_base / ing.uniform_stride;
             InsertUser u2 = *u;
             u2.direct_only = true;
@@ -974,6 +1055,7 @@ static int32_t pairs_launch(rb_ctx* ctx, const Ingest& ing, void* user) {
     const BitFilter pk = bit_view(u->pk);
     const int grid = (int)div_up(div_up(ing.n_pos, kChunk), kThreads);
     const int maxh = std::max(u->g->hd, u->pk->num_hash);
+    PROF("k_pairs");
     if (maxh <= 2) launch_pairs_mode<2>(u->mode, u->op, grid, ctx->stream, ing, gd, pk, u->d);
     else if (maxh <= 3) launch_pairs_mode<3>(u->mode, u->op, grid, ctx->stream, ing, gd, pk, u->d);
     else if (maxh <= 4) launch_pairs_mode<4>(u->mode, u->op, grid, ctx->stream, ing, gd, pk, u->d);
@@ -1031,13 +1113,9 @@ extern "C" int32_t rb_graph_add_reads_dev(rb_graph* g, const uint64_t* packed, c
     return graph_add_reads(g, ra, flags, n_kmers_out);
 }
 
-extern "C" int32_t rb_graph_add_reads_ascii(rb_graph* g, const char* bases, const char* quals, const int64_t* ascii_off, int64_t n_reads,
-                                            int32_t min_qual, uint32_t flags, int64_t* n_kmers_out) {
-    if (!g || !bases || !ascii_off || n_reads < 0) return RB_EINVAL;
-    rb_ctx* ctx = g->ctx;
-    LOCK(ctx);
-    if (n_kmers_out) *n_kmers_out = 0;
-    if (n_reads == 0) return RB_OK;
+// ASCII records -> 2-bit codes + unusable-base mask + reverse-seed plane, on the device, in grow-only staging of the context (no
+// allocation per call).  The chunk of records a Java worker hands over (RNABloom.java:551-634) arrives here as three host arrays.
+static int32_t ascii_pack(rb_ctx* ctx, const char* bases, const char* quals, const int64_t* ascii_off, int64_t n_reads, int32_t min_qual, ReadsArg* out) {
     // per-read word offsets (reads start on 32-base word boundaries) -- host pass over n_reads+1 integers only
     std::vector<int64_t> word_off((size_t)n_reads + 1), read_off((size_t)n_reads);
     std::vector<int32_t> read_len((size_t)n_reads);
@@ -1050,37 +1128,132 @@ extern "C" int32_t rb_graph_add_reads_ascii(rb_graph* g, const char* bases, cons
     }
     word_off[(size_t)n_reads] = words;
     const int64_t a_lo = ascii_off[0], a_hi = ascii_off[n_reads];
-    char *d_b = nullptr, *d_q = nullptr; int64_t *d_ao = nullptr, *d_wo = nullptr, *d_ro = nullptr; int32_t* d_rl = nullptr;
-    uint64_t* d_packed = nullptr; uint32_t* d_mask = nullptr;
-    auto cleanup = [&]() { cudaFree(d_b); cudaFree(d_q); cudaFree(d_ao); cudaFree(d_wo); cudaFree(d_ro); cudaFree(d_rl); cudaFree(d_packed); cudaFree(d_mask); };
-#define CKF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ctx, RB_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
-    CKF(cudaMalloc(&d_b, (size_t)(a_hi - a_lo) + 16));
-    if (quals) CKF(cudaMalloc(&d_q, (size_t)(a_hi - a_lo) + 16));
-    CKF(cudaMalloc(&d_ao, (size_t)(n_reads + 1) * 8));
-    CKF(cudaMalloc(&d_wo, (size_t)(n_reads + 1) * 8));
-    CKF(cudaMalloc(&d_ro, (size_t)n_reads * 8));
-    CKF(cudaMalloc(&d_rl, (size_t)n_reads * 4));
-    CKF(cudaMalloc(&d_packed, (size_t)(words + 2) * 8));
-    CKF(cudaMalloc(&d_mask, (size_t)(words + 2) * 4));
-    CKF(cudaMemcpyAsync(d_b, bases + a_lo, (size_t)(a_hi - a_lo), cudaMemcpyHostToDevice, ctx->stream));
-    if (quals) CKF(cudaMemcpyAsync(d_q, quals + a_lo, (size_t)(a_hi - a_lo), cudaMemcpyHostToDevice, ctx->stream));
-    CKF(cudaMemcpyAsync(d_ao, ascii_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CKF(cudaMemcpyAsync(d_wo, word_off.data(), (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CKF(cudaMemcpyAsync(d_ro, read_off.data(), (size_t)n_reads * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CKF(cudaMemcpyAsync(d_rl, read_len.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, ctx->stream));
+    void *d_b, *d_q = nullptr, *d_ao, *d_wo, *d_ro, *d_rl, *d_packed, *d_mask, *d_rcm;
+    int32_t rc;
+    if ((rc = stage_get(ctx, 16, (a_hi - a_lo) + 16, &d_b))) return rc;
+    if (quals && (rc = stage_get(ctx, 17, (a_hi - a_lo) + 16, &d_q))) return rc;
+    if ((rc = stage_get(ctx, 18, (n_reads + 1) * 8, &d_ao))) return rc;
+    if ((rc = stage_get(ctx, 19, (n_reads + 1) * 8, &d_wo))) return rc;
+    if ((rc = stage_get(ctx, 20, n_reads * 8, &d_ro))) return rc;
+    if ((rc = stage_get(ctx, 21, n_reads * 4, &d_rl))) return rc;
+    if ((rc = stage_get(ctx, 22, (words + 2) * 8, &d_packed))) return rc;
+    if ((rc = stage_get(ctx, 23, (words + 2) * 4, &d_mask))) return rc;
+    if ((rc = stage_get(ctx, 24, (words + 2) * 4, &d_rcm))) return rc;
+    CK(cudaMemcpyAsync(d_b, bases + a_lo, (size_t)(a_hi - a_lo), cudaMemcpyHostToDevice, ctx->stream));
+    if (quals) CK(cudaMemcpyAsync(d_q, quals + a_lo, (size_t)(a_hi - a_lo), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_ao, ascii_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_wo, word_off.data(), (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_ro, read_off.data(), (size_t)n_reads * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_rl, read_len.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, ctx->stream));
     if (words > 0) {
-        RB_LAUNCH((int)div_up(words, kThreads), kThreads, 0, ctx->stream, k_pack_ascii)(d_b - a_lo, d_q ? d_q - a_lo : nullptr, d_ao, d_wo, n_reads, words,
-                                                                                 min_qual, d_packed, d_mask);
-        ++ctx->launches;
-        CKF(cudaGetLastError());
+        RB_LAUNCH((int)div_up(words, kThreads), kThreads, 0, ctx->stream, k_pack_ascii)((const char*)d_b - a_lo, d_q ? (const char*)d_q - a_lo : nullptr, (const int64_t*)d_ao,
+                                                                                 (const int64_t*)d_wo, n_reads, words, min_qual, (uint64_t*)d_packed,
+                                                                                 (uint32_t*)d_mask, (uint32_t*)d_rcm);
+        LAUNCH_CHECK();
     }
-    ReadsArg ra{d_packed, d_mask, d_ro, d_rl, n_reads, 0, 0, true};
-    int32_t rc = graph_add_reads(g, ra, flags, n_kmers_out);
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    cleanup();
+    CK(cudaStreamSynchronize(ctx->stream));   // the host vectors go out of scope
+    *out = ReadsArg{(const uint64_t*)d_packed, (const uint32_t*)d_mask, (const int64_t*)d_ro, (const int32_t*)d_rl, n_reads, 0, 0, true};
+    out->rcm = (const uint32_t*)d_rcm;
+    return RB_OK;
+}
+extern "C" int32_t rb_graph_add_reads_ascii(rb_graph* g, const char* bases, const char* quals, const int64_t* ascii_off, int64_t n_reads,
+                                            int32_t min_qual, uint32_t flags, int64_t* n_kmers_out) {
+    if (!g || !bases || !ascii_off || n_reads < 0) return RB_EINVAL;
+    rb_ctx* ctx = g->ctx;
+    LOCK(ctx);
+    if (n_kmers_out) *n_kmers_out = 0;
+    if (n_reads == 0) return RB_OK;
+    ReadsArg ra{};
+    int32_t rc = ascii_pack(ctx, bases, quals, ascii_off, n_reads, min_qual, &ra);
+    if (rc) return rc;
+    rc = graph_add_reads(g, ra, flags, n_kmers_out);
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (!rc && e != cudaSuccess) rc = fail(ctx, RB_ECUDA, cudaGetErrorString(e));
     return rc;
-#undef CKF
+}
+
+// ---- f2: the reference's .2bit fragment records (stage-3 rebuild: FragmentsToGraphWorker, RNABloom.java:1489-1516 reads them with
+// io/NucleotideBitsReader.java:39-49) ------------------------------------------------------------------------------------------------------------
+// Host helpers: the codec itself (deterministic for ACGTU input; the reference writes a RANDOM base for anything else, SeqBitsUtils.java:138-156)
+extern "C" int64_t rb_2bit_record_bytes(int32_t seq_len) { return 4 + (int64_t)(seq_len / 4 + (seq_len % 4 ? 1 : 0)); }
+extern "C" int64_t rb_2bit_encode_records(const char* bases, const int64_t* ascii_off, int64_t n_reads, uint8_t* out) {
+    int64_t at = 0;
+    for (int64_t r = 0; r < n_reads; ++r) {
+        const int64_t a0 = ascii_off[r];
+        const int len = (int)(ascii_off[r + 1] - a0);
+        if (out) { out[at] = (uint8_t)(len >> 24); out[at + 1] = (uint8_t)(len >> 16); out[at + 2] = (uint8_t)(len >> 8); out[at + 3] = (uint8_t)len; }   // intToFourBytes :209
+        at += 4;
+        for (int i = 0; i < len; i += 4) {
+            int v = 0;
+            for (int j = 0; j < 4; ++j) {
+                int code = 0;   // bases past the end count as A (seqToBits :236-243)
+                if (i + j < len) {
+                    switch (bases[a0 + i + j]) {
+                        case 'C': case 'c': code = 1; break;
+                        case 'G': case 'g': code = 2; break;
+                        case 'T': case 't': case 'U': case 'u': code = 3; break;
+                        default: code = 0;
+                    }
+                }
+                v = v * 4 + code;
+            }
+            if (out) out[at] = (uint8_t)(v - 128);
+            ++at;
+        }
+    }
+    return at;
+}
+// number of complete records in `records` (n_bytes bytes); fills data_off / read_len when non-NULL (capacity max_reads).  -1: truncated stream
+extern "C" int64_t rb_2bit_index_records(const uint8_t* records, int64_t n_bytes, int64_t* data_off, int32_t* read_len, int64_t max_reads) {
+    int64_t at = 0, n = 0;
+    while (at < n_bytes) {
+        if (at + 4 > n_bytes) return -1;
+        const int64_t len = ((int64_t)records[at] << 24) | ((int64_t)records[at + 1] << 16) | ((int64_t)records[at + 2] << 8) | (int64_t)records[at + 3];   // fourBytesToInt :213
+        const int64_t nb = len / 4 + (len % 4 ? 1 : 0);
+        if (len < 0 || len > INT32_MAX || at + 4 + nb > n_bytes) return -1;
+        if (data_off && n < max_reads) { data_off[n] = at + 4; read_len[n] = (int32_t)len; }
+        at += 4 + nb;
+        ++n;
+    }
+    return n;
+}
+// graph.add & co. for a buffer of .2bit records in host memory: the tetramer bytes are re-packed on the GPU
+extern "C" int32_t rb_graph_add_reads_2bit(rb_graph* g, const uint8_t* records, int64_t n_bytes, uint32_t flags, int64_t* n_reads_out, int64_t* n_kmers_out) {
+    if (!g || (n_bytes > 0 && !records) || n_bytes < 0) return RB_EINVAL;
+    rb_ctx* ctx = g->ctx;
+    LOCK(ctx);
+    if (n_reads_out) *n_reads_out = 0;
+    if (n_kmers_out) *n_kmers_out = 0;
+    const int64_t n_reads = rb_2bit_index_records(records, n_bytes, nullptr, nullptr, 0);
+    if (n_reads < 0) return fail(ctx, RB_EINVAL, "2bit records: truncated or corrupt stream");
+    if (n_reads == 0) return RB_OK;
+    std::vector<int64_t> data_off((size_t)n_reads), word_off((size_t)n_reads + 1), read_off((size_t)n_reads);
+    std::vector<int32_t> read_len((size_t)n_reads);
+    rb_2bit_index_records(records, n_bytes, data_off.data(), read_len.data(), n_reads);
+    int64_t words = 0;
+    for (int64_t r = 0; r < n_reads; ++r) { word_off[(size_t)r] = words; read_off[(size_t)r] = words * 32; words += (read_len[(size_t)r] + 31) / 32; }
+    word_off[(size_t)n_reads] = words;
+    void *d_rec, *d_do, *d_wo, *d_ro, *d_rl, *d_packed;
+    int32_t rc;
+    if ((rc = stage_get(ctx, 16, n_bytes + 16, &d_rec)) || (rc = stage_get(ctx, 18, n_reads * 8, &d_do)) || (rc = stage_get(ctx, 19, (n_reads + 1) * 8, &d_wo)) ||
+        (rc = stage_get(ctx, 20, n_reads * 8, &d_ro)) || (rc = stage_get(ctx, 21, n_reads * 4, &d_rl)) || (rc = stage_get(ctx, 22, (words + 2) * 8, &d_packed))) return rc;
+    CK(cudaMemcpyAsync(d_rec, records, (size_t)n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_do, data_off.data(), (size_t)n_reads * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_wo, word_off.data(), (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_ro, read_off.data(), (size_t)n_reads * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_rl, read_len.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (words > 0) {
+        RB_LAUNCH((int)div_up(words, kThreads), kThreads, 0, ctx->stream, k_unpack_2bit)((const uint8_t*)d_rec, (const int64_t*)d_do, (const int32_t*)d_rl, (const int64_t*)d_wo,
+                                                                                  n_reads, words, (uint64_t*)d_packed);
+        LAUNCH_CHECK();
+    }
+    CK(cudaStreamSynchronize(ctx->stream));   // the host vectors go out of scope
+    ReadsArg ra{(const uint64_t*)d_packed, nullptr, (const int64_t*)d_ro, (const int32_t*)d_rl, n_reads, 0, 0, true};
+    rc = graph_add_reads(g, ra, flags, n_kmers_out);
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (!rc && e != cudaSuccess) rc = fail(ctx, RB_ECUDA, cudaGetErrorString(e));
+    if (!rc && n_reads_out) *n_reads_out = n_reads;
+    return rc;
 }
 
 struct CountUser { rb_graph* g; int mode; float* counts; int64_t *fh, *rh; bool on_device; };
@@ -1131,9 +1304,9 @@ static int32_t count_launch(rb_ctx* ctx, const Ingest& ing_in, void* user) {
     }
     return RB_OK;
 }
-static int32_t graph_count_reads(rb_graph* g, const ReadsArg& ra, float* counts, int64_t* fh, int64_t* rh, int64_t* n_out) {
-    CountUser u{g, g->stranded ? RB_MODE_FWD : RB_MODE_CANON, counts, fh, g->stranded ? nullptr : rh, ra.on_device};
-    RoundSize rs(g, !ra.on_device);
+static int32_t graph_count_reads(rb_graph* g, const ReadsArg& ra, float* counts, int64_t* fh, int64_t* rh, int64_t* n_out, bool results_on_device) {
+    CountUser u{g, g->stranded ? RB_MODE_FWD : RB_MODE_CANON, counts, fh, g->stranded ? nullptr : rh, results_on_device};
+    RoundSize rs(g, !results_on_device);
     return for_each_launch(g->ctx, ra, g->k, count_launch, &u, n_out);
 }
 extern "C" int32_t rb_graph_count_reads(rb_graph* g, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
@@ -1143,7 +1316,7 @@ extern "C" int32_t rb_graph_count_reads(rb_graph* g, const uint64_t* packed, con
     rb_ctx* ctx = g->ctx;
     LOCK(ctx);
     ReadsArg ra{packed, mask, read_off, read_len, n_reads, uniform_len, uniform_stride, false};
-    const int32_t rc = graph_count_reads(g, ra, counts, fhash, rhash, n_kmers_out);
+    const int32_t rc = graph_count_reads(g, ra, counts, fhash, rhash, n_kmers_out, false);
     if (rc) { cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->copy_stream); return rc; }
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->copy_stream));
@@ -1155,7 +1328,36 @@ extern "C" int32_t rb_graph_count_reads_dev(rb_graph* g, const uint64_t* packed,
     if (!g) return RB_EINVAL;
     LOCK(g->ctx);
     ReadsArg ra{packed, mask, read_off, read_len, n_reads, uniform_len, uniform_stride, true};
-    return graph_count_reads(g, ra, counts, fhash, rhash, n_kmers_out);
+    return graph_count_reads(g, ra, counts, fhash, rhash, n_kmers_out, true);
+}
+// graph.getKmers(String) for a chunk of sequences (graph :1224-1234; bloom/hash/HashFunction.java:55-85): counts and hashes of every
+// k-mer window; windows over a non-ACGTU character get count 0 but are still hashed through exactly as NTHash does (forward row 0,
+// reverse row c & 0x07).  Results in host memory.
+extern "C" int32_t rb_graph_count_reads_ascii(rb_graph* g, const char* bases, const int64_t* ascii_off, int64_t n_reads, float* counts, int64_t* fhash,
+                                              int64_t* rhash, int64_t* n_kmers_out) {
+    if (!g || !bases || !ascii_off || n_reads < 0) return RB_EINVAL;
+    rb_ctx* ctx = g->ctx;
+    LOCK(ctx);
+    if (n_kmers_out) *n_kmers_out = 0;
+    if (n_reads == 0) return RB_OK;
+    ReadsArg ra{};
+    int32_t rc = ascii_pack(ctx, bases, nullptr, ascii_off, n_reads, 0, &ra);
+    if (!rc) rc = graph_count_reads(g, ra, counts, fhash, rhash, n_kmers_out, false);
+    const cudaError_t e1 = cudaStreamSynchronize(ctx->stream), e2 = cudaStreamSynchronize(ctx->copy_stream);
+    if (!rc && (e1 != cudaSuccess || e2 != cudaSuccess)) rc = fail(ctx, RB_ECUDA, cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    return rc;
+}
+// NTHashIterator / ReverseComplement... / Canonical... over ASCII sequences: hashes of every window, bit-exact for EVERY byte value
+extern "C" int32_t rb_kmerize_ascii(rb_ctx* ctx, const char* bases, const int64_t* ascii_off, int64_t n_reads, int32_t k, int32_t mode, int64_t* fhash,
+                                    int64_t* rhash, int64_t* base) {
+    if (!ctx || !bases || !ascii_off || n_reads < 0 || k < 1 || mode < 0 || mode > 2) return RB_EINVAL;
+    LOCK(ctx);
+    if (n_reads == 0) return RB_OK;
+    ReadsArg ra{};
+    const int32_t rc = ascii_pack(ctx, bases, nullptr, ascii_off, n_reads, 0, &ra);
+    if (rc) return rc;
+    KmerizeUser u{k, mode, 0, nullptr, nullptr, nullptr, fhash, rhash, base, false};
+    return for_each_launch(ctx, ra, k, kmerize_launch, &u, nullptr);
 }
 extern "C" int32_t rb_graph_add_hashes(rb_graph* g, const int64_t* base, int64_t n, uint32_t flags) {
     if (!g) return RB_EINVAL;
@@ -1215,6 +1417,100 @@ extern "C" int32_t rb_graph_neighbor_counts(rb_graph* g, const int64_t* fhash, c
         CK(cudaMemcpyAsync(counts + i0 * 8, dc, (size_t)m * 32, cudaMemcpyDeviceToHost, ctx->stream));
         if (dnf) CK(cudaMemcpyAsync(nbr_fhash + i0 * 8, dnf, (size_t)m * 64, cudaMemcpyDeviceToHost, ctx->stream));
         if (dnr) CK(cudaMemcpyAsync(nbr_rhash + i0 * 8, dnr, (size_t)m * 64, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return RB_OK;
+}
+
+// variants of the first / last base (graph/Kmer.java:357-405): out arrays [n][2][4] -- per k-mer the 4 left variants (A,C,G,T at position 0) then
+// the 4 right variants (position k-1); the entry of the k-mer's own base is the k-mer itself
+extern "C" int32_t rb_graph_variant_counts(rb_graph* g, const int64_t* fhash, const int64_t* rhash, const uint8_t* first_base, const uint8_t* last_base,
+                                           int64_t n, float* counts, int64_t* var_fhash, int64_t* var_rhash) {
+    if (!g || n < 0 || (n > 0 && (!fhash || !first_base || !last_base || !counts))) return RB_EINVAL;
+    rb_ctx* ctx = g->ctx;
+    LOCK(ctx);
+    const int canonical = g->stranded ? 0 : 1;
+    if (canonical && n > 0 && !rhash) return fail(ctx, RB_EINVAL, "variants of canonical k-mers need the reverse-strand hashes");
+    const GraphDev gd = graph_view(g);
+    const int64_t step = std::max<int64_t>(1024, ctx->subbatch_kmers / 8);
+    for (int64_t i0 = 0; i0 < n; i0 += step) {
+        const int64_t m = std::min(step, n - i0);
+        void *df, *dr = nullptr, *d1, *d2, *dc, *dnf = nullptr, *dnr = nullptr;
+        int32_t rc = stage_get(ctx, 0, m * 8, &df); if (rc) return rc;
+        if (canonical) { rc = stage_get(ctx, 1, m * 8, &dr); if (rc) return rc; }
+        rc = stage_get(ctx, 2, m, &d1); if (rc) return rc;
+        rc = stage_get(ctx, 3, m, &d2); if (rc) return rc;
+        rc = stage_get(ctx, 5, m * 32, &dc); if (rc) return rc;
+        if (var_fhash) { rc = stage_get(ctx, 6, m * 64, &dnf); if (rc) return rc; }
+        if (var_rhash && canonical) { rc = stage_get(ctx, 7, m * 64, &dnr); if (rc) return rc; }
+        CK(cudaMemcpyAsync(df, fhash + i0, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (canonical) CK(cudaMemcpyAsync(dr, rhash + i0, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d1, first_base + i0, (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d2, last_base + i0, (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        const int grid = (int)div_up(2 * m, kThreads);
+        PROF("k_variants");
+        if (g->hmax <= 3) RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_variants<3>)((const int64_t*)df, (const int64_t*)dr, (const uint8_t*)d1, (const uint8_t*)d2, m, gd, canonical, (float*)dc, (int64_t*)dnf, (int64_t*)dnr);
+        else RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_variants<8>)((const int64_t*)df, (const int64_t*)dr, (const uint8_t*)d1, (const uint8_t*)d2, m, gd, canonical, (float*)dc, (int64_t*)dnf, (int64_t*)dnr);
+        LAUNCH_CHECK();
+        CK(cudaMemcpyAsync(counts + i0 * 8, dc, (size_t)m * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        if (dnf) CK(cudaMemcpyAsync(var_fhash + i0 * 8, dnf, (size_t)m * 64, cudaMemcpyDeviceToHost, ctx->stream));
+        if (dnr) CK(cudaMemcpyAsync(var_rhash + i0 * 8, dnr, (size_t)m * 64, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return RB_OK;
+}
+// Kmer.getMaxCovSuccessor / getMaxCovPredecessor (graph/Kmer.java:301-355) for a batch: best[n][2] = base code (0..3) of the successor /
+// predecessor with the largest count >= min_cov, the first of equal ones in A, C, G, T order; -1 if there is none.  best_count[n][2] likewise.
+extern "C" int32_t rb_graph_max_cov_neighbors(rb_graph* g, const int64_t* fhash, const int64_t* rhash, const uint8_t* first_base, const uint8_t* last_base,
+                                              int64_t n, float min_cov, int8_t* best, float* best_count, int64_t* best_fhash, int64_t* best_rhash) {
+    if (!g || n < 0 || (n > 0 && !best)) return RB_EINVAL;
+    std::vector<float> counts((size_t)n * 8);
+    std::vector<int64_t> nf((size_t)(best_fhash ? n * 8 : 0)), nr((size_t)(best_rhash ? n * 8 : 0));
+    const int32_t rc = rb_graph_neighbor_counts(g, fhash, rhash, first_base, last_base, n, counts.data(), best_fhash ? nf.data() : nullptr,
+                                                best_rhash ? nr.data() : nullptr);
+    if (rc) return rc;
+    for (int64_t i = 0; i < n * 2; ++i) {
+        float bc = -1.f; int b = -1;
+        for (int c = 0; c < 4; ++c) { const float v = counts[(size_t)i * 4 + c]; if (v >= min_cov && v > bc) { bc = v; b = c; } }   // :312-317
+        best[i] = (int8_t)b;
+        if (best_count) best_count[i] = b < 0 ? 0.f : bc;
+        if (best_fhash) best_fhash[i] = b < 0 ? 0 : nf[(size_t)i * 4 + b];
+        if (best_rhash) best_rhash[i] = b < 0 ? 0 : (g->stranded ? 0 : nr[(size_t)i * 4 + b]);
+    }
+    return RB_OK;
+}
+// GraphUtils.greedyExtendRight / greedyExtendLeft with lookahead <= 1 for a batch of start k-mers (util/GraphUtils.java:1961-1976): kmer_bits =
+// 2 x uint64 per k-mer (2-bit codes, base i at bits 2 * (i & 31) of word i >> 5), k <= 64.  ext_codes[n][bound] receives the added bases in
+// walking order (to the left: the bases as they are prepended), ext_len[n] how many.
+extern "C" int32_t rb_graph_greedy_extend(rb_graph* g, const uint64_t* kmer_bits, const int64_t* fhash, const int64_t* rhash, int64_t n, int32_t right,
+                                          int32_t bound, float min_cov, int32_t* ext_len, uint8_t* ext_codes, float* ext_counts) {
+    if (!g || n < 0 || bound < 1 || (n > 0 && (!kmer_bits || !fhash || !ext_len || !ext_codes))) return RB_EINVAL;
+    rb_ctx* ctx = g->ctx;
+    LOCK(ctx);
+    if (g->k > 64) return fail(ctx, RB_EINVAL, "greedy extension carries the k-mer in 128 bits: k <= 64");
+    const int canonical = g->stranded ? 0 : 1;
+    if (canonical && n > 0 && !rhash) return fail(ctx, RB_EINVAL, "canonical k-mers need the reverse-strand hashes");
+    const GraphDev gd = graph_view(g);
+    const int64_t step = std::max<int64_t>(1024, std::min<int64_t>(1 << 22, (1LL << 30) / bound));
+    for (int64_t i0 = 0; i0 < n; i0 += step) {
+        const int64_t m = std::min(step, n - i0);
+        void *dk, *df, *dr = nullptr, *dl, *dc, *dn = nullptr;
+        int32_t rc;
+        if ((rc = stage_get(ctx, 0, m * 16, &dk)) || (rc = stage_get(ctx, 1, m * 8, &df)) || (rc = stage_get(ctx, 3, m * 4, &dl)) ||
+            (rc = stage_get(ctx, 5, m * bound, &dc))) return rc;
+        if (canonical && (rc = stage_get(ctx, 2, m * 8, &dr))) return rc;
+        if (ext_counts && (rc = stage_get(ctx, 6, m * bound * 4, &dn))) return rc;
+        CK(cudaMemcpyAsync(dk, kmer_bits + 2 * i0, (size_t)m * 16, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(df, fhash + i0, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (canonical) CK(cudaMemcpyAsync(dr, rhash + i0, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+        const int grid = (int)div_up(m, kThreads);
+        PROF("k_greedy_extend");
+        if (g->hmax <= 3) RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_greedy_extend<3>)((const uint64_t*)dk, (const int64_t*)df, (const int64_t*)dr, m, gd, canonical, right ? 1 : 0, bound, min_cov, (int32_t*)dl, (uint8_t*)dc, (float*)dn);
+        else RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_greedy_extend<8>)((const uint64_t*)dk, (const int64_t*)df, (const int64_t*)dr, m, gd, canonical, right ? 1 : 0, bound, min_cov, (int32_t*)dl, (uint8_t*)dc, (float*)dn);
+        LAUNCH_CHECK();
+        CK(cudaMemcpyAsync(ext_len + i0, dl, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ext_codes + i0 * bound, dc, (size_t)m * bound, cudaMemcpyDeviceToHost, ctx->stream));
+        if (ext_counts) CK(cudaMemcpyAsync(ext_counts + i0 * bound, dn, (size_t)m * bound * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
     return RB_OK;

@@ -114,10 +114,35 @@ class Context:
         self.check(self.L.rb_kmerize(self.h, *reads.args(), k, mode, _ptr(f), _ptr(r), _ptr(b)))
         return f, r, b
 
+    def kmerize_ascii(self, seqs, k, mode):
+        """The same over ASCII sequences, bit-exact for every byte value (IUPAC codes contribute their c & 0x07 row on the reverse strand)."""
+        bases, off, n_reads = _ascii_chunk(seqs)
+        n = int(np.maximum(np.diff(off) - k + 1, 0).sum())
+        f, r, b = (np.zeros(n, dtype=np.int64) for _ in range(3))
+        self.check(self.L.rb_kmerize_ascii(self.h, _ptr(bases), _ptr(off), n_reads, k, mode, _ptr(f), _ptr(r), _ptr(b)))
+        return f, r, b
+
     def kmerize_pairs(self, reads, k, d, mode):
         p = np.zeros(reads.n_positions(k + d), dtype=np.int64)
         self.check(self.L.rb_kmerize_pairs(self.h, *reads.args(), k, d, mode, _ptr(p)))
         return p
+
+
+def encode_2bit_records(seqs):
+    """ASCII sequences -> the reference's .2bit record stream (util/SeqBitsUtils.java:218-247 + 4-byte big-endian lengths)."""
+    bases, off, n = _ascii_chunk(seqs)
+    L = B.lib()
+    size = L.rb_2bit_encode_records(_ptr(bases), _ptr(off), n, None)
+    out = np.zeros(size, dtype=np.uint8)
+    L.rb_2bit_encode_records(_ptr(bases), _ptr(off), n, _ptr(out))
+    return out
+
+
+def _ascii_chunk(seqs):
+    bs = [s.encode("latin-1") if isinstance(s, str) else bytes(s) for s in seqs]
+    off = np.zeros(len(bs) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(b) for b in bs])
+    return np.frombuffer(b"".join(bs) + b"\0", dtype=np.uint8), off, len(bs)
 
 
 class PackedReads:
@@ -272,6 +297,48 @@ class BloomFilter(_Filter):
         return B.lib().rb_expected_size(expNumElements, fpr, numHash)
 
 
+class CascadingBloomFilter:
+    """bloom/CascadingBloomFilter.java: numLevels Bloom filters of size / numLevels bits; add walks the levels with lookupThenAdd."""
+
+    def __init__(self, ctx, size, numHash, k, numLevels):
+        self.ctx, self.numLevels = ctx, numLevels
+        h = C.c_void_p()
+        ctx.check(ctx.L.rb_cascade_create(ctx.h, size, numHash, k, numLevels, C.byref(h)))
+        self.h = h
+
+    def destroy(self):
+        if self.h:
+            self.ctx.check(self.ctx.L.rb_cascade_destroy(self.h))
+            self.h = None
+
+    def getNumLevels(self):
+        return self.numLevels
+
+    def getBloomFilter(self, level):
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.L.rb_cascade_level(self.h, level, C.byref(h)))
+        return BloomFilter(self.ctx, 0, 0, 0, _handle=h)
+
+    def add(self, hashVals):
+        a = _hashes(hashVals)
+        self.ctx.check(self.ctx.L.rb_cascade_add_hashes(self.h, _ptr(a), len(a)))
+
+    def lookup(self, hashVals):
+        a = _hashes(hashVals)
+        out = np.zeros(len(a), dtype=np.uint8)
+        self.ctx.check(self.ctx.L.rb_cascade_lookup_hashes(self.h, _ptr(a), len(a), _ptr(out)))
+        return out.astype(bool)
+
+    def lookupThenAdd(self, hashVals):
+        a = _hashes(hashVals)
+        out = np.zeros(len(a), dtype=np.uint8)
+        self.ctx.check(self.ctx.L.rb_cascade_lookup_then_add_hashes(self.h, _ptr(a), len(a), _ptr(out)))
+        return out.astype(bool)
+
+    def getFPR(self, level=None):
+        return self.getBloomFilter(self.numLevels - 1 if level is None else level).getFPR()
+
+
 class CountingBloomFilter(_Filter):
     """bloom/CountingBloomFilter.java"""
 
@@ -395,6 +462,24 @@ class BloomFilterDeBruijnGraph:
         self.ctx.check(self.ctx.L.rb_graph_add_reads_ascii(self.h, _ptr(bases), _ptr(q), _ptr(off), len(bs), minQual, flags, C.byref(n)))
         return n.value
 
+    def addReads2bit(self, records, flags=0):
+        """A buffer of the reference's .2bit fragment records (io/NucleotideBitsWriter.java:24-31): returns (reads, k-mers) inserted."""
+        rec = np.ascontiguousarray(records, dtype=np.uint8)
+        nr, nk = C.c_int64(), C.c_int64()
+        self.ctx.check(self.ctx.L.rb_graph_add_reads_2bit(self.h, _ptr(rec), rec.nbytes, flags, C.byref(nr), C.byref(nk)))
+        return nr.value, nk.value
+
+    def getKmersAscii(self, seqs):
+        """graph.getKmers(String) for a chunk of sequences (graph :1224-1234): (counts, fHashVals, rHashVals) of every k-mer window."""
+        bases, off, n_reads = _ascii_chunk(seqs)
+        n = int(np.maximum(np.diff(off) - self.k + 1, 0).sum())
+        counts = np.zeros(n, dtype=np.float32)
+        f, r = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64)
+        got = C.c_int64()
+        self.ctx.check(self.ctx.L.rb_graph_count_reads_ascii(self.h, _ptr(bases), _ptr(off), n_reads, _ptr(counts), _ptr(f), _ptr(r), C.byref(got)))
+        assert got.value == n
+        return counts, f, r
+
     def addReadsDev(self, packed_dev, n_reads, uniform_len, uniform_stride, flags=0):
         n = C.c_int64()
         self.ctx.check(self.ctx.L.rb_graph_add_reads_dev(self.h, packed_dev, None, None, None, n_reads, uniform_len, uniform_stride, flags,
@@ -452,6 +537,56 @@ class BloomFilterDeBruijnGraph:
         nr = np.zeros((n, 2, 4), dtype=np.int64) if with_hashes and not self.stranded else None
         self.ctx.check(self.ctx.L.rb_graph_neighbor_counts(self.h, _ptr(f), _ptr(r), _ptr(b0), _ptr(b1), n, _ptr(counts), _ptr(nf), _ptr(nr)))
         return counts, nf, nr
+
+    def getVariantCounts(self, fHashVals, rHashVals, firstBases, lastBases, with_hashes=True):
+        """Batched Kmer.getLeftVariants / getRightVariants (graph/Kmer.java:357-405): counts[n, 2, 4] of the k-mers with base A, C, G, T in
+        the first (index 0) / last (index 1) position; the entry of the k-mer's own base is the k-mer itself."""
+        f = _hashes(fHashVals)
+        r = None if rHashVals is None else _hashes(rHashVals)
+        b0 = np.ascontiguousarray(firstBases, dtype=np.uint8)
+        b1 = np.ascontiguousarray(lastBases, dtype=np.uint8)
+        n = f.size
+        counts = np.zeros((n, 2, 4), dtype=np.float32)
+        vf = np.zeros((n, 2, 4), dtype=np.int64) if with_hashes else None
+        vr = np.zeros((n, 2, 4), dtype=np.int64) if with_hashes and not self.stranded else None
+        self.ctx.check(self.ctx.L.rb_graph_variant_counts(self.h, _ptr(f), _ptr(r), _ptr(b0), _ptr(b1), n, _ptr(counts), _ptr(vf), _ptr(vr)))
+        return counts, vf, vr
+
+    def getMaxCovNeighbors(self, fHashVals, rHashVals, firstBases, lastBases, minKmerCov=1.0):
+        """Batched Kmer.getMaxCovSuccessor / getMaxCovPredecessor (graph/Kmer.java:301-355): (best base code or -1, its count), each [n, 2]."""
+        f = _hashes(fHashVals)
+        r = None if rHashVals is None else _hashes(rHashVals)
+        b0 = np.ascontiguousarray(firstBases, dtype=np.uint8)
+        b1 = np.ascontiguousarray(lastBases, dtype=np.uint8)
+        n = f.size
+        best = np.zeros((n, 2), dtype=np.int8)
+        cnt = np.zeros((n, 2), dtype=np.float32)
+        self.ctx.check(self.ctx.L.rb_graph_max_cov_neighbors(self.h, _ptr(f), _ptr(r), _ptr(b0), _ptr(b1), n, minKmerCov, _ptr(best), _ptr(cnt), None, None))
+        return best, cnt
+
+    def greedyExtend(self, kmers, right=True, bound=100, minKmerCov=1.0):
+        """Batched GraphUtils.greedyExtendRight / greedyExtendLeft with lookahead <= 1 (util/GraphUtils.java:1961-1976): list of ASCII k-mers ->
+        list of extension strings (to the left: in genome order, i.e. the prepended bases reversed)."""
+        k = self.k
+        code = np.full(256, 0, dtype=np.uint64)
+        for ch, v in zip("ACGTUacgtu", (0, 1, 2, 3, 3, 0, 1, 2, 3, 3)):
+            code[ord(ch)] = v
+        n = len(kmers)
+        arr = code[np.frombuffer("".join(kmers).encode(), dtype=np.uint8).reshape(n, k)]
+        bits = np.zeros((n, 2), dtype=np.uint64)
+        for i in range(k):
+            bits[:, i >> 5] |= arr[:, i] << np.uint64(2 * (i & 31))
+        f, r, _ = self.ctx.kmerize_ascii(kmers, k, B.MODE_CANON)
+        ext_len = np.zeros(n, dtype=np.int32)
+        ext = np.zeros((n, bound), dtype=np.uint8)
+        self.ctx.check(self.ctx.L.rb_graph_greedy_extend(self.h, _ptr(np.ascontiguousarray(bits)), _ptr(f), _ptr(r), n, int(right), bound, minKmerCov,
+                                                         _ptr(ext_len), _ptr(ext), None))
+        nt = np.frombuffer(b"ACGT", dtype=np.uint8)
+        out = []
+        for i in range(n):
+            s_ = bytes(nt[ext[i, :ext_len[i]]]).decode()
+            out.append(s_ if right else s_[::-1])
+        return out
 
     def addReadSingleKmerPair(self, pairHashVals):
         a = _hashes(pairHashVals)

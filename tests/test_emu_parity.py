@@ -55,10 +55,12 @@ SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_
 SPILL_ENV = {"RB_SLICED_SPILL": "1", "RB_SLICED_SUBCAP": "40", "RB_SLICED_KEYCAP": "1500"}
 ONLY = {
     "sliced-small-spill": ("test_duplicates_inside_one_batch_are_linearised", "test_skewed_batch_is_redone_by_the_direct_engine"),
-    "direct": ("test_getkmers_with_invalid_nucleotides", "test_neighbor_counts_match_oracle"),
+    "direct": ("test_getkmers_with_invalid_nucleotides", "test_neighbor_counts_match_oracle", "test_kmerize_ascii_is_exact_for_every_character",
+               "test_cascading_bloom_filter_matches_oracle", "test_loaded_cbf_envelope_at_scale", "test_2bit_fragment_records_round_trip",
+               "test_variants_max_cov_and_greedy_extension_match_oracle", "test_stage1_driver_writes_the_reference_files"),
     "sliced-default": ("test_getkmers_with_invalid_nucleotides", "test_insert_policies_and_pair_filters", "test_kernels_are_race_free_under_tsan",
                        "test_random_geometry_matches_oracle", "test_random_uniform_layout_matches_oracle", "test_paired_slices_match_oracle",
-                       "test_config3_settings_match_oracle", "test_config4_long_reads_match_oracle"),
+                       "test_config3_settings_match_oracle", "test_config4_long_reads_match_oracle", "test_loaded_cbf_envelope_at_scale"),
 }
 SKIP = {"sliced-small": ("test_kernels_are_race_free_under_tsan", "test_neighbor_counts_match_oracle", "test_random_geometry_matches_oracle",
                          "test_random_uniform_layout_matches_oracle"),
@@ -89,6 +91,15 @@ def engine(request):
 
 test_duplicates_inside_one_batch_are_linearised = G.test_duplicates_inside_one_batch_are_linearised
 test_getkmers_with_invalid_nucleotides = G.test_getkmers_with_invalid_nucleotides
+test_kmerize_ascii_is_exact_for_every_character = G.test_kmerize_ascii_is_exact_for_every_character
+test_cascading_bloom_filter_matches_oracle = G.test_cascading_bloom_filter_matches_oracle
+test_2bit_fragment_records_round_trip = G.test_2bit_fragment_records_round_trip
+test_stage1_driver_writes_the_reference_files = G.test_stage1_driver_writes_the_reference_files
+
+
+@pytest.mark.parametrize("stranded,k", [(False, 25), (True, 31), (False, 64)])
+def test_variants_max_cov_and_greedy_extension_match_oracle(ctx, orc, stranded, k):
+    G.test_variants_max_cov_and_greedy_extension_match_oracle(ctx, orc, stranded, k)
 test_insert_policies_and_pair_filters = G.test_insert_policies_and_pair_filters
 test_neighbor_counts_match_oracle = G.test_neighbor_counts_match_oracle
 
@@ -102,8 +113,14 @@ def test_paired_slices_match_oracle(ctx, orc, stranded, k, hd, hc, dbg_bits, cbf
     G.test_paired_slices_match_oracle(ctx, orc, stranded, k, hd, hc, dbg_bits, cbf_bytes, layout)
 
 
+def test_loaded_cbf_envelope_at_scale(ctx, orc, monkeypatch):
+    monkeypatch.setattr(G, "N_ENVELOPE_READS", 1500)
+    G.test_loaded_cbf_envelope_at_scale(ctx, orc)
+
+
 def test_config3_settings_match_oracle(ctx, orc, monkeypatch):
     monkeypatch.setattr(G, "N_CFG3_READS", 1200)
+    monkeypatch.setattr(G, "CFG3_SIZES", (1 << 27, 1 << 24, 1 << 24))
     G.test_config3_settings_match_oracle(ctx, orc)
 
 
@@ -166,6 +183,7 @@ def test_random_geometry_matches_oracle(ctx, orc, seed, monkeypatch):
         cbf_bytes = 1 << int(rng.integers(20, 23))
         dbg_bits = cbf_bytes * int(rng.integers(1, 17))
         monkeypatch.setenv("RB_SLICE_PAIR_LOG2", str(int(rng.integers(8, 19))))
+        monkeypatch.setenv("RB_SLICE_REGION_TARGET", str(int(rng.choice([2, 8, 64, 512]))))   # wide regions consumed in several passes
     for name, lo, hi in (("RB_SLICE_BITS_LOG2", 12, 22), ("RB_SLICE_BYTES_LOG2", 10, 20), ("RB_SLICE_RAISE_LOG2", 8, 18),
                          ("RB_SLICED_SUBRANGE_LOG2", 4, 9)):
         monkeypatch.setenv(name, str(int(rng.integers(lo, hi + 1))))

@@ -82,7 +82,7 @@ def _worker(rank, world, port, stranded, out, cfg=None):
 
 # paired: cbf_bytes = 2^c dividing dbg_bits and h_d >= h_c -> one probe record per hash, a rank owns paired slices (its bits are a
 # range inside every chunk of cbf_bytes bits: gather_filter reassembles them)
-PAIRED = {"dbg_bits": 5 << 22, "cbf_bytes": 1 << 22, "hd": 3, "hc": 3, "env": {"RB_SLICE_PAIR_LOG2": "13"}}
+PAIRED = {"dbg_bits": 5 << 22, "cbf_bytes": 1 << 22, "hd": 3, "hc": 3, "env": {"RB_SLICE_PAIR_LOG2": "13", "RB_SLICE_REGION_TARGET": "64"}}
 
 
 @pytest.mark.parametrize("world,stranded,paired", [(2, False, False), (2, True, False), (4, False, False), (8, False, False), (2, False, True),
