@@ -176,13 +176,21 @@ RB_API int32_t rb_graph_init_fpkbf(rb_graph* g, int64_t pkbf_bits, int32_t pkbf_
 RB_API int32_t rb_graph_set_distances(rb_graph* g, int32_t d_read, int32_t d_frag);
 RB_API int32_t rb_graph_filter(rb_graph* g, int32_t which, rb_filter** out); /* borrowed handle; NULL if absent */
 RB_API int32_t rb_graph_clear(rb_graph* g);
-/* Execution engine of the read-level insert/lookup calls (same results, different HBM schedule):
- *   RB_ENGINE_DIRECT  one fused kernel, every probe an isolated random HBM access (one DRAM line request per probe)
+/* Execution engine of the read-level insert/lookup calls (different HBM schedule; DESIGN.md sections 3 and 4):
+ *   RB_ENGINE_DIRECT  one fused kernel, every probe an isolated random HBM access (one DRAM line request per probe); counter updates are
+ *                     linearisable per k-mer instance
  *   RB_ENGINE_SLICED  probes tile-sorted by 64 MiB filter slice, applied slice by slice out of L2, answers picked up per tile;
- *                     rounds of up to 2^29 k-mers.  Needs numHash(dbgbf) <= 3 and numHash(cbf) <= 3 and un-skewed hashes; a
- *                     round it cannot take is done by the direct engine (before anything was modified)
+ *                     rounds of up to 2^29 k-mers.  Needs numHash(dbgbf) <= 3 and numHash(cbf) <= 3; heavy hitters (one k-mer with
+ *                     thousands of copies in a round) take a spill path, a round beyond even that is done by the direct engine (before
+ *                     anything was modified)
  *   RB_ENGINE_AUTO    (default) sliced for rounds of at least 2^20 k-mers, direct below
- * The environment variable RB_ENGINE = direct | sliced | auto sets the engine of graphs created afterwards. */
+ * Results: the bit filters (dbgbf, rpkbf, fpkbf) are byte-identical for either engine, any round size and any GPU count.  The counting filter
+ * is byte-identical to the sequential reference wherever no two distinct k-mers share a counter.  Where they do, the sliced engine has
+ * SNAPSHOT-PER-ROUND semantics: duplicates of one k-mer inside a round are aggregated exactly (m copies = m-1 or m increments), but two
+ * different k-mers of the same round that share a counter both start from the counter's value at the start of the round and the larger
+ * result is kept, so such a counter can end one increment below any serial order (measured: ~1e-4 of the counters at 30 % occupancy).
+ * The result therefore depends (only on such counters) on the engine and on the round size.
+ * The environment variable RB_ENGINE = direct | sliced | auto sets the engine of graphs created afterwards (and of graphs loaded from files). */
 enum { RB_ENGINE_DIRECT = 0, RB_ENGINE_SLICED = 2, RB_ENGINE_AUTO = 3 };
 RB_API int32_t rb_graph_set_engine(rb_graph* g, int32_t engine);                                 /* clearDbgbf/Cbf/Rpkbf/Fpkbf :211-245 */
 
