@@ -253,30 +253,53 @@ def main():
     e2e = None
     if not args.no_e2e:
         e_steps = max(2, min(args.steps, 5))
-        h_packed = [ctx.host_alloc(words * 8, np.uint64) for _ in range(e_steps + 1)]
+        h_packed = [ctx.host_alloc(words * 8, np.uint64) for _ in range(e_steps + 4)]   # 1 + 2 for the blocking calls, 1 + e_steps pipelined
         tmp = ctx.dev_alloc(words * 8 + 64)
         for i, hp in enumerate(h_packed):   # fresh reads (ids after the timed ones), generated on the device, parked in pinned host memory
             ctx.synth_reads_dev(SEED, args.genome, (total_steps + i) * n_reads, n_reads, READ_LEN, ERR_PPM, STRIDE, tmp)
             ctx.sync()
             ctx.d2h(hp, tmp)
         ctx.dev_free(tmp)
-        h_counts = ctx.host_alloc(nk * 4, np.float32)
+        h_counts = [ctx.host_alloc(nk * 4, np.float32) for _ in range(2)]
         reads = [rb.PackedReads(hp, None, None, None, n_reads, READ_LEN, STRIDE) for hp in h_packed]
         from rnabloom_b200.filters import _ptr
         import ctypes as C
 
+        # (a) every call waits for its results: rb_graph_add_reads + rb_graph_count_reads
         def e2e_step(pr):
             n = C.c_int64()
             ctx.check(ctx.L.rb_graph_add_reads(g.h, *pr.args(), 0, C.byref(n)))
-            ctx.check(ctx.L.rb_graph_count_reads(g.h, *pr.args(), _ptr(h_counts), None, None, C.byref(n)))
-            return float(h_counts[:1024].sum())
+            ctx.check(ctx.L.rb_graph_count_reads(g.h, *pr.args(), _ptr(h_counts[0]), None, None, C.byref(n)))
+            return float(h_counts[0][:1024].sum())
         e2e_step(reads[0])
         t0 = time.perf_counter()
-        for i in range(1, e_steps + 1):
+        for i in range(1, 3):
             e2e_step(reads[i])
+        te_sync = (time.perf_counter() - t0) / 2
+
+        # (b) the headline: the same work with rb_graph_count_reads_async -- the D2H of step i's counts (4 B per k-mer: 2 GB) runs behind
+        # the insert of step i + 1; two pinned result arrays used alternately; every step's result is read on the host after its ticket
+        def e2e_pipelined(idx):
+            n = C.c_int64()
+            prev, acc = None, 0.0
+            for i in idx:
+                ctx.check(ctx.L.rb_graph_add_reads(g.h, *reads[i].args(), 0, C.byref(n)))
+                t = g.getKmersAsync(reads[i], h_counts[i & 1])
+                if prev is not None:
+                    ctx.wait(prev[0])
+                    acc += float(prev[1][:1024].sum())
+                prev = (t, h_counts[i & 1])
+            ctx.wait(prev[0])
+            return acc + float(prev[1][:1024].sum())
+        e2e_pipelined([3])
+        t0 = time.perf_counter()
+        chk = e2e_pipelined(list(range(4, e_steps + 4)))
         te = time.perf_counter() - t0
+        assert chk >= 1024.0 * e_steps   # every k-mer of a step was inserted before it was looked up: count >= 1
         e2e = {"value": nk * e_steps / te, "unit": "k-mers/s", "h2d_bytes_per_step": 2 * words * 8, "d2h_bytes_per_step": nk * 4,
-               "steps": e_steps, "ms_per_step": 1e3 * te / e_steps}
+               "steps": e_steps, "ms_per_step": 1e3 * te / e_steps,
+               "calls": "rb_graph_add_reads + rb_graph_count_reads_async / rb_ctx_wait (pinned host buffers, results double-buffered)",
+               "blocking_calls": {"value": nk / te_sync, "ms_per_step": 1e3 * te_sync, "calls": "rb_graph_add_reads + rb_graph_count_reads"}}
 
         # the same through the ASCII entry points -- what the Java insert workers and graph.getKmers(String) call (RNABloom.java:551-634,
         # graph :1224-1234): ASCII bases in host memory in, segmentation + 2-bit packing on the GPU, counts back to host memory
@@ -284,12 +307,13 @@ def main():
         w_a = n_a * STRIDE // 32
         pk = np.zeros(w_a, dtype=np.uint64)
         tmp = ctx.dev_alloc(w_a * 8 + 64)
-        ctx.synth_reads_dev(SEED, args.genome, (total_steps + e_steps + 2) * n_reads, n_a, READ_LEN, ERR_PPM, STRIDE, tmp)
+        ctx.synth_reads_dev(SEED, args.genome, (total_steps + e_steps + 5) * n_reads, n_a, READ_LEN, ERR_PPM, STRIDE, tmp)
         ctx.sync()
         ctx.d2h(pk, tmp)
         ctx.dev_free(tmp)
         codes = ((pk[:, None] >> (2 * np.arange(32, dtype=np.uint64))[None, :]) & np.uint64(3)).astype(np.uint8).reshape(n_a, STRIDE)[:, :READ_LEN]
-        ascii_bases = np.ascontiguousarray(np.frombuffer(b"ACGT", dtype=np.uint8)[codes]).reshape(-1)
+        ascii_bases = ctx.host_alloc(n_a * READ_LEN, np.uint8)   # the chunk buffer a worker fills: pinned (rb_host_alloc; Java: a direct ByteBuffer over it)
+        ascii_bases[:] = np.frombuffer(b"ACGT", dtype=np.uint8)[codes].reshape(-1)
         ascii_off = np.arange(n_a + 1, dtype=np.int64) * READ_LEN
         a_counts = ctx.host_alloc(n_a * KMERS_PER_READ * 4, np.float32)
         na = C.c_int64()
@@ -305,7 +329,7 @@ def main():
         assert na.value == n_a * KMERS_PER_READ and float(a_counts[:1024].min()) >= 1.0
         e2e["ascii"] = {"value": n_a * KMERS_PER_READ * 2 / ta, "unit": "k-mers/s", "reads_per_call": n_a, "h2d_bytes_per_step": 2 * (n_a * READ_LEN + 8 * (n_a + 1)),
                         "d2h_bytes_per_step": n_a * KMERS_PER_READ * 4,
-                        "note": "rb_graph_add_reads_ascii + rb_graph_count_reads_ascii: ASCII records in pageable host memory, packed on the GPU"}
+                        "note": "rb_graph_add_reads_ascii + rb_graph_count_reads_ascii: ASCII records of equal length in pinned host memory, segmented and packed on the GPU"}
 
     # ---- roofline (live CUDA-event times of the timed region; algorithmic bytes = SURVEY 8d sector model, 192.15 B per k-mer and phase)
     kmers_total = nk * args.steps

@@ -234,6 +234,15 @@ RB_API int32_t rb_graph_count_reads(rb_graph* g, const uint64_t* packed, const u
 RB_API int32_t rb_graph_count_reads_dev(rb_graph* g, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off,
                                         const int32_t* read_len, int64_t n_reads, int32_t uniform_len, int64_t uniform_stride,
                                         float* counts, int64_t* fhash, int64_t* rhash, int64_t* n_kmers_out);
+/* rb_graph_count_reads without waiting for the results: returns when the kernels of the last round are queued; the device->host copies
+ * of counts / hashes run behind whatever the caller does next (the next rb_graph_add_reads, typically: 4 B of count per k-mer take longer
+ * over PCIe than the look-up itself).  The read buffers and the (pinned) result buffers must stay untouched until rb_ctx_wait(ticket)
+ * returns; tickets complete in order.  rb_graph_sync also waits for everything.  The Java side of it is a pair of direct ByteBuffers
+ * used alternately by the worker that consumes the counts. */
+RB_API int32_t rb_graph_count_reads_async(rb_graph* g, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off,
+                                          const int32_t* read_len, int64_t n_reads, int32_t uniform_len, int64_t uniform_stride,
+                                          float* counts, int64_t* fhash, int64_t* rhash, int64_t* n_kmers_out, int64_t* ticket);
+RB_API int32_t rb_ctx_wait(rb_ctx* ctx, int64_t ticket);
 /* per-hash forms: graph.add(long[]) :405, contains :538, getCount(long) :552 */
 RB_API int32_t rb_graph_add_hashes(rb_graph* g, const int64_t* base, int64_t n, uint32_t flags);
 RB_API int32_t rb_graph_count_hashes(rb_graph* g, const int64_t* base, int64_t n, float* counts);
@@ -294,7 +303,8 @@ RB_API int32_t rb_graph_greedy_extend(rb_graph* g, const uint64_t* kmer_bits, co
  * reads if it has none left); one round holds at most max_kmers_per_round k-mers per rank.  Pointers of the round calls are DEVICE
  * pointers.  insert = graph.add (:405-412) and its policies via the RB_* flags; count = graph.getKmers counts (:562-570).
  * Errors: a hash skew that overflows the fixed-capacity regions of a round is detected on the device, agreed between the ranks and
- * reported as RB_ESTATE with NOTHING modified (retry with smaller rounds); overflowing counter-raise regions are retried internally. */
+ * reported as RB_ESTATE with NOTHING modified (retry with smaller rounds); once the probes of a round are routed the round always completes
+ * (counter raises travel back over the probes' own answer bytes: there is no second routing step that could overflow). */
 typedef struct rb_mgraph rb_mgraph;
 typedef struct rb_transport {
     void* user;

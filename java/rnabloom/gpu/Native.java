@@ -32,6 +32,10 @@ public final class Native {
                                                   ByteBuffer readLen, long numReads, int flags);
     public static native long graphCountReads(long ctx, long graph, ByteBuffer packed, ByteBuffer mask, ByteBuffer readOff,
                                               ByteBuffer readLen, long numReads, ByteBuffer counts, ByteBuffer fHash, ByteBuffer rHash);
+    /** graphCountReads without waiting: returns a ticket; counts / hashes are complete once ctxWait(ticket) has returned. */
+    public static native long graphCountReadsAsync(long ctx, long graph, ByteBuffer packed, ByteBuffer mask, ByteBuffer readOff,
+                                                   ByteBuffer readLen, long numReads, ByteBuffer counts, ByteBuffer fHashVals, ByteBuffer rHashVals);
+    public static native void ctxWait(long ctx, long ticket);
     /** graph.getKmers(String) for a chunk of sequences: counts + forward / reverse hashes of every window, exact for every character. */
     public static native long graphCountReadsAscii(long ctx, long graph, ByteBuffer bases, ByteBuffer offsets, long numReads, ByteBuffer counts,
                                                    ByteBuffer fHash, ByteBuffer rHash);

@@ -86,6 +86,22 @@ JNIEXPORT jlong JNICALL Java_rnabloom_gpu_Native_graphCountReads(JNIEnv* env, jc
                                                             (float*)addr(env, counts), (int64_t*)addr(env, fHash), (int64_t*)addr(env, rHash), &n));
     return n;
 }
+/* the same without waiting for the results (rb_graph_count_reads_async): returns the ticket for ctxWait; the buffers must be direct
+ * ByteBuffers over pinned memory and stay untouched until the wait returns */
+JNIEXPORT jlong JNICALL Java_rnabloom_gpu_Native_graphCountReadsAsync(JNIEnv* env, jclass cls, jlong ctx, jlong g, jobject packed, jobject mask,
+                                                                     jobject readOff, jobject readLen, jlong nReads, jobject counts, jobject fHash,
+                                                                     jobject rHash) {
+    int64_t n = 0, ticket = 0;
+    (void)cls;
+    check(env, (rb_ctx*)(intptr_t)ctx, rb_graph_count_reads_async((rb_graph*)(intptr_t)g, (const uint64_t*)addr(env, packed), (const uint32_t*)addr(env, mask),
+                                                                  (const int64_t*)addr(env, readOff), (const int32_t*)addr(env, readLen), nReads, 0, 0,
+                                                                  (float*)addr(env, counts), (int64_t*)addr(env, fHash), (int64_t*)addr(env, rHash), &n, &ticket));
+    return ticket;
+}
+JNIEXPORT void JNICALL Java_rnabloom_gpu_Native_ctxWait(JNIEnv* env, jclass cls, jlong ctx, jlong ticket) {
+    (void)cls;
+    check(env, (rb_ctx*)(intptr_t)ctx, rb_ctx_wait((rb_ctx*)(intptr_t)ctx, ticket));
+}
 /* graph.getKmers(String) over a chunk of sequences: counts + hashes, bit-exact for every byte value (graph :1224-1234) */
 JNIEXPORT jlong JNICALL Java_rnabloom_gpu_Native_graphCountReadsAscii(JNIEnv* env, jclass cls, jlong ctx, jlong g, jobject bases, jobject offsets, jlong nReads,
                                                                      jobject counts, jobject fHash, jobject rHash) {

@@ -8,7 +8,8 @@
 // answers go back with the mirror-image all-to-all: they land exactly where the producer's tile metadata points.  Per round and rank:
 //   lookup: route -> | probes -> apply -> | answers back -> combine
 //   insert: keys -> | (home rank of the key's hash range) -> split + dedup -> probes -> | -> apply (test-and-set) -> | answers back ->
-//           combine -> raises -> | -> apply raises                                            ( | = one all-to-all )
+//           combine (raise bytes over the answers) -> | raise bytes to the owners -> apply raises     ( | = one all-to-all )
+// The raise bytes travel like the probes did (same regions, one byte per record) to the owner, which still holds the probe records.
 // With paired probe records (cbf_bytes = 2^c dividing dbg_bits, h_d >= h_c) a rank owns whole paired slices: its counters are a
 // contiguous range of the cbf, its bits are that range inside every chunk of cbf_bytes bits (rb_mgraph_layout tells how to reassemble).
 //
@@ -121,18 +122,18 @@ struct rb_mgraph {
     int64_t dbg_bits, cbf_bytes;      // global sizes
     SlGeom sg_route, sg_apply;        // producer view (global regions) / consumer view (local regions, region_div = W)
     bool paired;
-    int R, SR, KR;                    // per rank: probe regions, raise regions, key ranges
+    int R, KR;                        // per rank: probe regions, key ranges
     int lg1, sub_bits;
     int64_t n_max, n_dense;           // instances per rank and round; capacity of the dense distinct-key arrays
-    uint32_t probe_cap, key_cap, raise_cap, sub_cap;
+    uint32_t probe_cap, key_cap, sub_cap;
     rb_filter *dbg, *cbf;             // local shares
-    unsigned int *probe_cursor, *key_cursor, *raise_cursor, *cons_cursor, *sub_cursor, *n_distinct;
+    unsigned int *probe_cursor, *key_cursor, *cons_cursor, *sub_cursor, *n_distinct;
     uint32_t *cons_rlo, *pos;
     uint2* tile_meta;
     unsigned long long *sub_data, *dkey;
     unsigned int* dmult;
     int* chunk_prefix;
-    int* flags;                       // device: [0] a region overflowed before anything was modified, [1] a raise region overflowed
+    int* flags;                       // device: [0] a region overflowed before anything was modified, [2] never set (barrier word)
     int64_t n_items;                  // instances of the last route_lookup
     bool lookup_fast;                 // which route kernel (and so which combine mapping) the last route_lookup used
     // exchange
@@ -142,7 +143,7 @@ struct rb_mgraph {
     uint32_t *send32, *recv32, *cnt_s, *cnt_r;
     unsigned long long *send64, *recv64;
     uint8_t *ans, *home_ans;
-    int64_t n_probe, n_key, n_raise;  // records of one send buffer (all destinations)
+    int64_t n_probe, n_key;           // records of one send buffer (all destinations)
     int64_t exchanged_bytes, rounds;
     // peer-to-peer mode (GPUs of one box, CUDA IPC): a consumer kernel reads the producers' send arenas directly over NVLink and writes
     // its answers straight into the producers' answer arrays -- the transfer overlaps the filter work tile by tile and no separate
@@ -163,7 +164,7 @@ extern "C" int32_t rb_mgraph_destroy(rb_mgraph* mg) {
 #endif
     if (mg->dbg) filter_free(mg->dbg);
     if (mg->cbf) filter_free(mg->cbf);
-    cudaFree(mg->probe_cursor); cudaFree(mg->key_cursor); cudaFree(mg->raise_cursor); cudaFree(mg->cons_cursor); cudaFree(mg->sub_cursor);
+    cudaFree(mg->probe_cursor); cudaFree(mg->key_cursor); cudaFree(mg->cons_cursor); cudaFree(mg->sub_cursor);
     cudaFree(mg->n_distinct); cudaFree(mg->cons_rlo); cudaFree(mg->pos); cudaFree(mg->tile_meta); cudaFree(mg->sub_data); cudaFree(mg->dkey);
     cudaFree(mg->dmult); cudaFree(mg->chunk_prefix); cudaFree(mg->flags);
 #ifndef RB_EMU
@@ -260,26 +261,20 @@ static int32_t mgraph_create(rb_ctx* ctx, int32_t n_ranks, int32_t rank, const r
         if (tot_d >= tot_c && sg.dbg_log2 < 31) ++sg.dbg_log2; else if (sg.cbf_log2 < 31) ++sg.cbf_log2; else break;
     }
     sg.shard_d = (int)div_up(tot_d, W); sg.shard_c = (int)div_up(tot_c, W);
-    if (mg->paired) {   // the counters of a rank are its paired slices: the raise slices subdivide exactly that range
+    if (mg->paired) {   // the counters of a rank are its paired slices
         sg.shard_p = sg.n_pair / W;                                   // also for one rank (sl_pair_geometry leaves it 0 there)
         sg.pair_local_c = (uint64_t)sg.shard_p << sg.pair_log2;
         sg.cbf_log2 = sg.pair_log2;
         sg.shard_c = sg.shard_p;
         sg.shard_d = 0;   // unused: a paired region is the global slice number
     }
-    sg.raise_log2 = std::min(sg.cbf_log2, env_int("RB_SLICE_RAISE_LOG2", 25, 2, 25));
-    while (((int64_t)sg.shard_c << (sg.cbf_log2 - sg.raise_log2)) * W > kSlMaxRegions && sg.raise_log2 < std::min(sg.cbf_log2, 25)) ++sg.raise_log2;
-    sg.shard_r = sg.shard_c << (sg.cbf_log2 - sg.raise_log2);
     sg.region_div = 1;
     mg->R = mg->paired ? sg.shard_p : sg.shard_d + sg.shard_c;
-    mg->SR = sg.shard_r;
-    if ((int64_t)mg->R * W > kSlMaxRegions || (int64_t)mg->SR * W > kSlMaxRegions) { delete mg; return fail(ctx, RB_EINVAL, "mgraph: too many filter slices for this many ranks"); }
+    if ((int64_t)mg->R * W > kSlMaxRegions) { delete mg; return fail(ctx, RB_EINVAL, "mgraph: too many filter slices for this many ranks"); }
     if (!mg->paired) { sg.n_dbg = sg.shard_d * W; sg.n_cbf = sg.shard_c * W; }
-    sg.n_raise = sg.shard_r * W;
     mg->sg_route = sg;
     mg->sg_apply = sg;
     mg->sg_apply.region_div = W;
-    mg->sg_apply.n_raise = sg.shard_r;
     if (!mg->paired) { mg->sg_apply.n_dbg = sg.shard_d; mg->sg_apply.n_cbf = sg.shard_c; }
     // the shard_* fields make the region functions of the producer interleave (owner, local slice); the consumer sees local regions
     // local shares: whole slices, so that the ranks' shares reassemble to the global arrays (rb_mgraph_layout)
@@ -311,28 +306,24 @@ static int32_t mgraph_create(rb_ctx* ctx, int32_t n_ranks, int32_t rank, const r
         const double slices_d = std::max(1.0, (double)dbg_bits / (double)(1LL << sg.dbg_log2)), slices_c = std::max(1.0, (double)cbf_bytes / (double)(1LL << sg.cbf_log2));
         mg->probe_cap = (uint32_t)sl_capacity(std::max((double)mg->n_dense * hd / slices_d, (double)mg->n_dense * hc / slices_c));
     }
-    const double slices_r = std::max(1.0, (double)cbf_bytes / (double)(1LL << sg.raise_log2));
-    mg->raise_cap = (uint32_t)sl_capacity((double)mg->n_dense * hc / slices_r);
     const int64_t n_sub_regions = (int64_t)mg->KR << mg->sub_bits;
     if (mg->sub_cap >= (uint32_t)kSlDedupSlots || (int64_t)mg->R * W * mg->probe_cap >= (1LL << 32) - (1LL << 20) ||
-        n_sub_regions * mg->sub_cap >= (1LL << 32) - (1LL << 20) || (int64_t)mg->SR * W * mg->raise_cap >= (1LL << 32) - (1LL << 20)) {
+        n_sub_regions * mg->sub_cap >= (1LL << 32) - (1LL << 20)) {
         delete mg;
         return fail(ctx, RB_EINVAL, "mgraph: max_kmers_per_round too large for 32-bit record positions");
     }
     mg->n_probe = (int64_t)W * mg->R * mg->probe_cap;
     mg->n_key = (int64_t)W * mg->KR * mg->key_cap;
-    mg->n_raise = (int64_t)W * mg->SR * mg->raise_cap;
     int32_t rc = filter_alloc(ctx, RB_BLOOM, std::max<int64_t>(local_d, 32), hd, k, &mg->dbg);
     if (!rc) rc = filter_alloc(ctx, RB_COUNTING, std::max<int64_t>(local_c, 4), hc, k, &mg->cbf);
     cudaError_t er = cudaSuccess;
     if (!rc) {
         const int nj = mg->paired ? 3 : kSlNJ;
-        const int maxB = std::max(std::max(mg->R, mg->SR), mg->KR) * W;
+        const int maxB = std::max(mg->R, mg->KR) * W;
         const int64_t n_tiles = mg->n_dense / (mg->paired ? SlShape<3>::TILE : SlShape<6>::TILE) + 8;
-        const size_t n32 = (size_t)std::max(mg->n_probe, mg->n_raise) + kSlSpill;
+        const size_t n32 = (size_t)mg->n_probe + kSlSpill;
         er = cudaMalloc(&mg->probe_cursor, (size_t)mg->R * W * kSlPad * 4);
         if (er == cudaSuccess) er = cudaMalloc(&mg->key_cursor, (size_t)mg->KR * W * kSlPad * 4);
-        if (er == cudaSuccess) er = cudaMalloc(&mg->raise_cursor, (size_t)mg->SR * W * kSlPad * 4);
         if (er == cudaSuccess) er = cudaMalloc(&mg->cons_cursor, (size_t)maxB * 4 + 64);
         if (er == cudaSuccess) er = cudaMalloc(&mg->cons_rlo, (size_t)maxB * 4 + 64);
         if (er == cudaSuccess) er = cudaMalloc(&mg->sub_cursor, (size_t)n_sub_regions * 4 + 64);
@@ -358,8 +349,8 @@ static int32_t mgraph_create(rb_ctx* ctx, int32_t n_ranks, int32_t rank, const r
         return rc;
     }
     mg->dbg->in_graph = mg->cbf->in_graph = true;
-    const int maxB_all = std::max(std::max(mg->R, mg->SR), mg->KR) * W;
-    const size_t n32_all = (size_t)std::max(mg->n_probe, mg->n_raise) + kSlSpill;
+    const int maxB_all = std::max(mg->R, mg->KR) * W;
+    const size_t n32_all = (size_t)mg->n_probe + kSlSpill;
     if (tr) mg->tr = *tr;
     else if (W > 1) {
 #ifdef RB_EMU
@@ -419,7 +410,7 @@ extern "C" int32_t rb_mgraph_layout(rb_mgraph* mg, int64_t* layout) {
     layout[5] = mg->paired ? mg->dbg_bits / mg->cbf_bytes : 0;
     layout[6] = mg->n_max;
     const int64_t cnt = 4 * (int64_t)mg->W;
-    layout[7] = mg->n_key * 8 + mg->n_probe * 5 + mg->n_raise * 4 + cnt * (mg->KR + mg->R + mg->SR);
+    layout[7] = mg->n_key * 8 + mg->n_probe * 6 + cnt * (mg->KR + mg->R);   // keys, probes, answers back, raise bytes
     layout[8] = mg->n_probe * 5 + cnt * mg->R;
     return RB_OK;
 }
@@ -642,42 +633,38 @@ static int32_t mg_combine_lookup(rb_mgraph* mg, float* counts) {
     }
     return RB_OK;
 }
-// one pass of the raise phase: combine (raises of the keys of this pass) -> | -> apply raises
-static int32_t mg_raise_pass(rb_mgraph* mg, int policy, uint64_t seed, int pass, int n_pass) {
+// the raise phase: combine at the home rank (raise bytes over the answers) -> | -> the owner sweeps its probe regions again
+static int32_t mg_raises(rb_mgraph* mg, int policy, uint64_t seed) {
     rb_ctx* ctx = mg->ctx;
     int32_t rc;
-    const HashMults hm = make_hm(mg->k);
-    const SlArena raises = mg_producer(mg, mg->send32, mg->raise_cursor, mg->SR, mg->raise_cap);
-    CK(cudaMemsetAsync(raises.cursor, 0, (size_t)raises.B * kSlPad * 4, ctx->stream));
     const int B = mg->R * mg->W;
-    const size_t sm_r = std::max(TileSort<uint32_t, kSlTileRecords>::smem_bytes(raises.B), TileAnswers::smem_bytes(B, kSlThreads * kSlTileRecords));
+    const size_t sm_r = TileAnswers::smem_bytes(B, kSlThreads * kSlTileRecords);
     const int grid_d = (int)div_up(mg->n_dense, (int64_t)(mg->paired ? SlShape<3>::TILE : SlShape<6>::TILE));
-    if (mg->paired) SL_LAUNCH("ks_combine_insert", ks_combine_insert<3>, grid_d, sm_r, mg->dkey, mg->dmult, mg->n_distinct, mg->pos, mg->tile_meta, B, mg->home_ans, hm, mg->sg_route,
-                              policy, seed, raises, mg->flags + 1, (const int*)mg->flags, pass, n_pass);
-    else SL_LAUNCH("ks_combine_insert", ks_combine_insert<6>, grid_d, sm_r, mg->dkey, mg->dmult, mg->n_distinct, mg->pos, mg->tile_meta, B, mg->home_ans, hm, mg->sg_route,
-                   policy, seed, raises, mg->flags + 1, (const int*)mg->flags, pass, n_pass);
-    rc = mg_pack_counts(mg, raises, mg->cnt_s);
+    if (mg->paired) SL_LAUNCH("ks_combine_insert", ks_combine_insert<3>, grid_d, sm_r, mg->dkey, mg->dmult, mg->n_distinct, mg->pos, mg->tile_meta, B, mg->home_ans, mg->sg_route,
+                              policy, seed, (const int*)mg->flags);
+    else SL_LAUNCH("ks_combine_insert", ks_combine_insert<6>, grid_d, sm_r, mg->dkey, mg->dmult, mg->n_distinct, mg->pos, mg->tile_meta, B, mg->home_ans, mg->sg_route,
+                   policy, seed, (const int*)mg->flags);
+    // staged: the raise bytes travel to the owners like the probes did; p2p: a barrier, then the owners read them in place
+    rc = mg_exchange(mg, mg->home_ans, mg->ans, mg->R, mg->probe_cap, 1, false);
     if (rc) return rc;
-    rc = mg_agree(mg, 1, 1);   // p2p mode: also the barrier after which the raise arenas are complete everywhere
+    SlArena a;   // the regions mg_apply consumed (their counts are still where they were)
+    rc = mg_consumer(mg, mg->recv32, mg->cnt_r, mg->d_peer32, mg->d_peer_cnt, mg->R, mg->probe_cap, sl_chunk(), &a,
+                     mg->paired ? 1 << mg->sg_apply.pair_sub_log2 : 1);
     if (rc) return rc;
-    if (!mg->p2p) { rc = mg_exchange(mg, mg->send32, mg->recv32, mg->SR, mg->raise_cap, 4, true); if (rc) return rc; }
-    SlArena a;
-    rc = mg_consumer(mg, mg->recv32, mg->cnt_r, mg->d_peer32, mg->d_peer_cnt, mg->SR, mg->raise_cap, sl_chunk(), &a);
-    if (rc) return rc;
-    const size_t sm_rp = (size_t)(a.B + 1) * 4;
+    if (mg->p2p) a.peer_ans = (uint8_t* const*)mg->d_peer_ans;
+    const size_t sm_pre = (size_t)(a.B + 1) * 4;
     int grid = 0;
-    rc = sl_persistent_grid(ctx, ks_apply_raises, sm_rp, &grid);
+    rc = sl_persistent_grid(ctx, ks_apply_raises, sm_pre, &grid);
     if (rc) return rc;
-    // flags[0] (nothing may be modified) or flags[1] (this pass overflowed somewhere): the raise kernel checks flags[1]; flags[0]
-    // already stopped ks_combine_insert from emitting anything
-    SL_LAUNCH("ks_apply_raises", ks_apply_raises, grid, sm_rp, a, mg->chunk_prefix, mg->sg_apply, mg->cbf->dev, (const int*)(mg->flags + 1));
+    SL_LAUNCH("ks_apply_raises", ks_apply_raises, grid, sm_pre, a, mg->chunk_prefix, mg->sg_apply, mg->cbf->dev, (const uint8_t*)mg->ans, (const int*)mg->flags);
     return RB_OK;
 }
 static int32_t mg_read_flags(rb_mgraph* mg, int* f2) {   // the one host synchronisation of a round
     rb_ctx* ctx = mg->ctx;
-    CK(cudaMemcpyAsync(f2, mg->flags, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    f2[1] = 0;
+    CK(cudaMemcpyAsync(f2, mg->flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (f2[0] || f2[1]) CK(cudaMemsetAsync(mg->flags, 0, 8, ctx->stream));
+    if (f2[0]) CK(cudaMemsetAsync(mg->flags, 0, 4, ctx->stream));
     return RB_OK;
 }
 
@@ -709,21 +696,10 @@ extern "C" int32_t rb_mgraph_add_round_dev(rb_mgraph* mg, const uint64_t* packed
         rc = mg_exchange(mg, mg->ans, mg->home_ans, mg->R, mg->probe_cap, 1, false);
         if (rc) return rc;
         const uint64_t seed = ctx->rng_seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(ctx->launches + 1);
-        // the raise phase is repeated with the keys spread over more passes when a raise region overflowed (a raise is a max: an aborted
-        // pass applied nothing, a repeated raise changes nothing) -- see sliced_insert_round
-        for (int n_pass = 1;; n_pass *= 2) {
-            if (n_pass > 256) return fail(ctx, RB_ESTATE, "mgraph: raise regions overflow even with the keys spread over 256 passes");
-            bool over = false;
-            for (int pass = 0; pass < n_pass && !over; ++pass) {
-                rc = mg_raise_pass(mg, policy, seed, pass, n_pass);
-                if (rc) return rc;
-                rc = mg_read_flags(mg, f2);
-                if (rc) return rc;
-                if (f2[0]) break;
-                over = f2[1] != 0;
-            }
-            if (!over || f2[0]) break;
-        }
+        rc = mg_raises(mg, policy, seed);
+        if (rc) return rc;
+        rc = mg_read_flags(mg, f2);
+        if (rc) return rc;
     } else {
         rc = mg_read_flags(mg, f2);
         if (rc) return rc;

@@ -22,8 +22,9 @@
 //     I4 ks_emit_probes     per distinct key: probes tile-sorted by filter slice, positions remembered
 //     I5 ks_apply_probes<1> test-and-set the dbgbf bits (old bit is the answer), read the counters
 //     I6 ks_combine_insert  present = AND(old bits); replay m-1+present min-increments on the counter values
-//                           (bloom/CountingBloomFilter.java:170-194); raises tile-sorted by counter slice
-//     I7 ks_apply_raises    counter = max(counter, value), slice by slice
+//                           (bloom/CountingBloomFilter.java:170-194); the new value of every counter that grew is written over the
+//                           probe's answer byte -- the raise travels back to where the probe record already sits, sorted by slice
+//     I7 ks_apply_raises    second sweep over the probe regions: counter = max(counter, raise byte), slice by slice
 // Linearisation is the one DESIGN.md section 4 states for batches: duplicates of a k-mer inside a round are aggregated, so exactly
 // one of them is the first sighting; k-mers that share a counter inside one round see the counter's value at the start of the round.
 //
@@ -90,7 +91,6 @@ struct SlGeom {
     int hd, hc;
     int dbg_log2, cbf_log2;   // slice sizes: 2^dbg_log2 bits, 2^cbf_log2 bytes
     int n_dbg, n_cbf;         // probe region = dbgbf slice, or n_dbg + cbf slice
-    int raise_log2, n_raise;  // counter raises: record = slice-local byte index | value << raise_log2 (raise_log2 <= 25)
     // paired records (NJ = 3): slice s = counters [s << pair_log2, (s + 1) << pair_log2) and, for every chunk c < dbg_bits / cbf_bytes,
     // the bits c * cbf_bytes + the same range; record = chunk << pair_log2 | offset inside the slice.  n_dbg = n_cbf = 0, n_pair regions.
     int paired, pair_log2, cbf_size_log2, n_pair;
@@ -101,10 +101,10 @@ struct SlGeom {
     uint64_t pair_local_c;    // counters (= bits per chunk) of the consumer's share: cbf_bytes on one GPU, shard_p << pair_log2 when sharded
     int shard_p;              // paired slices per rank (sharded graph): region = global slice, owner = slice / shard_p
     // hash-sharded graph (rb_sshard_*, one process per GPU): rank r owns dbgbf slices [r * shard_d, (r+1) * shard_d) and cbf slices
-    // [r * shard_c, ...); a producer's probe region = owner * (shard_d + shard_c) + (local dbgbf slice | shard_d + local cbf slice),
-    // raise region = owner * shard_r + local raise slice.  A consumer sees the regions it received ordered by local region first,
-    // source rank second: region / region_div = local region.  Single GPU: shard_d = 0, region_div = 1.
-    int shard_d, shard_c, shard_r, region_div;
+    // [r * shard_c, ...); a producer's probe region = owner * (shard_d + shard_c) + (local dbgbf slice | shard_d + local cbf slice).
+    // A consumer sees the regions it received ordered by local region first, source rank second: region / region_div = local
+    // region.  Single GPU: shard_d = 0, region_div = 1.
+    int shard_d, shard_c, region_div;
 };
 __device__ __forceinline__ int sl_dbg_region(const SlGeom& sg, uint64_t gi) {
     const int s = (int)(gi >> sg.dbg_log2);
@@ -114,9 +114,10 @@ __device__ __forceinline__ int sl_cbf_region(const SlGeom& sg, uint64_t gi) {
     const int s = (int)(gi >> sg.cbf_log2);
     return sg.shard_d ? (s / sg.shard_c) * (sg.shard_d + sg.shard_c) + sg.shard_d + s % sg.shard_c : sg.n_dbg + s;
 }
-__device__ __forceinline__ int sl_raise_region(const SlGeom& sg, uint64_t gi) {
-    const int s = (int)(gi >> sg.raise_log2);
-    return sg.shard_d ? (s / sg.shard_r) * sg.shard_r + s % sg.shard_r : s;
+// producer view: does region b hold counter probes (its answer bytes carry the raises back)?
+__device__ __forceinline__ bool sl_region_has_counters(const SlGeom& sg, int b) {
+    if (sg.paired) return true;
+    return sg.shard_d ? (b % (sg.shard_d + sg.shard_c)) >= sg.shard_d : b >= sg.n_dbg;
 }
 __device__ __forceinline__ uint64_t sl_mixkey(uint64_t key) { return key * 0x9E3779B97F4A7C15ULL; }
 
@@ -318,7 +319,9 @@ struct TileAnswers {
     static __host__ __device__ size_t smem_bytes(int B, int tile_records) { return ((size_t)(2 * B + 2) * 4 + (size_t)tile_records + 15) & ~(size_t)15; }
     // every thread of the CTA calls it; meta = the tile's B + 1 entries written by TileSort::run.  Eight lanes copy one run (a run
     // is ~12-24 bytes), 32 runs per CTA step, and nothing in a step depends on the step before: the loads of many runs overlap.
-    __device__ __forceinline__ void load(unsigned char* smem, int B, const uint2* __restrict__ meta, const uint8_t* __restrict__ ans) {
+    // RO = false: the kernel writes the runs back later (store): no non-coherent loads of `ans`
+    template <bool RO = true>
+    __device__ __forceinline__ void load(unsigned char* smem, int B, const uint2* __restrict__ meta, const uint8_t* ans) {
         start = reinterpret_cast<uint32_t*>(smem);
         uint32_t* gpos = start + (B + 1);
         bytes = smem + (size_t)(2 * B + 2) * 4;
@@ -327,11 +330,23 @@ struct TileAnswers {
         const int grp = threadIdx.x >> 3, l8 = threadIdx.x & 7;
         for (int b = grp; b < B; b += kSlThreads / 8) {
             const uint32_t lo = start[b], n = start[b + 1] - lo, g = gpos[b];
-            for (uint32_t i = l8; i < n; i += 8) bytes[lo + i] = __ldg(ans + g + i);
+            for (uint32_t i = l8; i < n; i += 8) bytes[lo + i] = RO ? __ldg(ans + g + i) : __ldcg(ans + g + i);
         }
         __syncthreads();
     }
     __device__ __forceinline__ uint32_t get(uint32_t place) const { return place != kNoSlot ? (uint32_t)bytes[start[place & 0xFFFu] + (place >> 12)] : 0u; }
+    // the way back (ks_combine_insert): a thread overwrites the staged bytes of its own records, then the runs go back where they came from
+    __device__ __forceinline__ void put(uint32_t place, uint32_t v) { if (place != kNoSlot) bytes[start[place & 0xFFFu] + (place >> 12)] = (uint8_t)v; }
+    // every thread of the CTA calls it (after a __syncthreads that follows the last put); ONLY_COUNTERS: runs of dbgbf-only regions stay as they are
+    __device__ __forceinline__ void store(int B, uint8_t* __restrict__ ans, const SlGeom& sg) const {
+        const uint32_t* gpos = start + (B + 1);
+        const int grp = threadIdx.x >> 3, l8 = threadIdx.x & 7;
+        for (int b = grp; b < B; b += kSlThreads / 8) {
+            if (!sl_region_has_counters(sg, b)) continue;
+            const uint32_t lo = start[b], n = start[b + 1] - lo, g = gpos[b];
+            for (uint32_t i = l8; i < n; i += 8) ans[g + i] = bytes[lo + i];
+        }
+    }
 };
 
 // ---- prefix k-merizer (uniform read layout) ----------------------------------------------------------------------------------------------
@@ -908,113 +923,105 @@ __global__ void __launch_bounds__(kSlThreads) ks_emit_probes(const unsigned long
     for (int i = 0; i < KPT; ++i) if (d0 + i * kSlThreads < nd) sl_store_places<NJ>(pos, d0 + i * kSlThreads, &slot[i * NJ]);
 }
 
-// ---- I6: per distinct key: present?, replay the increments, emit one raise per counter that grew ----------------------------------------------
+// ---- I6: per distinct key: present?, replay the increments, write the new value of every counter that grew over the probe's answer byte ----
+// The raise goes back the way the answer came: the probe record of that counter still sits in the region of its slice (where the tile
+// sort put it), so "raise counter c to v" is one byte at the record's position -- no raise records, no second sort, no region that
+// could overflow.  0 = no raise (a counter that grew is >= 1).
 template <int NJ>
 __global__ void __launch_bounds__(kSlThreads) ks_combine_insert(const unsigned long long* __restrict__ dkey, const unsigned int* __restrict__ dmult,
                                                                const unsigned int* __restrict__ n_distinct, const uint32_t* __restrict__ pos,
-                                                               const uint2* __restrict__ tile_meta, int probe_B, const uint8_t* __restrict__ ans,
-                                                               const HashMults hm, const SlGeom sg, int policy, uint64_t rng_seed, const SlArena raises,
-                                                               int* overflow, const int* abort, int pass, int n_pass) {
+                                                               const uint2* __restrict__ tile_meta, int probe_B, uint8_t* ans,
+                                                               const SlGeom sg, int policy, uint64_t rng_seed, const int* abort) {
     constexpr int KPT = SlShape<NJ>::KPT, TILE = SlShape<NJ>::TILE;
     if (abort && *abort) return;
     const int64_t nd = (int64_t)*n_distinct;
     if ((int64_t)blockIdx.x * TILE >= nd) return;   // whole CTA
     RB_DYN_SMEM(unsigned char, sl_smem);
     const int64_t d0 = (int64_t)blockIdx.x * TILE + threadIdx.x;   // item i of the thread = distinct key d0 + i * 256 (as in ks_emit_probes)
-    uint32_t rec[KPT * kSlMaxH], rslot[KPT * kSlMaxH];
-#pragma unroll
-    for (int e = 0; e < KPT * kSlMaxH; ++e) { rslot[e] = kNoSlot; rec[e] = 0; }
     TileAnswers ta;   // the tile of ks_emit_probes with the same block index
-    ta.load(sl_smem, probe_B, tile_meta + (size_t)blockIdx.x * (probe_B + 1), ans);
-    uint32_t a[KPT * NJ];
+    ta.load<false>(sl_smem, probe_B, tile_meta + (size_t)blockIdx.x * (probe_B + 1), ans);
 #pragma unroll
     for (int i = 0; i < KPT; ++i) {
-        uint32_t place[NJ];
+        if (d0 + i * kSlThreads < nd) {
+            uint32_t place[NJ], a[NJ];
+            sl_load_places<NJ>(pos, d0 + i * kSlThreads, place);
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) place[j] = kNoSlot;
-        if (d0 + i * kSlThreads < nd) sl_load_places<NJ>(pos, d0 + i * kSlThreads, place);
+            for (int j = 0; j < NJ; ++j) a[j] = ta.get(place[j]);
+            const uint64_t key = (uint64_t)dkey[d0 + i * kSlThreads];
+            const unsigned int m = dmult[d0 + i * kSlThreads];
+            bool present = true;
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) a[i * NJ + j] = ta.get(place[j]);
-    }
-    __syncthreads();   // the tile sort of the raises reuses the shared memory
-    TileSort<uint32_t, KPT * kSlMaxH> ts;
-    ts.init(sl_smem, raises.B);
-    {
+            for (int h = 0; h < kSlMaxH; ++h) if (h < sg.hd) present = present && sl_ans_bit(a[h]);
+            // graph.add :405-412 -- the first sighting of an absent k-mer only sets bits; addCountIfPresent :424-428 needs presence
+            unsigned int n_inc = (policy == POLICY_COUNT_IF_PRESENT) ? (present ? m : 0u) : (m - 1u + (present ? 1u : 0u));
+            int v0[kSlMaxH], v[kSlMaxH];
+            int mn0 = 127;
 #pragma unroll
-        for (int i = 0; i < KPT; ++i) {
-            if (d0 + i * kSlThreads < nd) {
-                const uint64_t key = (uint64_t)dkey[d0 + i * kSlThreads];
-                const unsigned int m = dmult[d0 + i * kSlThreads];
-                bool present = true;
+            for (int h = 0; h < kSlMaxH; ++h) {
+                v0[h] = 127;
+                if (h < sg.hc) { v0[h] = sl_ans_counter<NJ>(a, h); mn0 = min(mn0, v0[h]); }
+                v[h] = v0[h];
+            }
+            if (policy == POLICY_COUNT_IF_PRESENT && mn0 == 0) n_inc = 0;   // "&& cbf.getCount(hashVals) > 0" (graph :425)
+            uint64_t rr = mix64(key ^ rng_seed);
+            for (unsigned int it = 0; it < n_inc; ++it) {   // CountingBloomFilter.increment :170-194, n_inc times
+                int mn = 127;
 #pragma unroll
-                for (int h = 0; h < kSlMaxH; ++h) if (h < sg.hd) present = present && sl_ans_bit(a[i * NJ + h]);
-                // graph.add :405-412 -- the first sighting of an absent k-mer only sets bits; addCountIfPresent :424-428 needs presence
-                unsigned int n_inc = (policy == POLICY_COUNT_IF_PRESENT) ? (present ? m : 0u) : (m - 1u + (present ? 1u : 0u));
-                int v0[kSlMaxH], v[kSlMaxH];
-                uint64_t gi[kSlMaxH];
-                int mn0 = 127;
+                for (int h = 0; h < kSlMaxH; ++h) if (h < sg.hc) mn = min(mn, v[h]);
+                if (mn >= 127) break;
+                rr = mix64(rr + it);
+                const int u = minifloat_increment(mn, rr);
+                if (u != mn) {
 #pragma unroll
-                for (int h = 0; h < kSlMaxH; ++h) {
-                    v0[h] = 127; gi[h] = ~0ULL;
-                    if (h < sg.hc) {
-                        v0[h] = sl_ans_counter<NJ>(&a[i * NJ], h);
-                        gi[h] = fm_index(expand_hash(key, h, hm), sg.cbf_fm);
-                        mn0 = min(mn0, v0[h]);
-                    }
-                    v[h] = v0[h];
+                    for (int h = 0; h < kSlMaxH; ++h) if (h < sg.hc && v[h] == mn) v[h] = u;
                 }
-                if (policy == POLICY_COUNT_IF_PRESENT && mn0 == 0) n_inc = 0;   // "&& cbf.getCount(hashVals) > 0" (graph :425)
-                uint64_t rr = mix64(key ^ rng_seed);
-                for (unsigned int it = 0; it < n_inc; ++it) {   // CountingBloomFilter.increment :170-194, n_inc times
-                    int mn = 127;
+            }
+            // two hashes of one key on the same counter read the same value and replay to the same value: both records carry the same raise
 #pragma unroll
-                    for (int h = 0; h < kSlMaxH; ++h) if (h < sg.hc) mn = min(mn, v[h]);
-                    if (mn >= 127) break;
-                    rr = mix64(rr + it);
-                    const int u = minifloat_increment(mn, rr);
-                    if (u != mn) {
-#pragma unroll
-                        for (int h = 0; h < kSlMaxH; ++h) if (h < sg.hc && v[h] == mn) v[h] = u;
-                    }
-                }
-#pragma unroll
-                for (int h = 0; h < kSlMaxH; ++h) {
-                    bool dup = false;
-#pragma unroll
-                    for (int h2 = 0; h2 < kSlMaxH; ++h2) if (h2 < h && gi[h2] == gi[h]) dup = true;   // one raise per distinct counter
-                    // n_pass > 1: the raise regions of an earlier attempt overflowed (hash skew); the keys are spread over n_pass passes.
-                    // A raise is a max: applying one twice, or the passes in any order, gives the same counters.
-                    const bool mine = n_pass <= 1 || (int)((sl_mixkey(key) >> 20) % (uint64_t)n_pass) == pass;
-                    if (h < sg.hc && !dup && mine && v[h] > v0[h]) {
-                        rslot[i * kSlMaxH + h] = (uint32_t)sl_raise_region(sg, gi[h]);
-                        rec[i * kSlMaxH + h] = (uint32_t)(gi[h] & ((1ULL << sg.raise_log2) - 1)) | ((uint32_t)v[h] << sg.raise_log2);
-                    }
-                }
+            for (int j = 0; j < NJ; ++j) {
+                const int h = NJ == 3 ? j : j - kSlMaxH;   // counter hash of slot j (separate records: slots 0..2 are dbgbf probes)
+                if (h >= 0) ta.put(place[j], (h < sg.hc && v[h] > v0[h]) ? (uint32_t)v[h] : 0u);
             }
         }
     }
-    ts.run(raises, 0, rslot, rec, overflow, nullptr);
+    __syncthreads();
+    ta.store(probe_B, ans, sg);
 }
 
-// ---- I7: raise the counters slice by slice ------------------------------------------------------------------------------------------------------
+// ---- I7: raise the counters slice by slice: the second sweep over the probe regions, this time reading the raise bytes ------------------------
 __global__ void __launch_bounds__(kSlThreads) ks_apply_raises(const SlArena arena, int* chunk_prefix, const SlGeom sg,
-                                                             uint32_t* __restrict__ cbf_words, const int* abort) {
-    if (abort && *abort) return;   // a raise region overflowed (on this or another rank): the pass is repeated with the keys spread wider
+                                                             uint32_t* __restrict__ cbf_words, const uint8_t* __restrict__ raise, const int* abort) {
+    if (abort && *abort) return;   // a region overflowed while the round was routed (on this or another rank): nothing may be modified
     RB_DYN_SMEM(unsigned char, sl_smem);
     int* pre = reinterpret_cast<int*>(sl_smem);
     sl_load_prefix(pre, chunk_prefix, arena.B);
     const int total = pre[arena.B];
+    constexpr int U = 4;
     const L2Keep keep = l2_keep_policy();
     __shared__ int s_c;
     for (int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c); c < total; c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c)) {
         const SlWork w = sl_work_item(arena, pre, c);
-        const uint32_t* rec = sl_region_records<uint32_t>(arena, w.b);
-        const int64_t word0 = (int64_t)(w.b / sg.region_div) << (sg.raise_log2 - 2);
-        for (uint32_t i = threadIdx.x; i < w.n; i += kSlThreads) {
-            const uint32_t a = __ldcs(rec + w.first + i);
-            const uint32_t li = a & ((1u << sg.raise_log2) - 1u);
-            uint32_t* wp = cbf_words + word0 + (li >> 2);
-            byte_raise_keep(wp, (int)(li & 3) * 8, a >> sg.raise_log2, ld_cg_keep(wp, keep), keep);
+        const int lr = w.b / sg.region_div;   // local region
+        if (!sg.paired && lr < sg.n_dbg) continue;   // dbgbf probes (the whole CTA)
+        const uint32_t* rec = sl_region_records<uint32_t>(arena, w.b);                              // local, or the source rank's arena over NVLink
+        const uint8_t* rb = arena.peer_ans ? arena.peer_ans[w.b % arena.n_peers] : raise;   // ... and the source rank's raise bytes
+        const uint64_t byte0 = sg.paired ? (uint64_t)lr << sg.pair_log2 : (uint64_t)(lr - sg.n_dbg) << sg.cbf_log2;
+        const uint32_t off_mask = sg.paired ? (1u << sg.pair_log2) - 1u : 0xFFFFFFFFu;
+        const int sub_shift = sg.paired ? sg.pair_log2 - sg.pair_sub_log2 : 31;
+        for (uint32_t i0 = threadIdx.x; i0 < w.n; i0 += kSlThreads * U) {
+            uint32_t v[U], li[U], wd[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = (i0 + u * kSlThreads < w.n) ? (uint32_t)__ldcs(rb + w.first + i0 + u * kSlThreads) : 0u;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                li[u] = v[u] ? __ldcs(rec + w.first + i0 + u * kSlThreads) & off_mask : 0u;
+                if (arena.passes > 1 && (int)(li[u] >> sub_shift) != w.pass) v[u] = 0;   // another pass handles this sub-slice
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) { wd[u] = 0; if (v[u]) wd[u] = ld_cg_keep(cbf_words + ((byte0 + li[u]) >> 2), keep); }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (v[u]) byte_raise_keep(cbf_words + ((byte0 + li[u]) >> 2), (int)((byte0 + li[u]) & 3) * 8, v[u], wd[u], keep);
         }
     }
 }

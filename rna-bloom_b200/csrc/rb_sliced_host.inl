@@ -9,14 +9,13 @@ struct SlicedEngine {
     uint32_t* probe_data; uint8_t* ans; unsigned int* probe_cursor; uint32_t* probe_roff; int probe_B;
     uint32_t* pos;
     uint2* tile_meta;             // per tile sort of probes: where each bucket's run went (TileSort::run), B + 1 entries per tile
-    // insert: keys by range, hash table, dense distinct keys, raises
+    // insert: keys by range, hash table, dense distinct keys (raises need no buffers: they ride the answer bytes of the probe records)
     unsigned long long* key_data; unsigned int* key_cursor; uint32_t* key_roff; int key_B; int key_shift;   // level 1: key_B ranges
     unsigned long long* sub_data; unsigned int* sub_cursor; int sub_bits; uint32_t sub_cap;                   // level 2: key_B << sub_bits sub-ranges
     unsigned long long* dkey; unsigned int* dmult; unsigned int* n_distinct;
     // heavy hitters (RB_SLICED_SPILL=1, off by default until it has been measured): keys that overflow their range / sub-range
     bool spill_on; unsigned long long* spill_keys; unsigned int* spill_cursor; uint32_t spill_cap;
     unsigned long long* htab_keys; unsigned int* htab_counts; int64_t htab_slots; int htab_shift;
-    uint32_t* raise_data; unsigned int* raise_cursor; uint32_t* raise_roff;
     int* chunk_prefix;
     int* overflow;
 };
@@ -28,7 +27,6 @@ static void sliced_engine_free(rb_graph* g) {
     cudaFree(e->key_data); cudaFree(e->key_cursor); cudaFree(e->key_roff);
     cudaFree(e->spill_keys); cudaFree(e->spill_cursor); cudaFree(e->htab_keys); cudaFree(e->htab_counts);
     cudaFree(e->sub_data); cudaFree(e->sub_cursor); cudaFree(e->dkey); cudaFree(e->dmult); cudaFree(e->n_distinct);
-    cudaFree(e->raise_data); cudaFree(e->raise_cursor); cudaFree(e->raise_roff);
     cudaFree(e->chunk_prefix); cudaFree(e->overflow);
     delete e;
     g->se = nullptr;
@@ -122,13 +120,9 @@ static int32_t sliced_engine_get(rb_graph* g, int64_t n_round, SlicedEngine** ou
         else if (sg.cbf_log2 < 31) ++sg.cbf_log2;
         else break;
     }
-    sg.shard_d = sg.shard_c = sg.shard_r = 0; sg.region_div = 1;
+    sg.shard_d = sg.shard_c = 0; sg.region_div = 1;
     e->paired = sl_pair_geometry(g->dbg->size, g->cbf->size, g->hd, g->hc, 1, &sg);
-    sg.raise_log2 = std::min(sg.cbf_log2, env_int("RB_SLICE_RAISE_LOG2", 25, 2, 25));
-    while (div_up(g->cbf->size, 1LL << sg.raise_log2) > kSlMaxRegions && sg.raise_log2 < std::min(sg.cbf_log2, 25)) ++sg.raise_log2;
-    const int64_t n_raise = div_up(g->cbf->size, 1LL << sg.raise_log2);
-    sg.n_raise = (int)std::min<int64_t>(n_raise, 1 << 20);
-    if (g->hd > kSlMaxH || g->hc > kSlMaxH || sg.n_dbg + sg.n_cbf > kSlMaxRegions || n_raise > kSlMaxRegions) { e->unsupported = true; return RB_OK; }
+    if (g->hd > kSlMaxH || g->hc > kSlMaxH || sg.n_dbg + sg.n_cbf > kSlMaxRegions) { e->unsupported = true; return RB_OK; }
     const int64_t n_max = sl_pow2_at_least(n_round);
     e->n_max = n_max;
     // duplicates of a key are found in sub-ranges of ~2^RB_SLICED_SUBRANGE_LOG2 keys (two tile sorts: key_B ranges x 2^sub_bits each)
@@ -152,7 +146,6 @@ static int32_t sliced_engine_get(rb_graph* g, int64_t n_round, SlicedEngine** ou
     // ---- capacities ----
     const double dbg_slices = std::max(1.0, (double)g->dbg->size / (double)(1LL << sg.dbg_log2));
     const double cbf_slices = std::max(1.0, (double)g->cbf->size / (double)(1LL << sg.cbf_log2));
-    const double raise_slices = std::max(1.0, (double)g->cbf->size / (double)(1LL << sg.raise_log2));
     std::vector<int64_t> caps;
     if (e->paired) {
         for (int b = 0; b < sg.n_pair; ++b) caps.push_back(sl_capacity((double)n_max * g->hd / (double)sg.n_pair));
@@ -160,16 +153,13 @@ static int32_t sliced_engine_get(rb_graph* g, int64_t n_round, SlicedEngine** ou
         for (int b = 0; b < sg.n_dbg; ++b) caps.push_back(sl_capacity((double)n_max * g->hd / dbg_slices));
         for (int b = 0; b < sg.n_cbf; ++b) caps.push_back(sl_capacity((double)n_max * g->hc / cbf_slices));
     }
-    int64_t probe_slots = 0, key_slots = 0, raise_slots = 0;
+    int64_t probe_slots = 0, key_slots = 0;
     int32_t rc = sl_make_roff(ctx, caps, &e->probe_roff, &probe_slots);
     if (rc) { sliced_engine_free(g); return rc; }
     caps.assign((size_t)e->key_B, getenv("RB_SLICED_KEYCAP") ? (int64_t)env_int("RB_SLICED_KEYCAP", 1 << 20, 8, 1 << 30) : sl_capacity((double)n_max / e->key_B));
     rc = sl_make_roff(ctx, caps, &e->key_roff, &key_slots);
     if (rc) { sliced_engine_free(g); return rc; }
-    caps.assign((size_t)sg.n_raise, sl_capacity((double)n_max * g->hc / raise_slices));
-    rc = sl_make_roff(ctx, caps, &e->raise_roff, &raise_slots);
-    if (rc) { sliced_engine_free(g); return rc; }
-    const int maxB = std::max(std::max(e->probe_B, e->key_B), sg.n_raise);
+    const int maxB = std::max(e->probe_B, e->key_B);
     const int nj = e->paired ? 3 : kSlNJ;
     const int64_t n_tiles = n_max / (e->paired ? SlShape<3>::TILE : SlShape<6>::TILE) + 8;
     cudaError_t er = cudaMalloc(&e->probe_data, ((size_t)probe_slots + kSlSpill) * 4);
@@ -192,8 +182,6 @@ static int32_t sliced_engine_get(rb_graph* g, int64_t n_round, SlicedEngine** ou
     if (er == cudaSuccess) er = cudaMalloc(&e->dkey, ((size_t)n_max + 8) * 8);
     if (er == cudaSuccess) er = cudaMalloc(&e->dmult, ((size_t)n_max + 8) * 4);
     if (er == cudaSuccess) er = cudaMalloc(&e->n_distinct, 64);
-    if (er == cudaSuccess) er = cudaMalloc(&e->raise_data, ((size_t)raise_slots + kSlSpill) * 4);
-    if (er == cudaSuccess) er = cudaMalloc(&e->raise_cursor, (size_t)sg.n_raise * kSlPad * 4);
     if (er == cudaSuccess) er = cudaMalloc(&e->chunk_prefix, (size_t)(maxB + 2) * 4 + 64);
     if (er == cudaSuccess) er = cudaMalloc(&e->overflow, 64);
     if (er == cudaSuccess) er = cudaMemsetAsync(e->overflow, 0, 4, ctx->stream);
@@ -436,35 +424,19 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
         SL_LAUNCH("ks_apply_probes<0>", ks_apply_probes<0>, grid, sm_pre, probes, e->chunk_prefix, e->sg, g->dbg->dev, g->cbf->dev, e->ans, (const int*)nullptr);
     }
     if (with_cbf) {
-        // I6 + I7
-        const SlArena raises = sl_arena(e->raise_data, e->raise_cursor, e->raise_roff, e->sg.n_raise, sl_chunk());
-        CK(cudaMemsetAsync(raises.cursor, 0, (size_t)raises.B * kSlPad * 4, ctx->stream));
+        // I6: the new counter values go back over the answer bytes of the probe records; I7: a second sweep over the same regions applies
+        // them.  Nothing is sorted and nothing can overflow here: once the probes are routed the round always completes.
         const uint64_t seed = ctx->rng_seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(ctx->launches + 1);
-        const size_t sm_r = std::max(TileSort<uint32_t, kSlTileRecords>::smem_bytes(raises.B), TileAnswers::smem_bytes(probes.B, kSlThreads * kSlTileRecords));
-        // A raise region that overflows (hash skew beyond the slack) is only seen after the dbgbf bits were set -- but the answers of
-        // the round are still there and a raise is a max, so the raise phase can simply be repeated with the keys spread over more
-        // passes: an aborted pass applies nothing (ks_apply_raises sees the flag), a repeated raise changes nothing.
-        for (int n_pass = 1;; n_pass *= 2) {
-            if (n_pass > 256) return fail(ctx, RB_ESTATE, "sliced engine: raise regions overflow even with the keys spread over 256 passes");
-            bool over = false;
-            for (int pass = 0; pass < n_pass && !over; ++pass) {
-                CK(cudaMemsetAsync(raises.cursor, 0, (size_t)raises.B * kSlPad * 4, ctx->stream));
-                if (e->paired) SL_LAUNCH("ks_combine_insert", ks_combine_insert<3>, grid_d, sm_r, e->dkey, e->dmult, e->n_distinct, e->pos, e->tile_meta, probes.B, e->ans, hm, e->sg,
-                                         policy, seed, raises, e->overflow, (const int*)nullptr, pass, n_pass);
-                else SL_LAUNCH("ks_combine_insert", ks_combine_insert<6>, grid_d, sm_r, e->dkey, e->dmult, e->n_distinct, e->pos, e->tile_meta, probes.B, e->ans, hm, e->sg,
-                               policy, seed, raises, e->overflow, (const int*)nullptr, pass, n_pass);
-                rc = sl_chunk_prefix(ctx, e, raises);
-                if (rc) return rc;
-                const size_t sm_rp = (size_t)(raises.B + 1) * 4;
-                rc = sl_persistent_grid(ctx, ks_apply_raises, sm_rp, &grid);
-                if (rc) return rc;
-                SL_LAUNCH("ks_apply_raises", ks_apply_raises, grid, sm_rp, raises, e->chunk_prefix, e->sg, g->cbf->dev, (const int*)e->overflow);
-                rc = sl_read_flag(ctx, e->overflow, &flag);
-                if (rc) return rc;
-                over = flag != 0;
-            }
-            if (!over) break;
-        }
+        const size_t sm_r = TileAnswers::smem_bytes(probes.B, kSlThreads * kSlTileRecords);
+        if (e->paired) SL_LAUNCH("ks_combine_insert", ks_combine_insert<3>, grid_d, sm_r, e->dkey, e->dmult, e->n_distinct, e->pos, e->tile_meta, probes.B, e->ans, e->sg,
+                                 policy, seed, (const int*)nullptr);
+        else SL_LAUNCH("ks_combine_insert", ks_combine_insert<6>, grid_d, sm_r, e->dkey, e->dmult, e->n_distinct, e->pos, e->tile_meta, probes.B, e->ans, e->sg,
+                       policy, seed, (const int*)nullptr);
+        rc = sl_chunk_prefix(ctx, e, probes);   // the same work list again (the consumers' counter starts from 0)
+        if (rc) return rc;
+        rc = sl_persistent_grid(ctx, ks_apply_raises, sm_pre, &grid);
+        if (rc) return rc;
+        SL_LAUNCH("ks_apply_raises", ks_apply_raises, grid, sm_pre, probes, e->chunk_prefix, e->sg, g->cbf->dev, (const uint8_t*)e->ans, (const int*)nullptr);
     }
     claim_invalidate(ctx);   // bits were set without going through the claim table
     return RB_OK;

@@ -38,6 +38,8 @@ struct rb_ctx {
     cudaEvent_t ev_kernel[2] = {nullptr, nullptr};  // kernel of parity p finished (results ready in staging p)
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};    // D2H out of staging p finished (staging p reusable)
     int64_t count_launch_index = 0;
+    cudaEvent_t ticket_ev[8] = {};                  // rb_graph_count_reads_async: ticket t completes with event (t - 1) % 8 on the copy stream
+    int64_t ticket_seq = 0;
     unsigned long long* scratch = nullptr;  // 8-byte device scalar
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // per-kernel CUDA-event timing (rb_ctx_profile_enable / rb_ctx_profile_read): bench.py's roofline numbers come from here
@@ -164,7 +166,7 @@ static HashMults make_hm(int k) {
 static inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- context ---------------------------------------------------------------------------------------------------------
-extern "C" int32_t rb_version(void) { return 110; }   // 110: sliced engine, rb_sshard_*, neighbour query, profile spans
+extern "C" int32_t rb_version(void) { return 120; }   // 120: raises ride the probe records' answer bytes, rb_graph_count_reads_async / rb_ctx_wait
 
 extern "C" int32_t rb_ctx_create(int32_t device, rb_ctx** out) {
     if (!out) return fail(nullptr, RB_EINVAL, "rb_ctx_create: out is NULL");
@@ -210,6 +212,7 @@ extern "C" int32_t rb_ctx_destroy(rb_ctx* ctx) {
         if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
         for (int i = 0; i < 32; ++i) if (ctx->stage[i]) cudaFree(ctx->stage[i]);
         for (int i = 0; i < 2; ++i) { if (ctx->ev_kernel[i]) cudaEventDestroy(ctx->ev_kernel[i]); if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]); }
+        for (int i = 0; i < 8; ++i) if (ctx->ticket_ev[i]) cudaEventDestroy(ctx->ticket_ev[i]);
         if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
         if (ctx->claim) cudaFree(ctx->claim);
         if (ctx->scratch) cudaFree(ctx->scratch);
@@ -1120,22 +1123,26 @@ static int32_t ascii_pack(rb_ctx* ctx, const char* bases, const char* quals, con
     std::vector<int64_t> word_off((size_t)n_reads + 1), read_off((size_t)n_reads);
     std::vector<int32_t> read_len((size_t)n_reads);
     int64_t words = 0;
+    bool same_len = true;   // untrimmed short reads: every record has the same length -> the uniform ingest layout (prefix k-merizer, no per-read tables)
     for (int64_t r = 0; r < n_reads; ++r) {
         const int64_t len = ascii_off[r + 1] - ascii_off[r];
         if (len < 0 || len > INT32_MAX) return fail(ctx, RB_EINVAL, "ascii_off must be non-decreasing");
         word_off[(size_t)r] = words; read_off[(size_t)r] = words * 32; read_len[(size_t)r] = (int32_t)len;
         words += (len + 31) / 32;
+        same_len = same_len && len == ascii_off[1] - ascii_off[0];
     }
+    const int64_t len0 = ascii_off[1] - ascii_off[0];
+    const bool uniform = same_len && len0 > 0 && !getenv("RB_ASCII_RAGGED");
     word_off[(size_t)n_reads] = words;
     const int64_t a_lo = ascii_off[0], a_hi = ascii_off[n_reads];
-    void *d_b, *d_q = nullptr, *d_ao, *d_wo, *d_ro, *d_rl, *d_packed, *d_mask, *d_rcm;
+    void *d_b, *d_q = nullptr, *d_ao, *d_wo, *d_ro = nullptr, *d_rl = nullptr, *d_packed, *d_mask, *d_rcm;
     int32_t rc;
     if ((rc = stage_get(ctx, 16, (a_hi - a_lo) + 16, &d_b))) return rc;
     if (quals && (rc = stage_get(ctx, 17, (a_hi - a_lo) + 16, &d_q))) return rc;
     if ((rc = stage_get(ctx, 18, (n_reads + 1) * 8, &d_ao))) return rc;
     if ((rc = stage_get(ctx, 19, (n_reads + 1) * 8, &d_wo))) return rc;
-    if ((rc = stage_get(ctx, 20, n_reads * 8, &d_ro))) return rc;
-    if ((rc = stage_get(ctx, 21, n_reads * 4, &d_rl))) return rc;
+    if (!uniform && (rc = stage_get(ctx, 20, n_reads * 8, &d_ro))) return rc;
+    if (!uniform && (rc = stage_get(ctx, 21, n_reads * 4, &d_rl))) return rc;
     if ((rc = stage_get(ctx, 22, (words + 2) * 8, &d_packed))) return rc;
     if ((rc = stage_get(ctx, 23, (words + 2) * 4, &d_mask))) return rc;
     if ((rc = stage_get(ctx, 24, (words + 2) * 4, &d_rcm))) return rc;
@@ -1143,8 +1150,10 @@ static int32_t ascii_pack(rb_ctx* ctx, const char* bases, const char* quals, con
     if (quals) CK(cudaMemcpyAsync(d_q, quals + a_lo, (size_t)(a_hi - a_lo), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_ao, ascii_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_wo, word_off.data(), (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_ro, read_off.data(), (size_t)n_reads * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_rl, read_len.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (!uniform) {
+        CK(cudaMemcpyAsync(d_ro, read_off.data(), (size_t)n_reads * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_rl, read_len.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
     if (words > 0) {
         RB_LAUNCH((int)div_up(words, kThreads), kThreads, 0, ctx->stream, k_pack_ascii)((const char*)d_b - a_lo, d_q ? (const char*)d_q - a_lo : nullptr, (const int64_t*)d_ao,
                                                                                  (const int64_t*)d_wo, n_reads, words, min_qual, (uint64_t*)d_packed,
@@ -1152,7 +1161,8 @@ static int32_t ascii_pack(rb_ctx* ctx, const char* bases, const char* quals, con
         LAUNCH_CHECK();
     }
     CK(cudaStreamSynchronize(ctx->stream));   // the host vectors go out of scope
-    *out = ReadsArg{(const uint64_t*)d_packed, (const uint32_t*)d_mask, (const int64_t*)d_ro, (const int32_t*)d_rl, n_reads, 0, 0, true};
+    if (uniform) *out = ReadsArg{(const uint64_t*)d_packed, (const uint32_t*)d_mask, nullptr, nullptr, n_reads, (int32_t)len0, ((len0 + 31) / 32) * 32, true};
+    else *out = ReadsArg{(const uint64_t*)d_packed, (const uint32_t*)d_mask, (const int64_t*)d_ro, (const int32_t*)d_rl, n_reads, 0, 0, true};
     out->rcm = (const uint32_t*)d_rcm;
     return RB_OK;
 }
@@ -1304,9 +1314,12 @@ static int32_t count_launch(rb_ctx* ctx, const Ingest& ing_in, void* user) {
     }
     return RB_OK;
 }
-static int32_t graph_count_reads(rb_graph* g, const ReadsArg& ra, float* counts, int64_t* fh, int64_t* rh, int64_t* n_out, bool results_on_device) {
+// big_rounds: host results, but the caller does not wait for them (rb_graph_count_reads_async): one round as large as for device results,
+// its results parked in device staging while the copy stream drains them behind the caller's next calls
+static int32_t graph_count_reads(rb_graph* g, const ReadsArg& ra, float* counts, int64_t* fh, int64_t* rh, int64_t* n_out, bool results_on_device,
+                                 bool big_rounds = false) {
     CountUser u{g, g->stranded ? RB_MODE_FWD : RB_MODE_CANON, counts, fh, g->stranded ? nullptr : rh, results_on_device};
-    RoundSize rs(g, !results_on_device);
+    RoundSize rs(g, !results_on_device && !big_rounds);
     return for_each_launch(g->ctx, ra, g->k, count_launch, &u, n_out);
 }
 extern "C" int32_t rb_graph_count_reads(rb_graph* g, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
@@ -1321,6 +1334,35 @@ extern "C" int32_t rb_graph_count_reads(rb_graph* g, const uint64_t* packed, con
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->copy_stream));
     return RB_OK;
+}
+// The same without waiting for the results: the call returns when the last round's kernels are queued; the device->host copies run on
+// the copy stream behind whatever the caller does next (typically the next rb_graph_add_reads: 2 GB of counts per 504 M k-mers take
+// longer over PCIe than the look-up kernels themselves).  `packed` / `mask` and the result buffers (pinned host memory) must stay
+// untouched until rb_ctx_wait(ticket) returns.
+extern "C" int32_t rb_graph_count_reads_async(rb_graph* g, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
+                                              int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, float* counts, int64_t* fhash, int64_t* rhash,
+                                              int64_t* n_kmers_out, int64_t* ticket) {
+    if (!g || !ticket) return RB_EINVAL;
+    rb_ctx* ctx = g->ctx;
+    LOCK(ctx);
+    ReadsArg ra{packed, mask, read_off, read_len, n_reads, uniform_len, uniform_stride, false};
+    const int32_t rc = graph_count_reads(g, ra, counts, fhash, rhash, n_kmers_out, false, true);
+    if (rc) { cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->copy_stream); return rc; }
+    const int slot = (int)(ctx->ticket_seq % 8);
+    if (!ctx->ticket_ev[slot]) CK(cudaEventCreateWithFlags(&ctx->ticket_ev[slot], cudaEventDisableTiming));
+    // the copy stream has every D2H of this call queued behind its kernels (count_launch); a call without any launch completes at once
+    CK(cudaEventRecord(ctx->ticket_ev[slot], ctx->copy_stream));
+    *ticket = ++ctx->ticket_seq;
+    return RB_OK;
+}
+// Blocks until the results of that call (and of every earlier asynchronous call) are in host memory.  Takes no lock: a thread may wait
+// while another one is inside an insert call of the same context.
+extern "C" int32_t rb_ctx_wait(rb_ctx* ctx, int64_t ticket) {
+    if (!ctx || ticket < 1 || ticket > ctx->ticket_seq) return RB_EINVAL;
+    cudaEvent_t ev = ctx->ticket_ev[(ticket - 1) % 8];   // a slot recorded again by a later ticket completes later on the same stream: still correct
+    if (!ev) return RB_EINVAL;
+    const cudaError_t e = cudaEventSynchronize(ev);
+    return e == cudaSuccess ? RB_OK : RB_ECUDA;
 }
 extern "C" int32_t rb_graph_count_reads_dev(rb_graph* g, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off,
                                             const int32_t* read_len, int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, float* counts,

@@ -39,6 +39,10 @@ class Context:
     def sync(self):
         self.check(self.L.rb_ctx_sync(self.h))
 
+    def wait(self, ticket):
+        """rb_ctx_wait: the results of the asynchronous call with this ticket (and of all earlier ones) are in host memory."""
+        self.check(self.L.rb_ctx_wait(self.h, ticket))
+
     def set_stream(self, cuda_stream_ptr):
         self.check(self.L.rb_ctx_set_stream(self.h, cuda_stream_ptr))
 
@@ -496,6 +500,12 @@ class BloomFilterDeBruijnGraph:
         self.ctx.check(self.ctx.L.rb_graph_count_reads(self.h, *reads.args(), _ptr(counts), _ptr(fh), _ptr(rh), C.byref(got)))
         assert got.value == n
         return counts, fh, rh
+
+    def getKmersAsync(self, reads, counts, fh=None, rh=None):
+        """rb_graph_count_reads_async: results land in the caller's (pinned) arrays once Context.wait(ticket) has returned."""
+        got, ticket = C.c_int64(), C.c_int64()
+        self.ctx.check(self.ctx.L.rb_graph_count_reads_async(self.h, *reads.args(), _ptr(counts), _ptr(fh), _ptr(rh), C.byref(got), C.byref(ticket)))
+        return ticket.value
 
     def getKmersDev(self, packed_dev, n_reads, uniform_len, uniform_stride, counts_dev, fhash_dev=None, rhash_dev=None):
         n = C.c_int64()

@@ -55,10 +55,10 @@ SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_
 SPILL_ENV = {"RB_SLICED_SPILL": "1", "RB_SLICED_SUBCAP": "40", "RB_SLICED_KEYCAP": "1500"}
 ONLY = {
     "sliced-small-spill": ("test_duplicates_inside_one_batch_are_linearised", "test_skewed_batch_is_redone_by_the_direct_engine"),
-    "direct": ("test_getkmers_with_invalid_nucleotides", "test_neighbor_counts_match_oracle", "test_kmerize_ascii_is_exact_for_every_character",
+    "direct": ("test_getkmers_with_invalid_nucleotides", "test_equal_length_ascii_records_and_async_counts", "test_neighbor_counts_match_oracle", "test_kmerize_ascii_is_exact_for_every_character",
                "test_cascading_bloom_filter_matches_oracle", "test_loaded_cbf_envelope_at_scale", "test_2bit_fragment_records_round_trip",
                "test_variants_max_cov_and_greedy_extension_match_oracle", "test_stage1_driver_writes_the_reference_files"),
-    "sliced-default": ("test_getkmers_with_invalid_nucleotides", "test_insert_policies_and_pair_filters", "test_kernels_are_race_free_under_tsan",
+    "sliced-default": ("test_getkmers_with_invalid_nucleotides", "test_equal_length_ascii_records_and_async_counts", "test_insert_policies_and_pair_filters", "test_kernels_are_race_free_under_tsan",
                        "test_random_geometry_matches_oracle", "test_random_uniform_layout_matches_oracle", "test_paired_slices_match_oracle",
                        "test_config3_settings_match_oracle", "test_config4_long_reads_match_oracle", "test_loaded_cbf_envelope_at_scale"),
 }
@@ -92,6 +92,7 @@ def engine(request):
 test_duplicates_inside_one_batch_are_linearised = G.test_duplicates_inside_one_batch_are_linearised
 test_getkmers_with_invalid_nucleotides = G.test_getkmers_with_invalid_nucleotides
 test_kmerize_ascii_is_exact_for_every_character = G.test_kmerize_ascii_is_exact_for_every_character
+test_equal_length_ascii_records_and_async_counts = G.test_equal_length_ascii_records_and_async_counts
 test_cascading_bloom_filter_matches_oracle = G.test_cascading_bloom_filter_matches_oracle
 test_2bit_fragment_records_round_trip = G.test_2bit_fragment_records_round_trip
 test_stage1_driver_writes_the_reference_files = G.test_stage1_driver_writes_the_reference_files

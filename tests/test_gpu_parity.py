@@ -558,6 +558,52 @@ def test_fastq_ascii_ingest_matches_regex_segmentation(ctx, orc, kat):
     g.destroy(), og.close()
 
 
+def test_equal_length_ascii_records_and_async_counts(ctx, orc):
+    """Records of one length take the uniform ingest layout inside the ASCII entry points (prefix k-merizer, no per-read tables): same
+    filters, counts and hashes as the oracle and as the ragged path; rb_graph_count_reads_async + rb_ctx_wait return what the blocking
+    call returns."""
+    rng = np.random.default_rng(97)
+    L = 151
+    seqs, quals = [], []
+    for _ in range(500):
+        s = rng.choice(list("ACGT"), size=L)
+        s[rng.random(L) < 0.01] = "N"
+        q = rng.integers(35, 74, size=L)
+        q[rng.random(L) < 0.03] = 33 + rng.integers(0, 3)
+        seqs.append("".join(s)), quals.append("".join(chr(x) for x in q))
+    bases = all_bases(orc, seqs, 25, [MODE_CANON])
+    for ragged in (False, True):
+        g, og = make_graphs(ctx, orc, (1 << 28) + 1, (1 << 26) + 1, 64, 3, 3, 1, 25, False, False)
+        for s_, q_ in zip(seqs, quals):
+            og.add_read(s_, q_, 3)
+        if ragged:
+            os.environ["RB_ASCII_RAGGED"] = "1"
+        try:
+            g.addReadsAscii(seqs, quals, 3)
+            assert_same_state(g, og, bases=bases)
+            seqs2 = ["".join(IUPAC[rng.integers(len(IUPAC))] if ch == "N" else ch for ch in s_) for s_ in seqs]
+            counts, fh, rh = g.getKmersAscii(seqs2)
+        finally:
+            os.environ.pop("RB_ASCII_RAGGED", None)
+        want = [og.count_seq(s_) for s_ in seqs2]
+        assert (counts == np.concatenate([w[0] for w in want])).all()
+        assert (fh == np.concatenate([w[1] for w in want])).all() and (rh == np.concatenate([w[2] for w in want])).all()
+        if not ragged:
+            pr = rb.pack_reads(seqs)
+            c0, f0, r0 = g.getKmers(pr)
+            n = c0.size
+            tickets, outs = [], []
+            for _ in range(3):   # several calls in flight, results double-buffered by the caller
+                c1, f1, r1 = ctx.host_alloc(n * 4, np.float32), ctx.host_alloc(n * 8, np.int64), ctx.host_alloc(n * 8, np.int64)
+                tickets.append(g.getKmersAsync(pr, c1, f1, r1)), outs.append((c1, f1, r1))
+            for t, (c1, f1, r1) in zip(tickets, outs):
+                ctx.wait(t)
+                assert (c1 == c0).all() and (f1 == f0).all() and (r1 == r0).all()
+            with pytest.raises(rb.RBError):
+                ctx.wait(tickets[-1] + 1)
+        g.destroy(), og.close()
+
+
 def test_getkmers_with_invalid_nucleotides(ctx, orc):
     rng = np.random.default_rng(37)
     seqs = rand_reads(rng, 120, 10, 300, n_rate=0.01)
