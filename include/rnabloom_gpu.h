@@ -262,6 +262,19 @@ RB_API int32_t rb_graph_sync_to_host(rb_graph* g, void* dbgbf, void* cbf, void* 
 RB_API int32_t rb_graph_save(rb_graph* g, const char* path);
 RB_API int32_t rb_graph_load(rb_ctx* ctx, const char* path, int32_t load_dbgbf, int32_t load_fpkbf, rb_graph** out);
 
+/* ---- f4: a lone Bloom filter over whole sequences: the screening filter of the assembly stages -------------------
+ * op RB_SEQ_ADD                for (Kmer kmer : kmers) bf.add(kmer.getHash())              RNABloom.java:1680,2536,2553,2607,2624
+ *    RB_SEQ_CONTAINS_ALL       all_found[r] = containsAllKmers(bf, kmers of read r)         util/GraphUtils.java:627-640 (false for a read without k-mers
+ *                                                                                           or with a k-mer over an unusable base: "kmer == null")
+ *    RB_SEQ_LOOKUP_AND_ADD_ALL all_found[r] = lookupAndAddAllKmers(bf, kmers of read r)     util/GraphUtils.java:642-650, RNABloom.java:4264
+ * mode: RB_MODE_FWD / RB_MODE_RC / RB_MODE_CANON = which hash Kmer.getHash() is (graph/Kmer.java, CanonicalKmer.java).  Host pointers, reads
+ * as in rb_graph_add_reads; all_found (n_reads bytes, NULL for RB_SEQ_ADD) in host memory.  The final bit array is the same for any order
+ * of the reads; the answers of RB_SEQ_LOOKUP_AND_ADD_ALL for two reads of one batch that share a k-mer depend on their order, exactly as
+ * they do between the reference's worker threads, which share the screening filter without a lock. */
+enum { RB_SEQ_ADD = 0, RB_SEQ_CONTAINS_ALL = 1, RB_SEQ_LOOKUP_AND_ADD_ALL = 2 };
+RB_API int32_t rb_filter_seq_op(rb_filter* f, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
+                                int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, int32_t mode, int32_t op, uint8_t* all_found);
+
 /* ---- synthetic workload generator (bench + fixtures; not a reference operator) ----------------------------------
  * Deterministic, counter-based: read r of a virtual genome (seed, genome_len), length L, err_ppm substitutions per
  * 1e6 bases; written in the uniform ingest layout (stride = stride_bases, multiple of 32) into device memory. */

@@ -150,6 +150,7 @@ def bind(path, allow_missing=False):
         "rb_graph_count_reads_dev": (i32, [vp] + reads + [vp, vp, vp, C.POINTER(i64)]),
         "rb_graph_count_reads_async": (i32, [vp] + reads + [vp, vp, vp, C.POINTER(i64), C.POINTER(i64)]),
         "rb_ctx_wait": (i32, [vp, i64]),
+        "rb_filter_seq_op": (i32, [vp] + reads + [i32, i32, vp]),
         "rb_graph_add_hashes": (i32, [vp, vp, i64, u32]),
         "rb_graph_count_hashes": (i32, [vp, vp, i64, vp]),
         "rb_graph_add_pair_hashes": (i32, [vp, i32, vp, i64]),

@@ -334,6 +334,7 @@ struct Ingest {
     int32_t uniform_npos;     // positions per read in the uniform layout
     int64_t first_base;       // uniform layout: base offset of read 0 of this launch
     int64_t pos_bias;         // pos_off value of read 0 of this launch (pos_off holds absolute prefix values)
+    int64_t read_base;        // index of read 0 of this launch in the caller's per-read outputs
 };
 
 // per-CTA lookup tables for the rolling update (a3: NTHash.java:584-586, 627-629, 491-495)

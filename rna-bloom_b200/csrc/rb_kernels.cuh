@@ -374,6 +374,37 @@ __global__ void __launch_bounds__(kThreads) k_pairs(const Ingest g, const GraphD
     }
 }
 
+// ---- f4: a lone Bloom filter over whole sequences -- the screening filter of the assembly stages (RNABloom.java:1680,2530-2536,4264;
+// util/GraphUtils.java:627-650).  SEQ_OP 0: bf.add(kmer.getHash()) for every k-mer; 1: containsAllKmers; 2: lookupAndAddAllKmers.
+// missing[r] is set when a k-mer of read r was not found, or is unusable ("kmer == null" :635); the caller has cleared it.  A read without
+// any k-mer is the host's business (containsAllKmers :629-631 returns false, lookupAndAddAllKmers true).
+enum { SEQ_ADD = 0, SEQ_CONTAINS_ALL = 1, SEQ_LOOKUP_AND_ADD_ALL = 2 };
+template <int MODE, int MAXH, int SEQ_OP>
+__global__ void __launch_bounds__(kThreads) k_seq_filter(const Ingest g, int k, const BitFilter bf, const HashMults hm, uint8_t* __restrict__ missing) {
+    __shared__ RollLut lut;
+    build_lut(&lut, k);
+    const int64_t pos = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * kChunk;
+    if (pos >= g.n_pos) return;
+    const int n = (int)min((int64_t)kChunk, g.n_pos - pos);
+    PositionWalker<MODE> pw;
+    pw.start(g, pos, k, lut);
+    for (int i = 0; i < n; ++i) {
+        pw.advance(g, k, lut);
+        bool found = false;
+        if (pw.wk.bad == 0) {
+            const uint64_t b = pw.wk.base();
+            if (SEQ_OP == SEQ_ADD) { bf_add<MAXH>(bf, b, hm); found = true; }
+            else {
+                found = bf_lookup<MAXH>(bf, b, hm);
+                // lookupThenAdd (bloom/BloomFilter.java:147-155) returns whether every bit was set before; two copies of a k-mer in one
+                // batch may both report "absent" -- the reference's worker threads race in the same way on the shared screening filter
+                if (SEQ_OP == SEQ_LOOKUP_AND_ADD_ALL && !found) bf_add<MAXH>(bf, b, hm);
+            }
+        }
+        if (SEQ_OP != SEQ_ADD && !found) missing[g.read_base + pw.read] = 1;
+    }
+}
+
 // ---- per-hash operators: the `long hashVal` overloads (bloom/BloomFilter.java:139-182, CountingBloomFilter.java:126-251) -
 enum { OP_BF_ADD = 0, OP_BF_LOOKUP, OP_BF_LTA, OP_CBF_INC, OP_CBF_INC_GET, OP_CBF_COUNT, OP_GRAPH_ADD, OP_GRAPH_COUNT_IF_PRESENT,
        OP_GRAPH_COUNT };

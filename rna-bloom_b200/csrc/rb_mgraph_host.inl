@@ -162,6 +162,7 @@ extern "C" int32_t rb_mgraph_destroy(rb_mgraph* mg) {
 #ifndef RB_EMU
     if (mg->own_comm && mg->nccl.comm) g_nccl.CommDestroy(mg->nccl.comm);
 #endif
+    if (mg->dbg && mg->dbg->cs) cells_destroy(mg->dbg->cs);
     if (mg->dbg) filter_free(mg->dbg);
     if (mg->cbf) filter_free(mg->cbf);
     cudaFree(mg->probe_cursor); cudaFree(mg->key_cursor); cudaFree(mg->cons_cursor); cudaFree(mg->sub_cursor);
@@ -349,6 +350,9 @@ static int32_t mgraph_create(rb_ctx* ctx, int32_t n_ranks, int32_t rank, const r
         return rc;
     }
     mg->dbg->in_graph = mg->cbf->in_graph = true;
+    // paired slices with at most 8 chunks: the owner works on co-located cells (SlGeom::cells); rb_mgraph_filter hands out the logical
+    // arrays, converted back on demand
+    if (mg->paired && cells_create(ctx, mg->dbg, mg->cbf)) mg->sg_apply.cells = 1;
     const int maxB_all = std::max(mg->R, mg->KR) * W;
     const size_t n32_all = (size_t)mg->n_probe + kSlSpill;
     if (tr) mg->tr = *tr;
@@ -572,14 +576,20 @@ static int32_t mg_apply(rb_mgraph* mg, bool set_bits) {
                              mg->paired ? 1 << mg->sg_apply.pair_sub_log2 : 1);
     if (rc) return rc;
     if (mg->p2p) a.peer_ans = (uint8_t* const*)mg->d_peer_ans;
+    uint32_t *fd = mg->dbg->dev, *fc = mg->cbf->dev;
+    if (mg->sg_apply.cells) {
+        rc = cells_ensure_cells(ctx, mg->dbg->cs);
+        if (rc) return rc;
+        fd = fc = mg->dbg->cs->cells;
+    }
     const size_t sm_pre = (size_t)(a.B + 1) * 4;
     int grid = 0;
     if (set_bits) {
         rc = sl_persistent_grid(ctx, ks_apply_probes<1>, sm_pre, &grid); if (rc) return rc;
-        SL_LAUNCH("ks_apply_probes<1>", ks_apply_probes<1>, grid, sm_pre, a, mg->chunk_prefix, mg->sg_apply, mg->dbg->dev, mg->cbf->dev, mg->ans, (const int*)mg->flags);
+        SL_LAUNCH("ks_apply_probes<1>", ks_apply_probes<1>, grid, sm_pre, a, mg->chunk_prefix, mg->sg_apply, fd, fc, mg->ans, (const int*)mg->flags);
     } else {
         rc = sl_persistent_grid(ctx, ks_apply_probes<0>, sm_pre, &grid); if (rc) return rc;
-        SL_LAUNCH("ks_apply_probes<0>", ks_apply_probes<0>, grid, sm_pre, a, mg->chunk_prefix, mg->sg_apply, mg->dbg->dev, mg->cbf->dev, mg->ans, (const int*)mg->flags);
+        SL_LAUNCH("ks_apply_probes<0>", ks_apply_probes<0>, grid, sm_pre, a, mg->chunk_prefix, mg->sg_apply, fd, fc, mg->ans, (const int*)mg->flags);
     }
     return RB_OK;
 }
@@ -656,7 +666,13 @@ static int32_t mg_raises(rb_mgraph* mg, int policy, uint64_t seed) {
     int grid = 0;
     rc = sl_persistent_grid(ctx, ks_apply_raises, sm_pre, &grid);
     if (rc) return rc;
-    SL_LAUNCH("ks_apply_raises", ks_apply_raises, grid, sm_pre, a, mg->chunk_prefix, mg->sg_apply, mg->cbf->dev, (const uint8_t*)mg->ans, (const int*)mg->flags);
+    uint32_t* fc = mg->cbf->dev;
+    if (mg->sg_apply.cells) {   // still in cells: nothing but mg_apply ran since
+        rc = cells_ensure_cells(ctx, mg->dbg->cs);
+        if (rc) return rc;
+        fc = mg->dbg->cs->cells;
+    }
+    SL_LAUNCH("ks_apply_raises", ks_apply_raises, grid, sm_pre, a, mg->chunk_prefix, mg->sg_apply, fc, (const uint8_t*)mg->ans, (const int*)mg->flags);
     return RB_OK;
 }
 static int32_t mg_read_flags(rb_mgraph* mg, int* f2) {   // the one host synchronisation of a round

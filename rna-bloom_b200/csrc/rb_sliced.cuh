@@ -94,6 +94,12 @@ struct SlGeom {
     // paired records (NJ = 3): slice s = counters [s << pair_log2, (s + 1) << pair_log2) and, for every chunk c < dbg_bits / cbf_bytes,
     // the bits c * cbf_bytes + the same range; record = chunk << pair_log2 | offset inside the slice.  n_dbg = n_cbf = 0, n_pair regions.
     int paired, pair_log2, cbf_size_log2, n_pair;
+    // cells (paired slices with dbg_bits / cbf_bytes <= 8): the engine works on a co-located copy of both filters, one 16-bit cell per
+    // counter index ci: bits 0..7 = counter ci, bit 8 + c = dbgbf bit c * C + ci (C = counters of the share).  A paired record then costs ONE
+    // random 32-bit access instead of two (the apply kernels are bound by exactly those: ~218 G divergent L2 loads per second).
+    // The kernels receive the cell array through their dbg_words argument; k_cells_pack / k_cells_unpack convert to and from the logical
+    // arrays, which stay the layout of everything else (direct kernels, download, save, host mirror).
+    int cells;
     // A region of 2^pair_log2 counters is consumed in 2^pair_sub_log2 passes over sub-slices of 2^(pair_log2 - pair_sub_log2) counters:
     // only the sub-slice has to stay L2-resident, so a producer with many owners / slices can sort into fewer, wider regions (the tile
     // sort's cost per tile grows with the number of regions) at the price of streaming the region's records once per pass.
@@ -641,6 +647,24 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
                     li[u] = in ? __ldcs(rec + w.first + i0 + u * kSlThreads) : 0u;
                     act[u] = in && (int)((li[u] & off_mask) >> sub_shift) == w.pass;
                 }
+                if (sg.cells) {   // one access per record: the cell word holds the counter and the bit
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        wd[u] = 0;
+                        if (act[u]) wd[u] = ld_cg_keep(dbg_words + ((byte0 + (li[u] & off_mask)) >> 1), keep);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (act[u]) {
+                            const uint64_t ci = byte0 + (li[u] & off_mask);
+                            const int sh = (int)(ci & 1) * 16;
+                            const uint32_t bit = 1u << (sh + 8 + (int)(li[u] >> sg.pair_log2));
+                            if (SET && !(wd[u] & bit)) wd[u] = atomic_or_keep(dbg_words + (ci >> 1), bit, keep);
+                            __stcs(ans_out + w.first + i0 + u * kSlThreads, (uint8_t)(((wd[u] & bit) ? 0x80u : 0u) | ((wd[u] >> sh) & 0x7Fu)));
+                        }
+                    }
+                    continue;
+                }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     wd[u] = 0; wc[u] = 0;
@@ -1017,13 +1041,87 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_raises(const SlArena aren
                 li[u] = v[u] ? __ldcs(rec + w.first + i0 + u * kSlThreads) & off_mask : 0u;
                 if (arena.passes > 1 && (int)(li[u] >> sub_shift) != w.pass) v[u] = 0;   // another pass handles this sub-slice
             }
+            // cells: cbf_words is the cell array, two 16-bit cells per word, the counter in the low byte of its cell
+            const int wsh = sg.cells ? 1 : 2, bsh = sg.cells ? 16 : 8;
 #pragma unroll
-            for (int u = 0; u < U; ++u) { wd[u] = 0; if (v[u]) wd[u] = ld_cg_keep(cbf_words + ((byte0 + li[u]) >> 2), keep); }
+            for (int u = 0; u < U; ++u) { wd[u] = 0; if (v[u]) wd[u] = ld_cg_keep(cbf_words + ((byte0 + li[u]) >> wsh), keep); }
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (v[u]) byte_raise_keep(cbf_words + ((byte0 + li[u]) >> 2), (int)((byte0 + li[u]) & 3) * 8, v[u], wd[u], keep);
+                if (v[u]) byte_raise_keep(cbf_words + ((byte0 + li[u]) >> wsh), (int)((byte0 + li[u]) & (sg.cells ? 1 : 3)) * bsh, v[u], wd[u], keep);
         }
     }
+}
+
+// ---- cells <-> logical arrays (SlGeom::cells).  One thread = 32 consecutive counter indices: 8 words of counters, one word of bits per
+// chunk, 16 words of cells.  C (counters of the share) is a multiple of 32; q <= 8 chunks.
+__global__ void __launch_bounds__(kSlThreads) k_cells_pack(const uint32_t* __restrict__ dbg, const uint32_t* __restrict__ cbf, uint32_t* __restrict__ cells,
+                                                          int64_t C, int q) {
+  for (int64_t t = (int64_t)blockIdx.x * kSlThreads + threadIdx.x; t < (C >> 5); t += (int64_t)gridDim.x * kSlThreads) {
+    uint32_t bits[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) bits[c] = c < q ? __ldg(dbg + ((c * C) >> 5) + t) : 0u;
+    const uint4* src = reinterpret_cast<const uint4*>(cbf + t * 8);
+    uint4* dst = reinterpret_cast<uint4*>(cells + t * 16);
+    uint32_t any_bit = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) any_bit |= bits[c];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint4 cw = __ldg(src + h);
+        if (!(any_bit | cw.x | cw.y | cw.z | cw.w)) {   // an untouched stretch of the filters
+            dst[2 * h] = make_uint4(0u, 0u, 0u, 0u); dst[2 * h + 1] = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+        }
+        const uint32_t w4[4] = {cw.x, cw.y, cw.z, cw.w};
+        uint32_t out[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {   // counter word j of this half: counters i0 .. i0 + 3
+            const int i0 = h * 16 + j * 4;
+            uint32_t cell[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                uint32_t b = 0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) b |= ((bits[c] >> (i0 + e)) & 1u) << c;
+                cell[e] = ((w4[j] >> (8 * e)) & 0xFFu) | (b << 8);
+            }
+            out[2 * j] = cell[0] | (cell[1] << 16);
+            out[2 * j + 1] = cell[2] | (cell[3] << 16);
+        }
+        dst[2 * h] = make_uint4(out[0], out[1], out[2], out[3]);
+        dst[2 * h + 1] = make_uint4(out[4], out[5], out[6], out[7]);
+    }
+  }
+}
+__global__ void __launch_bounds__(kSlThreads) k_cells_unpack(const uint32_t* __restrict__ cells, uint32_t* __restrict__ dbg, uint32_t* __restrict__ cbf,
+                                                            int64_t C, int q) {
+  for (int64_t t = (int64_t)blockIdx.x * kSlThreads + threadIdx.x; t < (C >> 5); t += (int64_t)gridDim.x * kSlThreads) {
+    uint32_t bits[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    const uint4* src = reinterpret_cast<const uint4*>(cells + t * 16);
+    uint4* dst = reinterpret_cast<uint4*>(cbf + t * 8);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint4 a = __ldg(src + 2 * h), b4 = __ldg(src + 2 * h + 1);
+        if (!(a.x | a.y | a.z | a.w | b4.x | b4.y | b4.z | b4.w)) { dst[h] = make_uint4(0u, 0u, 0u, 0u); continue; }
+        const uint32_t in[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
+        uint32_t cw[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i0 = h * 16 + j * 4;
+            const uint32_t cell[4] = {in[2 * j] & 0xFFFFu, in[2 * j] >> 16, in[2 * j + 1] & 0xFFFFu, in[2 * j + 1] >> 16};
+            cw[j] = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                cw[j] |= (cell[e] & 0xFFu) << (8 * e);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) bits[c] |= ((cell[e] >> (8 + c)) & 1u) << (i0 + e);
+            }
+        }
+        dst[h] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) if (c < q) dbg[((c * C) >> 5) + t] = bits[c];
+  }
 }
 
 // ---- exchange helpers of the hash-sharded graph ----------------------------------------------------------------------------------------------

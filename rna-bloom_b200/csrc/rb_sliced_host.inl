@@ -77,7 +77,10 @@ static bool sl_pair_geometry(int64_t dbg_bits, int64_t cbf_bytes, int hd, int hc
     const int64_t q = dbg_bits / cbf_bytes;
     int c = 0; while ((1LL << c) < cbf_bytes) ++c;
     int w = 2;
-    while (w < c && (double)(1LL << (w + 1)) * (1.0 + (double)q / 8.0) <= 64.0 * 1024 * 1024) ++w;
+    // 64 MiB slices when the regions are (owner, slice) pairs of a sharded graph (the tile sorts pay for every region); 32 MiB on one GPU:
+    // measured (profiles/r02_notes.md) the apply kernels fetch a 64 MiB slice 2.3 times from DRAM, a 32 MiB slice stays put
+    const double slice_bytes = (n_ranks > 1 ? 64.0 : 32.0) * 1024 * 1024;
+    while (w < c && (double)(1LL << (w + 1)) * (1.0 + (double)q / 8.0) <= slice_bytes) ++w;
     w = env_int("RB_SLICE_PAIR_LOG2", w, 2, 31);
     if (w > c) w = c;
     // RB_SLICE_REGION_TARGET < the number of slices: widen the regions to 2^p sub-slices each, consumed in 2^p passes
@@ -143,6 +146,8 @@ static int32_t sliced_engine_get(rb_graph* g, int64_t n_round, SlicedEngine** ou
     { int lg = 0; while ((1LL << lg) < e->htab_slots) ++lg; e->htab_shift = 64 - lg; }
     if (e->sub_cap >= (uint32_t)kSlDedupSlots) { e->unsupported = true; return RB_OK; }   // cannot happen with lgSub <= 11, n_max <= 2^29
     e->probe_B = e->paired ? sg.n_pair : sg.n_dbg + sg.n_cbf;
+    sg.cells = 0;   // decided per round (sl_round_layout)
+    if (e->paired && !g->cells_tried) { g->cells_tried = true; cells_create(ctx, g->dbg, g->cbf); }
     // ---- capacities ----
     const double dbg_slices = std::max(1.0, (double)g->dbg->size / (double)(1LL << sg.dbg_log2));
     const double cbf_slices = std::max(1.0, (double)g->cbf->size / (double)(1LL << sg.cbf_log2));
@@ -274,6 +279,22 @@ static int32_t sl_stream_grid(rb_ctx* ctx, K kernel, size_t smem, int* grid) {
         LAUNCH_CHECK();                                                          \
     } while (0)
 
+// Which representation of dbgbf + cbf this round works on.  The cell array (one access per paired record) when the graph has one and is
+// already in it, or the round is large enough to pay for the conversion (one streaming pass over both filters), or RB_SLICED_CELLS=1.
+struct SlLayout { SlGeom sg; uint32_t *dbg, *cbf; };
+static int32_t sl_round_layout(rb_graph* g, SlicedEngine* e, int64_t n_pos, SlLayout* out) {
+    out->sg = e->sg; out->sg.cells = 0; out->dbg = g->dbg->dev; out->cbf = g->cbf->dev;
+    CellStore* cs = e->paired ? g->dbg->cs : nullptr;
+    if (!cs) return RB_OK;
+    const char* v = getenv("RB_SLICED_CELLS");
+    const bool forced = v && !strcmp(v, "1");
+    if (!(cs->in_cells || forced || n_pos >= (1LL << 24))) return RB_OK;
+    const int32_t rc = cells_ensure_cells(g->ctx, cs);
+    if (rc) return rc;
+    out->sg.cells = 1; out->dbg = cs->cells; out->cbf = cs->cells;
+    return RB_OK;
+}
+
 // S1..S3
 template <int NJ>
 static int32_t sliced_count_round_t(rb_graph* g, SlicedEngine* e, const Ingest& ing, int mode, float* counts, int64_t* fh, int64_t* rh, bool* fell_back) {
@@ -306,11 +327,14 @@ static int32_t sliced_count_round_t(rb_graph* g, SlicedEngine* e, const Ingest& 
     if (flag) { *fell_back = true; return RB_OK; }   // skewed hashes (one k-mer dominating the batch): the direct engine redoes the round
     rc = sl_chunk_prefix(ctx, e, probes);
     if (rc) return rc;
+    SlLayout lay;
+    rc = sl_round_layout(g, e, ing.n_pos, &lay);
+    if (rc) return rc;
     const size_t sm_pre = (size_t)(probes.B + 1) * 4;
     int grid = 0;
     rc = sl_persistent_grid(ctx, ks_apply_probes<0>, sm_pre, &grid);
     if (rc) return rc;
-    SL_LAUNCH("ks_apply_probes<0>", ks_apply_probes<0>, grid, sm_pre, probes, e->chunk_prefix, e->sg, g->dbg->dev, g->cbf->dev, e->ans, (const int*)nullptr);
+    SL_LAUNCH("ks_apply_probes<0>", ks_apply_probes<0>, grid, sm_pre, probes, e->chunk_prefix, lay.sg, lay.dbg, lay.cbf, e->ans, (const int*)nullptr);
     // same CTA -> k-mer mapping as the route kernel
     const size_t sm_ans = TileAnswers::smem_bytes(probes.B, TILE * NJ);
     auto k1 = ks_combine_lookup<1, NJ>;
@@ -415,13 +439,16 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     // I5 apply
     rc = sl_chunk_prefix(ctx, e, probes);
     if (rc) return rc;
+    SlLayout lay;
+    rc = sl_round_layout(g, e, ing.n_pos, &lay);
+    if (rc) return rc;
     const size_t sm_pre = (size_t)(probes.B + 1) * 4;
     if (policy != POLICY_COUNT_IF_PRESENT) {
         rc = sl_persistent_grid(ctx, ks_apply_probes<1>, sm_pre, &grid); if (rc) return rc;
-        SL_LAUNCH("ks_apply_probes<1>", ks_apply_probes<1>, grid, sm_pre, probes, e->chunk_prefix, e->sg, g->dbg->dev, g->cbf->dev, e->ans, (const int*)nullptr);
+        SL_LAUNCH("ks_apply_probes<1>", ks_apply_probes<1>, grid, sm_pre, probes, e->chunk_prefix, lay.sg, lay.dbg, lay.cbf, e->ans, (const int*)nullptr);
     } else {
         rc = sl_persistent_grid(ctx, ks_apply_probes<0>, sm_pre, &grid); if (rc) return rc;
-        SL_LAUNCH("ks_apply_probes<0>", ks_apply_probes<0>, grid, sm_pre, probes, e->chunk_prefix, e->sg, g->dbg->dev, g->cbf->dev, e->ans, (const int*)nullptr);
+        SL_LAUNCH("ks_apply_probes<0>", ks_apply_probes<0>, grid, sm_pre, probes, e->chunk_prefix, lay.sg, lay.dbg, lay.cbf, e->ans, (const int*)nullptr);
     }
     if (with_cbf) {
         // I6: the new counter values go back over the answer bytes of the probe records; I7: a second sweep over the same regions applies
@@ -436,7 +463,7 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
         if (rc) return rc;
         rc = sl_persistent_grid(ctx, ks_apply_raises, sm_pre, &grid);
         if (rc) return rc;
-        SL_LAUNCH("ks_apply_raises", ks_apply_raises, grid, sm_pre, probes, e->chunk_prefix, e->sg, g->cbf->dev, (const uint8_t*)e->ans, (const int*)nullptr);
+        SL_LAUNCH("ks_apply_raises", ks_apply_raises, grid, sm_pre, probes, e->chunk_prefix, lay.sg, lay.cbf, (const uint8_t*)e->ans, (const int*)nullptr);
     }
     claim_invalidate(ctx);   // bits were set without going through the claim table
     return RB_OK;

@@ -50,6 +50,7 @@ struct rb_ctx {
     std::vector<ProfSpan> prof_spans;
     std::vector<cudaEvent_t> prof_pool;
 };
+struct CellStore;
 struct rb_filter {
     rb_ctx* ctx;
     int kind;
@@ -59,6 +60,18 @@ struct rb_filter {
     int num_hash, k;
     uint32_t* dev;
     bool in_graph;
+    CellStore* cs;     // dbgbf / cbf of a graph whose sliced engine works on co-located cells (SlGeom::cells); nullptr otherwise
+};
+// The co-located copy of a graph's dbgbf + cbf (rb_sliced.cuh SlGeom::cells).  Exactly one of the two representations is current:
+// in_cells = the cell array (the sliced engine's rounds), else the logical arrays (everything else).  Whoever needs the other one
+// converts first (one streaming pass over both, ~5 ms for 16 GiB): cells_ensure_logical at the top of every entry point that reads or
+// writes the logical arrays, cells_ensure_cells before a sliced round.
+struct CellStore {
+    uint32_t* cells;   // C 16-bit cells
+    int64_t C;         // counters of the share (= cbf bytes)
+    int q;             // chunks of C bits in the dbgbf share
+    bool in_cells;
+    rb_filter *dbg, *cbf;
 };
 struct SlicedEngine;
 struct rb_graph {
@@ -68,6 +81,7 @@ struct rb_graph {
     int d_read, d_frag;
     int engine;            // RB_ENGINE_AUTO / RB_ENGINE_DIRECT / RB_ENGINE_SLICED
     SlicedEngine* se;      // lazily built
+    bool cells_tried;      // the cell store (g->dbg->cs) is created with the first sliced engine, once
 };
 
 static thread_local std::string g_create_err;
@@ -164,6 +178,57 @@ static HashMults make_hm(int k) {
     return hm;
 }
 static inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// grid-stride kernels: enough CTAs to fill the part (the host emulation of tests/emu runs one fiber per CUDA thread: a handful there)
+static int cells_grid(rb_ctx* ctx, const CellStore* cs) {
+#ifdef RB_EMU
+    (void)ctx;
+    return (int)std::min<int64_t>(div_up(cs->C >> 5, kSlThreads), 2);
+#else
+    return (int)std::min<int64_t>(div_up(cs->C >> 5, kSlThreads), (int64_t)ctx->sm_count * 32);
+#endif
+}
+static int32_t cells_ensure_logical(rb_ctx* ctx, CellStore* cs) {
+    if (!cs || !cs->in_cells) return RB_OK;
+    PROF("k_cells_unpack");
+    RB_LAUNCH(cells_grid(ctx, cs), kSlThreads, 0, ctx->stream, k_cells_unpack)(cs->cells, cs->dbg->dev, cs->cbf->dev, cs->C, cs->q);
+    LAUNCH_CHECK();
+    cs->in_cells = false;
+    return RB_OK;
+}
+static int32_t cells_ensure_cells(rb_ctx* ctx, CellStore* cs) {
+    if (!cs || cs->in_cells) return RB_OK;
+    PROF("k_cells_pack");
+    RB_LAUNCH(cells_grid(ctx, cs), kSlThreads, 0, ctx->stream, k_cells_pack)(cs->dbg->dev, cs->cbf->dev, cs->cells, cs->C, cs->q);
+    LAUNCH_CHECK();
+    cs->in_cells = true;
+    return RB_OK;
+}
+static int32_t filter_ensure_logical(rb_filter* f) { return f ? cells_ensure_logical(f->ctx, f->cs) : RB_OK; }
+// a cell store for the pair (dbg, cbf) if the geometry allows it (cbf_bytes = C a power of two >= 32, dbg_bits = q * C with q <= 8) and
+// the memory is there; RB_SLICED_CELLS=0 turns it off
+static CellStore* cells_create(rb_ctx* ctx, rb_filter* dbg, rb_filter* cbf) {
+    const char* v = getenv("RB_SLICED_CELLS");
+    if (v && !strcmp(v, "0")) return nullptr;
+    const int64_t C = cbf->size;
+    if (C < 32 || (C & (C - 1)) != 0 || dbg->size % C != 0 || dbg->size / C > 8) return nullptr;
+#ifdef RB_EMU
+    if (C > (1LL << 26)) return nullptr;   // tests/emu runs one fiber per CUDA thread: converting GiB-sized filters would dominate the CPU suite
+#endif
+    CellStore* cs = new CellStore();
+    cs->C = C; cs->q = (int)(dbg->size / C); cs->in_cells = false; cs->dbg = dbg; cs->cbf = cbf; cs->cells = nullptr;
+    if (cudaMalloc(&cs->cells, (size_t)C * 2 + 256) != cudaSuccess) { cudaGetLastError(); delete cs; return nullptr; }
+    (void)ctx;
+    dbg->cs = cs; cbf->cs = cs;
+    return cs;
+}
+static void cells_destroy(CellStore* cs) {
+    if (!cs) return;
+    if (cs->dbg) cs->dbg->cs = nullptr;
+    if (cs->cbf) cs->cbf->cs = nullptr;
+    cudaFree(cs->cells);
+    delete cs;
+}
 
 // ---- context ---------------------------------------------------------------------------------------------------------
 extern "C" int32_t rb_version(void) { return 120; }   // 120: raises ride the probe records' answer bytes, rb_graph_count_reads_async / rb_ctx_wait
@@ -395,7 +460,7 @@ static int32_t filter_alloc(rb_ctx* ctx, int kind, int64_t size, int num_hash, i
     if (!ctx || !out) return RB_EINVAL;
     if (size <= 0 || num_hash < 1 || num_hash > kMaxHash || k < 1) return fail(ctx, RB_EINVAL, "filter: size/num_hash/k out of range");
     rb_filter* f = new rb_filter();
-    f->ctx = ctx; f->kind = kind; f->size = size; f->num_hash = num_hash; f->k = k; f->in_graph = false;
+    f->ctx = ctx; f->kind = kind; f->size = size; f->num_hash = num_hash; f->k = k; f->in_graph = false; f->cs = nullptr;
     f->nbytes = kind == RB_BLOOM ? size / 8 + ((size % 8) ? 1 : 0) : size;  // UnsafeBitBuffer.java:44-49
     f->alloc = div_up(f->nbytes + 16, 256) * 256;
     cudaError_t e = cudaMalloc(&f->dev, (size_t)f->alloc);
@@ -428,6 +493,7 @@ extern "C" int32_t rb_filter_empty(rb_filter* f) {
     if (!f) return RB_EINVAL;
     rb_ctx* ctx = f->ctx;
     LOCK(ctx);
+    { const int32_t rc = filter_ensure_logical(f); if (rc) return rc; }
     CK(cudaMemsetAsync(f->dev, 0, (size_t)f->alloc, ctx->stream));
     claim_invalidate(ctx);
     return RB_OK;
@@ -435,7 +501,15 @@ extern "C" int32_t rb_filter_empty(rb_filter* f) {
 extern "C" int64_t rb_filter_size(const rb_filter* f) { return f ? f->size : 0; }
 extern "C" int64_t rb_filter_num_bytes(const rb_filter* f) { return f ? f->nbytes : 0; }
 extern "C" int32_t rb_filter_num_hash(const rb_filter* f) { return f ? f->num_hash : 0; }
-extern "C" int32_t rb_filter_device_ptr(rb_filter* f, void** p) { if (!f || !p) return RB_EINVAL; *p = f->dev; return RB_OK; }
+// the logical array; for a graph's filter it is current until the next read-level call on the graph
+extern "C" int32_t rb_filter_device_ptr(rb_filter* f, void** p) {
+    if (!f || !p) return RB_EINVAL;
+    LOCK(f->ctx);
+    const int32_t rc = filter_ensure_logical(f);
+    if (rc) return rc;
+    *p = f->dev;
+    return RB_OK;
+}
 
 static GraphDev filter_view(rb_filter* f) {  // a lone filter seen through the graph-shaped kernel argument
     GraphDev gd;
@@ -495,6 +569,7 @@ static int32_t run_hash_op(rb_ctx* ctx, int op, GraphDev gd, int maxh, const int
     rb_ctx* ctx = (f)->ctx;                                                                      \
     LOCK(ctx);                                                                                   \
     if ((f)->kind != (want_kind)) return fail(ctx, RB_EINVAL, "wrong filter kind for this call"); \
+    { const int32_t rc_ = filter_ensure_logical(f); if (rc_) return rc_; }                       \
     return run_hash_op(ctx, (op), filter_view(f), (f)->num_hash, base, n, (o8), (of))
 
 extern "C" int32_t rb_filter_add_hashes(rb_filter* f, const int64_t* base, int64_t n) { FILTER_OP(f, RB_BLOOM, OP_BF_ADD, nullptr, nullptr); }
@@ -508,6 +583,7 @@ extern "C" int32_t rb_filter_popcount(rb_filter* f, int64_t* out) {
     if (!f || !out) return RB_EINVAL;
     rb_ctx* ctx = f->ctx;
     LOCK(ctx);
+    { const int32_t rc = filter_ensure_logical(f); if (rc) return rc; }
     CK(cudaMemsetAsync(ctx->scratch, 0, 8, ctx->stream));
     const int64_t n_vec = f->alloc / 16;  // the padding beyond nbytes is always zero
     const int grid = (int)std::min<int64_t>(div_up(n_vec, kThreads), (int64_t)ctx->sm_count * 16);
@@ -533,6 +609,7 @@ extern "C" int32_t rb_filter_download(rb_filter* f, void* dst, int64_t nbytes) {
     rb_ctx* ctx = f->ctx;
     LOCK(ctx);
     if (nbytes != f->nbytes) return fail(ctx, RB_EINVAL, "download: nbytes must equal rb_filter_num_bytes()");
+    { const int32_t rc = filter_ensure_logical(f); if (rc) return rc; }
     CK(cudaMemcpyAsync(dst, f->dev, (size_t)nbytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return RB_OK;
@@ -542,6 +619,7 @@ extern "C" int32_t rb_filter_upload(rb_filter* f, const void* src, int64_t nbyte
     rb_ctx* ctx = f->ctx;
     LOCK(ctx);
     if (nbytes != f->nbytes) return fail(ctx, RB_EINVAL, "upload: nbytes must equal rb_filter_num_bytes()");
+    { const int32_t rc = filter_ensure_logical(f); if (rc) return rc; }
     CK(cudaMemcpyAsync(f->dev, src, (size_t)nbytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     claim_invalidate(ctx);
@@ -766,7 +844,7 @@ static int32_t for_each_launch(rb_ctx* ctx, const ReadsArg& ra, int span, Launch
                 const int64_t nr = std::min(reads_per, ra.n_reads - r0);
                 Ingest ing;
                 memset(&ing, 0, sizeof ing);
-                ing.n_reads = nr; ing.n_pos = nr * npos; ing.out_base = r0 * npos;
+                ing.n_reads = nr; ing.n_pos = nr * npos; ing.out_base = r0 * npos; ing.read_base = r0;
                 ing.uniform_stride = ra.uniform_stride; ing.uniform_len = ra.uniform_len; ing.uniform_npos = npos;
                 const int64_t b_lo = (ra.read0 + r0) * ra.uniform_stride, b_hi = (ra.read0 + r0 + nr - 1) * ra.uniform_stride + ra.uniform_len;
                 if (ra.on_device) { ing.packed = ra.packed; ing.mask = ra.mask; ing.rcm = ra.rcm; ing.first_base = b_lo; }
@@ -808,7 +886,7 @@ static int32_t for_each_launch(rb_ctx* ctx, const ReadsArg& ra, int span, Launch
             if (npos > 0) {
                 Ingest ing;
                 memset(&ing, 0, sizeof ing);
-                ing.n_reads = nr; ing.n_pos = npos; ing.out_base = pos_off[(size_t)r0]; ing.pos_bias = pos_off[(size_t)r0];
+                ing.n_reads = nr; ing.n_pos = npos; ing.out_base = pos_off[(size_t)r0]; ing.pos_bias = pos_off[(size_t)r0]; ing.read_base = r0;
                 void *d_po, *d_ro = nullptr, *d_rl = nullptr;
                 int32_t rc = stage_get(ctx, 2, (nr + 1) * 8, &d_po); if (rc) return rc;
                 CK(cudaMemcpyAsync(d_po, pos_off.data() + r0, (size_t)(nr + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -895,6 +973,66 @@ extern "C" int32_t rb_kmerize_pairs(rb_ctx* ctx, const uint64_t* packed, const u
 }
 
 // ---- graph ---------------------------------------------------------------------------------------------------------------
+// ---- f4: the screening Bloom filter over whole sequences (RNABloom.java:1680,2530-2536,4264; util/GraphUtils.java:627-650) ----------------
+struct SeqUser { rb_filter* f; int mode, op; uint8_t* missing; };
+template <int MODE, int MAXH>
+static void launch_seq_op(int op, int grid, cudaStream_t s, const Ingest& ing, int k, const BitFilter& bf, const HashMults& hm, uint8_t* missing) {
+    if (op == SEQ_ADD) RB_LAUNCH(grid, kThreads, 0, s, k_seq_filter<MODE, MAXH, SEQ_ADD>)(ing, k, bf, hm, missing);
+    else if (op == SEQ_CONTAINS_ALL) RB_LAUNCH(grid, kThreads, 0, s, k_seq_filter<MODE, MAXH, SEQ_CONTAINS_ALL>)(ing, k, bf, hm, missing);
+    else RB_LAUNCH(grid, kThreads, 0, s, k_seq_filter<MODE, MAXH, SEQ_LOOKUP_AND_ADD_ALL>)(ing, k, bf, hm, missing);
+}
+template <int MAXH>
+static void launch_seq_mode(int mode, int op, int grid, cudaStream_t s, const Ingest& ing, int k, const BitFilter& bf, const HashMults& hm, uint8_t* missing) {
+    if (mode == RB_MODE_FWD) launch_seq_op<0, MAXH>(op, grid, s, ing, k, bf, hm, missing);
+    else if (mode == RB_MODE_RC) launch_seq_op<1, MAXH>(op, grid, s, ing, k, bf, hm, missing);
+    else launch_seq_op<2, MAXH>(op, grid, s, ing, k, bf, hm, missing);
+}
+static int32_t seq_launch(rb_ctx* ctx, const Ingest& ing, void* user) {
+    SeqUser* u = (SeqUser*)user;
+    BitFilter bf; bf.words = u->f->dev; bf.fm = make_fm(u->f->size); bf.num_hash = u->f->num_hash;
+    const HashMults hm = make_hm(u->f->k);
+    const int grid = (int)div_up(div_up(ing.n_pos, kChunk), kThreads);
+    PROF("k_seq_filter");
+    if (u->f->num_hash <= 2) launch_seq_mode<2>(u->mode, u->op, grid, ctx->stream, ing, u->f->k, bf, hm, u->missing);
+    else if (u->f->num_hash <= 3) launch_seq_mode<3>(u->mode, u->op, grid, ctx->stream, ing, u->f->k, bf, hm, u->missing);
+    else if (u->f->num_hash <= 4) launch_seq_mode<4>(u->mode, u->op, grid, ctx->stream, ing, u->f->k, bf, hm, u->missing);
+    else launch_seq_mode<8>(u->mode, u->op, grid, ctx->stream, ing, u->f->k, bf, hm, u->missing);
+    LAUNCH_CHECK();
+    return RB_OK;
+}
+extern "C" int32_t rb_filter_seq_op(rb_filter* f, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
+                                    int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, int32_t mode, int32_t op, uint8_t* all_found) {
+    if (!f || n_reads < 0 || mode < 0 || mode > 2 || op < SEQ_ADD || op > SEQ_LOOKUP_AND_ADD_ALL) return RB_EINVAL;
+    if (op != SEQ_ADD && !all_found) return RB_EINVAL;
+    rb_ctx* ctx = f->ctx;
+    LOCK(ctx);
+    if (f->kind != RB_BLOOM) return fail(ctx, RB_EINVAL, "wrong filter kind for this call");
+    if (n_reads == 0) return RB_OK;
+    int32_t rc = filter_ensure_logical(f);
+    if (rc) return rc;
+    void* d_missing = nullptr;
+    if (op != SEQ_ADD) {
+        rc = stage_get(ctx, 25, n_reads, &d_missing);
+        if (rc) return rc;
+        CK(cudaMemsetAsync(d_missing, 0, (size_t)n_reads, ctx->stream));
+    }
+    SeqUser u{f, mode, op, (uint8_t*)d_missing};
+    ReadsArg ra{packed, mask, read_off, read_len, n_reads, uniform_len, uniform_stride, false};
+    rc = for_each_launch(ctx, ra, f->k, seq_launch, &u, nullptr);
+    if (rc) return rc;
+    if (op != SEQ_ADD) {
+        CK(cudaMemcpyAsync(all_found, d_missing, (size_t)n_reads, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        // missing -> found; a read without k-mers: containsAllKmers returns false (:629-631), lookupAndAddAllKmers true (empty loop)
+        for (int64_t r = 0; r < n_reads; ++r) {
+            const int64_t len = read_off ? read_len[r] : uniform_len;
+            all_found[r] = len < f->k ? (op == SEQ_LOOKUP_AND_ADD_ALL ? 1 : 0) : (all_found[r] ? 0 : 1);
+        }
+    } else CK(cudaStreamSynchronize(ctx->stream));
+    claim_invalidate(ctx);
+    return RB_OK;
+}
+
 static int engine_from_env() {   // RB_ENGINE = direct | sliced | (anything else) auto
     const char* eng = getenv("RB_ENGINE");
     return (eng && !strcmp(eng, "direct")) ? RB_ENGINE_DIRECT : (eng && !strcmp(eng, "sliced")) ? RB_ENGINE_SLICED : RB_ENGINE_AUTO;
@@ -934,6 +1072,7 @@ extern "C" int32_t rb_graph_destroy(rb_graph* g) {
     if (!g) return RB_EINVAL;
     LOCK(g->ctx);
     sliced_engine_free(g);
+    if (g->dbg && g->dbg->cs) { cudaStreamSynchronize(g->ctx->stream); cells_destroy(g->dbg->cs); }
     if (g->dbg) filter_free(g->dbg);
     if (g->cbf) filter_free(g->cbf);
     if (g->rpk) filter_free(g->rpk);
@@ -964,7 +1103,10 @@ extern "C" int32_t rb_graph_clear(rb_graph* g) {
     if (!rc && g->fpk) rc = rb_filter_empty(g->fpk);
     return rc;
 }
-static GraphDev graph_view(rb_graph* g) {
+// the graph as the direct kernels see it: the logical arrays.  need_filters = false: the caller's kernel touches neither dbgbf nor cbf (pair
+// inserts), so a graph whose current representation is the sliced engine's cell array stays that way
+static GraphDev graph_view(rb_graph* g, bool need_filters = true) {
+    if (need_filters) (void)cells_ensure_logical(g->ctx, g->dbg->cs);   // a failed launch surfaces at the caller's own launch check
     GraphDev gd;
     memset(&gd, 0, sizeof gd);
     gd.k = g->k; gd.hm = make_hm(g->k);
@@ -1054,7 +1196,7 @@ static void launch_pairs_mode(int mode, int op, int grid, cudaStream_t s, const 
 }
 static int32_t pairs_launch(rb_ctx* ctx, const Ingest& ing, void* user) {
     PairUser* u = (PairUser*)user;
-    const GraphDev gd = graph_view(u->g);
+    const GraphDev gd = graph_view(u->g, u->op == 2);   // only RB_PAIRS_EXISTING_ONLY looks the k-mers up in dbgbf
     const BitFilter pk = bit_view(u->pk);
     const int grid = (int)div_up(div_up(ing.n_pos, kChunk), kThreads);
     const int maxh = std::max(u->g->hd, u->pk->num_hash);
@@ -1274,7 +1416,6 @@ static void launch_count_mode(int mode, int grid, cudaStream_t s, const Ingest& 
 }
 static int32_t count_launch(rb_ctx* ctx, const Ingest& ing_in, void* user) {
     CountUser* u = (CountUser*)user;
-    const GraphDev gd = graph_view(u->g);
     Ingest ing = ing_in;
     float* dc = u->counts; int64_t *df = u->fh, *dr = u->rh;
     const int64_t out0 = ing.out_base;
@@ -1297,6 +1438,8 @@ static int32_t count_launch(rb_ctx* ctx, const Ingest& ing_in, void* user) {
     }
     const int grid = (int)div_up(div_up(ing.n_pos, kChunk), kThreads);
     const int maxh = u->g->hmax;
+    GraphDev gd;
+    if (!sliced_done) gd = graph_view(u->g);
     if (!sliced_done) PROF("k_graph_count");
     if (sliced_done) { /* counts are already in dc */ }
     else if (maxh <= 2) launch_count_mode<2>(u->mode, grid, ctx->stream, ing, gd, dc, df, dr);
@@ -1638,6 +1781,7 @@ extern "C" int32_t rb_graph_sync_to_host(rb_graph* g, void* dbgbf, void* cbf, vo
     rb_ctx* ctx = g->ctx;
     LOCK(ctx);
     if ((rpkbf && !g->rpk) || (fpkbf && !g->fpk)) return fail(ctx, RB_ESTATE, "sync_to_host: the graph has no such pair filter");
+    { const int32_t rc = cells_ensure_logical(ctx, g->dbg->cs); if (rc) return rc; }
     // the four copies are queued back to back (pageable destinations are staged by the driver; pinned ones run at PCIe speed)
     if (dbgbf) CK(cudaMemcpyAsync(dbgbf, g->dbg->dev, (size_t)g->dbg->nbytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (cbf) CK(cudaMemcpyAsync(cbf, g->cbf->dev, (size_t)g->cbf->nbytes, cudaMemcpyDeviceToHost, ctx->stream));

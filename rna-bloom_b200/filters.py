@@ -296,6 +296,22 @@ class BloomFilter(_Filter):
         self.ctx.check(self.ctx.L.rb_filter_lookup_then_add_hashes(self.h, _ptr(a), a.size, _ptr(out)))
         return out.astype(bool)
 
+    # ---- whole sequences against this filter: the screening filter of the assembly stages (util/GraphUtils.java:627-650) ----
+    def _seq_op(self, reads, mode, op):
+        out = np.zeros(reads.n_reads, dtype=np.uint8) if op else None
+        self.ctx.check(self.ctx.L.rb_filter_seq_op(self.h, *reads.args(), mode, op, _ptr(out)))
+        return None if out is None else out.astype(bool)
+
+    def addAllKmers(self, reads, mode=2):
+        """for (Kmer kmer : kmers) bf.add(kmer.getHash()) for every read (RNABloom.java:1680); mode 0 fwd, 1 rc, 2 canonical"""
+        self._seq_op(reads, mode, 0)
+
+    def containsAllKmers(self, reads, mode=2):
+        return self._seq_op(reads, mode, 1)
+
+    def lookupAndAddAllKmers(self, reads, mode=2):
+        return self._seq_op(reads, mode, 2)
+
     @staticmethod
     def getExpectedSize(expNumElements, fpr, numHash):
         return B.lib().rb_expected_size(expNumElements, fpr, numHash)

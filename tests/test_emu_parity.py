@@ -46,7 +46,7 @@ def ctx(emu_lib):
     c.close()
 
 
-SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_RAISE_LOG2": "14", "RB_SLICED_SUBRANGE_LOG2": "6",
+SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICED_CELLS": "1", "RB_SLICED_SUBRANGE_LOG2": "6",
              "RB_SLICE_PAIR_LOG2": "13"}
 # sliced-small: tiny slices / sub-ranges so that the small test filters span hundreds of regions (every test);
 # sliced-default: the production geometry; direct: validates the emulation itself (that engine is verified on the GPU)
@@ -55,7 +55,7 @@ SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_
 SPILL_ENV = {"RB_SLICED_SPILL": "1", "RB_SLICED_SUBCAP": "40", "RB_SLICED_KEYCAP": "1500"}
 ONLY = {
     "sliced-small-spill": ("test_duplicates_inside_one_batch_are_linearised", "test_skewed_batch_is_redone_by_the_direct_engine"),
-    "direct": ("test_getkmers_with_invalid_nucleotides", "test_equal_length_ascii_records_and_async_counts", "test_neighbor_counts_match_oracle", "test_kmerize_ascii_is_exact_for_every_character",
+    "direct": ("test_getkmers_with_invalid_nucleotides", "test_screening_filter_over_whole_sequences", "test_equal_length_ascii_records_and_async_counts", "test_neighbor_counts_match_oracle", "test_kmerize_ascii_is_exact_for_every_character",
                "test_cascading_bloom_filter_matches_oracle", "test_loaded_cbf_envelope_at_scale", "test_2bit_fragment_records_round_trip",
                "test_variants_max_cov_and_greedy_extension_match_oracle", "test_stage1_driver_writes_the_reference_files"),
     "sliced-default": ("test_getkmers_with_invalid_nucleotides", "test_equal_length_ascii_records_and_async_counts", "test_insert_policies_and_pair_filters", "test_kernels_are_race_free_under_tsan",
@@ -93,6 +93,11 @@ test_duplicates_inside_one_batch_are_linearised = G.test_duplicates_inside_one_b
 test_getkmers_with_invalid_nucleotides = G.test_getkmers_with_invalid_nucleotides
 test_kmerize_ascii_is_exact_for_every_character = G.test_kmerize_ascii_is_exact_for_every_character
 test_equal_length_ascii_records_and_async_counts = G.test_equal_length_ascii_records_and_async_counts
+
+
+@pytest.mark.parametrize("mode,k,num_hash", [(2, 25, 3), (0, 31, 2)])
+def test_screening_filter_over_whole_sequences(ctx, orc, mode, k, num_hash):
+    G.test_screening_filter_over_whole_sequences(ctx, orc, mode, k, num_hash)
 test_cascading_bloom_filter_matches_oracle = G.test_cascading_bloom_filter_matches_oracle
 test_2bit_fragment_records_round_trip = G.test_2bit_fragment_records_round_trip
 test_stage1_driver_writes_the_reference_files = G.test_stage1_driver_writes_the_reference_files
@@ -185,7 +190,7 @@ def test_random_geometry_matches_oracle(ctx, orc, seed, monkeypatch):
         dbg_bits = cbf_bytes * int(rng.integers(1, 17))
         monkeypatch.setenv("RB_SLICE_PAIR_LOG2", str(int(rng.integers(8, 19))))
         monkeypatch.setenv("RB_SLICE_REGION_TARGET", str(int(rng.choice([2, 8, 64, 512]))))   # wide regions consumed in several passes
-    for name, lo, hi in (("RB_SLICE_BITS_LOG2", 12, 22), ("RB_SLICE_BYTES_LOG2", 10, 20), ("RB_SLICE_RAISE_LOG2", 8, 18),
+    for name, lo, hi in (("RB_SLICE_BITS_LOG2", 12, 22), ("RB_SLICE_BYTES_LOG2", 10, 20), ("RB_SLICED_CELLS", 0, 1),
                          ("RB_SLICED_SUBRANGE_LOG2", 4, 9)):
         monkeypatch.setenv(name, str(int(rng.integers(lo, hi + 1))))
     if rng.integers(0, 2):
@@ -242,7 +247,7 @@ def test_random_uniform_layout_matches_oracle(ctx, orc, seed, monkeypatch):
     L = int(rng.integers(k, k + 500))
     stride = ((L + 31) // 32 + int(rng.integers(0, 3))) * 32
     n_reads = max(2, int(rng.integers(20000, 90000)) // (L - k + 1))
-    for name, lo, hi in (("RB_SLICE_BITS_LOG2", 14, 22), ("RB_SLICE_BYTES_LOG2", 12, 20), ("RB_SLICE_RAISE_LOG2", 10, 18),
+    for name, lo, hi in (("RB_SLICE_BITS_LOG2", 14, 22), ("RB_SLICE_BYTES_LOG2", 12, 20), ("RB_SLICED_CELLS", 0, 1),
                          ("RB_SLICED_SUBRANGE_LOG2", 4, 9)):
         monkeypatch.setenv(name, str(int(rng.integers(lo, hi + 1))))
     monkeypatch.setenv("RB_ENGINE", "sliced")

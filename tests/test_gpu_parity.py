@@ -28,7 +28,7 @@ ENGINE_TESTS = {"test_graph_add_collision_free_is_bit_exact", "test_duplicates_i
                 "test_config4_long_reads_match_oracle", "test_loaded_cbf_envelope_at_scale"}
 # "sliced-small": slices of 16 KiB / 32 KiB so that the small test filters span hundreds of regions (the default 64 MiB slices
 # would put every test filter into one or two regions and leave the multi-region paths to the full-size test alone)
-SMALL_SLICES = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_RAISE_LOG2": "14", "RB_SLICED_SUBRANGE_LOG2": "6",
+SMALL_SLICES = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICED_CELLS": "1", "RB_SLICED_SUBRANGE_LOG2": "6",
                 "RB_SLICE_PAIR_LOG2": "13", "RB_SLICE_REGION_TARGET": "128"}
 
 
@@ -602,6 +602,65 @@ def test_equal_length_ascii_records_and_async_counts(ctx, orc):
             with pytest.raises(rb.RBError):
                 ctx.wait(tickets[-1] + 1)
         g.destroy(), og.close()
+
+
+@pytest.mark.parametrize("mode,k,num_hash", [(MODE_CANON, 25, 3), (0, 31, 2), (MODE_CANON, 17, 4)])
+def test_screening_filter_over_whole_sequences(ctx, orc, mode, k, num_hash):
+    """f4: containsAllKmers / lookupAndAddAllKmers / add of every k-mer of a sequence against a lone Bloom filter (util/GraphUtils.java:627-650,
+    RNABloom.java:1680,2530-2536), against the per-hash oracle filter driven by the reference's loops."""
+    rng = np.random.default_rng(211 + k)
+    seqs = rand_reads(rng, 160, 5, 400, n_rate=0.002)
+    seqs += [s[: len(s) // 2] for s in seqs[:40]] + seqs[:20]            # substrings and exact copies of earlier sequences
+    size = (1 << 24) + 5
+    bf = rb.BloomFilter(ctx, size, num_hash, k)
+    lib = orc.lib
+    obf = lib.orc_bf_create(size, num_hash, k)
+
+    def kmers(s):   # Kmer.getHash() of every window; None where the window covers a non-ACGT character (graph.getKmers returns no Kmer there)
+        _, _, base = orc.kmer_hashes(s, k, mode)
+        ok = [all(ch in "ACGTacgtUu" for ch in s[i:i + k]) for i in range(len(base))]
+        return [int(b) if o else None for b, o in zip(base, ok)]
+
+    def contains_all(ks):   # GraphUtils.containsAllKmers :627-640
+        if not ks:
+            return False
+        return all(h is not None and lib.orc_bf_lookup1(obf, h) for h in ks)
+
+    first, second = seqs[:100], seqs[100:]
+    for s in first:
+        for h in kmers(s):
+            if h is not None:
+                lib.orc_bf_add1(obf, h)
+    bf.addAllKmers(rb.pack_reads(first), mode)
+    assert (bf.download() == orc.bf_array(obf)).all()
+    got = bf.containsAllKmers(rb.pack_reads(seqs), mode)
+    want = np.array([contains_all(kmers(s)) for s in seqs])
+    assert (got == want).all()
+    # lookupAndAddAllKmers: sequences of one batch that share k-mers race in the reference too (worker threads on one filter); the batch is
+    # checked where no order matters: sequences without new k-mers report true, sequences with a k-mer nobody else has report false, and the
+    # final bit array is the union
+    before = {h for s in first for h in kmers(s) if h is not None}
+    counts = {}
+    for s in second:
+        for h in set(kmers(s)):
+            counts[h] = counts.get(h, 0) + 1
+    got2 = bf.lookupAndAddAllKmers(rb.pack_reads(second), mode)
+    for s, g_ in zip(second, got2):
+        ks = kmers(s)
+        if len(s) < k:
+            assert g_      # the empty loop of :642-650 returns true
+        elif all(h is not None and lib.orc_bf_lookup1(obf, h) for h in ks):
+            assert g_
+        elif any(h is None or (h not in before and counts[h] == 1 and not lib.orc_bf_lookup1(obf, h)) for h in ks):
+            assert not g_
+    for s in second:
+        for h in kmers(s):
+            if h is not None:
+                lib.orc_bf_add1(obf, h)
+    assert (bf.download() == orc.bf_array(obf)).all()
+    assert bf.containsAllKmers(rb.pack_reads(second), mode).tolist() == [contains_all(kmers(s)) for s in second]
+    bf.destroy()
+    lib.orc_bf_destroy(obf)
 
 
 def test_getkmers_with_invalid_nucleotides(ctx, orc):

@@ -20,7 +20,7 @@ for p in (ROOT, HERE):
 
 K, HD, HC = 25, 3, 2
 DBG_BITS, CBF_BYTES = 3_000_017, 1_000_003
-SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICE_RAISE_LOG2": "14", "RB_SLICED_SUBRANGE_LOG2": "6",
+SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICED_CELLS": "1", "RB_SLICED_SUBRANGE_LOG2": "6",
              "RB_SLICED_CHUNK": "8192"}
 
 
@@ -134,7 +134,7 @@ def test_sharded_sliced_graph_random_configurations(tmp_path, orc, seed):
     cfg = {"k": int(rng.integers(15, 61)), "hd": int(rng.integers(1, 4)), "hc": int(rng.integers(1, 4)), "seed": 100 + seed,
            "dbg_bits": int(rng.integers(1 << 22, 1 << 25)) | 1, "cbf_bytes": int(rng.integers(1 << 19, 1 << 22)) | 1,
            "env": {"RB_SLICE_BITS_LOG2": str(int(rng.integers(15, 21))), "RB_SLICE_BYTES_LOG2": str(int(rng.integers(13, 19))),
-                   "RB_SLICE_RAISE_LOG2": str(int(rng.integers(10, 16))), "RB_SLICED_SUBRANGE_LOG2": str(int(rng.integers(4, 8)))}}
+                   "RB_SLICED_CELLS": str(int(rng.integers(0, 2))), "RB_SLICED_SUBRANGE_LOG2": str(int(rng.integers(4, 8)))}}
     port = 33500 + os.getpid() % 2000 + seed
     mp.spawn(_worker, args=(world, port, stranded, str(tmp_path), cfg), nprocs=world, join=True)
     k, hd, hc, dbg_bits, cbf_bytes = cfg["k"], cfg["hd"], cfg["hc"], cfg["dbg_bits"], cfg["cbf_bytes"]
