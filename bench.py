@@ -252,7 +252,7 @@ def main():
     # ---- end to end: host-pointer C-ABI calls, pinned host buffers, H2D + D2H inside the timed region ----------------
     e2e = None
     if not args.no_e2e:
-        e_steps = max(2, min(args.steps, 5))
+        e_steps = max(2, min(args.steps, 8))
         h_packed = [ctx.host_alloc(words * 8, np.uint64) for _ in range(e_steps + 4)]   # 1 + 2 for the blocking calls, 1 + e_steps pipelined
         tmp = ctx.dev_alloc(words * 8 + 64)
         for i, hp in enumerate(h_packed):   # fresh reads (ids after the timed ones), generated on the device, parked in pinned host memory

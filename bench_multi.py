@@ -251,7 +251,7 @@ def run_sharded(args, rank, world, local_rank):
     # stream out of one of two count buffers, so it overlaps the next step's insert rounds (as the single-GPU host-pointer calls do)
     e2e = None
     if not args.no_e2e:
-        e_steps = 3
+        e_steps = 5
         h_in = torch.empty(words + 8, dtype=torch.int64).pin_memory()
         h_in.copy_(batches[0].cpu())
         h_out = torch.empty(n_reads * kpr, dtype=torch.float32).pin_memory()

@@ -615,6 +615,21 @@ __device__ __forceinline__ SlWork sl_work_item(const SlArena& arena, const int* 
     return w;
 }
 
+// the first U records per thread of a work item (thread t takes records t, t + 256, ...), 0 beyond its end
+template <int U>
+__device__ __forceinline__ void sl_fetch_records(const SlArena& arena, const SlWork& w, uint32_t (&dst)[U]) {
+    const uint32_t* rec = sl_region_records<uint32_t>(arena, w.b);
+#pragma unroll
+    for (int u = 0; u < U; ++u) dst[u] = threadIdx.x + u * kSlThreads < w.n ? __ldcs(rec + w.first + threadIdx.x + u * kSlThreads) : 0u;
+}
+
+template <int U>
+__device__ __forceinline__ void sl_fetch_raise_bytes(const SlArena& arena, const SlWork& w, const uint8_t* local, uint32_t (&dst)[U]) {
+    const uint8_t* rb = arena.peer_ans ? arena.peer_ans[w.b % arena.n_peers] : local;
+#pragma unroll
+    for (int u = 0; u < U; ++u) dst[u] = threadIdx.x + u * kSlThreads < w.n ? (uint32_t)__ldcs(rb + w.first + threadIdx.x + u * kSlThreads) : 0u;
+}
+
 // ---- S2 / I5: apply the probes.  SET = 1: dbgbf probes are test-and-set (graph.add / addDbgOnly) -------------------------------------
 template <int SET>
 __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena arena, int* chunk_prefix, const SlGeom sg,
@@ -628,8 +643,20 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
     constexpr int U = 8;   // probes in flight per thread
     const L2Keep keep = l2_keep_policy();
     __shared__ int s_c;
-    for (int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c); c < total; c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c)) {
-        const SlWork w = sl_work_item(arena, pre, c);
+    // Software pipeline over the work items: the first U records per thread of the NEXT item are requested before the current item is
+    // processed, so their latency (a microsecond out of local HBM, several over NVLink in peer-to-peer mode) hides behind the filter
+    // accesses of the current one instead of standing in front of every item.
+    uint32_t ahead[U];
+    SlWork w_ahead;
+    int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c);
+    if (c < total) { w_ahead = sl_work_item(arena, pre, c); sl_fetch_records<U>(arena, w_ahead, ahead); }
+    while (c < total) {
+        const SlWork w = w_ahead;
+        uint32_t cur[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) cur[u] = ahead[u];
+        c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c);
+        if (c < total) { w_ahead = sl_work_item(arena, pre, c); sl_fetch_records<U>(arena, w_ahead, ahead); }
         const int lr = w.b / sg.region_div;   // local region: dbgbf slices first, then cbf slices -- or paired slices
         const uint32_t* rec = sl_region_records<uint32_t>(arena, w.b);                      // local, or the source rank's arena over NVLink
         uint8_t* ans_out = arena.peer_ans ? arena.peer_ans[w.b % arena.n_peers] : ans;  // answers land where the producer will look
@@ -644,7 +671,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const bool in = i0 + u * kSlThreads < w.n;
-                    li[u] = in ? __ldcs(rec + w.first + i0 + u * kSlThreads) : 0u;
+                    li[u] = i0 == threadIdx.x ? cur[u] : in ? __ldcs(rec + w.first + i0 + u * kSlThreads) : 0u;
                     act[u] = in && (int)((li[u] & off_mask) >> sub_shift) == w.pass;
                 }
                 if (sg.cells) {   // one access per record: the cell word holds the counter and the bit
@@ -693,7 +720,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
         for (uint32_t i0 = threadIdx.x; i0 < w.n; i0 += kSlThreads * U) {
             uint32_t li[U], wd[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) li[u] = (i0 + u * kSlThreads < w.n) ? __ldcs(rec + w.first + i0 + u * kSlThreads) : 0u;
+            for (int u = 0; u < U; ++u) li[u] = i0 == threadIdx.x ? cur[u] : (i0 + u * kSlThreads < w.n) ? __ldcs(rec + w.first + i0 + u * kSlThreads) : 0u;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 wd[u] = 0;
@@ -1020,11 +1047,29 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_raises(const SlArena aren
     int* pre = reinterpret_cast<int*>(sl_smem);
     sl_load_prefix(pre, chunk_prefix, arena.B);
     const int total = pre[arena.B];
-    constexpr int U = 4;
+    constexpr int U = 8;
     const L2Keep keep = l2_keep_policy();
     __shared__ int s_c;
-    for (int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c); c < total; c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c)) {
-        const SlWork w = sl_work_item(arena, pre, c);
+    // the same software pipeline as ks_apply_probes: raise bytes and records of the next work item are in flight while this one is applied
+    uint32_t ahead_v[U], ahead_r[U];
+    SlWork w_ahead;
+    int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c);
+    if (c < total) {
+        w_ahead = sl_work_item(arena, pre, c);
+        sl_fetch_raise_bytes<U>(arena, w_ahead, raise, ahead_v);
+        sl_fetch_records<U>(arena, w_ahead, ahead_r);
+    }
+    while (c < total) {
+        const SlWork w = w_ahead;
+        uint32_t cur_v[U], cur_r[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { cur_v[u] = ahead_v[u]; cur_r[u] = ahead_r[u]; }
+        c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c);
+        if (c < total) {
+            w_ahead = sl_work_item(arena, pre, c);
+            sl_fetch_raise_bytes<U>(arena, w_ahead, raise, ahead_v);
+            sl_fetch_records<U>(arena, w_ahead, ahead_r);
+        }
         const int lr = w.b / sg.region_div;   // local region
         if (!sg.paired && lr < sg.n_dbg) continue;   // dbgbf probes (the whole CTA)
         const uint32_t* rec = sl_region_records<uint32_t>(arena, w.b);                              // local, or the source rank's arena over NVLink
@@ -1032,17 +1077,18 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_raises(const SlArena aren
         const uint64_t byte0 = sg.paired ? (uint64_t)lr << sg.pair_log2 : (uint64_t)(lr - sg.n_dbg) << sg.cbf_log2;
         const uint32_t off_mask = sg.paired ? (1u << sg.pair_log2) - 1u : 0xFFFFFFFFu;
         const int sub_shift = sg.paired ? sg.pair_log2 - sg.pair_sub_log2 : 31;
+        // cells: cbf_words is the cell array, two 16-bit cells per word, the counter in the low byte of its cell
+        const int wsh = sg.cells ? 1 : 2, bsh = sg.cells ? 16 : 8;
         for (uint32_t i0 = threadIdx.x; i0 < w.n; i0 += kSlThreads * U) {
             uint32_t v[U], li[U], wd[U];
+            const bool first = i0 == threadIdx.x;
 #pragma unroll
-            for (int u = 0; u < U; ++u) v[u] = (i0 + u * kSlThreads < w.n) ? (uint32_t)__ldcs(rb + w.first + i0 + u * kSlThreads) : 0u;
+            for (int u = 0; u < U; ++u) v[u] = first ? cur_v[u] : (i0 + u * kSlThreads < w.n) ? (uint32_t)__ldcs(rb + w.first + i0 + u * kSlThreads) : 0u;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                li[u] = v[u] ? __ldcs(rec + w.first + i0 + u * kSlThreads) & off_mask : 0u;
+                li[u] = (first ? cur_r[u] : v[u] ? __ldcs(rec + w.first + i0 + u * kSlThreads) : 0u) & off_mask;
                 if (arena.passes > 1 && (int)(li[u] >> sub_shift) != w.pass) v[u] = 0;   // another pass handles this sub-slice
             }
-            // cells: cbf_words is the cell array, two 16-bit cells per word, the counter in the low byte of its cell
-            const int wsh = sg.cells ? 1 : 2, bsh = sg.cells ? 16 : 8;
 #pragma unroll
             for (int u = 0; u < U; ++u) { wd[u] = 0; if (v[u]) wd[u] = ld_cg_keep(cbf_words + ((byte0 + li[u]) >> wsh), keep); }
 #pragma unroll
