@@ -275,6 +275,23 @@ enum { RB_SEQ_ADD = 0, RB_SEQ_CONTAINS_ALL = 1, RB_SEQ_LOOKUP_AND_ADD_ALL = 2 };
 RB_API int32_t rb_filter_seq_op(rb_filter* f, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
                                 int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, int32_t mode, int32_t op, uint8_t* all_found);
 
+/* ---- f3: k-mer multiplicity histogram by hash sampling -----------------------------------------------------------
+ * The reference sizes its filters from the histogram of the external `ntcard` binary (RNABloom.java:5745-5768, 6939-7010; parsed by
+ * util/NTCardHistogram.java:33-63: F1 = k-mers, F0 = distinct k-mers, f_m = distinct k-mers of multiplicity m).  Here: a k-mer is sampled
+ * when the top sample_bits bits of a multiplicative mix of its hash are zero; sampled k-mers are counted exactly in a device table, so the
+ * sample's histogram is exact and F0 / f_m are that histogram times 2^sample_bits (sample_bits = 0: exact counts).  Accumulates over calls.
+ * rb_card_histogram: totals[0] = F1, [1] = sampled instances, [2] = sampled distinct k-mers, [3] = 2^sample_bits; hist[m - 1] = sampled
+ * distinct k-mers of multiplicity m for m <= max_mult (<= 65535), hist[max_mult] = those above (max_mult + 1 entries).  stage1.py writes
+ * them in ntcard's file format, which the unmodified JAR parses instead of running ntcard when the file exists (RNABloom.java:5750). */
+typedef struct rb_card rb_card;
+RB_API int32_t rb_card_create(rb_ctx* ctx, int32_t k, int32_t stranded, int32_t sample_bits, int64_t table_slots, rb_card** out);
+RB_API int32_t rb_card_destroy(rb_card* c);
+RB_API int32_t rb_card_add_reads(rb_card* c, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
+                                 int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, int64_t* n_kmers_out);
+RB_API int32_t rb_card_add_reads_dev(rb_card* c, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
+                                     int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, int64_t* n_kmers_out);
+RB_API int32_t rb_card_histogram(rb_card* c, int64_t* totals, int64_t* hist, int32_t max_mult);
+
 /* ---- synthetic workload generator (bench + fixtures; not a reference operator) ----------------------------------
  * Deterministic, counter-based: read r of a virtual genome (seed, genome_len), length L, err_ppm substitutions per
  * 1e6 bases; written in the uniform ingest layout (stride = stride_bases, multiple of 32) into device memory. */

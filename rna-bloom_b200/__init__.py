@@ -11,5 +11,6 @@ from .binding import (  # noqa: F401
     REVCOMP, ADD_COUNT_IF_PRESENT, DBG_ONLY, STORE_READ_PAIRS, STORE_FRAG_PAIRS, PAIRS_EXISTING_ONLY,
 )
 from .filters import (  # noqa: F401
-    Context, BloomFilter, CountingBloomFilter, CascadingBloomFilter, BloomFilterDeBruijnGraph, PackedReads, pack_reads, pack_uniform, encode_2bit_records,
+    Context, BloomFilter, CountingBloomFilter, CascadingBloomFilter, KmerHistogram, BloomFilterDeBruijnGraph, PackedReads, pack_reads, pack_uniform,
+    encode_2bit_records,
 )

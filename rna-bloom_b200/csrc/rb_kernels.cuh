@@ -405,6 +405,56 @@ __global__ void __launch_bounds__(kThreads) k_seq_filter(const Ingest g, int k, 
     }
 }
 
+// ---- f3: k-mer multiplicity histogram by hash sampling -- what the reference shells out to `ntcard` for (RNABloom.java:5745-5768; the
+// histogram it parses: util/NTCardHistogram.java:33-63).  A k-mer is sampled when the top `sample_bits` bits of a multiplicative mix of
+// its hash are zero (ntCard samples on the hash in the same way); sampled k-mers are counted EXACTLY in an open-addressing table, so the
+// histogram of the sample is exact and only the scaling by 2^sample_bits is an estimate.  One in 2^sample_bits k-mers reaches the table.
+struct CardTable {
+    unsigned long long* keys;     // n_slots + 1; 0 = empty; slot n_slots stands for key 0
+    unsigned int* counts;
+    uint64_t n_slots;             // power of two
+    int shift;                    // 64 - log2(n_slots)
+    int sample_bits;
+    unsigned long long* totals;   // [0] usable k-mers seen (F1)  [1] sampled instances  [2] overflow flag
+};
+__device__ __forceinline__ uint64_t card_mix(uint64_t key) { return key * 0x9E3779B97F4A7C15ULL; }
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) k_card_add(const Ingest g, int k, const CardTable ct) {
+    __shared__ RollLut lut;
+    build_lut(&lut, k);
+    const int64_t pos = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * kChunk;
+    if (pos >= g.n_pos) return;
+    const int n = (int)min((int64_t)kChunk, g.n_pos - pos);
+    PositionWalker<MODE> pw;
+    pw.start(g, pos, k, lut);
+    unsigned int usable = 0, sampled = 0;
+    for (int i = 0; i < n; ++i) {
+        pw.advance(g, k, lut);
+        if (pw.wk.bad) continue;
+        ++usable;
+        const uint64_t key = pw.wk.base(), m = card_mix(key);
+        if (ct.sample_bits && (m >> (64 - ct.sample_bits)) != 0) continue;
+        ++sampled;
+        if (key == 0ULL) { atomicAdd(&ct.counts[ct.n_slots], 1u); continue; }
+        uint64_t s = (m << ct.sample_bits) >> ct.shift;   // the bits below the sampling prefix
+        for (uint64_t tries = 0;; ++tries) {
+            const unsigned long long old = atomicCAS(&ct.keys[s], 0ULL, (unsigned long long)key);
+            if (old == 0ULL || old == key) { atomicAdd(&ct.counts[s], 1u); break; }
+            if (tries >= ct.n_slots) { atomicExch(&ct.totals[2], 1ULL); break; }   // table full
+            s = (s + 1) & (ct.n_slots - 1);
+        }
+    }
+    if (usable) atomicAdd(&ct.totals[0], (unsigned long long)usable);
+    if (sampled) atomicAdd(&ct.totals[1], (unsigned long long)sampled);
+}
+// hist[m - 1] += 1 for every sampled distinct k-mer of multiplicity m <= max_mult; hist[max_mult] counts the ones above
+__global__ void __launch_bounds__(kThreads) k_card_hist(const CardTable ct, unsigned long long* __restrict__ hist, int max_mult) {
+    for (uint64_t s = (uint64_t)blockIdx.x * kThreads + threadIdx.x; s <= ct.n_slots; s += (uint64_t)gridDim.x * kThreads) {
+        const unsigned int c = ct.counts[s];
+        if (c) atomicAdd(&hist[c <= (unsigned int)max_mult ? c - 1 : max_mult], 1ULL);
+    }
+}
+
 // ---- per-hash operators: the `long hashVal` overloads (bloom/BloomFilter.java:139-182, CountingBloomFilter.java:126-251) -
 enum { OP_BF_ADD = 0, OP_BF_LOOKUP, OP_BF_LTA, OP_CBF_INC, OP_CBF_INC_GET, OP_CBF_COUNT, OP_GRAPH_ADD, OP_GRAPH_COUNT_IF_PRESENT,
        OP_GRAPH_COUNT };

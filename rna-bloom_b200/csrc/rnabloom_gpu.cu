@@ -1033,6 +1033,92 @@ extern "C" int32_t rb_filter_seq_op(rb_filter* f, const uint64_t* packed, const 
     return RB_OK;
 }
 
+// ---- f3: k-mer multiplicity histogram by hash sampling (the reference runs the external `ntcard`, RNABloom.java:5745-5768) ----------------
+struct rb_card { rb_ctx* ctx; int k, mode; CardTable ct; unsigned long long* hist; };
+extern "C" int32_t rb_card_create(rb_ctx* ctx, int32_t k, int32_t stranded, int32_t sample_bits, int64_t table_slots, rb_card** out) {
+    if (!ctx || !out || k < 1 || sample_bits < 0 || sample_bits > 30 || table_slots < 64) return RB_EINVAL;
+    LOCK(ctx);
+    rb_card* c = new rb_card();
+    memset(c, 0, sizeof *c);
+    c->ctx = ctx; c->k = k; c->mode = stranded ? RB_MODE_FWD : RB_MODE_CANON;
+    int lg = 6; while ((1LL << lg) < table_slots && lg < 34) ++lg;
+    c->ct.n_slots = 1ULL << lg; c->ct.shift = 64 - lg; c->ct.sample_bits = sample_bits;
+    cudaError_t e = cudaMalloc(&c->ct.keys, (size_t)(c->ct.n_slots + 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&c->ct.counts, (size_t)(c->ct.n_slots + 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&c->ct.totals, 64);
+    if (e == cudaSuccess) e = cudaMalloc(&c->hist, (size_t)65536 * 8);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->ct.keys, 0, (size_t)(c->ct.n_slots + 1) * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->ct.counts, 0, (size_t)(c->ct.n_slots + 1) * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->ct.totals, 0, 64, ctx->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(c->ct.keys); cudaFree(c->ct.counts); cudaFree(c->ct.totals); cudaFree(c->hist);
+        delete c;
+        return fail(ctx, RB_ENOMEM, std::string("rb_card_create: ") + cudaGetErrorString(e));
+    }
+    *out = c;
+    return RB_OK;
+}
+extern "C" int32_t rb_card_destroy(rb_card* c) {
+    if (!c) return RB_EINVAL;
+    rb_ctx* ctx = c->ctx;
+    LOCK(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(c->ct.keys); cudaFree(c->ct.counts); cudaFree(c->ct.totals); cudaFree(c->hist);
+    delete c;
+    return RB_OK;
+}
+static int32_t card_launch(rb_ctx* ctx, const Ingest& ing, void* user) {
+    rb_card* c = (rb_card*)user;
+    const int grid = (int)div_up(div_up(ing.n_pos, kChunk), kThreads);
+    PROF("k_card_add");
+    if (c->mode == RB_MODE_FWD) RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_card_add<0>)(ing, c->k, c->ct);
+    else RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_card_add<2>)(ing, c->k, c->ct);
+    LAUNCH_CHECK();
+    return RB_OK;
+}
+static int32_t card_add(rb_card* c, const ReadsArg& ra, int64_t* n_kmers_out) {
+    rb_ctx* ctx = c->ctx;
+    const int32_t rc = for_each_launch(ctx, ra, c->k, card_launch, c, n_kmers_out);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RB_OK;
+}
+extern "C" int32_t rb_card_add_reads(rb_card* c, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
+                                     int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, int64_t* n_kmers_out) {
+    if (!c) return RB_EINVAL;
+    LOCK(c->ctx);
+    ReadsArg ra{packed, mask, read_off, read_len, n_reads, uniform_len, uniform_stride, false};
+    return card_add(c, ra, n_kmers_out);
+}
+extern "C" int32_t rb_card_add_reads_dev(rb_card* c, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
+                                         int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, int64_t* n_kmers_out) {
+    if (!c) return RB_EINVAL;
+    LOCK(c->ctx);
+    ReadsArg ra{packed, mask, read_off, read_len, n_reads, uniform_len, uniform_stride, true};
+    return card_add(c, ra, n_kmers_out);
+}
+// totals[0] = F1 (usable k-mer instances), [1] = sampled instances, [2] = sampled distinct k-mers, [3] = 2^sample_bits;
+// hist[m - 1] = sampled distinct k-mers of multiplicity m (m <= max_mult <= 65535), hist[max_mult] = those above.  F0 ~ totals[2] * totals[3].
+extern "C" int32_t rb_card_histogram(rb_card* c, int64_t* totals, int64_t* hist, int32_t max_mult) {
+    if (!c || !totals || !hist || max_mult < 1 || max_mult > 65535) return RB_EINVAL;
+    rb_ctx* ctx = c->ctx;
+    LOCK(ctx);
+    unsigned long long t3[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(t3, c->ct.totals, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemsetAsync(c->hist, 0, (size_t)(max_mult + 1) * 8, ctx->stream));
+    const int grid = (int)std::min<int64_t>(div_up((int64_t)c->ct.n_slots + 1, kThreads), (int64_t)ctx->sm_count * 16);
+    RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_card_hist)(c->ct, c->hist, max_mult);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(hist, c->hist, (size_t)(max_mult + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (t3[2]) return fail(ctx, RB_ESTATE, "rb_card: the sample table is full -- more sample_bits or more table_slots");
+    int64_t distinct = 0;
+    for (int i = 0; i <= max_mult; ++i) distinct += hist[i];
+    totals[0] = (int64_t)t3[0]; totals[1] = (int64_t)t3[1]; totals[2] = distinct; totals[3] = 1LL << c->ct.sample_bits;
+    return RB_OK;
+}
+
 static int engine_from_env() {   // RB_ENGINE = direct | sliced | (anything else) auto
     const char* eng = getenv("RB_ENGINE");
     return (eng && !strcmp(eng, "direct")) ? RB_ENGINE_DIRECT : (eng && !strcmp(eng, "sliced")) ? RB_ENGINE_SLICED : RB_ENGINE_AUTO;

@@ -317,6 +317,74 @@ class BloomFilter(_Filter):
         return B.lib().rb_expected_size(expNumElements, fpr, numHash)
 
 
+class KmerHistogram:
+    """k-mer multiplicity histogram by hash sampling on the GPU (rb_card_*): what RNA-Bloom obtains from the external `ntcard` binary
+    (RNABloom.java:5745-5768); the accessors are util/NTCardHistogram.java:28-100."""
+    MAX_MULTIPLICITY = 65535
+
+    def __init__(self, ctx, k, stranded, sample_bits=11, table_slots=1 << 26):
+        self.ctx, self.k, self.sample_bits = ctx, k, sample_bits
+        h = C.c_void_p()
+        ctx.check(ctx.L.rb_card_create(ctx.h, k, int(stranded), sample_bits, table_slots, C.byref(h)))
+        self.h = h
+        self.numKmers = self.numUniqueKmers = self.numUniqueOverrepresentedKmers = 0
+        self.counts = np.zeros(self.MAX_MULTIPLICITY, dtype=np.int64)
+
+    def destroy(self):
+        if self.h:
+            self.ctx.check(self.ctx.L.rb_card_destroy(self.h))
+            self.h = None
+
+    def addReads(self, reads):
+        n = C.c_int64()
+        self.ctx.check(self.ctx.L.rb_card_add_reads(self.h, *reads.args(), C.byref(n)))
+        return n.value
+
+    def addReadsDev(self, packed_dev, n_reads, uniform_len, uniform_stride):
+        n = C.c_int64()
+        self.ctx.check(self.ctx.L.rb_card_add_reads_dev(self.h, packed_dev, None, None, None, n_reads, uniform_len, uniform_stride, C.byref(n)))
+        return n.value
+
+    def finish(self):
+        """Reads the table: the sample's exact histogram, scaled by 2^sample_bits.  Returns (totals, raw histogram of the sample)."""
+        totals = np.zeros(4, dtype=np.int64)
+        raw = np.zeros(self.MAX_MULTIPLICITY + 1, dtype=np.int64)
+        self.ctx.check(self.ctx.L.rb_card_histogram(self.h, _ptr(totals), _ptr(raw), self.MAX_MULTIPLICITY))
+        scale = int(totals[3])
+        self.numKmers = int(totals[0])                                   # F1
+        self.numUniqueKmers = int(totals[2]) * scale                     # F0
+        self.counts = raw[:self.MAX_MULTIPLICITY] * scale
+        self.numUniqueOverrepresentedKmers = self.numUniqueKmers - int(self.counts.sum())
+        return totals, raw
+
+    def getNumSingletons(self):
+        return int(self.counts[0])
+
+    def getMinCovThreshold(self, multiplier):                            # NTCardHistogram.java:70-78
+        for i in range(1, self.MAX_MULTIPLICITY):
+            if multiplier * self.counts[i] > self.counts[i - 1]:
+                return i
+        return 0
+
+    def getMaxCovThreshold(self, fraction):                              # :80-98
+        num = int(round(fraction * self.numUniqueKmers))
+        total = self.numUniqueOverrepresentedKmers
+        if total >= num:
+            return self.MAX_MULTIPLICITY + 1
+        for i in range(self.MAX_MULTIPLICITY - 1, -1, -1):
+            total += int(self.counts[i])
+            if total >= num:
+                return i + 1
+        return self.MAX_MULTIPLICITY + 1
+
+    def write(self, path):
+        """ntcard's histogram file (F1, F0, then multiplicity <TAB> count), the input of NTCardHistogram(path) (:33-63)."""
+        with open(path, "w") as fh:
+            fh.write("F1\t%d\nF0\t%d\n" % (self.numKmers, self.numUniqueKmers))
+            for i in range(self.MAX_MULTIPLICITY):
+                fh.write("%d\t%d\n" % (i + 1, int(self.counts[i])))
+
+
 class CascadingBloomFilter:
     """bloom/CascadingBloomFilter.java: numLevels Bloom filters of size / numLevels bits; add walks the levels with lookupThenAdd."""
 

@@ -168,8 +168,39 @@ class Stage1:
         m = max(pops)
         return [rb.BloomFilter.getExpectedSize(m, max_fpr, h) for h in self.num_hash]
 
-    def run(self, left, right, revcomp_right, outdir, name, max_fpr=0.01, sample=1000, save=True, use_pairs=True):
+    def histogram(self, paths, sample_bits=11, table_slots=1 << 24):
+        """The k-mer multiplicity histogram the reference gets from `ntcard` (RNABloom.java:5745-5768), by hash sampling on the GPU."""
+        import rnabloom_b200 as rb
+        h = rb.KmerHistogram(self.ctx, self.k, self.stranded, sample_bits, table_slots)
+        for p in paths:
+            seqs = []
+            for seq, _ in records(p):
+                seqs.append(seq)
+                if len(seqs) >= self.chunk_reads:
+                    h.addReads(rb.pack_reads(seqs))
+                    seqs = []
+            if seqs:
+                h.addReads(rb.pack_reads(seqs))
+        h.finish()
+        return h
+
+    def sizes_from_histogram(self, hist, max_fpr):
+        """RNABloom.java:6963,6986-7010: dbgbf / pkbf for F0 k-mers, cbf for the non-singletons."""
+        import rnabloom_b200 as rb
+        unexpected = (hist.numKmers > 0 and hist.numUniqueKmers < 1) or hist.numKmers < hist.numUniqueKmers
+        exp = max(hist.numKmers, hist.numUniqueKmers) if unexpected else hist.numUniqueKmers
+        hd, hc, hp = self.num_hash
+        singletons = hist.getNumSingletons()
+        cbf_n = exp if (exp == singletons or unexpected) else exp - singletons
+        return [rb.BloomFilter.getExpectedSize(exp, max_fpr, hd), rb.BloomFilter.getExpectedSize(cbf_n, max_fpr, hc), rb.BloomFilter.getExpectedSize(exp, max_fpr, hp)]
+
+    def run(self, left, right, revcomp_right, outdir, name, max_fpr=0.01, sample=1000, save=True, use_pairs=True, ntcard=False):
         os.makedirs(outdir, exist_ok=True)
+        if ntcard:   # size the filters from the histogram and leave it where the JAR looks for ntcard's output (:5747-5750, :6934)
+            hist = self.histogram(list(left) + list(right))
+            hist.write(os.path.join(outdir, "%s_k%d.hist" % (name, self.k)))
+            self.sizes = self.sizes_from_histogram(hist, max_fpr)
+            hist.destroy()
         q = read_length_quartiles(list(left) + list(right), self.k, sample)
         write_quartiles(q, os.path.join(outdir, name + ".readstats"))
         # setReadLengthBasedParams (RNABloom.java:1017-1031): readPairedKmerDistance = max(1, Q1 - k - minNumKmerPairs(10))
@@ -204,12 +235,13 @@ def main(argv=None):
     ap.add_argument("-cbf-gb", type=float, default=0.5, dest="cbf_gb")
     ap.add_argument("-pkbf-gb", type=float, default=0.25, dest="pkbf_gb")
     ap.add_argument("-hash", type=int, default=2, help="number of hash functions of every filter")
+    ap.add_argument("-ntcard", action="store_true", help="size the filters from a k-mer histogram computed on the GPU (what RNA-Bloom runs ntcard for)")
     ap.add_argument("-device", type=int, default=0)
     a = ap.parse_args(argv)
     import rnabloom_b200 as rb
     ctx = rb.Context(a.device)
     s1 = Stage1(ctx, a.k, a.stranded, int(a.dbgbf_gb * NUM_BITS_1GB), int(a.cbf_gb * NUM_BYTES_1GB), int(a.pkbf_gb * NUM_BITS_1GB), a.hash, a.hash, a.hash, a.q)
-    rep = s1.run(a.left, a.right, a.revcomp_right, a.outdir, a.name, a.fpr)
+    rep = s1.run(a.left, a.right, a.revcomp_right, a.outdir, a.name, a.fpr, ntcard=a.ntcard)
     print("stage 1 on the GPU: %d k-mers, sizes %s%s, FPR %s -> %s" % (rep["kmers"], rep["sizes"], " (resized)" if rep["resized"] else "", rep["fpr"],
                                                                       os.path.join(a.outdir, a.name + ".graph")))
     s1.graph.destroy()

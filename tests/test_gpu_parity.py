@@ -663,6 +663,54 @@ def test_screening_filter_over_whole_sequences(ctx, orc, mode, k, num_hash):
     lib.orc_bf_destroy(obf)
 
 
+@pytest.mark.parametrize("stranded,k,sample_bits", [(False, 25, 0), (False, 21, 3), (True, 31, 2)])
+def test_kmer_histogram_by_hash_sampling(ctx, orc, stranded, k, sample_bits, tmp_path):
+    """f3: the multiplicity histogram RNA-Bloom gets from `ntcard` (RNABloom.java:5745-5768; util/NTCardHistogram.java:33-100): the sample is
+    counted exactly, so totals and histogram must equal a dictionary count over the oracle's hashes with the same sampling rule."""
+    rng = np.random.default_rng(401 + k)
+    genome = "".join(rng.choice(list("ACGT"), size=6000))
+    seqs = []
+    for _ in range(900):   # ~20x coverage of a short genome: multiplicities well above 1
+        L = int(rng.integers(k - 3, 220))
+        p0 = int(rng.integers(0, len(genome) - L))
+        s_ = list(genome[p0:p0 + L])
+        if rng.random() < 0.1:
+            s_[int(rng.integers(0, L))] = "N"
+        seqs.append("".join(s_))
+    mode = 0 if stranded else MODE_CANON
+    want = {}
+    usable = 0
+    for s_ in seqs:
+        _, _, base = orc.kmer_hashes(s_, k, mode)
+        for i, b in enumerate(base):
+            if "N" in s_[i:i + k]:
+                continue
+            usable += 1
+            key = int(b) & 0xFFFFFFFFFFFFFFFF
+            if sample_bits == 0 or ((key * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF) >> (64 - sample_bits) == 0:
+                want[key] = want.get(key, 0) + 1
+    h = rb.KmerHistogram(ctx, k, stranded, sample_bits, 1 << 16)
+    n = 0
+    for lo in range(0, len(seqs), 300):                     # accumulates over calls
+        n += h.addReads(rb.pack_reads(seqs[lo:lo + 300]))
+    totals, raw = h.finish()
+    assert int(totals[0]) == usable and int(totals[1]) == sum(want.values()) and int(totals[2]) == len(want) and int(totals[3]) == 1 << sample_bits
+    mult = np.bincount(np.array(list(want.values())), minlength=2)
+    assert (raw[:len(mult) - 1] == mult[1:]).all() and raw[len(mult) - 1:].sum() == 0
+    assert h.numKmers == usable and h.numUniqueKmers == len(want) << sample_bits and h.getNumSingletons() == int(mult[1]) << sample_bits
+    # the file the unmodified JAR parses instead of running ntcard (NTCardHistogram(path)): F1, F0, then multiplicity <TAB> count
+    path = tmp_path / ("x_k%d.hist" % k)
+    h.write(str(path))
+    lines = path.read_text().split("\n")
+    assert lines[0] == "F1\t%d" % usable and lines[1] == "F0\t%d" % (len(want) << sample_bits) and lines[2] == "1\t%d" % (int(mult[1]) << sample_bits)
+    # a full table is reported, not silently dropped
+    tiny = rb.KmerHistogram(ctx, k, stranded, 0, 64)
+    tiny.addReads(rb.pack_reads(seqs[:50]))
+    with pytest.raises(rb.RBError):
+        tiny.finish()
+    tiny.destroy(), h.destroy()
+
+
 def test_getkmers_with_invalid_nucleotides(ctx, orc):
     rng = np.random.default_rng(37)
     seqs = rand_reads(rng, 120, 10, 300, n_rate=0.01)
