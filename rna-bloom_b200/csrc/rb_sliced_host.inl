@@ -238,7 +238,7 @@ static SlArena sl_arena(void* data, unsigned int* cursor, const uint32_t* roff, 
     SlArena a;
     a.data = data; a.cursor = cursor; a.roff = roff; a.B = B; a.chunk = chunk; a.cap = 0; a.cursor_stride = kSlPad; a.rlo = nullptr;
     a.spill_data = nullptr; a.spill_cursor = nullptr; a.spill_cap = 0;
-    a.peer_data = nullptr; a.peer_ans = nullptr; a.n_peers = 1; a.passes = 1;
+    a.push_data = nullptr; a.push_per_rank = 1; a.peer_ans = nullptr; a.n_peers = 1; a.me = 0; a.push_stride = 0; a.passes = 1;
     return a;
 }
 static SlArena sl_probe_arena(SlicedEngine* e) {
@@ -456,9 +456,9 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
         const uint64_t seed = ctx->rng_seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(ctx->launches + 1);
         const size_t sm_r = TileAnswers::smem_bytes(probes.B, kSlThreads * kSlTileRecords);
         if (e->paired) SL_LAUNCH("ks_combine_insert", ks_combine_insert<3>, grid_d, sm_r, e->dkey, e->dmult, e->n_distinct, e->pos, e->tile_meta, probes.B, e->ans, e->sg,
-                                 policy, seed, (const int*)nullptr);
+                                 policy, seed, (const int*)nullptr, TileAnswers::Push{nullptr, 1, 0, 0});
         else SL_LAUNCH("ks_combine_insert", ks_combine_insert<6>, grid_d, sm_r, e->dkey, e->dmult, e->n_distinct, e->pos, e->tile_meta, probes.B, e->ans, e->sg,
-                       policy, seed, (const int*)nullptr);
+                       policy, seed, (const int*)nullptr, TileAnswers::Push{nullptr, 1, 0, 0});
         rc = sl_chunk_prefix(ctx, e, probes);   // the same work list again (the consumers' counter starts from 0)
         if (rc) return rc;
         rc = sl_persistent_grid(ctx, ks_apply_raises, sm_pre, &grid);
