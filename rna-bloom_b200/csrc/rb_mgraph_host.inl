@@ -157,6 +157,7 @@ struct rb_mgraph {
     void **d_peer32, **d_peer64, **d_peer_ans, **d_peer_raise, **d_peer_cnt, **d_peer_cntk;   // device tables [W]: recv32, recv64, home_ans, ans, cnt_s, cnt_k
 };
 
+constexpr int kPeerBufs = 6;   // buffers every rank exports with CUDA IPC
 extern "C" int32_t rb_mgraph_destroy(rb_mgraph* mg) {
     if (!mg) return RB_EINVAL;
     rb_ctx* ctx = mg->ctx;
@@ -187,7 +188,6 @@ extern "C" int32_t rb_mgraph_destroy(rb_mgraph* mg) {
 // Peer-to-peer mode: every rank exports its send arenas, its answer array and its count arrays with CUDA IPC, the handles travel through
 // the transport's all_gather, every rank maps the others'.  All ranks agree (max-reduce of a failure flag) so that a box without
 // peer access falls back to the staged exchange everywhere.  RB_MGRAPH_P2P=0 forces the staged exchange.
-constexpr int kPeerBufs = 6;
 static int32_t mg_setup_p2p(rb_mgraph* mg) {
     mg->p2p = false;
 #ifndef RB_EMU

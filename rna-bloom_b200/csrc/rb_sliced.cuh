@@ -636,22 +636,6 @@ __device__ __forceinline__ SlWork sl_work_item(const SlArena& arena, const int* 
     return w;
 }
 
-// the first U records per thread of a work item (thread t takes records t, t + 256, ...), 0 beyond its end
-template <int U>
-__device__ __forceinline__ void sl_fetch_records(const SlArena& arena, const SlWork& w, uint32_t (&dst)[U]) {
-    const uint32_t* rec = sl_region_records<uint32_t>(arena, w.b);
-#pragma unroll
-    for (int u = 0; u < U; ++u) dst[u] = threadIdx.x + u * kSlThreads < w.n ? __ldcs(rec + w.first + threadIdx.x + u * kSlThreads) : 0u;
-}
-
-template <int U>
-__device__ __forceinline__ void sl_fetch_raise_bytes(const SlArena& arena, const SlWork& w, const uint8_t* local, uint32_t (&dst)[U]) {
-    const uint8_t* rb = local;   // the raise bytes were pushed into this rank's own array
-    (void)arena;
-#pragma unroll
-    for (int u = 0; u < U; ++u) dst[u] = threadIdx.x + u * kSlThreads < w.n ? (uint32_t)__ldcs(rb + w.first + threadIdx.x + u * kSlThreads) : 0u;
-}
-
 // ---- S2 / I5: apply the probes.  SET = 1: dbgbf probes are test-and-set (graph.add / addDbgOnly) -------------------------------------
 template <int SET>
 __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena arena, int* chunk_prefix, const SlGeom sg,
@@ -665,20 +649,11 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
     constexpr int U = 8;   // probes in flight per thread
     const L2Keep keep = l2_keep_policy();
     __shared__ int s_c;
-    // Software pipeline over the work items: the first U records per thread of the NEXT item are requested before the current item is
-    // processed, so their latency (a microsecond out of local HBM, several over NVLink in peer-to-peer mode) hides behind the filter
-    // accesses of the current one instead of standing in front of every item.
-    uint32_t ahead[U];
-    SlWork w_ahead;
-    int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c);
-    if (c < total) { w_ahead = sl_work_item(arena, pre, c); sl_fetch_records<U>(arena, w_ahead, ahead); }
-    while (c < total) {
-        const SlWork w = w_ahead;
-        uint32_t cur[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) cur[u] = ahead[u];
-        c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c);
-        if (c < total) { w_ahead = sl_work_item(arena, pre, c); sl_fetch_records<U>(arena, w_ahead, ahead); }
+    // (A software pipeline over the work items -- the records of the next item requested before the current one is applied -- was
+    // measured and lost: 9.1 -> 9.8 ms look-up, 12.7 -> 20.7 ms raises on local records; the extra registers cost more occupancy than the
+    // hidden latency gives back.  Remote latency is avoided altogether: in peer-to-peer mode the producers push, every read here is local.)
+    for (int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c); c < total; c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c)) {
+        const SlWork w = sl_work_item(arena, pre, c);
         const int lr = w.b / sg.region_div;   // local region: dbgbf slices first, then cbf slices -- or paired slices
         const uint32_t* rec = sl_region_records<uint32_t>(arena, w.b);                      // local, or the source rank's arena over NVLink
         uint8_t* ans_out = sl_answer_base(arena, w.b, ans);   // answers land where the producer will look (its own array, its own coordinates)
@@ -693,7 +668,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const bool in = i0 + u * kSlThreads < w.n;
-                    li[u] = i0 == threadIdx.x ? cur[u] : in ? __ldcs(rec + w.first + i0 + u * kSlThreads) : 0u;
+                    li[u] = in ? __ldcs(rec + w.first + i0 + u * kSlThreads) : 0u;
                     act[u] = in && (int)((li[u] & off_mask) >> sub_shift) == w.pass;
                 }
                 if (sg.cells) {   // one access per record: the cell word holds the counter and the bit
@@ -742,7 +717,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
         for (uint32_t i0 = threadIdx.x; i0 < w.n; i0 += kSlThreads * U) {
             uint32_t li[U], wd[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) li[u] = i0 == threadIdx.x ? cur[u] : (i0 + u * kSlThreads < w.n) ? __ldcs(rec + w.first + i0 + u * kSlThreads) : 0u;
+            for (int u = 0; u < U; ++u) li[u] = (i0 + u * kSlThreads < w.n) ? __ldcs(rec + w.first + i0 + u * kSlThreads) : 0u;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 wd[u] = 0;
@@ -1070,29 +1045,11 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_raises(const SlArena aren
     int* pre = reinterpret_cast<int*>(sl_smem);
     sl_load_prefix(pre, chunk_prefix, arena.B);
     const int total = pre[arena.B];
-    constexpr int U = 8;
+    constexpr int U = 4;
     const L2Keep keep = l2_keep_policy();
     __shared__ int s_c;
-    // the same software pipeline as ks_apply_probes: raise bytes and records of the next work item are in flight while this one is applied
-    uint32_t ahead_v[U], ahead_r[U];
-    SlWork w_ahead;
-    int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c);
-    if (c < total) {
-        w_ahead = sl_work_item(arena, pre, c);
-        sl_fetch_raise_bytes<U>(arena, w_ahead, raise, ahead_v);
-        sl_fetch_records<U>(arena, w_ahead, ahead_r);
-    }
-    while (c < total) {
-        const SlWork w = w_ahead;
-        uint32_t cur_v[U], cur_r[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) { cur_v[u] = ahead_v[u]; cur_r[u] = ahead_r[u]; }
-        c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c);
-        if (c < total) {
-            w_ahead = sl_work_item(arena, pre, c);
-            sl_fetch_raise_bytes<U>(arena, w_ahead, raise, ahead_v);
-            sl_fetch_records<U>(arena, w_ahead, ahead_r);
-        }
+    for (int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c); c < total; c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c)) {
+        const SlWork w = sl_work_item(arena, pre, c);
         const int lr = w.b / sg.region_div;   // local region
         if (!sg.paired && lr < sg.n_dbg) continue;   // dbgbf probes (the whole CTA)
         const uint32_t* rec = sl_region_records<uint32_t>(arena, w.b);
@@ -1104,12 +1061,11 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_raises(const SlArena aren
         const int wsh = sg.cells ? 1 : 2, bsh = sg.cells ? 16 : 8;
         for (uint32_t i0 = threadIdx.x; i0 < w.n; i0 += kSlThreads * U) {
             uint32_t v[U], li[U], wd[U];
-            const bool first = i0 == threadIdx.x;
 #pragma unroll
-            for (int u = 0; u < U; ++u) v[u] = first ? cur_v[u] : (i0 + u * kSlThreads < w.n) ? (uint32_t)__ldcs(rb + w.first + i0 + u * kSlThreads) : 0u;
+            for (int u = 0; u < U; ++u) v[u] = (i0 + u * kSlThreads < w.n) ? (uint32_t)__ldcs(rb + w.first + i0 + u * kSlThreads) : 0u;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                li[u] = (first ? cur_r[u] : v[u] ? __ldcs(rec + w.first + i0 + u * kSlThreads) : 0u) & off_mask;
+                li[u] = (v[u] ? __ldcs(rec + w.first + i0 + u * kSlThreads) : 0u) & off_mask;
                 if (arena.passes > 1 && (int)(li[u] >> sub_shift) != w.pass) v[u] = 0;   // another pass handles this sub-slice
             }
 #pragma unroll
