@@ -145,19 +145,15 @@ struct rb_mgraph {
     uint8_t *ans, *home_ans;
     int64_t n_probe, n_key;           // records of one send buffer (all destinations)
     int64_t exchanged_bytes, rounds;
-    // peer-to-peer mode (GPUs of one box, CUDA IPC): everything that crosses NVLink is a store issued by the kernel that produced it --
-    // a producer's tile sort writes its runs straight into the owner's receive arena, the owner's apply kernel writes every answer
-    // straight into the producer's answer array, the producer's combine kernel writes the raise bytes into the owner's raise array --
-    // so the transfer overlaps the work tile by tile, every consumer reads local memory only, and no exchange step exists; the transport
-    // is only used for barriers / flag agreement.  (The first version let the consumers READ the producers' arenas in place: remote
-    // loads capped the apply kernels at ~330 GB/s per GPU at N = 8; profiles/r02_notes.md.)
+    // peer-to-peer mode (GPUs of one box, CUDA IPC): a consumer kernel reads the producers' send arenas directly over NVLink and writes
+    // its answers straight into the producers' answer arrays -- the transfer overlaps the filter work tile by tile and no separate
+    // exchange step (nor a receive buffer) exists; the transport is only used for barriers / flag agreement
     bool p2p;
     uint32_t* cnt_k;                  // packed key-range counts (its own array: peers may still read it while the probes are counted)
-    void** peer_open;                 // host: W * kPeerBufs pointers opened with cudaIpcOpenMemHandle (nullptr for this rank's own)
-    void **d_peer32, **d_peer64, **d_peer_ans, **d_peer_raise, **d_peer_cnt, **d_peer_cntk;   // device tables [W]: recv32, recv64, home_ans, ans, cnt_s, cnt_k
+    void** peer_open;                 // host: W * 5 pointers opened with cudaIpcOpenMemHandle (nullptr for this rank's own)
+    void **d_peer32, **d_peer64, **d_peer_ans, **d_peer_cnt, **d_peer_cntk;   // device tables [W]
 };
 
-constexpr int kPeerBufs = 6;   // buffers every rank exports with CUDA IPC
 extern "C" int32_t rb_mgraph_destroy(rb_mgraph* mg) {
     if (!mg) return RB_EINVAL;
     rb_ctx* ctx = mg->ctx;
@@ -174,13 +170,13 @@ extern "C" int32_t rb_mgraph_destroy(rb_mgraph* mg) {
     cudaFree(mg->dmult); cudaFree(mg->chunk_prefix); cudaFree(mg->flags);
 #ifndef RB_EMU
     if (mg->peer_open) {
-        for (int i = 0; i < mg->W * kPeerBufs; ++i) if (mg->peer_open[i]) cudaIpcCloseMemHandle(mg->peer_open[i]);
+        for (int i = 0; i < mg->W * 5; ++i) if (mg->peer_open[i]) cudaIpcCloseMemHandle(mg->peer_open[i]);
         free(mg->peer_open);
     }
 #endif
-    cudaFree(mg->d_peer32); cudaFree(mg->d_peer64); cudaFree(mg->d_peer_ans); cudaFree(mg->d_peer_raise); cudaFree(mg->d_peer_cnt); cudaFree(mg->d_peer_cntk);
+    cudaFree(mg->d_peer32); cudaFree(mg->d_peer64); cudaFree(mg->d_peer_ans); cudaFree(mg->d_peer_cnt); cudaFree(mg->d_peer_cntk);
     cudaFree(mg->send32); cudaFree(mg->send64); cudaFree(mg->home_ans); cudaFree(mg->cnt_s); cudaFree(mg->cnt_k);
-    if (mg->W > 1) { cudaFree(mg->recv32); cudaFree(mg->recv64); cudaFree(mg->ans); cudaFree(mg->cnt_r); }
+    if (mg->W > 1 && !mg->p2p) { cudaFree(mg->recv32); cudaFree(mg->recv64); cudaFree(mg->ans); cudaFree(mg->cnt_r); }
     delete mg;
     return RB_OK;
 }
@@ -194,29 +190,29 @@ static int32_t mg_setup_p2p(rb_mgraph* mg) {
     rb_ctx* ctx = mg->ctx;
     const int W = mg->W;
     if (W == 1 || !mg->tr.all_gather || !env_int("RB_MGRAPH_P2P", 1, 0, 1)) return RB_OK;
-    void* mine[kPeerBufs] = {mg->recv32, mg->recv64, mg->home_ans, mg->ans, mg->cnt_s, mg->cnt_k};
-    std::vector<cudaIpcMemHandle_t> hs(kPeerBufs), all((size_t)W * kPeerBufs);
+    void* mine[5] = {mg->send32, mg->send64, mg->home_ans, mg->cnt_s, mg->cnt_k};
+    std::vector<cudaIpcMemHandle_t> hs(5), all((size_t)W * 5);
     int failed = 0;
-    for (int i = 0; i < kPeerBufs; ++i) if (cudaIpcGetMemHandle(&hs[i], mine[i]) != cudaSuccess) failed = 1;
+    for (int i = 0; i < 5; ++i) if (cudaIpcGetMemHandle(&hs[i], mine[i]) != cudaSuccess) failed = 1;
     cudaGetLastError();
     void *d_h = nullptr, *d_all = nullptr;
     int* d_flag = nullptr;
-    const size_t hb = sizeof(cudaIpcMemHandle_t) * kPeerBufs;
+    const size_t hb = sizeof(cudaIpcMemHandle_t) * 5;
     CK(cudaMalloc(&d_h, hb)); CK(cudaMalloc(&d_all, hb * W)); CK(cudaMalloc(&d_flag, 64));
     CK(cudaMemcpyAsync(d_h, hs.data(), hb, cudaMemcpyHostToDevice, ctx->stream));
     int32_t rc = mg->tr.all_gather(mg->tr.user, d_h, d_all, (int64_t)hb, ctx->stream);
     if (rc) return rc;
     CK(cudaMemcpyAsync(all.data(), d_all, hb * W, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    mg->peer_open = (void**)calloc((size_t)W * kPeerBufs, sizeof(void*));
-    std::vector<void*> tab((size_t)W * kPeerBufs, nullptr);
+    mg->peer_open = (void**)calloc((size_t)W * 5, sizeof(void*));
+    std::vector<void*> tab((size_t)W * 5, nullptr);
     for (int p = 0; p < W && !failed; ++p)
-        for (int i = 0; i < kPeerBufs; ++i) {
-            if (p == mg->rank) { tab[(size_t)p * kPeerBufs + i] = mine[i]; continue; }
+        for (int i = 0; i < 5; ++i) {
+            if (p == mg->rank) { tab[(size_t)p * 5 + i] = mine[i]; continue; }
             void* ptr = nullptr;
-            if (cudaIpcOpenMemHandle(&ptr, all[(size_t)p * kPeerBufs + i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { failed = 1; cudaGetLastError(); break; }
-            mg->peer_open[(size_t)p * kPeerBufs + i] = ptr;
-            tab[(size_t)p * kPeerBufs + i] = ptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[(size_t)p * 5 + i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { failed = 1; cudaGetLastError(); break; }
+            mg->peer_open[(size_t)p * 5 + i] = ptr;
+            tab[(size_t)p * 5 + i] = ptr;
         }
     CK(cudaMemcpyAsync(d_flag, &failed, 4, cudaMemcpyHostToDevice, ctx->stream));
     rc = mg->tr.all_reduce_max(mg->tr.user, d_flag, 1, ctx->stream);
@@ -225,13 +221,13 @@ static int32_t mg_setup_p2p(rb_mgraph* mg) {
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(d_h); cudaFree(d_all); cudaFree(d_flag);
     if (failed) {   // somewhere a mapping failed: nobody uses peer memory
-        for (int i = 0; i < W * kPeerBufs; ++i) if (mg->peer_open[i]) { cudaIpcCloseMemHandle(mg->peer_open[i]); mg->peer_open[i] = nullptr; }
+        for (int i = 0; i < W * 5; ++i) if (mg->peer_open[i]) { cudaIpcCloseMemHandle(mg->peer_open[i]); mg->peer_open[i] = nullptr; }
         return RB_OK;
     }
-    void*** dst[kPeerBufs] = {&mg->d_peer32, &mg->d_peer64, &mg->d_peer_ans, &mg->d_peer_raise, &mg->d_peer_cnt, &mg->d_peer_cntk};
-    for (int i = 0; i < kPeerBufs; ++i) {
+    void*** dst[5] = {&mg->d_peer32, &mg->d_peer64, &mg->d_peer_ans, &mg->d_peer_cnt, &mg->d_peer_cntk};
+    for (int i = 0; i < 5; ++i) {
         std::vector<void*> col((size_t)W);
-        for (int p = 0; p < W; ++p) col[(size_t)p] = tab[(size_t)p * kPeerBufs + i];
+        for (int p = 0; p < W; ++p) col[(size_t)p] = tab[(size_t)p * 5 + i];
         CK(cudaMalloc(dst[i], sizeof(void*) * W));
         CK(cudaMemcpyAsync(*dst[i], col.data(), sizeof(void*) * W, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -378,15 +374,16 @@ static int32_t mgraph_create(rb_ctx* ctx, int32_t n_ranks, int32_t rank, const r
 #endif
     }
     if (W > 1) {
-        // receive arenas and an owner-side answer / raise array: the destinations of the peers' stores (peer-to-peer) or of the all-to-all
-        mg->recv32 = nullptr; mg->recv64 = nullptr; mg->ans = nullptr; mg->cnt_r = nullptr;   // they aliased the send side until here
-        er = cudaMalloc(&mg->recv32, n32_all * 4);
-        if (er == cudaSuccess) er = cudaMalloc(&mg->recv64, ((size_t)mg->n_key + kSlSpill) * 8);
-        if (er == cudaSuccess) er = cudaMalloc(&mg->ans, (size_t)mg->n_probe + kSlSpill);
-        if (er == cudaSuccess) er = cudaMalloc(&mg->cnt_r, (size_t)maxB_all * 4 + 64);
-        if (er != cudaSuccess) { rb_mgraph_destroy(mg); return fail(ctx, RB_ENOMEM, std::string("mgraph exchange buffers: ") + cudaGetErrorString(er)); }
         rc = mg_setup_p2p(mg);
         if (rc) { rb_mgraph_destroy(mg); return rc; }
+        if (!mg->p2p) {   // staged exchange: receive buffers and an owner-side answer array
+            mg->recv32 = nullptr; mg->recv64 = nullptr; mg->ans = nullptr; mg->cnt_r = nullptr;   // they aliased the send side until here
+            er = cudaMalloc(&mg->recv32, n32_all * 4);
+            if (er == cudaSuccess) er = cudaMalloc(&mg->recv64, ((size_t)mg->n_key + kSlSpill) * 8);
+            if (er == cudaSuccess) er = cudaMalloc(&mg->ans, (size_t)mg->n_probe + kSlSpill);
+            if (er == cudaSuccess) er = cudaMalloc(&mg->cnt_r, (size_t)maxB_all * 4 + 64);
+            if (er != cudaSuccess) { rb_mgraph_destroy(mg); return fail(ctx, RB_ENOMEM, std::string("mgraph exchange buffers: ") + cudaGetErrorString(er)); }
+        }
     }
     *out = mg;
     return RB_OK;
@@ -435,16 +432,14 @@ extern "C" int32_t rb_mgraph_stats(rb_mgraph* mg, int64_t* exchanged_bytes, int6
 }
 
 // ---- phases ---------------------------------------------------------------------------------------------------------------------------------
-// peer-to-peer: the runs go straight into the owners' receive arenas (`push` = device table of those, or nullptr)
-static SlArena mg_producer(rb_mgraph* mg, void* data, unsigned int* cursor, int per_rank, uint32_t cap, void** push = nullptr) {
+static SlArena mg_producer(rb_mgraph* mg, void* data, unsigned int* cursor, int per_rank, uint32_t cap) {
     SlArena a = sl_arena(data, cursor, nullptr, per_rank * mg->W, sl_chunk());
     a.cap = cap;
-    if (mg->p2p && push) { a.push_data = push; a.push_per_rank = per_rank; a.me = mg->rank; a.n_peers = mg->W; a.push_stride = (int64_t)per_rank * cap; }
     return a;
 }
 // regions received from every rank, in the consumer's order (local region first, source rank second)
-// p2p mode: peer_cnt = device table of the producers' packed counts, read in place (recv_cnt is not used); the records are in `data` either way
-static int32_t mg_consumer(rb_mgraph* mg, void* data, const uint32_t* recv_cnt, void** peer_cnt, int per_rank, uint32_t cap, int chunk,
+// p2p mode: peer_data / peer_cnt are the device tables of the producers' arenas / packed counts (data and recv_cnt are not used)
+static int32_t mg_consumer(rb_mgraph* mg, void* data, const uint32_t* recv_cnt, void** peer_data, void** peer_cnt, int per_rank, uint32_t cap, int chunk,
                            SlArena* out, int passes = 1) {
     rb_ctx* ctx = mg->ctx;
     const int n = per_rank * mg->W;
@@ -454,7 +449,7 @@ static int32_t mg_consumer(rb_mgraph* mg, void* data, const uint32_t* recv_cnt, 
     LAUNCH_CHECK();
     SlArena a = sl_arena(data, mg->cons_cursor, nullptr, n, chunk);
     a.cap = cap; a.cursor_stride = 1; a.rlo = mg->cons_rlo;
-    a.n_peers = mg->W; a.me = mg->rank; a.push_stride = (int64_t)per_rank * cap;
+    if (mg->p2p) { a.data = nullptr; a.peer_data = peer_data; a.n_peers = mg->W; }
     a.passes = passes;
     *out = a;
     RB_LAUNCH(1, kSlThreads, ((size_t)((a.B + 3) & ~3) + 296) * 4, ctx->stream, ks_chunk_prefix)(a, mg->chunk_prefix);
@@ -471,7 +466,7 @@ static int32_t mg_pack_counts(rb_mgraph* mg, const SlArena& a, uint32_t* dense) 
 static int32_t mg_barrier(rb_mgraph* mg);
 static int32_t mg_exchange(rb_mgraph* mg, const void* send, void* recv, int per_rank, uint32_t cap, int rec_bytes, bool with_counts) {
     if (mg->W == 1) return RB_OK;   // recv aliases send
-    if (mg->p2p) return mg_barrier(mg);   // the data was stored into the destination by the kernels that produced it: the consumer only has to know that all of it is there
+    if (mg->p2p) return mg_barrier(mg);   // the consumer reads the producers' arenas in place: it only has to know that they are complete
     rb_ctx* ctx = mg->ctx;
     int32_t rc;
     if (with_counts) {
@@ -510,7 +505,7 @@ static int32_t mg_route_lookup_t(rb_mgraph* mg, const Ingest& ing, int mode, int
     int32_t rc;
     constexpr int TILE = SlShape<NJ>::TILE, KPT = SlShape<NJ>::KPT;
     const HashMults hm = make_hm(mg->k);
-    const SlArena probes = mg_producer(mg, mg->send32, mg->probe_cursor, mg->R, mg->probe_cap, mg->d_peer32);
+    const SlArena probes = mg_producer(mg, mg->send32, mg->probe_cursor, mg->R, mg->probe_cap);
     CK(cudaMemsetAsync(probes.cursor, 0, (size_t)probes.B * kSlPad * 4, ctx->stream));
     const size_t sm_sort = TileSort<uint32_t, KPT * NJ>::smem_bytes(probes.B);
     const bool fast = sl_uniform_fast_probes<NJ>(ing, mg->k);
@@ -537,7 +532,7 @@ static int32_t mg_route_launch(rb_ctx* ctx, const Ingest& ing_in, void* user) {
     ing.out_base = 0;
     int32_t rc;
     if (u->lookup) return mg->paired ? mg_route_lookup_t<3>(mg, ing, u->mode, u->fh, u->rh) : mg_route_lookup_t<6>(mg, ing, u->mode, u->fh, u->rh);
-    const SlArena keys = mg_producer(mg, mg->send64, mg->key_cursor, mg->KR, mg->key_cap, mg->d_peer64);
+    const SlArena keys = mg_producer(mg, mg->send64, mg->key_cursor, mg->KR, mg->key_cap);
     CK(cudaMemsetAsync(keys.cursor, 0, (size_t)keys.B * kSlPad * 4, ctx->stream));
     const int n_ranges = 1 << mg->lg1, shift = 64 - mg->lg1;
     if (sl_uniform_fast_keys(ing, mg->k)) {
@@ -577,7 +572,7 @@ static int32_t mg_route(rb_mgraph* mg, const ReadsArg& ra, int mode, bool lookup
 static int32_t mg_apply(rb_mgraph* mg, bool set_bits) {
     rb_ctx* ctx = mg->ctx;
     SlArena a;
-    int32_t rc = mg_consumer(mg, mg->recv32, mg->cnt_r, mg->d_peer_cnt, mg->R, mg->probe_cap, sl_chunk(), &a,
+    int32_t rc = mg_consumer(mg, mg->recv32, mg->cnt_r, mg->d_peer32, mg->d_peer_cnt, mg->R, mg->probe_cap, sl_chunk(), &a,
                              mg->paired ? 1 << mg->sg_apply.pair_sub_log2 : 1);
     if (rc) return rc;
     if (mg->p2p) a.peer_ans = (uint8_t* const*)mg->d_peer_ans;
@@ -587,7 +582,7 @@ static int32_t mg_apply(rb_mgraph* mg, bool set_bits) {
         if (rc) return rc;
         fd = fc = mg->dbg->cs->cells;
     }
-    const size_t sm_pre = (size_t)(a.B + 1) * 4;
+    const size_t sm_pre = sl_apply_smem(a, false);
     int grid = 0;
     if (set_bits) {
         rc = sl_persistent_grid(ctx, ks_apply_probes<1>, sm_pre, &grid); if (rc) return rc;
@@ -602,7 +597,7 @@ static int32_t mg_apply(rb_mgraph* mg, bool set_bits) {
 static int32_t mg_dedup_emit(rb_mgraph* mg, bool with_cbf) {
     rb_ctx* ctx = mg->ctx;
     SlArena keys;
-    int32_t rc = mg_consumer(mg, mg->recv64, mg->cnt_r, mg->d_peer_cntk, mg->KR, mg->key_cap, kSlThreads * kKeyE, &keys);
+    int32_t rc = mg_consumer(mg, mg->recv64, mg->cnt_r, mg->d_peer64, mg->d_peer_cntk, mg->KR, mg->key_cap, kSlThreads * kKeyE, &keys);
     if (rc) return rc;
     const int n_sub = 1 << mg->sub_bits;
     const int n_sub_regions = mg->KR << mg->sub_bits;
@@ -621,7 +616,7 @@ static int32_t mg_dedup_emit(rb_mgraph* mg, bool with_cbf) {
     SL_LAUNCH("ks_dedup", ks_dedup, std::min(grid, n_sub_regions), sm_dedup, subs, n_sub_regions, mg->lg1 + mg->sub_bits, mg->dkey, mg->dmult, mg->n_distinct,
               (unsigned int)mg->n_dense, mg->flags, SpillTable{nullptr, nullptr, 0, 0});
     const HashMults hm = make_hm(mg->k);
-    const SlArena probes = mg_producer(mg, mg->send32, mg->probe_cursor, mg->R, mg->probe_cap, mg->d_peer32);
+    const SlArena probes = mg_producer(mg, mg->send32, mg->probe_cursor, mg->R, mg->probe_cap);
     CK(cudaMemsetAsync(probes.cursor, 0, (size_t)probes.B * kSlPad * 4, ctx->stream));
     const size_t sm_sort = TileSort<uint32_t, kSlTileRecords>::smem_bytes(probes.B);
     const int grid_d = (int)div_up(mg->n_dense, (int64_t)(mg->paired ? SlShape<3>::TILE : SlShape<6>::TILE));
@@ -655,21 +650,19 @@ static int32_t mg_raises(rb_mgraph* mg, int policy, uint64_t seed) {
     const int B = mg->R * mg->W;
     const size_t sm_r = TileAnswers::smem_bytes(B, kSlThreads * kSlTileRecords);
     const int grid_d = (int)div_up(mg->n_dense, (int64_t)(mg->paired ? SlShape<3>::TILE : SlShape<6>::TILE));
-    // peer-to-peer: the raise bytes are stored straight into the owners' arrays (mg->ans of every rank), at the owners' coordinates
-    TileAnswers::Push push{nullptr, 1, 0, 0};
-    if (mg->p2p) push = TileAnswers::Push{(uint8_t* const*)mg->d_peer_raise, mg->R, mg->rank, (int64_t)mg->R * mg->probe_cap};
     if (mg->paired) SL_LAUNCH("ks_combine_insert", ks_combine_insert<3>, grid_d, sm_r, mg->dkey, mg->dmult, mg->n_distinct, mg->pos, mg->tile_meta, B, mg->home_ans, mg->sg_route,
-                              policy, seed, (const int*)mg->flags, push);
+                              policy, seed, (const int*)mg->flags);
     else SL_LAUNCH("ks_combine_insert", ks_combine_insert<6>, grid_d, sm_r, mg->dkey, mg->dmult, mg->n_distinct, mg->pos, mg->tile_meta, B, mg->home_ans, mg->sg_route,
-                   policy, seed, (const int*)mg->flags, push);
-    // staged: the raise bytes travel to the owners like the probes did; p2p: they are already there, a barrier says when all of them are
+                   policy, seed, (const int*)mg->flags);
+    // staged: the raise bytes travel to the owners like the probes did; p2p: a barrier, then the owners read them in place
     rc = mg_exchange(mg, mg->home_ans, mg->ans, mg->R, mg->probe_cap, 1, false);
     if (rc) return rc;
     SlArena a;   // the regions mg_apply consumed (their counts are still where they were)
-    rc = mg_consumer(mg, mg->recv32, mg->cnt_r, mg->d_peer_cnt, mg->R, mg->probe_cap, sl_chunk(), &a,
+    rc = mg_consumer(mg, mg->recv32, mg->cnt_r, mg->d_peer32, mg->d_peer_cnt, mg->R, mg->probe_cap, sl_chunk(), &a,
                      mg->paired ? 1 << mg->sg_apply.pair_sub_log2 : 1);
     if (rc) return rc;
-    const size_t sm_pre = (size_t)(a.B + 1) * 4;
+    if (mg->p2p) a.peer_ans = (uint8_t* const*)mg->d_peer_ans;
+    const size_t sm_pre = sl_apply_smem(a, true);
     int grid = 0;
     rc = sl_persistent_grid(ctx, ks_apply_raises, sm_pre, &grid);
     if (rc) return rc;

@@ -24,7 +24,6 @@
 //     I6 ks_combine_insert  present = AND(old bits); replay m-1+present min-increments on the counter values
 //                           (bloom/CountingBloomFilter.java:170-194); the new value of every counter that grew is written over the
 //                           probe's answer byte -- the raise travels back to where the probe record already sits, sorted by slice
-//                           (sharded graph: pushed over NVLink into the owner's array)
 //     I7 ks_apply_raises    second sweep over the probe regions: counter = max(counter, raise byte), slice by slice
 // Linearisation is the one DESIGN.md section 4 states for batches: duplicates of a k-mer inside a round are aggregated, so exactly
 // one of them is the first sighting; k-mers that share a counter inside one round see the counter's value at the start of the round.
@@ -73,29 +72,19 @@ struct SlArena {
     void* spill_data;
     unsigned int* spill_cursor;
     uint32_t spill_cap;
-    // Sharded round in peer-to-peer mode (GPUs of one box, buffers mapped with CUDA IPC).  Everything that crosses NVLink is a STORE
-    // (posted, pipelined; remote loads were measured to cap the consumer kernels at ~330 GB/s):
-    //   producer  push_data[o] = the receive arena of owner rank o: the tile sort's copy-out writes the run of bucket b = o * push_per_rank + lr
-    //             to region me * push_per_rank + lr there, i.e. at its own arena coordinate + (me - o) * push_stride
-    //   consumer  reads its local receive arena (region b = (local region, source rank b % n_peers)), and writes the answer of a record
-    //             straight into the source's answer array peer_ans[src], at the source's coordinate = local + (me - src) * push_stride
-    // nullptr: one local arena (`data`), answers in the local array.
-    void* const* push_data;
-    int push_per_rank;
+    // consumer of a sharded round in peer-to-peer mode: region b lives in the arena of source rank b % n_peers, which this GPU reads
+    // directly over NVLink (peer_data[src] = that rank's send arena, mapped with CUDA IPC); answers are written straight into the
+    // source's answer array peer_ans[src].  nullptr: one local arena (`data`).
+    void* const* peer_data;
     uint8_t* const* peer_ans;
-    int n_peers, me;
-    int64_t push_stride;      // records of one rank's share of an arena (regions per rank * cap)
+    int n_peers;
     // consumer: every region is walked `passes` times (work items of pass 0 first, then pass 1 ...): a paired region may span several
     // L2-resident sub-slices, pass i handles the records of sub-slice i (SlGeom::pair_sub_log2).  1 everywhere else.
     int passes;
 };
 template <typename REC>
-__device__ __forceinline__ const REC* sl_region_records(const SlArena& a, int) { return reinterpret_cast<const REC*>(a.data); }
-// where the answers (consumer) of a region go: the local array, or the source rank's at the source's coordinates
-__device__ __forceinline__ uint8_t* sl_answer_base(const SlArena& a, int region, uint8_t* local) {
-    if (!a.peer_ans) return local;
-    const int src = region % a.n_peers;
-    return a.peer_ans[src] + (int64_t)(a.me - src) * a.push_stride;
+__device__ __forceinline__ const REC* sl_region_records(const SlArena& a, int region) {
+    return reinterpret_cast<const REC*>(a.peer_data ? a.peer_data[region % a.n_peers] : a.data);
 }
 struct SlGeom {
     FastMod dbg_fm, cbf_fm;   // global index arithmetic (reference semantics)
@@ -190,19 +179,18 @@ __device__ __forceinline__ uint32_t sl_region_hi(const SlArena& a, int region) {
 }
 template <typename REC, int E, bool SPILL = false>
 struct TileSort {
-    uint32_t *start, *scratch;           // [B] [296]
-    unsigned long long* dest;            // [B] address of staged position 0 of the tile if it belonged to the bucket's run (local or peer memory)
+    uint32_t *start, *delta, *scratch;   // [B] [B] [296]
     uint32_t *thresh, *delta2;           // SPILL: [B] staged positions from thresh[b] on go to the spill list, at delta2[b] + position
     REC* stage;                          // [256 * E] records in bucket order
     uint16_t* tag;                       // [256 * E] bucket of each staged record
     int B;
-    static __host__ __device__ size_t words_of(int B) { return ((size_t)(SPILL ? 5 : 3) * B + 296 + 3) & ~(size_t)3; }
+    static __host__ __device__ size_t words_of(int B) { return ((size_t)(SPILL ? 4 : 2) * B + 296 + 3) & ~(size_t)3; }
     static __host__ __device__ size_t smem_bytes(int B) { return words_of(B) * 4 + (size_t)kSlThreads * E * sizeof(REC) + (size_t)kSlThreads * E * 2; }
     __device__ __forceinline__ void init(unsigned char* smem, int B_) {
         B = B_;
-        dest = reinterpret_cast<unsigned long long*>(smem);   // first: 8-byte aligned
-        start = reinterpret_cast<uint32_t*>(dest + B);
-        scratch = start + B;
+        start = reinterpret_cast<uint32_t*>(smem);
+        delta = start + B;
+        scratch = delta + B;
         thresh = scratch + 296;
         delta2 = thresh + B;
         stage = reinterpret_cast<REC*>(smem + words_of(B) * 4);
@@ -243,12 +231,7 @@ struct TileSort {
                 const uint32_t cnt = (b + 1 < B ? start[b + 1] : total) - start[b];
                 const uint32_t lo = sl_region_lo(out, region0 + b), cap = sl_region_hi(out, region0 + b) - lo;
                 const uint32_t a = min(at[q], cap);
-                {   // the run starts at arena coordinate lo + a -- of this arena, or of the owner's receive arena (push mode)
-                    const int b_g = region0 + b;
-                    const int o = out.push_data ? b_g / out.push_per_rank : 0;
-                    REC* base = out.push_data ? reinterpret_cast<REC*>(out.push_data[o]) + (int64_t)(out.me - o) * out.push_stride : reinterpret_cast<REC*>(out.data);
-                    dest[b] = (unsigned long long)(uintptr_t)(base + ((int64_t)lo + a - (int64_t)start[b]));
-                }
+                delta[b] = lo + a - start[b];
                 if (meta) meta[b] = make_uint2(lo + a, start[b]);
                 bool failed = cnt && a + cnt > cap;
                 if (SPILL) {
@@ -264,14 +247,15 @@ struct TileSort {
         }
         if (meta && t == 0) meta[B] = make_uint2(0u, total);
         __syncthreads();
+        REC* data = reinterpret_cast<REC*>(out.data);
         if (SPILL) {
             REC* spill = reinterpret_cast<REC*>(out.spill_data);
             for (uint32_t p = t; p < total; p += kSlThreads) {
                 const uint32_t b = tag[p];
-                if (p < thresh[b]) reinterpret_cast<REC*>((uintptr_t)dest[b])[p] = stage[p]; else spill[delta2[b] + p] = stage[p];
+                if (p < thresh[b]) data[delta[b] + p] = stage[p]; else spill[delta2[b] + p] = stage[p];
             }
         } else {
-            for (uint32_t p = t; p < total; p += kSlThreads) reinterpret_cast<REC*>((uintptr_t)dest[tag[p]])[p] = stage[p];
+            for (uint32_t p = t; p < total; p += kSlThreads) data[delta[tag[p]] + p] = stage[p];
         }
         __syncthreads();
     }
@@ -360,18 +344,13 @@ struct TileAnswers {
     // the way back (ks_combine_insert): a thread overwrites the staged bytes of its own records, then the runs go back where they came from
     __device__ __forceinline__ void put(uint32_t place, uint32_t v) { if (place != kNoSlot) bytes[start[place & 0xFFFu] + (place >> 12)] = (uint8_t)v; }
     // every thread of the CTA calls it (after a __syncthreads that follows the last put); ONLY_COUNTERS: runs of dbgbf-only regions stay as they are
-    // push (sharded graph, peer-to-peer): the run of bucket b goes into the array of its owner rank o = b / per_rank, at this rank's
-    // coordinate + (me - o) * stride -- where the owner's second sweep over its received records will look for it
-    struct Push { uint8_t* const* tab; int per_rank, me; int64_t stride; };
-    __device__ __forceinline__ void store(int B, uint8_t* __restrict__ ans, const SlGeom& sg, const Push& push) const {
+    __device__ __forceinline__ void store(int B, uint8_t* __restrict__ ans, const SlGeom& sg) const {
         const uint32_t* gpos = start + (B + 1);
         const int grp = threadIdx.x >> 3, l8 = threadIdx.x & 7;
         for (int b = grp; b < B; b += kSlThreads / 8) {
             if (!sl_region_has_counters(sg, b)) continue;
             const uint32_t lo = start[b], n = start[b + 1] - lo, g = gpos[b];
-            uint8_t* dst = ans;
-            if (push.tab) { const int o = b / push.per_rank; dst = push.tab[o] + (int64_t)(push.me - o) * push.stride; }
-            for (uint32_t i = l8; i < n; i += 8) dst[g + i] = bytes[lo + i];
+            for (uint32_t i = l8; i < n; i += 8) ans[g + i] = bytes[lo + i];
         }
     }
 };
@@ -636,6 +615,39 @@ __device__ __forceinline__ SlWork sl_work_item(const SlArena& arena, const int* 
     return w;
 }
 
+// ---- asynchronous staging of a work item's records in shared memory (cp.async: SASS LDGSTS) ----------------------------------------------------
+// The apply kernels walk their arena one work item (<= kSlStageRecords records, contiguous) at a time.  The records of the NEXT item are
+// copied into shared memory with cp.async while the current item is applied: no registers are held for data in flight, so the latency of
+// the copy -- a microsecond out of local HBM, several over NVLink when the arena is a peer's (peer-to-peer mode of the sharded graph) --
+// hides behind the filter accesses of the current item.  (Holding the next item's records in registers instead was measured and lost:
+// the occupancy it costs is worth more than the latency it hides.)  16-byte pieces: region starts and work-item sizes are multiples of
+// 16 records (host: sl_capacity, sl_chunk), so every piece is aligned in global and shared memory.
+constexpr int kSlStageRecords = 4096;   // largest work item that is staged (2 buffers of 16 KiB + 2 of 4 KiB); larger ones are read directly
+__device__ __forceinline__ void sl_cp16(void* smem_dst, const void* gsrc) {
+#ifdef RB_EMU
+    memcpy(smem_dst, gsrc, 16);
+#else
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void sl_cp_commit() {
+#ifndef RB_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int PENDING>
+__device__ __forceinline__ void sl_cp_wait() {
+#ifndef RB_EMU
+    asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+#endif
+}
+// every thread of the CTA calls it: n_bytes (rounded up to 16) from src to dst, both 16-byte aligned
+__device__ __forceinline__ void sl_stage(void* dst, const void* src, uint32_t n_bytes) {
+    const uint32_t pieces = (n_bytes + 15u) >> 4;
+    for (uint32_t i = threadIdx.x; i < pieces; i += kSlThreads) sl_cp16(reinterpret_cast<char*>(dst) + (size_t)i * 16, reinterpret_cast<const char*>(src) + (size_t)i * 16);
+}
+
 // ---- S2 / I5: apply the probes.  SET = 1: dbgbf probes are test-and-set (graph.add / addDbgOnly) -------------------------------------
 template <int SET>
 __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena arena, int* chunk_prefix, const SlGeom sg,
@@ -649,14 +661,32 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
     constexpr int U = 8;   // probes in flight per thread
     const L2Keep keep = l2_keep_policy();
     __shared__ int s_c;
-    // (A software pipeline over the work items -- the records of the next item requested before the current one is applied -- was
-    // measured and lost: 9.1 -> 9.8 ms look-up, 12.7 -> 20.7 ms raises on local records; the extra registers cost more occupancy than the
-    // hidden latency gives back.  Remote latency is avoided altogether: in peer-to-peer mode the producers push, every read here is local.)
-    for (int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c); c < total; c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c)) {
-        const SlWork w = sl_work_item(arena, pre, c);
+    // two record buffers behind the prefix table (16-byte aligned); staged = the work items fit them
+    const bool staged = arena.chunk <= kSlStageRecords;
+    uint32_t* sbuf = reinterpret_cast<uint32_t*>(sl_smem + (((size_t)(arena.B + 1) * 4 + 15) & ~(size_t)15));
+    int buf = 0;
+    SlWork w_ahead;
+    int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c);
+    if (c < total) {
+        w_ahead = sl_work_item(arena, pre, c);
+        if (staged) { sl_stage(sbuf, sl_region_records<uint32_t>(arena, w_ahead.b) + w_ahead.first, w_ahead.n * 4u); sl_cp_commit(); }
+    }
+    while (c < total) {
+        const SlWork w = w_ahead;
+        c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c);   // its barrier: everybody is done with the buffer the next copy overwrites
+        if (c < total) {
+            w_ahead = sl_work_item(arena, pre, c);
+            if (staged) { sl_stage(sbuf + (buf ^ 1) * arena.chunk, sl_region_records<uint32_t>(arena, w_ahead.b) + w_ahead.first, w_ahead.n * 4u); sl_cp_commit(); }
+        }
+        if (staged) {
+            if (c < total) sl_cp_wait<1>(); else sl_cp_wait<0>();   // this item's copy has landed (the next one's may still fly)
+            __syncthreads();
+        }
+        const uint32_t* cur = sbuf + buf * arena.chunk;
+        buf ^= 1;
         const int lr = w.b / sg.region_div;   // local region: dbgbf slices first, then cbf slices -- or paired slices
         const uint32_t* rec = sl_region_records<uint32_t>(arena, w.b);                      // local, or the source rank's arena over NVLink
-        uint8_t* ans_out = sl_answer_base(arena, w.b, ans);   // answers land where the producer will look (its own array, its own coordinates)
+        uint8_t* ans_out = arena.peer_ans ? arena.peer_ans[w.b % arena.n_peers] : ans;  // answers land where the producer will look
         if (sg.paired) {
             // record = chunk << pair_log2 | offset: counter byte (lr << pair_log2) + offset, bit chunk * pair_local_c + the same
             const uint64_t byte0 = (uint64_t)lr << sg.pair_log2;
@@ -668,7 +698,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const bool in = i0 + u * kSlThreads < w.n;
-                    li[u] = in ? __ldcs(rec + w.first + i0 + u * kSlThreads) : 0u;
+                    li[u] = !in ? 0u : staged ? cur[i0 + u * kSlThreads] : __ldcs(rec + w.first + i0 + u * kSlThreads);
                     act[u] = in && (int)((li[u] & off_mask) >> sub_shift) == w.pass;
                 }
                 if (sg.cells) {   // one access per record: the cell word holds the counter and the bit
@@ -717,7 +747,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
         for (uint32_t i0 = threadIdx.x; i0 < w.n; i0 += kSlThreads * U) {
             uint32_t li[U], wd[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) li[u] = (i0 + u * kSlThreads < w.n) ? __ldcs(rec + w.first + i0 + u * kSlThreads) : 0u;
+            for (int u = 0; u < U; ++u) li[u] = !(i0 + u * kSlThreads < w.n) ? 0u : staged ? cur[i0 + u * kSlThreads] : __ldcs(rec + w.first + i0 + u * kSlThreads);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 wd[u] = 0;
@@ -979,8 +1009,7 @@ template <int NJ>
 __global__ void __launch_bounds__(kSlThreads) ks_combine_insert(const unsigned long long* __restrict__ dkey, const unsigned int* __restrict__ dmult,
                                                                const unsigned int* __restrict__ n_distinct, const uint32_t* __restrict__ pos,
                                                                const uint2* __restrict__ tile_meta, int probe_B, uint8_t* ans,
-                                                               const SlGeom sg, int policy, uint64_t rng_seed, const int* abort,
-                                                               const TileAnswers::Push push) {
+                                                               const SlGeom sg, int policy, uint64_t rng_seed, const int* abort) {
     constexpr int KPT = SlShape<NJ>::KPT, TILE = SlShape<NJ>::TILE;
     if (abort && *abort) return;
     const int64_t nd = (int64_t)*n_distinct;
@@ -1034,7 +1063,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_combine_insert(const unsigned l
         }
     }
     __syncthreads();
-    ta.store(probe_B, ans, sg, push);
+    ta.store(probe_B, ans, sg);
 }
 
 // ---- I7: raise the counters slice by slice: the second sweep over the probe regions, this time reading the raise bytes ------------------------
@@ -1048,12 +1077,43 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_raises(const SlArena aren
     constexpr int U = 4;
     const L2Keep keep = l2_keep_policy();
     __shared__ int s_c;
-    for (int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c); c < total; c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c)) {
-        const SlWork w = sl_work_item(arena, pre, c);
+    // the same cp.async pipeline as ks_apply_probes, for the records and their raise bytes (local, or a peer's over NVLink)
+    const bool staged = arena.chunk <= kSlStageRecords;
+    uint32_t* sbuf = reinterpret_cast<uint32_t*>(sl_smem + (((size_t)(arena.B + 1) * 4 + 15) & ~(size_t)15));
+    uint8_t* vbuf = reinterpret_cast<uint8_t*>(sbuf + 2 * arena.chunk);
+    int buf = 0;
+    SlWork w_ahead;
+    int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c);
+    if (c < total) {
+        w_ahead = sl_work_item(arena, pre, c);
+        if (staged) {
+            sl_stage(sbuf, sl_region_records<uint32_t>(arena, w_ahead.b) + w_ahead.first, w_ahead.n * 4u);
+            sl_stage(vbuf, (arena.peer_ans ? arena.peer_ans[w_ahead.b % arena.n_peers] : raise) + w_ahead.first, w_ahead.n);
+            sl_cp_commit();
+        }
+    }
+    while (c < total) {
+        const SlWork w = w_ahead;
+        c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c);   // its barrier: everybody is done with the buffers the next copy overwrites
+        if (c < total) {
+            w_ahead = sl_work_item(arena, pre, c);
+            if (staged) {
+                sl_stage(sbuf + (buf ^ 1) * arena.chunk, sl_region_records<uint32_t>(arena, w_ahead.b) + w_ahead.first, w_ahead.n * 4u);
+                sl_stage(vbuf + (buf ^ 1) * arena.chunk, (arena.peer_ans ? arena.peer_ans[w_ahead.b % arena.n_peers] : raise) + w_ahead.first, w_ahead.n);
+                sl_cp_commit();
+            }
+        }
+        if (staged) {
+            if (c < total) sl_cp_wait<1>(); else sl_cp_wait<0>();
+            __syncthreads();
+        }
+        const uint32_t* cur_r = sbuf + buf * arena.chunk;
+        const uint8_t* cur_v = vbuf + buf * arena.chunk;
+        buf ^= 1;
         const int lr = w.b / sg.region_div;   // local region
         if (!sg.paired && lr < sg.n_dbg) continue;   // dbgbf probes (the whole CTA)
-        const uint32_t* rec = sl_region_records<uint32_t>(arena, w.b);
-        const uint8_t* rb = raise;
+        const uint32_t* rec = sl_region_records<uint32_t>(arena, w.b);                              // local, or the source rank's arena over NVLink
+        const uint8_t* rb = arena.peer_ans ? arena.peer_ans[w.b % arena.n_peers] : raise;   // ... and the source rank's raise bytes
         const uint64_t byte0 = sg.paired ? (uint64_t)lr << sg.pair_log2 : (uint64_t)(lr - sg.n_dbg) << sg.cbf_log2;
         const uint32_t off_mask = sg.paired ? (1u << sg.pair_log2) - 1u : 0xFFFFFFFFu;
         const int sub_shift = sg.paired ? sg.pair_log2 - sg.pair_sub_log2 : 31;
@@ -1062,10 +1122,11 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_raises(const SlArena aren
         for (uint32_t i0 = threadIdx.x; i0 < w.n; i0 += kSlThreads * U) {
             uint32_t v[U], li[U], wd[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) v[u] = (i0 + u * kSlThreads < w.n) ? (uint32_t)__ldcs(rb + w.first + i0 + u * kSlThreads) : 0u;
+            for (int u = 0; u < U; ++u)
+                v[u] = !(i0 + u * kSlThreads < w.n) ? 0u : staged ? (uint32_t)cur_v[i0 + u * kSlThreads] : (uint32_t)__ldcs(rb + w.first + i0 + u * kSlThreads);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                li[u] = (v[u] ? __ldcs(rec + w.first + i0 + u * kSlThreads) : 0u) & off_mask;
+                li[u] = (!v[u] ? 0u : staged ? cur_r[i0 + u * kSlThreads] : __ldcs(rec + w.first + i0 + u * kSlThreads)) & off_mask;
                 if (arena.passes > 1 && (int)(li[u] >> sub_shift) != w.pass) v[u] = 0;   // another pass handles this sub-slice
             }
 #pragma unroll
@@ -1166,15 +1227,15 @@ __global__ void __launch_bounds__(kSlThreads) ks_order_counts(const uint32_t* __
     }
 }
 
-// the same in peer-to-peer mode: the counts are read from the source ranks' packed count arrays in place; the records were stored by the
-// sources into this rank's receive arena, source src's regions at (src * per_rank + local region) * cap as after an all-to-all
+// the same in peer-to-peer mode: the counts are read from the source ranks' packed count arrays, the regions stay where they are
+// (source src's arena holds the regions for this rank at (me * per_rank + local region) * cap)
 __global__ void __launch_bounds__(kSlThreads) ks_order_counts_p2p(const uint32_t* const* __restrict__ peer_cnt, int n_ranks, int me, int per_rank, uint32_t cap,
                                                                  unsigned int* __restrict__ cursor, uint32_t* __restrict__ rlo) {
     const int i = blockIdx.x * kSlThreads + threadIdx.x;   // consumer region
     if (i < n_ranks * per_rank) {
         const int lr = i / n_ranks, src = i % n_ranks;
         cursor[i] = peer_cnt[src][me * per_rank + lr];
-        rlo[i] = (uint32_t)(src * per_rank + lr) * cap;
+        rlo[i] = (uint32_t)(me * per_rank + lr) * cap;
     }
 }
 

@@ -40,11 +40,11 @@ static int env_int(const char* name, int dflt, int lo, int hi) {
 // Consumers walk an arena region by region with a window of grid * chunk records in flight; the window has to stay a small
 // fraction of a region or several filter / table slices are live at once and fall out of L2.
 static bool sliced_supports(const rb_graph* g) { return g->hd <= kSlMaxH && g->hc <= kSlMaxH && !(g->se && g->se->unsupported); }
-static int sl_chunk() { return env_int("RB_SLICED_CHUNK", 2048, 256, 1 << 16); }
+static int sl_chunk() { return env_int("RB_SLICED_CHUNK", 2048, 256, 1 << 16) & ~15; }   // a multiple of 16 records: the apply kernels stage work items with 16-byte cp.async
 static int sl_consumer_occ() { return env_int("RB_SLICED_CONSUMER_OCC", 8, 1, 8); }
 static int64_t sl_pow2_at_least(int64_t v) { int64_t p = 1024; while (p < v) p <<= 1; return p; }
 // capacity of a region that expects `expected` records from uniform hashes: 4 % + 8 sigma + a constant
-static int64_t sl_capacity(double expected) { return (int64_t)(expected * 1.04 + 8.0 * std::sqrt(expected + 1.0)) + 2048; }
+static int64_t sl_capacity(double expected) { return (((int64_t)(expected * 1.04 + 8.0 * std::sqrt(expected + 1.0)) + 2048) + 15) & ~(int64_t)15; }   // multiple of 16: regions start 16-byte aligned (cp.async staging)
 // Rounds are as large as the 32-bit record positions allow (one sweep of the filters is amortised over the round); look-ups whose
 // results go back to host memory use smaller rounds so that the D2H copy of one round overlaps the kernels of the next.
 static int64_t sliced_round_kmers(const rb_ctx* ctx, bool host_results) {
@@ -238,7 +238,7 @@ static SlArena sl_arena(void* data, unsigned int* cursor, const uint32_t* roff, 
     SlArena a;
     a.data = data; a.cursor = cursor; a.roff = roff; a.B = B; a.chunk = chunk; a.cap = 0; a.cursor_stride = kSlPad; a.rlo = nullptr;
     a.spill_data = nullptr; a.spill_cursor = nullptr; a.spill_cap = 0;
-    a.push_data = nullptr; a.push_per_rank = 1; a.peer_ans = nullptr; a.n_peers = 1; a.me = 0; a.push_stride = 0; a.passes = 1;
+    a.peer_data = nullptr; a.peer_ans = nullptr; a.n_peers = 1; a.passes = 1;
     return a;
 }
 static SlArena sl_probe_arena(SlicedEngine* e) {
@@ -295,6 +295,14 @@ static int32_t sl_round_layout(rb_graph* g, SlicedEngine* e, int64_t n_pos, SlLa
     return RB_OK;
 }
 
+// dynamic shared memory of the apply kernels: the work-list prefix table, then (when the work items fit) two staging buffers of records
+// and, for the raise sweep, two of raise bytes
+static size_t sl_apply_smem(const SlArena& a, bool with_raise_bytes) {
+    size_t sm = ((size_t)(a.B + 1) * 4 + 15) & ~(size_t)15;
+    if (a.chunk <= kSlStageRecords) sm += (size_t)2 * a.chunk * (with_raise_bytes ? 5 : 4);
+    return sm;
+}
+
 // S1..S3
 template <int NJ>
 static int32_t sliced_count_round_t(rb_graph* g, SlicedEngine* e, const Ingest& ing, int mode, float* counts, int64_t* fh, int64_t* rh, bool* fell_back) {
@@ -330,7 +338,7 @@ static int32_t sliced_count_round_t(rb_graph* g, SlicedEngine* e, const Ingest& 
     SlLayout lay;
     rc = sl_round_layout(g, e, ing.n_pos, &lay);
     if (rc) return rc;
-    const size_t sm_pre = (size_t)(probes.B + 1) * 4;
+    const size_t sm_pre = sl_apply_smem(probes, false);
     int grid = 0;
     rc = sl_persistent_grid(ctx, ks_apply_probes<0>, sm_pre, &grid);
     if (rc) return rc;
@@ -442,7 +450,7 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     SlLayout lay;
     rc = sl_round_layout(g, e, ing.n_pos, &lay);
     if (rc) return rc;
-    const size_t sm_pre = (size_t)(probes.B + 1) * 4;
+    const size_t sm_pre = sl_apply_smem(probes, false);
     if (policy != POLICY_COUNT_IF_PRESENT) {
         rc = sl_persistent_grid(ctx, ks_apply_probes<1>, sm_pre, &grid); if (rc) return rc;
         SL_LAUNCH("ks_apply_probes<1>", ks_apply_probes<1>, grid, sm_pre, probes, e->chunk_prefix, lay.sg, lay.dbg, lay.cbf, e->ans, (const int*)nullptr);
@@ -456,14 +464,15 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
         const uint64_t seed = ctx->rng_seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(ctx->launches + 1);
         const size_t sm_r = TileAnswers::smem_bytes(probes.B, kSlThreads * kSlTileRecords);
         if (e->paired) SL_LAUNCH("ks_combine_insert", ks_combine_insert<3>, grid_d, sm_r, e->dkey, e->dmult, e->n_distinct, e->pos, e->tile_meta, probes.B, e->ans, e->sg,
-                                 policy, seed, (const int*)nullptr, TileAnswers::Push{nullptr, 1, 0, 0});
+                                 policy, seed, (const int*)nullptr);
         else SL_LAUNCH("ks_combine_insert", ks_combine_insert<6>, grid_d, sm_r, e->dkey, e->dmult, e->n_distinct, e->pos, e->tile_meta, probes.B, e->ans, e->sg,
-                       policy, seed, (const int*)nullptr, TileAnswers::Push{nullptr, 1, 0, 0});
+                       policy, seed, (const int*)nullptr);
         rc = sl_chunk_prefix(ctx, e, probes);   // the same work list again (the consumers' counter starts from 0)
         if (rc) return rc;
-        rc = sl_persistent_grid(ctx, ks_apply_raises, sm_pre, &grid);
+        const size_t sm_raise = sl_apply_smem(probes, true);
+        rc = sl_persistent_grid(ctx, ks_apply_raises, sm_raise, &grid);
         if (rc) return rc;
-        SL_LAUNCH("ks_apply_raises", ks_apply_raises, grid, sm_pre, probes, e->chunk_prefix, lay.sg, lay.cbf, (const uint8_t*)e->ans, (const int*)nullptr);
+        SL_LAUNCH("ks_apply_raises", ks_apply_raises, grid, sm_raise, probes, e->chunk_prefix, lay.sg, lay.cbf, (const uint8_t*)e->ans, (const int*)nullptr);
     }
     claim_invalidate(ctx);   // bits were set without going through the claim table
     return RB_OK;
