@@ -648,18 +648,6 @@ __device__ __forceinline__ void sl_stage(void* dst, const void* src, uint32_t n_
     for (uint32_t i = threadIdx.x; i < pieces; i += kSlThreads) sl_cp16(reinterpret_cast<char*>(dst) + (size_t)i * 16, reinterpret_cast<const char*>(src) + (size_t)i * 16);
 }
 
-__device__ __forceinline__ void sl_put_answer(bool bulk, uint8_t* abuf, uint8_t* out, uint32_t idx, uint32_t value) {
-    if (bulk) abuf[idx] = (uint8_t)value; else __stcs(out + idx, (uint8_t)value);
-}
-// every thread of the CTA calls it: the n answer bytes collected in shared memory go out as 16-byte stores (`out` is 16-byte aligned: region
-// starts and work-item sizes are multiples of 16), the tail byte by byte
-__device__ __forceinline__ void sl_flush_answers(const uint8_t* abuf, uint8_t* out, uint32_t n) {
-    __syncthreads();
-    const uint32_t n16 = n >> 4;
-    for (uint32_t i = threadIdx.x; i < n16; i += kSlThreads) __stcs(reinterpret_cast<uint4*>(out) + i, reinterpret_cast<const uint4*>(abuf)[i]);
-    for (uint32_t i = (n16 << 4) + threadIdx.x; i < n; i += kSlThreads) __stcs(out + i, abuf[i]);
-}
-
 // ---- S2 / I5: apply the probes.  SET = 1: dbgbf probes are test-and-set (graph.add / addDbgOnly) -------------------------------------
 template <int SET>
 __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena arena, int* chunk_prefix, const SlGeom sg,
@@ -699,11 +687,6 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
         const int lr = w.b / sg.region_div;   // local region: dbgbf slices first, then cbf slices -- or paired slices
         const uint32_t* rec = sl_region_records<uint32_t>(arena, w.b);                      // local, or the source rank's arena over NVLink
         uint8_t* ans_out = arena.peer_ans ? arena.peer_ans[w.b % arena.n_peers] : ans;  // answers land where the producer will look
-        // The answers of a work item are collected in shared memory and leave as 16-byte stores (a peer's answer array is written over
-        // NVLink: one byte per thread made 32-byte write packets and cost the look-up 3 ms at N = 2).  Not with several passes per region:
-        // a pass answers only the records of its sub-slice.
-        const bool bulk = staged && arena.passes <= 1;
-        uint8_t* abuf = reinterpret_cast<uint8_t*>(sbuf + 2 * arena.chunk);
         if (sg.paired) {
             // record = chunk << pair_log2 | offset: counter byte (lr << pair_log2) + offset, bit chunk * pair_local_c + the same
             const uint64_t byte0 = (uint64_t)lr << sg.pair_log2;
@@ -731,7 +714,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
                             const int sh = (int)(ci & 1) * 16;
                             const uint32_t bit = 1u << (sh + 8 + (int)(li[u] >> sg.pair_log2));
                             if (SET && !(wd[u] & bit)) wd[u] = atomic_or_keep(dbg_words + (ci >> 1), bit, keep);
-                            sl_put_answer(bulk, abuf, ans_out + w.first, i0 + u * kSlThreads, ((wd[u] & bit) ? 0x80u : 0u) | ((wd[u] >> sh) & 0x7Fu));
+                            __stcs(ans_out + w.first + i0 + u * kSlThreads, (uint8_t)(((wd[u] & bit) ? 0x80u : 0u) | ((wd[u] >> sh) & 0x7Fu)));
                         }
                     }
                     continue;
@@ -753,11 +736,10 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
                         const uint64_t bi = (uint64_t)(li[u] >> sg.pair_log2) * sg.pair_local_c + ci;
                         const uint32_t bit = 1u << (bi & 31);
                         if (SET && !(wd[u] & bit)) wd[u] = atomic_or_keep(dbg_words + (bi >> 5), bit, keep);
-                        sl_put_answer(bulk, abuf, ans_out + w.first, i0 + u * kSlThreads, ((wd[u] & bit) ? 0x80u : 0u) | ((wc[u] >> ((ci & 3) * 8)) & 0x7Fu));
+                        __stcs(ans_out + w.first + i0 + u * kSlThreads, (uint8_t)(((wd[u] & bit) ? 0x80u : 0u) | ((wc[u] >> ((ci & 3) * 8)) & 0x7Fu)));
                     }
                 }
             }
-            if (bulk) sl_flush_answers(abuf, ans_out + w.first, w.n);
             continue;
         }
         const bool is_dbg = lr < sg.n_dbg;
@@ -782,11 +764,10 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
                     } else {
                         value = (wd[u] >> ((li[u] & 3) * 8)) & 0x7Fu;
                     }
-                    sl_put_answer(bulk, abuf, ans_out + w.first, i0 + u * kSlThreads, value);
+                    __stcs(ans_out + w.first + i0 + u * kSlThreads, (uint8_t)value);
                 }
             }
         }
-        if (bulk) sl_flush_answers(abuf, ans_out + w.first, w.n);
     }
 }
 

@@ -299,7 +299,7 @@ static int32_t sl_round_layout(rb_graph* g, SlicedEngine* e, int64_t n_pos, SlLa
 // and, for the raise sweep, two of raise bytes
 static size_t sl_apply_smem(const SlArena& a, bool with_raise_bytes) {
     size_t sm = ((size_t)(a.B + 1) * 4 + 15) & ~(size_t)15;
-    if (a.chunk <= kSlStageRecords) sm += (size_t)2 * a.chunk * (with_raise_bytes ? 5 : 4) + (with_raise_bytes ? 0 : (size_t)a.chunk);   // + the answers of one work item
+    if (a.chunk <= kSlStageRecords) sm += (size_t)2 * a.chunk * (with_raise_bytes ? 5 : 4);
     return sm;
 }
 
