@@ -451,6 +451,7 @@ static int32_t mg_consumer(rb_mgraph* mg, void* data, const uint32_t* recv_cnt, 
     a.cap = cap; a.cursor_stride = 1; a.rlo = mg->cons_rlo;
     if (mg->p2p) { a.data = nullptr; a.peer_data = peer_data; a.n_peers = mg->W; }
     a.passes = passes;
+    sl_apply_stage(&a);
     *out = a;
     RB_LAUNCH(1, kSlThreads, ((size_t)((a.B + 3) & ~3) + 296) * 4, ctx->stream, ks_chunk_prefix)(a, mg->chunk_prefix);
     LAUNCH_CHECK();

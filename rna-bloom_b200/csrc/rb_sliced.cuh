@@ -81,6 +81,10 @@ struct SlArena {
     // consumer: every region is walked `passes` times (work items of pass 0 first, then pass 1 ...): a paired region may span several
     // L2-resident sub-slices, pass i handles the records of sub-slice i (SlGeom::pair_sub_log2).  1 everywhere else.
     int passes;
+    // consumer: the apply kernels bring the next work item into shared memory with cp.async while the current one is applied (host:
+    // sl_apply_stage -- on when the records are a peer's, where it hides the NVLink latency; on local records it was measured to cost
+    // 0.8 ms per kernel and is off unless RB_SLICED_STAGE=1)
+    int stage;
 };
 template <typename REC>
 __device__ __forceinline__ const REC* sl_region_records(const SlArena& a, int region) {
@@ -662,7 +666,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
     const L2Keep keep = l2_keep_policy();
     __shared__ int s_c;
     // two record buffers behind the prefix table (16-byte aligned); staged = the work items fit them
-    const bool staged = arena.chunk <= kSlStageRecords;
+    const bool staged = arena.stage != 0;
     uint32_t* sbuf = reinterpret_cast<uint32_t*>(sl_smem + (((size_t)(arena.B + 1) * 4 + 15) & ~(size_t)15));
     int buf = 0;
     SlWork w_ahead;
@@ -1078,7 +1082,7 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_raises(const SlArena aren
     const L2Keep keep = l2_keep_policy();
     __shared__ int s_c;
     // the same cp.async pipeline as ks_apply_probes, for the records and their raise bytes (local, or a peer's over NVLink)
-    const bool staged = arena.chunk <= kSlStageRecords;
+    const bool staged = arena.stage != 0;
     uint32_t* sbuf = reinterpret_cast<uint32_t*>(sl_smem + (((size_t)(arena.B + 1) * 4 + 15) & ~(size_t)15));
     uint8_t* vbuf = reinterpret_cast<uint8_t*>(sbuf + 2 * arena.chunk);
     int buf = 0;

@@ -238,12 +238,14 @@ static SlArena sl_arena(void* data, unsigned int* cursor, const uint32_t* roff, 
     SlArena a;
     a.data = data; a.cursor = cursor; a.roff = roff; a.B = B; a.chunk = chunk; a.cap = 0; a.cursor_stride = kSlPad; a.rlo = nullptr;
     a.spill_data = nullptr; a.spill_cursor = nullptr; a.spill_cap = 0;
-    a.peer_data = nullptr; a.peer_ans = nullptr; a.n_peers = 1; a.passes = 1;
+    a.peer_data = nullptr; a.peer_ans = nullptr; a.n_peers = 1; a.passes = 1; a.stage = 0;
     return a;
 }
+static void sl_apply_stage(SlArena* a);
 static SlArena sl_probe_arena(SlicedEngine* e) {
     SlArena a = sl_arena(e->probe_data, e->probe_cursor, e->probe_roff, e->probe_B, sl_chunk());
     if (e->paired) a.passes = 1 << e->sg.pair_sub_log2;
+    sl_apply_stage(&a);
     return a;
 }
 
@@ -299,8 +301,12 @@ static int32_t sl_round_layout(rb_graph* g, SlicedEngine* e, int64_t n_pos, SlLa
 // and, for the raise sweep, two of raise bytes
 static size_t sl_apply_smem(const SlArena& a, bool with_raise_bytes) {
     size_t sm = ((size_t)(a.B + 1) * 4 + 15) & ~(size_t)15;
-    if (a.chunk <= kSlStageRecords) sm += (size_t)2 * a.chunk * (with_raise_bytes ? 5 : 4);
+    if (a.stage) sm += (size_t)2 * a.chunk * (with_raise_bytes ? 5 : 4);
     return sm;
+}
+// cp.async staging of the work items: when the records are read out of a peer's arena (NVLink latency), or when asked for (tests)
+static void sl_apply_stage(SlArena* a) {
+    a->stage = (a->peer_data != nullptr || env_int("RB_SLICED_STAGE", 0, 0, 1)) && a->chunk <= kSlStageRecords ? 1 : 0;
 }
 
 // S1..S3

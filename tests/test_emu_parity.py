@@ -46,7 +46,7 @@ def ctx(emu_lib):
     c.close()
 
 
-SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICED_CELLS": "1", "RB_SLICED_SUBRANGE_LOG2": "6",
+SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICED_CELLS": "1", "RB_SLICED_STAGE": "1", "RB_SLICED_SUBRANGE_LOG2": "6",
              "RB_SLICE_PAIR_LOG2": "13"}
 # sliced-small: tiny slices / sub-ranges so that the small test filters span hundreds of regions (every test);
 # sliced-default: the production geometry; direct: validates the emulation itself (that engine is verified on the GPU)
@@ -63,7 +63,7 @@ ONLY = {
                        "test_config3_settings_match_oracle", "test_config4_long_reads_match_oracle", "test_loaded_cbf_envelope_at_scale"),
 }
 SKIP = {"sliced-small": ("test_kernels_are_race_free_under_tsan", "test_neighbor_counts_match_oracle", "test_random_geometry_matches_oracle",
-                         "test_random_uniform_layout_matches_oracle"),
+                         "test_random_uniform_layout_matches_oracle", "test_config3_settings_match_oracle", "test_config4_long_reads_match_oracle"),
         "sliced-small-spill": ("test_random_geometry_matches_oracle", "test_random_uniform_layout_matches_oracle")}   # the random test sets its own geometry: it runs once, under "sliced-default"   # sets its own environment; runs once (under "sliced-default")
 
 
@@ -89,7 +89,9 @@ def engine(request):
             os.environ[k] = v
 
 
-test_duplicates_inside_one_batch_are_linearised = G.test_duplicates_inside_one_batch_are_linearised
+def test_duplicates_inside_one_batch_are_linearised(ctx, orc, monkeypatch):
+    monkeypatch.setattr(G, "DUP_FILTER_LOG2", 24)   # 2^30 filters cost minutes of memset / compare per graph in the emulation
+    G.test_duplicates_inside_one_batch_are_linearised(ctx, orc)
 test_getkmers_with_invalid_nucleotides = G.test_getkmers_with_invalid_nucleotides
 test_kmerize_ascii_is_exact_for_every_character = G.test_kmerize_ascii_is_exact_for_every_character
 test_equal_length_ascii_records_and_async_counts = G.test_equal_length_ascii_records_and_async_counts
@@ -118,8 +120,8 @@ test_neighbor_counts_match_oracle = G.test_neighbor_counts_match_oracle
 # paired probe records (cbf_bytes a power of two dividing dbg_bits): q = 8, q = 5 (stranded), h_d > h_c, and the h_d < h_c case that must
 # stay unpaired; both read layouts
 @pytest.mark.parametrize("layout", ["ragged", "uniform"])
-@pytest.mark.parametrize("stranded,k,hd,hc,dbg_bits,cbf_bytes", [(False, 25, 3, 3, 1 << 29, 1 << 26), (True, 25, 3, 3, 5 << 24, 1 << 24),
-                                                                 (False, 31, 3, 2, 1 << 27, 1 << 27), (False, 25, 2, 3, 1 << 29, 1 << 26)])
+@pytest.mark.parametrize("stranded,k,hd,hc,dbg_bits,cbf_bytes", [(False, 25, 3, 3, 1 << 27, 1 << 24), (True, 25, 3, 3, 5 << 24, 1 << 24),
+                                                                 (False, 31, 3, 2, 1 << 25, 1 << 25), (False, 25, 2, 3, 1 << 27, 1 << 24)])
 def test_paired_slices_match_oracle(ctx, orc, stranded, k, hd, hc, dbg_bits, cbf_bytes, layout):
     G.test_paired_slices_match_oracle(ctx, orc, stranded, k, hd, hc, dbg_bits, cbf_bytes, layout)
 

@@ -28,7 +28,7 @@ ENGINE_TESTS = {"test_graph_add_collision_free_is_bit_exact", "test_duplicates_i
                 "test_config4_long_reads_match_oracle", "test_loaded_cbf_envelope_at_scale"}
 # "sliced-small": slices of 16 KiB / 32 KiB so that the small test filters span hundreds of regions (the default 64 MiB slices
 # would put every test filter into one or two regions and leave the multi-region paths to the full-size test alone)
-SMALL_SLICES = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICED_CELLS": "1", "RB_SLICED_SUBRANGE_LOG2": "6",
+SMALL_SLICES = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICED_CELLS": "1", "RB_SLICED_STAGE": "1", "RB_SLICED_SUBRANGE_LOG2": "6",
                 "RB_SLICE_PAIR_LOG2": "13", "RB_SLICE_REGION_TARGET": "128"}
 
 
@@ -344,13 +344,16 @@ def test_paired_slices_match_oracle(ctx, orc, stranded, k, hd, hc, dbg_bits, cbf
     g.destroy(), og.close()
 
 
+DUP_FILTER_LOG2 = 30   # the host emulation of the kernels (tests/test_emu_parity.py) runs this test on smaller filters
+
+
 def test_duplicates_inside_one_batch_are_linearised(ctx, orc):
     """P4(i): m copies of a read in ONE call -> every k-mer ends with exactly m-1 increments (count m)."""
     rng = np.random.default_rng(17)
     base_reads = rand_reads(rng, 20, 150, 150)
     for m in (2, 5, 16):
         seqs = base_reads * m
-        g, og = make_graphs(ctx, orc, 1 << 30, 1 << 30, 64, 3, 3, 1, 25, False, False)
+        g, og = make_graphs(ctx, orc, 1 << DUP_FILTER_LOG2, 1 << DUP_FILTER_LOG2, 64, 3, 3, 1, 25, False, False)
         for s in seqs:
             og.add_read(s)
         g.addReads(rb.pack_reads(seqs))
@@ -362,10 +365,10 @@ def test_duplicates_inside_one_batch_are_linearised(ctx, orc):
     keys = rng.integers(-2 ** 63, 2 ** 63 - 1, size=50, dtype=np.int64)
     many = np.repeat(keys, 12)
     rng.shuffle(many)
-    g = rb.BloomFilterDeBruijnGraph(ctx, 1 << 30, 1 << 28, 64, 3, 3, 1, 25, False, False)
+    g = rb.BloomFilterDeBruijnGraph(ctx, 1 << DUP_FILTER_LOG2, 1 << (DUP_FILTER_LOG2 - 2), 64, 3, 3, 1, 25, False, False)
     g.add(many)
     assert (g.getCount(keys) == 12.0).all()
-    bf = rb.BloomFilter(ctx, 1 << 30, 3, 25)
+    bf = rb.BloomFilter(ctx, 1 << DUP_FILTER_LOG2, 3, 25)
     found = bf.lookupThenAdd(many)
     assert int((~found).sum()) == len(keys)  # exactly one "absent" per distinct key
     assert bf.lookupThenAdd(many).all()

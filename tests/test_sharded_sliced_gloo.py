@@ -20,7 +20,7 @@ for p in (ROOT, HERE):
 
 K, HD, HC = 25, 3, 2
 DBG_BITS, CBF_BYTES = 3_000_017, 1_000_003
-SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICED_CELLS": "1", "RB_SLICED_SUBRANGE_LOG2": "6",
+SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICED_CELLS": "1", "RB_SLICED_STAGE": "1", "RB_SLICED_SUBRANGE_LOG2": "6",
              "RB_SLICED_CHUNK": "8192"}
 
 
