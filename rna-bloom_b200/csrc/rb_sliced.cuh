@@ -671,21 +671,26 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_probes(const SlArena aren
     int buf = 0;
     SlWork w_ahead;
     int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c);
-    if (c < total) {
+    if (staged && c < total) {
         w_ahead = sl_work_item(arena, pre, c);
-        if (staged) { sl_stage(sbuf, sl_region_records<uint32_t>(arena, w_ahead.b) + w_ahead.first, w_ahead.n * 4u); sl_cp_commit(); }
+        sl_stage(sbuf, sl_region_records<uint32_t>(arena, w_ahead.b) + w_ahead.first, w_ahead.n * 4u);
+        sl_cp_commit();
     }
-    while (c < total) {
-        const SlWork w = w_ahead;
-        c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c);   // its barrier: everybody is done with the buffer the next copy overwrites
-        if (c < total) {
-            w_ahead = sl_work_item(arena, pre, c);
-            if (staged) { sl_stage(sbuf + (buf ^ 1) * arena.chunk, sl_region_records<uint32_t>(arena, w_ahead.b) + w_ahead.first, w_ahead.n * 4u); sl_cp_commit(); }
-        }
+    // not staged: claim an item, apply it, claim the next (a CTA that claimed ahead would double the window of records in flight and with
+    // it the slices that have to stay in L2: measured, 8.5 -> 9.8 ms look-up on local records); staged: the body claims the next item itself
+    for (; c < total; c = staged ? c : sl_next_chunk(chunk_prefix + arena.B + 1, &s_c)) {
+        SlWork w;
         if (staged) {
-            if (c < total) sl_cp_wait<1>(); else sl_cp_wait<0>();   // this item's copy has landed (the next one's may still fly)
+            w = w_ahead;
+            c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c);   // its barrier: everybody is done with the buffer the next copy overwrites
+            if (c < total) {
+                w_ahead = sl_work_item(arena, pre, c);
+                sl_stage(sbuf + (buf ^ 1) * arena.chunk, sl_region_records<uint32_t>(arena, w_ahead.b) + w_ahead.first, w_ahead.n * 4u);
+                sl_cp_commit();
+                sl_cp_wait<1>();   // this item's copy has landed (the next one's may still fly)
+            } else sl_cp_wait<0>();
             __syncthreads();
-        }
+        } else w = sl_work_item(arena, pre, c);
         const uint32_t* cur = sbuf + buf * arena.chunk;
         buf ^= 1;
         const int lr = w.b / sg.region_div;   // local region: dbgbf slices first, then cbf slices -- or paired slices
@@ -1088,29 +1093,26 @@ __global__ void __launch_bounds__(kSlThreads) ks_apply_raises(const SlArena aren
     int buf = 0;
     SlWork w_ahead;
     int c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c);
-    if (c < total) {
+    if (staged && c < total) {
         w_ahead = sl_work_item(arena, pre, c);
-        if (staged) {
-            sl_stage(sbuf, sl_region_records<uint32_t>(arena, w_ahead.b) + w_ahead.first, w_ahead.n * 4u);
-            sl_stage(vbuf, (arena.peer_ans ? arena.peer_ans[w_ahead.b % arena.n_peers] : raise) + w_ahead.first, w_ahead.n);
-            sl_cp_commit();
-        }
+        sl_stage(sbuf, sl_region_records<uint32_t>(arena, w_ahead.b) + w_ahead.first, w_ahead.n * 4u);
+        sl_stage(vbuf, (arena.peer_ans ? arena.peer_ans[w_ahead.b % arena.n_peers] : raise) + w_ahead.first, w_ahead.n);
+        sl_cp_commit();
     }
-    while (c < total) {
-        const SlWork w = w_ahead;
-        c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c);   // its barrier: everybody is done with the buffers the next copy overwrites
-        if (c < total) {
-            w_ahead = sl_work_item(arena, pre, c);
-            if (staged) {
+    for (; c < total; c = staged ? c : sl_next_chunk(chunk_prefix + arena.B + 1, &s_c)) {   // as in ks_apply_probes
+        SlWork w;
+        if (staged) {
+            w = w_ahead;
+            c = sl_next_chunk(chunk_prefix + arena.B + 1, &s_c);   // its barrier: everybody is done with the buffers the next copy overwrites
+            if (c < total) {
+                w_ahead = sl_work_item(arena, pre, c);
                 sl_stage(sbuf + (buf ^ 1) * arena.chunk, sl_region_records<uint32_t>(arena, w_ahead.b) + w_ahead.first, w_ahead.n * 4u);
                 sl_stage(vbuf + (buf ^ 1) * arena.chunk, (arena.peer_ans ? arena.peer_ans[w_ahead.b % arena.n_peers] : raise) + w_ahead.first, w_ahead.n);
                 sl_cp_commit();
-            }
-        }
-        if (staged) {
-            if (c < total) sl_cp_wait<1>(); else sl_cp_wait<0>();
+                sl_cp_wait<1>();
+            } else sl_cp_wait<0>();
             __syncthreads();
-        }
+        } else w = sl_work_item(arena, pre, c);
         const uint32_t* cur_r = sbuf + buf * arena.chunk;
         const uint8_t* cur_v = vbuf + buf * arena.chunk;
         buf ^= 1;
