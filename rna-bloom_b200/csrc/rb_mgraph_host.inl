@@ -583,16 +583,8 @@ static int32_t mg_apply(rb_mgraph* mg, bool set_bits) {
         if (rc) return rc;
         fd = fc = mg->dbg->cs->cells;
     }
-    const size_t sm_pre = sl_apply_smem(a, false);
-    int grid = 0;
-    if (set_bits) {
-        rc = sl_persistent_grid(ctx, ks_apply_probes<1>, sm_pre, &grid); if (rc) return rc;
-        SL_LAUNCH("ks_apply_probes<1>", ks_apply_probes<1>, grid, sm_pre, a, mg->chunk_prefix, mg->sg_apply, fd, fc, mg->ans, (const int*)mg->flags);
-    } else {
-        rc = sl_persistent_grid(ctx, ks_apply_probes<0>, sm_pre, &grid); if (rc) return rc;
-        SL_LAUNCH("ks_apply_probes<0>", ks_apply_probes<0>, grid, sm_pre, a, mg->chunk_prefix, mg->sg_apply, fd, fc, mg->ans, (const int*)mg->flags);
-    }
-    return RB_OK;
+    return set_bits ? sl_launch_apply<1>(ctx, a, mg->chunk_prefix, mg->sg_apply, fd, fc, mg->ans, (const int*)mg->flags)
+                    : sl_launch_apply<0>(ctx, a, mg->chunk_prefix, mg->sg_apply, fd, fc, mg->ans, (const int*)mg->flags);
 }
 // home side: keys of this rank's hash ranges from every rank -> distinct keys with multiplicities -> their probes (send32 / cnt_s)
 static int32_t mg_dedup_emit(rb_mgraph* mg, bool with_cbf) {
@@ -663,18 +655,13 @@ static int32_t mg_raises(rb_mgraph* mg, int policy, uint64_t seed) {
                      mg->paired ? 1 << mg->sg_apply.pair_sub_log2 : 1);
     if (rc) return rc;
     if (mg->p2p) a.peer_ans = (uint8_t* const*)mg->d_peer_ans;
-    const size_t sm_pre = sl_apply_smem(a, true);
-    int grid = 0;
-    rc = sl_persistent_grid(ctx, ks_apply_raises, sm_pre, &grid);
-    if (rc) return rc;
     uint32_t* fc = mg->cbf->dev;
     if (mg->sg_apply.cells) {   // still in cells: nothing but mg_apply ran since
         rc = cells_ensure_cells(ctx, mg->dbg->cs);
         if (rc) return rc;
         fc = mg->dbg->cs->cells;
     }
-    SL_LAUNCH("ks_apply_raises", ks_apply_raises, grid, sm_pre, a, mg->chunk_prefix, mg->sg_apply, fc, (const uint8_t*)mg->ans, (const int*)mg->flags);
-    return RB_OK;
+    return sl_launch_raises(ctx, a, mg->chunk_prefix, mg->sg_apply, fc, (const uint8_t*)mg->ans, (const int*)mg->flags);
 }
 static int32_t mg_read_flags(rb_mgraph* mg, int* f2) {   // the one host synchronisation of a round
     rb_ctx* ctx = mg->ctx;

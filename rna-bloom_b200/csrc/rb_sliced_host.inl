@@ -309,6 +309,30 @@ static void sl_apply_stage(SlArena* a) {
     a->stage = (a->peer_data != nullptr || env_int("RB_SLICED_STAGE", 0, 0, 1)) && a->chunk <= kSlStageRecords ? 1 : 0;
 }
 
+// the apply kernels, with or without cp.async staging of the work items (SlArena::stage)
+template <int SET>
+static int32_t sl_launch_apply(rb_ctx* ctx, const SlArena& a, int* chunk_prefix, const SlGeom& sg, uint32_t* dbg, const uint32_t* cbf, uint8_t* ans, const int* abort) {
+    const size_t sm = sl_apply_smem(a, false);
+    const char* name = SET ? "ks_apply_probes<1>" : "ks_apply_probes<0>";
+    int grid = 0;
+    int32_t rc;
+    auto ks = ks_apply_probes<SET, true>;
+    auto kd = ks_apply_probes<SET, false>;
+    if (a.stage) { rc = sl_persistent_grid(ctx, ks, sm, &grid); if (rc) return rc; SL_LAUNCH(name, ks, grid, sm, a, chunk_prefix, sg, dbg, cbf, ans, abort); }
+    else { rc = sl_persistent_grid(ctx, kd, sm, &grid); if (rc) return rc; SL_LAUNCH(name, kd, grid, sm, a, chunk_prefix, sg, dbg, cbf, ans, abort); }
+    return RB_OK;
+}
+static int32_t sl_launch_raises(rb_ctx* ctx, const SlArena& a, int* chunk_prefix, const SlGeom& sg, uint32_t* cbf, const uint8_t* raise, const int* abort) {
+    const size_t sm = sl_apply_smem(a, true);
+    int grid = 0;
+    int32_t rc;
+    auto ks = ks_apply_raises<true>;
+    auto kd = ks_apply_raises<false>;
+    if (a.stage) { rc = sl_persistent_grid(ctx, ks, sm, &grid); if (rc) return rc; SL_LAUNCH("ks_apply_raises", ks, grid, sm, a, chunk_prefix, sg, cbf, raise, abort); }
+    else { rc = sl_persistent_grid(ctx, kd, sm, &grid); if (rc) return rc; SL_LAUNCH("ks_apply_raises", kd, grid, sm, a, chunk_prefix, sg, cbf, raise, abort); }
+    return RB_OK;
+}
+
 // S1..S3
 template <int NJ>
 static int32_t sliced_count_round_t(rb_graph* g, SlicedEngine* e, const Ingest& ing, int mode, float* counts, int64_t* fh, int64_t* rh, bool* fell_back) {
@@ -344,11 +368,8 @@ static int32_t sliced_count_round_t(rb_graph* g, SlicedEngine* e, const Ingest& 
     SlLayout lay;
     rc = sl_round_layout(g, e, ing.n_pos, &lay);
     if (rc) return rc;
-    const size_t sm_pre = sl_apply_smem(probes, false);
-    int grid = 0;
-    rc = sl_persistent_grid(ctx, ks_apply_probes<0>, sm_pre, &grid);
+    rc = sl_launch_apply<0>(ctx, probes, e->chunk_prefix, lay.sg, lay.dbg, lay.cbf, e->ans, nullptr);
     if (rc) return rc;
-    SL_LAUNCH("ks_apply_probes<0>", ks_apply_probes<0>, grid, sm_pre, probes, e->chunk_prefix, lay.sg, lay.dbg, lay.cbf, e->ans, (const int*)nullptr);
     // same CTA -> k-mer mapping as the route kernel
     const size_t sm_ans = TileAnswers::smem_bytes(probes.B, TILE * NJ);
     auto k1 = ks_combine_lookup<1, NJ>;
@@ -456,14 +477,9 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
     SlLayout lay;
     rc = sl_round_layout(g, e, ing.n_pos, &lay);
     if (rc) return rc;
-    const size_t sm_pre = sl_apply_smem(probes, false);
-    if (policy != POLICY_COUNT_IF_PRESENT) {
-        rc = sl_persistent_grid(ctx, ks_apply_probes<1>, sm_pre, &grid); if (rc) return rc;
-        SL_LAUNCH("ks_apply_probes<1>", ks_apply_probes<1>, grid, sm_pre, probes, e->chunk_prefix, lay.sg, lay.dbg, lay.cbf, e->ans, (const int*)nullptr);
-    } else {
-        rc = sl_persistent_grid(ctx, ks_apply_probes<0>, sm_pre, &grid); if (rc) return rc;
-        SL_LAUNCH("ks_apply_probes<0>", ks_apply_probes<0>, grid, sm_pre, probes, e->chunk_prefix, lay.sg, lay.dbg, lay.cbf, e->ans, (const int*)nullptr);
-    }
+    rc = policy != POLICY_COUNT_IF_PRESENT ? sl_launch_apply<1>(ctx, probes, e->chunk_prefix, lay.sg, lay.dbg, lay.cbf, e->ans, nullptr)
+                                            : sl_launch_apply<0>(ctx, probes, e->chunk_prefix, lay.sg, lay.dbg, lay.cbf, e->ans, nullptr);
+    if (rc) return rc;
     if (with_cbf) {
         // I6: the new counter values go back over the answer bytes of the probe records; I7: a second sweep over the same regions applies
         // them.  Nothing is sorted and nothing can overflow here: once the probes are routed the round always completes.
@@ -475,10 +491,8 @@ static int32_t sliced_insert_round(rb_graph* g, const Ingest& ing, int mode, int
                        policy, seed, (const int*)nullptr);
         rc = sl_chunk_prefix(ctx, e, probes);   // the same work list again (the consumers' counter starts from 0)
         if (rc) return rc;
-        const size_t sm_raise = sl_apply_smem(probes, true);
-        rc = sl_persistent_grid(ctx, ks_apply_raises, sm_raise, &grid);
+        rc = sl_launch_raises(ctx, probes, e->chunk_prefix, lay.sg, lay.cbf, (const uint8_t*)e->ans, nullptr);
         if (rc) return rc;
-        SL_LAUNCH("ks_apply_raises", ks_apply_raises, grid, sm_raise, probes, e->chunk_prefix, lay.sg, lay.cbf, (const uint8_t*)e->ans, (const int*)nullptr);
     }
     claim_invalidate(ctx);   // bits were set without going through the claim table
     return RB_OK;
