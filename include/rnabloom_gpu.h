@@ -275,6 +275,20 @@ enum { RB_SEQ_ADD = 0, RB_SEQ_CONTAINS_ALL = 1, RB_SEQ_LOOKUP_AND_ADD_ALL = 2 };
 RB_API int32_t rb_filter_seq_op(rb_filter* f, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
                                 int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, int32_t mode, int32_t op, uint8_t* all_found);
 
+/* The other two consumers of SURVEY 8f rank 4, as the batched primitives their loops are made of:
+ *  - MinimizerHashIterator.next() for every window of w consecutive k-mers of every read (bloom/hash/MinimizerHashIterator.java:42-101,
+ *    util/LongRollingWindow.java:43-73: the signed minimum of hVals[0]) -- the key generator of SeqSubsampler.minimizerBased
+ *    (util/SeqSubsampler.java:50-117), whose keys then go through rb_cbf_increment_and_get_hashes sequence by sequence.  max(0, len - k - w + 2)
+ *    values per read (offsets: rb_kmer_offsets with k + w - 1); w <= 64.
+ *  - graph.lookupReadKmerPair / lookupFragmentKmerPair (:526-532) for every pair position of every read: the test inside
+ *    breakWithReadPairedKmers / breakWithFragPairedKmers (util/GraphUtils.java:4184-4310).  One byte per pair position (rb_kmer_offsets
+ *    with k + d); 0 where the span covers an unusable base. */
+RB_API int32_t rb_minimizers(rb_ctx* ctx, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
+                             int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, int32_t k, int32_t w, int32_t mode, int64_t* minimizers);
+RB_API int32_t rb_graph_lookup_pairs_reads(rb_graph* g, int32_t which, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off,
+                                           const int32_t* read_len, int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, uint32_t flags,
+                                           uint8_t* found);
+
 /* ---- f3: k-mer multiplicity histogram by hash sampling -----------------------------------------------------------
  * The reference sizes its filters from the histogram of the external `ntcard` binary (RNABloom.java:5745-5768, 6939-7010; parsed by
  * util/NTCardHistogram.java:33-63: F1 = k-mers, F0 = distinct k-mers, f_m = distinct k-mers of multiplicity m).  Here: a k-mer is sampled

@@ -151,6 +151,8 @@ def bind(path, allow_missing=False):
         "rb_graph_count_reads_async": (i32, [vp] + reads + [vp, vp, vp, C.POINTER(i64), C.POINTER(i64)]),
         "rb_ctx_wait": (i32, [vp, i64]),
         "rb_filter_seq_op": (i32, [vp] + reads + [i32, i32, vp]),
+        "rb_minimizers": (i32, [vp] + reads + [i32, i32, i32, vp]),
+        "rb_graph_lookup_pairs_reads": (i32, [vp, i32] + reads + [u32, vp]),
         "rb_card_create": (i32, [vp, i32, i32, i32, i64, C.POINTER(vp)]),
         "rb_card_destroy": (i32, [vp]),
         "rb_card_add_reads": (i32, [vp] + reads + [C.POINTER(i64)]),

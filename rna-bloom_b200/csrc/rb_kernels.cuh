@@ -314,7 +314,9 @@ __global__ void __launch_bounds__(kThreads) k_kmerize(const Ingest g, int k, int
 
 // ---- paired k-mers: Paired*NTHashIterator (bloom/hash/PairedNTHashIterator.java:55-85, Canonical...:39-60, RC...:35-56)
 // positions are pair positions (len-k-d+1 per read).  PAIR_OP: 0 = write hValsP[0]; 1 = pkbf.add (graph :455-461);
-// 2 = pkbf.add only when both k-mers are in dbgbf (RNABloom.java:389-399)
+// 2 = pkbf.add only when both k-mers are in dbgbf (RNABloom.java:389-399); 3 = pkbf.lookup (graph.lookupReadKmerPair / lookupFragmentKmerPair
+// :526-532, the test inside breakWith{Read,Frag}PairedKmers, util/GraphUtils.java:4184-4310): one byte per pair position, written through
+// pair_out seen as a byte array
 __device__ __forceinline__ int count_masked(const uint32_t* mask, int64_t start, int n) {
     if (!mask) return 0;
     int c = 0;
@@ -365,6 +367,7 @@ __global__ void __launch_bounds__(kThreads) k_pairs(const Ingest g, const GraphD
             p = ((int64_t)p2 < (int64_t)p1) ? p2 : p1;  // Math.min on long
         }
         if (PAIR_OP == 0) pair_out[g.out_base + pos + i] = (int64_t)p;
+        else if (PAIR_OP == 3) reinterpret_cast<uint8_t*>(pair_out)[g.out_base + pos + i] = (span_bad == 0 && bf_lookup<MAXH>(pk, p, gd.hm)) ? 1 : 0;
         else if (span_bad == 0) {
             bool go = true;
             if (PAIR_OP == 2) go = bf_lookup<MAXH>(gd.dbg, L.base(), gd.hm) && bf_lookup<MAXH>(gd.dbg, R.base(), gd.hm);
@@ -402,6 +405,44 @@ __global__ void __launch_bounds__(kThreads) k_seq_filter(const Ingest g, int k, 
             }
         }
         if (SEQ_OP != SEQ_ADD && !found) missing[g.read_base + pw.read] = 1;
+    }
+}
+
+// ---- minimizers: MinimizerHashIterator.next() for every window of w consecutive k-mers (bloom/hash/MinimizerHashIterator.java:42-101 over
+// util/LongRollingWindow.java:43-73: the signed minimum of hVals[0] over the window) -- the key generator of SeqSubsampler.minimizerBased
+// (util/SeqSubsampler.java:50-117).  Positions are window positions (len - k - w + 2 per read); a thread walks kChunk consecutive windows
+// with a ring of the last w hashes.  w <= kMaxMinimizerWindow.
+constexpr int kMaxMinimizerWindow = 64;
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) k_minimizers(const Ingest g, int k, int w, int64_t* __restrict__ out) {
+    __shared__ RollLut lut;
+    build_lut(&lut, k);
+    const int64_t pos = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * kChunk;
+    if (pos >= g.n_pos) return;
+    const int n = (int)min((int64_t)kChunk, g.n_pos - pos);
+    int64_t read; int32_t in_read;
+    locate(g, pos, read, in_read);
+    int32_t npos = read_npos(g, read);
+    KmerWalker<MODE> wk;
+    int64_t ring[kMaxMinimizerWindow];
+    int head = 0;   // ring[head] is the oldest hash of the window
+    bool primed = false;
+    for (int i = 0; i < n; ++i) {
+        if (!primed || in_read >= npos) {
+            if (primed) { do { ++read; npos = read_npos(g, read); } while (npos <= 0); in_read = 0; }
+            wk.init(g, read_start(g, read) + in_read, k, lut);
+            for (int j = 0; j < w; ++j) { if (j) wk.roll(lut); ring[j] = (int64_t)wk.base(); }
+            head = 0;
+            primed = true;
+        } else {
+            wk.roll(lut);
+            ring[head] = (int64_t)wk.base();
+            head = head + 1 == w ? 0 : head + 1;
+        }
+        int64_t mn = ring[0];
+        for (int j = 1; j < w; ++j) mn = ring[j] < mn ? ring[j] : mn;
+        out[g.out_base + pos + i] = mn;
+        ++in_read;
     }
 }
 

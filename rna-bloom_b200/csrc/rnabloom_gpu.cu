@@ -972,6 +972,36 @@ extern "C" int32_t rb_kmerize_pairs(rb_ctx* ctx, const uint64_t* packed, const u
     return for_each_launch(ctx, ra, k + d, kmerize_launch, &u, nullptr);
 }
 
+// MinimizerHashIterator.next() for every window of w k-mers of every read (bloom/hash/MinimizerHashIterator.java:42-101): out has
+// max(0, len - k - w + 2) values per read, in read order (rb_kmer_offsets with k + w - 1)
+struct MinimizerUser { int k, w, mode; int64_t* out; };
+static int32_t minimizer_launch(rb_ctx* ctx, const Ingest& ing, void* user) {
+    MinimizerUser* u = (MinimizerUser*)user;
+    const int grid = (int)div_up(div_up(ing.n_pos, kChunk), kThreads);
+    Ingest g = ing;
+    const int64_t out0 = ing.out_base;
+    g.out_base = 0;
+    void* p;
+    const int32_t rc = stage_get(ctx, 5, ing.n_pos * 8, &p);
+    if (rc) return rc;
+    PROF("k_minimizers");
+    if (u->mode == RB_MODE_FWD) RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_minimizers<0>)(g, u->k, u->w, (int64_t*)p);
+    else if (u->mode == RB_MODE_RC) RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_minimizers<1>)(g, u->k, u->w, (int64_t*)p);
+    else RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_minimizers<2>)(g, u->k, u->w, (int64_t*)p);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(u->out + out0, p, (size_t)ing.n_pos * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RB_OK;
+}
+extern "C" int32_t rb_minimizers(rb_ctx* ctx, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off, const int32_t* read_len,
+                                 int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, int32_t k, int32_t w, int32_t mode, int64_t* minimizers) {
+    if (!ctx || k < 1 || w < 1 || w > kMaxMinimizerWindow || mode < 0 || mode > 2 || !minimizers) return RB_EINVAL;
+    LOCK(ctx);
+    ReadsArg ra{packed, mask, read_off, read_len, n_reads, uniform_len, uniform_stride, false};
+    MinimizerUser u{k, w, mode, minimizers};
+    return for_each_launch(ctx, ra, k + w - 1, minimizer_launch, &u, nullptr);
+}
+
 // ---- graph ---------------------------------------------------------------------------------------------------------------
 // ---- f4: the screening Bloom filter over whole sequences (RNABloom.java:1680,2530-2536,4264; util/GraphUtils.java:627-650) ----------------
 struct SeqUser { rb_filter* f; int mode, op; uint8_t* missing; };
@@ -1293,6 +1323,49 @@ static int32_t pairs_launch(rb_ctx* ctx, const Ingest& ing, void* user) {
     else launch_pairs_mode<8>(u->mode, u->op, grid, ctx->stream, ing, gd, pk, u->d);
     LAUNCH_CHECK();
     return RB_OK;
+}
+// graph.lookupReadKmerPair / lookupFragmentKmerPair (:526-532) for every pair position of every read: the test inside
+// breakWith{Read,Frag}PairedKmers (util/GraphUtils.java:4184-4310).  found has max(0, len - k - d + 1) bytes per read (rb_kmer_offsets with k + d).
+struct PairLookupUser { rb_graph* g; rb_filter* pk; int mode, d; uint8_t* found; };
+static int32_t pair_lookup_launch(rb_ctx* ctx, const Ingest& ing, void* user) {
+    PairLookupUser* u = (PairLookupUser*)user;
+    const GraphDev gd = graph_view(u->g, false);
+    const BitFilter pk = bit_view(u->pk);
+    const int grid = (int)div_up(div_up(ing.n_pos, kChunk), kThreads);
+    Ingest g = ing;
+    const int64_t out0 = ing.out_base;
+    g.out_base = 0;
+    void* p;
+    const int32_t rc = stage_get(ctx, 26, ing.n_pos, &p);
+    if (rc) return rc;
+    PROF("k_pairs");
+    if (u->pk->num_hash <= 3) {
+        if (u->mode == RB_MODE_FWD) RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_pairs<0, 3, 3>)(g, gd, pk, u->d, (int64_t*)p);
+        else if (u->mode == RB_MODE_RC) RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_pairs<1, 3, 3>)(g, gd, pk, u->d, (int64_t*)p);
+        else RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_pairs<2, 3, 3>)(g, gd, pk, u->d, (int64_t*)p);
+    } else {
+        if (u->mode == RB_MODE_FWD) RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_pairs<0, 8, 3>)(g, gd, pk, u->d, (int64_t*)p);
+        else if (u->mode == RB_MODE_RC) RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_pairs<1, 8, 3>)(g, gd, pk, u->d, (int64_t*)p);
+        else RB_LAUNCH(grid, kThreads, 0, ctx->stream, k_pairs<2, 8, 3>)(g, gd, pk, u->d, (int64_t*)p);
+    }
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(u->found + out0, p, (size_t)ing.n_pos, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RB_OK;
+}
+static int graph_mode(const rb_graph* g, uint32_t flags);
+extern "C" int32_t rb_graph_lookup_pairs_reads(rb_graph* g, int32_t which, const uint64_t* packed, const uint32_t* mask, const int64_t* read_off,
+                                               const int32_t* read_len, int64_t n_reads, int32_t uniform_len, int64_t uniform_stride, uint32_t flags,
+                                               uint8_t* found) {
+    if (!g || !found || (which != RB_RPKBF && which != RB_FPKBF)) return RB_EINVAL;
+    rb_ctx* ctx = g->ctx;
+    LOCK(ctx);
+    rb_filter* pk = which == RB_RPKBF ? g->rpk : g->fpk;
+    const int d = which == RB_RPKBF ? g->d_read : g->d_frag;
+    if (!pk || d < 1) return fail(ctx, RB_ESTATE, "pair look-up needs the pair filter and its distance");
+    PairLookupUser u{g, pk, graph_mode(g, flags), d, found};
+    ReadsArg ra{packed, mask, read_off, read_len, n_reads, uniform_len, uniform_stride, false};
+    return for_each_launch(ctx, ra, g->k + d, pair_lookup_launch, &u, nullptr);
 }
 static int graph_mode(const rb_graph* g, uint32_t flags) {  // CanonicalHashFunction.java:179-206 ignores reverse-complement
     if (!g->stranded) return RB_MODE_CANON;

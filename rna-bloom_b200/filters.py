@@ -126,6 +126,12 @@ class Context:
         self.check(self.L.rb_kmerize_ascii(self.h, _ptr(bases), _ptr(off), n_reads, k, mode, _ptr(f), _ptr(r), _ptr(b)))
         return f, r, b
 
+    def minimizers(self, reads, k, w, mode):
+        """MinimizerHashIterator.next() for every window of w consecutive k-mers of every read (bloom/hash/MinimizerHashIterator.java:42-101)."""
+        out = np.zeros(reads.n_positions(k + w - 1), dtype=np.int64)
+        self.check(self.L.rb_minimizers(self.h, *reads.args(), k, w, mode, _ptr(out)))
+        return out
+
     def kmerize_pairs(self, reads, k, d, mode):
         p = np.zeros(reads.n_positions(k + d), dtype=np.int64)
         self.check(self.L.rb_kmerize_pairs(self.h, *reads.args(), k, d, mode, _ptr(p)))
@@ -520,6 +526,13 @@ class BloomFilterDeBruijnGraph:
 
     def setPairedKmerDistances(self, readPairedKmersDistance, fragmentPairedKmersDistance=-1):
         self.ctx.check(self.ctx.L.rb_graph_set_distances(self.h, readPairedKmersDistance, fragmentPairedKmersDistance))
+        self._d_read, self._d_frag = readPairedKmersDistance, fragmentPairedKmersDistance
+
+    def _pair_distance(self, which):
+        d = getattr(self, "_d_read" if which == B.RB_RPKBF else "_d_frag", -1)
+        if d < 1:
+            raise ValueError("set the paired k-mer distance first (setPairedKmerDistances)")
+        return d
 
     def syncToHost(self, dbgbf=None, cbf=None, rpkbf=None, fpkbf=None):
         """Barrier + refresh of host mirrors (numpy uint8 arrays of the filters' byte lengths; None skips a filter): the host side of
@@ -694,6 +707,14 @@ class BloomFilterDeBruijnGraph:
         a = _hashes(pairHashVals)
         out = np.zeros(a.size, dtype=np.uint8)
         self.ctx.check(self.ctx.L.rb_graph_lookup_pair_hashes(self.h, B.RB_RPKBF, _ptr(a), a.size, _ptr(out)))
+        return out.astype(bool)
+
+    def lookupKmerPairsOfReads(self, reads, which=B.RB_RPKBF, flags=0):
+        """lookupReadKmerPair / lookupFragmentKmerPair (graph :526-532) at every pair position of every read: the test inside
+        breakWith{Read,Frag}PairedKmers (util/GraphUtils.java:4184-4310).  Returns one bool per pair position."""
+        d = self._pair_distance(which)
+        out = np.zeros(reads.n_positions(self.k + d), dtype=np.uint8)
+        self.ctx.check(self.ctx.L.rb_graph_lookup_pairs_reads(self.h, which, *reads.args(), flags, _ptr(out)))
         return out.astype(bool)
 
     def lookupFragmentKmerPair(self, pairHashVals):

@@ -714,6 +714,51 @@ def test_kmer_histogram_by_hash_sampling(ctx, orc, stranded, k, sample_bits, tmp
     tiny.destroy(), h.destroy()
 
 
+@pytest.mark.parametrize("mode,k,w", [(MODE_CANON, 25, 10), (0, 17, 1), (MODE_CANON, 31, 50)])
+def test_minimizers_match_the_rolling_window(ctx, orc, mode, k, w):
+    """f4: MinimizerHashIterator.next() (bloom/hash/MinimizerHashIterator.java:42-101; util/LongRollingWindow.java:43-73) = the signed minimum of
+    hVals[0] over every window of w consecutive k-mers, and the distinct-minimizer walk SeqSubsampler.minimizerBased makes of it (:70-100)."""
+    rng = np.random.default_rng(77 + w)
+    seqs = rand_reads(rng, 60, 1, 700) + ["ACGT" * 40, "A" * 90]
+    got = ctx.minimizers(rb.pack_reads(seqs), k, w, mode)
+    off = 0
+    for s_ in seqs:
+        _, _, base = orc.kmer_hashes(s_, k, mode)
+        n_win = max(0, len(base) - w + 1)
+        want = np.array([base[i:i + w].min() for i in range(n_win)], dtype=np.int64)   # int64: the signed comparison of LongRollingWindow
+        assert (got[off:off + n_win] == want).all()
+        off += n_win
+    assert off == got.size
+
+
+@pytest.mark.parametrize("stranded,k,d", [(False, 25, 30), (True, 21, 7)])
+def test_pair_lookups_at_every_position(ctx, orc, stranded, k, d):
+    """f4: graph.lookupReadKmerPair at every pair position of a sequence (graph :526-532), the test inside breakWithReadPairedKmers
+    (util/GraphUtils.java:4184-4246), against the oracle's pair filter."""
+    rng = np.random.default_rng(5 + k)
+    genome = "".join(rng.choice(list("ACGT"), size=5000))
+    seqs = [genome[p0:p0 + 150] for p0 in rng.integers(0, 4850, size=120)]
+    g, og = make_graphs(ctx, orc, (1 << 26) + 1, (1 << 24) + 3, (1 << 25) + 7, 3, 3, 2, k, stranded, True)
+    g.setPairedKmerDistances(d, -1)
+    og.set_distances(d, -1)
+    for s_ in seqs[:80]:
+        og.add_read(s_, flags=F_STORE_READ_PAIRS)
+    g.addReads(rb.pack_reads(seqs[:80]), flags=rb.STORE_READ_PAIRS)
+    assert (g.getRpkbf().download() == og.rpkbf()).all()
+    queries = seqs[60:] + [seqs[3][:k + d - 1], seqs[4][:70] + "N" + seqs[4][71:]]
+    got = g.lookupKmerPairsOfReads(rb.pack_reads(queries))
+    rp = orc.lib.orc_graph_rpkbf(og.g)
+    off = 0
+    for s_ in queries:
+        _, _, ph = orc.pair_hashes(s_, k, d, 0 if stranded else MODE_CANON)
+        for i, p in enumerate(ph):
+            want = ("N" not in s_[i:i + k + d]) and bool(orc.lib.orc_bf_lookup1(rp, int(p)))
+            assert bool(got[off + i]) == want
+        off += len(ph)
+    assert off == got.size
+    g.destroy(), og.close()
+
+
 def test_getkmers_with_invalid_nucleotides(ctx, orc):
     rng = np.random.default_rng(37)
     seqs = rand_reads(rng, 120, 10, 300, n_rate=0.01)
