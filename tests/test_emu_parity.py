@@ -130,9 +130,13 @@ test_neighbor_counts_match_oracle = G.test_neighbor_counts_match_oracle
 
 # paired probe records (cbf_bytes a power of two dividing dbg_bits): q = 8, q = 5 (stranded), h_d > h_c, and the h_d < h_c case that must
 # stay unpaired; both read layouts
-@pytest.mark.parametrize("layout", ["ragged", "uniform"])
-@pytest.mark.parametrize("stranded,k,hd,hc,dbg_bits,cbf_bytes", [(False, 25, 3, 3, 1 << 27, 1 << 24), (True, 25, 3, 3, 5 << 24, 1 << 24),
-                                                                 (False, 31, 3, 2, 1 << 25, 1 << 25), (False, 25, 2, 3, 1 << 27, 1 << 24)])
+PAIRED_CASES = [(False, 25, 3, 3, 1 << 27, 1 << 24, "ragged"), (False, 25, 3, 3, 1 << 27, 1 << 24, "uniform"), (True, 25, 3, 3, 5 << 24, 1 << 24, "uniform"),
+                (False, 31, 3, 2, 1 << 25, 1 << 25, "ragged"), (False, 25, 2, 3, 1 << 27, 1 << 24, "uniform")]
+if FULL:
+    PAIRED_CASES += [(True, 25, 3, 3, 5 << 24, 1 << 24, "ragged"), (False, 31, 3, 2, 1 << 25, 1 << 25, "uniform"), (False, 25, 2, 3, 1 << 27, 1 << 24, "ragged")]
+
+
+@pytest.mark.parametrize("stranded,k,hd,hc,dbg_bits,cbf_bytes,layout", PAIRED_CASES)
 def test_paired_slices_match_oracle(ctx, orc, stranded, k, hd, hc, dbg_bits, cbf_bytes, layout):
     G.test_paired_slices_match_oracle(ctx, orc, stranded, k, hd, hc, dbg_bits, cbf_bytes, layout)
 
@@ -160,7 +164,11 @@ def test_skewed_batch_is_redone_by_the_direct_engine(ctx, orc, monkeypatch):
 
 
 
-@pytest.mark.parametrize("stranded,k,hd,hc,n_reads", [(False, 25, 3, 3, 800), (True, 25, 3, 3, 120)])
+# RB_FULL_EMU=1 runs the whole matrix (about twice as long); the default keeps one case per distinct code path so that the CPU suite stays short
+FULL = os.environ.get("RB_FULL_EMU") == "1"
+
+
+@pytest.mark.parametrize("stranded,k,hd,hc,n_reads", [(False, 25, 3, 3, 800), (True, 25, 3, 3, 120)] if FULL else [(True, 25, 3, 3, 300)])
 def test_graph_add_collision_free_is_bit_exact(ctx, orc, stranded, k, hd, hc, n_reads):
     G.test_graph_add_collision_free_is_bit_exact(ctx, orc, stranded, k, hd, hc, n_reads)
 
