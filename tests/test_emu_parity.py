@@ -46,6 +46,10 @@ def ctx(emu_lib):
     c.close()
 
 
+# RB_FULL_EMU=1 runs the whole matrix (about twice as long); the default keeps one case per distinct code path so that the CPU suite stays short
+FULL = os.environ.get("RB_FULL_EMU") == "1"
+
+
 SLICE_ENV = {"RB_SLICE_BITS_LOG2": "17", "RB_SLICE_BYTES_LOG2": "15", "RB_SLICED_CELLS": "1", "RB_SLICED_STAGE": "1", "RB_SLICED_SUBRANGE_LOG2": "6",
              "RB_SLICE_PAIR_LOG2": "13"}
 # sliced-small: tiny slices / sub-ranges so that the small test filters span hundreds of regions (every test);
@@ -162,10 +166,6 @@ def test_skewed_batch_is_redone_by_the_direct_engine(ctx, orc, monkeypatch):
     G.test_skewed_batch_is_redone_by_the_direct_engine(ctx, orc)
 
 
-
-
-# RB_FULL_EMU=1 runs the whole matrix (about twice as long); the default keeps one case per distinct code path so that the CPU suite stays short
-FULL = os.environ.get("RB_FULL_EMU") == "1"
 
 
 @pytest.mark.parametrize("stranded,k,hd,hc,n_reads", [(False, 25, 3, 3, 800), (True, 25, 3, 3, 120)] if FULL else [(True, 25, 3, 3, 300)])
