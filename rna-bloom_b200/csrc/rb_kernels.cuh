@@ -801,17 +801,27 @@ __global__ void __launch_bounds__(kThreads) k_synth_long_reads(uint64_t seed, ui
 __global__ void __launch_bounds__(kThreads) k_pack_ascii(const char* __restrict__ bases, const char* __restrict__ quals,
                                                         const int64_t* __restrict__ ascii_off, const int64_t* __restrict__ word_off,
                                                         int64_t n_reads, int64_t n_words, int min_qual, uint64_t* __restrict__ packed,
-                                                        uint32_t* __restrict__ mask, uint32_t* __restrict__ rcm) {
+                                                        uint32_t* __restrict__ mask, uint32_t* __restrict__ rcm, int uniform_len, int64_t uniform_a0) {
     const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (t >= n_words) return;
-    int64_t lo = 0, hi = n_reads;  // read whose word range contains t
-    while (hi - lo > 1) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (__ldg(&word_off[mid]) <= t) lo = mid; else hi = mid;
+    int64_t a0;
+    int len, first;
+    if (uniform_len > 0) {   // records of one length: no offset tables (ascii_off / word_off are not read)
+        const int wpr = (uniform_len + 31) >> 5;
+        const int64_t r = t / wpr;
+        a0 = uniform_a0 + r * uniform_len;
+        len = uniform_len;
+        first = (int)(t - r * wpr) * 32;
+    } else {
+        int64_t lo = 0, hi = n_reads;  // read whose word range contains t
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(&word_off[mid]) <= t) lo = mid; else hi = mid;
+        }
+        a0 = __ldg(&ascii_off[lo]);
+        len = (int)(__ldg(&ascii_off[lo + 1]) - a0);
+        first = (int)(t - __ldg(&word_off[lo])) * 32;
     }
-    const int64_t a0 = __ldg(&ascii_off[lo]);
-    const int len = (int)(__ldg(&ascii_off[lo + 1]) - a0);
-    const int first = (int)(t - __ldg(&word_off[lo])) * 32;
     uint64_t w = 0;
     uint32_t m = 0, rm = 0;
     const int qlo = '!' + min_qual;

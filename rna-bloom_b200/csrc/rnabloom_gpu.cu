@@ -1420,45 +1420,52 @@ extern "C" int32_t rb_graph_add_reads_dev(rb_graph* g, const uint64_t* packed, c
 // ASCII records -> 2-bit codes + unusable-base mask + reverse-seed plane, on the device, in grow-only staging of the context (no
 // allocation per call).  The chunk of records a Java worker hands over (RNABloom.java:551-634) arrives here as three host arrays.
 static int32_t ascii_pack(rb_ctx* ctx, const char* bases, const char* quals, const int64_t* ascii_off, int64_t n_reads, int32_t min_qual, ReadsArg* out) {
-    // per-read word offsets (reads start on 32-base word boundaries) -- host pass over n_reads+1 integers only
-    std::vector<int64_t> word_off((size_t)n_reads + 1), read_off((size_t)n_reads);
-    std::vector<int32_t> read_len((size_t)n_reads);
-    int64_t words = 0;
-    bool same_len = true;   // untrimmed short reads: every record has the same length -> the uniform ingest layout (prefix k-merizer, no per-read tables)
-    for (int64_t r = 0; r < n_reads; ++r) {
-        const int64_t len = ascii_off[r + 1] - ascii_off[r];
-        if (len < 0 || len > INT32_MAX) return fail(ctx, RB_EINVAL, "ascii_off must be non-decreasing");
-        word_off[(size_t)r] = words; read_off[(size_t)r] = words * 32; read_len[(size_t)r] = (int32_t)len;
-        words += (len + 31) / 32;
-        same_len = same_len && len == ascii_off[1] - ascii_off[0];
-    }
+    // records of one length (untrimmed short reads) take the uniform ingest layout: prefix k-merizer, no per-read tables at all; otherwise
+    // per-read word offsets (reads start on 32-base word boundaries) -- a host pass over n_reads + 1 integers
     const int64_t len0 = ascii_off[1] - ascii_off[0];
-    const bool uniform = same_len && len0 > 0 && !getenv("RB_ASCII_RAGGED");
-    word_off[(size_t)n_reads] = words;
+    bool same_len = len0 > 0 && len0 <= INT32_MAX && !getenv("RB_ASCII_RAGGED");
+    for (int64_t r = 1; r < n_reads && same_len; ++r) same_len = ascii_off[r + 1] - ascii_off[r] == len0;
+    const bool uniform = same_len;
+    std::vector<int64_t> word_off, read_off;
+    std::vector<int32_t> read_len;
+    int64_t words = 0;
+    if (uniform) words = n_reads * ((len0 + 31) / 32);
+    else {
+        word_off.resize((size_t)n_reads + 1); read_off.resize((size_t)n_reads); read_len.resize((size_t)n_reads);
+        for (int64_t r = 0; r < n_reads; ++r) {
+            const int64_t len = ascii_off[r + 1] - ascii_off[r];
+            if (len < 0 || len > INT32_MAX) return fail(ctx, RB_EINVAL, "ascii_off must be non-decreasing");
+            word_off[(size_t)r] = words; read_off[(size_t)r] = words * 32; read_len[(size_t)r] = (int32_t)len;
+            words += (len + 31) / 32;
+        }
+        word_off[(size_t)n_reads] = words;
+    }
     const int64_t a_lo = ascii_off[0], a_hi = ascii_off[n_reads];
-    void *d_b, *d_q = nullptr, *d_ao, *d_wo, *d_ro = nullptr, *d_rl = nullptr, *d_packed, *d_mask, *d_rcm;
+    void *d_b, *d_q = nullptr, *d_ao = nullptr, *d_wo = nullptr, *d_ro = nullptr, *d_rl = nullptr, *d_packed, *d_mask, *d_rcm;
     int32_t rc;
     if ((rc = stage_get(ctx, 16, (a_hi - a_lo) + 16, &d_b))) return rc;
     if (quals && (rc = stage_get(ctx, 17, (a_hi - a_lo) + 16, &d_q))) return rc;
-    if ((rc = stage_get(ctx, 18, (n_reads + 1) * 8, &d_ao))) return rc;
-    if ((rc = stage_get(ctx, 19, (n_reads + 1) * 8, &d_wo))) return rc;
-    if (!uniform && (rc = stage_get(ctx, 20, n_reads * 8, &d_ro))) return rc;
-    if (!uniform && (rc = stage_get(ctx, 21, n_reads * 4, &d_rl))) return rc;
+    if (!uniform) {
+        if ((rc = stage_get(ctx, 18, (n_reads + 1) * 8, &d_ao))) return rc;
+        if ((rc = stage_get(ctx, 19, (n_reads + 1) * 8, &d_wo))) return rc;
+        if ((rc = stage_get(ctx, 20, n_reads * 8, &d_ro))) return rc;
+        if ((rc = stage_get(ctx, 21, n_reads * 4, &d_rl))) return rc;
+    }
     if ((rc = stage_get(ctx, 22, (words + 2) * 8, &d_packed))) return rc;
     if ((rc = stage_get(ctx, 23, (words + 2) * 4, &d_mask))) return rc;
     if ((rc = stage_get(ctx, 24, (words + 2) * 4, &d_rcm))) return rc;
     CK(cudaMemcpyAsync(d_b, bases + a_lo, (size_t)(a_hi - a_lo), cudaMemcpyHostToDevice, ctx->stream));
     if (quals) CK(cudaMemcpyAsync(d_q, quals + a_lo, (size_t)(a_hi - a_lo), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_ao, ascii_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_wo, word_off.data(), (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (!uniform) {
+        CK(cudaMemcpyAsync(d_ao, ascii_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_wo, word_off.data(), (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(d_ro, read_off.data(), (size_t)n_reads * 8, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(d_rl, read_len.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
     if (words > 0) {
         RB_LAUNCH((int)div_up(words, kThreads), kThreads, 0, ctx->stream, k_pack_ascii)((const char*)d_b - a_lo, d_q ? (const char*)d_q - a_lo : nullptr, (const int64_t*)d_ao,
                                                                                  (const int64_t*)d_wo, n_reads, words, min_qual, (uint64_t*)d_packed,
-                                                                                 (uint32_t*)d_mask, (uint32_t*)d_rcm);
+                                                                                 (uint32_t*)d_mask, (uint32_t*)d_rcm, uniform ? (int)len0 : 0, a_lo);
         LAUNCH_CHECK();
     }
     CK(cudaStreamSynchronize(ctx->stream));   // the host vectors go out of scope
