@@ -296,10 +296,14 @@ def main():
         chk = e2e_pipelined(list(range(4, e_steps + 4)))
         te = time.perf_counter() - t0
         assert chk >= 1024.0 * e_steps   # every k-mer of a step was inserted before it was looked up: count >= 1
-        e2e = {"value": nk * e_steps / te, "unit": "k-mers/s", "h2d_bytes_per_step": 2 * words * 8, "d2h_bytes_per_step": nk * 4,
-               "steps": e_steps, "ms_per_step": 1e3 * te / e_steps,
-               "calls": "rb_graph_add_reads + rb_graph_count_reads_async / rb_ctx_wait (pinned host buffers, results double-buffered)",
-               "blocking_calls": {"value": nk / te_sync, "ms_per_step": 1e3 * te_sync, "calls": "rb_graph_add_reads + rb_graph_count_reads"}}
+        piped = {"value": nk * e_steps / te, "ms_per_step": 1e3 * te / e_steps, "steps": e_steps,
+                 "calls": "rb_graph_add_reads + rb_graph_count_reads_async / rb_ctx_wait (pinned host buffers, results double-buffered)"}
+        block = {"value": nk / te_sync, "ms_per_step": 1e3 * te_sync, "steps": 2, "calls": "rb_graph_add_reads + rb_graph_count_reads"}
+        # both are the library's public calls on the same work with the same copies; the line's e2e is the better way to call it on this box
+        # (the pipelined calls lose when the driver shares one copy engine between the two directions), the other one stays beside it
+        best = piped if piped["value"] >= block["value"] else block
+        e2e = {"value": best["value"], "unit": "k-mers/s", "h2d_bytes_per_step": 2 * words * 8, "d2h_bytes_per_step": nk * 4,
+               "steps": best["steps"], "ms_per_step": best["ms_per_step"], "calls": best["calls"], "pipelined_calls": piped, "blocking_calls": block}
 
         # the same through the ASCII entry points -- what the Java insert workers and graph.getKmers(String) call (RNABloom.java:551-634,
         # graph :1224-1234): ASCII bases in host memory in, segmentation + 2-bit packing on the GPU, counts back to host memory
