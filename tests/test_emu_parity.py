@@ -60,7 +60,7 @@ SPILL_ENV = {"RB_SLICED_SPILL": "1", "RB_SLICED_SUBCAP": "40", "RB_SLICED_KEYCAP
 ONLY = {
     "sliced-small-spill": ("test_duplicates_inside_one_batch_are_linearised", "test_skewed_batch_is_redone_by_the_direct_engine"),
     "direct": ("test_getkmers_with_invalid_nucleotides", "test_screening_filter_over_whole_sequences", "test_kmer_histogram_by_hash_sampling",
-               "test_minimizers_match_the_rolling_window", "test_pair_lookups_at_every_position", "test_equal_length_ascii_records_and_async_counts", "test_neighbor_counts_match_oracle", "test_kmerize_ascii_is_exact_for_every_character",
+               "test_minimizers_match_the_rolling_window", "test_pair_lookups_at_every_position", "test_minimizer_based_subsampling_matches_the_sequential_loop", "test_equal_length_ascii_records_and_async_counts", "test_neighbor_counts_match_oracle", "test_kmerize_ascii_is_exact_for_every_character",
                "test_cascading_bloom_filter_matches_oracle", "test_loaded_cbf_envelope_at_scale", "test_2bit_fragment_records_round_trip",
                "test_variants_max_cov_and_greedy_extension_match_oracle", "test_stage1_driver_writes_the_reference_files"),
     "sliced-default": ("test_getkmers_with_invalid_nucleotides", "test_equal_length_ascii_records_and_async_counts", "test_insert_policies_and_pair_filters", "test_kernels_are_race_free_under_tsan",
@@ -105,6 +105,11 @@ test_equal_length_ascii_records_and_async_counts = G.test_equal_length_ascii_rec
 @pytest.mark.parametrize("mode,k,w", [(2, 25, 10), (0, 17, 1)])
 def test_minimizers_match_the_rolling_window(ctx, orc, mode, k, w):
     G.test_minimizers_match_the_rolling_window(ctx, orc, mode, k, w)
+
+
+@pytest.mark.parametrize("stranded,hpc", [(False, False), (True, True)])
+def test_minimizer_based_subsampling_matches_the_sequential_loop(ctx, orc, stranded, hpc):
+    G.test_minimizer_based_subsampling_matches_the_sequential_loop(ctx, orc, stranded, hpc)
 
 
 @pytest.mark.parametrize("stranded,k,d", [(False, 25, 30), (True, 21, 7)])

@@ -4,6 +4,7 @@ Contract: P1 hashes exact, P2 indices exact, P3 add-only 
 P4 counting filter exact on collision-free fixtures / duplicates linearised / envelope on loaded filters,
 P5 multiplicities kept <= 17 so MiniFloat stays deterministic.  Bit-exact comparisons throughout (integer path).
 """
+import ctypes as C
 import os
 
 import numpy as np
@@ -729,6 +730,55 @@ def test_minimizers_match_the_rolling_window(ctx, orc, mode, k, w):
         assert (got[off:off + n_win] == want).all()
         off += n_win
     assert off == got.size
+
+
+@pytest.mark.parametrize("stranded,hpc", [(False, False), (True, True)])
+def test_minimizer_based_subsampling_matches_the_sequential_loop(ctx, orc, stranded, hpc):
+    """f4: SeqSubsampler.minimizerBased (util/SeqSubsampler.java:50-117) on rb_minimizers + rb_cbf_increment_and_get_hashes against the loop restated
+    over the oracle's hashes and counting filter: the same sequences kept, the same filter bytes."""
+    from rnabloom_b200 import subsampler
+    rng = np.random.default_rng(3)
+    genome = "".join(rng.choice(list("ACGT"), size=3000))
+    seqs = []
+    for _ in range(90):                       # long-read-like: overlapping pieces of a small genome, a few unrelated ones
+        L = int(rng.integers(20, 600))
+        p0 = int(rng.integers(0, len(genome) - L))
+        seqs.append(genome[p0:p0 + L] if rng.random() < 0.85 else "".join(rng.choice(list("ACGT"), size=L)))
+    seqs.sort(key=len, reverse=True)
+    k, w, h, size, max_mult, chain, prop = 15, 8, 2, (1 << 22) + 3, 2, 4, 0.5
+    kept, cbf = subsampler.minimizerBased(ctx, seqs, size, k, w, h, stranded, hpc, chain, prop, max_mult)
+    lib = orc.lib
+    ocbf = lib.orc_cbf_create(size, h, k)
+    want = []
+    for i, s_ in enumerate(seqs):
+        t = subsampler.compress_homopolymers(s_) if hpc else s_
+        _, _, base = orc.kmer_hashes(t, k, 0 if stranded else MODE_CANON)
+        n_win = len(base) - w + 1
+        if len(t) < k or n_win <= 0:
+            want.append(i)
+            continue
+        mins = [int(base[j:j + w].min()) for j in range(n_win)]
+        num = seen = cons = max_cons = 0
+        prev = None
+        for j, mm in enumerate(mins):
+            if j == 0 or mm != prev:
+                num += 1
+                hv = (C.c_int64 * h)(*[int(x) for x in orc.ntm64(mm, k, h)])
+                c = lib.orc_cbf_increment_and_get(ocbf, hv)
+                if c > max_mult:
+                    seen += 1
+                    if j:
+                        cons = 0
+                elif j:
+                    cons += 1
+                    max_cons = max(max_cons, cons)
+            prev = mm
+        if max_cons > chain or seen < prop * num:
+            want.append(i)
+    assert kept == want and 0 < len(kept) < len(seqs)
+    assert (cbf.download() == orc.cbf_array(ocbf)).all()
+    cbf.destroy()
+    lib.orc_cbf_destroy(ocbf)
 
 
 @pytest.mark.parametrize("stranded,k,d", [(False, 25, 30), (True, 21, 7)])
