@@ -717,6 +717,34 @@ class BloomFilterDeBruijnGraph:
         self.ctx.check(self.ctx.L.rb_graph_lookup_pairs_reads(self.h, which, *reads.args(), flags, _ptr(out)))
         return out.astype(bool)
 
+    def breakWithPairedKmers(self, reads, numPairsRequired=3, which=B.RB_RPKBF, flags=0):
+        """GraphUtils.breakWithReadPairedKmers / breakWithFragPairedKmers (util/GraphUtils.java:4184-4310) for every read: the ranges [start, end) of
+        k-mer indices supported by paired k-mers.  The pair look-ups of all reads come from one batched call; the segment walk is the
+        reference's, per read, on the host."""
+        d = self._pair_distance(which)
+        found = self.lookupKmerPairsOfReads(reads, which, flags)
+        off = reads.offsets(self.k + d)
+        out = []
+        for r in range(reads.n_reads):
+            f = found[off[r]:off[r + 1]]          # f[i] = lookupKmerPair(kmers[i], kmers[i + d]), i = 0 .. lastIndex
+            segments, start, end, run = [], -1, -1, 0
+            for i, hit in enumerate(f):
+                if hit:
+                    run += 1
+                    if run >= numPairsRequired:
+                        if start < 0:
+                            start = i - numPairsRequired + 1
+                        end = i + d
+                else:
+                    if start >= 0 and i >= end:   # interlockDistance = 0
+                        segments.append((start, end + 1))
+                        start = end = -1
+                    run = 0
+            if start >= 0:
+                segments.append((start, end + 1))
+            out.append(segments)
+        return out
+
     def lookupFragmentKmerPair(self, pairHashVals):
         a = _hashes(pairHashVals)
         out = np.zeros(a.size, dtype=np.uint8)

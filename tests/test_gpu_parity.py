@@ -806,6 +806,29 @@ def test_pair_lookups_at_every_position(ctx, orc, stranded, k, d):
             assert bool(got[off + i]) == want
         off += len(ph)
     assert off == got.size
+    # breakWithReadPairedKmers (util/GraphUtils.java:4184-4246) on those answers, against the loop restated over the oracle's look-ups
+    for need in (1, 3):
+        segs = g.breakWithPairedKmers(rb.pack_reads(queries), need)
+        for s_, got_segs in zip(queries, segs):
+            _, _, ph = orc.pair_hashes(s_, k, d, 0 if stranded else MODE_CANON)
+            hits = [("N" not in s_[i:i + k + d]) and bool(orc.lib.orc_bf_lookup1(rp, int(p))) for i, p in enumerate(ph)]
+            want, start, end, prev = [], -1, -1, 0
+            for i, hit in enumerate(hits):       # the reference's two branches (numPairsRequired == 1 / > 1) are this loop with need = 1 / need
+                if hit:
+                    prev += 1
+                    if prev >= need:
+                        if start < 0:
+                            start = i - need + 1
+                        end = i + d
+                else:
+                    if start >= 0 and i >= end:
+                        want.append((start, end + 1))
+                        start = end = -1
+                    prev = 0
+            if start >= 0:
+                want.append((start, end + 1))
+            assert got_segs == want
+        assert any(segs) and not all(segs)       # inserted reads are supported by pairs, the others are not
     g.destroy(), og.close()
 
 
