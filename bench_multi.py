@@ -277,7 +277,9 @@ def run_sharded(args, rank, world, local_rank):
             done.record(stream)
             copy_stream.wait_event(done)
             with torch.cuda.stream(copy_stream):
-                h_out.copy_(c, non_blocking=True)
+                piece = 8 << 20   # floats: 32 MiB copies, so that the next step's reads (H2D) are not held behind one 2 GB D2H on a shared copy engine
+                for o in range(0, h_out.numel(), piece):
+                    h_out[o:o + piece].copy_(c[o:o + piece], non_blocking=True)
                 copied[i % 2] = torch.cuda.Event()
                 copied[i % 2].record(copy_stream)
         torch.cuda.synchronize()
